@@ -1,0 +1,467 @@
+// Batch-norm forward/backward fused with the ReLU / LeakyReLU / tanh / sigmoid epilogues.
+// Replaces tf.contrib.layers.batch_norm (/root/reference/models/recurrent_z/ops.py:18-24)
+// and tf.nn.moments + tf.nn.batch_normalization (rnn_test/recurrent_DCGAN.py:190-191),
+// plus the activation that always follows them (model.py:274-276, 307-319).
+//
+// HBM-bound: x is [rows, C] channel-contiguous.  Statistics pass = one coalesced read of x
+// (4 channels per thread, 16 B loads; per-thread fp32 partials over a bounded number of
+// rows, block-level smem reduction, one fp64 atomic per channel per CTA so the final
+// E[x^2]-mean^2 has no cancellation problem at the 1e-4 parity tolerance); apply pass = one
+// read + one write.  Algorithmic bytes: fwd 2 reads + 1 write, bwd 2x(x,dy) reads + 1 write.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int BN_THREADS = 256;
+
+struct ColGeom {
+  int tx, ty;         // block = tx * ty threads; tx over channel vectors, ty over rows
+  int cblocks;        // grid.y
+  int rblocks;        // grid.x
+  int vec;
+};
+
+static ColGeom col_geom(int64_t rows_per_group, int C, int groups, bool vec_ok) {
+  ColGeom g;
+  g.vec = (vec_ok && C % 4 == 0) ? 4 : 1;
+  const int lanes = C / g.vec;
+  int tx = 1;
+  while (tx < lanes && tx < BN_THREADS) tx <<= 1;
+  g.tx = tx;
+  g.ty = BN_THREADS / tx;
+  g.cblocks = ceil_div(lanes, tx);
+  int64_t want = std::max<int64_t>(1, (148 * 4) / ((int64_t)g.cblocks * groups));
+  int64_t maxr = ceil_div64(rows_per_group, (int64_t)g.ty * 4);  // >= 4 rows per thread
+  g.rblocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, maxr));
+  return g;
+}
+
+// ---- per-(group, channel) sums of f0(x,...) and f1(x,...) -----------------------------
+// MODE 0: (x, x^2)                                   -> batch statistics
+// MODE 1: (g, g*xhat), g = dy*act'(gamma*xhat+beta)  -> BN backward reductions
+// MODE 2: (x, 0) column sum                          -> bias gradient
+template <typename TX, typename TD, int VEC, int MODE>
+__global__ void __launch_bounds__(BN_THREADS)
+colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_per_group, int C,
+              const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+              const float* __restrict__ rstd, int act, float act_param, double* __restrict__ sums, int tx_dim) {
+  const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
+  const int grp = blockIdx.z;
+  const int c = (blockIdx.y * tx_dim + tx) * VEC;
+  const bool active = c < C;
+  float s0[VEC], s1[VEC], ga[VEC], be[VEC], mu[VEC], rs[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    s0[v] = s1[v] = 0.f;
+    ga[v] = 1.f; be[v] = 0.f; mu[v] = 0.f; rs[v] = 1.f;
+    if (MODE == 1 && active) {
+      if (gamma) ga[v] = gamma[c + v];
+      if (beta) be[v] = beta[c + v];
+      mu[v] = mean[(int64_t)grp * C + c + v];
+      rs[v] = rstd[(int64_t)grp * C + c + v];
+    }
+  }
+  if (active) {
+    const int64_t base = (int64_t)grp * rows_per_group;
+    for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += (int64_t)gridDim.x * ty_dim) {
+      const int64_t off = (base + r) * C + c;
+      float xv[VEC], dv[VEC];
+      if (VEC == 4) {
+        float4 t = ld4(x + off); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+        if (MODE == 1) { float4 u = ld4(dy + off); dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3] = u.w; }
+      } else {
+        xv[0] = ldf(x + off);
+        if (MODE == 1) dv[0] = ldf(dy + off);
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (MODE == 0) { s0[v] += xv[v]; s1[v] = fmaf(xv[v], xv[v], s1[v]); }
+        else if (MODE == 2) { s0[v] += xv[v]; }
+        else {
+          const float xh = (xv[v] - mu[v]) * rs[v];
+          const float g = dv[v] * act_grad_from_pre(fmaf(ga[v], xh, be[v]), act, act_param);
+          s0[v] += g; s1[v] = fmaf(g, xh, s1[v]);
+        }
+      }
+    }
+  }
+  // block reduction over ty
+  __shared__ float red[2][BN_THREADS * 4];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { red[0][threadIdx.x * VEC + v] = s0[v]; red[1][threadIdx.x * VEC + v] = s1[v]; }
+  __syncthreads();
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float a = 0.f, b = 0.f;
+      for (int j = 0; j < ty_dim; ++j) { a += red[0][(j * tx_dim + tx) * VEC + v]; b += red[1][(j * tx_dim + tx) * VEC + v]; }
+      atomicAdd(sums + ((int64_t)grp * 2 + 0) * C + c + v, (double)a);
+      if (MODE != 2) atomicAdd(sums + ((int64_t)grp * 2 + 1) * C + c + v, (double)b);
+    }
+  }
+}
+
+// ---- finalize: mean / rstd per group, sequential EMA over groups ------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t rows_per_group, int C, int groups, float eps,
+                                   float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mm = moving_mean ? moving_mean[c] : 0.f, mv = moving_var ? moving_var[c] : 0.f;
+  const double inv = 1.0 / (double)rows_per_group;
+  for (int g = 0; g < groups; ++g) {
+    const double m = sums[((int64_t)g * 2 + 0) * C + c] * inv;
+    double var = sums[((int64_t)g * 2 + 1) * C + c] * inv - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    const float mf = (float)m, vf = (float)var;
+    save_mean[(int64_t)g * C + c] = mf;
+    save_rstd[(int64_t)g * C + c] = rsqrtf(vf + eps);
+    // ops.py:18-24: assign_moving_average(moving, batch, decay) = moving - (moving - batch)*(1-decay)
+    mm -= (mm - mf) * (1.f - decay);
+    mv -= (mv - vf) * (1.f - decay);
+  }
+  if (moving_mean) moving_mean[c] = mm;
+  if (moving_var) moving_var[c] = mv;
+}
+
+__global__ void bn_infer_stats_kernel(const float* __restrict__ mm, const float* __restrict__ mv, float eps, int C,
+                                      float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  save_mean[c] = mm[c];
+  save_rstd[c] = rsqrtf(mv[c] + eps);
+}
+
+// ---- apply: y = act((x - mean) * rstd * gamma + beta) ----------------------------------
+template <typename TX, typename TY, int VEC>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows_per_group, int C, int lanes,
+                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                const float* __restrict__ rstd, int act, float act_param) {
+  const int grp = blockIdx.z;
+  const int64_t total = rows_per_group * lanes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / lanes;
+    const int c = (int)(i - r * lanes) * VEC;
+    const int64_t off = ((int64_t)grp * rows_per_group + r) * C + c;
+    float xv[VEC], o[VEC];
+    if (VEC == 4) { float4 t = ld4(x + off); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
+    else xv[0] = ldf(x + off);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float ga = gamma ? __ldg(gamma + c + v) : 1.f, be = beta ? __ldg(beta + c + v) : 0.f;
+      const float mu = __ldg(mean + (int64_t)grp * C + c + v), rs = __ldg(rstd + (int64_t)grp * C + c + v);
+      o[v] = act_fwd(fmaf((xv[v] - mu) * rs, ga, be), act, act_param);
+    }
+    if (VEC == 4) st4(y + off, make_float4(o[0], o[1], o[2], o[3]));
+    else stf(y + off, o[0]);
+  }
+}
+
+// ---- backward apply -------------------------------------------------------------------
+template <typename TX, typename TD, typename TO, int VEC>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __restrict__ dx, int64_t rows_per_group, int C,
+                    int lanes, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const double* __restrict__ sums, int act, float act_param, int train) {
+  const int grp = blockIdx.z;
+  const int64_t total = rows_per_group * lanes;
+  const float invM = 1.f / (float)rows_per_group;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / lanes;
+    const int c = (int)(i - r * lanes) * VEC;
+    const int64_t off = ((int64_t)grp * rows_per_group + r) * C + c;
+    float xv[VEC], dv[VEC], o[VEC];
+    if (VEC == 4) {
+      float4 t = ld4(x + off); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+      float4 u = ld4(dy + off); dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3] = u.w;
+    } else { xv[0] = ldf(x + off); dv[0] = ldf(dy + off); }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float ga = gamma ? __ldg(gamma + c + v) : 1.f, be = beta ? __ldg(beta + c + v) : 0.f;
+      const float mu = __ldg(mean + (int64_t)grp * C + c + v), rs = __ldg(rstd + (int64_t)grp * C + c + v);
+      const float xh = (xv[v] - mu) * rs;
+      const float g = dv[v] * act_grad_from_pre(fmaf(ga, xh, be), act, act_param);
+      if (train) {
+        const float sg = (float)sums[((int64_t)grp * 2 + 0) * C + c + v] * invM;
+        const float sgx = (float)sums[((int64_t)grp * 2 + 1) * C + c + v] * invM;
+        o[v] = ga * rs * (g - sg - xh * sgx);
+      } else {
+        o[v] = ga * rs * g;
+      }
+    }
+    if (VEC == 4) st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
+    else stf(dx + off, o[0]);
+  }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, int groups, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int g = 0; g < groups; ++g) { a += sums[((int64_t)g * 2 + 0) * C + c]; b += sums[((int64_t)g * 2 + 1) * C + c]; }
+  if (dbeta) dbeta[c] += (float)a;
+  if (dgamma) dgamma[c] += (float)b;
+}
+
+__global__ void add_colsum_kernel(const double* __restrict__ sums, int C, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) db[c] += (float)sums[c];
+}
+
+// ---- host -----------------------------------------------------------------------------
+template <typename TX, typename TD, int MODE>
+static void launch_colsum(const void* x, const void* dy, int64_t rpg, int C, int groups, const float* gamma, const float* beta,
+                          const float* mean, const float* rstd, int act, float ap, double* sums, bool vec_ok, cudaStream_t st) {
+  ColGeom g = col_geom(rpg, C, groups, vec_ok);
+  dim3 grid(g.rblocks, g.cblocks, groups);
+  if (g.vec == 4)
+    colsum_kernel<TX, TD, 4, MODE><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
+  else
+    colsum_kernel<TX, TD, 1, MODE><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
+}
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
+static inline int apply_blocks(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(total, BN_THREADS), 148 * 8)); }
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" size_t gg_bn_workspace_bytes(int32_t C, int32_t groups) { return (size_t)2 * C * groups * sizeof(double); }
+
+extern "C" int gg_bn_fwd_train(const void* x, int32_t x_dt, void* y, int32_t y_dt, int64_t rows, int32_t C, int32_t groups,
+                               const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* save_mean,
+                               float* save_rstd, float eps, float decay, int32_t act, float act_param, void* ws, size_t ws_bytes,
+                               void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GG_REQUIRE(x && y && save_mean && save_rstd && ws, GG_ERR_INVALID, "bn_fwd_train: null pointer");
+  GG_REQUIRE(groups >= 1 && rows > 0 && rows % groups == 0, GG_ERR_INVALID, "bn_fwd_train: rows %lld not divisible by groups %d", (long long)rows, groups);
+  GG_REQUIRE(ws_bytes >= gg_bn_workspace_bytes(C, groups), GG_ERR_WORKSPACE, "bn_fwd_train: workspace too small");
+  const int64_t rpg = rows / groups;
+  double* sums = (double*)ws;
+  cudaMemsetAsync(sums, 0, gg_bn_workspace_bytes(C, groups), st);
+  const bool vec_ok = aligned16(x) && aligned16(y);
+  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, rpg, C, groups, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, vec_ok, st)));
+  int rc = check_launch("bn_stats");
+  if (rc) return rc;
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, rpg, C, groups, eps, decay, moving_mean, moving_var, save_mean, save_rstd);
+  rc = check_launch("bn_finalize");
+  if (rc) return rc;
+  const int vec = (vec_ok && C % 4 == 0) ? 4 : 1;
+  const int lanes = C / vec;
+  dim3 grid(apply_blocks(rpg * lanes), 1, groups);
+#define GG_APPLY(TX, TY)                                                                                              \
+  do {                                                                                                                \
+    if (vec == 4) bn_apply_kernel<TX, TY, 4><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (TY*)y, rpg, C, lanes, gamma, beta, save_mean, save_rstd, act, act_param); \
+    else bn_apply_kernel<TX, TY, 1><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (TY*)y, rpg, C, lanes, gamma, beta, save_mean, save_rstd, act, act_param);          \
+  } while (0)
+  if (x_dt == GG_F32 && y_dt == GG_F32) GG_APPLY(float, float);
+  else if (x_dt == GG_F32) GG_APPLY(float, bf16);
+  else if (y_dt == GG_F32) GG_APPLY(bf16, float);
+  else GG_APPLY(bf16, bf16);
+  return check_launch("bn_apply");
+}
+
+extern "C" int gg_bn_infer_stats(const float* moving_mean, const float* moving_var, float eps, int32_t C, float* save_mean,
+                                 float* save_rstd, void* stream) {
+  GG_REQUIRE(moving_mean && moving_var && save_mean && save_rstd, GG_ERR_INVALID, "bn_infer_stats: null pointer");
+  bn_infer_stats_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(moving_mean, moving_var, eps, C, save_mean, save_rstd);
+  return check_launch("bn_infer_stats");
+}
+
+extern "C" int gg_bn_fwd_infer(const void* x, int32_t x_dt, void* y, int32_t y_dt, int64_t rows, int32_t C, const float* gamma,
+                               const float* beta, const float* moving_mean, const float* moving_var, float eps, int32_t act,
+                               float act_param, void* stream) {
+  // inference statistics are folded on the fly: mean = moving_mean, rstd = rsqrt(moving_var+eps)
+  // (bn_apply reads mean/rstd arrays, so stage them through a tiny kernel into caller memory is
+  // avoided by a dedicated lambda kernel below)
+  cudaStream_t st = (cudaStream_t)stream;
+  GG_REQUIRE(x && y && moving_mean && moving_var, GG_ERR_INVALID, "bn_fwd_infer: null pointer");
+  // Reuse bn_apply with rstd computed per element: implemented as a separate small-footprint kernel.
+  extern int bn_infer_apply(const void*, int, void*, int, int64_t, int, const float*, const float*, const float*, const float*, float, int, float, cudaStream_t);
+  return bn_infer_apply(x, x_dt, y, y_dt, rows, C, gamma, beta, moving_mean, moving_var, eps, act, act_param, st);
+}
+
+namespace gg {
+template <typename TX, typename TY, int VEC>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_infer_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows, int C, int lanes, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ mm, const float* __restrict__ mv, float eps, int act,
+                      float act_param) {
+  const int64_t total = rows * lanes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / lanes;
+    const int c = (int)(i - r * lanes) * VEC;
+    const int64_t off = r * C + c;
+    float xv[VEC], o[VEC];
+    if (VEC == 4) { float4 t = ld4(x + off); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
+    else xv[0] = ldf(x + off);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float ga = gamma ? __ldg(gamma + c + v) : 1.f, be = beta ? __ldg(beta + c + v) : 0.f;
+      const float rs = rsqrtf(__ldg(mv + c + v) + eps);
+      o[v] = act_fwd(fmaf((xv[v] - __ldg(mm + c + v)) * rs, ga, be), act, act_param);
+    }
+    if (VEC == 4) st4(y + off, make_float4(o[0], o[1], o[2], o[3]));
+    else stf(y + off, o[0]);
+  }
+}
+}  // namespace gg
+
+int bn_infer_apply(const void* x, int x_dt, void* y, int y_dt, int64_t rows, int C, const float* gamma, const float* beta,
+                   const float* mm, const float* mv, float eps, int act, float act_param, cudaStream_t st) {
+  const bool vec_ok = aligned16(x) && aligned16(y);
+  const int vec = (vec_ok && C % 4 == 0) ? 4 : 1;
+  const int lanes = C / vec;
+  dim3 grid(apply_blocks(rows * lanes));
+#define GG_IAPPLY(TX, TY)                                                                                             \
+  do {                                                                                                                \
+    if (vec == 4) bn_infer_apply_kernel<TX, TY, 4><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (TY*)y, rows, C, lanes, gamma, beta, mm, mv, eps, act, act_param); \
+    else bn_infer_apply_kernel<TX, TY, 1><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (TY*)y, rows, C, lanes, gamma, beta, mm, mv, eps, act, act_param);          \
+  } while (0)
+  if (x_dt == GG_F32 && y_dt == GG_F32) GG_IAPPLY(float, float);
+  else if (x_dt == GG_F32) GG_IAPPLY(float, bf16);
+  else if (y_dt == GG_F32) GG_IAPPLY(bf16, float);
+  else GG_IAPPLY(bf16, bf16);
+  return check_launch("bn_infer_apply");
+}
+
+extern "C" int gg_bn_bwd(const void* x, int32_t x_dt, const void* dy, int32_t dy_dt, void* dx, int32_t dx_dt, int64_t rows, int32_t C,
+                         int32_t groups, const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
+                         float* dgamma, float* dbeta, int32_t act, float act_param, int32_t train, void* ws, size_t ws_bytes,
+                         void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GG_REQUIRE(x && dy && dx && save_mean && save_rstd, GG_ERR_INVALID, "bn_bwd: null pointer");
+  GG_REQUIRE(groups >= 1 && rows > 0 && rows % groups == 0, GG_ERR_INVALID, "bn_bwd: rows not divisible by groups");
+  const int64_t rpg = rows / groups;
+  double* sums = (double*)ws;
+  const bool need_sums = train || dgamma || dbeta;
+  const bool vec_ok = aligned16(x) && aligned16(dy) && aligned16(dx);
+  int rc;
+  if (need_sums) {
+    GG_REQUIRE(ws && ws_bytes >= gg_bn_workspace_bytes(C, groups), GG_ERR_WORKSPACE, "bn_bwd: workspace too small");
+    cudaMemsetAsync(sums, 0, gg_bn_workspace_bytes(C, groups), st);
+#define GG_CS(TX, TD) launch_colsum<TX, TD, 1>(x, dy, rpg, C, groups, gamma, beta, save_mean, save_rstd, act, act_param, sums, vec_ok, st)
+    if (x_dt == GG_F32 && dy_dt == GG_F32) GG_CS(float, float);
+    else if (x_dt == GG_F32) GG_CS(float, bf16);
+    else if (dy_dt == GG_F32) GG_CS(bf16, float);
+    else GG_CS(bf16, bf16);
+#undef GG_CS
+    rc = check_launch("bn_bwd_reduce");
+    if (rc) return rc;
+    if (dgamma || dbeta) {
+      bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, groups, dgamma, dbeta);
+      rc = check_launch("bn_param_grad");
+      if (rc) return rc;
+    }
+  }
+  const int vec = (vec_ok && C % 4 == 0) ? 4 : 1;
+  const int lanes = C / vec;
+  dim3 grid(apply_blocks(rpg * lanes), 1, groups);
+#define GG_BA(TX, TD, TO)                                                                                                          \
+  do {                                                                                                                             \
+    if (vec == 4) bn_bwd_apply_kernel<TX, TD, TO, 4><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, lanes, gamma, beta, save_mean, save_rstd, sums, act, act_param, train); \
+    else bn_bwd_apply_kernel<TX, TD, TO, 1><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, lanes, gamma, beta, save_mean, save_rstd, sums, act, act_param, train);          \
+  } while (0)
+  const int key = (x_dt == GG_BF16 ? 4 : 0) | (dy_dt == GG_BF16 ? 2 : 0) | (dx_dt == GG_BF16 ? 1 : 0);
+  switch (key) {
+    case 0: GG_BA(float, float, float); break;
+    case 1: GG_BA(float, float, bf16); break;
+    case 2: GG_BA(float, bf16, float); break;
+    case 3: GG_BA(float, bf16, bf16); break;
+    case 4: GG_BA(bf16, float, float); break;
+    case 5: GG_BA(bf16, float, bf16); break;
+    case 6: GG_BA(bf16, bf16, float); break;
+    default: GG_BA(bf16, bf16, bf16); break;
+  }
+  return check_launch("bn_bwd_apply");
+}
+
+extern "C" int gg_bias_grad(const void* dy, int32_t dy_dt, float* db, int64_t rows, int32_t C, void* stream) {
+  // column sums through the same coalesced reduction; needs a small fp64 scratch: use a
+  // per-call static device buffer is not allowed (no allocation) -> accumulate via a
+  // dedicated float-atomic kernel instead.
+  extern int bias_grad_impl(const void*, int, float*, int64_t, int, cudaStream_t);
+  GG_REQUIRE(dy && db && rows > 0 && C > 0, GG_ERR_INVALID, "bias_grad: bad argument");
+  return bias_grad_impl(dy, dy_dt, db, rows, C, (cudaStream_t)stream);
+}
+
+namespace gg {
+template <typename TD, int VEC>
+__global__ void __launch_bounds__(BN_THREADS)
+bias_grad_kernel(const TD* __restrict__ dy, float* __restrict__ db, int64_t rows, int C, int tx_dim) {
+  const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
+  const int c = (blockIdx.y * tx_dim + tx) * VEC;
+  float s[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) s[v] = 0.f;
+  if (c < C) {
+    for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows; r += (int64_t)gridDim.x * ty_dim) {
+      if (VEC == 4) { float4 t = ld4(dy + r * C + c); s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w; }
+      else s[0] += ldf(dy + r * C + c);
+    }
+  }
+  __shared__ float red[BN_THREADS * 4];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) red[threadIdx.x * VEC + v] = s[v];
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float a = 0.f;
+      for (int j = 0; j < ty_dim; ++j) a += red[(j * tx_dim + tx) * VEC + v];
+      atomicAdd(db + c + v, a);
+    }
+  }
+}
+}  // namespace gg
+
+int bias_grad_impl(const void* dy, int dy_dt, float* db, int64_t rows, int C, cudaStream_t st) {
+  ColGeom g = col_geom(rows, C, 1, aligned16(dy));
+  dim3 grid(g.rblocks, g.cblocks, 1);
+  if (dy_dt == GG_F32) {
+    if (g.vec == 4) bias_grad_kernel<float, 4><<<grid, BN_THREADS, 0, st>>>((const float*)dy, db, rows, C, g.tx);
+    else bias_grad_kernel<float, 1><<<grid, BN_THREADS, 0, st>>>((const float*)dy, db, rows, C, g.tx);
+  } else {
+    if (g.vec == 4) bias_grad_kernel<bf16, 4><<<grid, BN_THREADS, 0, st>>>((const bf16*)dy, db, rows, C, g.tx);
+    else bias_grad_kernel<bf16, 1><<<grid, BN_THREADS, 0, st>>>((const bf16*)dy, db, rows, C, g.tx);
+  }
+  return check_launch("bias_grad");
+}
+
+// ops.get_std (ops.py:125-128): column statistics over the batch axis, then mean over features.
+namespace gg {
+__global__ void get_std_final_kernel(const double* __restrict__ sums, int64_t B, int64_t F, float* __restrict__ out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int64_t f = threadIdx.x; f < F; f += blockDim.x) {
+    const double m = sums[f] / (double)B;
+    double var = sums[F + f] / (double)B - m * m;
+    acc += var < 0.0 ? 0.0 : var;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)sqrt(red[0] / (double)F);
+}
+}  // namespace gg
+
+extern "C" int gg_get_std(const void* x, int32_t x_dt, int64_t B, int64_t F, float* out, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GG_REQUIRE(x && out && ws && B > 0 && F > 0 && F < (1ll << 31), GG_ERR_INVALID, "get_std: bad argument");
+  GG_REQUIRE(ws_bytes >= (size_t)2 * F * sizeof(double), GG_ERR_WORKSPACE, "get_std: workspace too small");
+  double* sums = (double*)ws;
+  cudaMemsetAsync(sums, 0, (size_t)2 * F * sizeof(double), st);
+  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, B, (int)F, 1, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, aligned16(x), st)));
+  int rc = check_launch("get_std_stats");
+  if (rc) return rc;
+  get_std_final_kernel<<<1, 256, 0, st>>>(sums, B, F, out);
+  return check_launch("get_std_final");
+}

@@ -1,0 +1,100 @@
+// C-ABI entry points of libgifgan.so (declared in include/gifgan.h): error plumbing and
+// dispatch between the SIMT fp32-accumulate kernels and the tcgen05 bf16 kernels.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gg {
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// tapgemm_simt.cu
+int simt_conv_down(const gg_conv_desc*, const void*, const float*, const float*, void*, cudaStream_t);
+int simt_conv_up(const gg_conv_desc*, const void*, const float*, const float*, void*, cudaStream_t);
+int simt_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStream_t);
+int simt_linear_fwd(const void*, int, const float*, const float*, void*, int, int, int, int, int, float, cudaStream_t);
+int simt_linear_dgrad(const void*, int, const float*, void*, int, int, int, int, cudaStream_t);
+int simt_linear_wgrad(const void*, int, const void*, int, float*, int, int, int, cudaStream_t);
+// pointwise.cu
+int skinny_linear_fwd(const void*, int, const float*, const float*, void*, int, int, int, int, int, float, cudaStream_t);
+int skinny_linear_dgrad(const void*, int, const float*, void*, int, int, int, int, cudaStream_t);
+int skinny_linear_wgrad(const void*, int, const void*, int, float*, int, int, int, cudaStream_t);
+// tc_tapgemm.cu
+int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int tc_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStream_t);
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int gg_version(void) { return GG_VERSION; }
+extern "C" const char* gg_last_error(void) { return g_err; }
+extern "C" uint64_t gg_launch_count(void) { return g_launches.load(); }
+
+extern "C" int gg_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); set_error("no CUDA device"); return GG_ERR_CUDA; }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return major * 10 + minor;
+}
+
+extern "C" int gg_conv_down(const gg_conv_desc* d, const void* large, const void* w, const float* bias, void* small, void* stream) {
+  GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_down: null pointer");
+  if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_down(d, large, w, bias, small, (cudaStream_t)stream);
+  return simt_conv_down(d, large, (const float*)w, bias, small, (cudaStream_t)stream);
+}
+extern "C" int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large, void* stream) {
+  GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_up: null pointer");
+  if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream);
+  return simt_conv_up(d, small, (const float*)w, bias, large, (cudaStream_t)stream);
+}
+extern "C" int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw, void* stream) {
+  GG_REQUIRE(d && large && dw && small, GG_ERR_INVALID, "conv_wgrad: null pointer");
+  if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
+  return simt_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
+}
+
+static gg_conv_desc no_act(const gg_conv_desc* d) { gg_conv_desc c = *d; c.act = GG_ACT_NONE; return c; }
+
+extern "C" int gg_conv2d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* s) { return gg_conv_down(d, x, w, b, y, s); }
+extern "C" int gg_conv2d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* s) { GG_REQUIRE(d, GG_ERR_INVALID, "null desc"); gg_conv_desc c = no_act(d); return gg_conv_up(&c, dy, w, nullptr, dx, s); }
+extern "C" int gg_conv2d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float* dw, void* s) { return gg_conv_wgrad(d, x, dy, dw, s); }
+extern "C" int gg_deconv2d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* s) { return gg_conv_up(d, x, w, b, y, s); }
+extern "C" int gg_deconv2d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* s) { GG_REQUIRE(d, GG_ERR_INVALID, "null desc"); gg_conv_desc c = no_act(d); return gg_conv_down(&c, dy, w, nullptr, dx, s); }
+extern "C" int gg_deconv2d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float* dw, void* s) { return gg_conv_wgrad(d, dy, x, dw, s); }
+extern "C" int gg_conv3d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* s) { return gg_conv_down(d, x, w, b, y, s); }
+extern "C" int gg_conv3d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* s) { GG_REQUIRE(d, GG_ERR_INVALID, "null desc"); gg_conv_desc c = no_act(d); return gg_conv_up(&c, dy, w, nullptr, dx, s); }
+extern "C" int gg_conv3d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float* dw, void* s) { return gg_conv_wgrad(d, x, dy, dw, s); }
+
+extern "C" int gg_linear_fwd(const void* x, int32_t x_dt, const float* matrix, const float* bias, void* y, int32_t y_dt, int32_t rows,
+                             int32_t in_dim, int32_t out_dim, int32_t act, float ap, void* stream) {
+  GG_REQUIRE(x && matrix && y && rows > 0 && in_dim > 0 && out_dim > 0, GG_ERR_INVALID, "linear_fwd: bad argument");
+  if (out_dim <= 4) return skinny_linear_fwd(x, x_dt, matrix, bias, y, y_dt, rows, in_dim, out_dim, act, ap, (cudaStream_t)stream);
+  return simt_linear_fwd(x, x_dt, matrix, bias, y, y_dt, rows, in_dim, out_dim, act, ap, (cudaStream_t)stream);
+}
+extern "C" int gg_linear_dgrad(const void* dy, int32_t dy_dt, const float* matrix, void* dx, int32_t dx_dt, int32_t rows, int32_t in_dim,
+                               int32_t out_dim, void* stream) {
+  GG_REQUIRE(dy && matrix && dx && rows > 0 && in_dim > 0 && out_dim > 0, GG_ERR_INVALID, "linear_dgrad: bad argument");
+  if (out_dim <= 4) return skinny_linear_dgrad(dy, dy_dt, matrix, dx, dx_dt, rows, in_dim, out_dim, (cudaStream_t)stream);
+  return simt_linear_dgrad(dy, dy_dt, matrix, dx, dx_dt, rows, in_dim, out_dim, (cudaStream_t)stream);
+}
+extern "C" int gg_linear_wgrad(const void* x, int32_t x_dt, const void* dy, int32_t dy_dt, float* dmatrix, float* dbias, int32_t rows,
+                               int32_t in_dim, int32_t out_dim, void* stream) {
+  GG_REQUIRE(x && dy && rows > 0 && in_dim > 0 && out_dim > 0, GG_ERR_INVALID, "linear_wgrad: bad argument");
+  int rc = GG_OK;
+  if (dmatrix) {
+    if (out_dim <= 4) rc = skinny_linear_wgrad(x, x_dt, dy, dy_dt, dmatrix, rows, in_dim, out_dim, (cudaStream_t)stream);
+    else rc = simt_linear_wgrad(x, x_dt, dy, dy_dt, dmatrix, rows, in_dim, out_dim, (cudaStream_t)stream);
+  }
+  if (rc == GG_OK && dbias) rc = gg_bias_grad(dy, dy_dt, dbias, rows, out_dim, stream);
+  return rc;
+}

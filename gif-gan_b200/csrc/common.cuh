@@ -1,0 +1,119 @@
+// Shared helpers for libgifgan.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/gifgan.h"
+
+namespace gg {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return GG_ERR_CUDA;
+  }
+  return GG_OK;
+}
+
+#define GG_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) {                  \
+      gg::set_error(__VA_ARGS__);   \
+      return (code);                \
+    }                               \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+typedef __nv_bfloat16 bf16;
+
+// ---- element load/store with conversion to/from fp32 ------------------------------
+__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 4 consecutive elements (address must be 16 B / 8 B aligned)
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---- activations (include/gifgan.h gg_act) ----------------------------------------
+__device__ __forceinline__ float act_fwd(float u, int act, float a) {
+  switch (act) {
+    case GG_ACT_RELU: return fmaxf(u, 0.f);
+    case GG_ACT_LRELU: return fmaxf(u, a * u);
+    case GG_ACT_TANH: return tanhf(u);
+    case GG_ACT_SIGMOID: return 1.f / (1.f + expf(-u));
+    case GG_ACT_TANH01: return 0.5f * (tanhf(u) + 1.f);
+    default: return u;
+  }
+}
+// derivative expressed through the OUTPUT y = act(u)
+__device__ __forceinline__ float act_grad_from_out(float y, int act, float a) {
+  switch (act) {
+    case GG_ACT_RELU: return y > 0.f ? 1.f : 0.f;           // tf.nn.relu: 0 at 0
+    case GG_ACT_LRELU: return y >= 0.f ? 1.f : a;            // tf.maximum(x, a*x): 1 at 0 (0<a<1)
+    case GG_ACT_TANH: return 1.f - y * y;
+    case GG_ACT_SIGMOID: return y * (1.f - y);
+    case GG_ACT_TANH01: { float t = 2.f * y - 1.f; return 0.5f * (1.f - t * t); }
+    default: return 1.f;
+  }
+}
+// derivative expressed through the pre-activation u
+__device__ __forceinline__ float act_grad_from_pre(float u, int act, float a) {
+  switch (act) {
+    case GG_ACT_RELU: return u > 0.f ? 1.f : 0.f;
+    case GG_ACT_LRELU: return u >= 0.f ? 1.f : a;
+    case GG_ACT_TANH: { float t = tanhf(u); return 1.f - t * t; }
+    case GG_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-u)); return s * (1.f - s); }
+    case GG_ACT_TANH01: { float t = tanhf(u); return 0.5f * (1.f - t * t); }
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline size_t dtype_size(int dt) { return dt == GG_BF16 ? 2 : 4; }
+
+// dispatch a lambda-like macro over (dtype) -> type
+#define GG_DISPATCH_DTYPE(dt, T, ...)                   \
+  do {                                                  \
+    if ((dt) == GG_F32) {                               \
+      typedef float T;                                  \
+      __VA_ARGS__;                                      \
+    } else {                                            \
+      typedef gg::bf16 T;                               \
+      __VA_ARGS__;                                      \
+    }                                                   \
+  } while (0)
+
+}  // namespace gg

@@ -1,0 +1,436 @@
+// Fused elementwise / small-reduction kernels: activation fwd/bwd, casts, filter packing,
+// sigmoid cross-entropy fwd+bwd, first-frame MSE, TF-flavoured Adam, skinny linear layers
+// (out_dim <= 4: d_h3_lin, dvideo_h4, d_final_fc) and the fused BasicLSTMCell step.
+// All HBM- or latency-bound; 16 B vector accesses, grid-stride loops sized to the SM count.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int PW_THREADS = 256;
+static inline int pw_blocks(int64_t n_vec) { return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n_vec, PW_THREADS), 148 * 8)); }
+static inline bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
+
+// ---- activations ------------------------------------------------------------------------
+template <typename TY, typename TD, typename TO, bool VEC>
+__global__ void act_bwd_kernel(const TY* __restrict__ y, const TD* __restrict__ dy, TO* __restrict__ dx, int64_t n, int act, float ap) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
+      const float4 a = ld4(y + i * 4), g = ld4(dy + i * 4);
+      st4(dx + i * 4, make_float4(g.x * act_grad_from_out(a.x, act, ap), g.y * act_grad_from_out(a.y, act, ap),
+                                  g.z * act_grad_from_out(a.z, act, ap), g.w * act_grad_from_out(a.w, act, ap)));
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      stf(dx + i, ldf(dy + i) * act_grad_from_out(ldf(y + i), act, ap));
+  }
+}
+
+template <typename TX, typename TY, bool VEC>
+__global__ void act_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t n, int act, float ap) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
+      const float4 a = ld4(x + i * 4);
+      st4(y + i * 4, make_float4(act_fwd(a.x, act, ap), act_fwd(a.y, act, ap), act_fwd(a.z, act, ap), act_fwd(a.w, act, ap)));
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) stf(y + i, act_fwd(ldf(x + i), act, ap));
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, float a, float* __restrict__ y, float b, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
+}
+
+// ---- filter packing for the tensor-core path ----------------------------------------------
+// w [taps][C][K] fp32 -> w_ck bf16 [taps][C][K] and w_kc bf16 [taps][K][C] (32x32 smem transpose)
+__global__ void pack_filter_kernel(const float* __restrict__ w, bf16* __restrict__ w_ck, bf16* __restrict__ w_kc, int C, int K) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z, c0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const float* src = w + (int64_t)t * C * K;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, k = k0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && k < K) {
+      v = src[(int64_t)c * K + k];
+      if (w_ck) w_ck[(int64_t)t * C * K + (int64_t)c * K + k] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (w_kc) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int k = k0 + i, c = c0 + threadIdx.x;
+      if (c < C && k < K) w_kc[(int64_t)t * C * K + (int64_t)k * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// ---- losses --------------------------------------------------------------------------------
+__global__ void sigmoid_ce_kernel(const float* __restrict__ logits, int64_t n, float target, float weight, float* __restrict__ loss_out,
+                                  int accumulate, float* __restrict__ dlogits) {
+  __shared__ float red[PW_THREADS];
+  float acc = 0.f;
+  const float inv = 1.f / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = logits[i];
+    // tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log(1+exp(-|x|))
+    acc += fmaxf(x, 0.f) - x * target + log1pf(expf(-fabsf(x)));
+    if (dlogits) dlogits[i] = weight * inv * (1.f / (1.f + expf(-x)) - target);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = PW_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (accumulate ? loss_out[0] : 0.f) + weight * red[0] * inv;
+}
+
+__global__ void mse_kernel(const float* __restrict__ a, int64_t as, const float* __restrict__ b, int64_t bs, int64_t rows, int64_t cols,
+                           float scalar, float* __restrict__ loss_out, int accumulate, float* __restrict__ da) {
+  __shared__ float red[PW_THREADS];
+  float acc = 0.f;
+  const int64_t n = rows * cols;
+  const float inv = 1.f / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const float d = a[r * as + c] - b[r * bs + c];
+    acc += d * d;
+    if (da) da[r * cols + c] = scalar * 2.f * d * inv;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = PW_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (accumulate ? loss_out[0] : 0.f) + scalar * red[0] * inv;
+}
+
+// ---- TF Adam (model.py:153-156) ----------------------------------------------
+__global__ void __launch_bounds__(PW_THREADS)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr_t,
+            float b1, float b2, float eps, float gs) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], gg4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; float* G = &gg4.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = G[k] * gs;
+      M[k] = b1 * M[k] + (1.f - b1) * gr;
+      V[k] = b2 * V[k] + (1.f - b2) * gr * gr;
+      P[k] -= lr_t * M[k] / (sqrtf(V[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gr = g[i] * gs;
+    const float mi = b1 * m[i] + (1.f - b1) * gr, vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// device-side step counter so that a captured CUDA graph advances Adam's bias correction:
+// state[0] = t (int32), state[1] = lr_t (float bits).  Double precision like the host formula.
+__global__ void adam_tick_kernel(int* __restrict__ state, float lr, float b1, float b2) {
+  const int t = state[0] + 1;
+  state[0] = t;
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
+  reinterpret_cast<float*>(state)[1] = (float)lr_t;
+}
+__global__ void __launch_bounds__(PW_THREADS)
+adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                const int* __restrict__ state, float b1, float b2, float eps, float gs) {
+  const float lr_t = reinterpret_cast<const float*>(state)[1];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], gg4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; float* G = &gg4.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = G[k] * gs;
+      M[k] = b1 * M[k] + (1.f - b1) * gr;
+      V[k] = b2 * V[k] + (1.f - b2) * gr * gr;
+      P[k] -= lr_t * M[k] / (sqrtf(V[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gr = g[i] * gs;
+    const float mi = b1 * m[i] + (1.f - b1) * gr, vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// ---- skinny linear (out_dim <= 4) ---------------------------------------------------------------
+// fwd: y[r, n] = act(sum_k x[r,k] W[k,n] + b[n]); one CTA per row
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(PW_THREADS)
+skinny_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, TY* __restrict__ y, int in_dim,
+                  int out_dim, int act, float ap) {
+  const int r = blockIdx.x;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = threadIdx.x; k < in_dim; k += blockDim.x) {
+    const float xv = ldf(x + (int64_t)r * in_dim + k);
+    for (int n = 0; n < out_dim; ++n) acc[n] = fmaf(xv, __ldg(W + (int64_t)k * out_dim + n), acc[n]);
+  }
+  __shared__ float red[4][PW_THREADS / 32];
+  for (int n = 0; n < out_dim; ++n) {
+    const float s = warp_sum(acc[n]);
+    if ((threadIdx.x & 31) == 0) red[n][threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < out_dim) {
+    float s = bias ? bias[threadIdx.x] : 0.f;
+    for (int w = 0; w < PW_THREADS / 32; ++w) s += red[threadIdx.x][w];
+    stf(y + (int64_t)r * out_dim + threadIdx.x, act_fwd(s, act, ap));
+  }
+}
+// dgrad: dx[r,k] = sum_n dy[r,n] W[k,n]
+template <typename TD, typename TO>
+__global__ void skinny_dgrad_kernel(const TD* __restrict__ dy, const float* __restrict__ W, TO* __restrict__ dx, int64_t rows, int in_dim, int out_dim) {
+  const int64_t total = rows * in_dim;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / in_dim;
+    const int k = (int)(i - r * in_dim);
+    float s = 0.f;
+    for (int n = 0; n < out_dim; ++n) s = fmaf(ldf(dy + r * out_dim + n), __ldg(W + (int64_t)k * out_dim + n), s);
+    stf(dx + i, s);
+  }
+}
+// wgrad: dW[k,n] += sum_r x[r,k] dy[r,n]
+template <typename TX, typename TD>
+__global__ void skinny_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __restrict__ dW, int rows, int in_dim, int out_dim) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= in_dim) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < rows; ++r) {
+    const float xv = ldf(x + (int64_t)r * in_dim + k);
+    for (int n = 0; n < out_dim; ++n) acc[n] = fmaf(xv, ldf(dy + (int64_t)r * out_dim + n), acc[n]);
+  }
+  for (int n = 0; n < out_dim; ++n) dW[(int64_t)k * out_dim + n] += acc[n];
+}
+
+// ---- BasicLSTMCell step (recurrent_DCGAN.py:199-200) --------------------------------
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+
+// one CTA per batch row; thread j < H produces the 4 gates of unit j
+__global__ void lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ Wh, const float* __restrict__ c_prev,
+                                const float* __restrict__ h_prev, float* __restrict__ c_out, float* __restrict__ h_out,
+                                float* __restrict__ gates_out, int H, float fb) {
+  extern __shared__ float hs[];
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) hs[k] = h_prev[(int64_t)b * H + k];
+  __syncthreads();
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] = gx[(int64_t)b * 4 * H + q * H + j];
+    for (int k = 0; k < H; ++k) {
+      const float hv = hs[k];
+      const float* wr = Wh + (int64_t)k * 4 * H + j;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g[q] = fmaf(hv, __ldg(wr + q * H), g[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gates_out[(int64_t)b * 4 * H + q * H + j] = g[q];
+    const float c = c_prev[(int64_t)b * H + j] * sigm(g[2] + fb) + sigm(g[0]) * tanhf(g[1]);
+    c_out[(int64_t)b * H + j] = c;
+    h_out[(int64_t)b * H + j] = tanhf(c) * sigm(g[3]);
+  }
+}
+
+__global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_out,
+                                const float* __restrict__ dh, const float* __restrict__ dc, const float* __restrict__ Wh,
+                                float* __restrict__ dgates, float* __restrict__ dc_prev, float* __restrict__ dh_prev, int H, float fb) {
+  extern __shared__ float dg[];  // [4H]
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const float gi = gates[(int64_t)b * 4 * H + j], gj = gates[(int64_t)b * 4 * H + H + j];
+    const float gf = gates[(int64_t)b * 4 * H + 2 * H + j], go = gates[(int64_t)b * 4 * H + 3 * H + j];
+    const float si = sigm(gi), tj = tanhf(gj), sf = sigm(gf + fb), so = sigm(go);
+    const float tc = tanhf(c_out[(int64_t)b * H + j]);
+    const float dhv = dh[(int64_t)b * H + j];
+    const float dct = (dc ? dc[(int64_t)b * H + j] : 0.f) + dhv * so * (1.f - tc * tc);
+    const float d_o = dhv * tc * so * (1.f - so);
+    const float d_i = dct * tj * si * (1.f - si);
+    const float d_j = dct * si * (1.f - tj * tj);
+    const float d_f = dct * c_prev[(int64_t)b * H + j] * sf * (1.f - sf);
+    dc_prev[(int64_t)b * H + j] = dct * sf;
+    dg[j] = d_i; dg[H + j] = d_j; dg[2 * H + j] = d_f; dg[3 * H + j] = d_o;
+    dgates[(int64_t)b * 4 * H + j] = d_i; dgates[(int64_t)b * 4 * H + H + j] = d_j;
+    dgates[(int64_t)b * 4 * H + 2 * H + j] = d_f; dgates[(int64_t)b * 4 * H + 3 * H + j] = d_o;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    const float* wr = Wh + (int64_t)k * 4 * H;
+    float s = 0.f;
+    for (int q = 0; q < 4 * H; ++q) s = fmaf(dg[q], __ldg(wr + q), s);
+    dh_prev[(int64_t)b * H + k] = s;
+  }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int gg_act_bwd(const void* y, int32_t y_dt, const void* dy, int32_t dy_dt, void* dx, int32_t dx_dt, int64_t n, int32_t act,
+                          float ap, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GG_REQUIRE(y && dy && dx && n > 0, GG_ERR_INVALID, "act_bwd: bad argument");
+  const bool vec = (n % 4 == 0) && al16(y) && al16(dy) && al16(dx);
+  const int blocks = pw_blocks(vec ? n / 4 : n);
+#define GG_AB(TY, TD, TO)                                                                                            \
+  do {                                                                                                               \
+    if (vec) act_bwd_kernel<TY, TD, TO, true><<<blocks, PW_THREADS, 0, st>>>((const TY*)y, (const TD*)dy, (TO*)dx, n, act, ap);  \
+    else act_bwd_kernel<TY, TD, TO, false><<<blocks, PW_THREADS, 0, st>>>((const TY*)y, (const TD*)dy, (TO*)dx, n, act, ap);     \
+  } while (0)
+  const int key = (y_dt == GG_BF16 ? 4 : 0) | (dy_dt == GG_BF16 ? 2 : 0) | (dx_dt == GG_BF16 ? 1 : 0);
+  switch (key) {
+    case 0: GG_AB(float, float, float); break;
+    case 1: GG_AB(float, float, bf16); break;
+    case 2: GG_AB(float, bf16, float); break;
+    case 3: GG_AB(float, bf16, bf16); break;
+    case 4: GG_AB(bf16, float, float); break;
+    case 5: GG_AB(bf16, float, bf16); break;
+    case 6: GG_AB(bf16, bf16, float); break;
+    default: GG_AB(bf16, bf16, bf16); break;
+  }
+  return check_launch("act_bwd");
+}
+
+static int act_fwd_impl(const void* x, int x_dt, void* y, int y_dt, int64_t n, int act, float ap, cudaStream_t st) {
+  const bool vec = (n % 4 == 0) && al16(x) && al16(y);
+  const int blocks = pw_blocks(vec ? n / 4 : n);
+#define GG_AF(TX, TY)                                                                                      \
+  do {                                                                                                     \
+    if (vec) act_fwd_kernel<TX, TY, true><<<blocks, PW_THREADS, 0, st>>>((const TX*)x, (TY*)y, n, act, ap);  \
+    else act_fwd_kernel<TX, TY, false><<<blocks, PW_THREADS, 0, st>>>((const TX*)x, (TY*)y, n, act, ap);     \
+  } while (0)
+  if (x_dt == GG_F32 && y_dt == GG_F32) GG_AF(float, float);
+  else if (x_dt == GG_F32) GG_AF(float, bf16);
+  else if (y_dt == GG_F32) GG_AF(bf16, float);
+  else GG_AF(bf16, bf16);
+  return check_launch("act_fwd");
+}
+
+extern "C" int gg_act_fwd(const void* x, int32_t x_dt, void* y, int32_t y_dt, int64_t n, int32_t act, float ap, void* stream) {
+  GG_REQUIRE(x && y && n > 0, GG_ERR_INVALID, "act_fwd: bad argument");
+  return act_fwd_impl(x, x_dt, y, y_dt, n, act, ap, (cudaStream_t)stream);
+}
+
+extern "C" int gg_cast(const void* src, int32_t s_dt, void* dst, int32_t d_dt, int64_t n, void* stream) {
+  GG_REQUIRE(src && dst && n > 0, GG_ERR_INVALID, "cast: bad argument");
+  return act_fwd_impl(src, s_dt, dst, d_dt, n, GG_ACT_NONE, 0.f, (cudaStream_t)stream);
+}
+
+extern "C" int gg_axpby(const float* x, float a, float* y, float b, int64_t n, void* stream) {
+  GG_REQUIRE(x && y && n > 0, GG_ERR_INVALID, "axpby: bad argument");
+  axpby_kernel<<<pw_blocks(n), PW_THREADS, 0, (cudaStream_t)stream>>>(x, a, y, b, n);
+  return check_launch("axpby");
+}
+
+extern "C" int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t C, int32_t K, void* stream) {
+  GG_REQUIRE(w && (w_ck || w_kc) && taps > 0 && C > 0 && K > 0, GG_ERR_INVALID, "pack_filter: bad argument");
+  dim3 grid(ceil_div(K, 32), ceil_div(C, 32), taps), block(32, 8);
+  pack_filter_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, (bf16*)w_ck, (bf16*)w_kc, C, K);
+  return check_launch("pack_filter");
+}
+
+extern "C" int gg_sigmoid_ce(const float* logits, int64_t n, float target, float weight, float* loss_out, int32_t accumulate,
+                             float* dlogits, void* stream) {
+  GG_REQUIRE(logits && loss_out && n > 0, GG_ERR_INVALID, "sigmoid_ce: bad argument");
+  sigmoid_ce_kernel<<<1, PW_THREADS, 0, (cudaStream_t)stream>>>(logits, n, target, weight, loss_out, accumulate, dlogits);
+  return check_launch("sigmoid_ce");
+}
+
+extern "C" int gg_mse(const float* a, int64_t as, const float* b, int64_t bs, int64_t rows, int64_t cols, float scalar, float* loss_out,
+                      int32_t accumulate, float* da, void* stream) {
+  GG_REQUIRE(a && b && loss_out && rows > 0 && cols > 0, GG_ERR_INVALID, "mse: bad argument");
+  mse_kernel<<<1, PW_THREADS, 0, (cudaStream_t)stream>>>(a, as, b, bs, rows, cols, scalar, loss_out, accumulate, da);
+  return check_launch("mse");
+}
+
+extern "C" int gg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps, float gs,
+                       void* stream) {
+  GG_REQUIRE(p && g && m && v && n > 0, GG_ERR_INVALID, "adam: bad argument");
+  GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v), GG_ERR_INVALID, "adam: buffers must be 16-byte aligned");
+  adam_kernel<<<pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, b1, b2, eps, gs);
+  return check_launch("adam");
+}
+
+extern "C" int gg_adam_graph(float* p, const float* g, float* m, float* v, int64_t n, int32_t* state, float lr, float b1, float b2,
+                             float eps, float gs, void* stream) {
+  GG_REQUIRE(p && g && m && v && state && n > 0, GG_ERR_INVALID, "adam_graph: bad argument");
+  GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v), GG_ERR_INVALID, "adam_graph: buffers must be 16-byte aligned");
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, b1, b2);
+  int rc = check_launch("adam_tick");
+  if (rc) return rc;
+  adam_dev_kernel<<<pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state, b1, b2, eps, gs);
+  return check_launch("adam_dev");
+}
+
+namespace gg {
+int skinny_linear_fwd(const void* x, int x_dt, const float* W, const float* bias, void* y, int y_dt, int rows, int in_dim, int out_dim,
+                      int act, float ap, cudaStream_t st) {
+#define GG_SF(TX, TY) skinny_fwd_kernel<TX, TY><<<rows, PW_THREADS, 0, st>>>((const TX*)x, W, bias, (TY*)y, in_dim, out_dim, act, ap)
+  if (x_dt == GG_F32 && y_dt == GG_F32) GG_SF(float, float);
+  else if (x_dt == GG_F32) GG_SF(float, bf16);
+  else if (y_dt == GG_F32) GG_SF(bf16, float);
+  else GG_SF(bf16, bf16);
+  return check_launch("skinny_fwd");
+}
+int skinny_linear_dgrad(const void* dy, int dy_dt, const float* W, void* dx, int dx_dt, int rows, int in_dim, int out_dim, cudaStream_t st) {
+  const int blocks = pw_blocks((int64_t)rows * in_dim);
+#define GG_SD(TD, TO) skinny_dgrad_kernel<TD, TO><<<blocks, PW_THREADS, 0, st>>>((const TD*)dy, W, (TO*)dx, rows, in_dim, out_dim)
+  if (dy_dt == GG_F32 && dx_dt == GG_F32) GG_SD(float, float);
+  else if (dy_dt == GG_F32) GG_SD(float, bf16);
+  else if (dx_dt == GG_F32) GG_SD(bf16, float);
+  else GG_SD(bf16, bf16);
+  return check_launch("skinny_dgrad");
+}
+int skinny_linear_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dW, int rows, int in_dim, int out_dim, cudaStream_t st) {
+  const int blocks = ceil_div(in_dim, 128);
+#define GG_SW(TX, TD) skinny_wgrad_kernel<TX, TD><<<blocks, 128, 0, st>>>((const TX*)x, (const TD*)dy, dW, rows, in_dim, out_dim)
+  if (x_dt == GG_F32 && dy_dt == GG_F32) GG_SW(float, float);
+  else if (x_dt == GG_F32) GG_SW(float, bf16);
+  else if (dy_dt == GG_F32) GG_SW(bf16, float);
+  else GG_SW(bf16, bf16);
+  return check_launch("skinny_wgrad");
+}
+}  // namespace gg
+
+extern "C" int gg_lstm_step_fwd(const float* gx, const float* Wh, const float* c_prev, const float* h_prev, float* c_out, float* h_out,
+                                float* gates_out, int32_t B, int32_t H, float fb, void* stream) {
+  GG_REQUIRE(gx && Wh && c_prev && h_prev && c_out && h_out && gates_out && B > 0 && H > 0, GG_ERR_INVALID, "lstm_fwd: bad argument");
+  GG_REQUIRE(H <= 4096, GG_ERR_UNSUPPORTED, "lstm_fwd: H > 4096 unsupported");
+  const int threads = std::min(256, ((H + 31) / 32) * 32);
+  lstm_fwd_kernel<<<B, threads, H * sizeof(float), (cudaStream_t)stream>>>(gx, Wh, c_prev, h_prev, c_out, h_out, gates_out, H, fb);
+  return check_launch("lstm_fwd");
+}
+
+extern "C" int gg_lstm_step_bwd(const float* gates, const float* c_prev, const float* c_out, const float* dh, const float* dc,
+                                const float* Wh, float* dgates, float* dc_prev, float* dh_prev, int32_t B, int32_t H, float fb,
+                                void* stream) {
+  GG_REQUIRE(gates && c_prev && c_out && dh && Wh && dgates && dc_prev && dh_prev && B > 0 && H > 0, GG_ERR_INVALID, "lstm_bwd: bad argument");
+  GG_REQUIRE(H <= 2048, GG_ERR_UNSUPPORTED, "lstm_bwd: H > 2048 unsupported");
+  const int threads = std::min(256, ((H + 31) / 32) * 32);
+  lstm_bwd_kernel<<<B, threads, 4 * H * sizeof(float), (cudaStream_t)stream>>>(gates, c_prev, c_out, dh, dc, Wh, dgates, dc_prev, dh_prev, H, fb);
+  return check_launch("lstm_bwd");
+}

@@ -1,0 +1,732 @@
+"""Operator layer -- the drop-in for /root/reference/models/recurrent_z/ops.py.
+
+Same function names, argument order and defaults as the reference (`conv2d`,
+`deconv2d`, `conv3d`, `linear`, `batch_norm`, `lrelu`, `add_noise`, `get_std`,
+`conv_cond_concat`), same variable names under the same scopes,
+NHWC activations -- but every op is a `torch.autograd.Function` whose forward and
+backward call the hand-written sm_100a kernels of libgifgan.so through the C ABI
+(`_cabi.py`).  TensorFlow's graph/variable machinery is replaced by:
+
+  * `VariableStore` + `variable_scope` / `get_variable`: named fp32 master variables,
+    re-packed into flat parameter/gradient/Adam buffers per optimiser group so that
+    one fused Adam launch and one gradient all-reduce bucket cover a whole var_list;
+  * "symbolic" graph construction = calling the ops on `device='meta'` tensors: shapes
+    propagate, variables get created, nothing is computed (what `build_model` does);
+  * filter gradients are written by the wgrad kernels straight into the flat gradient
+    buffer (accumulating, like TF's gradient aggregation when a variable is used
+    twice); autograd only routes activation gradients.
+
+Extensions over the reference signatures (keyword-only, default = reference
+behaviour): `act=` fuses the activation that follows into the producing kernel's
+epilogue; `groups=` on batch_norm normalises row blocks independently.
+
+Precision: `set_precision('fp32')` -- everything fp32, SIMT FFMA kernels (1e-4 parity
+mode); `set_precision('bf16')` -- activations bf16, fp32 master weights / statistics /
+accumulation, tcgen05 tensor-core kernels where the channel counts allow.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _cabi as cabi
+from ._cabi import ACT, ConvDesc, check, dt, ptr, stream
+
+# --------------------------------------------------------------------------------------
+# configuration
+# --------------------------------------------------------------------------------------
+_PRECISION = "fp32"
+TC_DEFAULT = False      # flipped to True once the tcgen05 kernels are validated on hardware
+_USE_TC = TC_DEFAULT
+
+
+def set_precision(p: str, tensor_cores=None):
+    """'fp32' | 'bf16'.  tensor_cores: use the tcgen05 kernels in bf16 mode (None -> TC_DEFAULT)."""
+    global _PRECISION, _USE_TC
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION, _USE_TC = p, (TC_DEFAULT if tensor_cores is None else bool(tensor_cores))
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def act_dtype():
+    return torch.float32 if _PRECISION == "fp32" else torch.bfloat16
+
+
+def same_pad(n: int, k: int, s: int):
+    """TF 'SAME' (SURVEY App. A.1): out = ceil(n/s), pad_lo = total//2."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return out, total // 2, total - total // 2
+
+
+# --------------------------------------------------------------------------------------
+# variables
+# --------------------------------------------------------------------------------------
+class Var:
+    """A named fp32 variable (tf.get_variable).  `.data` / `.grad` may be views into the
+    store's flat buffers after `VariableStore.finalize`."""
+
+    def __init__(self, name, data, trainable=True, filter_taps=None):
+        self.name, self.data, self.trainable = name, data, trainable
+        self.grad = None
+        self.filter_taps = filter_taps      # not None for conv/deconv/conv3d filters [taps..., C, K]
+        self.version = 0
+        self._packed = None
+        self._packed_version = -1
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    def numel(self):
+        return self.data.numel()
+
+    def packed(self):
+        """bf16 copies (w_ck, w_kc) for the tensor-core kernels, refreshed after each update."""
+        if self._packed is None:
+            self._packed = (torch.empty(self.data.shape, dtype=torch.bfloat16, device=self.data.device),
+                            torch.empty(self.data.shape, dtype=torch.bfloat16, device=self.data.device))
+        if self._packed_version != self.version:
+            C_, K_ = self.data.shape[-2], self.data.shape[-1]
+            taps = self.data.numel() // (C_ * K_)
+            check(cabi.lib().gg_pack_filter(ptr(self.data), ptr(self._packed[0]), ptr(self._packed[1]), taps, C_, K_, stream()),
+                  "gg_pack_filter")
+            self._packed_version = self.version
+        return self._packed
+
+
+class VariableStore:
+    def __init__(self, device=None, seed=0):
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"   # cpu: inventory/checkpoint logic only
+        self.device = torch.device(device)
+        self.vars: "OrderedDict[str, Var]" = OrderedDict()
+        self.rng = np.random.RandomState(seed)
+        self._scope: list[str] = []
+        self.flat = None           # dict(params=, grads=, m=, v=) after finalize
+        self.ranges = {}           # group name -> (begin, end) element range in the flat buffers
+
+    # -- scopes ---------------------------------------------------------------------
+    def scope_name(self):
+        return "".join(s + "/" for s in self._scope)
+
+    # -- creation -------------------------------------------------------------------
+    def get_variable(self, name, shape, initializer, trainable=True, filter_taps=None) -> Var:
+        full = self.scope_name() + name
+        v = self.vars.get(full)
+        if v is not None:
+            if tuple(v.shape) != tuple(int(s) for s in shape):
+                raise ValueError(f"variable {full} exists with shape {v.shape}, requested {tuple(shape)}")
+            return v
+        if self.flat is not None:
+            raise RuntimeError(f"variable {full} created after VariableStore.finalize()")
+        arr = initializer(self.rng, tuple(int(s) for s in shape))
+        data = torch.as_tensor(np.asarray(arr, dtype=np.float32)).to(self.device).contiguous()
+        v = Var(full, data, trainable, filter_taps)
+        self.vars[full] = v
+        return v
+
+    # -- flat buffers -----------------------------------------------------------------
+    def finalize(self, groups: "OrderedDict[str, list[Var]]"):
+        """Re-pack variables into one flat fp32 buffer; each group (an optimiser's
+        var_list) occupies a contiguous, 16-byte aligned range so that Adam and the
+        gradient all-reduce run once per group.  Adam slots m, v mirror it."""
+        ordered, seen = [], set()
+        self.ranges = {}
+        off = 0
+        for gname, vs in groups.items():
+            beg = off
+            for v in vs:
+                if v.name in seen:
+                    raise ValueError(f"{v.name} is in two optimiser groups")
+                seen.add(v.name)
+                ordered.append((v, off))
+                off += (v.numel() + 3) // 4 * 4
+            self.ranges[gname] = (beg, off)
+        for v in self.vars.values():
+            if v.name not in seen:
+                ordered.append((v, off))
+                off += (v.numel() + 3) // 4 * 4
+        total = off
+        dev = self.device
+        params = torch.zeros(total, dtype=torch.float32, device=dev)
+        grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        trainable_end = max([e for _, e in self.ranges.values()], default=0)
+        m = torch.zeros(trainable_end, dtype=torch.float32, device=dev)
+        v2 = torch.zeros(trainable_end, dtype=torch.float32, device=dev)
+        for v, o in ordered:
+            n = v.numel()
+            params[o:o + n].copy_(v.data.reshape(-1))
+            shape = v.data.shape
+            v.data = params[o:o + n].view(shape)
+            v.grad = grads[o:o + n].view(shape)
+            v.offset = o
+            v.version += 1
+        self.flat = dict(params=params, grads=grads, m=m, v=v2)
+
+    # -- checkpoint (keys = TF variable names) -------------------------
+    def state_dict(self):
+        return OrderedDict((k, v.data.detach().clone().cpu()) for k, v in self.vars.items())
+
+    def load_state_dict(self, sd, strict=True, prefix=""):
+        missing = []
+        with torch.no_grad():
+            for k, v in self.vars.items():
+                if not k.startswith(prefix):
+                    continue
+                key = k[len(prefix):]
+                if key in sd:
+                    v.data.copy_(torch.as_tensor(np.asarray(sd[key]), dtype=torch.float32).reshape(v.data.shape))
+                    v.version += 1
+                elif strict:
+                    missing.append(key)
+        if missing:
+            raise KeyError(f"missing variables in checkpoint: {missing[:5]}...")
+
+
+_STORE = VariableStore.__new__(VariableStore)  # replaced by reset_default_store()
+_STORE_READY = False
+
+
+def reset_default_store(device=None, seed=0) -> VariableStore:
+    """Start a fresh 'graph' (tf.reset_default_graph)."""
+    global _STORE, _STORE_READY
+    _STORE = VariableStore(device, seed)
+    _STORE_READY = True
+    return _STORE
+
+
+def default_store() -> VariableStore:
+    if not _STORE_READY:
+        reset_default_store()
+    return _STORE
+
+
+@contextlib.contextmanager
+def variable_scope(name, reuse=None):
+    """tf.variable_scope(name).  Reuse is automatic: get_variable returns the existing
+    variable of that name (the reference always calls reuse_variables() before a second use)."""
+    st = default_store()
+    st._scope.append(name)
+    try:
+        yield st
+    finally:
+        st._scope.pop()
+
+
+def truncated_normal_initializer(stddev=0.02):
+    def init(rs, shape):
+        out = rs.normal(0.0, 1.0, size=shape)
+        bad = np.abs(out) > 2.0
+        while bad.any():
+            out[bad] = rs.normal(0.0, 1.0, size=int(bad.sum()))
+            bad = np.abs(out) > 2.0
+        return out * stddev
+    return init
+
+
+def random_normal_initializer(stddev=0.02):
+    return lambda rs, shape: rs.normal(0.0, stddev, size=shape)
+
+
+def constant_initializer(value=0.0):
+    return lambda rs, shape: np.full(shape, value, dtype=np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+def _is_meta(t):
+    return t.device.type == "meta"
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: tensor on {t.device}; gif-gan_b200 has no CPU fallback (use CUDA, or 'meta' to build)")
+
+
+def _wtensor(var: Var, requires_grad: bool):
+    """The autograd handle of a variable: its data tensor with requires_grad set by the
+    current var_list (see `trainable`)."""
+    t = var.data
+    if t.requires_grad != requires_grad:
+        t.requires_grad_(requires_grad)
+    return t
+
+
+_TRAINABLE: set = set()
+
+
+@contextlib.contextmanager
+def trainable(var_list):
+    """Variables that receive gradients in this region -- the `var_list` of
+    tf.train.AdamOptimizer(...).minimize(loss, var_list=...) (model.py:153-156)."""
+    global _TRAINABLE
+    old = _TRAINABLE
+    _TRAINABLE = {v.name for v in var_list}
+    try:
+        yield
+    finally:
+        _TRAINABLE = old
+
+
+def _wants_grad(var: Var) -> bool:
+    return var.trainable and var.name in _TRAINABLE and torch.is_grad_enabled()
+
+
+def _tc_ok(C_, K_, *tensors) -> bool:
+    return (_PRECISION == "bf16" and _USE_TC and C_ % 64 == 0 and K_ % 64 == 0
+            and all(t.dtype == torch.bfloat16 for t in tensors))
+
+
+class _Geom:
+    """Geometry of one strided-conv relation (gg_conv_desc without dtypes)."""
+    __slots__ = ("N", "D", "H", "W", "C", "Do", "Ho", "Wo", "K", "k", "s", "p")
+
+    def __init__(self, N, large_sp, C_, small_sp, K_, k, s, p):
+        self.N, (self.D, self.H, self.W), self.C = N, large_sp, C_
+        (self.Do, self.Ho, self.Wo), self.K = small_sp, K_
+        self.k, self.s, self.p = k, s, p
+
+    def desc(self, large_dt, small_dt, act=None, act_param=0.2, tc=False) -> ConvDesc:
+        return ConvDesc(self.N, self.D, self.H, self.W, self.C, self.Do, self.Ho, self.Wo, self.K,
+                        self.k[0], self.k[1], self.k[2], self.s[0], self.s[1], self.s[2],
+                        self.p[0], self.p[1], self.p[2], large_dt, small_dt, ACT[act], float(act_param),
+                        cabi.CONV_TENSOR_CORE if tc else 0)
+
+    def large_shape(self, ndim):
+        return (self.N, self.H, self.W, self.C) if ndim == 4 else (self.N, self.D, self.H, self.W, self.C)
+
+    def small_shape(self, ndim):
+        return (self.N, self.Ho, self.Wo, self.K) if ndim == 4 else (self.N, self.Do, self.Ho, self.Wo, self.K)
+
+
+def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None):
+    small = out if out is not None else torch.empty(g.small_shape(ndim), dtype=out_dtype, device=large.device)
+    tc = _tc_ok(g.C, g.K, large, small)
+    d = g.desc(dt(large), dt(small), act, act_param, tc)
+    w = wvar.packed()[1] if tc else wvar.data
+    check(cabi.lib().gg_conv_down(ctypes.byref(d), ptr(large), ptr(w), ptr(bias), ptr(small), stream()), "gg_conv_down")
+    return small
+
+
+def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None):
+    large = out if out is not None else torch.empty(g.large_shape(ndim), dtype=out_dtype, device=small.device)
+    tc = _tc_ok(g.C, g.K, large, small)
+    d = g.desc(dt(large), dt(small), act, act_param, tc)
+    w = wvar.packed()[0] if tc else wvar.data
+    check(cabi.lib().gg_conv_up(ctypes.byref(d), ptr(small), ptr(w), ptr(bias), ptr(large), stream()), "gg_conv_up")
+    return large
+
+
+def _run_wgrad(g: _Geom, large, small, wvar: Var):
+    tc = _tc_ok(g.C, g.K, large, small)
+    d = g.desc(dt(large), dt(small), None, 0.0, tc)
+    check(cabi.lib().gg_conv_wgrad(ctypes.byref(d), ptr(large), ptr(small), ptr(wvar.grad), stream()), "gg_conv_wgrad")
+
+
+def _act_bwd(y, dy, act, act_param):
+    dpre = torch.empty_like(y)
+    check(cabi.lib().gg_act_bwd(ptr(y), dt(y), ptr(dy), dt(dy), ptr(dpre), dt(dpre), y.numel(), ACT[act], float(act_param), stream()),
+          "gg_act_bwd")
+    return dpre
+
+
+def _bias_grad(dpre, bvar: Var):
+    Cc = dpre.shape[-1]
+    check(cabi.lib().gg_bias_grad(ptr(dpre), dt(dpre), ptr(bvar.grad), dpre.numel() // Cc, Cc, stream()), "gg_bias_grad")
+
+
+class _ConvRel(torch.autograd.Function):
+    """conv2d / conv3d (direction 'down') and deconv2d (direction 'up') with fused bias and
+    optional fused activation.  Backward: activation', bias gradient, filter gradient into the
+    flat gradient buffer, input gradient through the opposite-direction kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, wvar, bvar, geom, direction, act, act_param, out_dtype, out):
+        ndim = x.dim()
+        run = _run_down if direction == "down" else _run_up
+        y = run(geom, x, wvar, b, out_dtype, act, act_param, ndim, out)
+        if out is not None:
+            ctx.mark_dirty(out)
+        ctx.wvar, ctx.bvar, ctx.geom, ctx.direction, ctx.act, ctx.act_param, ctx.ndim = wvar, bvar, geom, direction, act, act_param, ndim
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(x, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        dpre = _act_bwd(y, dy, ctx.act, ctx.act_param) if ctx.act else dy
+        g = ctx.geom
+        if ctx.bvar is not None and ctx.needs_input_grad[2]:
+            _bias_grad(dpre, ctx.bvar)
+        if ctx.needs_input_grad[1]:
+            if ctx.direction == "down":
+                _run_wgrad(g, x, dpre, ctx.wvar)
+            else:
+                _run_wgrad(g, dpre, x, ctx.wvar)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            run = _run_up if ctx.direction == "down" else _run_down
+            dx = run(g, dpre, ctx.wvar, None, ctx.x_dtype, None, 0.0, ctx.ndim)
+        return dx, None, None, None, None, None, None, None, None, None, None
+
+
+def _conv_common(input_, wvar, bvar, geom, direction, act, act_param, out_dtype, out=None):
+    if _is_meta(input_):
+        shp = geom.small_shape(input_.dim()) if direction == "down" else geom.large_shape(input_.dim())
+        return torch.empty(shp, dtype=out_dtype, device="meta")
+    _require_cuda(input_, "conv")
+    x = input_.contiguous()
+    w = _wtensor(wvar, _wants_grad(wvar))
+    b = _wtensor(bvar, _wants_grad(bvar)) if bvar is not None else None
+    if out is not None:
+        want = geom.small_shape(x.dim()) if direction == "down" else geom.large_shape(x.dim())
+        if tuple(out.shape) != tuple(want) or out.dtype != out_dtype or not out.is_contiguous():
+            raise ValueError(f"out= must be a contiguous {out_dtype} tensor of shape {want}")
+    return _ConvRel.apply(x, w, b, wvar, bvar, geom, direction, act, act_param, out_dtype, out)
+
+
+def _out_dtype(act, out_dtype):
+    if out_dtype is not None:
+        return out_dtype
+    return act_dtype()
+
+
+# --------------------------------------------------------------------------------------
+# the reference operator API (ops.py)
+# --------------------------------------------------------------------------------------
+def conv2d(input_, output_dim, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name="conv2d", *, act=None, act_param=0.2,
+           out_dtype=None, bias=True):
+    """ops.py:51-62 -- tf.nn.conv2d(input_, w, [1,d_h,d_w,1], 'SAME') + bias_add.
+    Variables `name/w` [k_h,k_w,Cin,Cout] (truncated normal) and `name/biases` (zeros)."""
+    B, H, W, Cin = input_.shape
+    with variable_scope(name) as st:
+        wvar = st.get_variable("w", [k_h, k_w, Cin, output_dim], truncated_normal_initializer(stddev), filter_taps=k_h * k_w)
+        bvar = st.get_variable("biases", [output_dim], constant_initializer(0.0)) if bias else None
+    Ho, ph, _ = same_pad(H, k_h, d_h)
+    Wo, pw, _ = same_pad(W, k_w, d_w)
+    geom = _Geom(B, (1, H, W), Cin, (1, Ho, Wo), output_dim, (1, k_h, k_w), (1, d_h, d_w), (0, ph, pw))
+    return _conv_common(input_, wvar, bvar, geom, "down", act, act_param, _out_dtype(act, out_dtype))
+
+
+def conv3d(input_, output_dim, k_d=3, k_h=3, k_w=3, d_d=2, d_h=2, d_w=2, stddev=0.02, name="conv3d", *, act=None,
+           act_param=0.2, out_dtype=None):
+    """ops.py:64-75 -- tf.nn.conv3d(input_, w, [1,d_d,d_h,d_w,1], 'SAME') + bias_add."""
+    B, D, H, W, Cin = input_.shape
+    with variable_scope(name) as st:
+        wvar = st.get_variable("w", [k_d, k_h, k_w, Cin, output_dim], truncated_normal_initializer(stddev), filter_taps=k_d * k_h * k_w)
+        bvar = st.get_variable("biases", [output_dim], constant_initializer(0.0))
+    Do, pd, _ = same_pad(D, k_d, d_d)
+    Ho, ph, _ = same_pad(H, k_h, d_h)
+    Wo, pw, _ = same_pad(W, k_w, d_w)
+    geom = _Geom(B, (D, H, W), Cin, (Do, Ho, Wo), output_dim, (k_d, k_h, k_w), (d_d, d_h, d_w), (pd, ph, pw))
+    return _conv_common(input_, wvar, bvar, geom, "down", act, act_param, _out_dtype(act, out_dtype))
+
+
+def deconv2d(input_, output_shape, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name="deconv2d", with_w=False, *, act=None,
+             act_param=0.2, out_dtype=None, bias=True, out=None):
+    """ops.py:77-100 -- tf.nn.conv2d_transpose(input_, w[k_h,k_w,Cout,Cin], output_shape, [1,d_h,d_w,1]) + bias_add.
+    Variables `name/w` (normal) and `name/biases` (zeros).  with_w=True also returns the Var objects."""
+    B, h, w_, Cin = input_.shape
+    _, Ho, Wo, Cout = [int(s) for s in output_shape]
+    with variable_scope(name) as st:
+        wvar = st.get_variable("w", [k_h, k_w, Cout, Cin], random_normal_initializer(stddev), filter_taps=k_h * k_w)
+        bvar = st.get_variable("biases", [Cout], constant_initializer(0.0)) if bias else None
+    oh, ph, _ = same_pad(Ho, k_h, d_h)
+    ow, pw, _ = same_pad(Wo, k_w, d_w)
+    if (oh, ow) != (h, w_):
+        raise ValueError(f"deconv2d: output_shape {output_shape} inconsistent with input {tuple(input_.shape)}")
+    geom = _Geom(B, (1, Ho, Wo), Cout, (1, h, w_), Cin, (1, k_h, k_w), (1, d_h, d_w), (0, ph, pw))
+    y = _conv_common(input_, wvar, bvar, geom, "up", act, act_param, _out_dtype(act, out_dtype), out)
+    return (y, wvar, bvar) if with_w else y
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, wvar, bvar, act, act_param, out_dtype):
+        rows, in_dim = x.shape
+        out_dim = w.shape[1]
+        y = torch.empty((rows, out_dim), dtype=out_dtype, device=x.device)
+        check(cabi.lib().gg_linear_fwd(ptr(x), dt(x), ptr(w), ptr(b), ptr(y), dt(y), rows, in_dim, out_dim, ACT[act], float(act_param),
+                                       stream()), "gg_linear_fwd")
+        ctx.wvar, ctx.bvar, ctx.act, ctx.act_param = wvar, bvar, act, act_param
+        ctx.save_for_backward(x, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        dpre = _act_bwd(y, dy, ctx.act, ctx.act_param) if ctx.act else dy
+        rows, in_dim = x.shape
+        out_dim = dpre.shape[1]
+        L = cabi.lib()
+        wg, bg = ctx.needs_input_grad[1], ctx.bvar is not None and ctx.needs_input_grad[2]
+        if wg or bg:
+            check(L.gg_linear_wgrad(ptr(x), dt(x), ptr(dpre), dt(dpre), ptr(ctx.wvar.grad) if wg else None,
+                                    ptr(ctx.bvar.grad) if bg else None, rows, in_dim, out_dim, stream()), "gg_linear_wgrad")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            check(L.gg_linear_dgrad(ptr(dpre), dt(dpre), ptr(ctx.wvar.data), ptr(dx), dt(dx), rows, in_dim, out_dim, stream()),
+                  "gg_linear_dgrad")
+        return dx, None, None, None, None, None, None, None
+
+
+def linear(input_, output_size, scope=None, stddev=0.02, bias_start=0.0, with_w=False, *, act=None, act_param=0.2, out_dtype=None):
+    """ops.py:106-117 -- tf.matmul(input_, Matrix) + bias; variables `scope/Matrix`, `scope/bias`."""
+    rows, in_dim = input_.shape
+    with variable_scope(scope or "Linear") as st:
+        mvar = st.get_variable("Matrix", [in_dim, output_size], random_normal_initializer(stddev))
+        bvar = st.get_variable("bias", [output_size], constant_initializer(bias_start))
+    od = out_dtype if out_dtype is not None else (torch.float32 if output_size <= 4 else act_dtype())
+    if _is_meta(input_):
+        y = torch.empty((rows, output_size), dtype=od, device="meta")
+    else:
+        _require_cuda(input_, "linear")
+        y = _Linear.apply(input_.contiguous(), _wtensor(mvar, _wants_grad(mvar)), _wtensor(bvar, _wants_grad(bvar)), mvar, bvar, act,
+                          act_param, od)
+    return (y, mvar, bvar) if with_w else y
+
+
+# ---- batch norm ----------------------------------------------------------------------
+class _BatchNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, train, act, act_param, out_dtype, groups):
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        L = cabi.lib()
+        y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        save_mean = torch.empty((groups, Cc), dtype=torch.float32, device=x.device)
+        save_rstd = torch.empty((groups, Cc), dtype=torch.float32, device=x.device)
+        mm = bn.moving_mean.data if bn.moving_mean is not None else None
+        mv = bn.moving_variance.data if bn.moving_variance is not None else None
+        if train:
+            nbytes = L.gg_bn_workspace_bytes(Cc, groups)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            check(L.gg_bn_fwd_train(ptr(x), dt(x), ptr(y), dt(y), rows, Cc, groups, ptr(gamma), ptr(beta), ptr(mm), ptr(mv),
+                                    ptr(save_mean), ptr(save_rstd), bn.epsilon, bn.momentum, ACT[act], float(act_param),
+                                    ptr(ws), nbytes, stream()), "gg_bn_fwd_train")
+        else:
+            check(L.gg_bn_infer_stats(ptr(mm), ptr(mv), bn.epsilon, Cc, ptr(save_mean), ptr(save_rstd), stream()), "gg_bn_infer_stats")
+            check(L.gg_bn_fwd_infer(ptr(x), dt(x), ptr(y), dt(y), rows, Cc, ptr(gamma), ptr(beta), ptr(mm), ptr(mv), bn.epsilon,
+                                    ACT[act], float(act_param), stream()), "gg_bn_fwd_infer")
+        ctx.bn, ctx.train, ctx.act, ctx.act_param, ctx.groups = bn, train, act, act_param, groups
+        ctx.save_for_backward(x, gamma, beta, save_mean, save_rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, save_mean, save_rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        bn = ctx.bn
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        L = cabi.lib()
+        gg_, bg_ = gamma is not None and ctx.needs_input_grad[1], beta is not None and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x)
+        nbytes = L.gg_bn_workspace_bytes(Cc, ctx.groups)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        check(L.gg_bn_bwd(ptr(x), dt(x), ptr(dy), dt(dy), ptr(dx), dt(dx), rows, Cc, ctx.groups, ptr(gamma), ptr(beta),
+                          ptr(save_mean), ptr(save_rstd), ptr(bn.gamma.grad) if gg_ else None, ptr(bn.beta.grad) if bg_ else None,
+                          ACT[ctx.act], float(ctx.act_param), 1 if ctx.train else 0, ptr(ws), nbytes, stream()), "gg_bn_bwd")
+        return dx, None, None, None, None, None, None, None, None
+
+
+class batch_norm(object):
+    """ops.py:10-24 -- tf.contrib.layers.batch_norm(decay=momentum, updates_collections=None,
+    epsilon, scale=True, is_training=train): variables `name/{beta,gamma,moving_mean,moving_variance}`.
+    Train mode updates the EMAs on every call (App. A.4)."""
+
+    def __init__(self, epsilon=1e-5, momentum=0.9, name="batch_norm", affine=True, ema=True):
+        self.epsilon, self.momentum, self.name = epsilon, momentum, name
+        self.affine, self.ema = affine, ema
+        self.beta = self.gamma = self.moving_mean = self.moving_variance = None
+
+    def _vars(self, Cc):
+        if self.affine and self.beta is None:
+            with variable_scope(self.name) as st:
+                self.beta = st.get_variable("beta", [Cc], constant_initializer(0.0))
+                self.gamma = st.get_variable("gamma", [Cc], constant_initializer(1.0))
+        if self.ema and self.moving_mean is None:
+            with variable_scope(self.name) as st:
+                self.moving_mean = st.get_variable("moving_mean", [Cc], constant_initializer(0.0), trainable=False)
+                self.moving_variance = st.get_variable("moving_variance", [Cc], constant_initializer(1.0), trainable=False)
+
+    def __call__(self, x, train=True, *, act=None, act_param=0.2, out_dtype=None, groups=1):
+        self._vars(x.shape[-1])
+        od = _out_dtype(act, out_dtype)
+        if _is_meta(x):
+            return torch.empty(x.shape, dtype=od, device="meta")
+        _require_cuda(x, "batch_norm")
+        if not train and not self.ema:
+            raise ValueError("inference-mode batch_norm needs moving statistics")
+        g = _wtensor(self.gamma, _wants_grad(self.gamma)) if self.affine else None
+        b = _wtensor(self.beta, _wants_grad(self.beta)) if self.affine else None
+        return _BatchNorm.apply(x.contiguous(), g, b, self, bool(train), act, act_param, od, groups)
+
+
+# ---- standalone activations ------------------------------------------------------------
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act, act_param, out_dtype):
+        y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        check(cabi.lib().gg_act_fwd(ptr(x), dt(x), ptr(y), dt(y), x.numel(), ACT[act], float(act_param), stream()), "gg_act_fwd")
+        ctx.act, ctx.act_param, ctx.x_dtype = act, act_param, x.dtype
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty(y.shape, dtype=ctx.x_dtype, device=y.device)
+        check(cabi.lib().gg_act_bwd(ptr(y), dt(y), ptr(dy), dt(dy), ptr(dx), dt(dx), y.numel(), ACT[ctx.act], float(ctx.act_param),
+                                    stream()), "gg_act_bwd")
+        return dx, None, None, None
+
+
+def _activation(x, act, act_param=0.0, out_dtype=None):
+    od = out_dtype if out_dtype is not None else x.dtype
+    if _is_meta(x):
+        return torch.empty(x.shape, dtype=od, device="meta")
+    _require_cuda(x, act)
+    return _Act.apply(x.contiguous(), act, act_param, od)
+
+
+def lrelu(x, leak=0.2, name="lrelu"):
+    """ops.py:103-104 -- tf.maximum(x, leak*x) (gradient 1 at x == 0)."""
+    return _activation(x, "lrelu", leak)
+
+
+def relu(x):
+    return _activation(x, "relu")
+
+
+def tanh(x, out_dtype=None):
+    return _activation(x, "tanh", 0.0, out_dtype)
+
+
+def sigmoid(x, out_dtype=None):
+    return _activation(x, "sigmoid", 0.0, out_dtype)
+
+
+# ---- misc reference ops --------------------------------------------------------------------
+def add_noise(inpt, stddev):
+    """ops.py:119-123.  Identity at stddev 0 (the default everywhere, z_model.py:50-51).  For
+    stddev > 0 Gaussian noise is added with torch's generator (TF's RNG stream cannot be reproduced)."""
+    if stddev == 0.0:
+        return inpt
+    if _is_meta(inpt):
+        return inpt
+    return inpt + torch.randn(inpt.shape, device=inpt.device, dtype=torch.float32).to(inpt.dtype) * stddev
+
+
+def get_std(inpt):
+    """ops.py:125-128 -- sqrt(mean(var over axis 0)); diagnostic, no gradient."""
+    if _is_meta(inpt):
+        return torch.empty((), dtype=torch.float32, device="meta")
+    _require_cuda(inpt, "get_std")
+    x = inpt.detach().contiguous()
+    B = x.shape[0]
+    F_ = x.numel() // B
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * F_ * 8, dtype=torch.uint8, device=x.device)
+    check(cabi.lib().gg_get_std(ptr(x), dt(x), B, F_, ptr(out), ptr(ws), ws.numel(), stream()), "gg_get_std")
+    return out[0]
+
+
+def conv_cond_concat(x, y):
+    """ops.py:45-49 -- concat y broadcast over H, W on the channel axis (MNIST branch; tensor plumbing)."""
+    B, H, W, _ = x.shape
+    return torch.cat([x, y.to(x.dtype).expand(B, H, W, y.shape[3])], dim=3)
+
+
+class _SigmoidCESum(torch.autograd.Function):
+    """sum over row segments of  weight * reduce_mean(sigmoid_cross_entropy_with_logits(logits[a:b], target))
+    with the backward fused into the forward launch (model.py:121-131).  Must be the root of backward()
+    (the upstream gradient is taken to be 1)."""
+
+    @staticmethod
+    def forward(ctx, logits, segments):
+        L = cabi.lib()
+        logits = logits.contiguous()
+        parts = torch.empty(len(segments) + 1, dtype=torch.float32, device=logits.device)   # [total, part_0, ...]
+        need = ctx.needs_input_grad[0]
+        dl = torch.empty_like(logits) if need else None
+        flat = logits.reshape(-1)
+        dflat = dl.reshape(-1) if need else None
+        for i, (a, b, tg, wt) in enumerate(segments):
+            check(L.gg_sigmoid_ce(ptr(flat[a:b]), b - a, float(tg), float(wt), ptr(parts[i + 1:i + 2]), 0,
+                                  ptr(dflat[a:b]) if need else None, stream()), "gg_sigmoid_ce")
+            check(L.gg_axpby(ptr(parts[i + 1:i + 2]), 1.0, ptr(parts[0:1]), 0.0 if i == 0 else 1.0, 1, stream()), "gg_axpby")
+        ctx.dl = dl
+        return parts
+
+    @staticmethod
+    def backward(ctx, g_parts):
+        return ctx.dl, None
+
+
+def sigmoid_cross_entropy_loss(logits, segments=None, target=None):
+    """Returns a float32 vector [total, part_0, part_1, ...]; total = sum_i w_i * mean(CE(logits[a_i:b_i], t_i)).
+    `segments` = [(begin, end, target, weight), ...] over the rows of `logits`; or pass a single `target`."""
+    n = logits.shape[0]
+    if segments is None:
+        segments = [(0, n, target, 1.0)]
+    if _is_meta(logits):
+        return torch.empty(len(segments) + 1, dtype=torch.float32, device="meta")
+    if logits.dtype != torch.float32:
+        raise TypeError("logits must be float32")
+    return _SigmoidCESum.apply(logits, segments)
+
+
+def binary_cross_entropy(preds, targets, name=None):
+    """ops.py:27-43 (unused by the reference's models; kept for API completeness, torch plumbing)."""
+    eps = 1e-12
+    return torch.mean(-(targets * torch.log(preds + eps) + (1. - targets) * torch.log(1. - preds + eps)))
+
+
+# ---- optimiser -----------------------------------------------------------------------------
+class AdamOptimizer:
+    """tf.train.AdamOptimizer(learning_rate, beta1).minimize(loss, var_list) (model.py:153-156),
+    TF semantics: one fused launch over the group's flat range."""
+
+    def __init__(self, store: VariableStore, group: str, learning_rate=2e-4, beta1=0.5, beta2=0.999, epsilon=1e-8):
+        self.store, self.group = store, group
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta1, beta2, epsilon
+        self.t = 0
+        self.var_list = None
+        self.state = torch.zeros(2, dtype=torch.int32, device=store.device)   # [t, lr_t bits] (device-side, graph-safe)
+
+    def range(self):
+        return self.store.ranges[self.group]
+
+    def zero_grad(self):
+        b, e = self.range()
+        self.store.flat["grads"][b:e].zero_()
+
+    def lr_t(self, t):
+        return self.lr * float(np.sqrt(1.0 - self.b2 ** t)) / (1.0 - self.b1 ** t)
+
+    def apply(self, grad_scale=1.0):
+        """One fused Adam launch over the group.  The step counter t lives on the device
+        (self.state) so the call can be captured in a CUDA graph and replayed."""
+        self.t += 1
+        b, e = self.range()
+        f = self.store.flat
+        check(cabi.lib().gg_adam_graph(ptr(f["params"][b:e]), ptr(f["grads"][b:e]), ptr(f["m"][b:e]), ptr(f["v"][b:e]), e - b,
+                                       ptr(self.state), self.lr, self.b1, self.b2, self.eps, grad_scale, stream()), "gg_adam_graph")
+        for v in self.var_list or []:
+            v.version += 1

@@ -1,0 +1,205 @@
+/* gifgan.h -- C ABI of libgifgan.so: the B200 (sm_100a) kernels behind gif-gan's
+ * conv-GAN training step.
+ *
+ * The reference has no FFI: its operator boundary is the Python module
+ * /root/reference/models/recurrent_z/ops.py (plus the tf.nn.* calls made directly by
+ * models/recurrent_image/rnn_test/recurrent_DCGAN.py), each of which bottoms out in a
+ * TensorFlow-0.12 op.  Every entry point below replaces one of those TF op call sites
+ * (forward, and the two gradients TF's autodiff derives for it); the citation after
+ * each prototype is the reference line it stands in for.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers owned by the caller
+ *     (including workspaces); the library never allocates or frees device memory
+ *     in a compute call, never synchronises, and enqueues all work on `stream`
+ *     (a cudaStream_t passed as void*), so calls are CUDA-graph-capturable;
+ *   - return 0 on success, a negative gg_status otherwise; gg_last_error() gives the
+ *     thread-local message.  Unsupported shapes/dtypes are ERRORS, never fallbacks;
+ *   - activations are NHWC / NDHWC, channel-contiguous; filters are
+ *     [taps..., C_large, C_small] (see gg_conv_desc), linear Matrix is [in, out];
+ *   - re-entrant: may be called from PyTorch's autograd thread.
+ */
+#ifndef GIFGAN_H_
+#define GIFGAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_VERSION 100
+
+typedef enum gg_status {
+  GG_OK = 0,
+  GG_ERR_INVALID = -1,      /* bad argument / inconsistent descriptor            */
+  GG_ERR_UNSUPPORTED = -2,  /* shape or dtype the sm_100a kernels do not cover   */
+  GG_ERR_CUDA = -3,         /* a CUDA runtime / driver call failed               */
+  GG_ERR_WORKSPACE = -4     /* caller-provided workspace too small               */
+} gg_status;
+
+typedef enum gg_dtype { GG_F32 = 0, GG_BF16 = 1 } gg_dtype;
+
+typedef enum gg_act {
+  GG_ACT_NONE = 0,
+  GG_ACT_RELU = 1,    /* tf.nn.relu                          model.py:307            */
+  GG_ACT_LRELU = 2,   /* ops.lrelu = tf.maximum(x, a*x)      ops.py:103-104 (d/dx=1 at 0) */
+  GG_ACT_TANH = 3,    /* tf.nn.tanh                          model.py:324            */
+  GG_ACT_SIGMOID = 4, /* tf.nn.sigmoid                       model.py:344            */
+  GG_ACT_TANH01 = 5   /* (tanh(x)+1)/2                       recurrent_DCGAN.py:225  */
+} gg_act;
+
+/* One strided-convolution relation between a LARGE grid [N,D,H,W,C] and a SMALL grid
+ * [N,Do,Ho,Wo,K]:   i = s*o + t - pad_lo   per spatial dim, filter w[kd,kh,kw,C,K].
+ *   conv2d / conv3d  : large = input  (C=Cin),  small = output (K=Cout), w is HWIO / DHWIO
+ *   deconv2d         : large = output (C=Cout), small = input  (K=Cin),  w is [kh,kw,Cout,Cin]
+ * i.e. the filter layout of ops.py is [taps, C_large, C_small] in both cases.
+ * 2-D problems set D=Do=kd=sd=1, pd=0.  pad_lo follows TF 'SAME' (total//2).          */
+typedef struct gg_conv_desc {
+  int32_t N;
+  int32_t D, H, W, C;     /* large grid and its channels */
+  int32_t Do, Ho, Wo, K;  /* small grid and its channels */
+  int32_t kd, kh, kw;
+  int32_t sd, sh, sw;
+  int32_t pd, ph, pw;     /* pad_lo */
+  int32_t large_dtype;    /* gg_dtype of the large-side activation tensor */
+  int32_t small_dtype;    /* gg_dtype of the small-side activation tensor */
+  int32_t act;            /* gg_act fused into the epilogue of the op that WRITES an activation */
+  float act_param;        /* lrelu leak */
+  int32_t flags;          /* GG_CONV_* */
+} gg_conv_desc;
+
+#define GG_CONV_ACCUMULATE 1 /* wgrad: dw += (default for wgrad; dw must be initialised) */
+#define GG_CONV_TENSOR_CORE 2 /* use the tcgen05 bf16 path: both dtypes BF16, packed bf16 weights */
+
+int gg_version(void);
+const char* gg_last_error(void);
+/* Number of SMs / compute capability of the current device: (major*10+minor) or <0.   */
+int gg_device_arch(void);
+
+/* ---- the three contractions of a strided-conv relation -------------------------------
+ * SIMT fp32-accumulate path: w, bias, dw are fp32.  Tensor-core path
+ * (GG_CONV_TENSOR_CORE): w_packed are the bf16 copies written by gg_pack_filter.        */
+
+/* small[o,k] = act( sum_{t,c} large[s*o+t-p, c] * w[t,c,k] + bias[k] )
+ * replaces tf.nn.conv2d + bias_add (ops.py:57-60), tf.nn.conv3d (ops.py:70-73), and the
+ * input-gradient of tf.nn.conv2d_transpose (ops.py:86).                                 */
+int gg_conv_down(const gg_conv_desc* d, const void* large, const void* w, const float* bias,
+                 void* small, void* stream);
+
+/* large[i,c] = act( sum_{t,o: s*o+t-p=i} sum_k small[o,k] * w[t,c,k] + bias[c] )
+ * replaces tf.nn.conv2d_transpose + bias_add (ops.py:86-95) and the input-gradient of
+ * tf.nn.conv2d / tf.nn.conv3d.                                                          */
+int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const float* bias,
+               void* large, void* stream);
+
+/* dw[t,c,k] += sum_o large[s*o+t-p, c] * small[o,k]      (fp32, accumulating)
+ * replaces the filter-gradient of tf.nn.conv2d / conv3d / conv2d_transpose.             */
+int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw,
+                  void* stream);
+
+/* Reference-named aliases (same arguments, fixed direction). */
+int gg_conv2d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* stream);     /* ops.py:57  */
+int gg_conv2d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* stream);                   /* grad of ops.py:57 wrt input_ */
+int gg_conv2d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);                  /* grad of ops.py:57 wrt w */
+int gg_deconv2d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* stream);   /* ops.py:86  */
+int gg_deconv2d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* stream);                 /* grad of ops.py:86 wrt input_ */
+int gg_deconv2d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);                /* grad of ops.py:86 wrt w */
+int gg_conv3d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* stream);     /* ops.py:70  */
+int gg_conv3d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* stream);
+int gg_conv3d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
+
+/* fp32 filter [taps,C,K] -> bf16 copies for the tensor-core path:
+ *   w_ck [taps,C,K] (K contiguous: B operand of conv_up) and w_kc [taps,K,C] (B operand of conv_down). */
+int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t C, int32_t K, void* stream);
+
+/* ---- linear (ops.py:106-117: tf.matmul(input_, Matrix) + bias) ---------------------- */
+int gg_linear_fwd(const void* x, int32_t x_dtype, const float* matrix, const float* bias, void* y, int32_t y_dtype,
+                  int32_t rows, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, void* stream);
+int gg_linear_dgrad(const void* dy, int32_t dy_dtype, const float* matrix, void* dx, int32_t dx_dtype,
+                    int32_t rows, int32_t in_dim, int32_t out_dim, void* stream);
+/* dmatrix += x^T dy ; dbias += colsum(dy) (either may be NULL) */
+int gg_linear_wgrad(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, float* dmatrix, float* dbias,
+                    int32_t rows, int32_t in_dim, int32_t out_dim, void* stream);
+
+/* ---- batch norm (ops.py:10-24: tf.contrib.layers.batch_norm; recurrent_DCGAN.py:190-191) ----
+ * x is [rows, C] (all leading axes flattened).  groups>1 normalises `groups` equal row
+ * blocks independently (the reference's separate D(real)/D(fake) calls batched into one
+ * launch); EMA updates are then applied group after group, as sequential calls would.
+ * gamma/beta may be NULL (affine-free rnn_test variant); moving_* may be NULL (no EMA).
+ * save_mean/save_rstd: [groups, C] fp32, consumed by gg_bn_bwd.
+ * ws: >= gg_bn_workspace_bytes(C, groups) bytes, caller-owned.                          */
+size_t gg_bn_workspace_bytes(int32_t C, int32_t groups);
+int gg_bn_fwd_train(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t rows, int32_t C, int32_t groups,
+                    const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                    float* save_mean, float* save_rstd, float eps, float decay, int32_t act, float act_param,
+                    void* ws, size_t ws_bytes, void* stream);
+int gg_bn_fwd_infer(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t rows, int32_t C,
+                    const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                    float eps, int32_t act, float act_param, void* stream);
+/* dx = d(loss)/dx given dy = d(loss)/d(act(bn(x))).  train=1: batch statistics
+ * (gradient flows through mean/var); train=0: inference statistics in save_mean/save_rstd
+ * as written by gg_bn_infer_stats.  dgamma/dbeta (+=, may be NULL).                      */
+int gg_bn_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, void* dx, int32_t dx_dtype,
+              int64_t rows, int32_t C, int32_t groups, const float* gamma, const float* beta,
+              const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta,
+              int32_t act, float act_param, int32_t train, void* ws, size_t ws_bytes, void* stream);
+int gg_bn_infer_stats(const float* moving_mean, const float* moving_var, float eps, int32_t C,
+                      float* save_mean, float* save_rstd, void* stream);
+
+/* ---- pointwise / reductions -------------------------------------------------------- */
+/* dx = dy * act'(.) evaluated from the activation OUTPUT y (lrelu, relu, tanh, sigmoid, tanh01) */
+int gg_act_bwd(const void* y, int32_t y_dtype, const void* dy, int32_t dy_dtype, void* dx, int32_t dx_dtype,
+               int64_t n, int32_t act, float act_param, void* stream);
+int gg_act_fwd(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, int32_t act, float act_param, void* stream);
+/* db[c] += sum_rows dy[r,c]   (gradient of tf.nn.bias_add, ops.py:60,95) */
+int gg_bias_grad(const void* dy, int32_t dy_dtype, float* db, int64_t rows, int32_t C, void* stream);
+int gg_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+/* y = a*x + b*y  (fp32; gradient accumulation where a tensor feeds two consumers) */
+int gg_axpby(const float* x, float a, float* y, float b, int64_t n, void* stream);
+/* ops.get_std (ops.py:125-128): sqrt(mean_f(var_batch(x[B,F]))) -> out[0]; ws >= 2*F*8 bytes */
+int gg_get_std(const void* x, int32_t x_dtype, int64_t B, int64_t F, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- loss (model.py:121-126: reduce_mean(sigmoid_cross_entropy_with_logits)) --------
+ * loss_out[0] (+)= weight * mean_i CE(logits_i, target);  dlogits_i = weight*(sigmoid(x_i)-target)/n
+ * (dlogits may be NULL for forward-only).  accumulate!=0 adds into loss_out.             */
+int gg_sigmoid_ce(const float* logits, int64_t n, float target, float weight, float* loss_out, int32_t accumulate,
+                  float* dlogits, void* stream);
+/* z_model_lib.py:109-111: loss (+)= scalar*mean((a-b)^2); da = scalar*2(a-b)/n  (a strided rows) */
+int gg_mse(const float* a, int64_t a_row_stride, const float* b, int64_t b_row_stride, int64_t rows, int64_t cols,
+           float scalar, float* loss_out, int32_t accumulate, float* da, void* stream);
+
+/* ---- optimiser (model.py:153-156: tf.train.AdamOptimizer(lr, beta1).minimize) -------
+ * TF semantics: p -= lr_t * m / (sqrt(v) + eps) with lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
+ * computed by the caller.  One launch over a flat fp32 parameter group.
+ * grad_scale multiplies g first (1/world_size after a sum all-reduce).                  */
+int gg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
+            float grad_scale, void* stream);
+
+/* CUDA-graph-friendly variant: the step counter lives on the device.  state[0] = t (int32, advanced
+ * by this call), state[1] = lr_t (float bits) = lr*sqrt(1-b2^t)/(1-b1^t) recomputed on the device.    */
+int gg_adam_graph(float* p, const float* g, float* m, float* v, int64_t n, int32_t* state, float lr, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream);
+
+/* ---- BasicLSTMCell (recurrent_DCGAN.py:199-200) --------------------------------------
+ * gates_x = x_t @ Matrix[:in] + Bias is batched over T by the caller with gg_linear_fwd;
+ * one fused launch per step does  gates = gates_x + h @ Wh;  i,j,f,o;  c',h'.
+ * gates_out (post-sum pre-activation) is saved for backward.                             */
+int gg_lstm_step_fwd(const float* gates_x, const float* Wh, const float* c_prev, const float* h_prev,
+                     float* c_out, float* h_out, float* gates_out, int32_t B, int32_t H, float forget_bias, void* stream);
+/* given dh (total gradient wrt h_t) and dc (wrt c_t from t+1): dgates[B,4H], dc_prev (overwritten),
+ * dh_prev = dgates @ Wh^T (overwritten).                                                 */
+int gg_lstm_step_bwd(const float* gates, const float* c_prev, const float* c_out, const float* dh, const float* dc,
+                     const float* Wh, float* dgates, float* dc_prev, float* dh_prev,
+                     int32_t B, int32_t H, float forget_bias, void* stream);
+
+/* ---- introspection for tests/bench -------------------------------------------------- */
+/* number of kernels this library has launched on any stream since load (monotonic) */
+uint64_t gg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIFGAN_H_ */
