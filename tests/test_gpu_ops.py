@@ -307,11 +307,12 @@ def test_lstm_step_vs_oracle():
     Wh = dev(M[I:])
     c_out, h_out, gates = torch.empty(B, H, device="cuda"), torch.empty(B, H, device="cuda"), torch.empty(B, 4 * H, device="cuda")
     L = cabi.lib()
-    cabi.check(L.gg_lstm_step_fwd(gates_x.data_ptr(), Wh.data_ptr(), dev(c).data_ptr(), dev(h).data_ptr(), c_out.data_ptr(),
+    cd, hd = dev(c), dev(h)      # keep alive: a freed temporary's block would be reused by the next allocation
+    cabi.check(L.gg_lstm_step_fwd(gates_x.data_ptr(), Wh.data_ptr(), cd.data_ptr(), hd.data_ptr(), c_out.data_ptr(),
                                   h_out.data_ptr(), gates.data_ptr(), B, H, 1.0, cabi.stream()))
     assert relerr(c_out, nc) < 1e-5 and relerr(h_out, nh) < 1e-5
     dg, dcp, dhp = torch.empty(B, 4 * H, device="cuda"), torch.empty(B, H, device="cuda"), torch.empty(B, H, device="cuda")
-    cd, dhd, dcd = dev(c), dev(dh), dev(dc)
+    dhd, dcd = dev(dh), dev(dc)
     cabi.check(L.gg_lstm_step_bwd(gates.data_ptr(), cd.data_ptr(), c_out.data_ptr(), dhd.data_ptr(), dcd.data_ptr(), Wh.data_ptr(),
                                   dg.data_ptr(), dcp.data_ptr(), dhp.data_ptr(), B, H, 1.0, cabi.stream()))
     assert relerr(dcp, gc) < 1e-5 and relerr(dhp, gh) < 1e-5
