@@ -1,8 +1,609 @@
-// placeholder until the tcgen05 kernels land (next commit): the tensor-core path reports
-// "unsupported" loudly instead of silently falling back.
-#include "common.cuh"
+// tcgen05 / TMEM / TMA implicit-GEMM kernels (bf16 operands, fp32 accumulation in tensor memory)
+// for the strided-conv relation of include/gifgan.h -- the dense contractions of gif-gan's hot
+// path: tf.nn.conv2d / conv2d_transpose / conv3d forward, dgrad and wgrad
+// (/root/reference/models/recurrent_z/ops.py:57,70,86 and their tf.gradients).
+//
+// Kernel 1  tc_pixgemm  (conv_down, conv_up):   D[pixel, n] = sum_tap sum_kc A_tap[pixel, kc] * W_tap[n, kc]
+//   * A tile  = 128 pixels x 64 channels, fetched by ONE 5-D TMA box (64, bw, bh, bd, bn) from the NHWC
+//     activation tensor; a tap is just a coordinate shift of the box and out-of-image pixels are
+//     zero-filled by the TMA unit (this is the SAME padding).  Stride-2 forward convs read through one
+//     tensor map per input-parity view (base offset + doubled strides), so every tap is a dense box.
+//     conv_up (deconv fwd / conv dgrad) is decomposed by OUTPUT parity class: each class is a dense
+//     stride-1 tap-GEMM over its own 4/6/6/9 taps -- no stride-inserted zero MACs.
+//   * W tile  = BN output channels x 64 reduction channels (K-major) from the packed bf16 filter.
+//   * both land in shared memory in the 128B-swizzled K-major layout that tcgen05.mma consumes directly.
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (single thread) + TMEM owner, warps 2-5 = epilogue
+//     (tcgen05.ld 32x32b, +bias, activation, bf16/fp32 stores).  STAGES-deep mbarrier ring.
+// Kernel 2  tc_wgrad:   dW[tap, c, k] += sum_pixels large[pixel*s + tap - p, c] * small[pixel, k]
+//   * reduction runs over pixels, which is the slow axis of NHWC: both operands are MN-major for UMMA
+//     (rows of 128 B = 64 channels per pixel), so the very same TMA boxes feed it, untransposed.
+//   * the M tile (128) = two 64-channel "atoms" (tap, c-chunk); accumulators are reduced into the
+//     fp32 gradient buffer with red.global.add (split over pixel ranges across CTAs).
+#include <algorithm>
+#include <mutex>
+#include <string.h>
+
+#include "tc_common.cuh"
+
 namespace gg {
-int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t) { set_error("tcgen05 conv_down not built"); return GG_ERR_UNSUPPORTED; }
-int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t) { set_error("tcgen05 conv_up not built"); return GG_ERR_UNSUPPORTED; }
-int tc_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStream_t) { set_error("tcgen05 conv_wgrad not built"); return GG_ERR_UNSUPPORTED; }
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor-map encoding
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
 }
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  GG_REQUIRE(enc != nullptr, GG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GG_REQUIRE(r == CUDA_SUCCESS, GG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+             (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0), (unsigned long long)(rank > 2 ? gdim[2] : 0),
+             (unsigned long long)(rank > 3 ? gdim[3] : 0), (unsigned long long)(rank > 4 ? gdim[4] : 0), bx[0], rank > 1 ? bx[1] : 0,
+             rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
+  return GG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: pixel-major tap GEMM
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_MAX_TAPS = 32;
+constexpr int TC_MAX_CLASSES = 8;
+constexpr int TC_MAX_VIEWS = 8;
+constexpr int TILE_M = 128;
+constexpr int KCHUNK = 64;                 // bf16 elements per 128-byte swizzle row
+constexpr int A_STAGE_BYTES = TILE_M * 128; // 16 KB
+constexpr int TC_THREADS = 192;
+
+struct TcTap {
+  int8_t view;              // which A tensor map
+  int8_t od, oh, ow;        // box coordinate shift
+  int16_t widx;             // tap index in the packed filter
+  int16_t pad_;
+};
+struct TcClass {
+  int Md, Mh, Mw;           // M grid (per image) of this class
+  int od0, oh0, ow0;        // output coordinate = m * os + o0
+  int tap_begin, tap_end;
+  int tile_begin;           // first linear tile index of this class
+  int tw, th, td, tn;       // number of tiles along each M axis
+};
+struct TcPixParams {
+  CUtensorMap amap[TC_MAX_VIEWS];
+  CUtensorMap bmap;
+  int nclasses, ntiles_n;   // N tiles (output-channel tiles)
+  int bw, bh, bd, bn;       // box extents: bw*bh*bd*bn == 128
+  int BN;                   // output-channel tile (UMMA N): 64 / 128 / 256
+  int R;                    // reduction channels per tap (multiple of 64)
+  int Nout;                 // output channels
+  int Mn;                   // images
+  int OD, OH, OW;           // output tensor spatial dims
+  int osd, osh, osw;
+  int act;
+  float act_param;
+  int out_bf16;
+  int stages;
+  TcClass cls[TC_MAX_CLASSES];
+  TcTap taps[TC_MAX_TAPS];
+};
+
+template <bool OUT_BF16>
+__device__ __forceinline__ void store_row32(void* out, int64_t elem_off, const float (&v)[32]) {
+  if (OUT_BF16) {
+    bf16* dst = reinterpret_cast<bf16*>(out) + elem_off;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]), p1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]), p3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      reinterpret_cast<uint4*>(dst)[q] = u;
+    }
+  } else {
+    float* dst = reinterpret_cast<float*>(out) + elem_off;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict__ bias, void* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;     // full[s], empty[s], tmem_full, tmem_slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 1);
+
+  // ---- which tile ------------------------------------------------------------------------
+  const int tile = blockIdx.x;
+  int ci = 0;
+#pragma unroll 1
+  for (int c = 1; c < p.nclasses; ++c) if (tile >= p.cls[c].tile_begin) ci = c;
+  const TcClass& C = p.cls[ci];
+  int t = tile - C.tile_begin;
+  const int nt = t % p.ntiles_n; t /= p.ntiles_n;
+  const int tw = t % C.tw; t /= C.tw;
+  const int th = t % C.th; t /= C.th;
+  const int td = t % C.td; t /= C.td;
+  const int tn = t;
+  const int mw0 = tw * p.bw, mh0 = th * p.bh, md0 = td * p.bd, mn0 = tn * p.bn;
+  const int n0 = nt * p.BN;
+  const int kchunks = p.R / KCHUNK;
+  const int iters = (C.tap_end - C.tap_begin) * kchunks;
+  const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;   // power of two >= 32
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.bmap);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        const TcTap tap = p.taps[C.tap_begin + it / kchunks];
+        const int kc = (it % kchunks) * KCHUNK;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t a_dst = smem_base + s * stage_bytes, b_dst = a_dst + A_STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
+        tma_load_5d(a_dst, &p.amap[tap.view], full_bar(s), kc, mw0 + tap.ow, mh0 + tap.oh, md0 + tap.od, mn0);
+        tma_load_3d(b_dst, &p.bmap, full_bar(s), kc, n0, tap.widx);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * stage_bytes, b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < KCHUNK / 16; ++k) {
+          const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));                       // frees this smem stage when the MMAs retire
+        if (it == iters - 1) umma_commit(tmem_full_bar);  // accumulator complete
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // accumulator row = pixel within the tile
+    const int iw = row % p.bw, ih = (row / p.bw) % p.bh, id = (row / (p.bw * p.bh)) % p.bd, in = row / (p.bw * p.bh * p.bd);
+    const int mw = mw0 + iw, mh = mh0 + ih, md = md0 + id, mn = mn0 + in;
+    const bool valid = mw < C.Mw && mh < C.Mh && md < C.Md && mn < p.Mn;
+    const int ow = mw * p.osw + C.ow0, oh = mh * p.osh + C.oh0, od = md * p.osd + C.od0;
+    const int64_t pix = (((int64_t)mn * p.OD + od) * p.OH + oh) * p.OW + ow;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float f = __uint_as_float(r[j]);
+        if (bias != nullptr) f += __ldg(bias + n0 + c0 + j);
+        v[j] = act_fwd(f, p.act, p.act_param);
+      }
+      if (valid) {
+        const int64_t off = pix * p.Nout + n0 + c0;
+        if (p.out_bf16) store_row32<true>(out, off, v);
+        else store_row32<false>(out, off, v);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: wgrad (MN-major operands, reduction over pixels)
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_PIX = 64;                      // pixels (reduction) per stage
+constexpr int WG_ATOM_BYTES = WG_PIX * 128;     // one 64-channel atom x 64 pixels = 8 KB
+
+struct WgAtom {           // one 64-row half of an M tile: (tap, channel chunk of the large tensor)
+  int8_t view, od, oh, ow;
+  int16_t widx;           // tap index in dw
+  int16_t c0;             // first channel (multiple of 64); -1 = padding atom
+};
+struct TcWgradParams {
+  CUtensorMap lmap[TC_MAX_VIEWS];   // large tensor views (same maps as conv_down's A operand, box = WG_PIX pixels)
+  CUtensorMap smap;                 // small tensor
+  int natoms, mtiles, ntiles_n, splits;
+  int BN;                           // k-channel tile (multiple of 64, <= 256)
+  int bw, bh, bd, bn;               // pixel box: product == WG_PIX
+  int tw, th, td, tn;               // pixel tiles along each axis of the small grid
+  int ptiles, ptiles_per_split;
+  int C, K;
+  int stages;
+  WgAtom atoms[2 * 208];            // up to 27 taps x 8 chunks (512 ch) = 216 -> mtiles <= 208
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = p.BN / 64;                                    // B atoms per stage
+  const int stage_bytes = (2 + nb) * WG_ATOM_BYTES;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 1);
+
+  int t = blockIdx.x;
+  const int split = t % p.splits; t /= p.splits;
+  const int nt = t % p.ntiles_n; t /= p.ntiles_n;
+  const int mt = t;
+  const WgAtom a0 = p.atoms[2 * mt], a1 = p.atoms[2 * mt + 1];
+  const int k0 = nt * p.BN;
+  const int pt_begin = split * p.ptiles_per_split;
+  const int pt_end = min(p.ptiles, pt_begin + p.ptiles_per_split);
+  const int iters = pt_end - pt_begin;
+  const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.smap);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (iters <= 0) {   // (cannot happen with the host's split computation; keep the teardown uniform)
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+    return;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const bool has1 = a1.c0 >= 0;
+      for (int it = 0; it < iters; ++it) {
+        int pt = pt_begin + it;
+        const int iw = pt % p.tw; pt /= p.tw;
+        const int ih = pt % p.th; pt /= p.th;
+        const int id = pt % p.td; pt /= p.td;
+        const int in = pt;
+        const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd, n0 = in * p.bn;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t dst = smem_base + s * stage_bytes;
+        mbar_expect_tx(full_bar(s), (uint32_t)((1 + (has1 ? 1 : 0) + nb) * WG_ATOM_BYTES));
+        tma_load_5d(dst, &p.lmap[a0.view], full_bar(s), a0.c0, w0 + a0.ow, h0 + a0.oh, d0 + a0.od, n0);
+        if (has1) tma_load_5d(dst + WG_ATOM_BYTES, &p.lmap[a1.view], full_bar(s), a1.c0, w0 + a1.ow, h0 + a1.oh, d0 + a1.od, n0);
+        for (int j = 0; j < nb; ++j)
+          tma_load_5d(dst + (2 + j) * WG_ATOM_BYTES, &p.smap, full_bar(s), k0 + j * 64, w0, h0, d0, n0);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // A: M = 128 = 2 atoms (LBO = atom stride), MN-major; B: N = BN = nb atoms, MN-major.
+      const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 1, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * stage_bytes, b_addr = a_addr + 2 * WG_ATOM_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_PIX / 16; ++k) {
+          // 16 pixels (K) per MMA = two 8-row groups: advance 2048 B per step
+          const uint64_t ad = make_smem_desc(a_addr + k * 2048, WG_ATOM_BYTES, 1024);
+          const uint64_t bd = make_smem_desc(b_addr + k * 2048, WG_ATOM_BYTES, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+        if (it == iters - 1) umma_commit(tmem_full_bar);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // 0..127: atom (row >> 6), channel (row & 63)
+    const WgAtom a = (row < 64) ? a0 : a1;
+    const bool valid = a.c0 >= 0;
+    float* dst = dw + ((int64_t)a.widx * p.C + (valid ? a.c0 : 0) + (row & 63)) * p.K + k0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(r[j])),
+                       "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                       : "memory");
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: plans
+// ------------------------------------------------------------------------------------------------
+static int pow2floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
+
+static void pick_box(int Mw, int Mh, int Md, int pixels, int* bw, int* bh, int* bd, int* bn) {
+  *bw = std::min(pow2floor(Mw), pixels);
+  *bh = std::min(pow2floor(Mh), pixels / *bw);
+  *bd = std::min(pow2floor(Md), pixels / (*bw * *bh));
+  *bn = pixels / (*bw * *bh * *bd);
+}
+
+static int check_tc(const gg_conv_desc* d, const void* a, const void* b) {
+  GG_REQUIRE(d->large_dtype == GG_BF16 && d->small_dtype == GG_BF16, GG_ERR_UNSUPPORTED, "tensor-core path needs bf16 activations");
+  GG_REQUIRE(d->C % 64 == 0 && d->K % 64 == 0, GG_ERR_UNSUPPORTED, "tensor-core path needs channel counts that are multiples of 64 (C=%d K=%d)", d->C, d->K);
+  GG_REQUIRE(d->kd * d->kh * d->kw <= TC_MAX_TAPS && d->sd * d->sh * d->sw <= TC_MAX_VIEWS, GG_ERR_UNSUPPORTED, "tensor-core path: too many taps / stride classes");
+  GG_REQUIRE(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0), GG_ERR_INVALID, "tensor-core path needs 16-byte aligned tensors");
+  return GG_OK;
+}
+
+// tensor maps of the stride-parity views of the large tensor: view index = (ad*sh + ah)*sw + aw
+static int make_large_views(const gg_conv_desc* d, const void* large, const uint32_t* box, CUtensorMap* maps) {
+  for (int ad = 0; ad < d->sd; ++ad)
+    for (int ah = 0; ah < d->sh; ++ah)
+      for (int aw = 0; aw < d->sw; ++aw) {
+        const int64_t base_elems = (((int64_t)ad * d->H + ah) * d->W + aw) * d->C;
+        const uint64_t dims[5] = {(uint64_t)d->C, (uint64_t)((d->W - aw + d->sw - 1) / d->sw), (uint64_t)((d->H - ah + d->sh - 1) / d->sh),
+                                  (uint64_t)((d->D - ad + d->sd - 1) / d->sd), (uint64_t)d->N};
+        const uint64_t str[4] = {(uint64_t)d->sw * d->C * 2, (uint64_t)d->sh * d->W * d->C * 2, (uint64_t)d->sd * d->H * d->W * d->C * 2,
+                                 (uint64_t)d->D * d->H * d->W * d->C * 2};
+        if (dims[1] == 0 || dims[2] == 0 || dims[3] == 0) {   // empty view (grid smaller than the stride): never referenced
+          memset(&maps[(ad * d->sh + ah) * d->sw + aw], 0, sizeof(CUtensorMap));
+          continue;
+        }
+        int rc = encode_tmap_bf16(&maps[(ad * d->sh + ah) * d->sw + aw], (const bf16*)large + base_elems, 5, dims, str, box);
+        if (rc) return rc;
+      }
+  return GG_OK;
+}
+
+static int make_small_map(const gg_conv_desc* d, const void* small, const uint32_t* box, CUtensorMap* map) {
+  const uint64_t dims[5] = {(uint64_t)d->K, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->Do, (uint64_t)d->N};
+  const uint64_t str[4] = {(uint64_t)d->K * 2, (uint64_t)d->Wo * d->K * 2, (uint64_t)d->Ho * d->Wo * d->K * 2,
+                           (uint64_t)d->Do * d->Ho * d->Wo * d->K * 2};
+  return encode_tmap_bf16(map, small, 5, dims, str, box);
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+static int pick_bn(int Nout, int64_t mtiles) {
+  // widest tile that still yields >= ~1 wave of CTAs
+  int bn = Nout % 256 == 0 ? 256 : (Nout % 128 == 0 ? 128 : 64);
+  while (bn > 64 && mtiles * (Nout / bn) < 120) bn /= 2;
+  return bn;
+}
+
+static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* out, cudaStream_t st) {
+  const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
+  p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2);
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(tc_pixgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  tc_pixgemm_kernel<<<total_tiles, TC_THREADS, smem, st>>>(p, bias, out);
+  return check_launch("tc_pixgemm");
+}
+
+int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, const float* bias, void* small, cudaStream_t st) {
+  int rc = check_tc(d, large, w_kc);
+  if (rc) return rc;
+  TcPixParams p;
+  memset(&p, 0, sizeof(p));
+  pick_box(d->Wo, d->Ho, d->Do, TILE_M, &p.bw, &p.bh, &p.bd, &p.bn);
+  const uint32_t abox[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+  rc = make_large_views(d, large, abox, p.amap);
+  if (rc) return rc;
+  TcClass& c = p.cls[0];
+  c.Md = d->Do; c.Mh = d->Ho; c.Mw = d->Wo;
+  c.tw = ceil_div(d->Wo, p.bw); c.th = ceil_div(d->Ho, p.bh); c.td = ceil_div(d->Do, p.bd); c.tn = ceil_div(d->N, p.bn);
+  const int64_t mtiles = (int64_t)c.tw * c.th * c.td * c.tn;
+  p.BN = pick_bn(d->K, mtiles);
+  const int taps = d->kd * d->kh * d->kw;
+  const uint64_t bdims[3] = {(uint64_t)d->C, (uint64_t)d->K, (uint64_t)taps};
+  const uint64_t bstr[2] = {(uint64_t)d->C * 2, (uint64_t)d->C * d->K * 2};
+  const uint32_t bbox[3] = {64, (uint32_t)p.BN, 1};
+  rc = encode_tmap_bf16(&p.bmap, w_kc, 3, bdims, bstr, bbox);
+  if (rc) return rc;
+  int t = 0;
+  for (int a = 0; a < d->kd; ++a)
+    for (int b = 0; b < d->kh; ++b)
+      for (int e = 0; e < d->kw; ++e, ++t) {
+        const int fd = a - d->pd, fh = b - d->ph, fw = e - d->pw;
+        TcTap tp;
+        tp.view = (int8_t)((posmod(fd, d->sd) * d->sh + posmod(fh, d->sh)) * d->sw + posmod(fw, d->sw));
+        tp.od = (int8_t)floordiv(fd, d->sd); tp.oh = (int8_t)floordiv(fh, d->sh); tp.ow = (int8_t)floordiv(fw, d->sw);
+        tp.widx = (int16_t)t; tp.pad_ = 0;
+        p.taps[t] = tp;
+      }
+  c.tap_begin = 0; c.tap_end = taps; c.tile_begin = 0;
+  p.nclasses = 1; p.ntiles_n = d->K / p.BN;
+  p.R = d->C; p.Nout = d->K; p.Mn = d->N;
+  p.OD = d->Do; p.OH = d->Ho; p.OW = d->Wo; p.osd = p.osh = p.osw = 1;
+  p.act = d->act; p.act_param = d->act_param; p.out_bf16 = 1;
+  return launch_pix(p, (int)(mtiles * p.ntiles_n), bias, small, st);
+}
+
+int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const float* bias, void* large, cudaStream_t st) {
+  int rc = check_tc(d, small, w_ck);
+  if (rc) return rc;
+  TcPixParams p;
+  memset(&p, 0, sizeof(p));
+  const int Mw = ceil_div(d->W, d->sw), Mh = ceil_div(d->H, d->sh), Md = ceil_div(d->D, d->sd);
+  pick_box(Mw, Mh, Md, TILE_M, &p.bw, &p.bh, &p.bd, &p.bn);
+  const uint32_t abox[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+  rc = make_small_map(d, small, abox, &p.amap[0]);
+  if (rc) return rc;
+  int ncls = 0, ntap = 0;
+  int64_t tiles = 0, mt_max = 0;
+  for (int ad = 0; ad < d->sd; ++ad)
+    for (int ah = 0; ah < d->sh; ++ah)
+      for (int aw = 0; aw < d->sw; ++aw) {
+        TcClass c;
+        memset(&c, 0, sizeof(c));
+        c.Md = (d->D - ad + d->sd - 1) / d->sd; c.Mh = (d->H - ah + d->sh - 1) / d->sh; c.Mw = (d->W - aw + d->sw - 1) / d->sw;
+        if (c.Md <= 0 || c.Mh <= 0 || c.Mw <= 0) continue;
+        c.od0 = ad; c.oh0 = ah; c.ow0 = aw;
+        c.tap_begin = ntap;
+        for (int a = 0; a < d->kd; ++a) {
+          if (posmod(ad + d->pd - a, d->sd) != 0) continue;
+          for (int b = 0; b < d->kh; ++b) {
+            if (posmod(ah + d->ph - b, d->sh) != 0) continue;
+            for (int e = 0; e < d->kw; ++e) {
+              if (posmod(aw + d->pw - e, d->sw) != 0) continue;
+              TcTap tp;
+              tp.view = 0;
+              tp.od = (int8_t)floordiv(ad + d->pd - a, d->sd); tp.oh = (int8_t)floordiv(ah + d->ph - b, d->sh);
+              tp.ow = (int8_t)floordiv(aw + d->pw - e, d->sw);
+              tp.widx = (int16_t)((a * d->kh + b) * d->kw + e); tp.pad_ = 0;
+              p.taps[ntap++] = tp;
+            }
+          }
+        }
+        c.tap_end = ntap;
+        c.tw = ceil_div(c.Mw, p.bw); c.th = ceil_div(c.Mh, p.bh); c.td = ceil_div(c.Md, p.bd); c.tn = ceil_div(d->N, p.bn);
+        const int64_t mt = (int64_t)c.tw * c.th * c.td * c.tn;
+        mt_max = std::max(mt_max, mt);
+        c.tile_begin = (int)tiles;   // scaled by ntiles_n below
+        tiles += mt;
+        p.cls[ncls++] = c;
+      }
+  p.BN = pick_bn(d->C, tiles);
+  p.ntiles_n = d->C / p.BN;
+  for (int i = 0; i < ncls; ++i) p.cls[i].tile_begin *= p.ntiles_n;
+  // a class without taps (stride > kernel) still has to write bias/zeros: the kernel handles iters == 0? no -> reject
+  for (int i = 0; i < ncls; ++i)
+    GG_REQUIRE(p.cls[i].tap_end > p.cls[i].tap_begin, GG_ERR_UNSUPPORTED, "tensor-core conv_up: an output parity class has no taps");
+  const int taps = d->kd * d->kh * d->kw;
+  const uint64_t bdims[3] = {(uint64_t)d->K, (uint64_t)d->C, (uint64_t)taps};
+  const uint64_t bstr[2] = {(uint64_t)d->K * 2, (uint64_t)d->C * d->K * 2};
+  const uint32_t bbox[3] = {64, (uint32_t)p.BN, 1};
+  rc = encode_tmap_bf16(&p.bmap, w_ck, 3, bdims, bstr, bbox);
+  if (rc) return rc;
+  p.nclasses = ncls;
+  p.R = d->K; p.Nout = d->C; p.Mn = d->N;
+  p.OD = d->D; p.OH = d->H; p.OW = d->W; p.osd = d->sd; p.osh = d->sh; p.osw = d->sw;
+  p.act = d->act; p.act_param = d->act_param; p.out_bf16 = 1;
+  return launch_pix(p, (int)(tiles * p.ntiles_n), bias, large, st);
+}
+
+int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw, cudaStream_t st) {
+  int rc = check_tc(d, large, small);
+  if (rc) return rc;
+  static TcWgradParams proto;   // large struct: build on the heap-free static under a lock, copy for the launch
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  TcWgradParams& p = proto;
+  memset(&p, 0, sizeof(p));
+  pick_box(d->Wo, d->Ho, d->Do, WG_PIX, &p.bw, &p.bh, &p.bd, &p.bn);
+  const uint32_t box[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+  rc = make_large_views(d, large, box, p.lmap);
+  if (rc) return rc;
+  rc = make_small_map(d, small, box, &p.smap);
+  if (rc) return rc;
+  p.tw = ceil_div(d->Wo, p.bw); p.th = ceil_div(d->Ho, p.bh); p.td = ceil_div(d->Do, p.bd); p.tn = ceil_div(d->N, p.bn);
+  p.ptiles = p.tw * p.th * p.td * p.tn;
+  const int cchunks = d->C / 64;
+  int na = 0;
+  for (int a = 0; a < d->kd; ++a)
+    for (int b = 0; b < d->kh; ++b)
+      for (int e = 0; e < d->kw; ++e)
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const int fd = a - d->pd, fh = b - d->ph, fw = e - d->pw;
+          WgAtom at;
+          at.view = (int8_t)((posmod(fd, d->sd) * d->sh + posmod(fh, d->sh)) * d->sw + posmod(fw, d->sw));
+          at.od = (int8_t)floordiv(fd, d->sd); at.oh = (int8_t)floordiv(fh, d->sh); at.ow = (int8_t)floordiv(fw, d->sw);
+          at.widx = (int16_t)((a * d->kh + b) * d->kw + e);
+          at.c0 = (int16_t)(cc * 64);
+          GG_REQUIRE(na < 2 * 208, GG_ERR_UNSUPPORTED, "tensor-core wgrad: too many (tap, channel-chunk) atoms");
+          p.atoms[na++] = at;
+        }
+  p.natoms = na;
+  if (na & 1) { WgAtom pad; memset(&pad, 0, sizeof(pad)); pad.c0 = -1; p.atoms[na] = pad; }
+  p.mtiles = (na + 1) / 2;
+  p.BN = d->K % 256 == 0 ? 256 : (d->K % 128 == 0 ? 128 : 64);
+  p.ntiles_n = d->K / p.BN;
+  const int64_t tiles = (int64_t)p.mtiles * p.ntiles_n;
+  int splits = (int)std::max<int64_t>(1, (148 * 2 + tiles - 1) / tiles);
+  splits = std::min(splits, std::max(1, p.ptiles / 4));
+  p.ptiles_per_split = ceil_div(p.ptiles, splits);
+  p.splits = ceil_div(p.ptiles, p.ptiles_per_split);
+  p.C = d->C; p.K = d->K;
+  const int stage_bytes = (2 + p.BN / 64) * WG_ATOM_BYTES;
+  p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2);
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  tc_wgrad_kernel<<<(unsigned)(tiles * p.splits), TC_THREADS, smem, st>>>(p, dw);
+  return check_launch("tc_wgrad");
+}
+
+}  // namespace gg
