@@ -12,6 +12,8 @@
 //         m over {i : i % s == a}, A = small, S = 1, off_t = (a + pad - t)/s for the taps with
 //         (a + pad - t) % s == 0, W_t[k, n] = w[t][n][k] (k contiguous).  No stride-inserted zeros.
 // wgrad:  dw[t][c][k] += sum_o large[s*o + t - p, c] * small[o, k]   (split over o, fp32 atomics)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gg {
@@ -76,11 +78,13 @@ pixgemm_kernel(const TA* __restrict__ A, const float* __restrict__ Wt, const flo
   // ---- compute role
   const int ty = tid >> 4, tx = tid & 15;
 
-  float acc[4][4];
+  // two-level accumulation: `part` collects FOLD k-chunks (128 products), then folds into `acc`, so the
+  // rounding error of a K = 25*512 reduction grows like a blocked sum, not a 12800-term running sum
+  float acc[4][4], part[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; part[i][j] = 0.f; }
 
   const int KC = (p.Ac + BK - 1) / BK;
   const int ntap = ci.tap_end - ci.tap_begin;
@@ -159,7 +163,13 @@ pixgemm_kernel(const TA* __restrict__ A, const float* __restrict__ Wt, const flo
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
+    }
+    if ((it & 7) == 7 || it == iters - 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j] += part[i][j]; part[i][j] = 0.f; }
     }
     __syncthreads();
   }
@@ -218,11 +228,11 @@ wgrad_kernel(const TL* __restrict__ large, const TS* __restrict__ small, float* 
   const int lp = tid >> 4, lq = (tid & 15) * 4;  // load role: pixel lp, channels lq..lq+3
   const int ty = tid >> 4, tx = tid & 15;
 
-  float acc[4][4];
+  float acc[4][4], part[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; part[i][j] = 0.f; }
 
   float a_reg[4], b_reg[4];
   const int64_t HoWo = (int64_t)p.Ho * p.Wo, DHW = (int64_t)p.Do * HoWo;
@@ -259,7 +269,8 @@ wgrad_kernel(const TL* __restrict__ large, const TS* __restrict__ small, float* 
   };
 
   load_tiles(mbeg);
-  for (int64_t mb = mbeg; mb < mend; mb += BK) {
+  int it = 0;
+  for (int64_t mb = mbeg; mb < mend; mb += BK, ++it) {
     *reinterpret_cast<float4*>(&As[lp][lq]) = make_float4(a_reg[0], a_reg[1], a_reg[2], a_reg[3]);
     *reinterpret_cast<float4*>(&Bs[lp][lq]) = make_float4(b_reg[0], b_reg[1], b_reg[2], b_reg[3]);
     __syncthreads();
@@ -272,7 +283,13 @@ wgrad_kernel(const TL* __restrict__ large, const TS* __restrict__ small, float* 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
+    }
+    if ((it & 7) == 7 || mb + BK >= mend) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j] += part[i][j]; part[i][j] = 0.f; }
     }
     __syncthreads();
   }
@@ -417,6 +434,7 @@ int simt_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small,
   p.Mtot = (int64_t)d->N * d->Do * d->Ho * d->Wo;
   const int64_t tiles = (int64_t)ceil_div(d->C, BM) * ceil_div(d->K, BN) * d->kd * d->kh * d->kw;
   int64_t splits = std::max<int64_t>(1, (148 * 4 + tiles - 1) / tiles);
+  splits = std::max<int64_t>(splits, ceil_div64(p.Mtot, 1024));   // <= 1024 pixels per CTA: bounded error growth, more parallelism
   splits = std::min<int64_t>(splits, std::max<int64_t>(1, p.Mtot / 128));
   splits = std::min<int64_t>(splits, 65535 / (d->kd * d->kh * d->kw));
   p.chunk = ceil_div64(ceil_div64(p.Mtot, splits), BK) * BK;

@@ -40,7 +40,7 @@ from ._cabi import ACT, ConvDesc, check, dt, ptr, stream
 # configuration
 # --------------------------------------------------------------------------------------
 _PRECISION = "fp32"
-TC_DEFAULT = False      # flipped to True once the tcgen05 kernels are validated on hardware
+TC_DEFAULT = True       # tcgen05 kernels validated on B200 (tools/tc_probe.py, tests/test_gpu_tc.py)
 _USE_TC = TC_DEFAULT
 
 

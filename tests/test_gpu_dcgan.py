@@ -70,7 +70,8 @@ def check_grads(m, names, ref_grads, tol, metric=relerr):
     for k in names:
         got, want = m.store.vars[k].grad, ref_grads[k]
         if any(k.endswith(zg) for zg in ZERO_GRAD):
-            assert got.abs().max().item() < 1e-4 + 10 * want.abs().max().item(), k
+            # exact value 0: only rounding noise (fp32: ~1e-6; bf16 activations: a sum of bf16-rounded terms)
+            assert got.abs().max().item() < (1e-4 if metric is relerr else 5e-2) + 10 * want.abs().max().item(), k
             continue
         worst[k] = metric(got, want)
     bad = {k: e for k, e in worst.items() if not e < tol}
@@ -139,7 +140,9 @@ def test_cuda_graph_replay_equals_eager():
         img, z = batch(B, size, step=step)
         got = m2.train_step(img, z, use_graph=True)
         for k in eager[step]:
-            assert abs(got[k] - eager[step][k]) < 1e-4 * max(1.0, abs(eager[step][k])), (step, k)
+            # step 0 differs only by the order of the wgrad atomics; later steps inherit Adam's amplification of it
+            tol = 2e-5 if step == 0 else 5e-3
+            assert abs(got[k] - eager[step][k]) < tol * max(1.0, abs(eager[step][k])), (step, k)
     assert m2._graph["launches"] > 50
     assert m2.d_optim.t == 4 and int(m2.d_optim.state[0].item()) == 4 and int(m2.g_optim.state[0].item()) == 8
     weights_close_after_adam(m2, {k: v.cpu() for k, v in w1.items()}, 2e-4, 8, "graph vs eager")

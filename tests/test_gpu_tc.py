@@ -1,0 +1,150 @@
+"""GPU parity tests for the tcgen05 / TMEM / TMA kernels (bf16 mode, tensor-core path) against the CPU oracle:
+every DCGAN-64 tensor-core layer shape (d_h1..3, g_h1..3), the video discriminator's conv3d shapes, ragged
+sizes that exercise the TMA zero-fill and partial tiles, and the forward/dgrad adjointness property at
+BASELINE.json's full config-2 batch.  Tolerance: 2e-2 relative (north_star, bf16)."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tf_ops as T  # noqa: E402
+
+TOL = 2e-2
+
+
+def relerr(got, want):
+    got = got.detach().float().cpu().double()
+    want = want.detach().double()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-12)).item()
+
+
+def bf16_round(a):
+    return torch.tensor(a, dtype=torch.float32).to(torch.bfloat16).float()
+
+
+def _store(builder, shape):
+    from gifgan import ops
+    ops.set_precision("bf16", tensor_cores=True)
+    st = ops.reset_default_store(device="cuda", seed=5)
+    builder(torch.empty(shape, device="meta", dtype=torch.bfloat16))
+    tv = [v for v in st.vars.values() if v.trainable]
+    st.finalize(OrderedDict(all=tv))
+    return ops, st, tv
+
+
+# (name, B, H, Cin, Cout): discriminator convs of DCGAN-64 (model.py:273-276) that run on tensor cores
+@pytest.mark.parametrize("name,B,H,Ci,Co", [("d_h1", 16, 32, 64, 128), ("d_h2", 16, 16, 128, 256), ("d_h3", 16, 8, 256, 512),
+                                           ("ragged", 3, 14, 64, 192), ("wide", 2, 40, 128, 64)])
+def test_tc_conv2d(name, B, H, Ci, Co):
+    rs = np.random.RandomState(Ci + H)
+    W = H if name != "ragged" else 10
+    x, w, b = bf16_round(rs.randn(B, H, W, Ci)), bf16_round(rs.randn(5, 5, Ci, Co) * 0.05), torch.tensor(rs.randn(Co) * 0.1, dtype=torch.float32)
+    from gifgan import ops as _o
+    ops, st, tv = _store(lambda t: _o.conv2d(t, Co, name="c"), (B, H, W, Ci))
+    st.load_state_dict({"c/w": w.numpy(), "c/biases": b.numpy()})
+    xt = x.cuda().to(torch.bfloat16).requires_grad_(True)
+    assert ops._tc_ok(Ci, Co, xt)
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    dy = bf16_round(rs.randn(B, Ho, Wo, Co))
+    with ops.trainable(tv):
+        y = ops.conv2d(xt, Co, name="c")
+        y.backward(dy.cuda().to(torch.bfloat16))
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = T.conv2d(xr, wr, br)
+    gx, gw, gb = torch.autograd.grad(yr, [xr, wr, br], dy.double())
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (B, Ho, Wo, Co)
+    assert relerr(y, yr) < TOL
+    assert relerr(xt.grad, gx) < TOL
+    assert relerr(st.vars["c/w"].grad, gw) < TOL
+    assert relerr(st.vars["c/biases"].grad, gb) < TOL
+
+
+@pytest.mark.parametrize("name,B,h,Ci,Co", [("g_h1", 16, 4, 512, 256), ("g_h2", 16, 8, 256, 128), ("g_h3", 16, 16, 128, 64),
+                                           ("ragged", 3, 7, 128, 64)])
+def test_tc_deconv2d(name, B, h, Ci, Co):
+    rs = np.random.RandomState(Ci + h)
+    w_ = h if name != "ragged" else 5
+    x, w, b = bf16_round(rs.randn(B, h, w_, Ci)), bf16_round(rs.randn(5, 5, Co, Ci) * 0.05), torch.tensor(rs.randn(Co) * 0.1, dtype=torch.float32)
+    out_shape = [B, 2 * h, 2 * w_, Co]
+    from gifgan import ops as _o
+    ops, st, tv = _store(lambda t: _o.deconv2d(t, out_shape, name="g"), (B, h, w_, Ci))
+    st.load_state_dict({"g/w": w.numpy(), "g/biases": b.numpy()})
+    xt = x.cuda().to(torch.bfloat16).requires_grad_(True)
+    dy = bf16_round(rs.randn(*out_shape))
+    with ops.trainable(tv):
+        y = ops.deconv2d(xt, out_shape, name="g")
+        y.backward(dy.cuda().to(torch.bfloat16))
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = T.conv2d_transpose(xr, wr, out_shape, br)
+    gx, gw, gb = torch.autograd.grad(yr, [xr, wr, br], dy.double())
+    assert relerr(y, yr) < TOL
+    assert relerr(xt.grad, gx) < TOL
+    assert relerr(st.vars["g/w"].grad, gw) < TOL
+    assert relerr(st.vars["g/biases"].grad, gb) < TOL
+
+
+# video discriminator (z_model_lib.py:409-413): [Bv,16,8,8,256] -> [Bv,8,4,4,256] -> [Bv,4,2,2,256] -> [Bv,2,1,1,256]
+@pytest.mark.parametrize("B,D,H", [(2, 16, 8), (4, 8, 4), (8, 4, 2), (3, 6, 5)])
+def test_tc_conv3d(B, D, H):
+    rs = np.random.RandomState(D)
+    Ci = Co = 256
+    x, w, b = bf16_round(rs.randn(B, D, H, H, Ci)), bf16_round(rs.randn(3, 3, 3, Ci, Co) * 0.03), torch.tensor(rs.randn(Co) * 0.1, dtype=torch.float32)
+    from gifgan import ops as _o
+    ops, st, tv = _store(lambda t: _o.conv3d(t, Co, name="v"), (B, D, H, H, Ci))
+    st.load_state_dict({"v/w": w.numpy(), "v/biases": b.numpy()})
+    xt = x.cuda().to(torch.bfloat16).requires_grad_(True)
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = T.conv3d(xr, wr, br)
+    dy = bf16_round(rs.randn(*yr.shape))
+    with ops.trainable(tv):
+        y = ops.conv3d(xt, Co, name="v")
+        y.backward(dy.cuda().to(torch.bfloat16))
+    gx, gw, gb = torch.autograd.grad(yr, [xr, wr, br], dy.double())
+    assert relerr(y, yr) < TOL
+    assert relerr(xt.grad, gx) < TOL
+    assert relerr(st.vars["v/w"].grad, gw) < TOL
+
+
+def test_tc_matches_simt_path_and_accumulates():
+    """Same library, two kernels: tensor-core vs SIMT on identical bf16 operands; and wgrad accumulates (+=)."""
+    from gifgan import ops as _o
+    B, H, Ci, Co = 64, 16, 128, 256
+    ops, st, tv = _store(lambda t: _o.conv2d(t, Co, name="c"), (B, H, H, Ci))
+    x = torch.randn(B, H, H, Ci, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(B, H // 2, H // 2, Co, device="cuda").to(torch.bfloat16)
+    res = {}
+    for tc in (True, False):
+        ops.set_precision("bf16", tensor_cores=tc)
+        for v in tv:
+            v.grad.zero_()
+        xt = x.clone().requires_grad_(True)
+        with ops.trainable(tv):
+            y = ops.conv2d(xt, Co, name="c")
+            y.backward(dy)
+            if tc:                      # a second use of the same filter adds its gradient
+                y2 = ops.conv2d(xt, Co, name="c")
+                y2.backward(dy)
+        res[tc] = (y.float(), xt.grad.float(), st.vars["c/w"].grad.clone())
+    assert relerr(res[True][0].cpu(), res[False][0].cpu()) < 1e-2
+    assert relerr(res[True][1].cpu(), 2 * res[False][1].cpu()) < 1e-2
+    assert relerr(res[True][2].cpu(), 2 * res[False][2].cpu()) < 1e-3
+
+
+def test_tc_adjointness_full_batch():
+    """<conv(x), dy> == <x, dgrad(dy)> at config-2 batch (2B = 128 images through d_h2): no oracle needed."""
+    from gifgan import ops as _o
+    B, H, Ci, Co = 128, 16, 128, 256
+    ops, st, tv = _store(lambda t: _o.conv2d(t, Co, name="c", bias=False), (B, H, H, Ci))
+    x = torch.randn(B, H, H, Ci, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    dy = torch.randn(B, H // 2, H // 2, Co, device="cuda").to(torch.bfloat16)
+    y = ops.conv2d(x, Co, name="c", bias=False)
+    y.backward(dy)
+    lhs = (y.float().double() * dy.float().double()).sum().item()
+    rhs = (x.detach().float().double() * x.grad.float().double()).sum().item()
+    assert abs(lhs - rhs) < 1e-2 * abs(lhs)
