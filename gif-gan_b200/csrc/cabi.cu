@@ -27,6 +27,11 @@ int simt_linear_wgrad(const void*, int, const void*, int, float*, int, int, int,
 int skinny_linear_fwd(const void*, int, const float*, const float*, void*, int, int, int, int, int, float, cudaStream_t);
 int skinny_linear_dgrad(const void*, int, const float*, void*, int, int, int, int, cudaStream_t);
 int skinny_linear_wgrad(const void*, int, const void*, int, float*, int, int, int, cudaStream_t);
+// conv_c3.cu
+bool c3_applicable(const gg_conv_desc*);
+int c3_conv_down(const gg_conv_desc*, const float*, const float*, const float*, void*, cudaStream_t);
+int c3_conv_up(const gg_conv_desc*, const void*, const float*, const float*, float*, cudaStream_t);
+int c3_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t);
 // tc_tapgemm.cu
 int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
@@ -50,16 +55,19 @@ extern "C" int gg_device_arch(void) {
 extern "C" int gg_conv_down(const gg_conv_desc* d, const void* large, const void* w, const float* bias, void* small, void* stream) {
   GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_down: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_down(d, large, w, bias, small, (cudaStream_t)stream);
+  if (c3_applicable(d)) return c3_conv_down(d, (const float*)large, (const float*)w, bias, small, (cudaStream_t)stream);
   return simt_conv_down(d, large, (const float*)w, bias, small, (cudaStream_t)stream);
 }
 extern "C" int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large, void* stream) {
   GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_up: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream);
+  if (c3_applicable(d)) return c3_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream);
   return simt_conv_up(d, small, (const float*)w, bias, large, (cudaStream_t)stream);
 }
 extern "C" int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw, void* stream) {
   GG_REQUIRE(d && large && dw && small, GG_ERR_INVALID, "conv_wgrad: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
+  if (c3_applicable(d)) return c3_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream);
   return simt_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
 }
 

@@ -186,9 +186,18 @@ skinny_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const f
                   int out_dim, int act, float ap) {
   const int r = blockIdx.x;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k = threadIdx.x; k < in_dim; k += blockDim.x) {
-    const float xv = ldf(x + (int64_t)r * in_dim + k);
-    for (int n = 0; n < out_dim; ++n) acc[n] = fmaf(xv, __ldg(W + (int64_t)k * out_dim + n), acc[n]);
+  if (out_dim == 1 && (in_dim & 3) == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)W % 16 == 0)) {
+    // the GEMV of d_h3_lin / dvideo_h4: 4 elements per thread per trip, all loads independent
+    const TX* xr = x + (int64_t)r * in_dim;
+    for (int k = threadIdx.x * 4; k < in_dim; k += blockDim.x * 4) {
+      const float4 xv = ld4(xr + k), wv = ld4(W + k);
+      acc[0] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[0]))));
+    }
+  } else {
+    for (int k = threadIdx.x; k < in_dim; k += blockDim.x) {
+      const float xv = ldf(x + (int64_t)r * in_dim + k);
+      for (int n = 0; n < out_dim; ++n) acc[n] = fmaf(xv, __ldg(W + (int64_t)k * out_dim + n), acc[n]);
+    }
   }
   __shared__ float red[4][PW_THREADS / 32];
   for (int n = 0; n < out_dim; ++n) {
@@ -217,14 +226,18 @@ __global__ void skinny_dgrad_kernel(const TD* __restrict__ dy, const float* __re
 // wgrad: dW[k,n] += sum_r x[r,k] dy[r,n]
 template <typename TX, typename TD>
 __global__ void skinny_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __restrict__ dW, int rows, int in_dim, int out_dim) {
+  // grid = (k blocks, row chunks): each CTA reduces a chunk of rows for 128 k's, then one atomic per element
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= in_dim) return;
+  const int rchunk = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rchunk, r1 = min(rows, r0 + rchunk);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int r = 0; r < rows; ++r) {
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
     const float xv = ldf(x + (int64_t)r * in_dim + k);
     for (int n = 0; n < out_dim; ++n) acc[n] = fmaf(xv, ldf(dy + (int64_t)r * out_dim + n), acc[n]);
   }
-  for (int n = 0; n < out_dim; ++n) dW[(int64_t)k * out_dim + n] += acc[n];
+  for (int n = 0; n < out_dim; ++n) atomicAdd(dW + (int64_t)k * out_dim + n, acc[n]);
 }
 
 // ---- BasicLSTMCell step (recurrent_DCGAN.py:199-200) --------------------------------
@@ -406,7 +419,9 @@ int skinny_linear_dgrad(const void* dy, int dy_dt, const float* W, void* dx, int
   return check_launch("skinny_dgrad");
 }
 int skinny_linear_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dW, int rows, int in_dim, int out_dim, cudaStream_t st) {
-  const int blocks = ceil_div(in_dim, 128);
+  const int kblocks = ceil_div(in_dim, 128);
+  const int rchunks = std::max(1, std::min(ceil_div(rows, 8), ceil_div(148 * 2, kblocks)));
+  const dim3 blocks(kblocks, rchunks);
 #define GG_SW(TX, TD) skinny_wgrad_kernel<TX, TD><<<blocks, 128, 0, st>>>((const TX*)x, (const TD*)dy, dW, rows, in_dim, out_dim)
   if (x_dt == GG_F32 && dy_dt == GG_F32) GG_SW(float, float);
   else if (x_dt == GG_F32) GG_SW(float, bf16);

@@ -398,8 +398,10 @@ static void pick_box(int Mw, int Mh, int Md, int pixels, int* bw, int* bh, int* 
   *bn = pixels / (*bw * *bh * *bd);
 }
 
-static int check_tc(const gg_conv_desc* d, const void* a, const void* b) {
-  GG_REQUIRE(d->large_dtype == GG_BF16 && d->small_dtype == GG_BF16, GG_ERR_UNSUPPORTED, "tensor-core path needs bf16 activations");
+// need_large / need_small: which activation tensors are GEMM OPERANDS (must be bf16); an output may be fp32 or bf16
+static int check_tc(const gg_conv_desc* d, const void* a, const void* b, bool need_large, bool need_small) {
+  GG_REQUIRE((!need_large || d->large_dtype == GG_BF16) && (!need_small || d->small_dtype == GG_BF16), GG_ERR_UNSUPPORTED,
+             "tensor-core path needs bf16 operand activations");
   GG_REQUIRE(d->C % 64 == 0 && d->K % 64 == 0, GG_ERR_UNSUPPORTED, "tensor-core path needs channel counts that are multiples of 64 (C=%d K=%d)", d->C, d->K);
   GG_REQUIRE(d->kd * d->kh * d->kw <= TC_MAX_TAPS && d->sd * d->sh * d->sw <= TC_MAX_VIEWS, GG_ERR_UNSUPPORTED, "tensor-core path: too many taps / stride classes");
   GG_REQUIRE(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0), GG_ERR_INVALID, "tensor-core path needs 16-byte aligned tensors");
@@ -454,7 +456,7 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
 }
 
 int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, const float* bias, void* small, cudaStream_t st) {
-  int rc = check_tc(d, large, w_kc);
+  int rc = check_tc(d, large, w_kc, true, false);
   if (rc) return rc;
   TcPixParams p;
   memset(&p, 0, sizeof(p));
@@ -488,12 +490,12 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, con
   p.nclasses = 1; p.ntiles_n = d->K / p.BN;
   p.R = d->C; p.Nout = d->K; p.Mn = d->N;
   p.OD = d->Do; p.OH = d->Ho; p.OW = d->Wo; p.osd = p.osh = p.osw = 1;
-  p.act = d->act; p.act_param = d->act_param; p.out_bf16 = 1;
+  p.act = d->act; p.act_param = d->act_param; p.out_bf16 = (d->small_dtype == GG_BF16);
   return launch_pix(p, (int)(mtiles * p.ntiles_n), bias, small, st);
 }
 
 int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const float* bias, void* large, cudaStream_t st) {
-  int rc = check_tc(d, small, w_ck);
+  int rc = check_tc(d, small, w_ck, false, true);
   if (rc) return rc;
   TcPixParams p;
   memset(&p, 0, sizeof(p));
@@ -551,12 +553,12 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
   p.nclasses = ncls;
   p.R = d->K; p.Nout = d->C; p.Mn = d->N;
   p.OD = d->D; p.OH = d->H; p.OW = d->W; p.osd = d->sd; p.osh = d->sh; p.osw = d->sw;
-  p.act = d->act; p.act_param = d->act_param; p.out_bf16 = 1;
+  p.act = d->act; p.act_param = d->act_param; p.out_bf16 = (d->large_dtype == GG_BF16);
   return launch_pix(p, (int)(tiles * p.ntiles_n), bias, large, st);
 }
 
 int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw, cudaStream_t st) {
-  int rc = check_tc(d, large, small);
+  int rc = check_tc(d, large, small, true, true);
   if (rc) return rc;
   static TcWgradParams proto;   // large struct: build on the heap-free static under a lock, copy for the launch
   static std::mutex mu;

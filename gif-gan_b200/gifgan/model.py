@@ -82,6 +82,7 @@ class DCGAN(object):
         self.dataset_name = dataset_name
         self.checkpoint_dir = checkpoint_dir
         self._graph = None
+        self.want_sigmoid = True    # D = sigmoid(logits) is only used for summaries; the train step skips it
         self.build_model(z, sample_z)
         if standalone:
             self.store.finalize(OrderedDict(d=self.d_vars, g=self.g_vars))
@@ -139,11 +140,12 @@ class DCGAN(object):
         if not self.y_dim:
             B = image.shape[0]
             h0 = conv2d(image, self.df_dim, name='d_h0_conv', act='lrelu')
-            h1 = self.d_bn1(conv2d(h0, self.df_dim * 2, name='d_h1_conv'), train=train, act='lrelu', groups=groups)
-            h2 = self.d_bn2(conv2d(h1, self.df_dim * 4, name='d_h2_conv'), train=train, act='lrelu', groups=groups)
-            h3 = self.d_bn3(conv2d(h2, self.df_dim * 8, name='d_h3_conv'), train=train, act='lrelu', groups=groups)
+            # lrelu(d_bnN(conv2d(...), train=train)) -- conv + batch norm + LeakyReLU as one fused node each
+            h1 = conv2d(h0, self.df_dim * 2, name='d_h1_conv', bn=self.d_bn1, train=train, act='lrelu', groups=groups)
+            h2 = conv2d(h1, self.df_dim * 4, name='d_h2_conv', bn=self.d_bn2, train=train, act='lrelu', groups=groups)
+            h3 = conv2d(h2, self.df_dim * 8, name='d_h3_conv', bn=self.d_bn3, train=train, act='lrelu', groups=groups)
             h4 = linear(h3.reshape(B, -1), 1, 'd_h3_lin')
-            return ops.sigmoid(h4), h4, h2
+            return (ops.sigmoid(h4) if self.want_sigmoid else None), h4, h2
         else:
             B = image.shape[0]
             yb = y.reshape(B, 1, 1, self.y_dim)
@@ -151,12 +153,12 @@ class DCGAN(object):
             h0 = conv2d(x, self.c_dim + self.y_dim, name='d_h0_conv', act='lrelu')
             h0 = conv_cond_concat(h0, yb)
             # model.py:287: no train= argument -> always batch statistics
-            h1 = self.d_bn1(conv2d(h0, self.df_dim + self.y_dim, name='d_h1_conv'), act='lrelu', groups=groups)
+            h1 = conv2d(h0, self.df_dim + self.y_dim, name='d_h1_conv', bn=self.d_bn1, act='lrelu', groups=groups)
             h1 = torch.cat([h1.reshape(B, -1), y.to(h1.dtype)], 1)
-            h2 = self.d_bn2(linear(h1, self.dfc_dim, 'd_h2_lin'), act='lrelu', groups=groups)
+            h2 = linear(h1, self.dfc_dim, 'd_h2_lin', bn=self.d_bn2, act='lrelu', groups=groups)
             h2 = torch.cat([h2, y.to(h2.dtype)], 1)
             h3 = linear(h2, 1, 'd_h3_lin')
-            return ops.sigmoid(h3), h3
+            return (ops.sigmoid(h3) if self.want_sigmoid else None), h3
 
     def generator(self, z, y=None, train=True, out=None):
         """model.py:298-344 (and, with train=False, the sampler graph of model.py:346-389).
@@ -166,15 +168,16 @@ class DCGAN(object):
             s = self.output_size
             s2, s4, s8, s16 = int(s / 2), int(s / 4), int(s / 8), int(s / 16)
             # project `z` and reshape
-            self.z_, self.h0_w, self.h0_b = linear(z, self.gf_dim * 8 * s16 * s16, 'g_h0_lin', with_w=True)
-            self.h0 = self.z_.reshape(-1, s16, s16, self.gf_dim * 8)
-            h0 = self.g_bn0(self.h0, train=train, act='relu')
-            self.h1, self.h1_w, self.h1_b = deconv2d(h0, [B, s8, s8, self.gf_dim * 4], name='g_h1', with_w=True)
-            h1 = self.g_bn1(self.h1, train=train, act='relu')
-            h2, self.h2_w, self.h2_b = deconv2d(h1, [B, s4, s4, self.gf_dim * 2], name='g_h2', with_w=True)
-            h2 = self.g_bn2(h2, train=train, act='relu')
-            h3, self.h3_w, self.h3_b = deconv2d(h2, [B, s2, s2, self.gf_dim * 1], name='g_h3', with_w=True)
-            h3 = self.g_bn3(h3, train=train, act='relu')
+            # relu(g_bnN(...)): linear/deconv + batch norm + ReLU as one fused node each (model.py:304-319)
+            h0, self.h0_w, self.h0_b = linear(z, self.gf_dim * 8 * s16 * s16, 'g_h0_lin', with_w=True, bn=self.g_bn0,
+                                              bn_channels=self.gf_dim * 8, train=train, act='relu')
+            h0 = h0.reshape(-1, s16, s16, self.gf_dim * 8)
+            h1, self.h1_w, self.h1_b = deconv2d(h0, [B, s8, s8, self.gf_dim * 4], name='g_h1', with_w=True, bn=self.g_bn1,
+                                                train=train, act='relu')
+            h2, self.h2_w, self.h2_b = deconv2d(h1, [B, s4, s4, self.gf_dim * 2], name='g_h2', with_w=True, bn=self.g_bn2,
+                                                train=train, act='relu')
+            h3, self.h3_w, self.h3_b = deconv2d(h2, [B, s2, s2, self.gf_dim * 1], name='g_h3', with_w=True, bn=self.g_bn3,
+                                                train=train, act='relu')
             h4, self.h4_w, self.h4_b = deconv2d(h3, [B, s, s, self.c_dim], name='g_h4', with_w=True, act='tanh',
                                                 out_dtype=torch.float32, out=out)
             return h4
@@ -184,12 +187,12 @@ class DCGAN(object):
             yb = y.reshape(B, 1, 1, self.y_dim)
             z = torch.cat([z, y], 1)
             # model.py:331 / 380: g_bn0 is never given train=False -> batch statistics even in the sampler
-            h0 = self.g_bn0(linear(z, self.gfc_dim, 'g_h0_lin'), act='relu')
+            h0 = linear(z, self.gfc_dim, 'g_h0_lin', bn=self.g_bn0, act='relu')
             h0 = torch.cat([h0, y.to(h0.dtype)], 1)
-            h1 = self.g_bn1(linear(h0, self.gf_dim * 2 * s4 * s4, 'g_h1_lin'), train=train, act='relu')
+            h1 = linear(h0, self.gf_dim * 2 * s4 * s4, 'g_h1_lin', bn=self.g_bn1, train=train, act='relu')
             h1 = h1.reshape(B, s4, s4, self.gf_dim * 2)
             h1 = conv_cond_concat(h1, yb)
-            h2 = self.g_bn2(deconv2d(h1, [B, s2, s2, self.gf_dim * 2], name='g_h2'), train=train, act='relu')
+            h2 = deconv2d(h1, [B, s2, s2, self.gf_dim * 2], name='g_h2', bn=self.g_bn2, train=train, act='relu')
             h2 = conv_cond_concat(h2, yb)
             return deconv2d(h2, [B, s, s, self.c_dim], name='g_h3', act='sigmoid', out_dtype=torch.float32, out=out)
 
@@ -277,6 +280,7 @@ class DCGAN(object):
 
     def _step_device(self, images, z, y, evals, loss_vec):
         """The loop body of model.py:226-243 on device tensors; scalar losses are gathered into loss_vec."""
+        self.want_sigmoid = False
         d = self.d_update(images, z, y)
         g1 = self.g_update(z, y)
         # Run g_optim twice to make sure that d_loss does not go to zero (model.py:236-239)
@@ -287,6 +291,7 @@ class DCGAN(object):
         L = ops.cabi.lib()
         for i, o in enumerate(outs):
             ops.check(L.gg_axpby(ops.ptr(o[0:1]), 1.0, ops.ptr(loss_vec[i:i + 1]), 0.0, 1, ops.stream()), "gg_axpby")
+        self.want_sigmoid = True
 
     def train_step(self, batch_images, batch_z, batch_labels=None, evals=False, use_graph=True, sync=True):
         """One iteration of the loop body of model.py:226-243.  The batch may be host memory (numpy / pinned

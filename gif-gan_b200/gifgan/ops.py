@@ -311,7 +311,7 @@ class _Geom:
 
 def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None):
     small = out if out is not None else torch.empty(g.small_shape(ndim), dtype=out_dtype, device=large.device)
-    tc = _tc_ok(g.C, g.K, large, small)
+    tc = _tc_ok(g.C, g.K, large)
     d = g.desc(dt(large), dt(small), act, act_param, tc)
     w = wvar.packed()[1] if tc else wvar.data
     check(cabi.lib().gg_conv_down(ctypes.byref(d), ptr(large), ptr(w), ptr(bias), ptr(small), stream()), "gg_conv_down")
@@ -320,7 +320,7 @@ def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim,
 
 def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None):
     large = out if out is not None else torch.empty(g.large_shape(ndim), dtype=out_dtype, device=small.device)
-    tc = _tc_ok(g.C, g.K, large, small)
+    tc = _tc_ok(g.C, g.K, small)
     d = g.desc(dt(large), dt(small), act, act_param, tc)
     w = wvar.packed()[0] if tc else wvar.data
     check(cabi.lib().gg_conv_up(ctypes.byref(d), ptr(small), ptr(w), ptr(bias), ptr(large), stream()), "gg_conv_up")
@@ -407,7 +407,7 @@ def _out_dtype(act, out_dtype):
 # the reference operator API (ops.py)
 # --------------------------------------------------------------------------------------
 def conv2d(input_, output_dim, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name="conv2d", *, act=None, act_param=0.2,
-           out_dtype=None, bias=True):
+           out_dtype=None, bias=True, bn=None, train=True, groups=1):
     """ops.py:51-62 -- tf.nn.conv2d(input_, w, [1,d_h,d_w,1], 'SAME') + bias_add.
     Variables `name/w` [k_h,k_w,Cin,Cout] (truncated normal) and `name/biases` (zeros)."""
     B, H, W, Cin = input_.shape
@@ -417,11 +417,13 @@ def conv2d(input_, output_dim, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name="co
     Ho, ph, _ = same_pad(H, k_h, d_h)
     Wo, pw, _ = same_pad(W, k_w, d_w)
     geom = _Geom(B, (1, H, W), Cin, (1, Ho, Wo), output_dim, (1, k_h, k_w), (1, d_h, d_w), (0, ph, pw))
+    if bn is not None:
+        return _fused_bn(input_, _ConvProducer(geom, "down", wvar, bvar, 4), bn, train, act, act_param, _out_dtype(act, out_dtype), groups)
     return _conv_common(input_, wvar, bvar, geom, "down", act, act_param, _out_dtype(act, out_dtype))
 
 
 def conv3d(input_, output_dim, k_d=3, k_h=3, k_w=3, d_d=2, d_h=2, d_w=2, stddev=0.02, name="conv3d", *, act=None,
-           act_param=0.2, out_dtype=None):
+           act_param=0.2, out_dtype=None, bn=None, train=True, groups=1):
     """ops.py:64-75 -- tf.nn.conv3d(input_, w, [1,d_d,d_h,d_w,1], 'SAME') + bias_add."""
     B, D, H, W, Cin = input_.shape
     with variable_scope(name) as st:
@@ -431,11 +433,13 @@ def conv3d(input_, output_dim, k_d=3, k_h=3, k_w=3, d_d=2, d_h=2, d_w=2, stddev=
     Ho, ph, _ = same_pad(H, k_h, d_h)
     Wo, pw, _ = same_pad(W, k_w, d_w)
     geom = _Geom(B, (D, H, W), Cin, (Do, Ho, Wo), output_dim, (k_d, k_h, k_w), (d_d, d_h, d_w), (pd, ph, pw))
+    if bn is not None:
+        return _fused_bn(input_, _ConvProducer(geom, "down", wvar, bvar, 5), bn, train, act, act_param, _out_dtype(act, out_dtype), groups)
     return _conv_common(input_, wvar, bvar, geom, "down", act, act_param, _out_dtype(act, out_dtype))
 
 
 def deconv2d(input_, output_shape, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name="deconv2d", with_w=False, *, act=None,
-             act_param=0.2, out_dtype=None, bias=True, out=None):
+             act_param=0.2, out_dtype=None, bias=True, out=None, bn=None, train=True, groups=1):
     """ops.py:77-100 -- tf.nn.conv2d_transpose(input_, w[k_h,k_w,Cout,Cin], output_shape, [1,d_h,d_w,1]) + bias_add.
     Variables `name/w` (normal) and `name/biases` (zeros).  with_w=True also returns the Var objects."""
     B, h, w_, Cin = input_.shape
@@ -448,7 +452,10 @@ def deconv2d(input_, output_shape, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name
     if (oh, ow) != (h, w_):
         raise ValueError(f"deconv2d: output_shape {output_shape} inconsistent with input {tuple(input_.shape)}")
     geom = _Geom(B, (1, Ho, Wo), Cout, (1, h, w_), Cin, (1, k_h, k_w), (1, d_h, d_w), (0, ph, pw))
-    y = _conv_common(input_, wvar, bvar, geom, "up", act, act_param, _out_dtype(act, out_dtype), out)
+    if bn is not None:
+        y = _fused_bn(input_, _ConvProducer(geom, "up", wvar, bvar, 4), bn, train, act, act_param, _out_dtype(act, out_dtype), groups)
+    else:
+        y = _conv_common(input_, wvar, bvar, geom, "up", act, act_param, _out_dtype(act, out_dtype), out)
     return (y, wvar, bvar) if with_w else y
 
 
@@ -484,13 +491,19 @@ class _Linear(torch.autograd.Function):
         return dx, None, None, None, None, None, None, None
 
 
-def linear(input_, output_size, scope=None, stddev=0.02, bias_start=0.0, with_w=False, *, act=None, act_param=0.2, out_dtype=None):
-    """ops.py:106-117 -- tf.matmul(input_, Matrix) + bias; variables `scope/Matrix`, `scope/bias`."""
+def linear(input_, output_size, scope=None, stddev=0.02, bias_start=0.0, with_w=False, *, act=None, act_param=0.2, out_dtype=None,
+           bn=None, bn_channels=None, train=True, groups=1):
+    """ops.py:106-117 -- tf.matmul(input_, Matrix) + bias; variables `scope/Matrix`, `scope/bias`.
+    `bn=` fuses the batch norm (+activation) that follows; `bn_channels` is the channel count it normalises
+    when the reference reshapes the output to [-1, h, w, bn_channels] first (model.py:306-307)."""
     rows, in_dim = input_.shape
     with variable_scope(scope or "Linear") as st:
         mvar = st.get_variable("Matrix", [in_dim, output_size], random_normal_initializer(stddev))
         bvar = st.get_variable("bias", [output_size], constant_initializer(bias_start))
     od = out_dtype if out_dtype is not None else (torch.float32 if output_size <= 4 else act_dtype())
+    if bn is not None:
+        y = _fused_bn(input_, _LinearProducer(mvar, bvar, rows, output_size), bn, train, act, act_param, od, groups, bn_channels or output_size)
+        return (y, mvar, bvar) if with_w else y
     if _is_meta(input_):
         y = torch.empty((rows, output_size), dtype=od, device="meta")
     else:
@@ -575,6 +588,131 @@ class batch_norm(object):
         g = _wtensor(self.gamma, _wants_grad(self.gamma)) if self.affine else None
         b = _wtensor(self.beta, _wants_grad(self.beta)) if self.affine else None
         return _BatchNorm.apply(x.contiguous(), g, b, self, bool(train), act, act_param, od, groups)
+
+
+# ---- fused producer + batch norm + activation -------------------------------------------------
+class _ConvProducer:
+    """A conv2d / conv3d ('down') or deconv2d ('up') feeding a batch norm."""
+
+    def __init__(self, geom, direction, wvar, bvar, ndim):
+        self.geom, self.direction, self.wvar, self.bvar, self.ndim = geom, direction, wvar, bvar, ndim
+
+    def out_shape(self):
+        return self.geom.small_shape(self.ndim) if self.direction == "down" else self.geom.large_shape(self.ndim)
+
+    def fwd(self, x, b):
+        run = _run_down if self.direction == "down" else _run_up
+        return run(self.geom, x, self.wvar, b, torch.float32, None, 0.0, self.ndim)
+
+    def wgrad(self, x, dpre):
+        if self.direction == "down":
+            _run_wgrad(self.geom, x, dpre, self.wvar)
+        else:
+            _run_wgrad(self.geom, dpre, x, self.wvar)
+
+    def dgrad(self, dpre, x_dtype):
+        run = _run_up if self.direction == "down" else _run_down
+        return run(self.geom, dpre, self.wvar, None, x_dtype, None, 0.0, self.ndim)
+
+
+class _LinearProducer:
+    def __init__(self, mvar, bvar, rows, out_dim):
+        self.wvar, self.bvar, self.rows, self.out_dim = mvar, bvar, rows, out_dim
+
+    def out_shape(self):
+        return (self.rows, self.out_dim)
+
+    def fwd(self, x, b):
+        rows, in_dim = x.shape
+        y = torch.empty((rows, self.out_dim), dtype=torch.float32, device=x.device)
+        check(cabi.lib().gg_linear_fwd(ptr(x), dt(x), ptr(self.wvar.data), ptr(b), ptr(y), dt(y), rows, in_dim, self.out_dim, 0, 0.0,
+                                       stream()), "gg_linear_fwd")
+        return y
+
+    def wgrad(self, x, dpre):
+        rows, in_dim = x.shape
+        check(cabi.lib().gg_linear_wgrad(ptr(x), dt(x), ptr(dpre), dt(dpre), ptr(self.wvar.grad), None, rows, in_dim, self.out_dim,
+                                         stream()), "gg_linear_wgrad")
+
+    def dgrad(self, dpre, x_dtype):
+        rows = dpre.shape[0]
+        in_dim = self.wvar.data.shape[0]
+        dx = torch.empty((rows, in_dim), dtype=x_dtype, device=dpre.device)
+        check(cabi.lib().gg_linear_dgrad(ptr(dpre), dt(dpre), ptr(self.wvar.data), ptr(dx), dt(dx), rows, in_dim, self.out_dim, stream()),
+              "gg_linear_dgrad")
+        return dx
+
+
+class _FusedBN(torch.autograd.Function):
+    """producer (conv / deconv / conv3d / linear, + bias) -> batch norm -> activation as ONE autograd node.
+    The pre-normalisation tensor stays fp32 inside the node in both precisions (the batch-norm backward
+    subtracts nearly equal quantities; bf16 there costs several % of gradient accuracy), while everything that
+    crosses the node boundary -- and every GEMM operand -- is in the activation dtype.
+    A bias that feeds a TRAIN-mode batch norm has an exactly zero gradient (the mean subtraction cancels it);
+    it is left at zero rather than filled with rounding noise."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, prod, bn, train, act, act_param, out_dtype, groups, Cc):
+        L = cabi.lib()
+        pre = prod.fwd(x, b)
+        rows = pre.numel() // Cc
+        y = torch.empty(pre.shape, dtype=out_dtype, device=x.device)
+        save_mean = torch.empty((groups, Cc), dtype=torch.float32, device=x.device)
+        save_rstd = torch.empty((groups, Cc), dtype=torch.float32, device=x.device)
+        mm = bn.moving_mean.data if bn.moving_mean is not None else None
+        mv = bn.moving_variance.data if bn.moving_variance is not None else None
+        if train:
+            nbytes = L.gg_bn_workspace_bytes(Cc, groups)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            check(L.gg_bn_fwd_train(ptr(pre), dt(pre), ptr(y), dt(y), rows, Cc, groups, ptr(gamma), ptr(beta), ptr(mm), ptr(mv),
+                                    ptr(save_mean), ptr(save_rstd), bn.epsilon, bn.momentum, ACT[act], float(act_param),
+                                    ptr(ws), nbytes, stream()), "gg_bn_fwd_train")
+        else:
+            check(L.gg_bn_infer_stats(ptr(mm), ptr(mv), bn.epsilon, Cc, ptr(save_mean), ptr(save_rstd), stream()), "gg_bn_infer_stats")
+            check(L.gg_bn_fwd_infer(ptr(pre), dt(pre), ptr(y), dt(y), rows, Cc, ptr(gamma), ptr(beta), ptr(mm), ptr(mv), bn.epsilon,
+                                    ACT[act], float(act_param), stream()), "gg_bn_fwd_infer")
+        ctx.prod, ctx.bn, ctx.train, ctx.act, ctx.act_param, ctx.groups, ctx.Cc = prod, bn, train, act, act_param, groups, Cc
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(x, pre, gamma, beta, save_mean, save_rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pre, gamma, beta, save_mean, save_rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        L = cabi.lib()
+        bn, prod, Cc = ctx.bn, ctx.prod, ctx.Cc
+        rows = pre.numel() // Cc
+        need_w, need_b = ctx.needs_input_grad[1], prod.bvar is not None and ctx.needs_input_grad[2]
+        need_g, need_be = gamma is not None and ctx.needs_input_grad[3], beta is not None and ctx.needs_input_grad[4]
+        dpre = torch.empty(pre.shape, dtype=act_dtype(), device=pre.device)     # GEMM operand precision
+        nbytes = L.gg_bn_workspace_bytes(Cc, ctx.groups)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=pre.device)
+        check(L.gg_bn_bwd(ptr(pre), dt(pre), ptr(dy), dt(dy), ptr(dpre), dt(dpre), rows, Cc, ctx.groups, ptr(gamma), ptr(beta),
+                          ptr(save_mean), ptr(save_rstd), ptr(bn.gamma.grad) if need_g else None, ptr(bn.beta.grad) if need_be else None,
+                          ACT[ctx.act], float(ctx.act_param), 1 if ctx.train else 0, ptr(ws), nbytes, stream()), "gg_bn_bwd")
+        if need_b and not ctx.train:
+            _bias_grad(dpre.reshape(-1, prod.bvar.data.numel()), prod.bvar)
+        if need_w:
+            prod.wgrad(x, dpre)
+        dx = prod.dgrad(dpre, ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        return (dx,) + (None,) * 12
+
+
+def _fused_bn(input_, prod, bn, train, act, act_param, out_dtype, groups, channels=None):
+    shape = prod.out_shape()
+    Cc = channels if channels is not None else shape[-1]
+    bn._vars(Cc)
+    if _is_meta(input_):
+        return torch.empty(shape, dtype=out_dtype, device="meta")
+    _require_cuda(input_, "fused batch norm")
+    if not train and not bn.ema:
+        raise ValueError("inference-mode batch_norm needs moving statistics")
+    w = _wtensor(prod.wvar, _wants_grad(prod.wvar))
+    b = _wtensor(prod.bvar, _wants_grad(prod.bvar)) if prod.bvar is not None else None
+    g = _wtensor(bn.gamma, _wants_grad(bn.gamma)) if bn.affine else None
+    be = _wtensor(bn.beta, _wants_grad(bn.beta)) if bn.affine else None
+    return _FusedBN.apply(input_.contiguous(), w, b, g, be, prod, bn, bool(train), act, act_param, out_dtype, groups, Cc)
 
 
 # ---- standalone activations ------------------------------------------------------------

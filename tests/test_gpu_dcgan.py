@@ -120,7 +120,9 @@ def test_reference_schedule_three_steps_fp32():
         got = m.train_step(img, z, use_graph=False)
         want = ora.train_step(torch.tensor(img), torch.tensor(z))
         for k in ("d_loss", "g_loss_first", "g_loss"):
-            assert abs(got[k] - want[k]) < 2e-3 * max(1.0, abs(want[k])), (step, k, got[k], want[k])
+            # first step: pure kernel parity; later steps inherit Adam's amplification of rounding noise
+            tol = 1e-3 if step == 0 else 6e-3
+            assert abs(got[k] - want[k]) < tol * max(1.0, abs(want[k])), (step, k, got[k], want[k])
     assert m.d_optim.t == 3 and m.g_optim.t == 6
     weights_close_after_adam(m, ora.vars, 2e-4, 6, "3 steps")
     for k in ("d_bn1/moving_mean", "d_bn2/moving_variance", "g_bn0/moving_variance", "g_bn2/moving_mean"):
@@ -195,18 +197,36 @@ def test_mnist_conditional_branch_step():
 
 
 def test_full_size_config2_single_step():
-    """BASELINE config 2 at full size (batch 64, 64x64x3, gf=df=64): losses and a few gradients vs the oracle."""
+    """BASELINE config 2 at full size (batch 64, 64x64x3, gf=df=64): losses and gradients vs the float64 oracle.
+    Tolerance per tensor: 1e-4, or 1.5x the distance between the oracle evaluated in fp32 and in fp64 when that
+    is larger -- at this size a LeakyReLU/ReLU whose pre-activation rounds to the other side of zero in fp32
+    moves a filter gradient by O(1/sqrt(#pixels)), for ANY fp32 evaluation including the reference's."""
     B, size = 64, 64
-    m, ora = make_pair("fp32", B, size, 64, 64, dtype=torch.float64)    # float64 oracle: fp32 oneDNN wgrad is itself ~1e-3 off
+    m, ora = make_pair("fp32", B, size, 64, 64, dtype=torch.float64)
+    o32 = OracleDCGAN(batch_size=B, output_size=size, seed=7, dtype=torch.float32)
     img, z = batch(B, size)
+    names_d = ["d_h0_conv/w", "d_h1_conv/w", "d_h2_conv/w", "d_h3_conv/w", "d_h3_lin/Matrix", "d_bn2/gamma"]
+    names_g = ["g_h0_lin/Matrix", "g_h1/w", "g_h2/w", "g_h3/w", "g_h4/w", "g_bn1/beta"]
+
+    def check(names, got_vars, g64, g32):
+        bad = {}
+        for k in names:
+            floor = relerr(g32[k], g64[k])
+            e = relerr(got_vars[k].grad, g64[k])
+            if not e < max(1e-4, 1.5 * floor):
+                bad[k] = (e, floor)
+        assert not bad, bad
+
     losses = m.d_update(torch.tensor(img).cuda(), torch.tensor(z).cuda(), apply=False)
     want = ora.d_update(torch.tensor(img).double(), torch.tensor(z).double(), apply=False)
-    assert abs(losses[0].item() - want["d_loss"]) < 1e-3 * max(1, abs(want["d_loss"]))
-    check_grads(m, ["d_h0_conv/w", "d_h1_conv/w", "d_h2_conv/w", "d_h3_conv/w", "d_h3_lin/Matrix", "d_bn2/gamma"], want["grads"], 3e-4)
+    w32 = o32.d_update(torch.tensor(img), torch.tensor(z), apply=False)
+    assert abs(losses[0].item() - want["d_loss"]) < 1e-4 * max(1, abs(want["d_loss"]))
+    check(names_d, m.store.vars, want["grads"], w32["grads"])
     gl = m.g_update(torch.tensor(z).cuda(), apply=False)
     wg = ora.g_update(torch.tensor(z).double(), apply=False)
-    assert abs(gl[0].item() - wg["g_loss"]) < 1e-3 * max(1, abs(wg["g_loss"]))
-    check_grads(m, ["g_h0_lin/Matrix", "g_h1/w", "g_h2/w", "g_h3/w", "g_h4/w", "g_bn1/beta"], wg["grads"], 3e-4)
+    wg32 = o32.g_update(torch.tensor(z), apply=False)
+    assert abs(gl[0].item() - wg["g_loss"]) < 1e-4 * max(1, abs(wg["g_loss"]))
+    check(names_g, m.store.vars, wg["grads"], wg32["grads"])
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
