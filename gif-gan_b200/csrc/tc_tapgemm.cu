@@ -75,7 +75,7 @@ constexpr int TC_MAX_VIEWS = 8;
 constexpr int TILE_M = 128;
 constexpr int KCHUNK = 64;                 // bf16 elements per 128-byte swizzle row
 constexpr int A_STAGE_BYTES = TILE_M * 128; // 16 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 224;             // warps: 0 = TMA(A), 1 = MMA + TMEM owner, 2..5 = epilogue, 6 = TMA(B)
 
 struct TcTap {
   int8_t view;              // which A tensor map
@@ -160,7 +160,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;   // power of two >= 32
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }   // full: A + B producers
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.bmap);
@@ -172,41 +172,69 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // The producer loops are single-thread and latency-bound: keep them free of divisions and of
+  // loop-invariant work (one nested loop over taps x k-chunks), and split A and B across two warps.
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer, A operand (activation boxes) =====
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < iters; ++it) {
-        const TcTap tap = p.taps[C.tap_begin + it / kchunks];
-        const int kc = (it % kchunks) * KCHUNK;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t a_dst = smem_base + s * stage_bytes, b_dst = a_dst + A_STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), (uint32_t)stage_bytes);
-        tma_load_5d(a_dst, &p.amap[tap.view], full_bar(s), kc, mw0 + tap.ow, mh0 + tap.oh, md0 + tap.od, mn0);
-        tma_load_3d(b_dst, &p.bmap, full_bar(s), kc, n0, tap.widx);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      uint32_t ph = 1;                       // fresh barriers: waiting on parity 1 passes immediately
+      uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
+      const int nst = p.stages;
+      for (int t = C.tap_begin; t < C.tap_end; ++t) {
+        const TcTap tap = p.taps[t];
+        const void* amap = &p.amap[tap.view];
+        const int cw = mw0 + tap.ow, ch = mh0 + tap.oh, cd = md0 + tap.od;
+        for (int kc = 0; kc < p.R; kc += KCHUNK) {
+          mbar_wait(eb, ph);
+          mbar_expect_tx(fb, (uint32_t)A_STAGE_BYTES);
+          tma_load_5d(dst, amap, fb, kc, cw, ch, cd, mn0);
+          dst += stage_bytes; fb += 8u; eb += 8u;
+          if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===== TMA producer, B operand (filter tiles) =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      uint32_t dst = smem_base + A_STAGE_BYTES, fb = bar_base, eb = bar_base + 8u * p.stages;
+      const int nst = p.stages;
+      const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+      for (int t = C.tap_begin; t < C.tap_end; ++t) {
+        const int widx = p.taps[t].widx;
+        for (int kc = 0; kc < p.R; kc += KCHUNK) {
+          mbar_wait(eb, ph);
+          mbar_expect_tx(fb, b_bytes);
+          tma_load_3d(dst, &p.bmap, fb, kc, n0, widx);
+          dst += stage_bytes; fb += 8u; eb += 8u;
+          if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base + A_STAGE_BYTES; fb = bar_base; eb = bar_base + 8u * nst; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 0, 0);
+      // descriptor = constant high word | (address >> 4): only the low word changes per stage / k-step
+      const uint64_t desc_hi = make_smem_desc(0, 16, 1024);
       int s = 0;
       uint32_t ph = 0;
+      uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
+      const int nst = p.stages;
       for (int it = 0; it < iters; ++it) {
-        mbar_wait(full_bar(s), ph);
+        mbar_wait(fb, ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * stage_bytes, b_addr = a_addr + A_STAGE_BYTES;
+        const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+        const uint64_t bd = desc_hi | (uint64_t)(((a_addr + A_STAGE_BYTES) & 0x3FFFFu) >> 4);
 #pragma unroll
-        for (int k = 0; k < KCHUNK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(empty_bar(s));                       // frees this smem stage when the MMAs retire
-        if (it == iters - 1) umma_commit(tmem_full_bar);  // accumulator complete
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        for (int k = 0; k < KCHUNK / 16; ++k)                // +32 B per K=16 step -> +2 in 16-byte units
+          umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(eb);                                   // frees this smem stage when the MMAs retire
+        if (it == iters - 1) umma_commit(tmem_full_bar);    // accumulator complete
+        a_addr += stage_bytes; fb += 8u; eb += 8u;
+        if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
     }
   } else {
@@ -218,7 +246,8 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     const bool valid = mw < C.Mw && mh < C.Mh && md < C.Md && mn < p.Mn;
     const int ow = mw * p.osw + C.ow0, oh = mh * p.osh + C.oh0, od = md * p.osd + C.od0;
     const int64_t pix = (((int64_t)mn * p.OD + od) * p.OH + oh) * p.OW + ow;
-    mbar_wait(tmem_full_bar, 0);
+    if (lane == 0) mbar_wait(tmem_full_bar, 0);   // one polling lane per warp: the spin must not steal issue slots
+    __syncwarp();                                 // from the producer / MMA threads that share these schedulers
     tc_fence_after();
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t r[32];
@@ -295,7 +324,7 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
   const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }   // full: A + B producers
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.smap);
@@ -312,48 +341,64 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
     return;
   }
 
-  if (warp == 0) {
+  // pixel-tile coordinates of the first tile of this split (one division chain, outside the loops)
+  int tiw, tih, tid_, tin;
+  {
+    int pt = pt_begin;
+    tiw = pt % p.tw; pt /= p.tw;
+    tih = pt % p.th; pt /= p.th;
+    tid_ = pt % p.td; pt /= p.td;
+    tin = pt;
+  }
+  if (warp == 0 || warp == 6) {
+    // warp 0: the two large-tensor atoms (A operand); warp 6: the small-tensor atoms (B operand)
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
+      const bool isA = warp == 0;
       const bool has1 = a1.c0 >= 0;
+      const void* m0 = &p.lmap[a0.view];
+      const void* m1 = &p.lmap[a1.view];
+      const uint32_t bytes = isA ? (uint32_t)((has1 ? 2 : 1) * WG_ATOM_BYTES) : (uint32_t)(nb * WG_ATOM_BYTES);
+      int s = 0;
+      uint32_t ph = 1;
+      uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
+      const int nst = p.stages;
+      int iw = tiw, ih = tih, id = tid_, in = tin;
       for (int it = 0; it < iters; ++it) {
-        int pt = pt_begin + it;
-        const int iw = pt % p.tw; pt /= p.tw;
-        const int ih = pt % p.th; pt /= p.th;
-        const int id = pt % p.td; pt /= p.td;
-        const int in = pt;
         const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd, n0 = in * p.bn;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t dst = smem_base + s * stage_bytes;
-        mbar_expect_tx(full_bar(s), (uint32_t)((1 + (has1 ? 1 : 0) + nb) * WG_ATOM_BYTES));
-        tma_load_5d(dst, &p.lmap[a0.view], full_bar(s), a0.c0, w0 + a0.ow, h0 + a0.oh, d0 + a0.od, n0);
-        if (has1) tma_load_5d(dst + WG_ATOM_BYTES, &p.lmap[a1.view], full_bar(s), a1.c0, w0 + a1.ow, h0 + a1.oh, d0 + a1.od, n0);
-        for (int j = 0; j < nb; ++j)
-          tma_load_5d(dst + (2 + j) * WG_ATOM_BYTES, &p.smap, full_bar(s), k0 + j * 64, w0, h0, d0, n0);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        mbar_wait(eb, ph);
+        mbar_expect_tx(fb, bytes);
+        if (isA) {
+          tma_load_5d(dst, m0, fb, a0.c0, w0 + a0.ow, h0 + a0.oh, d0 + a0.od, n0);
+          if (has1) tma_load_5d(dst + WG_ATOM_BYTES, m1, fb, a1.c0, w0 + a1.ow, h0 + a1.oh, d0 + a1.od, n0);
+        } else {
+          for (int j = 0; j < nb; ++j) tma_load_5d(dst + (2 + j) * WG_ATOM_BYTES, &p.smap, fb, k0 + j * 64, w0, h0, d0, n0);
+        }
+        if (++iw == p.tw) { iw = 0; if (++ih == p.th) { ih = 0; if (++id == p.td) { id = 0; ++in; } } }
+        dst += stage_bytes; fb += 8u; eb += 8u;
+        if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // A: M = 128 = 2 atoms (LBO = atom stride), MN-major; B: N = BN = nb atoms, MN-major.
       const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 1, 1);
+      const uint64_t desc_hi = make_smem_desc(0, WG_ATOM_BYTES, 1024);
       int s = 0;
       uint32_t ph = 0;
+      uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
+      const int nst = p.stages;
       for (int it = 0; it < iters; ++it) {
-        mbar_wait(full_bar(s), ph);
+        mbar_wait(fb, ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * stage_bytes, b_addr = a_addr + 2 * WG_ATOM_BYTES;
+        const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+        const uint64_t bd = desc_hi | (uint64_t)(((a_addr + 2 * WG_ATOM_BYTES) & 0x3FFFFu) >> 4);
 #pragma unroll
-        for (int k = 0; k < WG_PIX / 16; ++k) {
-          // 16 pixels (K) per MMA = two 8-row groups: advance 2048 B per step
-          const uint64_t ad = make_smem_desc(a_addr + k * 2048, WG_ATOM_BYTES, 1024);
-          const uint64_t bd = make_smem_desc(b_addr + k * 2048, WG_ATOM_BYTES, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(empty_bar(s));
+        for (int k = 0; k < WG_PIX / 16; ++k)   // 16 pixels (K) per MMA = two 8-row groups: +2048 B = +128 units per step
+          umma_bf16(tmem_base, ad + 128u * k, bd + 128u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(eb);
         if (it == iters - 1) umma_commit(tmem_full_bar);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        a_addr += stage_bytes; fb += 8u; eb += 8u;
+        if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
     }
   } else {
@@ -362,7 +407,8 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
     const WgAtom a = (row < 64) ? a0 : a1;
     const bool valid = a.c0 >= 0;
     float* dst = dw + ((int64_t)a.widx * p.C + (valid ? a.c0 : 0) + (row & 63)) * p.K + k0;
-    mbar_wait(tmem_full_bar, 0);
+    if (lane == 0) mbar_wait(tmem_full_bar, 0);
+    __syncwarp();
     tc_fence_after();
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t r[32];

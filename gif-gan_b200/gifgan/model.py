@@ -134,12 +134,17 @@ class DCGAN(object):
         self.all_vars = mine
 
     # ------------------------------------------------------------------------------
-    def discriminator(self, image, y=None, reuse=False, train=True, groups=1):
+    def discriminator(self, image, y=None, reuse=False, train=True, groups=1, stop_at_h2=False):
         """model.py:268-296.  `groups=2` runs D(real) and D(fake) as one batch whose halves are
-        batch-normalised separately (identical numbers to two calls, half the launches)."""
+        batch-normalised separately (identical numbers to two calls, half the launches).  `stop_at_h2`
+        evaluates only what D_activations needs (what TF's pruning does for VID_DCGAN's fetches)."""
         if not self.y_dim:
             B = image.shape[0]
             h0 = conv2d(image, self.df_dim, name='d_h0_conv', act='lrelu')
+            if stop_at_h2:
+                h1 = conv2d(h0, self.df_dim * 2, name='d_h1_conv', bn=self.d_bn1, train=train, act='lrelu', groups=groups)
+                h2 = conv2d(h1, self.df_dim * 4, name='d_h2_conv', bn=self.d_bn2, train=train, act='lrelu', groups=groups)
+                return None, None, h2
             # lrelu(d_bnN(conv2d(...), train=train)) -- conv + batch norm + LeakyReLU as one fused node each
             h1 = conv2d(h0, self.df_dim * 2, name='d_h1_conv', bn=self.d_bn1, train=train, act='lrelu', groups=groups)
             h2 = conv2d(h1, self.df_dim * 4, name='d_h2_conv', bn=self.d_bn2, train=train, act='lrelu', groups=groups)

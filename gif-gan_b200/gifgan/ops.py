@@ -263,6 +263,7 @@ def _wtensor(var: Var, requires_grad: bool):
 
 
 _TRAINABLE: set = set()
+DEBUG_TAP = None     # tools/diag_parity.py sets this to a dict to capture per-layer tensors
 
 
 @contextlib.contextmanager
@@ -674,6 +675,8 @@ class _FusedBN(torch.autograd.Function):
         ctx.prod, ctx.bn, ctx.train, ctx.act, ctx.act_param, ctx.groups, ctx.Cc = prod, bn, train, act, act_param, groups, Cc
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(x, pre, gamma, beta, save_mean, save_rstd)
+        if DEBUG_TAP is not None:
+            DEBUG_TAP.setdefault("fwd", []).append((prod.wvar.name, pre, y))
         return y
 
     @staticmethod
@@ -691,6 +694,8 @@ class _FusedBN(torch.autograd.Function):
         check(L.gg_bn_bwd(ptr(pre), dt(pre), ptr(dy), dt(dy), ptr(dpre), dt(dpre), rows, Cc, ctx.groups, ptr(gamma), ptr(beta),
                           ptr(save_mean), ptr(save_rstd), ptr(bn.gamma.grad) if need_g else None, ptr(bn.beta.grad) if need_be else None,
                           ACT[ctx.act], float(ctx.act_param), 1 if ctx.train else 0, ptr(ws), nbytes, stream()), "gg_bn_bwd")
+        if DEBUG_TAP is not None:
+            DEBUG_TAP.setdefault("bwd", []).append((prod.wvar.name, dy, dpre))
         if need_b and not ctx.train:
             _bias_grad(dpre.reshape(-1, prod.bvar.data.numel()), prod.bvar)
         if need_w:
@@ -849,6 +854,14 @@ class AdamOptimizer:
         self.state = torch.zeros(2, dtype=torch.int32, device=store.device)   # [t, lr_t bits] (device-side, graph-safe)
 
     def range(self):
+        """Element range of this optimiser's var_list in the flat buffers.  `group` may be a tuple of
+        adjacent groups (e.g. video vars + image vars when --train_img_disc is set)."""
+        if isinstance(self.group, (tuple, list)):
+            rs = [self.store.ranges[g] for g in self.group]
+            for (_, e0), (b1, _) in zip(rs, rs[1:]):
+                if e0 != b1:
+                    raise ValueError(f"optimiser groups {self.group} are not adjacent in the flat buffer")
+            return rs[0][0], rs[-1][1]
         return self.store.ranges[self.group]
 
     def zero_grad(self):

@@ -30,14 +30,70 @@ def _is_trainable(name):
     return not (name.endswith("moving_mean") or name.endswith("moving_variance"))
 
 
+def _bf16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _RoundBoth(torch.autograd.Function):
+    """value rounded to bf16 forward, gradient rounded to bf16 backward (a tensor the product stores in bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _RoundGrad(torch.autograd.Function):
+    """identity forward, gradient rounded to bf16 backward (fp32 pre-norm tensor whose gradient is a bf16 GEMM operand)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _RoundValue(torch.autograd.Function):
+    """value rounded to bf16 forward, gradient untouched (the packed bf16 copy of an fp32 master filter)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 class _Graph:
-    """Shared helpers: a variable store + the ops.py wrappers bound to it."""
+    """Shared helpers: a variable store + the ops.py wrappers bound to it.
+
+    `quant="bf16"` reproduces the product's bf16-mode quantisation points in the oracle (activations and their
+    gradients stored in bf16, bf16 filter copies on the tensor-core layers, bf16 pre-norm gradients) so that the
+    end-to-end bf16 parity test compares like with like: against a plain float64 oracle ~0.5 % of the
+    ReLU/LeakyReLU masks flip under bf16 rounding noise, which by itself is a 5-10 % L2 gradient difference."""
 
     def __init__(self, dtype):
         self.dtype = dtype
         self.vars: dict[str, torch.Tensor] = {}
         self.prefix = ""
         self.trace = None  # when a dict, activations are recorded under their layer names
+        self.quant = None
+
+    def qa(self, x):
+        return _RoundBoth.apply(x) if self.quant else x
+
+    def qg(self, x, on=True):
+        return _RoundGrad.apply(x) if (self.quant and on) else x
+
+    def qw(self, w):
+        C, K = w.shape[-2], w.shape[-1]
+        return _RoundValue.apply(w) if (self.quant and C % 64 == 0 and K % 64 == 0) else w
 
     def _v(self, name):
         return self.vars[self.prefix + name]
@@ -45,6 +101,8 @@ class _Graph:
     def _rec(self, name, t):
         if self.trace is not None:
             self.trace[name] = t
+            if t.requires_grad and not t.is_leaf:
+                t.retain_grad()          # per-layer activation gradients for the parity diagnostics
         return t
 
     def bn(self, name, x, train):
@@ -58,16 +116,16 @@ class _Graph:
         return T.batch_norm_infer(x, g, b, mm, mv)
 
     def conv2d(self, name, x):
-        return T.conv2d(x, self._v(f"{name}/w"), self._v(f"{name}/biases"))
+        return self.qg(T.conv2d(x, self.qw(self._v(f"{name}/w")), self._v(f"{name}/biases")))
 
     def conv3d(self, name, x):
-        return T.conv3d(x, self._v(f"{name}/w"), self._v(f"{name}/biases"))
+        return self.qg(T.conv3d(x, self.qw(self._v(f"{name}/w")), self._v(f"{name}/biases")))
 
-    def deconv2d(self, name, x, out_shape):
-        return T.conv2d_transpose(x, self._v(f"{name}/w"), out_shape, self._v(f"{name}/biases"))
+    def deconv2d(self, name, x, out_shape, grad_round=True):
+        return self.qg(T.conv2d_transpose(x, self.qw(self._v(f"{name}/w")), out_shape, self._v(f"{name}/biases")), grad_round)
 
-    def linear(self, name, x):
-        return T.linear(x, self._v(f"{name}/Matrix"), self._v(f"{name}/bias"))
+    def linear(self, name, x, grad_round=False):
+        return self.qg(T.linear(x, self._v(f"{name}/Matrix"), self._v(f"{name}/bias")), grad_round)
 
     def set_requires_grad(self, names):
         for k, v in self.vars.items():
@@ -145,10 +203,10 @@ class DCGAN(_Graph):
     def discriminator(self, image, y=None, train=True, tag="d"):
         B = image.shape[0]
         if not self.y_dim:
-            h0 = self._rec(f"{tag}_h0", T.lrelu(self._rec(f"{tag}_h0_conv", self.conv2d("d_h0_conv", image))))
-            h1 = self._rec(f"{tag}_h1", T.lrelu(self.bn("d_bn1", self._rec(f"{tag}_h1_conv", self.conv2d("d_h1_conv", h0)), train)))
-            h2 = self._rec(f"{tag}_h2", T.lrelu(self.bn("d_bn2", self._rec(f"{tag}_h2_conv", self.conv2d("d_h2_conv", h1)), train)))
-            h3 = self._rec(f"{tag}_h3", T.lrelu(self.bn("d_bn3", self._rec(f"{tag}_h3_conv", self.conv2d("d_h3_conv", h2)), train)))
+            h0 = self._rec(f"{tag}_h0", self.qa(T.lrelu(self._rec(f"{tag}_h0_conv", self.conv2d("d_h0_conv", image)))))
+            h1 = self._rec(f"{tag}_h1", self.qa(T.lrelu(self.bn("d_bn1", self._rec(f"{tag}_h1_conv", self.conv2d("d_h1_conv", h0)), train))))
+            h2 = self._rec(f"{tag}_h2", self.qa(T.lrelu(self.bn("d_bn2", self._rec(f"{tag}_h2_conv", self.conv2d("d_h2_conv", h1)), train))))
+            h3 = self._rec(f"{tag}_h3", self.qa(T.lrelu(self.bn("d_bn3", self._rec(f"{tag}_h3_conv", self.conv2d("d_h3_conv", h2)), train))))
             h4 = self._rec(f"{tag}_logits", self.linear("d_h3_lin", h3.reshape(B, -1)))
             return torch.sigmoid(h4), h4, h2
         yb = y.reshape(B, 1, 1, self.y_dim)
@@ -167,15 +225,15 @@ class DCGAN(_Graph):
         gf = self.gf_dim
         if not self.y_dim:
             s2, s4, s8, s16 = s // 2, s // 4, s // 8, s // 16
-            h0 = self._rec(f"{tag}_h0_lin", self.linear("g_h0_lin", z)).reshape(-1, s16, s16, gf * 8)
-            h0 = self._rec(f"{tag}_h0", torch.relu(self.bn("g_bn0", h0, train)))
+            h0 = self._rec(f"{tag}_h0_lin", self.linear("g_h0_lin", z, grad_round=True)).reshape(-1, s16, s16, gf * 8)
+            h0 = self._rec(f"{tag}_h0", self.qa(torch.relu(self.bn("g_bn0", h0, train))))
             h1 = self._rec(f"{tag}_h1_deconv", self.deconv2d("g_h1", h0, [B, s8, s8, gf * 4]))
-            h1 = self._rec(f"{tag}_h1", torch.relu(self.bn("g_bn1", h1, train)))
+            h1 = self._rec(f"{tag}_h1", self.qa(torch.relu(self.bn("g_bn1", h1, train))))
             h2 = self._rec(f"{tag}_h2_deconv", self.deconv2d("g_h2", h1, [B, s4, s4, gf * 2]))
-            h2 = self._rec(f"{tag}_h2", torch.relu(self.bn("g_bn2", h2, train)))
+            h2 = self._rec(f"{tag}_h2", self.qa(torch.relu(self.bn("g_bn2", h2, train))))
             h3 = self._rec(f"{tag}_h3_deconv", self.deconv2d("g_h3", h2, [B, s2, s2, gf]))
-            h3 = self._rec(f"{tag}_h3", torch.relu(self.bn("g_bn3", h3, train)))
-            h4 = self._rec(f"{tag}_h4_deconv", self.deconv2d("g_h4", h3, [B, s, s, self.c_dim]))
+            h3 = self._rec(f"{tag}_h3", self.qa(torch.relu(self.bn("g_bn3", h3, train))))
+            h4 = self._rec(f"{tag}_h4_deconv", self.deconv2d("g_h4", h3, [B, s, s, self.c_dim], grad_round=False))
             return self._rec(f"{tag}_out", torch.tanh(h4))
         s2, s4 = s // 2, s // 4
         yb = y.reshape(B, 1, 1, self.y_dim)

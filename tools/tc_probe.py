@@ -25,6 +25,8 @@ CASES = [
     ("c3d_h1", 2, (16, 8, 8), 256, 256, (3, 3, 3), (2, 2, 2)),
     ("c3d_h3", 4, (4, 2, 2), 256, 256, (3, 3, 3), (2, 2, 2)),
     ("d_h1_full", 128, (1, 32, 32), 64, 128, (1, 5, 5), (1, 2, 2)),
+    ("d_h2_full", 128, (1, 16, 16), 128, 256, (1, 5, 5), (1, 2, 2)),
+    ("g_h1_full", 64, (1, 8, 8), 256, 512, (1, 5, 5), (1, 2, 2)),
 ]
 OPS = ["down", "up", "wgrad"]
 
