@@ -36,6 +36,8 @@ int c3_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaSt
 int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int tc_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStream_t);
+void tc_set_repeat(int);
+void tc_set_prof(void*);
 }  // namespace gg
 
 using namespace gg;
@@ -43,6 +45,11 @@ using namespace gg;
 extern "C" int gg_version(void) { return GG_VERSION; }
 extern "C" const char* gg_last_error(void) { return g_err; }
 extern "C" uint64_t gg_launch_count(void) { return g_launches.load(); }
+
+// measurement hook: every tensor-core conv call launches its kernel n times (host planning amortised)
+extern "C" void gg_debug_set_repeat(int n) { tc_set_repeat(n); }
+// measurement hook: device buffer of 512 x 8 uint64 receiving a per-CTA clock64 breakdown of tc_pixgemm (NULL = off)
+extern "C" void gg_debug_set_prof(void* buf) { tc_set_prof(buf); }
 
 extern "C" int gg_device_arch(void) {
   int dev = 0, major = 0, minor = 0;

@@ -63,37 +63,40 @@ __device__ __forceinline__ void st4(bf16* p, float4 v) {
 }
 
 // ---- activations (include/gifgan.h gg_act) ----------------------------------------
+// NOTE: no `switch` on the runtime activation code inside per-element code: nvcc lowers it to an indirect
+// jump-table branch (BRX) per element, which cost ~20k cycles per tile in the tcgen05 epilogue (profiles/).
+// none / relu / lrelu share one branch-free form y = max(u, slope*u) with slope = 1 / 0 / leak; the
+// transcendental ones sit behind a warp-uniform if-chain.
+__device__ __forceinline__ float act_slope(int act, float a) { return act == GG_ACT_NONE ? 1.f : (act == GG_ACT_RELU ? 0.f : a); }
+
 __device__ __forceinline__ float act_fwd(float u, int act, float a) {
-  switch (act) {
-    case GG_ACT_RELU: return fmaxf(u, 0.f);
-    case GG_ACT_LRELU: return fmaxf(u, a * u);
-    case GG_ACT_TANH: return tanhf(u);
-    case GG_ACT_SIGMOID: return 1.f / (1.f + expf(-u));
-    case GG_ACT_TANH01: return 0.5f * (tanhf(u) + 1.f);
-    default: return u;
-  }
+  if (act <= GG_ACT_LRELU) return fmaxf(u, u * act_slope(act, a));
+  if (act == GG_ACT_TANH) return tanhf(u);
+  if (act == GG_ACT_SIGMOID) return 1.f / (1.f + expf(-u));
+  return 0.5f * (tanhf(u) + 1.f);   // GG_ACT_TANH01
 }
 // derivative expressed through the OUTPUT y = act(u)
 __device__ __forceinline__ float act_grad_from_out(float y, int act, float a) {
-  switch (act) {
-    case GG_ACT_RELU: return y > 0.f ? 1.f : 0.f;           // tf.nn.relu: 0 at 0
-    case GG_ACT_LRELU: return y >= 0.f ? 1.f : a;            // tf.maximum(x, a*x): 1 at 0 (0<a<1)
-    case GG_ACT_TANH: return 1.f - y * y;
-    case GG_ACT_SIGMOID: return y * (1.f - y);
-    case GG_ACT_TANH01: { float t = 2.f * y - 1.f; return 0.5f * (1.f - t * t); }
-    default: return 1.f;
+  if (act <= GG_ACT_LRELU) {
+    // tf.nn.relu: 0 at 0;  tf.maximum(x, a*x): 1 at 0 (0 < a < 1);  identity: 1
+    const float at_zero = act == GG_ACT_RELU ? 0.f : 1.f;
+    return y > 0.f ? 1.f : (y == 0.f ? at_zero : act_slope(act, a));
   }
+  if (act == GG_ACT_TANH) return 1.f - y * y;
+  if (act == GG_ACT_SIGMOID) return y * (1.f - y);
+  const float t = 2.f * y - 1.f;
+  return 0.5f * (1.f - t * t);
 }
 // derivative expressed through the pre-activation u
 __device__ __forceinline__ float act_grad_from_pre(float u, int act, float a) {
-  switch (act) {
-    case GG_ACT_RELU: return u > 0.f ? 1.f : 0.f;
-    case GG_ACT_LRELU: return u >= 0.f ? 1.f : a;
-    case GG_ACT_TANH: { float t = tanhf(u); return 1.f - t * t; }
-    case GG_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-u)); return s * (1.f - s); }
-    case GG_ACT_TANH01: { float t = tanhf(u); return 0.5f * (1.f - t * t); }
-    default: return 1.f;
+  if (act <= GG_ACT_LRELU) {
+    const float at_zero = act == GG_ACT_RELU ? 0.f : 1.f;
+    return u > 0.f ? 1.f : (u == 0.f ? at_zero : act_slope(act, a));
   }
+  if (act == GG_ACT_TANH) { const float t = tanhf(u); return 1.f - t * t; }
+  if (act == GG_ACT_SIGMOID) { const float s = 1.f / (1.f + expf(-u)); return s * (1.f - s); }
+  const float t = tanhf(u);
+  return 0.5f * (1.f - t * t);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -21,6 +21,7 @@
 //     fp32 gradient buffer with red.global.add (split over pixel ranges across CTAs).
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -50,13 +51,19 @@ static EncodeTiledFn get_encode() {
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box) {
+  return encode_tmap(out, GG_BF16, base, rank, dims, strides_bytes, box);
+}
+
+int encode_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
   GG_REQUIRE(enc != nullptr, GG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = enc(out, dtype == GG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                   const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GG_REQUIRE(r == CUDA_SUCCESS, GG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
@@ -93,6 +100,7 @@ struct TcClass {
 struct TcPixParams {
   CUtensorMap amap[TC_MAX_VIEWS];
   CUtensorMap bmap;
+  CUtensorMap omap[TC_MAX_CLASSES];   // output tensor (per output-parity class for conv_up), box = (128 B of channels, bw, bh, bd, bn)
   int nclasses, ntiles_n;   // N tiles (output-channel tiles)
   int bw, bh, bd, bn;       // box extents: bw*bh*bd*bn == 128
   int BN;                   // output-channel tile (UMMA N): 64 / 128 / 256
@@ -105,6 +113,7 @@ struct TcPixParams {
   float act_param;
   int out_bf16;
   int stages;
+  unsigned long long* prof;   // optional per-CTA clock64 breakdown (tools/tc_sweep.py --prof), 8 slots per CTA
   TcClass cls[TC_MAX_CLASSES];
   TcTap taps[TC_MAX_TAPS];
 };
@@ -132,6 +141,7 @@ __device__ __forceinline__ void store_row32(void* out, int64_t elem_off, const f
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict__ bias, void* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
+  const long long t_begin = clock64();
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
@@ -171,6 +181,8 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  unsigned long long* prof = (p.prof != nullptr && blockIdx.x < 512) ? p.prof + 8 * blockIdx.x : nullptr;
+  const long long t_setup = clock64();
 
   // The producer loops are single-thread and latency-bound: keep them free of divisions and of
   // loop-invariant work (one nested loop over taps x k-chunks), and split A and B across two warps.
@@ -181,18 +193,22 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       uint32_t ph = 1;                       // fresh barriers: waiting on parity 1 passes immediately
       uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
       const int nst = p.stages;
+      long long wait_cycles = 0;
       for (int t = C.tap_begin; t < C.tap_end; ++t) {
         const TcTap tap = p.taps[t];
         const void* amap = &p.amap[tap.view];
         const int cw = mw0 + tap.ow, ch = mh0 + tap.oh, cd = md0 + tap.od;
         for (int kc = 0; kc < p.R; kc += KCHUNK) {
+          const long long w0 = clock64();
           mbar_wait(eb, ph);
+          wait_cycles += clock64() - w0;
           mbar_expect_tx(fb, (uint32_t)A_STAGE_BYTES);
           tma_load_5d(dst, amap, fb, kc, cw, ch, cd, mn0);
           dst += stage_bytes; fb += 8u; eb += 8u;
           if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
         }
       }
+      if (prof) { prof[0] = (unsigned long long)(clock64() - t_setup); prof[1] = (unsigned long long)wait_cycles; }
     }
   } else if (warp == 6) {
     // ===== TMA producer, B operand (filter tiles) =====
@@ -223,8 +239,11 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       uint32_t ph = 0;
       uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
       const int nst = p.stages;
+      long long wait_cycles = 0;
       for (int it = 0; it < iters; ++it) {
+        const long long w0 = clock64();
         mbar_wait(fb, ph);
+        wait_cycles += clock64() - w0;
         tc_fence_after();
         const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
         const uint64_t bd = desc_hi | (uint64_t)(((a_addr + A_STAGE_BYTES) & 0x3FFFFu) >> 4);
@@ -236,19 +255,24 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
         a_addr += stage_bytes; fb += 8u; eb += 8u;
         if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
+      if (prof) { prof[2] = (unsigned long long)(clock64() - t_setup); prof[3] = (unsigned long long)wait_cycles; }
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;                 // accumulator row = pixel within the tile
     const int iw = row % p.bw, ih = (row / p.bw) % p.bh, id = (row / (p.bw * p.bh)) % p.bd, in = row / (p.bw * p.bh * p.bd);
-    const int mw = mw0 + iw, mh = mh0 + ih, md = md0 + id, mn = mn0 + in;
-    const bool valid = mw < C.Mw && mh < C.Mh && md < C.Md && mn < p.Mn;
-    const int ow = mw * p.osw + C.ow0, oh = mh * p.osh + C.oh0, od = md * p.osd + C.od0;
-    const int64_t pix = (((int64_t)mn * p.OD + od) * p.OH + oh) * p.OW + ow;
+    (void)iw; (void)ih; (void)id; (void)in;
     if (lane == 0) mbar_wait(tmem_full_bar, 0);   // one polling lane per warp: the spin must not steal issue slots
     __syncwarp();                                 // from the producer / MMA threads that share these schedulers
     tc_fence_after();
+    const long long t_acc = clock64();
+    // Accumulator -> (+bias, activation) -> shared memory in the 128B-swizzled box layout -> TMA tensor store.
+    // All pipeline stages are free once tmem_full fired (every MMA that read them has retired), so the tile
+    // is staged at smem_base: [BN*esz/128 column blocks][128 rows][128 B], 16-byte chunk index XOR (row & 7).
+    // The TMA store clips partial tiles and, for conv_up, scatters to the stride-s output parity view.
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -260,19 +284,45 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
         if (bias != nullptr) f += __ldg(bias + n0 + c0 + j);
         v[j] = act_fwd(f, p.act, p.act_param);
       }
-      if (valid) {
-        const int64_t off = pix * p.Nout + n0 + c0;
-        if (p.out_bf16) store_row32<true>(out, off, v);
-        else store_row32<false>(out, off, v);
+      if (p.out_bf16) {
+        // 32 bf16 = 64 B = 4 chunks: half of the 128-byte row of column block c0/64
+        const uint32_t blk = smem_base + (uint32_t)(c0 >> 6) * (TILE_M * 128u) + row_off;
+        const uint32_t ch0 = (uint32_t)((c0 & 63) >> 3);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]), p1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]), p3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch0 + g) ^ sw) << 4)), "r"(*reinterpret_cast<uint32_t*>(&p0)),
+                       "r"(*reinterpret_cast<uint32_t*>(&p1)), "r"(*reinterpret_cast<uint32_t*>(&p2)), "r"(*reinterpret_cast<uint32_t*>(&p3)) : "memory");
+        }
+      } else {
+        // 32 fp32 = 128 B = the whole row of column block c0/32
+        const uint32_t blk = smem_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((((uint32_t)g) ^ sw) << 4)), "f"(v[g * 4]), "f"(v[g * 4 + 1]),
+                       "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3]) : "memory");
       }
     }
+    fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA engine
+    asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+    if (warp == 2 && lane == 0) {
+      const int nblk = p.out_bf16 ? (p.BN >> 6) : (p.BN >> 5);
+      const int cstep = p.out_bf16 ? 64 : 32;
+      for (int b = 0; b < nblk; ++b)
+        tma_store_5d(&p.omap[ci], smem_base + (uint32_t)b * (TILE_M * 128u), n0 + b * cstep, mw0, mh0, md0, mn0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after this
+    }
     tc_fence_before();
+    if (prof && warp == 2 && lane == 0) { prof[4] = (unsigned long long)(t_acc - t_setup); prof[5] = (unsigned long long)(clock64() - t_setup); }
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+  if (prof && threadIdx.x == 0) { prof[6] = (unsigned long long)(clock64() - t_setup); prof[7] = (unsigned long long)(t_setup - t_begin); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -484,21 +534,45 @@ static int make_small_map(const gg_conv_desc* d, const void* small, const uint32
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
 
+// ---- tuning / measurement hooks (tools/tc_sweep.py, bench.py): not part of the product path ----
+static int g_repeat = 1;
+static unsigned long long* g_prof = nullptr;      // device buffer [512][8] set by tc_set_prof
+void tc_set_prof(void* buf) { g_prof = (unsigned long long*)buf; }                 // launches per call (amortises host planning when timing a kernel)
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+void tc_set_repeat(int n) { g_repeat = n < 1 ? 1 : n; }
+
 static int pick_bn(int Nout, int64_t mtiles) {
   // widest tile that still yields >= ~1 wave of CTAs
   int bn = Nout % 256 == 0 ? 256 : (Nout % 128 == 0 ? 128 : 64);
   while (bn > 64 && mtiles * (Nout / bn) < 120) bn /= 2;
+  const int forced = env_int("GG_TC_BN", 0);
+  if (forced > 0 && Nout % forced == 0) bn = forced;
   return bn;
 }
 
 static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* out, cudaStream_t st) {
   const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
-  p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+  // The main loop is bound by per-iteration issue latency, not by pipeline depth (tools/tc_sweep.py): when the grid
+  // exceeds one wave prefer 2 co-resident CTAs per SM (<= ~100 KB each) over deep pipelines.
+  const int budget = total_tiles > 148 ? 100 * 1024 : 200 * 1024;
+  p.stages = std::max(2, std::min(8, budget / stage_bytes));
+  const int out_bytes = TILE_M * p.BN * (p.out_bf16 ? 2 : 4);          // the epilogue stages the tile in the pipeline buffers
+  while (p.stages * stage_bytes < out_bytes) ++p.stages;
+  p.stages = std::max(1, std::min(p.stages, env_int("GG_TC_STAGES", p.stages)));
+  GG_REQUIRE(p.stages * stage_bytes >= out_bytes, GG_ERR_INVALID, "tc_pixgemm: GG_TC_STAGES too small for the output tile");
+  p.prof = g_prof;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2);
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(tc_pixgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  tc_pixgemm_kernel<<<total_tiles, TC_THREADS, smem, st>>>(p, bias, out);
-  return check_launch("tc_pixgemm");
+  int rc = GG_OK;
+  for (int r = 0; r < g_repeat && rc == GG_OK; ++r) {
+    tc_pixgemm_kernel<<<total_tiles, TC_THREADS, smem, st>>>(p, bias, out);
+    rc = check_launch("tc_pixgemm");
+  }
+  return rc;
 }
 
 int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, const float* bias, void* small, cudaStream_t st) {
@@ -521,6 +595,15 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, con
   const uint32_t bbox[3] = {64, (uint32_t)p.BN, 1};
   rc = encode_tmap_bf16(&p.bmap, w_kc, 3, bdims, bstr, bbox);
   if (rc) return rc;
+  {  // output map: the small tensor, dense
+    const uint64_t esz = d->small_dtype == GG_BF16 ? 2 : 4;
+    const uint64_t odims[5] = {(uint64_t)d->K, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->Do, (uint64_t)d->N};
+    const uint64_t ostr[4] = {(uint64_t)d->K * esz, (uint64_t)d->Wo * d->K * esz, (uint64_t)d->Ho * d->Wo * d->K * esz,
+                              (uint64_t)d->Do * d->Ho * d->Wo * d->K * esz};
+    const uint32_t obox[5] = {(uint32_t)(128 / esz), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+    rc = encode_tmap(&p.omap[0], d->small_dtype, small, 5, odims, ostr, obox);
+    if (rc) return rc;
+  }
   int t = 0;
   for (int a = 0; a < d->kd; ++a)
     for (int b = 0; b < d->kh; ++b)
@@ -582,6 +665,16 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
         mt_max = std::max(mt_max, mt);
         c.tile_begin = (int)tiles;   // scaled by ntiles_n below
         tiles += mt;
+        {  // output map of this class: the stride-s parity view of the large tensor that the class writes
+          const uint64_t esz = d->large_dtype == GG_BF16 ? 2 : 4;
+          const uint64_t base_elems = (((uint64_t)ad * d->H + ah) * d->W + aw) * d->C;
+          const uint64_t odims[5] = {(uint64_t)d->C, (uint64_t)c.Mw, (uint64_t)c.Mh, (uint64_t)c.Md, (uint64_t)d->N};
+          const uint64_t ostr[4] = {(uint64_t)d->sw * d->C * esz, (uint64_t)d->sh * d->W * d->C * esz,
+                                    (uint64_t)d->sd * d->H * d->W * d->C * esz, (uint64_t)d->D * d->H * d->W * d->C * esz};
+          const uint32_t obox[5] = {(uint32_t)(128 / esz), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+          rc = encode_tmap(&p.omap[ncls], d->large_dtype, (const char*)large + base_elems * esz, 5, odims, ostr, obox);
+          if (rc) return rc;
+        }
         p.cls[ncls++] = c;
       }
   p.BN = pick_bn(d->C, tiles);
@@ -650,8 +743,12 @@ int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, f
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2);
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  tc_wgrad_kernel<<<(unsigned)(tiles * p.splits), TC_THREADS, smem, st>>>(p, dw);
-  return check_launch("tc_wgrad");
+  int rcl = GG_OK;
+  for (int r = 0; r < g_repeat && rcl == GG_OK; ++r) {
+    tc_wgrad_kernel<<<(unsigned)(tiles * p.splits), TC_THREADS, smem, st>>>(p, dw);
+    rcl = check_launch("tc_wgrad");
+  }
+  return rcl;
 }
 
 }  // namespace gg

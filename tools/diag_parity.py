@@ -27,6 +27,8 @@ def main():
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     size, gf = (64, 64) if B >= 32 else (32, 16)
     ora = OracleDCGAN(batch_size=B, output_size=size, gf_dim=gf, df_dim=gf, seed=7, dtype=torch.float64)
+    if len(sys.argv) > 3 and sys.argv[3] == "quant":
+        ora.quant = "bf16"       # oracle with the product's bf16 quantisation points
     ops.set_precision(precision)
     ops.reset_default_store(device="cuda")
     m = DCGAN(None, batch_size=B, output_size=size, gf_dim=gf, df_dim=gf)

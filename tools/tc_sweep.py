@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Kernel-time sensitivity sweep for the tcgen05 kernels: true device time per launch (plan built once, 20
+back-to-back launches, CUDA events, warm L2) for full-size DCGAN layer shapes under GG_TC_STAGES / GG_TC_BN overrides.
+Each configuration runs in a subprocess (the overrides are read from the environment at plan time)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "gif-gan_b200")):
+    sys.path.insert(0, p)
+
+SHAPES = {   # name: N, H(large), C(large), K(small)
+    "d_h1": (128, 32, 64, 128), "d_h2": (128, 16, 128, 256), "d_h3": (128, 8, 256, 512),
+    "g_h1": (64, 8, 256, 512), "g_h2": (64, 16, 128, 256), "g_h3": (64, 32, 64, 128),
+}
+
+
+def one(shape, op, reps=20):
+    import torch
+    from collections import OrderedDict
+    from gifgan import ops, _cabi
+    N, H, C, K = SHAPES[shape]
+    g = ops._Geom(N, (1, H, H), C, (1, H // 2, H // 2), K, (1, 5, 5), (1, 2, 2), (0, 1, 1))
+    ops.set_precision("bf16", tensor_cores=True)
+    st = ops.reset_default_store(device="cuda")
+    wv = st.get_variable("w", (5, 5, C, K), lambda r, s: __import__("numpy").zeros(s, dtype="float32") + 0.01, filter_taps=25)
+    st.finalize(OrderedDict(all=[wv]))
+    large = torch.randn(N, H, H, C, device="cuda").to(torch.bfloat16)
+    small = torch.randn(N, H // 2, H // 2, K, device="cuda").to(torch.bfloat16)
+    out_l, out_s = torch.empty_like(large), torch.empty_like(small)
+    fn = {"down": lambda: ops._run_down(g, large, wv, None, torch.bfloat16, None, 0.0, 4, out=out_s),
+          "up": lambda: ops._run_up(g, small, wv, None, torch.bfloat16, None, 0.0, 4, out=out_l),
+          "wgrad": lambda: ops._run_wgrad(g, large, small, wv)}[op]
+    fn(); torch.cuda.synchronize()
+    _cabi.lib().gg_debug_set_repeat(reps)
+    best = 1e9
+    for _ in range(3):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record(); fn(); e.record(); e.synchronize()
+        best = min(best, s.elapsed_time(e) / reps)
+    _cabi.lib().gg_debug_set_repeat(1)
+    if op != "wgrad" and os.environ.get("GG_PROF"):
+        buf = torch.zeros(512 * 8, dtype=torch.int64, device="cuda")
+        _cabi.lib().gg_debug_set_prof(buf.data_ptr())
+        fn(); torch.cuda.synchronize()
+        _cabi.lib().gg_debug_set_prof(None)
+        b = buf.cpu().reshape(512, 8).double()
+        b = b[b[:, 6] > 0]
+        names = ["prodA_loop", "prodA_wait_empty", "mma_loop", "mma_wait_full", "acc_ready", "epi_done", "cta_total", "setup"]
+        print("PROF ctas=%d " % len(b) + " ".join("%s=%.0f" % (n, b[:, i].mean().item()) for i, n in enumerate(names)), flush=True)
+    import bench
+    fl = bench.conv_flops_per_image(H, C, K) * N
+    print("RESULT " + json.dumps(dict(shape=shape, op=op, us=round(best * 1e3, 2), tflops=round(fl / best / 1e9, 1),
+                                      stages=os.environ.get("GG_TC_STAGES", ""), bn=os.environ.get("GG_TC_BN", ""))), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2:
+        one(sys.argv[1], sys.argv[2])
+        sys.exit(0)
+    configs = [dict()] + [dict(GG_TC_STAGES=str(s)) for s in (2, 4)] + [dict(GG_TC_BN=str(b)) for b in (64, 128, 256)]
+    if os.environ.get("GG_PROF"):
+        configs = [dict(), dict(GG_TC_STAGES="2")]
+    for shape in (["d_h2", "g_h1", "g_h3"] if len(sys.argv) < 2 else [sys.argv[1]]):
+        for op in ("down", "up", "wgrad"):
+            for cfg in (configs if op != "wgrad" else configs[:3]):
+                env = dict(os.environ); env.update(cfg)
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), shape, op], capture_output=True, text=True, env=env, timeout=120)
+                for l in r.stdout.splitlines():
+                    if l.startswith("PROF "):
+                        print(l, flush=True)
+                lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+                print(lines[-1][7:] if lines else json.dumps(dict(shape=shape, op=op, cfg=cfg, err=(r.stderr or r.stdout)[-300:])), flush=True)
