@@ -76,13 +76,18 @@ colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_
         if (MODE == 1) dv[0] = ldf(dy + off);
       }
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        if (MODE == 0) { s0[v] += xv[v]; s1[v] = fmaf(xv[v], xv[v], s1[v]); }
-        else if (MODE == 2) { s0[v] += xv[v]; }
-        else {
-          const float xh = (xv[v] - mu[v]) * rs[v];
-          const float g = dv[v] * act_grad_from_pre(fmaf(ga[v], xh, be[v]), act, act_param);
-          s0[v] += g; s1[v] = fmaf(g, xh, s1[v]);
+      if (MODE == 1) {
+        float xh[VEC], u[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { xh[v] = (xv[v] - mu[v]) * rs[v]; u[v] = fmaf(ga[v], xh[v], be[v]); }
+        act_bwd_pre_vec<VEC>(dv, u, act, act_param);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { s0[v] += dv[v]; s1[v] = fmaf(dv[v], xh[v], s1[v]); }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          s0[v] += xv[v];
+          if (MODE == 0) s1[v] = fmaf(xv[v], xv[v], s1[v]);
         }
       }
     }
@@ -153,8 +158,9 @@ bn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows_per_g
     for (int v = 0; v < VEC; ++v) {
       const float ga = gamma ? __ldg(gamma + c + v) : 1.f, be = beta ? __ldg(beta + c + v) : 0.f;
       const float mu = __ldg(mean + (int64_t)grp * C + c + v), rs = __ldg(rstd + (int64_t)grp * C + c + v);
-      o[v] = act_fwd(fmaf((xv[v] - mu) * rs, ga, be), act, act_param);
+      o[v] = fmaf((xv[v] - mu) * rs, ga, be);
     }
+    act_fwd_vec<VEC>(o, act, act_param);
     if (VEC == 4) st4(y + off, make_float4(o[0], o[1], o[2], o[3]));
     else stf(y + off, o[0]);
   }
@@ -179,17 +185,24 @@ bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
       float4 u = ld4(dy + off); dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3] = u.w;
     } else { xv[0] = ldf(x + off); dv[0] = ldf(dy + off); }
 #pragma unroll
+    float xh[VEC], u[VEC], gar[VEC];
+#pragma unroll
     for (int v = 0; v < VEC; ++v) {
       const float ga = gamma ? __ldg(gamma + c + v) : 1.f, be = beta ? __ldg(beta + c + v) : 0.f;
       const float mu = __ldg(mean + (int64_t)grp * C + c + v), rs = __ldg(rstd + (int64_t)grp * C + c + v);
-      const float xh = (xv[v] - mu) * rs;
-      const float g = dv[v] * act_grad_from_pre(fmaf(ga, xh, be), act, act_param);
+      xh[v] = (xv[v] - mu) * rs;
+      u[v] = fmaf(ga, xh[v], be);
+      gar[v] = ga * rs;
+    }
+    act_bwd_pre_vec<VEC>(dv, u, act, act_param);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
       if (train) {
         const float sg = (float)sums[((int64_t)grp * 2 + 0) * C + c + v] * invM;
         const float sgx = (float)sums[((int64_t)grp * 2 + 1) * C + c + v] * invM;
-        o[v] = ga * rs * (g - sg - xh * sgx);
+        o[v] = gar[v] * (dv[v] - sg - xh[v] * sgx);
       } else {
-        o[v] = ga * rs * g;
+        o[v] = gar[v] * dv[v];
       }
     }
     if (VEC == 4) st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
@@ -304,8 +317,9 @@ bn_infer_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows
     for (int v = 0; v < VEC; ++v) {
       const float ga = gamma ? __ldg(gamma + c + v) : 1.f, be = beta ? __ldg(beta + c + v) : 0.f;
       const float rs = rsqrtf(__ldg(mv + c + v) + eps);
-      o[v] = act_fwd(fmaf((xv[v] - __ldg(mm + c + v)) * rs, ga, be), act, act_param);
+      o[v] = fmaf((xv[v] - __ldg(mm + c + v)) * rs, ga, be);
     }
+    act_fwd_vec<VEC>(o, act, act_param);
     if (VEC == 4) st4(y + off, make_float4(o[0], o[1], o[2], o[3]));
     else stf(y + off, o[0]);
   }

@@ -99,6 +99,44 @@ __device__ __forceinline__ float act_grad_from_pre(float u, int act, float a) {
   return 0.5f * (1.f - t * t);
 }
 
+// Vector forms: ONE warp-uniform branch per N elements (the scalar forms, inlined N times in an unrolled loop,
+// leave a branch chain per element because the tanhf/expf paths keep control flow inside the loop).
+template <int N>
+__device__ __forceinline__ void act_fwd_vec(float (&x)[N], int act, float a) {
+  if (act <= GG_ACT_LRELU) {
+    const float slope = act_slope(act, a);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = fmaxf(x[i], x[i] * slope);
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) x[i] = act_fwd(x[i], act, a);
+  }
+}
+// g[i] *= act'(u[i])  (derivative through the pre-activation)
+template <int N>
+__device__ __forceinline__ void act_bwd_pre_vec(float (&g)[N], const float (&u)[N], int act, float a) {
+  if (act <= GG_ACT_LRELU) {
+    const float slope = act_slope(act, a), at_zero = act == GG_ACT_RELU ? 0.f : 1.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] *= (u[i] > 0.f ? 1.f : (u[i] == 0.f ? at_zero : slope));
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) g[i] *= act_grad_from_pre(u[i], act, a);
+  }
+}
+// g[i] *= act'(.) evaluated from the output y[i]
+template <int N>
+__device__ __forceinline__ void act_bwd_out_vec(float (&g)[N], const float (&y)[N], int act, float a) {
+  if (act <= GG_ACT_LRELU) {
+    const float slope = act_slope(act, a), at_zero = act == GG_ACT_RELU ? 0.f : 1.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] *= (y[i] > 0.f ? 1.f : (y[i] == 0.f ? at_zero : slope));
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) g[i] *= act_grad_from_out(y[i], act, a);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

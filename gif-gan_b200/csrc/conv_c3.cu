@@ -74,10 +74,8 @@ c3_down_kernel(const float* __restrict__ large, const float* __restrict__ w, con
     for (int g = 0; g < 4; ++g) {
       float v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float b = bias ? __ldg(bias + k0 + kg * 16 + g * 4 + j) : 0.f;
-        v[j] = act_fwd(acc[g * 4 + j] + b, act, act_param);
-      }
+      for (int j = 0; j < 4; ++j) v[j] = acc[g * 4 + j] + (bias ? __ldg(bias + k0 + kg * 16 + g * 4 + j) : 0.f);
+      act_fwd_vec<4>(v, act, act_param);
       st4(dst + g * 4, make_float4(v[0], v[1], v[2], v[3]));
     }
   }
@@ -141,7 +139,10 @@ c3_up_kernel(const TSM* __restrict__ small, const float* __restrict__ w, const f
   if (i < H && j < W) {
     float* dst = large + (((int64_t)n * H + i) * W + j) * C3;
 #pragma unroll
-    for (int c = 0; c < C3; ++c) dst[c] = act_fwd(acc[c] + (bias ? __ldg(bias + c) : 0.f), act, act_param);
+    for (int c = 0; c < C3; ++c) acc[c] += (bias ? __ldg(bias + c) : 0.f);
+    act_fwd_vec<C3>(acc, act, act_param);
+#pragma unroll
+    for (int c = 0; c < C3; ++c) dst[c] = acc[c];
   }
 }
 

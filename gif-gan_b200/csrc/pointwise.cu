@@ -19,8 +19,10 @@ __global__ void act_bwd_kernel(const TY* __restrict__ y, const TD* __restrict__ 
   if (VEC) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
       const float4 a = ld4(y + i * 4), g = ld4(dy + i * 4);
-      st4(dx + i * 4, make_float4(g.x * act_grad_from_out(a.x, act, ap), g.y * act_grad_from_out(a.y, act, ap),
-                                  g.z * act_grad_from_out(a.z, act, ap), g.w * act_grad_from_out(a.w, act, ap)));
+      float gv[4] = {g.x, g.y, g.z, g.w};
+      const float yv[4] = {a.x, a.y, a.z, a.w};
+      act_bwd_out_vec<4>(gv, yv, act, ap);
+      st4(dx + i * 4, make_float4(gv[0], gv[1], gv[2], gv[3]));
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -34,7 +36,9 @@ __global__ void act_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, int
   if (VEC) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
       const float4 a = ld4(x + i * 4);
-      st4(y + i * 4, make_float4(act_fwd(a.x, act, ap), act_fwd(a.y, act, ap), act_fwd(a.z, act, ap), act_fwd(a.w, act, ap)));
+      float v[4] = {a.x, a.y, a.z, a.w};
+      act_fwd_vec<4>(v, act, ap);
+      st4(y + i * 4, make_float4(v[0], v[1], v[2], v[3]));
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) stf(y + i, act_fwd(ldf(x + i), act, ap));

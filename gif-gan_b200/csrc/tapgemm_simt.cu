@@ -193,7 +193,8 @@ pixgemm_kernel(const TA* __restrict__ A, const float* __restrict__ Wt, const flo
     TO* dst = out + ((((int64_t)nb * p.OD + od) * p.OH + oh) * p.OW + ow) * p.Nc + n;
     float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = act_fwd(acc[i][j] + bv[j], p.act, p.act_param);
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bv[j];
+    act_fwd_vec<4>(v, p.act, p.act_param);
     if (VEC_O) {
       if (n < p.Nc) st4(dst, make_float4(v[0], v[1], v[2], v[3]));
     } else {

@@ -279,11 +279,13 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       tmem_ld_wait();
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float f = __uint_as_float(r[j]);
-        if (bias != nullptr) f += __ldg(bias + n0 + c0 + j);
-        v[j] = act_fwd(f, p.act, p.act_param);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float4 b = __ldg(b4 + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
       }
+      act_fwd_vec<32>(v, p.act, p.act_param);
       if (p.out_bf16) {
         // 32 bf16 = 64 B = 4 chunks: half of the 128-byte row of column block c0/64
         const uint32_t blk = smem_base + (uint32_t)(c0 >> 6) * (TILE_M * 128u) + row_off;
