@@ -32,8 +32,10 @@ static ColGeom col_geom(int64_t rows_per_group, int C, int groups, bool vec_ok) 
   g.tx = tx;
   g.ty = BN_THREADS / tx;
   g.cblocks = ceil_div(lanes, tx);
-  int64_t want = std::max<int64_t>(1, (148 * 4) / ((int64_t)g.cblocks * groups));
-  int64_t maxr = ceil_div64(rows_per_group, (int64_t)g.ty * 4);  // >= 4 rows per thread
+  // ~2 CTAs per SM in total: every CTA ends with 2*C fp64 atomics on the same C addresses, so the tail cost grows
+  // with the CTA count while the streaming part is bandwidth-trivial at these sizes
+  int64_t want = std::max<int64_t>(1, (148 * 2) / ((int64_t)g.cblocks * groups));
+  int64_t maxr = ceil_div64(rows_per_group, (int64_t)g.ty * 8);  // >= 8 rows per thread
   g.rblocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, maxr));
   return g;
 }
@@ -246,6 +248,34 @@ using namespace gg;
 
 extern "C" size_t gg_bn_workspace_bytes(int32_t C, int32_t groups) { return (size_t)2 * C * groups * sizeof(double); }
 
+namespace gg {
+// sums[groups][2][C] += (sum x, sum x^2) per row group -- the separate statistics pass (used when the producer
+// kernel could not fuse it into its epilogue)
+int bn_accumulate_stats(const void* x, int x_dt, int64_t rows, int C, int groups, double* sums, cudaStream_t st) {
+  GG_REQUIRE(rows % groups == 0, GG_ERR_INVALID, "bn stats: rows not divisible by groups");
+  const bool vec_ok = aligned16(x);
+  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, rows / groups, C, groups, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, vec_ok, st)));
+  return check_launch("bn_stats");
+}
+}  // namespace gg
+
+static int bn_finalize_and_apply(const void* x, int32_t x_dt, void* y, int32_t y_dt, int64_t rpg, int32_t C, int32_t groups,
+                                 const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* save_mean,
+                                 float* save_rstd, float eps, float decay, int32_t act, float act_param, const double* sums,
+                                 cudaStream_t st);
+
+// Same as gg_bn_fwd_train, but the per-group (sum, sum of squares) are already in `stats` (written by
+// gg_conv_down_stats / gg_conv_up_stats): only finalize (+EMA) and the apply pass run.
+extern "C" int gg_bn_fwd_train_stats(const void* x, int32_t x_dt, void* y, int32_t y_dt, int64_t rows, int32_t C, int32_t groups,
+                                     const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* save_mean,
+                                     float* save_rstd, float eps, float decay, int32_t act, float act_param, const double* stats,
+                                     void* stream) {
+  GG_REQUIRE(x && y && save_mean && save_rstd && stats, GG_ERR_INVALID, "bn_fwd_train_stats: null pointer");
+  GG_REQUIRE(groups >= 1 && rows > 0 && rows % groups == 0, GG_ERR_INVALID, "bn_fwd_train_stats: rows not divisible by groups");
+  return bn_finalize_and_apply(x, x_dt, y, y_dt, rows / groups, C, groups, gamma, beta, moving_mean, moving_var, save_mean, save_rstd,
+                               eps, decay, act, act_param, stats, (cudaStream_t)stream);
+}
+
 extern "C" int gg_bn_fwd_train(const void* x, int32_t x_dt, void* y, int32_t y_dt, int64_t rows, int32_t C, int32_t groups,
                                const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* save_mean,
                                float* save_rstd, float eps, float decay, int32_t act, float act_param, void* ws, size_t ws_bytes,
@@ -261,8 +291,17 @@ extern "C" int gg_bn_fwd_train(const void* x, int32_t x_dt, void* y, int32_t y_d
   GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, rpg, C, groups, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, vec_ok, st)));
   int rc = check_launch("bn_stats");
   if (rc) return rc;
+  return bn_finalize_and_apply(x, x_dt, y, y_dt, rpg, C, groups, gamma, beta, moving_mean, moving_var, save_mean, save_rstd, eps, decay,
+                               act, act_param, sums, st);
+}
+
+static int bn_finalize_and_apply(const void* x, int32_t x_dt, void* y, int32_t y_dt, int64_t rpg, int32_t C, int32_t groups,
+                                 const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* save_mean,
+                                 float* save_rstd, float eps, float decay, int32_t act, float act_param, const double* sums,
+                                 cudaStream_t st) {
+  const bool vec_ok = aligned16(x) && aligned16(y);
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, rpg, C, groups, eps, decay, moving_mean, moving_var, save_mean, save_rstd);
-  rc = check_launch("bn_finalize");
+  int rc = check_launch("bn_finalize");
   if (rc) return rc;
   const int vec = (vec_ok && C % 4 == 0) ? 4 : 1;
   const int lanes = C / vec;

@@ -33,8 +33,10 @@ int c3_conv_down(const gg_conv_desc*, const float*, const float*, const float*, 
 int c3_conv_up(const gg_conv_desc*, const void*, const float*, const float*, float*, cudaStream_t);
 int c3_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t);
 // tc_tapgemm.cu
-int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
-int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
+int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
+// bn.cu
+int bn_accumulate_stats(const void* x, int x_dt, int64_t rows, int C, int groups, double* sums, cudaStream_t st);
 int tc_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStream_t);
 void tc_set_repeat(int);
 void tc_set_prof(void*);
@@ -76,6 +78,31 @@ extern "C" int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const voi
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
   if (c3_applicable(d)) return c3_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream);
   return simt_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
+}
+
+// conv + batch statistics of its (pre-norm) output: stats[groups][2][channels] += (sum, sum of squares) per row group.
+// On the tensor-core path the statistics come out of the GEMM epilogue; otherwise a separate coalesced pass runs.
+extern "C" int gg_conv_down_stats(const gg_conv_desc* d, const void* large, const void* w, const float* bias, void* small,
+                                  double* stats, int32_t groups, void* stream) {
+  GG_REQUIRE(d && large && w && small && stats && groups >= 1, GG_ERR_INVALID, "conv_down_stats: bad argument");
+  int fused = 0;
+  int rc;
+  if (d->flags & GG_CONV_TENSOR_CORE) rc = tc_conv_down(d, large, w, bias, small, (cudaStream_t)stream, stats, groups, &fused);
+  else rc = gg_conv_down(d, large, w, bias, small, stream);
+  if (rc || fused) return rc;
+  const int64_t rows = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+  return bn_accumulate_stats(small, d->small_dtype, rows, d->K, groups, stats, (cudaStream_t)stream);
+}
+extern "C" int gg_conv_up_stats(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large,
+                                double* stats, int32_t groups, void* stream) {
+  GG_REQUIRE(d && large && w && small && stats && groups >= 1, GG_ERR_INVALID, "conv_up_stats: bad argument");
+  int fused = 0;
+  int rc;
+  if (d->flags & GG_CONV_TENSOR_CORE) rc = tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream, stats, groups, &fused);
+  else rc = gg_conv_up(d, small, w, bias, large, stream);
+  if (rc || fused) return rc;
+  const int64_t rows = (int64_t)d->N * d->D * d->H * d->W;
+  return bn_accumulate_stats(large, d->large_dtype, rows, d->C, groups, stats, (cudaStream_t)stream);
 }
 
 static gg_conv_desc no_act(const gg_conv_desc* d) { gg_conv_desc c = *d; c.act = GG_ACT_NONE; return c; }

@@ -114,6 +114,8 @@ struct TcPixParams {
   int out_bf16;
   int stages;
   unsigned long long* prof;   // optional per-CTA clock64 breakdown (tools/tc_sweep.py --prof), 8 slots per CTA
+  double* stats;              // optional fused batch-norm statistics [groups][2][Nout] (fp32 output only)
+  int stats_groups;
   TcClass cls[TC_MAX_CLASSES];
   TcTap taps[TC_MAX_TAPS];
 };
@@ -262,7 +264,11 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     const int q = warp & 3;
     const int row = q * 32 + lane;                 // accumulator row = pixel within the tile
     const int iw = row % p.bw, ih = (row / p.bw) % p.bh, id = (row / (p.bw * p.bh)) % p.bd, in = row / (p.bw * p.bh * p.bd);
-    (void)iw; (void)ih; (void)id; (void)in;
+    // rows of a partial tile that fall outside the M grid must not enter the fused batch statistics
+    const bool row_valid = (mw0 + iw) < C.Mw && (mh0 + ih) < C.Mh && (md0 + id) < C.Md && (mn0 + in) < p.Mn;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, row_valid);
+    const uint32_t mask_smem = bar_base + 8u * (2 * p.stages + 2);        // 4 x u32 after the barriers
+    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(mask_smem + 4u * q), "r"(vmask) : "memory");
     if (lane == 0) mbar_wait(tmem_full_bar, 0);   // one polling lane per warp: the spin must not steal issue slots
     __syncwarp();                                 // from the producer / MMA threads that share these schedulers
     tc_fence_after();
@@ -314,8 +320,35 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       for (int b = 0; b < nblk; ++b)
         tma_store_5d(&p.omap[ci], smem_base + (uint32_t)b * (TILE_M * 128u), n0 + b * cstep, mw0, mh0, md0, mn0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after this
     }
+    if (p.stats != nullptr) {
+      // Fused batch-norm statistics (tf.nn.moments of the pre-norm tensor): the fp32 tile is in shared memory;
+      // epilogue thread t sums column t over the tile's valid rows (a warp reads 32 consecutive floats of one
+      // swizzled row per step: conflict-free) and adds (sum, sum of squares) to the fp64 accumulators of its group.
+      uint32_t m[4];
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(mask_smem));
+      const int grp = (int)(((long long)mn0 * p.stats_groups) / p.Mn);
+      for (int col = (warp - 2) * 32 + lane; col < p.BN; col += 128) {
+        const uint32_t base = smem_base + (uint32_t)(col >> 5) * (TILE_M * 128u) + (uint32_t)((col & 3) << 2);
+        const uint32_t ch = (uint32_t)((col & 31) >> 2);
+        float s = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+          const uint32_t mrow = m[w4];
+#pragma unroll 8
+          for (int b = 0; b < 32; ++b) {
+            const int r = w4 * 32 + b;
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (uint32_t)r * 128u + ((ch ^ (uint32_t)(r & 7)) << 4)));
+            if ((mrow >> b) & 1u) { s += v; s2 = fmaf(v, v, s2); }
+          }
+        }
+        double* dst = p.stats + ((long long)grp * 2) * p.Nout + n0 + col;
+        atomicAdd(dst, (double)s);
+        atomicAdd(dst + p.Nout, (double)s2);
+      }
+    }
+    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after this
     tc_fence_before();
     if (prof && warp == 2 && lane == 0) { prof[4] = (unsigned long long)(t_acc - t_setup); prof[5] = (unsigned long long)(clock64() - t_setup); }
   }
@@ -566,7 +599,7 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   p.stages = std::max(1, std::min(p.stages, env_int("GG_TC_STAGES", p.stages)));
   GG_REQUIRE(p.stages * stage_bytes >= out_bytes, GG_ERR_INVALID, "tc_pixgemm: GG_TC_STAGES too small for the output tile");
   p.prof = g_prof;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2) + 16;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(tc_pixgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   int rc = GG_OK;
@@ -577,7 +610,10 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   return rc;
 }
 
-int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, const float* bias, void* small, cudaStream_t st) {
+// stats != nullptr: also accumulate per-channel (sum, sum of squares) of the fp32 output into stats[groups][2][channels].
+// *fused is set to 1 when the kernel did it (otherwise the caller runs a separate statistics pass).
+int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, const float* bias, void* small, cudaStream_t st,
+                 double* stats = nullptr, int groups = 1, int* fused = nullptr) {
   int rc = check_tc(d, large, w_kc, true, false);
   if (rc) return rc;
   TcPixParams p;
@@ -622,10 +658,15 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, con
   p.R = d->C; p.Nout = d->K; p.Mn = d->N;
   p.OD = d->Do; p.OH = d->Ho; p.OW = d->Wo; p.osd = p.osh = p.osw = 1;
   p.act = d->act; p.act_param = d->act_param; p.out_bf16 = (d->small_dtype == GG_BF16);
+  if (stats != nullptr && d->small_dtype == GG_F32 && groups >= 1 && d->N % groups == 0 && (d->N / groups) % p.bn == 0) {
+    p.stats = stats; p.stats_groups = groups;
+    if (fused) *fused = 1;
+  }
   return launch_pix(p, (int)(mtiles * p.ntiles_n), bias, small, st);
 }
 
-int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const float* bias, void* large, cudaStream_t st) {
+int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const float* bias, void* large, cudaStream_t st,
+               double* stats = nullptr, int groups = 1, int* fused = nullptr) {
   int rc = check_tc(d, small, w_ck, false, true);
   if (rc) return rc;
   TcPixParams p;
@@ -695,6 +736,10 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
   p.R = d->K; p.Nout = d->C; p.Mn = d->N;
   p.OD = d->D; p.OH = d->H; p.OW = d->W; p.osd = d->sd; p.osh = d->sh; p.osw = d->sw;
   p.act = d->act; p.act_param = d->act_param; p.out_bf16 = (d->large_dtype == GG_BF16);
+  if (stats != nullptr && d->large_dtype == GG_F32 && groups >= 1 && d->N % groups == 0 && (d->N / groups) % p.bn == 0) {
+    p.stats = stats; p.stats_groups = groups;
+    if (fused) *fused = 1;
+  }
   return launch_pix(p, (int)(tiles * p.ntiles_n), bias, large, st);
 }
 

@@ -310,28 +310,100 @@ class _Geom:
         return (self.N, self.Ho, self.Wo, self.K) if ndim == 4 else (self.N, self.Do, self.Ho, self.Wo, self.K)
 
 
-def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None):
+def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None, stats=None, groups=1):
+    """stats: optional fp64 [groups, 2, K] accumulator for the batch-norm statistics of the output."""
     small = out if out is not None else torch.empty(g.small_shape(ndim), dtype=out_dtype, device=large.device)
     tc = _tc_ok(g.C, g.K, large)
     d = g.desc(dt(large), dt(small), act, act_param, tc)
     w = wvar.packed()[1] if tc else wvar.data
-    check(cabi.lib().gg_conv_down(ctypes.byref(d), ptr(large), ptr(w), ptr(bias), ptr(small), stream()), "gg_conv_down")
+    if stats is not None:
+        check(cabi.lib().gg_conv_down_stats(ctypes.byref(d), ptr(large), ptr(w), ptr(bias), ptr(small), ptr(stats), groups, stream()),
+              "gg_conv_down_stats")
+    else:
+        check(cabi.lib().gg_conv_down(ctypes.byref(d), ptr(large), ptr(w), ptr(bias), ptr(small), stream()), "gg_conv_down")
     return small
 
 
-def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None):
+def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None, stats=None, groups=1):
     large = out if out is not None else torch.empty(g.large_shape(ndim), dtype=out_dtype, device=small.device)
     tc = _tc_ok(g.C, g.K, small)
     d = g.desc(dt(large), dt(small), act, act_param, tc)
     w = wvar.packed()[0] if tc else wvar.data
-    check(cabi.lib().gg_conv_up(ctypes.byref(d), ptr(small), ptr(w), ptr(bias), ptr(large), stream()), "gg_conv_up")
+    if stats is not None:
+        check(cabi.lib().gg_conv_up_stats(ctypes.byref(d), ptr(small), ptr(w), ptr(bias), ptr(large), ptr(stats), groups, stream()),
+              "gg_conv_up_stats")
+    else:
+        check(cabi.lib().gg_conv_up(ctypes.byref(d), ptr(small), ptr(w), ptr(bias), ptr(large), stream()), "gg_conv_up")
     return large
+
+
+# Filter gradients are leaves of the backward pass: nothing downstream of them runs before the optimiser.  They are
+# issued on a side stream so that they overlap with the activation-gradient chain (under CUDA-graph capture the
+# fork/join becomes parallel branches of the graph).  join_side() is the join point (optimiser / all-reduce).
+OVERLAP_WGRAD = False      # enabled inside `with overlap_wgrad():` (the model's update functions)
+_SIDE = {}
+
+
+@contextlib.contextmanager
+def overlap_wgrad(enable=True):
+    """Region in which filter-gradient kernels go to the side stream; joined on exit."""
+    global OVERLAP_WGRAD
+    old = OVERLAP_WGRAD
+    OVERLAP_WGRAD = bool(enable) and torch.cuda.is_available()
+    try:
+        yield
+    finally:
+        OVERLAP_WGRAD = old
+        join_side()
+
+
+def _side_stream():
+    dev = torch.cuda.current_device()
+    s = _SIDE.get(dev)
+    if s is None:
+        s = _SIDE[dev] = dict(stream=torch.cuda.Stream(), dirty=False)
+    return s
+
+
+class _on_side:
+    """with _on_side(tensors...): work enqueued inside runs on the side stream, ordered after everything already
+    enqueued on the current stream."""
+
+    def __init__(self, *tensors):
+        self.tensors = tensors
+
+    def __enter__(self):
+        if not OVERLAP_WGRAD:
+            return self
+        s = _side_stream()
+        s["stream"].wait_stream(torch.cuda.current_stream())
+        s["dirty"] = True
+        for t in self.tensors:
+            if t is not None:
+                t.record_stream(s["stream"])
+        self.ctx = torch.cuda.stream(s["stream"])
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if OVERLAP_WGRAD:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_side():
+    """Make the current stream wait for all side-stream work (call before consuming filter gradients)."""
+    s = _SIDE.get(torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if s is not None and s["dirty"]:
+        torch.cuda.current_stream().wait_stream(s["stream"])
+        s["dirty"] = False
 
 
 def _run_wgrad(g: _Geom, large, small, wvar: Var):
     tc = _tc_ok(g.C, g.K, large, small)
     d = g.desc(dt(large), dt(small), None, 0.0, tc)
-    check(cabi.lib().gg_conv_wgrad(ctypes.byref(d), ptr(large), ptr(small), ptr(wvar.grad), stream()), "gg_conv_wgrad")
+    with _on_side(large, small):
+        check(cabi.lib().gg_conv_wgrad(ctypes.byref(d), ptr(large), ptr(small), ptr(wvar.grad), stream()), "gg_conv_wgrad")
 
 
 def _act_bwd(y, dy, act, act_param):
@@ -601,9 +673,11 @@ class _ConvProducer:
     def out_shape(self):
         return self.geom.small_shape(self.ndim) if self.direction == "down" else self.geom.large_shape(self.ndim)
 
-    def fwd(self, x, b):
+    fuses_stats = True      # batch statistics come out of the conv call (GEMM epilogue on the tensor-core path)
+
+    def fwd(self, x, b, stats=None, groups=1):
         run = _run_down if self.direction == "down" else _run_up
-        return run(self.geom, x, self.wvar, b, torch.float32, None, 0.0, self.ndim)
+        return run(self.geom, x, self.wvar, b, torch.float32, None, 0.0, self.ndim, stats=stats, groups=groups)
 
     def wgrad(self, x, dpre):
         if self.direction == "down":
@@ -620,10 +694,12 @@ class _LinearProducer:
     def __init__(self, mvar, bvar, rows, out_dim):
         self.wvar, self.bvar, self.rows, self.out_dim = mvar, bvar, rows, out_dim
 
+    fuses_stats = False
+
     def out_shape(self):
         return (self.rows, self.out_dim)
 
-    def fwd(self, x, b):
+    def fwd(self, x, b, stats=None, groups=1):
         rows, in_dim = x.shape
         y = torch.empty((rows, self.out_dim), dtype=torch.float32, device=x.device)
         check(cabi.lib().gg_linear_fwd(ptr(x), dt(x), ptr(self.wvar.data), ptr(b), ptr(y), dt(y), rows, in_dim, self.out_dim, 0, 0.0,
@@ -655,14 +731,20 @@ class _FusedBN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, prod, bn, train, act, act_param, out_dtype, groups, Cc):
         L = cabi.lib()
-        pre = prod.fwd(x, b)
+        fused_stats = train and prod.fuses_stats and Cc == prod.out_shape()[-1]
+        stats = torch.zeros((groups, 2, Cc), dtype=torch.float64, device=x.device) if fused_stats else None
+        pre = prod.fwd(x, b, stats=stats, groups=groups)
         rows = pre.numel() // Cc
         y = torch.empty(pre.shape, dtype=out_dtype, device=x.device)
         save_mean = torch.empty((groups, Cc), dtype=torch.float32, device=x.device)
         save_rstd = torch.empty((groups, Cc), dtype=torch.float32, device=x.device)
         mm = bn.moving_mean.data if bn.moving_mean is not None else None
         mv = bn.moving_variance.data if bn.moving_variance is not None else None
-        if train:
+        if fused_stats:
+            check(L.gg_bn_fwd_train_stats(ptr(pre), dt(pre), ptr(y), dt(y), rows, Cc, groups, ptr(gamma), ptr(beta), ptr(mm), ptr(mv),
+                                          ptr(save_mean), ptr(save_rstd), bn.epsilon, bn.momentum, ACT[act], float(act_param),
+                                          ptr(stats), stream()), "gg_bn_fwd_train_stats")
+        elif train:
             nbytes = L.gg_bn_workspace_bytes(Cc, groups)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             check(L.gg_bn_fwd_train(ptr(pre), dt(pre), ptr(y), dt(y), rows, Cc, groups, ptr(gamma), ptr(beta), ptr(mm), ptr(mv),

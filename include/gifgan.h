@@ -100,6 +100,15 @@ int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const fl
 int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw,
                   void* stream);
 
+/* conv + batch statistics of its pre-norm output in one call (what `batch_norm(conv2d(...))` needs, ops.py:10-24 after
+ * ops.py:57/86): stats[groups][2][channels] (fp64, zero-initialised by the caller) += per-channel (sum, sum of squares)
+ * over each of `groups` equal blocks of the batch.  On the tensor-core path the sums are produced in the GEMM epilogue
+ * (the tile is already in shared memory); otherwise by a coalesced pass.  Consumed by gg_bn_fwd_train_stats.            */
+int gg_conv_down_stats(const gg_conv_desc* d, const void* large, const void* w, const float* bias, void* small,
+                       double* stats, int32_t groups, void* stream);
+int gg_conv_up_stats(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large,
+                     double* stats, int32_t groups, void* stream);
+
 /* Reference-named aliases (same arguments, fixed direction). */
 int gg_conv2d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* stream);     /* ops.py:57  */
 int gg_conv2d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* stream);                   /* grad of ops.py:57 wrt input_ */
@@ -136,6 +145,11 @@ int gg_bn_fwd_train(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, in
                     const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                     float* save_mean, float* save_rstd, float eps, float decay, int32_t act, float act_param,
                     void* ws, size_t ws_bytes, void* stream);
+/* gg_bn_fwd_train without the statistics pass: `stats` = the [groups][2][C] sums written by gg_conv_*_stats */
+int gg_bn_fwd_train_stats(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t rows, int32_t C, int32_t groups,
+                          const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                          float* save_mean, float* save_rstd, float eps, float decay, int32_t act, float act_param,
+                          const double* stats, void* stream);
 int gg_bn_fwd_infer(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t rows, int32_t C,
                     const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
                     float eps, int32_t act, float act_param, void* stream);
