@@ -171,23 +171,32 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def time_kernel(fn, flush, reps=10):
-    """Average device time (ms) of fn() alone, L2 flushed before every launch, CUDA events on the current stream."""
+def time_kernel(fn, flush, reps=5, launches=10):
+    """Average device time (ms) of ONE launch of the kernel behind fn(), CUDA events on the launching stream.
+    The host-side planning of a conv call (tensor-map encoding, ctypes) costs more than the kernel itself at these
+    sizes, so each fn() enqueues `launches` back-to-back launches (gg_debug_set_repeat: plan once, launch n times);
+    L2 is flushed before every timed batch (operands of one layer, 4-34 MB, then stay L2-resident across the batch,
+    as they are inside the real step where the producer kernel has just written them)."""
+    from gifgan import _cabi
     fn()
     torch.cuda.synchronize()
+    _cabi.lib().gg_debug_set_repeat(launches)
     tot = 0.0
-    for _ in range(reps):
-        flush.zero_()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        fn()
-        e.record()
-        e.synchronize()
-        tot += s.elapsed_time(e)
-    return tot / reps
+    try:
+        for _ in range(reps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            e.synchronize()
+            tot += s.elapsed_time(e)
+    finally:
+        _cabi.lib().gg_debug_set_repeat(1)
+    return tot / reps / launches
 
 
-def layer_rooflines(model, batch, precision, flush):
+def layer_rooflines(model, batch, precision, flush, reps=5, launches=10):
     """Time each conv layer's three kernels in isolation at the step's shapes; returns rows sorted by their
     share of the step (time x launches per step)."""
     import ctypes
@@ -216,7 +225,7 @@ def layer_rooflines(model, batch, precision, flush):
                     continue
                 if is_d and kind == "up" and C == 3 and B_ == 2 * batch:
                     continue   # d_h0 dgrad is not needed in the D update
-                ms = time_kernel(fns[kind], flush)
+                ms = time_kernel(fns[kind], flush, reps, launches)
                 tc = ops._tc_ok(C, K, large, small)
                 rows.append(dict(kernel=f"{name}.{kind}[B={B_}]", ms=ms, flops=fl, tflops=fl / ms / 1e9, uses=n_use,
                                  path="tcgen05" if tc else "simt", share_ms=ms * n_use))

@@ -49,7 +49,9 @@ extern "C" const char* gg_last_error(void) { return g_err; }
 extern "C" uint64_t gg_launch_count(void) { return g_launches.load(); }
 
 // measurement hook: every tensor-core conv call launches its kernel n times (host planning amortised)
-extern "C" void gg_debug_set_repeat(int n) { tc_set_repeat(n); }
+static int g_cabi_repeat = 1;
+extern "C" void gg_debug_set_repeat(int n) { g_cabi_repeat = n < 1 ? 1 : n; tc_set_repeat(n); }
+#define GG_REPEAT(call) do { int rc_ = GG_OK; for (int r_ = 0; r_ < g_cabi_repeat && rc_ == GG_OK; ++r_) rc_ = (call); return rc_; } while (0)
 // measurement hook: device buffer of 512 x 8 uint64 receiving a per-CTA clock64 breakdown of tc_pixgemm (NULL = off)
 extern "C" void gg_debug_set_prof(void* buf) { tc_set_prof(buf); }
 
@@ -64,20 +66,20 @@ extern "C" int gg_device_arch(void) {
 extern "C" int gg_conv_down(const gg_conv_desc* d, const void* large, const void* w, const float* bias, void* small, void* stream) {
   GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_down: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_down(d, large, w, bias, small, (cudaStream_t)stream);
-  if (c3_applicable(d)) return c3_conv_down(d, (const float*)large, (const float*)w, bias, small, (cudaStream_t)stream);
-  return simt_conv_down(d, large, (const float*)w, bias, small, (cudaStream_t)stream);
+  if (c3_applicable(d)) GG_REPEAT(c3_conv_down(d, (const float*)large, (const float*)w, bias, small, (cudaStream_t)stream));
+  GG_REPEAT(simt_conv_down(d, large, (const float*)w, bias, small, (cudaStream_t)stream));
 }
 extern "C" int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large, void* stream) {
   GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_up: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream);
-  if (c3_applicable(d)) return c3_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream);
-  return simt_conv_up(d, small, (const float*)w, bias, large, (cudaStream_t)stream);
+  if (c3_applicable(d)) GG_REPEAT(c3_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream));
+  GG_REPEAT(simt_conv_up(d, small, (const float*)w, bias, large, (cudaStream_t)stream));
 }
 extern "C" int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw, void* stream) {
   GG_REQUIRE(d && large && dw && small, GG_ERR_INVALID, "conv_wgrad: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
-  if (c3_applicable(d)) return c3_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream);
-  return simt_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
+  if (c3_applicable(d)) GG_REPEAT(c3_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream));
+  GG_REPEAT(simt_conv_wgrad(d, large, small, dw, (cudaStream_t)stream));
 }
 
 // conv + batch statistics of its (pre-norm) output: stats[groups][2][channels] += (sum, sum of squares) per row group.

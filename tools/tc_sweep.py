@@ -14,6 +14,7 @@ for p in (ROOT, os.path.join(ROOT, "gif-gan_b200")):
 SHAPES = {   # name: N, H(large), C(large), K(small)
     "d_h1": (128, 32, 64, 128), "d_h2": (128, 16, 128, 256), "d_h3": (128, 8, 256, 512),
     "g_h1": (64, 8, 256, 512), "g_h2": (64, 16, 128, 256), "g_h3": (64, 32, 64, 128),
+    "b256_h1": (256, 8, 256, 512), "b256_h2": (256, 16, 128, 256), "b256_h3": (256, 32, 64, 128),
 }
 
 
@@ -63,8 +64,9 @@ if __name__ == "__main__":
         sys.exit(0)
     configs = [dict()] + [dict(GG_TC_STAGES=str(s)) for s in (2, 4)] + [dict(GG_TC_BN=str(b)) for b in (64, 128, 256)]
     if os.environ.get("GG_PROF"):
-        configs = [dict(), dict(GG_TC_STAGES="2")]
-    for shape in (["d_h2", "g_h1", "g_h3"] if len(sys.argv) < 2 else [sys.argv[1]]):
+        configs = [dict()]
+    default_shapes = list(SHAPES) if os.environ.get("GG_PROF") else ["d_h2", "g_h1", "g_h3"]
+    for shape in (default_shapes if len(sys.argv) < 2 else [sys.argv[1]]):
         for op in ("down", "up", "wgrad"):
             for cfg in (configs if op != "wgrad" else configs[:3]):
                 env = dict(os.environ); env.update(cfg)
