@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_per_group, int C,
               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
               const float* __restrict__ rstd, int act, float act_param, double* __restrict__ sums, int tx_dim) {
+  pdl_grid_sync();
   const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
   const int grp = blockIdx.z;
   const int c = (blockIdx.y * tx_dim + tx) * VEC;
@@ -114,6 +115,7 @@ colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t rows_per_group, int C, int groups, float eps,
                                    float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var,
                                    float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mm = moving_mean ? moving_mean[c] : 0.f, mv = moving_var ? moving_var[c] : 0.f;
@@ -135,6 +137,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t rows
 
 __global__ void bn_infer_stats_kernel(const float* __restrict__ mm, const float* __restrict__ mv, float eps, int C,
                                       float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   save_mean[c] = mm[c];
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows_per_group, int C, int lanes,
                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                 const float* __restrict__ rstd, int act, float act_param) {
+  pdl_grid_sync();
   const int grp = blockIdx.z;
   const int64_t total = rows_per_group * lanes;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __restrict__ dx, int64_t rows_per_group, int C,
                     int lanes, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const double* __restrict__ sums, int act, float act_param, int train) {
+  pdl_grid_sync();
   const int grp = blockIdx.z;
   const int64_t total = rows_per_group * lanes;
   const float invM = 1.f / (float)rows_per_group;
@@ -214,6 +219,7 @@ bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
 
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, int groups, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double a = 0.0, b = 0.0;
@@ -223,6 +229,7 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, int
 }
 
 __global__ void add_colsum_kernel(const double* __restrict__ sums, int C, float* __restrict__ db) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) db[c] += (float)sums[c];
 }
@@ -234,9 +241,9 @@ static void launch_colsum(const void* x, const void* dy, int64_t rpg, int C, int
   ColGeom g = col_geom(rpg, C, groups, vec_ok);
   dim3 grid(g.rblocks, g.cblocks, groups);
   if (g.vec == 4)
-    colsum_kernel<TX, TD, 4, MODE><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
+    Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 4, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
   else
-    colsum_kernel<TX, TD, 1, MODE><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
+    Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 1, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
 }
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
@@ -300,7 +307,7 @@ static int bn_finalize_and_apply(const void* x, int32_t x_dt, void* y, int32_t y
                                  float* save_rstd, float eps, float decay, int32_t act, float act_param, const double* sums,
                                  cudaStream_t st) {
   const bool vec_ok = aligned16(x) && aligned16(y);
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, rpg, C, groups, eps, decay, moving_mean, moving_var, save_mean, save_rstd);
+  Launch(ceil_div(C, 128), 128, 0, st)(bn_finalize_kernel, sums, rpg, C, groups, eps, decay, moving_mean, moving_var, save_mean, save_rstd);
   int rc = check_launch("bn_finalize");
   if (rc) return rc;
   const int vec = (vec_ok && C % 4 == 0) ? 4 : 1;
@@ -308,8 +315,8 @@ static int bn_finalize_and_apply(const void* x, int32_t x_dt, void* y, int32_t y
   dim3 grid(apply_blocks(rpg * lanes), 1, groups);
 #define GG_APPLY(TX, TY)                                                                                              \
   do {                                                                                                                \
-    if (vec == 4) bn_apply_kernel<TX, TY, 4><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (TY*)y, rpg, C, lanes, gamma, beta, save_mean, save_rstd, act, act_param); \
-    else bn_apply_kernel<TX, TY, 1><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (TY*)y, rpg, C, lanes, gamma, beta, save_mean, save_rstd, act, act_param);          \
+    if (vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_apply_kernel<TX, TY, 4>, (const TX*)x, (TY*)y, rpg, C, lanes, gamma, beta, save_mean, save_rstd, act, act_param); \
+    else Launch(grid, BN_THREADS, 0, st)(bn_apply_kernel<TX, TY, 1>, (const TX*)x, (TY*)y, rpg, C, lanes, gamma, beta, save_mean, save_rstd, act, act_param);          \
   } while (0)
   if (x_dt == GG_F32 && y_dt == GG_F32) GG_APPLY(float, float);
   else if (x_dt == GG_F32) GG_APPLY(float, bf16);
@@ -321,7 +328,7 @@ static int bn_finalize_and_apply(const void* x, int32_t x_dt, void* y, int32_t y
 extern "C" int gg_bn_infer_stats(const float* moving_mean, const float* moving_var, float eps, int32_t C, float* save_mean,
                                  float* save_rstd, void* stream) {
   GG_REQUIRE(moving_mean && moving_var && save_mean && save_rstd, GG_ERR_INVALID, "bn_infer_stats: null pointer");
-  bn_infer_stats_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(moving_mean, moving_var, eps, C, save_mean, save_rstd);
+  Launch(ceil_div(C, 128), 128, 0, (cudaStream_t)stream)(bn_infer_stats_kernel, moving_mean, moving_var, eps, C, save_mean, save_rstd);
   return check_launch("bn_infer_stats");
 }
 
@@ -344,6 +351,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 bn_infer_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows, int C, int lanes, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ mm, const float* __restrict__ mv, float eps, int act,
                       float act_param) {
+  pdl_grid_sync();
   const int64_t total = rows * lanes;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / lanes;
@@ -373,8 +381,8 @@ int bn_infer_apply(const void* x, int x_dt, void* y, int y_dt, int64_t rows, int
   dim3 grid(apply_blocks(rows * lanes));
 #define GG_IAPPLY(TX, TY)                                                                                             \
   do {                                                                                                                \
-    if (vec == 4) bn_infer_apply_kernel<TX, TY, 4><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (TY*)y, rows, C, lanes, gamma, beta, mm, mv, eps, act, act_param); \
-    else bn_infer_apply_kernel<TX, TY, 1><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (TY*)y, rows, C, lanes, gamma, beta, mm, mv, eps, act, act_param);          \
+    if (vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_infer_apply_kernel<TX, TY, 4>, (const TX*)x, (TY*)y, rows, C, lanes, gamma, beta, mm, mv, eps, act, act_param); \
+    else Launch(grid, BN_THREADS, 0, st)(bn_infer_apply_kernel<TX, TY, 1>, (const TX*)x, (TY*)y, rows, C, lanes, gamma, beta, mm, mv, eps, act, act_param);          \
   } while (0)
   if (x_dt == GG_F32 && y_dt == GG_F32) GG_IAPPLY(float, float);
   else if (x_dt == GG_F32) GG_IAPPLY(float, bf16);
@@ -407,7 +415,7 @@ extern "C" int gg_bn_bwd(const void* x, int32_t x_dt, const void* dy, int32_t dy
     rc = check_launch("bn_bwd_reduce");
     if (rc) return rc;
     if (dgamma || dbeta) {
-      bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, C, groups, dgamma, dbeta);
+      Launch(ceil_div(C, 128), 128, 0, st)(bn_param_grad_kernel, sums, C, groups, dgamma, dbeta);
       rc = check_launch("bn_param_grad");
       if (rc) return rc;
     }
@@ -417,8 +425,8 @@ extern "C" int gg_bn_bwd(const void* x, int32_t x_dt, const void* dy, int32_t dy
   dim3 grid(apply_blocks(rpg * lanes), 1, groups);
 #define GG_BA(TX, TD, TO)                                                                                                          \
   do {                                                                                                                             \
-    if (vec == 4) bn_bwd_apply_kernel<TX, TD, TO, 4><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, lanes, gamma, beta, save_mean, save_rstd, sums, act, act_param, train); \
-    else bn_bwd_apply_kernel<TX, TD, TO, 1><<<grid, BN_THREADS, 0, st>>>((const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, lanes, gamma, beta, save_mean, save_rstd, sums, act, act_param, train);          \
+    if (vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 4>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, lanes, gamma, beta, save_mean, save_rstd, sums, act, act_param, train); \
+    else Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 1>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, lanes, gamma, beta, save_mean, save_rstd, sums, act, act_param, train);          \
   } while (0)
   const int key = (x_dt == GG_BF16 ? 4 : 0) | (dy_dt == GG_BF16 ? 2 : 0) | (dx_dt == GG_BF16 ? 1 : 0);
   switch (key) {
@@ -447,6 +455,7 @@ namespace gg {
 template <typename TD, int VEC>
 __global__ void __launch_bounds__(BN_THREADS)
 bias_grad_kernel(const TD* __restrict__ dy, float* __restrict__ db, int64_t rows, int C, int tx_dim) {
+  pdl_grid_sync();
   const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
   const int c = (blockIdx.y * tx_dim + tx) * VEC;
   float s[VEC];
@@ -477,11 +486,11 @@ int bias_grad_impl(const void* dy, int dy_dt, float* db, int64_t rows, int C, cu
   ColGeom g = col_geom(rows, C, 1, aligned16(dy));
   dim3 grid(g.rblocks, g.cblocks, 1);
   if (dy_dt == GG_F32) {
-    if (g.vec == 4) bias_grad_kernel<float, 4><<<grid, BN_THREADS, 0, st>>>((const float*)dy, db, rows, C, g.tx);
-    else bias_grad_kernel<float, 1><<<grid, BN_THREADS, 0, st>>>((const float*)dy, db, rows, C, g.tx);
+    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bias_grad_kernel<float, 4>, (const float*)dy, db, rows, C, g.tx);
+    else Launch(grid, BN_THREADS, 0, st)(bias_grad_kernel<float, 1>, (const float*)dy, db, rows, C, g.tx);
   } else {
-    if (g.vec == 4) bias_grad_kernel<bf16, 4><<<grid, BN_THREADS, 0, st>>>((const bf16*)dy, db, rows, C, g.tx);
-    else bias_grad_kernel<bf16, 1><<<grid, BN_THREADS, 0, st>>>((const bf16*)dy, db, rows, C, g.tx);
+    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bias_grad_kernel<bf16, 4>, (const bf16*)dy, db, rows, C, g.tx);
+    else Launch(grid, BN_THREADS, 0, st)(bias_grad_kernel<bf16, 1>, (const bf16*)dy, db, rows, C, g.tx);
   }
   return check_launch("bias_grad");
 }
@@ -489,6 +498,7 @@ int bias_grad_impl(const void* dy, int dy_dt, float* db, int64_t rows, int C, cu
 // ops.get_std (ops.py:125-128): column statistics over the batch axis, then mean over features.
 namespace gg {
 __global__ void get_std_final_kernel(const double* __restrict__ sums, int64_t B, int64_t F, float* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ double red[256];
   double acc = 0.0;
   for (int64_t f = threadIdx.x; f < F; f += blockDim.x) {
@@ -515,6 +525,6 @@ extern "C" int gg_get_std(const void* x, int32_t x_dt, int64_t B, int64_t F, flo
   GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, B, (int)F, 1, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, aligned16(x), st)));
   int rc = check_launch("get_std_stats");
   if (rc) return rc;
-  get_std_final_kernel<<<1, 256, 0, st>>>(sums, B, F, out);
+  Launch(1, 256, 0, st)(get_std_final_kernel, sums, B, F, out);
   return check_launch("get_std_final");
 }

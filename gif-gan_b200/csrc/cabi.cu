@@ -1,6 +1,7 @@
 // C-ABI entry points of libgifgan.so (declared in include/gifgan.h): error plumbing and
 // dispatch between the SIMT fp32-accumulate kernels and the tcgen05 bf16 kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -8,6 +9,11 @@
 namespace gg {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("GG_PDL"); return !(v && v[0] == '0'); }();
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -32,6 +38,11 @@ bool c3_applicable(const gg_conv_desc*);
 int c3_conv_down(const gg_conv_desc*, const float*, const float*, const float*, void*, cudaStream_t);
 int c3_conv_up(const gg_conv_desc*, const void*, const float*, const float*, float*, cudaStream_t);
 int c3_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t);
+// conv_c3_mma.cu (bf16 mode: warp-level tensor-core MMAs; the fp32 parity mode keeps the SIMT kernels)
+int c3m_conv_down(const gg_conv_desc*, const float*, const float*, const float*, void*, cudaStream_t);
+int c3m_conv_up(const gg_conv_desc*, const void*, const float*, const float*, float*, cudaStream_t);
+int c3m_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t);
+static inline bool c3m_applicable(const gg_conv_desc* d) { return c3_applicable(d) && d->small_dtype == GG_BF16; }
 // tc_tapgemm.cu
 int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
 int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
@@ -66,18 +77,21 @@ extern "C" int gg_device_arch(void) {
 extern "C" int gg_conv_down(const gg_conv_desc* d, const void* large, const void* w, const float* bias, void* small, void* stream) {
   GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_down: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_down(d, large, w, bias, small, (cudaStream_t)stream);
+  if (c3m_applicable(d)) GG_REPEAT(c3m_conv_down(d, (const float*)large, (const float*)w, bias, small, (cudaStream_t)stream));
   if (c3_applicable(d)) GG_REPEAT(c3_conv_down(d, (const float*)large, (const float*)w, bias, small, (cudaStream_t)stream));
   GG_REPEAT(simt_conv_down(d, large, (const float*)w, bias, small, (cudaStream_t)stream));
 }
 extern "C" int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large, void* stream) {
   GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_up: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream);
+  if (c3m_applicable(d)) GG_REPEAT(c3m_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream));
   if (c3_applicable(d)) GG_REPEAT(c3_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream));
   GG_REPEAT(simt_conv_up(d, small, (const float*)w, bias, large, (cudaStream_t)stream));
 }
 extern "C" int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw, void* stream) {
   GG_REQUIRE(d && large && dw && small, GG_ERR_INVALID, "conv_wgrad: null pointer");
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_wgrad(d, large, small, dw, (cudaStream_t)stream);
+  if (c3m_applicable(d)) GG_REPEAT(c3m_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream));
   if (c3_applicable(d)) GG_REPEAT(c3_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream));
   GG_REPEAT(simt_conv_wgrad(d, large, small, dw, (cudaStream_t)stream));
 }

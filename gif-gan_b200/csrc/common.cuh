@@ -25,6 +25,36 @@ inline int check_launch(const char* what) {
   return GG_OK;
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+// pdl_grid_sync(): the next kernel's CTAs may be scheduled (and run their prologue: barrier init, TMEM allocation,
+// descriptor prefetch) while the previous kernel drains, but touch global memory only after the previous grid has
+// completed and flushed.  Inside a captured CUDA graph the attribute becomes a programmatic dependency edge; the
+// step has ~200 short kernels, so the launch-to-launch bubble is a first-order cost.  GG_PDL=0 disables it.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
+struct Launch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  Launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    cfg = cudaLaunchConfig_t();
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  template <typename... KArgs, typename... Args>
+  void operator()(void (*kernel)(KArgs...), Args&&... args) {
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in check_launch()
+  }
+};
+
 #define GG_REQUIRE(cond, code, ...) \
   do {                              \
     if (!(cond)) {                  \
@@ -99,17 +129,24 @@ __device__ __forceinline__ float act_grad_from_pre(float u, int act, float a) {
   return 0.5f * (1.f - t * t);
 }
 
-// Vector forms: ONE warp-uniform branch per N elements (the scalar forms, inlined N times in an unrolled loop,
-// leave a branch chain per element because the tanhf/expf paths keep control flow inside the loop).
+// Vector forms: ONE warp-uniform branch per N elements, every loop fully unrolled.  (A `#pragma unroll 1` loop
+// over the register array indexes it dynamically, which moves the whole array -- on EVERY path -- to local memory:
+// ptxas reported a 128-byte stack frame for the tcgen05 epilogue until the slow paths were unrolled as well.)
 template <int N>
 __device__ __forceinline__ void act_fwd_vec(float (&x)[N], int act, float a) {
   if (act <= GG_ACT_LRELU) {
     const float slope = act_slope(act, a);
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = fmaxf(x[i], x[i] * slope);
+  } else if (act == GG_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = tanhf(x[i]);
+  } else if (act == GG_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = 1.f / (1.f + expf(-x[i]));
   } else {
-#pragma unroll 1
-    for (int i = 0; i < N; ++i) x[i] = act_fwd(x[i], act, a);
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = 0.5f * (tanhf(x[i]) + 1.f);
   }
 }
 // g[i] *= act'(u[i])  (derivative through the pre-activation)
@@ -119,9 +156,13 @@ __device__ __forceinline__ void act_bwd_pre_vec(float (&g)[N], const float (&u)[
     const float slope = act_slope(act, a), at_zero = act == GG_ACT_RELU ? 0.f : 1.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] *= (u[i] > 0.f ? 1.f : (u[i] == 0.f ? at_zero : slope));
+  } else if (act == GG_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const float s = 1.f / (1.f + expf(-u[i])); g[i] *= s * (1.f - s); }
   } else {
-#pragma unroll 1
-    for (int i = 0; i < N; ++i) g[i] *= act_grad_from_pre(u[i], act, a);
+    const float sc = act == GG_ACT_TANH ? 1.f : 0.5f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const float t = tanhf(u[i]); g[i] *= sc * (1.f - t * t); }
   }
 }
 // g[i] *= act'(.) evaluated from the output y[i]
@@ -131,9 +172,15 @@ __device__ __forceinline__ void act_bwd_out_vec(float (&g)[N], const float (&y)[
     const float slope = act_slope(act, a), at_zero = act == GG_ACT_RELU ? 0.f : 1.f;
 #pragma unroll
     for (int i = 0; i < N; ++i) g[i] *= (y[i] > 0.f ? 1.f : (y[i] == 0.f ? at_zero : slope));
+  } else if (act == GG_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] *= 1.f - y[i] * y[i];
+  } else if (act == GG_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] *= y[i] * (1.f - y[i]);
   } else {
-#pragma unroll 1
-    for (int i = 0; i < N; ++i) g[i] *= act_grad_from_out(y[i], act, a);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const float t = 2.f * y[i] - 1.f; g[i] *= 0.5f * (1.f - t * t); }
   }
 }
 

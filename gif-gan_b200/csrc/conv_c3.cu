@@ -36,6 +36,7 @@ template <typename TSM>
 __global__ void __launch_bounds__(256)
 c3_down_kernel(const float* __restrict__ large, const float* __restrict__ w, const float* __restrict__ bias, TSM* __restrict__ small,
                int H, int W, int Ho, int Wo, int K, int act, float act_param) {
+  pdl_grid_sync();
   __shared__ __align__(16) float sw[RED * 64];
   __shared__ float sp[PATCH * PROW];
   const int tid = threadIdx.x;
@@ -91,6 +92,7 @@ template <typename TSM>
 __global__ void __launch_bounds__(256)
 c3_up_kernel(const TSM* __restrict__ small, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ large,
              int H, int W, int Ho, int Wo, int K, int act, float act_param) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) float smem_up[];
   float* sw = smem_up;                         // [25][3][64] for the current 64-channel block
   float* sx = smem_up + NTAP * C3 * 64;        // [10*10][UP_STRIDE]
@@ -154,6 +156,7 @@ template <typename TSM>
 __global__ void __launch_bounds__(WG_THREADS)
 c3_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small, float* __restrict__ dw, int N, int H, int W, int Ho, int Wo,
                 int K, int kblocks) {
+  pdl_grid_sync();
   __shared__ float sp[PATCH * PROW];
   __shared__ __align__(16) float sy[64 * 64];
   const int tid = threadIdx.x;
@@ -214,9 +217,9 @@ bool c3_applicable(const gg_conv_desc* d) {
 int c3_conv_down(const gg_conv_desc* d, const float* large, const float* w, const float* bias, void* small, cudaStream_t st) {
   dim3 grid(ceil_div(d->Ho, TS_) * ceil_div(d->Wo, TS_), d->K / 64, d->N);
   if (d->small_dtype == GG_F32)
-    c3_down_kernel<float><<<grid, 256, 0, st>>>(large, w, bias, (float*)small, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
+    Launch(grid, 256, 0, st)(c3_down_kernel<float>, large, w, bias, (float*)small, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
   else
-    c3_down_kernel<bf16><<<grid, 256, 0, st>>>(large, w, bias, (bf16*)small, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
+    Launch(grid, 256, 0, st)(c3_down_kernel<bf16>, large, w, bias, (bf16*)small, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
   return check_launch("c3_down");
 }
 
@@ -230,9 +233,9 @@ int c3_conv_up(const gg_conv_desc* d, const void* small, const float* w, const f
     attr_done = true;
   }
   if (d->small_dtype == GG_F32)
-    c3_up_kernel<float><<<grid, 256, smem, st>>>((const float*)small, w, bias, large, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
+    Launch(grid, 256, smem, st)(c3_up_kernel<float>, (const float*)small, w, bias, large, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
   else
-    c3_up_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)small, w, bias, large, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
+    Launch(grid, 256, smem, st)(c3_up_kernel<bf16>, (const bf16*)small, w, bias, large, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
   return check_launch("c3_up");
 }
 
@@ -242,9 +245,9 @@ int c3_conv_wgrad(const gg_conv_desc* d, const float* large, const void* small, 
   const int per_k = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (148 * 3) / kblocks));
   const int grid = per_k * kblocks;
   if (d->small_dtype == GG_F32)
-    c3_wgrad_kernel<float><<<grid, WG_THREADS, 0, st>>>(large, (const float*)small, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
+    Launch(grid, WG_THREADS, 0, st)(c3_wgrad_kernel<float>, large, (const float*)small, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
   else
-    c3_wgrad_kernel<bf16><<<grid, WG_THREADS, 0, st>>>(large, (const bf16*)small, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
+    Launch(grid, WG_THREADS, 0, st)(c3_wgrad_kernel<bf16>, large, (const bf16*)small, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
   return check_launch("c3_wgrad");
 }
 

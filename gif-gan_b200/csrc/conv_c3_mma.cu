@@ -1,0 +1,364 @@
+// bf16-mode kernels for the image-side layers of the DCGAN (3 channels <-> 64k channels, 5x5, stride 2, SAME):
+//   d_h0_conv (model.py:273) and g_h4 (model.py:321) -- forward, dgrad and wgrad.
+// With C = 3 the reduction of the forward conv is K = 75 and the deconv has N = 3: there is no 64-channel row for a
+// TMA box / tcgen05 K-chunk, and at ~31 flop/B the layers sit below the tensor ridge.  What bounded the fp32 SIMT
+// versions (conv_c3.cu) was FFMA + shared-memory issue, not HBM, so the bf16 mode runs the same sums on warp-level
+// tensor-core MMAs (mma.sync.m16n8k16, bf16 x bf16 -> fp32) with operands gathered from a staged image patch:
+//   c3m_down : small[n,p,q,k] = act(sum_{r,s,c} large[n,2p+r-1,2q+s-1,c] w[r,s,c,k] + b[k])
+//              GEMM  M = pixels, N = 64 channels, K = 5 kernel rows x 16 (15 used: (s,c) pairs + one zero column)
+//   c3m_up   : large[n,2m+a,2l+b,c] = act(sum_{dp,dq,k} small[n,m+dp,l+dq,k] w[a+1-2dp, b+1-2dq, c, k] + bias[c])
+//              GEMM  M = small-grid positions, N = 16 (4 output parities x 3 channels, 12 used), K = 9 neighbours x 64
+//   c3m_wgrad: dw[r,s,c,k] += sum_{n,p,q} large[n,2p+r-1,2q+s-1,c] small[n,p,q,k]
+//              GEMM  M = 15 blocks of 8 (kernel row, column pair, channel padded to 4), N = 64, K = pixels;
+//              both operands are pixel-major in shared memory and enter through ldmatrix.trans.
+// The large tensor (image / image gradient) is fp32 in HBM and rounded to bf16 while staging; accumulation is fp32.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gg {
+
+namespace {
+
+constexpr int KT5 = 5;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// c3m_down.  CTA = 8 warps; tile = 8 rows x 16 columns of the small grid; warp w owns row w (one m16 tile).
+// K index kk = r*16 + sc with sc = s*3 + c (sc = 15 is a zero-weight column): one kernel row per k16 step, and the
+// 16 values of a step are CONTIGUOUS in the staged patch row, so an A fragment is four 32-bit shared loads.
+// Output-channel permutation: column e of n-tile j is channel (e>>1)*16 + 2j + (e&1), so that a thread ends up
+// with 16 consecutive channels of a pixel (32 B of bf16) and a quad writes the pixel's whole 128-byte row.
+constexpr int DN_TH = 8, DN_TW = 16;
+constexpr int DN_PR = 2 * DN_TH + 3;            // 19 patch rows
+constexpr int DN_PC = 2 * DN_TW + 3;            // 35 patch columns
+constexpr int DN_PROW = DN_PC * 3 + 1;          // 106 bf16 per patch row (105 + the column read by the zero weight)
+constexpr int DN_WROW = 88;                     // bf16 per channel row of the transposed filter (80 + 8: bank spread)
+
+template <typename TSM>
+__global__ void __launch_bounds__(256, 1)
+c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, const float* __restrict__ bias, TSM* __restrict__ small,
+                int N, int H, int W, int Ho, int Wo, int K, int kblocks, int act, float act_param) {
+  pdl_grid_sync();
+  __shared__ __align__(16) bf16 swt[64 * DN_WROW];          // [channel][kk]
+  __shared__ __align__(16) bf16 sp[DN_PR * DN_PROW];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int kb = (blockIdx.x % kblocks) * 64;
+  const int tiles_w = (Wo + DN_TW - 1) / DN_TW, tiles_h = (Ho + DN_TH - 1) / DN_TH;
+  const int ntiles = N * tiles_h * tiles_w;
+
+  // ---- filter block -> shared (transposed, bf16, zero pad columns) -> B fragments in registers
+  for (int e = tid; e < 64 * DN_WROW; e += 256) swt[e] = __float2bfloat16_rn(0.f);
+  __syncthreads();
+  for (int e = tid; e < 75 * 64; e += 256) {
+    const int tc = e >> 6, ch = e & 63;
+    const int kk = (tc / 15) * 16 + (tc % 15);
+    swt[ch * DN_WROW + kk] = __float2bfloat16_rn(__ldg(w + (int64_t)tc * K + kb + ch));
+  }
+  for (int e = tid; e < DN_PR; e += 256) sp[e * DN_PROW + DN_PROW - 1] = __float2bfloat16_rn(0.f);
+  __syncthreads();
+  uint32_t bw[KT5][8][2];
+  {
+    const uint32_t* swt32 = reinterpret_cast<const uint32_t*>(swt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = (g >> 1) * 16 + 2 * j + (g & 1);
+#pragma unroll
+      for (int r = 0; r < KT5; ++r) {
+        bw[r][j][0] = swt32[(ch * DN_WROW + r * 16 + 2 * t) >> 1];
+        bw[r][j][1] = swt32[(ch * DN_WROW + r * 16 + 2 * t + 8) >> 1];
+      }
+    }
+  }
+  float bv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) bv[i] = bias ? __ldg(bias + kb + t * 16 + i) : 0.f;
+
+  for (int tile = blockIdx.x / kblocks; tile < ntiles; tile += gridDim.x / kblocks) {
+    const int n = tile / (tiles_h * tiles_w);
+    const int rem = tile - n * tiles_h * tiles_w;
+    const int p0 = (rem / tiles_w) * DN_TH, q0 = (rem % tiles_w) * DN_TW;
+    const int i0 = 2 * p0 - 1, j0 = 2 * q0 - 1;
+    __syncthreads();                                  // previous tile's fragments are consumed
+    for (int e = tid; e < DN_PR * (DN_PC * 3); e += 256) {
+      const int a = e / (DN_PC * 3), x = e - a * (DN_PC * 3);
+      const int i = i0 + a, j = j0 + x / 3;
+      float v = 0.f;
+      if (i >= 0 && i < H && j >= 0 && j < W) v = __ldg(large + ((int64_t)n * H + i) * W * 3 + (int64_t)j0 * 3 + x);
+      sp[a * DN_PROW + x] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+    const uint32_t* sp32 = reinterpret_cast<const uint32_t*>(sp);
+#pragma unroll
+    for (int r = 0; r < KT5; ++r) {
+      const uint32_t* row = sp32 + (2 * warp + r) * (DN_PROW / 2);
+      uint32_t a[4];
+      a[0] = row[3 * g + t];
+      a[1] = row[3 * (g + 8) + t];
+      a[2] = row[3 * g + t + 4];
+      a[3] = row[3 * (g + 8) + t + 4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mma16816(acc[j], a, bw[r][j][0], bw[r][j][1]);
+    }
+    const int p = p0 + warp;
+    if (p < Ho) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int q = q0 + g + 8 * half;
+        if (q >= Wo) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[2 * j] = acc[j][2 * half] + bv[2 * j]; v[2 * j + 1] = acc[j][2 * half + 1] + bv[2 * j + 1]; }
+        act_fwd_vec<16>(v, act, act_param);
+        TSM* dst = small + (((int64_t)n * Ho + p) * Wo + q) * K + kb + t * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// c3m_up.  CTA = 8 warps; tile = 8 rows x 16 columns of small-grid POSITIONS (= 16 x 32 output pixels);
+// warp w owns position row w.  n = (a*2 + b)*3 + c  (a, b: output row / column parity).
+constexpr int UP_TH = 8, UP_TW = 16;
+constexpr int UP_PR = UP_TH + 2, UP_PC = UP_TW + 2;       // 10 x 18 staged small pixels (halo 1)
+constexpr int UP_PIX = 72;                                 // bf16 per staged pixel (64 + 8: conflict-free ldmatrix rows)
+constexpr int UP_WROW = 9 * 64 + 8;                        // 584 bf16 per n row of the expanded filter
+
+template <typename TSM>
+__global__ void __launch_bounds__(256, 2)
+c3m_up_kernel(const TSM* __restrict__ small, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ large,
+              int N, int H, int W, int Ho, int Wo, int K, int act, float act_param) {
+  pdl_grid_sync();
+  __shared__ __align__(16) bf16 sx[UP_PR * UP_PC * UP_PIX];     // 25,920 B
+  __shared__ __align__(16) bf16 swu[16 * UP_WROW];              // 18,688 B
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tiles_w = (Wo + UP_TW - 1) / UP_TW, tiles_h = (Ho + UP_TH - 1) / UP_TH;
+  const int ntiles = N * tiles_h * tiles_w;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / (tiles_h * tiles_w);
+    const int rem = tile - n * tiles_h * tiles_w;
+    const int p0 = (rem / tiles_w) * UP_TH, q0 = (rem % tiles_w) * UP_TW;
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+    for (int kb = 0; kb < K; kb += 64) {
+      __syncthreads();
+      // expanded filter of this channel block: swu[n][(dp+1)*3 + (dq+1)][k] = w[a+1-2dp][b+1-2dq][c][kb+k] (0 if outside 5x5)
+      if (kb > 0 || tile == (int)blockIdx.x || K > 64) {
+        for (int e = tid; e < 16 * 9 * 16; e += 256) {          // 4 channels per item
+          const int k4 = (e & 15) * 4, nb = (e >> 4) % 9, nn = e / (16 * 9);
+          const int cls = nn / 3, c = nn - cls * 3, a = cls >> 1, b = cls & 1;
+          const int r = a + 1 - 2 * (nb / 3 - 1), s = b + 1 - 2 * (nb % 3 - 1);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (nn < 12 && r >= 0 && r < KT5 && s >= 0 && s < KT5) v = ld4(w + ((int64_t)((r * KT5 + s) * 3 + c)) * K + kb + k4);
+          st4(swu + nn * UP_WROW + nb * 64 + k4, v);
+        }
+      }
+      for (int e = tid; e < UP_PR * UP_PC * 8; e += 256) {      // 8 chunks of 8 channels (16 B) per pixel
+        const int pix = e >> 3, c8 = (e & 7) * 8;
+        const int p = p0 - 1 + pix / UP_PC, q = q0 - 1 + pix % UP_PC;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (p >= 0 && p < Ho && q >= 0 && q < Wo) {
+          const TSM* src = small + (((int64_t)n * Ho + p) * Wo + q) * K + kb + c8;
+          if (sizeof(TSM) == 2) {
+            v = __ldg(reinterpret_cast<const uint4*>(src));
+          } else {
+            const float4 f0 = ld4(reinterpret_cast<const float*>(src)), f1 = ld4(reinterpret_cast<const float*>(src) + 4);
+            v = make_uint4(pack2(f0.x, f0.y), pack2(f0.z, f0.w), pack2(f1.x, f1.y), pack2(f1.z, f1.w));
+          }
+        }
+        *reinterpret_cast<uint4*>(sx + pix * UP_PIX + c8) = v;
+      }
+      __syncthreads();
+      const uint32_t* swu32 = reinterpret_cast<const uint32_t*>(swu);
+      // ldmatrix lane -> (matrix mi = lane / 8: rows +8 for odd mi, k +8 for mi >= 2)
+      const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1), lk = 8 * (lane >> 4);
+#pragma unroll 1
+      for (int nb = 0; nb < 9; ++nb) {
+        const int py = warp + nb / 3, px = lrow + nb % 3;        // staged coordinates (halo offset +1, dp/dq offset -1)
+        const uint32_t abase = smem_addr(sx + (py * UP_PC + px) * UP_PIX + lk);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          uint32_t a[4];
+          ldsm_x4(a, abase + kc * 32);
+          const int kw = (nb * 64 + kc * 16 + 2 * t) >> 1;
+          mma16816(acc[0], a, swu32[g * (UP_WROW / 2) + kw], swu32[g * (UP_WROW / 2) + kw + 4]);
+          mma16816(acc[1], a, swu32[(g + 8) * (UP_WROW / 2) + kw], swu32[(g + 8) * (UP_WROW / 2) + kw + 4]);
+        }
+      }
+    }
+    // ---- epilogue: n = 2t, 2t+1 (n-tile 0) and 8+2t, 9+2t (n-tile 1); rows g and g+8 of the position row
+    const int mi = p0 + warp;
+    if (mi < Ho) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int mj = q0 + g + 8 * half;
+        if (mj >= Wo) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int nn = 8 * j + 2 * t;
+          if (nn >= 12) continue;
+          float v[2] = {acc[j][2 * half], acc[j][2 * half + 1]};
+          if (bias) { v[0] += __ldg(bias + nn % 3); v[1] += __ldg(bias + (nn + 1) % 3); }
+          act_fwd_vec<2>(v, act, act_param);
+          const int arow = nn / 6, off = nn - 6 * arow;             // output row parity, offset inside the 6-float run
+          float* dst = large + (((int64_t)n * H + 2 * mi + arow) * W + 2 * mj) * 3 + off;
+          *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// c3m_wgrad.  CTA = 8 warps, persistent over tiles of 8 x 16 small pixels (K = 128 pixels per tile);
+// warp w owns m16 tile w = m-blocks 2w, 2w+1;  m-block mb = (r = mb/3, s0 = 2*(mb%3)), entry i8 -> (s0 + i8/4, c = i8%4).
+constexpr int WG_TH = 8, WG_TW = 16;
+constexpr int WG_PR = 2 * WG_TH + 3;            // 19 patch rows
+constexpr int WG_PC = 2 * WG_TW + 4;            // 36 patch columns (35 + the column the discarded s = 5 entries read)
+constexpr int WG_YPIX = 72;                     // bf16 per staged small pixel
+
+template <typename TSM>
+__global__ void __launch_bounds__(256, 2)
+c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small, float* __restrict__ dw,
+                 int N, int H, int W, int Ho, int Wo, int K, int kblocks) {
+  pdl_grid_sync();
+  __shared__ __align__(16) bf16 sp[WG_PR * WG_PC * 4];          // [row][col][4]   5,472 B
+  __shared__ __align__(16) bf16 sy[WG_TH * WG_TW * WG_YPIX];    // [pixel][72]    18,432 B
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int kb = (blockIdx.x % kblocks) * 64;
+  const int tiles_w = (Wo + WG_TW - 1) / WG_TW, tiles_h = (Ho + WG_TH - 1) / WG_TH;
+  const int ntiles = N * tiles_h * tiles_w;
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+  // ldmatrix.trans lane roles.  A: matrix mi = lane/8 -> (k block = mi >> 1, m block = 2*warp + (mi & 1));
+  // B: matrix mi -> (k block = mi & 1, n block = jn + (mi >> 1)).
+  const int l8 = lane & 7, lm = lane >> 3;
+  const int mblk = min(2 * warp + (lm & 1), 14);
+  const int a_r = mblk / 3, a_s0 = 2 * (mblk % 3);
+  for (int tile = blockIdx.x / kblocks; tile < ntiles; tile += gridDim.x / kblocks) {
+    const int n = tile / (tiles_h * tiles_w);
+    const int rem = tile - n * tiles_h * tiles_w;
+    const int p0 = (rem / tiles_w) * WG_TH, q0 = (rem % tiles_w) * WG_TW;
+    const int i0 = 2 * p0 - 1, j0 = 2 * q0 - 1;
+    __syncthreads();
+    for (int e = tid; e < WG_PR * WG_PC; e += 256) {
+      const int a = e / WG_PC, b = e - a * WG_PC;
+      const int i = i0 + a, j = j0 + b;
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+      if (i >= 0 && i < H && j >= 0 && j < W) {
+        const float* src = large + (((int64_t)n * H + i) * W + j) * 3;
+        v0 = __ldg(src); v1 = __ldg(src + 1); v2 = __ldg(src + 2);
+      }
+      *reinterpret_cast<uint2*>(sp + e * 4) = make_uint2(pack2(v0, v1), pack2(v2, 0.f));
+    }
+    for (int e = tid; e < WG_TH * WG_TW * 8; e += 256) {
+      const int pix = e >> 3, c8 = (e & 7) * 8;
+      const int p = p0 + pix / WG_TW, q = q0 + pix % WG_TW;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (p < Ho && q < Wo) {
+        const TSM* src = small + (((int64_t)n * Ho + p) * Wo + q) * K + kb + c8;
+        if (sizeof(TSM) == 2) {
+          v = __ldg(reinterpret_cast<const uint4*>(src));
+        } else {
+          const float4 f0 = ld4(reinterpret_cast<const float*>(src)), f1 = ld4(reinterpret_cast<const float*>(src) + 4);
+          v = make_uint4(pack2(f0.x, f0.y), pack2(f0.z, f0.w), pack2(f1.x, f1.y), pack2(f1.z, f1.w));
+        }
+      }
+      *reinterpret_cast<uint4*>(sy + pix * WG_YPIX + c8) = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ks = 0; ks < WG_TH * WG_TW / 16; ++ks) {          // 16 pixels per step = one tile row (WG_TW == 16)
+      // A: stored rows = pixels (py = ks, px = 8*(lm>>1) + l8), 8 consecutive m = 2 columns x 4 channels
+      uint32_t a[4];
+      {
+        const int px = 8 * (lm >> 1) + l8;
+        ldsm_x4_t(a, smem_addr(sp + (((2 * ks + a_r) * WG_PC) + 2 * px + a_s0) * 4));
+      }
+#pragma unroll
+      for (int jn = 0; jn < 8; jn += 2) {
+        uint32_t b[4];
+        const int pix = ks * 16 + 8 * (lm & 1) + l8;
+        ldsm_x4_t(b, smem_addr(sy + pix * WG_YPIX + (jn + (lm >> 1)) * 8));
+        mma16816(acc[jn], a, b[0], b[1]);
+        mma16816(acc[jn + 1], a, b[2], b[3]);
+      }
+    }
+  }
+  // ---- reduce into dw: rows m = g, g+8 of this warp's m16 tile
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int mb = 2 * warp + half;                             // m = 8*half + g  ->  m block, entry g
+    const int r = mb / 3, s = 2 * (mb % 3) + (g >> 2), c = g & 3;
+    if (mb >= 15 || s >= KT5 || c >= 3) continue;
+    float* dst = dw + ((int64_t)((r * KT5 + s) * 3 + c)) * K + kb + 2 * t;
+#pragma unroll
+    for (int jn = 0; jn < 8; ++jn) {
+      asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + jn * 8), "f"(acc[jn][2 * half]), "f"(acc[jn][2 * half + 1]) : "memory");
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+int c3m_conv_down(const gg_conv_desc* d, const float* large, const float* w, const float* bias, void* small, cudaStream_t st) {
+  const int kblocks = d->K / 64;
+  const int ntiles = d->N * ceil_div(d->Ho, DN_TH) * ceil_div(d->Wo, DN_TW);
+  const int per_k = std::max(1, std::min(ntiles, 148 / std::min(kblocks, 148)));
+  const int grid = per_k * kblocks;
+  if (d->small_dtype == GG_F32)
+    Launch(grid, 256, 0, st)(c3m_down_kernel<float>, large, w, bias, (float*)small, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks, d->act, d->act_param);
+  else
+    Launch(grid, 256, 0, st)(c3m_down_kernel<bf16>, large, w, bias, (bf16*)small, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks, d->act, d->act_param);
+  return check_launch("c3m_down");
+}
+
+int c3m_conv_up(const gg_conv_desc* d, const void* small, const float* w, const float* bias, float* large, cudaStream_t st) {
+  const int ntiles = d->N * ceil_div(d->Ho, UP_TH) * ceil_div(d->Wo, UP_TW);
+  const int grid = std::min(ntiles, 148 * 2);
+  if (d->small_dtype == GG_F32)
+    Launch(grid, 256, 0, st)(c3m_up_kernel<float>, (const float*)small, w, bias, large, d->N, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
+  else
+    Launch(grid, 256, 0, st)(c3m_up_kernel<bf16>, (const bf16*)small, w, bias, large, d->N, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
+  return check_launch("c3m_up");
+}
+
+int c3m_conv_wgrad(const gg_conv_desc* d, const float* large, const void* small, float* dw, cudaStream_t st) {
+  const int kblocks = d->K / 64;
+  const int ntiles = d->N * ceil_div(d->Ho, WG_TH) * ceil_div(d->Wo, WG_TW);
+  const int per_k = std::max(1, std::min(ntiles, (148 * 2) / std::min(kblocks, 296)));
+  const int grid = per_k * kblocks;
+  if (d->small_dtype == GG_F32)
+    Launch(grid, 256, 0, st)(c3m_wgrad_kernel<float>, large, (const float*)small, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
+  else
+    Launch(grid, 256, 0, st)(c3m_wgrad_kernel<bf16>, large, (const bf16*)small, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
+  return check_launch("c3m_wgrad");
+}
+
+}  // namespace gg

@@ -15,6 +15,7 @@ static inline bool al16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 // ---- activations ------------------------------------------------------------------------
 template <typename TY, typename TD, typename TO, bool VEC>
 __global__ void act_bwd_kernel(const TY* __restrict__ y, const TD* __restrict__ dy, TO* __restrict__ dx, int64_t n, int act, float ap) {
+  pdl_grid_sync();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (VEC) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
@@ -32,6 +33,7 @@ __global__ void act_bwd_kernel(const TY* __restrict__ y, const TD* __restrict__ 
 
 template <typename TX, typename TY, bool VEC>
 __global__ void act_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t n, int act, float ap) {
+  pdl_grid_sync();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (VEC) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
@@ -46,6 +48,7 @@ __global__ void act_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, int
 }
 
 __global__ void axpby_kernel(const float* __restrict__ x, float a, float* __restrict__ y, float b, int64_t n) {
+  pdl_grid_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
 }
@@ -53,6 +56,7 @@ __global__ void axpby_kernel(const float* __restrict__ x, float a, float* __rest
 // ---- filter packing for the tensor-core path ----------------------------------------------
 // w [taps][C][K] fp32 -> w_ck bf16 [taps][C][K] and w_kc bf16 [taps][K][C] (32x32 smem transpose)
 __global__ void pack_filter_kernel(const float* __restrict__ w, bf16* __restrict__ w_ck, bf16* __restrict__ w_kc, int C, int K) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int t = blockIdx.z, c0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
   const float* src = w + (int64_t)t * C * K;
@@ -77,6 +81,7 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, bf16* __restrict
 // ---- losses --------------------------------------------------------------------------------
 __global__ void sigmoid_ce_kernel(const float* __restrict__ logits, int64_t n, float target, float weight, float* __restrict__ loss_out,
                                   int accumulate, float* __restrict__ dlogits) {
+  pdl_grid_sync();
   __shared__ float red[PW_THREADS];
   float acc = 0.f;
   const float inv = 1.f / (float)n;
@@ -97,6 +102,7 @@ __global__ void sigmoid_ce_kernel(const float* __restrict__ logits, int64_t n, f
 
 __global__ void mse_kernel(const float* __restrict__ a, int64_t as, const float* __restrict__ b, int64_t bs, int64_t rows, int64_t cols,
                            float scalar, float* __restrict__ loss_out, int accumulate, float* __restrict__ da) {
+  pdl_grid_sync();
   __shared__ float red[PW_THREADS];
   float acc = 0.f;
   const int64_t n = rows * cols;
@@ -120,6 +126,7 @@ __global__ void mse_kernel(const float* __restrict__ a, int64_t as, const float*
 __global__ void __launch_bounds__(PW_THREADS)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr_t,
             float b1, float b2, float eps, float gs) {
+  pdl_grid_sync();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -148,6 +155,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // device-side step counter so that a captured CUDA graph advances Adam's bias correction:
 // state[0] = t (int32), state[1] = lr_t (float bits).  Double precision like the host formula.
 __global__ void adam_tick_kernel(int* __restrict__ state, float lr, float b1, float b2) {
+  pdl_grid_sync();
   const int t = state[0] + 1;
   state[0] = t;
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
@@ -156,6 +164,7 @@ __global__ void adam_tick_kernel(int* __restrict__ state, float lr, float b1, fl
 __global__ void __launch_bounds__(PW_THREADS)
 adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
                 const int* __restrict__ state, float b1, float b2, float eps, float gs) {
+  pdl_grid_sync();
   const float lr_t = reinterpret_cast<const float*>(state)[1];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
@@ -188,6 +197,7 @@ template <typename TX, typename TY>
 __global__ void __launch_bounds__(PW_THREADS)
 skinny_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, TY* __restrict__ y, int in_dim,
                   int out_dim, int act, float ap) {
+  pdl_grid_sync();
   const int r = blockIdx.x;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (out_dim == 1 && (in_dim & 3) == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)W % 16 == 0)) {
@@ -218,6 +228,7 @@ skinny_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const f
 // dgrad: dx[r,k] = sum_n dy[r,n] W[k,n]
 template <typename TD, typename TO>
 __global__ void skinny_dgrad_kernel(const TD* __restrict__ dy, const float* __restrict__ W, TO* __restrict__ dx, int64_t rows, int in_dim, int out_dim) {
+  pdl_grid_sync();
   const int64_t total = rows * in_dim;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / in_dim;
@@ -230,6 +241,7 @@ __global__ void skinny_dgrad_kernel(const TD* __restrict__ dy, const float* __re
 // wgrad: dW[k,n] += sum_r x[r,k] dy[r,n]
 template <typename TX, typename TD>
 __global__ void skinny_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __restrict__ dW, int rows, int in_dim, int out_dim) {
+  pdl_grid_sync();
   // grid = (k blocks, row chunks): each CTA reduces a chunk of rows for 128 k's, then one atomic per element
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= in_dim) return;
@@ -251,6 +263,7 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); 
 __global__ void lstm_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ Wh, const float* __restrict__ c_prev,
                                 const float* __restrict__ h_prev, float* __restrict__ c_out, float* __restrict__ h_out,
                                 float* __restrict__ gates_out, int H, float fb) {
+  pdl_grid_sync();
   extern __shared__ float hs[];
   const int b = blockIdx.x;
   for (int k = threadIdx.x; k < H; k += blockDim.x) hs[k] = h_prev[(int64_t)b * H + k];
@@ -276,6 +289,7 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ gx, const float* __res
 __global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_out,
                                 const float* __restrict__ dh, const float* __restrict__ dc, const float* __restrict__ Wh,
                                 float* __restrict__ dgates, float* __restrict__ dc_prev, float* __restrict__ dh_prev, int H, float fb) {
+  pdl_grid_sync();
   extern __shared__ float dg[];  // [4H]
   const int b = blockIdx.x;
   for (int j = threadIdx.x; j < H; j += blockDim.x) {
@@ -315,8 +329,8 @@ extern "C" int gg_act_bwd(const void* y, int32_t y_dt, const void* dy, int32_t d
   const int blocks = pw_blocks(vec ? n / 4 : n);
 #define GG_AB(TY, TD, TO)                                                                                            \
   do {                                                                                                               \
-    if (vec) act_bwd_kernel<TY, TD, TO, true><<<blocks, PW_THREADS, 0, st>>>((const TY*)y, (const TD*)dy, (TO*)dx, n, act, ap);  \
-    else act_bwd_kernel<TY, TD, TO, false><<<blocks, PW_THREADS, 0, st>>>((const TY*)y, (const TD*)dy, (TO*)dx, n, act, ap);     \
+    if (vec) Launch(blocks, PW_THREADS, 0, st)(act_bwd_kernel<TY, TD, TO, true>, (const TY*)y, (const TD*)dy, (TO*)dx, n, act, ap);  \
+    else Launch(blocks, PW_THREADS, 0, st)(act_bwd_kernel<TY, TD, TO, false>, (const TY*)y, (const TD*)dy, (TO*)dx, n, act, ap);     \
   } while (0)
   const int key = (y_dt == GG_BF16 ? 4 : 0) | (dy_dt == GG_BF16 ? 2 : 0) | (dx_dt == GG_BF16 ? 1 : 0);
   switch (key) {
@@ -337,8 +351,8 @@ static int act_fwd_impl(const void* x, int x_dt, void* y, int y_dt, int64_t n, i
   const int blocks = pw_blocks(vec ? n / 4 : n);
 #define GG_AF(TX, TY)                                                                                      \
   do {                                                                                                     \
-    if (vec) act_fwd_kernel<TX, TY, true><<<blocks, PW_THREADS, 0, st>>>((const TX*)x, (TY*)y, n, act, ap);  \
-    else act_fwd_kernel<TX, TY, false><<<blocks, PW_THREADS, 0, st>>>((const TX*)x, (TY*)y, n, act, ap);     \
+    if (vec) Launch(blocks, PW_THREADS, 0, st)(act_fwd_kernel<TX, TY, true>, (const TX*)x, (TY*)y, n, act, ap);  \
+    else Launch(blocks, PW_THREADS, 0, st)(act_fwd_kernel<TX, TY, false>, (const TX*)x, (TY*)y, n, act, ap);     \
   } while (0)
   if (x_dt == GG_F32 && y_dt == GG_F32) GG_AF(float, float);
   else if (x_dt == GG_F32) GG_AF(float, bf16);
@@ -359,28 +373,28 @@ extern "C" int gg_cast(const void* src, int32_t s_dt, void* dst, int32_t d_dt, i
 
 extern "C" int gg_axpby(const float* x, float a, float* y, float b, int64_t n, void* stream) {
   GG_REQUIRE(x && y && n > 0, GG_ERR_INVALID, "axpby: bad argument");
-  axpby_kernel<<<pw_blocks(n), PW_THREADS, 0, (cudaStream_t)stream>>>(x, a, y, b, n);
+  Launch(pw_blocks(n), PW_THREADS, 0, (cudaStream_t)stream)(axpby_kernel, x, a, y, b, n);
   return check_launch("axpby");
 }
 
 extern "C" int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t C, int32_t K, void* stream) {
   GG_REQUIRE(w && (w_ck || w_kc) && taps > 0 && C > 0 && K > 0, GG_ERR_INVALID, "pack_filter: bad argument");
   dim3 grid(ceil_div(K, 32), ceil_div(C, 32), taps), block(32, 8);
-  pack_filter_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, (bf16*)w_ck, (bf16*)w_kc, C, K);
+  Launch(grid, block, 0, (cudaStream_t)stream)(pack_filter_kernel, w, (bf16*)w_ck, (bf16*)w_kc, C, K);
   return check_launch("pack_filter");
 }
 
 extern "C" int gg_sigmoid_ce(const float* logits, int64_t n, float target, float weight, float* loss_out, int32_t accumulate,
                              float* dlogits, void* stream) {
   GG_REQUIRE(logits && loss_out && n > 0, GG_ERR_INVALID, "sigmoid_ce: bad argument");
-  sigmoid_ce_kernel<<<1, PW_THREADS, 0, (cudaStream_t)stream>>>(logits, n, target, weight, loss_out, accumulate, dlogits);
+  Launch(1, PW_THREADS, 0, (cudaStream_t)stream)(sigmoid_ce_kernel, logits, n, target, weight, loss_out, accumulate, dlogits);
   return check_launch("sigmoid_ce");
 }
 
 extern "C" int gg_mse(const float* a, int64_t as, const float* b, int64_t bs, int64_t rows, int64_t cols, float scalar, float* loss_out,
                       int32_t accumulate, float* da, void* stream) {
   GG_REQUIRE(a && b && loss_out && rows > 0 && cols > 0, GG_ERR_INVALID, "mse: bad argument");
-  mse_kernel<<<1, PW_THREADS, 0, (cudaStream_t)stream>>>(a, as, b, bs, rows, cols, scalar, loss_out, accumulate, da);
+  Launch(1, PW_THREADS, 0, (cudaStream_t)stream)(mse_kernel, a, as, b, bs, rows, cols, scalar, loss_out, accumulate, da);
   return check_launch("mse");
 }
 
@@ -388,7 +402,7 @@ extern "C" int gg_adam(float* p, const float* g, float* m, float* v, int64_t n, 
                        void* stream) {
   GG_REQUIRE(p && g && m && v && n > 0, GG_ERR_INVALID, "adam: bad argument");
   GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v), GG_ERR_INVALID, "adam: buffers must be 16-byte aligned");
-  adam_kernel<<<pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, b1, b2, eps, gs);
+  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_kernel, p, g, m, v, n, lr_t, b1, b2, eps, gs);
   return check_launch("adam");
 }
 
@@ -396,17 +410,17 @@ extern "C" int gg_adam_graph(float* p, const float* g, float* m, float* v, int64
                              float eps, float gs, void* stream) {
   GG_REQUIRE(p && g && m && v && state && n > 0, GG_ERR_INVALID, "adam_graph: bad argument");
   GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v), GG_ERR_INVALID, "adam_graph: buffers must be 16-byte aligned");
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, b1, b2);
+  Launch(1, 1, 0, (cudaStream_t)stream)(adam_tick_kernel, state, lr, b1, b2);
   int rc = check_launch("adam_tick");
   if (rc) return rc;
-  adam_dev_kernel<<<pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream>>>(p, g, m, v, n, state, b1, b2, eps, gs);
+  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel, p, g, m, v, n, state, b1, b2, eps, gs);
   return check_launch("adam_dev");
 }
 
 namespace gg {
 int skinny_linear_fwd(const void* x, int x_dt, const float* W, const float* bias, void* y, int y_dt, int rows, int in_dim, int out_dim,
                       int act, float ap, cudaStream_t st) {
-#define GG_SF(TX, TY) skinny_fwd_kernel<TX, TY><<<rows, PW_THREADS, 0, st>>>((const TX*)x, W, bias, (TY*)y, in_dim, out_dim, act, ap)
+#define GG_SF(TX, TY) Launch(rows, PW_THREADS, 0, st)(skinny_fwd_kernel<TX, TY>, (const TX*)x, W, bias, (TY*)y, in_dim, out_dim, act, ap)
   if (x_dt == GG_F32 && y_dt == GG_F32) GG_SF(float, float);
   else if (x_dt == GG_F32) GG_SF(float, bf16);
   else if (y_dt == GG_F32) GG_SF(bf16, float);
@@ -415,7 +429,7 @@ int skinny_linear_fwd(const void* x, int x_dt, const float* W, const float* bias
 }
 int skinny_linear_dgrad(const void* dy, int dy_dt, const float* W, void* dx, int dx_dt, int rows, int in_dim, int out_dim, cudaStream_t st) {
   const int blocks = pw_blocks((int64_t)rows * in_dim);
-#define GG_SD(TD, TO) skinny_dgrad_kernel<TD, TO><<<blocks, PW_THREADS, 0, st>>>((const TD*)dy, W, (TO*)dx, rows, in_dim, out_dim)
+#define GG_SD(TD, TO) Launch(blocks, PW_THREADS, 0, st)(skinny_dgrad_kernel<TD, TO>, (const TD*)dy, W, (TO*)dx, rows, in_dim, out_dim)
   if (dy_dt == GG_F32 && dx_dt == GG_F32) GG_SD(float, float);
   else if (dy_dt == GG_F32) GG_SD(float, bf16);
   else if (dx_dt == GG_F32) GG_SD(bf16, float);
@@ -426,7 +440,7 @@ int skinny_linear_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, floa
   const int kblocks = ceil_div(in_dim, 128);
   const int rchunks = std::max(1, std::min(ceil_div(rows, 8), ceil_div(148 * 2, kblocks)));
   const dim3 blocks(kblocks, rchunks);
-#define GG_SW(TX, TD) skinny_wgrad_kernel<TX, TD><<<blocks, 128, 0, st>>>((const TX*)x, (const TD*)dy, dW, rows, in_dim, out_dim)
+#define GG_SW(TX, TD) Launch(blocks, 128, 0, st)(skinny_wgrad_kernel<TX, TD>, (const TX*)x, (const TD*)dy, dW, rows, in_dim, out_dim)
   if (x_dt == GG_F32 && dy_dt == GG_F32) GG_SW(float, float);
   else if (x_dt == GG_F32) GG_SW(float, bf16);
   else if (dy_dt == GG_F32) GG_SW(bf16, float);
@@ -440,7 +454,7 @@ extern "C" int gg_lstm_step_fwd(const float* gx, const float* Wh, const float* c
   GG_REQUIRE(gx && Wh && c_prev && h_prev && c_out && h_out && gates_out && B > 0 && H > 0, GG_ERR_INVALID, "lstm_fwd: bad argument");
   GG_REQUIRE(H <= 4096, GG_ERR_UNSUPPORTED, "lstm_fwd: H > 4096 unsupported");
   const int threads = std::min(256, ((H + 31) / 32) * 32);
-  lstm_fwd_kernel<<<B, threads, H * sizeof(float), (cudaStream_t)stream>>>(gx, Wh, c_prev, h_prev, c_out, h_out, gates_out, H, fb);
+  Launch(B, threads, H * sizeof(float), (cudaStream_t)stream)(lstm_fwd_kernel, gx, Wh, c_prev, h_prev, c_out, h_out, gates_out, H, fb);
   return check_launch("lstm_fwd");
 }
 
@@ -450,6 +464,6 @@ extern "C" int gg_lstm_step_bwd(const float* gates, const float* c_prev, const f
   GG_REQUIRE(gates && c_prev && c_out && dh && Wh && dgates && dc_prev && dh_prev && B > 0 && H > 0, GG_ERR_INVALID, "lstm_bwd: bad argument");
   GG_REQUIRE(H <= 2048, GG_ERR_UNSUPPORTED, "lstm_bwd: H > 2048 unsupported");
   const int threads = std::min(256, ((H + 31) / 32) * 32);
-  lstm_bwd_kernel<<<B, threads, 4 * H * sizeof(float), (cudaStream_t)stream>>>(gates, c_prev, c_out, dh, dc, Wh, dgates, dc_prev, dh_prev, H, fb);
+  Launch(B, threads, 4 * H * sizeof(float), (cudaStream_t)stream)(lstm_bwd_kernel, gates, c_prev, c_out, dh, dc, Wh, dgates, dc_prev, dh_prev, H, fb);
   return check_launch("lstm_bwd");
 }

@@ -50,6 +50,7 @@ template <typename TA, typename TO, bool B_KCONTIG, bool VEC_A, bool VEC_B, bool
 __global__ void __launch_bounds__(256)
 pixgemm_kernel(const TA* __restrict__ A, const float* __restrict__ Wt, const float* __restrict__ bias,
                TO* __restrict__ out, const __grid_constant__ PixGemmParams p) {
+  pdl_grid_sync();
   const ClassInfo ci = p.cls[blockIdx.z];
   const int64_t Mper = (int64_t)ci.Md * ci.Mh * ci.Mw;
   const int64_t M = Mper * p.Mn;
@@ -216,6 +217,7 @@ template <typename TL, typename TS, bool VEC_L, bool VEC_S>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const TL* __restrict__ large, const TS* __restrict__ small, float* __restrict__ dw,
              const __grid_constant__ WgradParams p) {
+  pdl_grid_sync();
   const int c0 = blockIdx.x * BM, k0 = blockIdx.y * BN;
   const int tap = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const int td = tap / (p.kh * p.kw), th = (tap / p.kw) % p.kh, tw = tap % p.kw;
@@ -335,7 +337,7 @@ static int launch_pixgemm(const void* A, const float* Wt, const float* bias, voi
   const bool vecO = (p.Nc % 4 == 0) && ((uintptr_t)out % 16 == 0);
   const bool vB = vecB && wofs_ok;
 #define GG_LAUNCH(VA, VB, VO)                                                                                   \
-  pixgemm_kernel<TA, TO, BKC, VA, VB, VO><<<grid, 256, 0, st>>>((const TA*)A, Wt, bias, (TO*)out, p)
+  Launch(grid, 256, 0, st)(pixgemm_kernel<TA, TO, BKC, VA, VB, VO>, (const TA*)A, Wt, bias, (TO*)out, p)
   if (vecA && vB && vecO) GG_LAUNCH(true, true, true);
   else if (vecA && vB) GG_LAUNCH(true, true, false);
   else if (vB && vecO) GG_LAUNCH(false, true, true);
@@ -419,10 +421,10 @@ template <typename TL, typename TS>
 static int launch_wgrad(const void* large, const void* small, float* dw, const WgradParams& p, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(p.C, BM), (unsigned)ceil_div(p.K, BN), (unsigned)(p.kd * p.kh * p.kw * p.splits));
   const bool vl = (p.C % 4 == 0) && ((uintptr_t)large % 16 == 0), vs = (p.K % 4 == 0) && ((uintptr_t)small % 16 == 0);
-  if (vl && vs) wgrad_kernel<TL, TS, true, true><<<grid, 256, 0, st>>>((const TL*)large, (const TS*)small, dw, p);
-  else if (vs) wgrad_kernel<TL, TS, false, true><<<grid, 256, 0, st>>>((const TL*)large, (const TS*)small, dw, p);
-  else if (vl) wgrad_kernel<TL, TS, true, false><<<grid, 256, 0, st>>>((const TL*)large, (const TS*)small, dw, p);
-  else wgrad_kernel<TL, TS, false, false><<<grid, 256, 0, st>>>((const TL*)large, (const TS*)small, dw, p);
+  if (vl && vs) Launch(grid, 256, 0, st)(wgrad_kernel<TL, TS, true, true>, (const TL*)large, (const TS*)small, dw, p);
+  else if (vs) Launch(grid, 256, 0, st)(wgrad_kernel<TL, TS, false, true>, (const TL*)large, (const TS*)small, dw, p);
+  else if (vl) Launch(grid, 256, 0, st)(wgrad_kernel<TL, TS, true, false>, (const TL*)large, (const TS*)small, dw, p);
+  else Launch(grid, 256, 0, st)(wgrad_kernel<TL, TS, false, false>, (const TL*)large, (const TS*)small, dw, p);
   return check_launch("wgrad");
 }
 

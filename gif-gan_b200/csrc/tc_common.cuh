@@ -44,6 +44,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One elected lane of a CONVERGED warp.  The single-thread roles (TMA producer, MMA issuer) run their loops with the
+// whole warp and elect only around the instruction itself: the loop control and address arithmetic then stay
+// warp-uniform (uniform datapath, no R2UR / per-instruction ELECT-retry wrappers), which is what bounds a
+// one-thread issue loop (measured: ~140 cycles per tcgen05.mma when the loop body sits inside `if (lane == 0)`).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

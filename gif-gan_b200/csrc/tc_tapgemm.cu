@@ -184,81 +184,77 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   unsigned long long* prof = (p.prof != nullptr && blockIdx.x < 512) ? p.prof + 8 * blockIdx.x : nullptr;
+  pdl_grid_sync();            // everything above overlapped the previous kernel's tail; global memory from here on
   const long long t_setup = clock64();
 
-  // The producer loops are single-thread and latency-bound: keep them free of divisions and of
-  // loop-invariant work (one nested loop over taps x k-chunks), and split A and B across two warps.
+  // The TMA-producer and MMA-issuer roles are one-instruction-stream roles.  Their loops run with the whole warp
+  // converged and elect a lane only around the issue (tc::elect_one): loop control and descriptor arithmetic stay
+  // on the uniform datapath.  A and B operands have their own producer warps.
   if (warp == 0) {
     // ===== TMA producer, A operand (activation boxes) =====
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 1;                       // fresh barriers: waiting on parity 1 passes immediately
-      uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
-      const int nst = p.stages;
-      long long wait_cycles = 0;
-      for (int t = C.tap_begin; t < C.tap_end; ++t) {
-        const TcTap tap = p.taps[t];
-        const void* amap = &p.amap[tap.view];
-        const int cw = mw0 + tap.ow, ch = mh0 + tap.oh, cd = md0 + tap.od;
-        for (int kc = 0; kc < p.R; kc += KCHUNK) {
-          const long long w0 = clock64();
-          mbar_wait(eb, ph);
-          wait_cycles += clock64() - w0;
+    int s = 0;
+    uint32_t ph = 1;                       // fresh barriers: waiting on parity 1 passes immediately
+    uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
+    const int nst = p.stages;
+    for (int t = C.tap_begin; t < C.tap_end; ++t) {
+      const TcTap tap = p.taps[t];
+      const void* amap = &p.amap[tap.view];
+      const int cw = mw0 + tap.ow, ch = mh0 + tap.oh, cd = md0 + tap.od;
+      for (int kc = 0; kc < p.R; kc += KCHUNK) {
+        mbar_wait(eb, ph);
+        if (elect_one()) {
           mbar_expect_tx(fb, (uint32_t)A_STAGE_BYTES);
           tma_load_5d(dst, amap, fb, kc, cw, ch, cd, mn0);
-          dst += stage_bytes; fb += 8u; eb += 8u;
-          if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
         }
+        dst += stage_bytes; fb += 8u; eb += 8u;
+        if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
-      if (prof) { prof[0] = (unsigned long long)(clock64() - t_setup); prof[1] = (unsigned long long)wait_cycles; }
     }
+    if (prof && lane == 0) { prof[0] = (unsigned long long)(clock64() - t_setup); prof[1] = 0; }
   } else if (warp == 6) {
     // ===== TMA producer, B operand (filter tiles) =====
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 1;
-      uint32_t dst = smem_base + A_STAGE_BYTES, fb = bar_base, eb = bar_base + 8u * p.stages;
-      const int nst = p.stages;
-      const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-      for (int t = C.tap_begin; t < C.tap_end; ++t) {
-        const int widx = p.taps[t].widx;
-        for (int kc = 0; kc < p.R; kc += KCHUNK) {
-          mbar_wait(eb, ph);
+    int s = 0;
+    uint32_t ph = 1;
+    uint32_t dst = smem_base + A_STAGE_BYTES, fb = bar_base, eb = bar_base + 8u * p.stages;
+    const int nst = p.stages;
+    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+    for (int t = C.tap_begin; t < C.tap_end; ++t) {
+      const int widx = p.taps[t].widx;
+      for (int kc = 0; kc < p.R; kc += KCHUNK) {
+        mbar_wait(eb, ph);
+        if (elect_one()) {
           mbar_expect_tx(fb, b_bytes);
           tma_load_3d(dst, &p.bmap, fb, kc, n0, widx);
-          dst += stage_bytes; fb += 8u; eb += 8u;
-          if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base + A_STAGE_BYTES; fb = bar_base; eb = bar_base + 8u * nst; }
         }
+        dst += stage_bytes; fb += 8u; eb += 8u;
+        if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base + A_STAGE_BYTES; fb = bar_base; eb = bar_base + 8u * nst; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 0, 0);
-      // descriptor = constant high word | (address >> 4): only the low word changes per stage / k-step
-      const uint64_t desc_hi = make_smem_desc(0, 16, 1024);
-      int s = 0;
-      uint32_t ph = 0;
-      uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
-      const int nst = p.stages;
-      long long wait_cycles = 0;
-      for (int it = 0; it < iters; ++it) {
-        const long long w0 = clock64();
-        mbar_wait(fb, ph);
-        wait_cycles += clock64() - w0;
-        tc_fence_after();
-        const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-        const uint64_t bd = desc_hi | (uint64_t)(((a_addr + A_STAGE_BYTES) & 0x3FFFFu) >> 4);
+    const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 0, 0);
+    // descriptor = constant high word | (address >> 4): only the low word changes per stage / k-step
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024);
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
+    const int nst = p.stages;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(fb, ph);
+      tc_fence_after();
+      const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+      const uint64_t bd = desc_hi | (uint64_t)(((a_addr + A_STAGE_BYTES) & 0x3FFFFu) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < KCHUNK / 16; ++k)                // +32 B per K=16 step -> +2 in 16-byte units
           umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(eb);                                   // frees this smem stage when the MMAs retire
         if (it == iters - 1) umma_commit(tmem_full_bar);    // accumulator complete
-        a_addr += stage_bytes; fb += 8u; eb += 8u;
-        if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
-      if (prof) { prof[2] = (unsigned long long)(clock64() - t_setup); prof[3] = (unsigned long long)wait_cycles; }
+      a_addr += stage_bytes; fb += 8u; eb += 8u;
+      if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
     }
+    if (prof && lane == 0) { prof[2] = (unsigned long long)(clock64() - t_setup); prof[3] = 0; }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int q = warp & 3;
@@ -420,6 +416,7 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_grid_sync();
   if (iters <= 0) {   // (cannot happen with the host's split computation; keep the teardown uniform)
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
@@ -436,21 +433,22 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
     tin = pt;
   }
   if (warp == 0 || warp == 6) {
-    // warp 0: the two large-tensor atoms (A operand); warp 6: the small-tensor atoms (B operand)
-    if (lane == 0) {
-      const bool isA = warp == 0;
-      const bool has1 = a1.c0 >= 0;
-      const void* m0 = &p.lmap[a0.view];
-      const void* m1 = &p.lmap[a1.view];
-      const uint32_t bytes = isA ? (uint32_t)((has1 ? 2 : 1) * WG_ATOM_BYTES) : (uint32_t)(nb * WG_ATOM_BYTES);
-      int s = 0;
-      uint32_t ph = 1;
-      uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
-      const int nst = p.stages;
-      int iw = tiw, ih = tih, id = tid_, in = tin;
-      for (int it = 0; it < iters; ++it) {
-        const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd, n0 = in * p.bn;
-        mbar_wait(eb, ph);
+    // warp 0: the two large-tensor atoms (A operand); warp 6: the small-tensor atoms (B operand).
+    // Whole-warp loops, one elected lane around the TMA issue (see tc_pixgemm_kernel).
+    const bool isA = warp == 0;
+    const bool has1 = a1.c0 >= 0;
+    const void* m0 = &p.lmap[a0.view];
+    const void* m1 = &p.lmap[a1.view];
+    const uint32_t bytes = isA ? (uint32_t)((has1 ? 2 : 1) * WG_ATOM_BYTES) : (uint32_t)(nb * WG_ATOM_BYTES);
+    int s = 0;
+    uint32_t ph = 1;
+    uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
+    const int nst = p.stages;
+    int iw = tiw, ih = tih, id = tid_, in = tin;
+    for (int it = 0; it < iters; ++it) {
+      const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd, n0 = in * p.bn;
+      mbar_wait(eb, ph);
+      if (elect_one()) {
         mbar_expect_tx(fb, bytes);
         if (isA) {
           tma_load_5d(dst, m0, fb, a0.c0, w0 + a0.ow, h0 + a0.oh, d0 + a0.od, n0);
@@ -458,33 +456,33 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
         } else {
           for (int j = 0; j < nb; ++j) tma_load_5d(dst + (2 + j) * WG_ATOM_BYTES, &p.smap, fb, k0 + j * 64, w0, h0, d0, n0);
         }
-        if (++iw == p.tw) { iw = 0; if (++ih == p.th) { ih = 0; if (++id == p.td) { id = 0; ++in; } } }
-        dst += stage_bytes; fb += 8u; eb += 8u;
-        if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
+      if (++iw == p.tw) { iw = 0; if (++ih == p.th) { ih = 0; if (++id == p.td) { id = 0; ++in; } } }
+      dst += stage_bytes; fb += 8u; eb += 8u;
+      if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // A: M = 128 = 2 atoms (LBO = atom stride), MN-major; B: N = BN = nb atoms, MN-major.
-      const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 1, 1);
-      const uint64_t desc_hi = make_smem_desc(0, WG_ATOM_BYTES, 1024);
-      int s = 0;
-      uint32_t ph = 0;
-      uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
-      const int nst = p.stages;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(fb, ph);
-        tc_fence_after();
-        const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-        const uint64_t bd = desc_hi | (uint64_t)(((a_addr + 2 * WG_ATOM_BYTES) & 0x3FFFFu) >> 4);
+    // A: M = 128 = 2 atoms (LBO = atom stride), MN-major; B: N = BN = nb atoms, MN-major.
+    const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 1, 1);
+    const uint64_t desc_hi = make_smem_desc(0, WG_ATOM_BYTES, 1024);
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
+    const int nst = p.stages;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(fb, ph);
+      tc_fence_after();
+      const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+      const uint64_t bd = desc_hi | (uint64_t)(((a_addr + 2 * WG_ATOM_BYTES) & 0x3FFFFu) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < WG_PIX / 16; ++k)   // 16 pixels (K) per MMA = two 8-row groups: +2048 B = +128 units per step
           umma_bf16(tmem_base, ad + 128u * k, bd + 128u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(eb);
         if (it == iters - 1) umma_commit(tmem_full_bar);
-        a_addr += stage_bytes; fb += 8u; eb += 8u;
-        if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
+      a_addr += stage_bytes; fb += 8u; eb += 8u;
+      if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
     }
   } else {
     const int q = warp & 3;
@@ -604,7 +602,7 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   std::call_once(once, [] { cudaFuncSetAttribute(tc_pixgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   int rc = GG_OK;
   for (int r = 0; r < g_repeat && rc == GG_OK; ++r) {
-    tc_pixgemm_kernel<<<total_tiles, TC_THREADS, smem, st>>>(p, bias, out);
+    Launch(total_tiles, TC_THREADS, smem, st)(tc_pixgemm_kernel, p, bias, out);
     rc = check_launch("tc_pixgemm");
   }
   return rc;
@@ -792,7 +790,7 @@ int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, f
   std::call_once(once, [] { cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   int rcl = GG_OK;
   for (int r = 0; r < g_repeat && rcl == GG_OK; ++r) {
-    tc_wgrad_kernel<<<(unsigned)(tiles * p.splits), TC_THREADS, smem, st>>>(p, dw);
+    Launch((unsigned)(tiles * p.splits), TC_THREADS, smem, st)(tc_wgrad_kernel, p, dw);
     rcl = check_launch("tc_wgrad");
   }
   return rcl;

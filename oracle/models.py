@@ -93,7 +93,12 @@ class _Graph:
 
     def qw(self, w):
         C, K = w.shape[-2], w.shape[-1]
-        return _RoundValue.apply(w) if (self.quant and C % 64 == 0 and K % 64 == 0) else w
+        # tensor-core layers (tcgen05: C, K multiples of 64) and the image-side layers (warp MMA: C == 3, K multiple of 64)
+        return _RoundValue.apply(w) if (self.quant and (C % 64 == 0 or C == 3) and K % 64 == 0) else w
+
+    def qimg(self, x):
+        """the fp32 image is rounded to bf16 while it is staged as an MMA operand of d_h0_conv (conv_c3_mma.cu)"""
+        return _RoundValue.apply(x) if (self.quant and x.shape[-1] == 3 and getattr(self, "df_dim", 0) % 64 == 0 and getattr(self, "df_dim", 0) > 0) else x
 
     def _v(self, name):
         return self.vars[self.prefix + name]
@@ -203,7 +208,7 @@ class DCGAN(_Graph):
     def discriminator(self, image, y=None, train=True, tag="d"):
         B = image.shape[0]
         if not self.y_dim:
-            h0 = self._rec(f"{tag}_h0", self.qa(T.lrelu(self._rec(f"{tag}_h0_conv", self.conv2d("d_h0_conv", image)))))
+            h0 = self._rec(f"{tag}_h0", self.qa(T.lrelu(self._rec(f"{tag}_h0_conv", self.conv2d("d_h0_conv", self.qimg(image))))))
             h1 = self._rec(f"{tag}_h1", self.qa(T.lrelu(self.bn("d_bn1", self._rec(f"{tag}_h1_conv", self.conv2d("d_h1_conv", h0)), train))))
             h2 = self._rec(f"{tag}_h2", self.qa(T.lrelu(self.bn("d_bn2", self._rec(f"{tag}_h2_conv", self.conv2d("d_h2_conv", h1)), train))))
             h3 = self._rec(f"{tag}_h3", self.qa(T.lrelu(self.bn("d_bn3", self._rec(f"{tag}_h3_conv", self.conv2d("d_h3_conv", h2)), train))))
@@ -233,7 +238,7 @@ class DCGAN(_Graph):
             h2 = self._rec(f"{tag}_h2", self.qa(torch.relu(self.bn("g_bn2", h2, train))))
             h3 = self._rec(f"{tag}_h3_deconv", self.deconv2d("g_h3", h2, [B, s2, s2, gf]))
             h3 = self._rec(f"{tag}_h3", self.qa(torch.relu(self.bn("g_bn3", h3, train))))
-            h4 = self._rec(f"{tag}_h4_deconv", self.deconv2d("g_h4", h3, [B, s, s, self.c_dim], grad_round=False))
+            h4 = self._rec(f"{tag}_h4_deconv", self.deconv2d("g_h4", h3, [B, s, s, self.c_dim], grad_round=(self.c_dim == 3 and gf % 64 == 0)))
             return self._rec(f"{tag}_out", torch.tanh(h4))
         s2, s4 = s // 2, s // 4
         yb = y.reshape(B, 1, 1, self.y_dim)

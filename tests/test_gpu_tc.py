@@ -148,3 +148,56 @@ def test_tc_adjointness_full_batch():
     lhs = (y.float().double() * dy.float().double()).sum().item()
     rhs = (x.detach().float().double() * x.grad.float().double()).sum().item()
     assert abs(lhs - rhs) < 1e-2 * abs(lhs)
+
+
+# ---- image-side layers (3 channels <-> 64k channels): warp-MMA kernels of conv_c3_mma.cu in bf16 mode --------------
+# d_h0_conv (model.py:273): fp32 image in, bf16 activation out.  Sizes cover: one partial tile (20x20 -> 10x10),
+# several tiles per image (64x64), two 64-channel blocks (Co=128), many images per persistent CTA.
+@pytest.mark.parametrize("B,H,W,Co", [(2, 16, 16, 64), (3, 20, 20, 64), (2, 64, 64, 64), (5, 32, 32, 128), (40, 64, 64, 64)])
+def test_c3_conv2d_image_side(B, H, W, Co):
+    rs = np.random.RandomState(H + Co + B)
+    x = torch.tensor(rs.uniform(-1, 1, (B, H, W, 3)), dtype=torch.float32)
+    w, b = bf16_round(rs.randn(5, 5, 3, Co) * 0.05), torch.tensor(rs.randn(Co) * 0.1, dtype=torch.float32)
+    from gifgan import ops as _o
+    ops, st, tv = _store(lambda t: _o.conv2d(t, Co, name="c"), (B, H, W, 3))
+    st.load_state_dict({"c/w": w.numpy(), "c/biases": b.numpy()})
+    xt = x.cuda().requires_grad_(True)                      # images stay fp32 in HBM
+    Ho, Wo = H // 2, W // 2
+    dy = bf16_round(rs.randn(B, Ho, Wo, Co))
+    with ops.trainable(tv):
+        y = ops.conv2d(xt, Co, name="c")
+        y.backward(dy.cuda().to(torch.bfloat16))
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = T.conv2d(xr, wr, br)
+    gx, gw, gb = torch.autograd.grad(yr, [xr, wr, br], dy.double())
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (B, Ho, Wo, Co)
+    assert relerr(y, yr) < TOL
+    assert relerr(xt.grad, gx) < TOL
+    assert relerr(st.vars["c/w"].grad, gw) < TOL
+    assert relerr(st.vars["c/biases"].grad, gb) < TOL
+
+
+# g_h4 (model.py:321): bf16 activation in, fp32 image out (tanh applied by the caller in the model; here plain).
+@pytest.mark.parametrize("B,h,w_,Ci", [(2, 8, 8, 64), (3, 10, 6, 64), (2, 32, 32, 64), (4, 16, 16, 128), (40, 32, 32, 64)])
+def test_c3_deconv2d_image_side(B, h, w_, Ci):
+    rs = np.random.RandomState(h + Ci + B)
+    x, w, b = bf16_round(rs.randn(B, h, w_, Ci)), bf16_round(rs.randn(5, 5, 3, Ci) * 0.05), torch.tensor(rs.randn(3) * 0.1, dtype=torch.float32)
+    out_shape = [B, 2 * h, 2 * w_, 3]
+    from gifgan import ops as _o
+    ops, st, tv = _store(lambda t: _o.deconv2d(t, out_shape, name="g"), (B, h, w_, Ci))
+    st.load_state_dict({"g/w": w.numpy(), "g/biases": b.numpy()})
+    xt = x.cuda().to(torch.bfloat16).requires_grad_(True)
+    dy = torch.tensor(rs.randn(*out_shape), dtype=torch.float32)
+    with ops.trainable(tv):
+        y = ops.deconv2d(xt, out_shape, name="g")
+        y.backward(dy.cuda().to(y.dtype))
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = T.conv2d_transpose(xr, wr, out_shape, br)
+    gx, gw, gb = torch.autograd.grad(yr, [xr, wr, br], dy.double())
+    assert tuple(y.shape) == tuple(out_shape)
+    assert relerr(y, yr) < TOL
+    assert relerr(xt.grad, gx) < TOL
+    assert relerr(st.vars["g/w"].grad, gw) < TOL
+    assert relerr(st.vars["g/biases"].grad, gb) < TOL

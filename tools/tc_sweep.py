@@ -51,7 +51,8 @@ def one(shape, op, reps=20):
         b = buf.cpu().reshape(512, 8).double()
         b = b[b[:, 6] > 0]
         names = ["prodA_loop", "prodA_wait_empty", "mma_loop", "mma_wait_full", "acc_ready", "epi_done", "cta_total", "setup"]
-        print("PROF ctas=%d " % len(b) + " ".join("%s=%.0f" % (n, b[:, i].mean().item()) for i, n in enumerate(names)), flush=True)
+        print("PROF ctas=%d " % len(b) + " ".join("%s=%.0f" % (n, b[:, i].mean().item()) for i, n in enumerate(names)) +
+              " cta_total_max=%.0f acc_ready_max=%.0f" % (b[:, 6].max().item(), b[:, 4].max().item()), flush=True)
     import bench
     fl = bench.conv_flops_per_image(H, C, K) * N
     print("RESULT " + json.dumps(dict(shape=shape, op=op, us=round(best * 1e3, 2), tflops=round(fl / best / 1e9, 1),
@@ -59,6 +60,11 @@ def one(shape, op, reps=20):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) == 2 and sys.argv[1] == "--inproc":      # default plan only, every shape, one process
+        for shape in SHAPES:
+            for op in ("down", "up", "wgrad"):
+                one(shape, op)
+        sys.exit(0)
     if len(sys.argv) > 2:
         one(sys.argv[1], sys.argv[2])
         sys.exit(0)
