@@ -111,30 +111,6 @@ colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_
   }
 }
 
-// ---- finalize: mean / rstd per group, sequential EMA over groups ------------------------
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t rows_per_group, int C, int groups, float eps,
-                                   float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var,
-                                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
-  pdl_grid_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float mm = moving_mean ? moving_mean[c] : 0.f, mv = moving_var ? moving_var[c] : 0.f;
-  const double inv = 1.0 / (double)rows_per_group;
-  for (int g = 0; g < groups; ++g) {
-    const double m = sums[((int64_t)g * 2 + 0) * C + c] * inv;
-    double var = sums[((int64_t)g * 2 + 1) * C + c] * inv - m * m;
-    var = var < 0.0 ? 0.0 : var;
-    const float mf = (float)m, vf = (float)var;
-    save_mean[(int64_t)g * C + c] = mf;
-    save_rstd[(int64_t)g * C + c] = rsqrtf(vf + eps);
-    // ops.py:18-24: assign_moving_average(moving, batch, decay) = moving - (moving - batch)*(1-decay)
-    mm -= (mm - mf) * (1.f - decay);
-    mv -= (mv - vf) * (1.f - decay);
-  }
-  if (moving_mean) moving_mean[c] = mm;
-  if (moving_var) moving_var[c] = mv;
-}
-
 __global__ void bn_infer_stats_kernel(const float* __restrict__ mm, const float* __restrict__ mv, float eps, int C,
                                       float* __restrict__ save_mean, float* __restrict__ save_rstd) {
   pdl_grid_sync();
@@ -144,88 +120,117 @@ __global__ void bn_infer_stats_kernel(const float* __restrict__ mm, const float*
   save_rstd[c] = rsqrtf(mv[c] + eps);
 }
 
-// ---- apply: y = act((x - mean) * rstd * gamma + beta) ----------------------------------
+// ---- train-mode apply: y = act((x - mean) * rstd * gamma + beta), statistics finalised in the same kernel ----------
+// 2-D mapping (tx over channel vectors, ty over rows): a thread owns ONE channel vector for the whole kernel, so the
+// per-channel constants live in registers and the row loop has no divisions.  Every thread derives mean / rstd of
+// its channels from the fp64 sums (cheap, redundant); the first row-block also stores them for the backward pass and
+// applies the EMA updates, sequentially over the row groups (ops.py:18-24: real batch first, then fake).
 template <typename TX, typename TY, int VEC>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows_per_group, int C, int lanes,
-                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                const float* __restrict__ rstd, int act, float act_param) {
+bn_train_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows_per_group, int C, int groups,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ sums, float eps,
+                      float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ save_mean,
+                      float* __restrict__ save_rstd, int act, float act_param, int tx_dim) {
   pdl_grid_sync();
+  const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
   const int grp = blockIdx.z;
-  const int64_t total = rows_per_group * lanes;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / lanes;
-    const int c = (int)(i - r * lanes) * VEC;
-    const int64_t off = ((int64_t)grp * rows_per_group + r) * C + c;
-    float xv[VEC], o[VEC];
-    if (VEC == 4) { float4 t = ld4(x + off); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
-    else xv[0] = ldf(x + off);
+  const int c = (blockIdx.y * tx_dim + tx) * VEC;
+  if (c >= C) return;
+  const double inv = 1.0 / (double)rows_per_group;
+  float mu[VEC], rs[VEC], ga[VEC], be[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const float ga = gamma ? __ldg(gamma + c + v) : 1.f, be = beta ? __ldg(beta + c + v) : 0.f;
-      const float mu = __ldg(mean + (int64_t)grp * C + c + v), rs = __ldg(rstd + (int64_t)grp * C + c + v);
-      o[v] = fmaf((xv[v] - mu) * rs, ga, be);
+  for (int v = 0; v < VEC; ++v) {
+    const double m = sums[((int64_t)grp * 2 + 0) * C + c + v] * inv;
+    double var = sums[((int64_t)grp * 2 + 1) * C + c + v] * inv - m * m;
+    var = var < 0.0 ? 0.0 : var;
+    mu[v] = (float)m;
+    rs[v] = rsqrtf((float)var + eps);
+    ga[v] = gamma ? __ldg(gamma + c + v) : 1.f;
+    be[v] = beta ? __ldg(beta + c + v) : 0.f;
+  }
+  if (blockIdx.x == 0 && ty == 0) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { save_mean[(int64_t)grp * C + c + v] = mu[v]; save_rstd[(int64_t)grp * C + c + v] = rs[v]; }
+    if (grp == 0 && (moving_mean || moving_var)) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float mm = moving_mean ? moving_mean[c + v] : 0.f, mv = moving_var ? moving_var[c + v] : 0.f;
+        for (int g = 0; g < groups; ++g) {
+          const double m = sums[((int64_t)g * 2 + 0) * C + c + v] * inv;
+          double var = sums[((int64_t)g * 2 + 1) * C + c + v] * inv - m * m;
+          var = var < 0.0 ? 0.0 : var;
+          // assign_moving_average(moving, batch, decay) = moving - (moving - batch) * (1 - decay)
+          mm -= (mm - (float)m) * (1.f - decay);
+          mv -= (mv - (float)var) * (1.f - decay);
+        }
+        if (moving_mean) moving_mean[c + v] = mm;
+        if (moving_var) moving_var[c + v] = mv;
+      }
     }
+  }
+  const int64_t base = (int64_t)grp * rows_per_group;
+  for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += (int64_t)gridDim.x * ty_dim) {
+    const int64_t off = (base + r) * C + c;
+    float o[VEC];
+    if (VEC == 4) { float4 t = ld4(x + off); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+    else o[0] = ldf(x + off);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o[v] = fmaf((o[v] - mu[v]) * rs[v], ga[v], be[v]);
     act_fwd_vec<VEC>(o, act, act_param);
     if (VEC == 4) st4(y + off, make_float4(o[0], o[1], o[2], o[3]));
     else stf(y + off, o[0]);
   }
 }
 
-// ---- backward apply -------------------------------------------------------------------
+// ---- backward apply (+ gamma / beta gradients from the same reductions) ----------------------------------------------
 template <typename TX, typename TD, typename TO, int VEC>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __restrict__ dx, int64_t rows_per_group, int C,
-                    int lanes, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const double* __restrict__ sums, int act, float act_param, int train) {
+                    int groups, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const double* __restrict__ sums, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, int act, float act_param, int train, int tx_dim) {
   pdl_grid_sync();
+  const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
   const int grp = blockIdx.z;
-  const int64_t total = rows_per_group * lanes;
+  const int c = (blockIdx.y * tx_dim + tx) * VEC;
+  if (c >= C) return;
   const float invM = 1.f / (float)rows_per_group;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / lanes;
-    const int c = (int)(i - r * lanes) * VEC;
-    const int64_t off = ((int64_t)grp * rows_per_group + r) * C + c;
+  float mu[VEC], rs[VEC], ga[VEC], be[VEC], sg[VEC], sgx[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    ga[v] = gamma ? __ldg(gamma + c + v) : 1.f;
+    be[v] = beta ? __ldg(beta + c + v) : 0.f;
+    mu[v] = __ldg(mean + (int64_t)grp * C + c + v);
+    rs[v] = __ldg(rstd + (int64_t)grp * C + c + v);
+    sg[v] = train ? (float)sums[((int64_t)grp * 2 + 0) * C + c + v] * invM : 0.f;
+    sgx[v] = train ? (float)sums[((int64_t)grp * 2 + 1) * C + c + v] * invM : 0.f;
+  }
+  if (blockIdx.x == 0 && ty == 0 && grp == 0 && (dgamma || dbeta)) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      double a = 0.0, b = 0.0;
+      for (int g = 0; g < groups; ++g) { a += sums[((int64_t)g * 2 + 0) * C + c + v]; b += sums[((int64_t)g * 2 + 1) * C + c + v]; }
+      if (dbeta) dbeta[c + v] += (float)a;
+      if (dgamma) dgamma[c + v] += (float)b;
+    }
+  }
+  const int64_t base = (int64_t)grp * rows_per_group;
+  for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += (int64_t)gridDim.x * ty_dim) {
+    const int64_t off = (base + r) * C + c;
     float xv[VEC], dv[VEC], o[VEC];
     if (VEC == 4) {
       float4 t = ld4(x + off); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
       float4 u = ld4(dy + off); dv[0] = u.x; dv[1] = u.y; dv[2] = u.z; dv[3] = u.w;
     } else { xv[0] = ldf(x + off); dv[0] = ldf(dy + off); }
+    float xh[VEC], u[VEC];
 #pragma unroll
-    float xh[VEC], u[VEC], gar[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const float ga = gamma ? __ldg(gamma + c + v) : 1.f, be = beta ? __ldg(beta + c + v) : 0.f;
-      const float mu = __ldg(mean + (int64_t)grp * C + c + v), rs = __ldg(rstd + (int64_t)grp * C + c + v);
-      xh[v] = (xv[v] - mu) * rs;
-      u[v] = fmaf(ga, xh[v], be);
-      gar[v] = ga * rs;
-    }
+    for (int v = 0; v < VEC; ++v) { xh[v] = (xv[v] - mu[v]) * rs[v]; u[v] = fmaf(ga[v], xh[v], be[v]); }
     act_bwd_pre_vec<VEC>(dv, u, act, act_param);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      if (train) {
-        const float sg = (float)sums[((int64_t)grp * 2 + 0) * C + c + v] * invM;
-        const float sgx = (float)sums[((int64_t)grp * 2 + 1) * C + c + v] * invM;
-        o[v] = gar[v] * (dv[v] - sg - xh[v] * sgx);
-      } else {
-        o[v] = gar[v] * dv[v];
-      }
-    }
+    for (int v = 0; v < VEC; ++v) o[v] = train ? ga[v] * rs[v] * (dv[v] - sg[v] - xh[v] * sgx[v]) : ga[v] * rs[v] * dv[v];
     if (VEC == 4) st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
     else stf(dx + off, o[0]);
   }
-}
-
-__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, int groups, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  pdl_grid_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double a = 0.0, b = 0.0;
-  for (int g = 0; g < groups; ++g) { a += sums[((int64_t)g * 2 + 0) * C + c]; b += sums[((int64_t)g * 2 + 1) * C + c]; }
-  if (dbeta) dbeta[c] += (float)a;
-  if (dgamma) dgamma[c] += (float)b;
 }
 
 __global__ void add_colsum_kernel(const double* __restrict__ sums, int C, float* __restrict__ db) {
@@ -244,6 +249,15 @@ static void launch_colsum(const void* x, const void* dy, int64_t rpg, int C, int
     Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 4, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
   else
     Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 1, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
+}
+
+// streaming (apply) kernels: same 2-D mapping, but sized to fill the machine (no atomics at the end)
+static ColGeom apply_geom(int64_t rows_per_group, int C, int groups, bool vec_ok) {
+  ColGeom g = col_geom(rows_per_group, C, groups, vec_ok);
+  int64_t want = std::max<int64_t>(1, (148 * 6) / ((int64_t)g.cblocks * groups));
+  int64_t maxr = ceil_div64(rows_per_group, (int64_t)g.ty * 2);  // >= 2 rows per thread
+  g.rblocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, maxr));
+  return g;
 }
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
@@ -306,23 +320,18 @@ static int bn_finalize_and_apply(const void* x, int32_t x_dt, void* y, int32_t y
                                  const float* gamma, const float* beta, float* moving_mean, float* moving_var, float* save_mean,
                                  float* save_rstd, float eps, float decay, int32_t act, float act_param, const double* sums,
                                  cudaStream_t st) {
-  const bool vec_ok = aligned16(x) && aligned16(y);
-  Launch(ceil_div(C, 128), 128, 0, st)(bn_finalize_kernel, sums, rpg, C, groups, eps, decay, moving_mean, moving_var, save_mean, save_rstd);
-  int rc = check_launch("bn_finalize");
-  if (rc) return rc;
-  const int vec = (vec_ok && C % 4 == 0) ? 4 : 1;
-  const int lanes = C / vec;
-  dim3 grid(apply_blocks(rpg * lanes), 1, groups);
+  const ColGeom g = apply_geom(rpg, C, groups, aligned16(x) && aligned16(y));
+  dim3 grid(g.rblocks, g.cblocks, groups);
 #define GG_APPLY(TX, TY)                                                                                              \
   do {                                                                                                                \
-    if (vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_apply_kernel<TX, TY, 4>, (const TX*)x, (TY*)y, rpg, C, lanes, gamma, beta, save_mean, save_rstd, act, act_param); \
-    else Launch(grid, BN_THREADS, 0, st)(bn_apply_kernel<TX, TY, 1>, (const TX*)x, (TY*)y, rpg, C, lanes, gamma, beta, save_mean, save_rstd, act, act_param);          \
+    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_train_apply_kernel<TX, TY, 4>, (const TX*)x, (TY*)y, rpg, C, groups, gamma, beta, sums, eps, decay, moving_mean, moving_var, save_mean, save_rstd, act, act_param, g.tx); \
+    else Launch(grid, BN_THREADS, 0, st)(bn_train_apply_kernel<TX, TY, 1>, (const TX*)x, (TY*)y, rpg, C, groups, gamma, beta, sums, eps, decay, moving_mean, moving_var, save_mean, save_rstd, act, act_param, g.tx);          \
   } while (0)
   if (x_dt == GG_F32 && y_dt == GG_F32) GG_APPLY(float, float);
   else if (x_dt == GG_F32) GG_APPLY(float, bf16);
   else if (y_dt == GG_F32) GG_APPLY(bf16, float);
   else GG_APPLY(bf16, bf16);
-  return check_launch("bn_apply");
+  return check_launch("bn_train_apply");
 }
 
 extern "C" int gg_bn_infer_stats(const float* moving_mean, const float* moving_var, float eps, int32_t C, float* save_mean,
@@ -414,19 +423,13 @@ extern "C" int gg_bn_bwd(const void* x, int32_t x_dt, const void* dy, int32_t dy
 #undef GG_CS
     rc = check_launch("bn_bwd_reduce");
     if (rc) return rc;
-    if (dgamma || dbeta) {
-      Launch(ceil_div(C, 128), 128, 0, st)(bn_param_grad_kernel, sums, C, groups, dgamma, dbeta);
-      rc = check_launch("bn_param_grad");
-      if (rc) return rc;
-    }
   }
-  const int vec = (vec_ok && C % 4 == 0) ? 4 : 1;
-  const int lanes = C / vec;
-  dim3 grid(apply_blocks(rpg * lanes), 1, groups);
+  const ColGeom g = apply_geom(rpg, C, groups, vec_ok);
+  dim3 grid(g.rblocks, g.cblocks, groups);
 #define GG_BA(TX, TD, TO)                                                                                                          \
   do {                                                                                                                             \
-    if (vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 4>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, lanes, gamma, beta, save_mean, save_rstd, sums, act, act_param, train); \
-    else Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 1>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, lanes, gamma, beta, save_mean, save_rstd, sums, act, act_param, train);          \
+    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 4>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, groups, gamma, beta, save_mean, save_rstd, sums, dgamma, dbeta, act, act_param, train, g.tx); \
+    else Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 1>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, groups, gamma, beta, save_mean, save_rstd, sums, dgamma, dbeta, act, act_param, train, g.tx);          \
   } while (0)
   const int key = (x_dt == GG_BF16 ? 4 : 0) | (dy_dt == GG_BF16 ? 2 : 0) | (dx_dt == GG_BF16 ? 1 : 0);
   switch (key) {

@@ -32,6 +32,10 @@ inline int check_launch(const char* what) {
 // completed and flushed.  Inside a captured CUDA graph the attribute becomes a programmatic dependency edge; the
 // step has ~200 short kernels, so the launch-to-launch bubble is a first-order cost.  GG_PDL=0 disables it.
 bool pdl_enabled();
+// Experiment switch (GG_CARVEOUT=1): ask for the same shared-memory carveout (maximum shared memory) in every kernel
+// so that SMs are not reconfigured when a tcgen05 kernel (200 KB of stages) follows a streaming kernel.  Measured on
+// B200: no gain, so the driver default stays.
+void prefer_max_shared(const void* kernel);
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_grid_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -51,6 +55,7 @@ struct Launch {
   }
   template <typename... KArgs, typename... Args>
   void operator()(void (*kernel)(KArgs...), Args&&... args) {
+    prefer_max_shared(reinterpret_cast<const void*>(kernel));
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in check_launch()
   }
 };

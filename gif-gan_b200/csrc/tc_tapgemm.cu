@@ -113,6 +113,7 @@ struct TcPixParams {
   float act_param;
   int out_bf16;
   int stages;
+  int cps;                    // 64-wide K chunks per pipeline stage (MMAs per commit = 4 * cps)
   unsigned long long* prof;   // optional per-CTA clock64 breakdown (tools/tc_sweep.py --prof), 8 slots per CTA
   double* stats;              // optional fused batch-norm statistics [groups][2][Nout] (fp32 output only)
   int stats_groups;
@@ -146,7 +147,8 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const long long t_begin = clock64();
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
+  const int b_chunk_bytes = p.BN * 128;
+  const int stage_bytes = p.cps * (A_STAGE_BYTES + b_chunk_bytes);    // [A chunk 0..cps-1 | B chunk 0..cps-1]
   const uint32_t bar_base = smem_base + p.stages * stage_bytes;     // full[s], empty[s], tmem_full, tmem_slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -168,7 +170,8 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const int mw0 = tw * p.bw, mh0 = th * p.bh, md0 = td * p.bd, mn0 = tn * p.bn;
   const int n0 = nt * p.BN;
   const int kchunks = p.R / KCHUNK;
-  const int iters = (C.tap_end - C.tap_begin) * kchunks;
+  const int total_chunks = (C.tap_end - C.tap_begin) * kchunks;
+  const int iters = (total_chunks + p.cps - 1) / p.cps;                // pipeline stages to run; the last may be partial
   const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;   // power of two >= 32
 
   if (warp == 0 && lane == 0) {
@@ -190,69 +193,102 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   // The TMA-producer and MMA-issuer roles are one-instruction-stream roles.  Their loops run with the whole warp
   // converged and elect a lane only around the issue (tc::elect_one): loop control and descriptor arithmetic stay
   // on the uniform datapath.  A and B operands have their own producer warps.
+  // Each role loop is FLAT over the 64-wide K chunks (one TMA box / four MMAs per trip) with a handful of loop-carried
+  // scalars: these loops are instruction-bound (one warp, dependent uniform-datapath ops), so every instruction in
+  // them is paid ~4 cycles, 25-200 times per tile.  A stage spans `cps` consecutive chunks.
+  const int cps = p.cps, nst = p.stages;
   if (warp == 0) {
     // ===== TMA producer, A operand (activation boxes) =====
-    int s = 0;
+    int t = C.tap_begin, kc = 0, sub = 0, s = 0, left = total_chunks;
     uint32_t ph = 1;                       // fresh barriers: waiting on parity 1 passes immediately
-    uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
-    const int nst = p.stages;
-    for (int t = C.tap_begin; t < C.tap_end; ++t) {
-      const TcTap tap = p.taps[t];
-      const void* amap = &p.amap[tap.view];
-      const int cw = mw0 + tap.ow, ch = mh0 + tap.oh, cd = md0 + tap.od;
-      for (int kc = 0; kc < p.R; kc += KCHUNK) {
+    uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * nst;
+    const uint32_t stage_skip = (uint32_t)(stage_bytes - cps * A_STAGE_BYTES);
+    TcTap tap = p.taps[t];
+    const void* amap = &p.amap[tap.view];
+    int cw = mw0 + tap.ow, ch = mh0 + tap.oh, cd = md0 + tap.od;
+#pragma unroll 1
+    for (int c = 0; c < total_chunks; ++c) {
+      if (sub == 0) {
         mbar_wait(eb, ph);
-        if (elect_one()) {
-          mbar_expect_tx(fb, (uint32_t)A_STAGE_BYTES);
-          tma_load_5d(dst, amap, fb, kc, cw, ch, cd, mn0);
-        }
-        dst += stage_bytes; fb += 8u; eb += 8u;
+        if (elect_one()) mbar_expect_tx(fb, (uint32_t)((left < cps ? left : cps) * A_STAGE_BYTES));
+      }
+      if (elect_one()) tma_load_5d(dst, amap, fb, kc, cw, ch, cd, mn0);
+      dst += A_STAGE_BYTES;
+      kc += KCHUNK;
+      --left;
+      if (kc == p.R && left > 0) {
+        kc = 0;
+        tap = p.taps[++t];
+        amap = &p.amap[tap.view];
+        cw = mw0 + tap.ow; ch = mh0 + tap.oh; cd = md0 + tap.od;
+      }
+      if (++sub == cps) {
+        sub = 0; dst += stage_skip; fb += 8u; eb += 8u;
         if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
       }
     }
     if (prof && lane == 0) { prof[0] = (unsigned long long)(clock64() - t_setup); prof[1] = 0; }
   } else if (warp == 6) {
     // ===== TMA producer, B operand (filter tiles) =====
-    int s = 0;
+    int t = C.tap_begin, kc = 0, sub = 0, s = 0, left = total_chunks;
     uint32_t ph = 1;
-    uint32_t dst = smem_base + A_STAGE_BYTES, fb = bar_base, eb = bar_base + 8u * p.stages;
-    const int nst = p.stages;
-    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-    for (int t = C.tap_begin; t < C.tap_end; ++t) {
-      const int widx = p.taps[t].widx;
-      for (int kc = 0; kc < p.R; kc += KCHUNK) {
+    const uint32_t b_off = (uint32_t)(cps * A_STAGE_BYTES);
+    uint32_t dst = smem_base + b_off, fb = bar_base, eb = bar_base + 8u * nst;
+    const uint32_t stage_skip = (uint32_t)(stage_bytes - cps * b_chunk_bytes);
+    int widx = p.taps[t].widx;
+#pragma unroll 1
+    for (int c = 0; c < total_chunks; ++c) {
+      if (sub == 0) {
         mbar_wait(eb, ph);
-        if (elect_one()) {
-          mbar_expect_tx(fb, b_bytes);
-          tma_load_3d(dst, &p.bmap, fb, kc, n0, widx);
-        }
-        dst += stage_bytes; fb += 8u; eb += 8u;
-        if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base + A_STAGE_BYTES; fb = bar_base; eb = bar_base + 8u * nst; }
+        if (elect_one()) mbar_expect_tx(fb, (uint32_t)((left < cps ? left : cps) * b_chunk_bytes));
+      }
+      if (elect_one()) tma_load_3d(dst, &p.bmap, fb, kc, n0, widx);
+      dst += b_chunk_bytes;
+      kc += KCHUNK;
+      --left;
+      if (kc == p.R && left > 0) { kc = 0; widx = p.taps[++t].widx; }
+      if (++sub == cps) {
+        sub = 0; dst += stage_skip; fb += 8u; eb += 8u;
+        if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base + b_off; fb = bar_base; eb = bar_base + 8u * nst; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 0, 0);
-    // descriptor = constant high word | (address >> 4): only the low word changes per stage / k-step
+    // descriptor = constant high word | (address >> 4): only the low word changes per stage / chunk / k-step
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024);
-    int s = 0;
+    const uint32_t b_off = (uint32_t)(cps * A_STAGE_BYTES);
+    int sub = 0, s = 0, left = total_chunks;
     uint32_t ph = 0;
-    uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
-    const int nst = p.stages;
-    for (int it = 0; it < iters; ++it) {
-      mbar_wait(fb, ph);
-      tc_fence_after();
-      const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-      const uint64_t bd = desc_hi | (uint64_t)(((a_addr + A_STAGE_BYTES) & 0x3FFFFu) >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < KCHUNK / 16; ++k)                // +32 B per K=16 step -> +2 in 16-byte units
-          umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(eb);                                   // frees this smem stage when the MMAs retire
-        if (it == iters - 1) umma_commit(tmem_full_bar);    // accumulator complete
+    uint32_t a_addr = smem_base, b_addr = smem_base + b_off, fb = bar_base, eb = bar_base + 8u * nst;
+    uint32_t acc = 0u;
+#pragma unroll 1
+    for (int c = 0; c < total_chunks; ++c) {
+      if (sub == 0) {
+        mbar_wait(fb, ph);
+        tc_fence_after();
       }
-      a_addr += stage_bytes; fb += 8u; eb += 8u;
-      if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
+      --left;
+      ++sub;
+      if (elect_one()) {
+        const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+        const uint64_t bd = desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+        umma_bf16(tmem_base, ad, bd, idesc, acc);
+#pragma unroll
+        for (int k = 1; k < KCHUNK / 16; ++k)                // +32 B per K=16 step -> +2 in 16-byte units
+          umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc, 1u);
+        if (sub == cps || left == 0) {
+          umma_commit(eb);                                 // frees this smem stage when the MMAs retire
+          if (left == 0) umma_commit(tmem_full_bar);        // accumulator complete
+        }
+      }
+      acc = 1u;
+      a_addr += A_STAGE_BYTES; b_addr += b_chunk_bytes;
+      if (sub == cps) {
+        sub = 0; fb += 8u; eb += 8u;
+        a_addr += (uint32_t)(stage_bytes - cps * A_STAGE_BYTES); b_addr += (uint32_t)(stage_bytes - cps * b_chunk_bytes);
+        if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; b_addr = smem_base + b_off; fb = bar_base; eb = bar_base + 8u * nst; }
+      }
     }
     if (prof && lane == 0) { prof[2] = (unsigned long long)(clock64() - t_setup); prof[3] = 0; }
   } else {
@@ -377,6 +413,7 @@ struct TcWgradParams {
   int ptiles, ptiles_per_split;
   int C, K;
   int stages;
+  int pps;                          // 64-pixel tiles per pipeline stage (MMAs per commit = 4 * pps)
   WgAtom atoms[2 * 208];            // up to 27 taps x 8 chunks (512 ch) = 216 -> mtiles <= 208
 };
 
@@ -386,7 +423,8 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = p.BN / 64;                                    // B atoms per stage
-  const int stage_bytes = (2 + nb) * WG_ATOM_BYTES;
+  const int sub_bytes = (2 + nb) * WG_ATOM_BYTES;              // one 64-pixel tile: [A atom 0 | A atom 1 | B atoms]
+  const int stage_bytes = p.pps * sub_bytes;
   const uint32_t bar_base = smem_base + p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -401,7 +439,8 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
   const int k0 = nt * p.BN;
   const int pt_begin = split * p.ptiles_per_split;
   const int pt_end = min(p.ptiles, pt_begin + p.ptiles_per_split);
-  const int iters = pt_end - pt_begin;
+  const int npt = pt_end - pt_begin;                           // 64-pixel tiles of this split
+  const int iters = (npt + p.pps - 1) / p.pps;                 // pipeline stages (the last may be partial)
   const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;
 
   if (warp == 0 && lane == 0) {
@@ -443,21 +482,29 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
     int s = 0;
     uint32_t ph = 1;
     uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
-    const int nst = p.stages;
+    const int nst = p.stages, pps = p.pps;
     int iw = tiw, ih = tih, id = tid_, in = tin;
+    int left = npt;
     for (int it = 0; it < iters; ++it) {
-      const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd, n0 = in * p.bn;
+      const int nsub = left < pps ? left : pps;
+      left -= nsub;
       mbar_wait(eb, ph);
-      if (elect_one()) {
-        mbar_expect_tx(fb, bytes);
-        if (isA) {
-          tma_load_5d(dst, m0, fb, a0.c0, w0 + a0.ow, h0 + a0.oh, d0 + a0.od, n0);
-          if (has1) tma_load_5d(dst + WG_ATOM_BYTES, m1, fb, a1.c0, w0 + a1.ow, h0 + a1.oh, d0 + a1.od, n0);
-        } else {
-          for (int j = 0; j < nb; ++j) tma_load_5d(dst + (2 + j) * WG_ATOM_BYTES, &p.smap, fb, k0 + j * 64, w0, h0, d0, n0);
+      const bool issue = elect_one();
+      if (issue) mbar_expect_tx(fb, bytes * (uint32_t)nsub);
+      for (int u = 0; u < nsub; ++u) {
+        const int w0 = iw * p.bw, h0 = ih * p.bh, d0 = id * p.bd, n0 = in * p.bn;
+        const uint32_t sub = dst + u * sub_bytes;
+        if (issue) {
+          if (isA) {
+            tma_load_5d(sub, m0, fb, a0.c0, w0 + a0.ow, h0 + a0.oh, d0 + a0.od, n0);
+            if (has1) tma_load_5d(sub + WG_ATOM_BYTES, m1, fb, a1.c0, w0 + a1.ow, h0 + a1.oh, d0 + a1.od, n0);
+          } else {
+            for (int j = 0; j < nb; ++j) tma_load_5d(sub + (2 + j) * WG_ATOM_BYTES, &p.smap, fb, k0 + j * 64, w0, h0, d0, n0);
+          }
         }
+        if (++iw == p.tw) { iw = 0; if (++ih == p.th) { ih = 0; if (++id == p.td) { id = 0; ++in; } } }
       }
-      if (++iw == p.tw) { iw = 0; if (++ih == p.th) { ih = 0; if (++id == p.td) { id = 0; ++in; } } }
+      __syncwarp();
       dst += stage_bytes; fb += 8u; eb += 8u;
       if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
     }
@@ -468,16 +515,22 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
     int s = 0;
     uint32_t ph = 0;
     uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * p.stages;
-    const int nst = p.stages;
+    const int nst = p.stages, pps = p.pps;
+    int left = npt;
     for (int it = 0; it < iters; ++it) {
+      const int nsub = left < pps ? left : pps;
+      left -= nsub;
       mbar_wait(fb, ph);
       tc_fence_after();
-      const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-      const uint64_t bd = desc_hi | (uint64_t)(((a_addr + 2 * WG_ATOM_BYTES) & 0x3FFFFu) >> 4);
       if (elect_one()) {
+        for (int u = 0; u < nsub; ++u) {
+          const uint32_t sub = a_addr + u * sub_bytes;
+          const uint64_t ad = desc_hi | (uint64_t)((sub & 0x3FFFFu) >> 4);
+          const uint64_t bd = desc_hi | (uint64_t)(((sub + 2 * WG_ATOM_BYTES) & 0x3FFFFu) >> 4);
 #pragma unroll
-        for (int k = 0; k < WG_PIX / 16; ++k)   // 16 pixels (K) per MMA = two 8-row groups: +2048 B = +128 units per step
-          umma_bf16(tmem_base, ad + 128u * k, bd + 128u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < WG_PIX / 16; ++k)   // 16 pixels (K) per MMA = two 8-row groups: +2048 B = +128 units per step
+            umma_bf16(tmem_base, ad + 128u * k, bd + 128u * k, idesc, (it > 0 || u > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(eb);
         if (it == iters - 1) umma_commit(tmem_full_bar);
       }
@@ -587,15 +640,21 @@ static int pick_bn(int Nout, int64_t mtiles) {
 }
 
 static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* out, cudaStream_t st) {
-  const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
-  // The main loop is bound by per-iteration issue latency, not by pipeline depth (tools/tc_sweep.py): when the grid
-  // exceeds one wave prefer 2 co-resident CTAs per SM (<= ~100 KB each) over deep pipelines.
+  const int chunk_bytes = A_STAGE_BYTES + p.BN * 128;
+  // Issue-side measurements (tools/mma_bench.cu): a pipeline stage costs ~450 cycles of fixed issue/commit latency on
+  // top of its MMAs, so a stage should carry >= 8 MMAs (two 64-wide K chunks): 128 x 128 x 16 then runs at ~80
+  // cycles per MMA instead of ~137.  When the grid exceeds one wave, two co-resident CTAs per SM (<= ~100 KB each)
+  // hide each other's prologue / epilogue and are preferred over deeper stages.
   const int budget = total_tiles > 148 ? 100 * 1024 : 200 * 1024;
+  p.cps = (budget / (2 * chunk_bytes)) >= 2 ? 2 : 1;
+  p.cps = std::max(1, std::min(4, env_int("GG_TC_CPS", p.cps)));
+  const int stage_bytes = p.cps * chunk_bytes;
   p.stages = std::max(2, std::min(8, budget / stage_bytes));
   const int out_bytes = TILE_M * p.BN * (p.out_bf16 ? 2 : 4);          // the epilogue stages the tile in the pipeline buffers
   while (p.stages * stage_bytes < out_bytes) ++p.stages;
   p.stages = std::max(1, std::min(p.stages, env_int("GG_TC_STAGES", p.stages)));
   GG_REQUIRE(p.stages * stage_bytes >= out_bytes, GG_ERR_INVALID, "tc_pixgemm: GG_TC_STAGES too small for the output tile");
+  GG_REQUIRE((size_t)p.stages * stage_bytes + 2048 <= 227 * 1024, GG_ERR_INVALID, "tc_pixgemm: pipeline does not fit in shared memory");
   p.prof = g_prof;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2) + 16;
   static std::once_flag once;
@@ -783,8 +842,10 @@ int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, f
   p.ptiles_per_split = ceil_div(p.ptiles, splits);
   p.splits = ceil_div(p.ptiles, p.ptiles_per_split);
   p.C = d->C; p.K = d->K;
-  const int stage_bytes = (2 + p.BN / 64) * WG_ATOM_BYTES;
+  p.pps = std::max(1, std::min(4, env_int("GG_WG_PPS", 2)));      // 8 MMAs per commit (see launch_pix)
+  const int stage_bytes = p.pps * (2 + p.BN / 64) * WG_ATOM_BYTES;
   p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+  GG_REQUIRE((size_t)p.stages * stage_bytes + 2048 <= 227 * 1024, GG_ERR_INVALID, "tc_wgrad: pipeline does not fit in shared memory");
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2);
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });

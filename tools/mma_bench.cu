@@ -18,6 +18,7 @@ constexpr int A_BYTES = 128 * 128;
 
 struct Args {
   int N, iters, stages, mode;   // mode 0: MMA only; 1: + bulk-copy producer (A and B per stage); 2: producer only (no MMA)
+  int commit_every, alt;        // (conv path) commit once per this many iterations; alternate between two accumulators
   int conv;                     // 1: converged-warp loops with elect.sync around the issue; 0: loops inside if (lane == 0)
   int kblocks;                  // MMAs (K=16) per stage: 4 = one 128-byte swizzle row
   const uint8_t* src;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(192, 1) mma_bench_kernel(Args a) {
   for (uint32_t i = threadIdx.x * 16; i < (uint32_t)(a.stages * stage_bytes); i += blockDim.x * 16)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem_base + i), "r"(0x3c003c00u) : "memory");
   fence_proxy_async();
-  const uint32_t tmem_cols = a.N < 32 ? 32 : a.N;
+  const uint32_t tmem_cols = a.alt ? 2 * a.N : (a.N < 32 ? 32 : a.N);
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -77,13 +78,14 @@ __global__ void __launch_bounds__(192, 1) mma_bench_kernel(Args a) {
       const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
       const uint64_t bd = desc_hi | (uint64_t)(((a_addr + A_BYTES) & 0x3FFFFu) >> 4);
       if (elect_one()) {
+        const uint32_t alt = a.alt ? (uint32_t)a.N : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        if (a.kblocks == 8) {
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + (k & 1) * alt, ad + 2u * k, bd + 2u * k, idesc, (it > 0 || k > 1) ? 1u : 0u);
+        for (int rep = 4; rep < a.kblocks; rep += 4) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + (k & 1) * alt, ad + 2u * k, bd + 2u * k, idesc, 1u);
         }
-        umma_commit(bar_base + 8u * (a.stages + s));
+        if ((it + 1) % a.commit_every == 0) umma_commit(bar_base + 8u * (a.stages + s));
       }
       __syncwarp();
       if (++s == a.stages) { s = 0; ph ^= 1u; }
@@ -143,13 +145,15 @@ int main() {
   cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   unsigned long long h[296];
   const int Ns[3] = {64, 128, 256};
-  for (int conv : {1, 0})
+  struct V { int mode, kb, ce, alt; };
+  const V variants[] = {{0, 4, 1, 0}, {0, 8, 1, 0}, {0, 16, 1, 0}, {0, 4, 4, 0}, {0, 4, 1000000, 0}, {0, 4, 1, 1}, {0, 8, 1, 1}, {1, 4, 1, 0}, {1, 8, 1, 0}, {2, 4, 1, 0}};
+  for (int conv : {1})
   for (int grid : {148})
-    for (int mode : {0, 1, 2})
+    for (const V& v : variants)
       for (int ni = 0; ni < 3; ++ni)
-        for (int kb : {4, 8}) {
-          if (mode == 2 && kb == 8) continue;
-          Args a; a.conv = conv; a.N = Ns[ni]; a.iters = 400; a.stages = stages_max; a.mode = mode; a.kblocks = kb; a.src = src; a.out = out;
+        {
+          const int mode = v.mode, kb = v.kb;
+          Args a; a.conv = conv; a.commit_every = v.ce; a.alt = v.alt; a.N = Ns[ni]; a.iters = 400; a.stages = stages_max; a.mode = mode; a.kblocks = kb; a.src = src; a.out = out;
           const int stage_bytes = A_BYTES + a.N * 128;
           const size_t smem = (size_t)a.stages * stage_bytes + 1024 + 8 * (2 * a.stages + 2) + 16;
           cudaMemset(out, 0, sizeof(h));
@@ -166,8 +170,8 @@ int main() {
           for (int c = 0; c < grid; ++c) { issue += h[2 * c]; total += h[2 * c + 1]; }
           issue /= grid; total /= grid;
           const double nm = (double)a.iters * kb;
-          printf("conv=%d grid=%3d mode=%d N=%3d mma_per_stage=%d stage_bytes=%6d : issue %.1f cyc/mma, total %.1f cyc/mma (%.0f cyc/stage, %.1f B/cyc/SM), kernel %.1f us\n",
-                 conv, grid, mode, a.N, kb, stage_bytes, issue / nm, total / nm, total / a.iters, (double)stage_bytes * a.iters / total, ms * 1e3);
+          printf("commit_every=%d alt=%d conv=%d grid=%3d mode=%d N=%3d mma_per_stage=%d stage_bytes=%6d : issue %.1f cyc/mma, total %.1f cyc/mma (%.0f cyc/stage, %.1f B/cyc/SM), kernel %.1f us\n",
+                 v.ce > 1000 ? 0 : v.ce, v.alt, conv, grid, mode, a.N, kb, stage_bytes, issue / nm, total / nm, total / a.iters, (double)stage_bytes * a.iters / total, ms * 1e3);
         }
   return 0;
 }
