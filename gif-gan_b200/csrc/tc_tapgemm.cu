@@ -82,7 +82,8 @@ constexpr int TC_MAX_VIEWS = 8;
 constexpr int TILE_M = 128;
 constexpr int KCHUNK = 64;                 // bf16 elements per 128-byte swizzle row
 constexpr int A_STAGE_BYTES = TILE_M * 128; // 16 KB
-constexpr int TC_THREADS = 224;             // warps: 0 = TMA(A), 1 = MMA + TMEM owner, 2..5 = epilogue, 6 = TMA(B)
+constexpr int TC_THREADS = 288;             // warps: 0 / 7 = TMA(A) even / odd chunks, 1 = MMA + TMEM owner, 2..5 = epilogue, 6 / 8 = TMA(B) even / odd chunks
+constexpr int TC_WG_THREADS = 224;          // tc_wgrad: 0 = TMA(A), 1 = MMA, 2..5 = epilogue, 6 = TMA(B)
 
 struct TcTap {
   int8_t view;              // which A tensor map
@@ -175,7 +176,8 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;   // power of two >= 32
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }   // full: A + B producers
+    // full: one arrival per producer warp that touches the stage (2 operands x cps chunk slots)
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2 * p.cps); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.bmap);
@@ -193,104 +195,98 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   // The TMA-producer and MMA-issuer roles are one-instruction-stream roles.  Their loops run with the whole warp
   // converged and elect a lane only around the issue (tc::elect_one): loop control and descriptor arithmetic stay
   // on the uniform datapath.  A and B operands have their own producer warps.
-  // Each role loop is FLAT over the 64-wide K chunks (one TMA box / four MMAs per trip) with a handful of loop-carried
-  // scalars: these loops are instruction-bound (one warp, dependent uniform-datapath ops), so every instruction in
-  // them is paid ~4 cycles, 25-200 times per tile.  A stage spans `cps` consecutive chunks.
+  // Role loops.  They are instruction-bound (one warp, dependent uniform-datapath ops: ~400 cycles per TMA issue were
+  // measured), so each operand has TWO producer warps taking alternate 64-wide K chunks, and the MMA warp issues a
+  // whole stage (cps chunks = 4 * cps MMAs) per barrier wait.  Chunk c lives in stage c / cps, slot c % cps.
   const int cps = p.cps, nst = p.stages;
-  if (warp == 0) {
-    // ===== TMA producer, A operand (activation boxes) =====
-    int t = C.tap_begin, kc = 0, sub = 0, s = 0, left = total_chunks;
-    uint32_t ph = 1;                       // fresh barriers: waiting on parity 1 passes immediately
-    uint32_t dst = smem_base, fb = bar_base, eb = bar_base + 8u * nst;
-    const uint32_t stage_skip = (uint32_t)(stage_bytes - cps * A_STAGE_BYTES);
-    TcTap tap = p.taps[t];
-    const void* amap = &p.amap[tap.view];
-    int cw = mw0 + tap.ow, ch = mh0 + tap.oh, cd = md0 + tap.od;
+  if (warp == 0 || warp == 7 || warp == 6 || warp == 8) {
+    // ===== TMA producers: warps 0 / 7 -> A operand (activation boxes), warps 6 / 8 -> B operand (filter tiles) =====
+    const bool isA = (warp == 0 || warp == 7);
+    const int j = (warp == 0 || warp == 6) ? 0 : 1;                 // parity of the chunks this warp loads
+    const int slot = (cps == 2) ? j : 0;
+    const int sstep = 2 / cps;                                      // stages advanced per trip
+    const uint32_t chunk_bytes = isA ? (uint32_t)A_STAGE_BYTES : (uint32_t)b_chunk_bytes;
+    const uint32_t slot_off = (isA ? 0u : (uint32_t)(cps * A_STAGE_BYTES)) + (uint32_t)slot * chunk_bytes;
+    int s = (cps == 2) ? 0 : j;
+    uint32_t ph = 1;                                                // fresh barriers: waiting on parity 1 passes immediately
+    if (s >= nst) { s -= nst; ph ^= 1u; }
+    int t = C.tap_begin, kc = j * KCHUNK;
+    while (kc >= p.R) { kc -= p.R; ++t; }
+    const int nstage_total = iters;                                 // stages of this tile
+    // trips: one per chunk of parity j; with cps == 2 a final odd stage still needs this warp's arrival on the barrier
+    const int my_chunks = (total_chunks - j + 1) / 2;
+    const int my_trips = (cps == 2) ? nstage_total : my_chunks;
 #pragma unroll 1
-    for (int c = 0; c < total_chunks; ++c) {
-      if (sub == 0) {
-        mbar_wait(eb, ph);
-        if (elect_one()) mbar_expect_tx(fb, (uint32_t)((left < cps ? left : cps) * A_STAGE_BYTES));
+    for (int i = 0; i < my_trips; ++i) {
+      const uint32_t fb = bar_base + 8u * s, eb = bar_base + 8u * (nst + s);
+      const uint32_t dst = smem_base + (uint32_t)s * (uint32_t)stage_bytes + slot_off;
+      mbar_wait(eb, ph);
+      if (i < my_chunks) {
+        if (isA) {
+          const TcTap tap = p.taps[t];
+          if (elect_one()) {
+            mbar_expect_tx(fb, chunk_bytes);
+            tma_load_5d(dst, &p.amap[tap.view], fb, kc, mw0 + tap.ow, mh0 + tap.oh, md0 + tap.od, mn0);
+          }
+        } else {
+          const int widx = p.taps[t].widx;
+          if (elect_one()) {
+            mbar_expect_tx(fb, chunk_bytes);
+            tma_load_3d(dst, &p.bmap, fb, kc, n0, widx);
+          }
+        }
+      } else if (elect_one()) {
+        mbar_arrive(fb);                                            // odd tail: this slot stays empty
       }
-      if (elect_one()) tma_load_5d(dst, amap, fb, kc, cw, ch, cd, mn0);
-      dst += A_STAGE_BYTES;
-      kc += KCHUNK;
-      --left;
-      if (kc == p.R && left > 0) {
-        kc = 0;
-        tap = p.taps[++t];
-        amap = &p.amap[tap.view];
-        cw = mw0 + tap.ow; ch = mh0 + tap.oh; cd = md0 + tap.od;
-      }
-      if (++sub == cps) {
-        sub = 0; dst += stage_skip; fb += 8u; eb += 8u;
-        if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
-      }
+      kc += 2 * KCHUNK;
+      while (kc >= p.R) { kc -= p.R; ++t; }
+      s += sstep;
+      if (s >= nst) { s -= nst; ph ^= 1u; }
     }
-    if (prof && lane == 0) { prof[0] = (unsigned long long)(clock64() - t_setup); prof[1] = 0; }
-  } else if (warp == 6) {
-    // ===== TMA producer, B operand (filter tiles) =====
-    int t = C.tap_begin, kc = 0, sub = 0, s = 0, left = total_chunks;
-    uint32_t ph = 1;
-    const uint32_t b_off = (uint32_t)(cps * A_STAGE_BYTES);
-    uint32_t dst = smem_base + b_off, fb = bar_base, eb = bar_base + 8u * nst;
-    const uint32_t stage_skip = (uint32_t)(stage_bytes - cps * b_chunk_bytes);
-    int widx = p.taps[t].widx;
-#pragma unroll 1
-    for (int c = 0; c < total_chunks; ++c) {
-      if (sub == 0) {
-        mbar_wait(eb, ph);
-        if (elect_one()) mbar_expect_tx(fb, (uint32_t)((left < cps ? left : cps) * b_chunk_bytes));
-      }
-      if (elect_one()) tma_load_3d(dst, &p.bmap, fb, kc, n0, widx);
-      dst += b_chunk_bytes;
-      kc += KCHUNK;
-      --left;
-      if (kc == p.R && left > 0) { kc = 0; widx = p.taps[++t].widx; }
-      if (++sub == cps) {
-        sub = 0; dst += stage_skip; fb += 8u; eb += 8u;
-        if (++s == nst) { s = 0; ph ^= 1u; dst = smem_base + b_off; fb = bar_base; eb = bar_base + 8u * nst; }
-      }
-    }
+    if (prof && warp == 0 && lane == 0) { prof[0] = (unsigned long long)(clock64() - t_setup); prof[1] = 0; }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 0, 0);
     // descriptor = constant high word | (address >> 4): only the low word changes per stage / chunk / k-step
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024);
     const uint32_t b_off = (uint32_t)(cps * A_STAGE_BYTES);
-    int sub = 0, s = 0, left = total_chunks;
+    int s = 0, left = total_chunks;
     uint32_t ph = 0;
-    uint32_t a_addr = smem_base, b_addr = smem_base + b_off, fb = bar_base, eb = bar_base + 8u * nst;
+    uint32_t a_addr = smem_base, fb = bar_base, eb = bar_base + 8u * nst;
     uint32_t acc = 0u;
+    long long wait_cycles = 0;
 #pragma unroll 1
-    for (int c = 0; c < total_chunks; ++c) {
-      if (sub == 0) {
+    for (int it = 0; it < iters; ++it) {
+      if (prof) {
+        const long long w0 = clock64();
         mbar_wait(fb, ph);
-        tc_fence_after();
+        wait_cycles += clock64() - w0;
+      } else {
+        mbar_wait(fb, ph);
       }
-      --left;
-      ++sub;
+      tc_fence_after();
+      const bool two = (cps == 2) && (left >= 2);
+      left -= cps;
       if (elect_one()) {
         const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-        const uint64_t bd = desc_hi | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+        const uint64_t bd = desc_hi | (uint64_t)(((a_addr + b_off) & 0x3FFFFu) >> 4);
         umma_bf16(tmem_base, ad, bd, idesc, acc);
 #pragma unroll
         for (int k = 1; k < KCHUNK / 16; ++k)                // +32 B per K=16 step -> +2 in 16-byte units
           umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc, 1u);
-        if (sub == cps || left == 0) {
-          umma_commit(eb);                                 // frees this smem stage when the MMAs retire
-          if (left == 0) umma_commit(tmem_full_bar);        // accumulator complete
+        if (two) {
+          const uint64_t ad2 = ad + (uint64_t)(A_STAGE_BYTES >> 4), bd2 = bd + (uint64_t)(b_chunk_bytes >> 4);
+#pragma unroll
+          for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16(tmem_base, ad2 + 2u * k, bd2 + 2u * k, idesc, 1u);
         }
+        umma_commit(eb);                                   // frees this smem stage when the MMAs retire
+        if (it == iters - 1) umma_commit(tmem_full_bar);    // accumulator complete
       }
       acc = 1u;
-      a_addr += A_STAGE_BYTES; b_addr += b_chunk_bytes;
-      if (sub == cps) {
-        sub = 0; fb += 8u; eb += 8u;
-        a_addr += (uint32_t)(stage_bytes - cps * A_STAGE_BYTES); b_addr += (uint32_t)(stage_bytes - cps * b_chunk_bytes);
-        if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; b_addr = smem_base + b_off; fb = bar_base; eb = bar_base + 8u * nst; }
-      }
+      a_addr += stage_bytes; fb += 8u; eb += 8u;
+      if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
     }
-    if (prof && lane == 0) { prof[2] = (unsigned long long)(clock64() - t_setup); prof[3] = 0; }
+    if (prof && lane == 0) { prof[2] = (unsigned long long)(clock64() - t_setup); prof[3] = (unsigned long long)wait_cycles; }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int q = warp & 3;
@@ -417,7 +413,7 @@ struct TcWgradParams {
   WgAtom atoms[2 * 208];            // up to 27 taps x 8 chunks (512 ch) = 216 -> mtiles <= 208
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_WG_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -647,7 +643,7 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   // hide each other's prologue / epilogue and are preferred over deeper stages.
   const int budget = total_tiles > 148 ? 100 * 1024 : 200 * 1024;
   p.cps = (budget / (2 * chunk_bytes)) >= 2 ? 2 : 1;
-  p.cps = std::max(1, std::min(4, env_int("GG_TC_CPS", p.cps)));
+  p.cps = std::max(1, std::min(2, env_int("GG_TC_CPS", p.cps)));
   const int stage_bytes = p.cps * chunk_bytes;
   p.stages = std::max(2, std::min(8, budget / stage_bytes));
   const int out_bytes = TILE_M * p.BN * (p.out_bf16 ? 2 : 4);          // the epilogue stages the tile in the pipeline buffers
@@ -851,7 +847,7 @@ int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, f
   std::call_once(once, [] { cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   int rcl = GG_OK;
   for (int r = 0; r < g_repeat && rcl == GG_OK; ++r) {
-    Launch((unsigned)(tiles * p.splits), TC_THREADS, smem, st)(tc_wgrad_kernel, p, dw);
+    Launch((unsigned)(tiles * p.splits), TC_WG_THREADS, smem, st)(tc_wgrad_kernel, p, dw);
     rcl = check_launch("tc_wgrad");
   }
   return rcl;

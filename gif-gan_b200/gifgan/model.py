@@ -135,6 +135,10 @@ class DCGAN(object):
 
     # ------------------------------------------------------------------------------
     def discriminator(self, image, y=None, reuse=False, train=True, groups=1, stop_at_h2=False):
+        with self.store.absolute_scope(self.scope_prefix):
+            return self._discriminator(image, y, reuse, train, groups, stop_at_h2)
+
+    def _discriminator(self, image, y=None, reuse=False, train=True, groups=1, stop_at_h2=False):
         """model.py:268-296.  `groups=2` runs D(real) and D(fake) as one batch whose halves are
         batch-normalised separately (identical numbers to two calls, half the launches).  `stop_at_h2`
         evaluates only what D_activations needs (what TF's pruning does for VID_DCGAN's fetches)."""
@@ -166,6 +170,10 @@ class DCGAN(object):
             return (ops.sigmoid(h3) if self.want_sigmoid else None), h3
 
     def generator(self, z, y=None, train=True, out=None):
+        with self.store.absolute_scope(self.scope_prefix):
+            return self._generator(z, y, train, out)
+
+    def _generator(self, z, y=None, train=True, out=None):
         """model.py:298-344 (and, with train=False, the sampler graph of model.py:346-389).
         `out=` lets the last layer write the images into a caller buffer (e.g. the fake half of D's batch)."""
         B = z.shape[0]

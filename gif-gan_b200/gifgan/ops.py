@@ -118,6 +118,17 @@ class VariableStore:
     def scope_name(self):
         return "".join(s + "/" for s in self._scope)
 
+    @contextlib.contextmanager
+    def absolute_scope(self, prefix: str):
+        """Enter the scope `prefix` ("a/b/") regardless of the caller's current scope: a model remembers the scope
+        it was built under, so its methods find their variables wherever they are called from."""
+        saved = self._scope
+        self._scope = [p for p in prefix.split("/") if p]
+        try:
+            yield self
+        finally:
+            self._scope = saved
+
     # -- creation -------------------------------------------------------------------
     def get_variable(self, name, shape, initializer, trainable=True, filter_taps=None) -> Var:
         full = self.scope_name() + name

@@ -69,6 +69,7 @@ class VID_DCGAN(object):
         self.activation_noise_std = activation_noise_std
         self.first_frame_loss_scalar = first_frame_loss_scalar
         self.store = store if store is not None else ops.default_store()
+        self.scope_prefix = self.store.scope_name()      # e.g. 'video_gan/' (z_model.py:63)
         self.dp = dp
 
         # Batch norm layers (z_model_lib.py:36-44; bn3 / bn0,1,4 are constructed but never used there either)
@@ -149,6 +150,10 @@ class VID_DCGAN(object):
         return torch.cat([z[:, None, :].expand(Bv, T, z.shape[1]), self._frame_numbers], 2).reshape(Bv * T, -1)
 
     def generator(self, z, reuse=False, train=True):
+        with self.store.absolute_scope(self.scope_prefix + 'video_generator/'):
+            return self._generator(z, reuse, train)
+
+    def _generator(self, z, reuse=False, train=True):
         layers = Layers()
         z_reshaped = self._z_with_numbers(z)
         layers.gr0 = linear(z_reshaped, 512, 'gvideo_0', bn=self.g_bn0, train=train, act='relu')
@@ -158,6 +163,10 @@ class VID_DCGAN(object):
         return layers.gr3, layers
 
     def discriminator(self, vid, reuse=False, groups=1):
+        with self.store.absolute_scope(self.scope_prefix + 'video_discriminator/'):
+            return self._discriminator(vid, reuse, groups)
+
+    def _discriminator(self, vid, reuse=False, groups=1):
         """z_model_lib.py:384-418 (batch norm always in train mode).  `groups=2`: real and fake clips as one batch."""
         layers = Layers()
         nclips = vid.shape[0] // self.vid_length
