@@ -45,13 +45,19 @@ __device__ __forceinline__ void pdl_grid_sync() {
 
 struct Launch {
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
-  Launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  cudaLaunchAttribute attr[2];
+  // cluster_x > 1: thread-block cluster (cluster_x, 1, 1); grid.x must be a multiple of it
+  Launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x = 1) {
     cfg = cudaLaunchConfig_t();
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cluster_x > 1) {
+      attr[1].id = cudaLaunchAttributeClusterDimension;
+      attr[1].val.clusterDim.x = (unsigned)cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+      cfg.numAttrs = 2;
+    }
   }
   template <typename... KArgs, typename... Args>
   void operator()(void (*kernel)(KArgs...), Args&&... args) {

@@ -115,6 +115,7 @@ struct TcPixParams {
   int out_bf16;
   int stages;
   int cps;                    // 64-wide K chunks per pipeline stage (MMAs per commit = 4 * cps)
+  int splitk;                 // cluster size along K: the CTAs of a cluster share one output tile (1 = no cluster)
   unsigned long long* prof;   // optional per-CTA clock64 breakdown (tools/tc_sweep.py --prof), 8 slots per CTA
   double* stats;              // optional fused batch-norm statistics [groups][2][Nout] (fp32 output only)
   int stats_groups;
@@ -157,7 +158,9 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 1);
 
   // ---- which tile ------------------------------------------------------------------------
-  const int tile = blockIdx.x;
+  const int S = p.splitk;                      // cluster (S, 1, 1): rank in cluster == blockIdx.x % S
+  const int tile = (int)blockIdx.x / S;
+  const int rank = (int)blockIdx.x - tile * S;
   int ci = 0;
 #pragma unroll 1
   for (int c = 1; c < p.nclasses; ++c) if (tile >= p.cls[c].tile_begin) ci = c;
@@ -171,7 +174,11 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const int mw0 = tw * p.bw, mh0 = th * p.bh, md0 = td * p.bd, mn0 = tn * p.bn;
   const int n0 = nt * p.BN;
   const int kchunks = p.R / KCHUNK;
-  const int total_chunks = (C.tap_end - C.tap_begin) * kchunks;
+  // split-K: rank r of the cluster reduces the chunk range [c_begin, c_begin + total_chunks) of the tile's K loop
+  const int tile_chunks = (C.tap_end - C.tap_begin) * kchunks;
+  const int per_rank = (tile_chunks + S - 1) / S;
+  const int c_begin = rank * per_rank;
+  const int total_chunks = min(per_rank, tile_chunks - c_begin);       // >= 1 (host guarantees (S - 1) * per_rank < tile_chunks)
   const int iters = (total_chunks + p.cps - 1) / p.cps;                // pipeline stages to run; the last may be partial
   const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;   // power of two >= 32
 
@@ -210,8 +217,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     int s = (cps == 2) ? 0 : j;
     uint32_t ph = 1;                                                // fresh barriers: waiting on parity 1 passes immediately
     if (s >= nst) { s -= nst; ph ^= 1u; }
-    int t = C.tap_begin, kc = j * KCHUNK;
-    while (kc >= p.R) { kc -= p.R; ++t; }
+    int t = C.tap_begin + (c_begin + j) / kchunks, kc = ((c_begin + j) % kchunks) * KCHUNK;
     const int nstage_total = iters;                                 // stages of this tile
     // trips: one per chunk of parity j; with cps == 2 a final odd stage still needs this warp's arrival on the barrier
     const int my_chunks = (total_chunks - j + 1) / 2;
@@ -287,33 +293,89 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       if (++s == nst) { s = 0; ph ^= 1u; a_addr = smem_base; fb = bar_base; eb = bar_base + 8u * nst; }
     }
     if (prof && lane == 0) { prof[2] = (unsigned long long)(clock64() - t_setup); prof[3] = (unsigned long long)wait_cycles; }
-  } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
-    const int q = warp & 3;
-    const int row = q * 32 + lane;                 // accumulator row = pixel within the tile
+  }
+
+  // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+  const bool epi = (warp >= 2 && warp <= 5);
+  const int q = warp & 3;
+  const int row = q * 32 + lane;                 // accumulator row = pixel within the tile
+  const uint32_t row_off = (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+  const uint32_t mask_smem = bar_base + 8u * (2 * p.stages + 2);        // 4 x u32 after the barriers
+  long long t_acc = 0;
+  if (epi) {
     const int iw = row % p.bw, ih = (row / p.bw) % p.bh, id = (row / (p.bw * p.bh)) % p.bd, in = row / (p.bw * p.bh * p.bd);
     // rows of a partial tile that fall outside the M grid must not enter the fused batch statistics
     const bool row_valid = (mw0 + iw) < C.Mw && (mh0 + ih) < C.Mh && (md0 + id) < C.Md && (mn0 + in) < p.Mn;
     const uint32_t vmask = __ballot_sync(0xffffffffu, row_valid);
-    const uint32_t mask_smem = bar_base + 8u * (2 * p.stages + 2);        // 4 x u32 after the barriers
     if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(mask_smem + 4u * q), "r"(vmask) : "memory");
     if (lane == 0) mbar_wait(tmem_full_bar, 0);   // one polling lane per warp: the spin must not steal issue slots
     __syncwarp();                                 // from the producer / MMA threads that share these schedulers
     tc_fence_after();
-    const long long t_acc = clock64();
-    // Accumulator -> (+bias, activation) -> shared memory in the 128B-swizzled box layout -> TMA tensor store.
-    // All pipeline stages are free once tmem_full fired (every MMA that read them has retired), so the tile
-    // is staged at smem_base: [BN*esz/128 column blocks][128 rows][128 B], 16-byte chunk index XOR (row & 7).
-    // The TMA store clips partial tiles and, for conv_up, scatters to the stride-s output parity view.
-    const uint32_t row_off = (uint32_t)row * 128u;
-    const uint32_t sw = (uint32_t)(row & 7);
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      float v[32];
+    t_acc = clock64();
+  }
+
+  // ---- split-K: reduce the S partial accumulators of the cluster through distributed shared memory ----
+  // All pipeline stages are free once tmem_full fired (every MMA that read them has retired), so each CTA parks its raw
+  // fp32 partial at smem_base in the staging layout P = [BN/32 column blocks][128 rows][128 B, 16-byte chunk ^ (row & 7)].
+  // Rank r then sums rows [r*128/S, (r+1)*128/S) over all S partials (S-1 remote reads per 16-byte chunk) and writes the
+  // result into the LEADER's P (row slices are disjoint, so in place); the leader alone runs the normal epilogue from P.
+  if (S > 1) {
+    if (epi) {
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const uint32_t blk = smem_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int g = 0; g < 8; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((((uint32_t)g) ^ sw) << 4)), "r"(r[g * 4]), "r"(r[g * 4 + 1]),
+                       "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3]) : "memory");
+      }
+      tc_fence_before();
+    }
+    cluster_sync_all();
+    if (epi) {
+      const int rows_per = TILE_M / S;
+      const int cpr_log = (p.BN == 256) ? 6 : (p.BN == 128 ? 5 : 4);          // 16-byte chunks per row = BN / 4
+      const int nchunks = rows_per << cpr_log;
+      for (int i = (warp - 2) * 32 + lane; i < nchunks; i += 128) {
+        const int rr = rank * rows_per + (i >> cpr_log);
+        const int ch = i & ((1 << cpr_log) - 1);
+        const uint32_t off = smem_base + (uint32_t)(ch >> 3) * (TILE_M * 128u) + (uint32_t)rr * 128u + ((((uint32_t)ch & 7u) ^ (uint32_t)(rr & 7)) << 4);
+        float4 part[8];
+#pragma unroll
+        for (int pr = 0; pr < 8; ++pr)
+          part[pr] = (pr < S) ? dsmem_ld4(dsmem_addr(off, (uint32_t)pr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = part[0];
+#pragma unroll
+        for (int pr = 1; pr < 8; ++pr) { acc.x += part[pr].x; acc.y += part[pr].y; acc.z += part[pr].z; acc.w += part[pr].w; }
+        dsmem_st4(dsmem_addr(off, 0u), acc);
+      }
+    }
+    cluster_sync_all();
+  }
+
+  if (epi && rank == 0) {
+    // Accumulator (TMEM, or the reduced fp32 tile in P when S > 1) -> (+bias, activation) -> shared memory in the
+    // 128B-swizzled box layout -> TMA tensor store.  The TMA store clips partial tiles and, for conv_up, scatters to the
+    // stride-s output parity view.  bf16 staging of a split-K tile sits behind P (host checks the capacity).
+    const uint32_t out_base = (S > 1 && p.out_bf16) ? smem_base + (uint32_t)p.BN * 512u : smem_base;
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      float v[32];
+      if (S > 1) {
+        const uint32_t blk = smem_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[g * 4]), "=f"(v[g * 4 + 1]), "=f"(v[g * 4 + 2]), "=f"(v[g * 4 + 3])
+                       : "r"(blk + ((((uint32_t)g) ^ sw) << 4)) : "memory");
+      } else {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      }
       if (bias != nullptr) {
         const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
 #pragma unroll
@@ -322,7 +384,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       act_fwd_vec<32>(v, p.act, p.act_param);
       if (p.out_bf16) {
         // 32 bf16 = 64 B = 4 chunks: half of the 128-byte row of column block c0/64
-        const uint32_t blk = smem_base + (uint32_t)(c0 >> 6) * (TILE_M * 128u) + row_off;
+        const uint32_t blk = out_base + (uint32_t)(c0 >> 6) * (TILE_M * 128u) + row_off;
         const uint32_t ch0 = (uint32_t)((c0 & 63) >> 3);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -332,8 +394,8 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
                        "r"(*reinterpret_cast<uint32_t*>(&p1)), "r"(*reinterpret_cast<uint32_t*>(&p2)), "r"(*reinterpret_cast<uint32_t*>(&p3)) : "memory");
         }
       } else {
-        // 32 fp32 = 128 B = the whole row of column block c0/32
-        const uint32_t blk = smem_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
+        // 32 fp32 = 128 B = the whole row of column block c0/32 (in place when the source is P)
+        const uint32_t blk = out_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((((uint32_t)g) ^ sw) << 4)), "f"(v[g * 4]), "f"(v[g * 4 + 1]),
@@ -346,7 +408,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       const int nblk = p.out_bf16 ? (p.BN >> 6) : (p.BN >> 5);
       const int cstep = p.out_bf16 ? 64 : 32;
       for (int b = 0; b < nblk; ++b)
-        tma_store_5d(&p.omap[ci], smem_base + (uint32_t)b * (TILE_M * 128u), n0 + b * cstep, mw0, mh0, md0, mn0);
+        tma_store_5d(&p.omap[ci], out_base + (uint32_t)b * (TILE_M * 128u), n0 + b * cstep, mw0, mh0, md0, mn0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (p.stats != nullptr) {
@@ -402,6 +464,7 @@ struct WgAtom {           // one 64-row half of an M tile: (tap, channel chunk o
 struct TcWgradParams {
   CUtensorMap lmap[TC_MAX_VIEWS];   // large tensor views (same maps as conv_down's A operand, box = WG_PIX pixels)
   CUtensorMap smap;                 // small tensor
+  CUtensorMap dwmap;                // dw as a 2-D fp32 tensor [taps*C, K], box = (32 columns = 128 B, 64 rows), for the reduce-store
   int natoms, mtiles, ntiles_n, splits;
   int BN;                           // k-channel tile (multiple of 64, <= 256)
   int bw, bh, bd, bn;               // pixel box: product == WG_PIX
@@ -536,24 +599,39 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;                 // 0..127: atom (row >> 6), channel (row & 63)
-    const WgAtom a = (row < 64) ? a0 : a1;
-    const bool valid = a.c0 >= 0;
-    float* dst = dw + ((int64_t)a.widx * p.C + (valid ? a.c0 : 0) + (row & 63)) * p.K + k0;
     if (lane == 0) mbar_wait(tmem_full_bar, 0);
     __syncwarp();
     tc_fence_after();
+    // Accumulator -> shared memory (128B-swizzled boxes: [BN/32 column blocks][128 rows][128 B], the same staging as the
+    // fp32 epilogue of tc_pixgemm) -> TMA reduce-store (cp.reduce.async.bulk.tensor .add): the += into the flat gradient
+    // buffer is done by the L2 on whole 128-byte lines, one instruction per 64 x 32 box, instead of 64 scattered 16-byte
+    // red.global per thread (which bounded this kernel: 3 splits x 13 MB of 16-byte atomics for d_h3).
+    // All pipeline stages are free once tmem_full fired.
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
-      if (valid) {
+      const uint32_t blk = smem_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(r[j])),
-                       "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
-                       : "memory");
-        }
+      for (int g = 0; g < 8; ++g)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((((uint32_t)g) ^ sw) << 4)), "r"(r[g * 4]), "r"(r[g * 4 + 1]),
+                     "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3]) : "memory");
+    }
+    fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA engine
+    asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+    if (warp == 2 && lane == 0) {
+      const int nblk = p.BN >> 5;
+      for (int h = 0; h < 2; ++h) {
+        const WgAtom a = h ? a1 : a0;
+        if (a.c0 < 0) continue;                                // padding atom of an odd atom count
+        const int row0 = (int)a.widx * p.C + (int)a.c0;        // first dw row of this atom
+        for (int b = 0; b < nblk; ++b)
+          tma_reduce_add_2d(&p.dwmap, smem_base + (uint32_t)b * (TILE_M * 128u) + (uint32_t)h * (64u * 128u), k0 + b * 32, row0);
       }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // complete (not only read) before the CTA retires
     }
     tc_fence_before();
   }
@@ -626,13 +704,24 @@ static int env_int(const char* name, int dflt) {
 }
 void tc_set_repeat(int n) { g_repeat = n < 1 ? 1 : n; }
 
-static int pick_bn(int Nout, int64_t mtiles) {
-  // widest tile that still yields >= ~1 wave of CTAs
+// Output-channel tile and split-K factor.  An M=128 tcgen05.mma from shared memory costs max(~78, N/2) cycles, so a
+// wider N is cheaper per FLOP -- but at batch 64 the wide tiles leave most SMs idle.  Default: the widest tile that
+// still yields ~1 wave of CTAs, no split.  GG_TC_SPLITK=S (2/4/8) instead takes the widest N that divides Nout and
+// splits K over a cluster of S CTAs reduced through distributed shared memory (implemented and parity-tested; with
+// the current pull-style reduction the 13 k-cycle DSMEM phase eats the main-loop gain at these sizes: 22 -> 31 us for
+// g_h1.down, profiles/r01k_tc_clock64.log -- a push-style reduce-scatter is the next step).
+static void pick_tile(int Nout, int64_t mtiles, int min_chunks, int* bn_out, int* split_out) {
+  int S = std::max(1, std::min(8, env_int("GG_TC_SPLITK", 1)));
   int bn = Nout % 256 == 0 ? 256 : (Nout % 128 == 0 ? 128 : 64);
-  while (bn > 64 && mtiles * (Nout / bn) < 120) bn /= 2;
+  if (S == 1) while (bn > 64 && mtiles * (Nout / bn) < 120) bn /= 2;
   const int forced = env_int("GG_TC_BN", 0);
   if (forced > 0 && Nout % forced == 0) bn = forced;
-  return bn;
+  if (S > 1) {
+    const int64_t tiles = mtiles * (Nout / bn);
+    while (S > 1 && (tiles * S > 148 || min_chunks / S < 4)) S /= 2;
+    while (S > 1 && (int64_t)(S - 1) * ((min_chunks + S - 1) / S) >= min_chunks) S /= 2;   // every rank needs >= 1 chunk
+  }
+  *bn_out = bn; *split_out = S;
 }
 
 static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* out, cudaStream_t st) {
@@ -641,12 +730,13 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   // top of its MMAs, so a stage should carry >= 8 MMAs (two 64-wide K chunks): 128 x 128 x 16 then runs at ~80
   // cycles per MMA instead of ~137.  When the grid exceeds one wave, two co-resident CTAs per SM (<= ~100 KB each)
   // hide each other's prologue / epilogue and are preferred over deeper stages.
-  const int budget = total_tiles > 148 ? 100 * 1024 : 200 * 1024;
+  const int budget = (total_tiles * p.splitk > 148 && p.splitk == 1) ? 100 * 1024 : 200 * 1024;
   p.cps = (budget / (2 * chunk_bytes)) >= 2 ? 2 : 1;
   p.cps = std::max(1, std::min(2, env_int("GG_TC_CPS", p.cps)));
   const int stage_bytes = p.cps * chunk_bytes;
   p.stages = std::max(2, std::min(8, budget / stage_bytes));
-  const int out_bytes = TILE_M * p.BN * (p.out_bf16 ? 2 : 4);          // the epilogue stages the tile in the pipeline buffers
+  // the epilogue stages the tile in the pipeline buffers; a split-K tile parks its fp32 partial there first (+ bf16 staging behind it)
+  const int out_bytes = p.splitk > 1 ? TILE_M * p.BN * (p.out_bf16 ? 6 : 4) : TILE_M * p.BN * (p.out_bf16 ? 2 : 4);
   while (p.stages * stage_bytes < out_bytes) ++p.stages;
   p.stages = std::max(1, std::min(p.stages, env_int("GG_TC_STAGES", p.stages)));
   GG_REQUIRE(p.stages * stage_bytes >= out_bytes, GG_ERR_INVALID, "tc_pixgemm: GG_TC_STAGES too small for the output tile");
@@ -657,7 +747,7 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   std::call_once(once, [] { cudaFuncSetAttribute(tc_pixgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   int rc = GG_OK;
   for (int r = 0; r < g_repeat && rc == GG_OK; ++r) {
-    Launch(total_tiles, TC_THREADS, smem, st)(tc_pixgemm_kernel, p, bias, out);
+    Launch(total_tiles * p.splitk, TC_THREADS, smem, st, p.splitk)(tc_pixgemm_kernel, p, bias, out);
     rc = check_launch("tc_pixgemm");
   }
   return rc;
@@ -679,8 +769,8 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, con
   c.Md = d->Do; c.Mh = d->Ho; c.Mw = d->Wo;
   c.tw = ceil_div(d->Wo, p.bw); c.th = ceil_div(d->Ho, p.bh); c.td = ceil_div(d->Do, p.bd); c.tn = ceil_div(d->N, p.bn);
   const int64_t mtiles = (int64_t)c.tw * c.th * c.td * c.tn;
-  p.BN = pick_bn(d->K, mtiles);
   const int taps = d->kd * d->kh * d->kw;
+  pick_tile(d->K, mtiles, taps * (d->C / KCHUNK), &p.BN, &p.splitk);
   const uint64_t bdims[3] = {(uint64_t)d->C, (uint64_t)d->K, (uint64_t)taps};
   const uint64_t bstr[2] = {(uint64_t)d->C * 2, (uint64_t)d->C * d->K * 2};
   const uint32_t bbox[3] = {64, (uint32_t)p.BN, 1};
@@ -773,7 +863,11 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
         }
         p.cls[ncls++] = c;
       }
-  p.BN = pick_bn(d->C, tiles);
+  {
+    int min_taps = TC_MAX_TAPS;
+    for (int i = 0; i < ncls; ++i) min_taps = std::min(min_taps, p.cls[i].tap_end - p.cls[i].tap_begin);
+    pick_tile(d->C, tiles, min_taps * (d->K / KCHUNK), &p.BN, &p.splitk);
+  }
   p.ntiles_n = d->C / p.BN;
   for (int i = 0; i < ncls; ++i) p.cls[i].tile_begin *= p.ntiles_n;
   // a class without taps (stride > kernel) still has to write bias/zeros: the kernel handles iters == 0? no -> reject
@@ -833,11 +927,23 @@ int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, f
   p.BN = d->K % 256 == 0 ? 256 : (d->K % 128 == 0 ? 128 : 64);
   p.ntiles_n = d->K / p.BN;
   const int64_t tiles = (int64_t)p.mtiles * p.ntiles_n;
-  int splits = (int)std::max<int64_t>(1, (148 * 2 + tiles - 1) / tiles);
+  // One CTA per SM (the pipeline takes ~190 KB of shared memory): size the pixel split for ONE full wave.  (The
+  // earlier target of 2 x 148 CTAs ran as 2-3 waves, the last one nearly empty: d_h3 100 tiles x 3 = 300 CTAs.)
+  const int64_t cta_target = env_int("GG_WG_CTAS", 148);
+  int splits = (int)std::max<int64_t>(1, cta_target / tiles);
   splits = std::min(splits, std::max(1, p.ptiles / 4));
   p.ptiles_per_split = ceil_div(p.ptiles, splits);
   p.splits = ceil_div(p.ptiles, p.ptiles_per_split);
   p.C = d->C; p.K = d->K;
+  {
+    const int taps_total = d->kd * d->kh * d->kw;
+    const uint64_t ddims[2] = {(uint64_t)d->K, (uint64_t)taps_total * d->C};
+    const uint64_t dstr[1] = {(uint64_t)d->K * 4};
+    const uint32_t dbox[2] = {32, 64};
+    GG_REQUIRE(((uintptr_t)dw % 16) == 0, GG_ERR_INVALID, "tensor-core wgrad needs a 16-byte aligned gradient buffer");
+    rc = encode_tmap(&p.dwmap, GG_F32, dw, 2, ddims, dstr, dbox);
+    if (rc) return rc;
+  }
   p.pps = std::max(1, std::min(4, env_int("GG_WG_PPS", 2)));      // 8 MMAs per commit (see launch_pix)
   const int stage_bytes = p.pps * (2 + p.BN / 64) * WG_ATOM_BYTES;
   p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));

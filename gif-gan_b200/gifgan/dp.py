@@ -46,14 +46,76 @@ class DataParallel:
             b = e
         return out
 
-    def allreduce(self, optim):
-        """Sum-all-reduce the gradient range of `optim`'s group.  Adam divides by world_size."""
+    # -- overlapped exchange ------------------------------------------------------------
+    # Backward produces gradients in reverse creation order, and a group's gradients are one contiguous range laid out
+    # in creation order: when the filter gradient of layer L has been enqueued, everything at or above L's offset is
+    # final.  begin_update() arms a hook that ops._run_wgrad calls after each filter-gradient launch; once the finished
+    # tail [offset(L), done_hi) reaches `early_bytes` it is all-reduced on the communication stream while the rest of
+    # the backward pass (the remaining dgrad / batch-norm / wgrad kernels) keeps the SMs busy.  allreduce() then only
+    # has the head of the range left.  All collectives go to the one communication stream, in the same order on every
+    # rank; under CUDA-graph capture the stream fork/join becomes parallel graph branches.
+    early_bytes = 2 << 20
+
+    def _comm(self):
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() and dist.get_backend() == "nccl" else False
+        return self.comm_stream
+
+    def begin_update(self, optim):
+        """Call before the backward pass of an update whose gradients `optim` owns."""
         if self.world_size <= 1:
             return
-        grads = optim.store.flat["grads"]
+        from . import ops
         b, e = optim.range()
-        for (x, y) in self.buckets(b, e):
-            dist.all_reduce(grads[x:y], op=dist.ReduceOp.SUM)
+        self._cur = dict(optim=optim, lo=b, done_hi=e, issued=[])
+        ops.GRAD_READY_HOOK = self.grad_ready
+
+    def _issue(self, lo, hi, extra_streams=()):
+        grads = self._cur["optim"].store.flat["grads"]
+        comm = self._comm()
+        if comm is False:                          # gloo / CPU: no streams, reduce in place
+            for (x, y) in self.buckets(lo, hi):
+                dist.all_reduce(grads[x:y], op=dist.ReduceOp.SUM)
+        else:
+            comm.wait_stream(torch.cuda.current_stream())
+            for s in extra_streams:
+                comm.wait_stream(s)
+            with torch.cuda.stream(comm):
+                for (x, y) in self.buckets(lo, hi):
+                    dist.all_reduce(grads[x:y], op=dist.ReduceOp.SUM)
+        self._cur["issued"].append((lo, hi))
+
+    def grad_ready(self, var, producer_stream=None):
+        """Hook: `var`'s filter gradient has just been enqueued (on producer_stream, if not the current stream)."""
+        cur = getattr(self, "_cur", None)
+        if cur is None or not (cur["lo"] <= var.offset < cur["optim"].range()[1]):
+            return
+        if var.offset >= cur["done_hi"]:
+            raise RuntimeError(f"{var.name}: a gradient was produced after its bucket had been all-reduced "
+                               "(a filter used at two call sites of one update needs early_bytes = inf)")
+        if (cur["done_hi"] - var.offset) * 4 < self.early_bytes:
+            return
+        self._issue(var.offset, cur["done_hi"], (producer_stream,) if producer_stream is not None else ())
+        cur["done_hi"] = var.offset
+
+    def allreduce(self, optim):
+        """Sum-all-reduce the gradient range of `optim`'s group (what begin_update's early buckets have not covered yet)
+        and make the current stream wait for the exchange.  Adam divides by world_size."""
+        if self.world_size <= 1:
+            return
+        from . import ops
+        ops.GRAD_READY_HOOK = None
+        cur = getattr(self, "_cur", None)
+        if cur is None or cur["optim"] is not optim:
+            b, e = optim.range()
+            cur = self._cur = dict(optim=optim, lo=b, done_hi=e, issued=[])
+        if cur["done_hi"] > cur["lo"]:
+            self._issue(cur["lo"], cur["done_hi"])
+        comm = self._comm()
+        if comm is not False:
+            torch.cuda.current_stream().wait_stream(comm)
+        self.last_buckets = cur["issued"]
+        self._cur = None
 
     def broadcast_parameters(self, store):
         """Make every rank start from rank 0's variables (weights and EMAs)."""

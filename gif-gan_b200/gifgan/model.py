@@ -237,7 +237,9 @@ class DCGAN(object):
         if images.data_ptr() != both.data_ptr():
             both[:B].copy_(images)
         self.d_optim.zero_grad()
-        with ops.trainable(self.d_vars), ops.overlap_wgrad():
+        if self.dp is not None:
+            self.dp.begin_update(self.d_optim)
+        with ops.trainable(self.d_vars), ops.overlap_wgrad(), ops.stats_arena():
             with torch.no_grad():
                 self.generator(z, y, out=both[B:])
             if self.noise_std:
@@ -255,7 +257,9 @@ class DCGAN(object):
     def g_update(self, z, y=None, apply=True):
         """sess.run([g_optim, g_sum]) (model.py:232-234): G fwd, D(fake), backward through D into g_vars, Adam."""
         self.g_optim.zero_grad()
-        with ops.trainable(self.g_vars), ops.overlap_wgrad():
+        if self.dp is not None:
+            self.dp.begin_update(self.g_optim)
+        with ops.trainable(self.g_vars), ops.overlap_wgrad(), ops.stats_arena():
             G = self.generator(z, y)
             logits = self.discriminator(add_noise(G, self.noise_std), y, reuse=True)[1]
             losses = sigmoid_cross_entropy_loss(logits, target=1.0)

@@ -205,7 +205,9 @@ class VID_DCGAN(object):
         if images.data_ptr() != both.data_ptr():
             both[:n].copy_(images)
         self.d_optim.zero_grad()
-        with ops.trainable(self.d_var_list), ops.overlap_wgrad():
+        if self.dp is not None:
+            self.dp.begin_update(self.d_optim)
+        with ops.trainable(self.d_var_list), ops.overlap_wgrad(), ops.stats_arena():
             with torch.no_grad():
                 G_out, _ = self.generator(z, train=True)
                 img.generator(G_out, train=False, out=both[n:])                  # img_dcgan.sampler(G_out)
@@ -228,7 +230,9 @@ class VID_DCGAN(object):
         """One generator update (z_model_lib.py:233-239)."""
         img = self.img_dcgan
         self.g_optim.zero_grad()
-        with ops.trainable(self.g_var_list), ops.overlap_wgrad():
+        if self.dp is not None:
+            self.dp.begin_update(self.g_optim)
+        with ops.trainable(self.g_var_list), ops.overlap_wgrad(), ops.stats_arena():
             G_out, _ = self.generator(z, train=True)
             frames = img.generator(G_out, train=False)
             act = img.discriminator(add_noise(frames, self.image_noise_std), reuse=True, train=False, stop_at_h2=True)[2]

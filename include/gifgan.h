@@ -156,6 +156,8 @@ int gg_bn_fwd_infer(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, in
 /* dx = d(loss)/dx given dy = d(loss)/d(act(bn(x))).  train=1: batch statistics
  * (gradient flows through mean/var); train=0: inference statistics in save_mean/save_rstd
  * as written by gg_bn_infer_stats.  dgamma/dbeta (+=, may be NULL).                      */
+/* train: 0 = inference-mode statistics (dx = gamma*rstd*g), 1 = batch statistics, 2 = batch statistics with a workspace
+ * the caller has already zeroed (saves one memset per layer when a whole update shares one zeroed arena). */
 int gg_bn_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, void* dx, int32_t dx_dtype,
               int64_t rows, int32_t C, int32_t groups, const float* gamma, const float* beta,
               const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta,

@@ -48,6 +48,24 @@ def _worker(rank, world, port, out_dir):
     assert torch.all(c.grad == 100.0)                                   # the other group is untouched
     dp.allreduce(opt_g)
     assert torch.all(c.grad == 200.0)
+    # overlapped exchange: the hook reduces the finished tail of the range early, allreduce() the remaining head
+    a.grad.fill_(1.0 + rank); b.grad.fill_(10.0 * (rank + 1))
+    dp.early_bytes = 100
+    dp.begin_update(opt_d)
+    assert ops.GRAD_READY_HOOK is not None
+    dp.grad_ready(b)                                                    # [b.offset, end): 40 floats >= 100 B -> reduced now
+    assert torch.all(b.grad == 30.0) and torch.all(a.grad == 1.0 + rank)
+    dp.allreduce(opt_d)                                                 # the head [a.offset, b.offset)
+    assert torch.all(a.grad == 3.0) and torch.all(b.grad == 30.0)
+    assert dp.last_buckets == [(b.offset, opt_d.range()[1]), (a.offset, b.offset)] and ops.GRAD_READY_HOOK is None
+    dp.begin_update(opt_d)
+    dp.grad_ready(a)
+    try:
+        dp.grad_ready(b)                                                # a second gradient for an already reduced bucket
+        raise AssertionError("late gradient not detected")
+    except RuntimeError:
+        pass
+    dp.allreduce(opt_d)
     # broadcast: every rank ends with rank 0's variables
     dp.broadcast_parameters(st)
     assert torch.all(c.data == 0.0)

@@ -201,3 +201,16 @@ def test_c3_deconv2d_image_side(B, h, w_, Ci):
     assert relerr(xt.grad, gx) < TOL
     assert relerr(st.vars["g/w"].grad, gw) < TOL
     assert relerr(st.vars["g/biases"].grad, gb) < TOL
+
+
+@pytest.mark.parametrize("splitk", [2, 4, 8])
+def test_tc_cluster_split_k(splitk, monkeypatch):
+    """GG_TC_SPLITK: the K loop of a tile split over a thread-block cluster and reduced through distributed shared
+    memory must give the same conv / deconv results (fp32-accumulated partials, one final rounding)."""
+    monkeypatch.setenv("GG_TC_SPLITK", str(splitk))
+    try:
+        test_tc_conv2d("d_h3", 16, 8, 256, 512)
+        test_tc_deconv2d("g_h1", 16, 4, 512, 256)
+        test_tc_conv2d("d_h2", 16, 16, 128, 256)
+    finally:
+        monkeypatch.delenv("GG_TC_SPLITK", raising=False)
