@@ -77,6 +77,17 @@ def step_flops_per_image(size=64, c=3, gf=64, df=64, z_dim=100):
 
 
 # ---------------------------------------------------------------------------------------------
+def ncu_by_layer():
+    """profiles/*_ncu_by_layer.json (tools/summarize_profiles.py): per-launch DRAM traffic and tensor-pipe activity of each
+    layer kernel from the committed `ncu --set full` capture of tools/layer_kernels.py (newest file wins)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_by_layer.json")), key=os.path.getmtime)
+    if not files:
+        return {}, None
+    with open(files[-1]) as f:
+        return json.load(f), os.path.basename(files[-1])
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -227,8 +238,9 @@ def layer_rooflines(model, batch, precision, flush, reps=5, launches=10):
                     continue   # d_h0 dgrad is not needed in the D update
                 ms = time_kernel(fns[kind], flush, reps, launches)
                 tc = ops._tc_ok(C, K, large, small)
+                path = "tcgen05" if tc else ("mma.sync" if (C == 3 and K % 64 == 0 and precision == "bf16") else "simt")
                 rows.append(dict(kernel=f"{name}.{kind}[B={B_}]", ms=ms, flops=fl, tflops=fl / ms / 1e9, uses=n_use,
-                                 path="tcgen05" if tc else "simt", share_ms=ms * n_use))
+                                 path=path, share_ms=ms * n_use, order=len(rows)))
     rows.sort(key=lambda r: -r["share_ms"])
     return rows
 
@@ -320,8 +332,12 @@ def run_ours(args):
     rows = layer_rooflines(model, B, args.precision, flush)
     top = rows[0]
     step_fl = step_flops_per_image() * B
+    ncu, ncu_file = ncu_by_layer()
+    prof = ncu.get(top["kernel"], {})
+    traffic = (prof["dram_read_bytes"] + prof["dram_write_bytes"]) if prof else None
     roofline = {"bound": "tensor", "kernel": top["kernel"], "path": top["path"], "achieved": top["tflops"], "peak": peaks["tf_burst"],
-                "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tf_burst"], "traffic": None, "peak_source": peaks["source"],
+                "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tf_burst"], "traffic": traffic, "peak_source": peaks["source"],
+                "ncu": {"file": ncu_file, "tensor_pipe_active_pct": prof.get("tensor_pct"), "duration_us": prof.get("dur_us")} if prof else None,
                 "flops_per_launch": top["flops"], "launch_ms": top["ms"],
                 "step": {"gemm_tflop_per_step": step_fl / 1e12, "achieved_tflops": step_fl / (dev_ms / args.steps) / 1e9,
                          "frac_of_sustained": step_fl / (dev_ms / args.steps) / 1e9 / peaks["tf_sustained"]},

@@ -678,9 +678,25 @@ bias_grad_kernel(const TD* __restrict__ dy, float* __restrict__ db, int64_t rows
 #pragma unroll
   for (int v = 0; v < VEC; ++v) s[v] = 0.f;
   if (c < C) {
-    for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows; r += (int64_t)gridDim.x * ty_dim) {
-      if (VEC == 4) { float4 t = ld4(dy + r * C + c); s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w; }
-      else s[0] += ldf(dy + r * C + c);
+    constexpr int UB = 4;                            // 4 rows per trip, loads first (see colsum_kernel)
+    const int64_t rstep = (int64_t)gridDim.x * ty_dim;
+    for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows; r += UB * rstep) {
+      float t[UB][VEC];
+#pragma unroll
+      for (int ub = 0; ub < UB; ++ub) {
+        const int64_t rr = r + ub * rstep;
+        if (rr < rows) {
+          if (VEC == 4) { float4 q = ld4(dy + rr * C + c); t[ub][0] = q.x; t[ub][1] = q.y; t[ub][2] = q.z; t[ub][3] = q.w; }
+          else t[ub][0] = ldf(dy + rr * C + c);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) t[ub][v] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int ub = 0; ub < UB; ++ub)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] += t[ub][v];
     }
   }
   __shared__ float red[BN_THREADS * 4];

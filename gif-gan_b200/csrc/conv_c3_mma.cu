@@ -92,20 +92,42 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
 #pragma unroll
   for (int i = 0; i < 16; ++i) bv[i] = bias ? __ldg(bias + kb + t * 16 + i) : 0.f;
 
-  for (int tile = blockIdx.x / kblocks; tile < ntiles; tile += gridDim.x / kblocks) {
+  // Patch elements of this thread: e = tid + 256 k -> (row a, element x in the row, column x / 3), fixed for all tiles.
+  constexpr int PK = (DN_PR * DN_PC * 3 + 255) / 256;           // 8 elements per thread
+  int pdesc[PK];                                                // a | x << 8 | (x / 3) << 16, or -1
+#pragma unroll
+  for (int k = 0; k < PK; ++k) {
+    const int e = tid + 256 * k;
+    const int a = e / (DN_PC * 3), x = e - a * (DN_PC * 3);
+    pdesc[k] = (e < DN_PR * DN_PC * 3) ? (a | (x << 8) | ((x / 3) << 16)) : -1;
+  }
+  float pv[PK];
+  auto prefetch = [&](int tile) {                               // global -> registers (loads stay in flight)
+    const int n = tile / (tiles_h * tiles_w);
+    const int rem = tile - n * tiles_h * tiles_w;
+    const int i0 = 2 * ((rem / tiles_w) * DN_TH) - 1, j0 = 2 * ((rem % tiles_w) * DN_TW) - 1;
+    const float* img = large + (int64_t)n * H * W * 3;
+#pragma unroll
+    for (int k = 0; k < PK; ++k) {
+      const int dsc = pdesc[k];
+      const int i = i0 + (dsc & 0xff), j = j0 + (dsc >> 16);
+      const bool ok = dsc >= 0 && i >= 0 && i < H && j >= 0 && j < W;
+      pv[k] = ok ? __ldg(img + ((int64_t)i * W + j0) * 3 + ((dsc >> 8) & 0xff)) : 0.f;
+    }
+  };
+  const int tstride = gridDim.x / kblocks;
+  int tile = blockIdx.x / kblocks;
+  if (tile < ntiles) prefetch(tile);
+  for (; tile < ntiles; tile += tstride) {
     const int n = tile / (tiles_h * tiles_w);
     const int rem = tile - n * tiles_h * tiles_w;
     const int p0 = (rem / tiles_w) * DN_TH, q0 = (rem % tiles_w) * DN_TW;
-    const int i0 = 2 * p0 - 1, j0 = 2 * q0 - 1;
     __syncthreads();                                  // previous tile's fragments are consumed
-    for (int e = tid; e < DN_PR * (DN_PC * 3); e += 256) {
-      const int a = e / (DN_PC * 3), x = e - a * (DN_PC * 3);
-      const int i = i0 + a, j = j0 + x / 3;
-      float v = 0.f;
-      if (i >= 0 && i < H && j >= 0 && j < W) v = __ldg(large + ((int64_t)n * H + i) * W * 3 + (int64_t)j0 * 3 + x);
-      sp[a * DN_PROW + x] = __float2bfloat16_rn(v);
-    }
+#pragma unroll
+    for (int k = 0; k < PK; ++k)
+      if (pdesc[k] >= 0) sp[(pdesc[k] & 0xff) * DN_PROW + ((pdesc[k] >> 8) & 0xff)] = __float2bfloat16_rn(pv[k]);
     __syncthreads();
+    if (tile + tstride < ntiles) prefetch(tile + tstride);      // next patch streams in while this one is multiplied
     float acc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
@@ -148,7 +170,7 @@ constexpr int UP_PIX = 72;                                 // bf16 per staged pi
 constexpr int UP_WROW = 9 * 64 + 8;                        // 584 bf16 per n row of the expanded filter
 
 template <typename TSM>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 c3m_up_kernel(const TSM* __restrict__ small, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ large,
               int N, int H, int W, int Ho, int Wo, int K, int act, float act_param) {
   pdl_grid_sync();
@@ -341,7 +363,7 @@ int c3m_conv_down(const gg_conv_desc* d, const float* large, const float* w, con
 
 int c3m_conv_up(const gg_conv_desc* d, const void* small, const float* w, const float* bias, float* large, cudaStream_t st) {
   const int ntiles = d->N * ceil_div(d->Ho, UP_TH) * ceil_div(d->Wo, UP_TW);
-  const int grid = std::min(ntiles, 148 * 2);
+  const int grid = std::min(ntiles, 148 * 3);     // 3 co-resident CTAs per SM (45 KB of shared memory, <= 85 registers each)
   if (d->small_dtype == GG_F32)
     Launch(grid, 256, 0, st)(c3m_up_kernel<float>, (const float*)small, w, bias, large, d->N, d->H, d->W, d->Ho, d->Wo, d->K, d->act, d->act_param);
   else

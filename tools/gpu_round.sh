@@ -14,7 +14,7 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/plain_$TAG.log 2>&1 
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2600 --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_launches_$TAG.log 2>&1
 python tools/layer_kernels.py > $O/plain_layers_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'tc_pixgemm|tc_wgrad|c3_' -c 44 -o $O/prof_layers_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:'tc_pixgemm|tc_wgrad|c3m_|c3_' -c 64 -o $O/prof_layers_$TAG \
     python tools/layer_kernels.py > $O/ncu_full_$TAG.log 2>&1
 ncu -i $O/prof_layers_$TAG.ncu-rep --page raw --csv > $O/prof_layers_${TAG}_raw.csv 2>/dev/null
 SZ=$(stat -c %s $O/prof_layers_$TAG.ncu-rep 2>/dev/null || echo 0)

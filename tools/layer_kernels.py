@@ -30,6 +30,8 @@ def main():
     model = DCGAN(None, batch_size=a.batch, output_size=64, c_dim=3)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rows = bench.layer_rooflines(model, a.batch, a.precision, flush, reps=a.reps, launches=a.launches)
+    for r in sorted(rows, key=lambda r: r["order"]):
+        print("ORDER", r["kernel"], flush=True)                  # execution order: maps the ncu launch list back to layers
     for r in rows:
         print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}), flush=True)
     print("TOTAL share_ms", round(sum(r["share_ms"] for r in rows), 4))

@@ -81,8 +81,36 @@ def full(tag):
     print("wrote", f"{tag}_ncu_full.csv", len(rows), "kernels")
 
 
+def by_layer(tag):
+    """Map the `ncu --set full` rows (two launches per layer kernel: warm-up + timed) back to bench.py's layer labels
+    through the ORDER lines tools/layer_kernels.py prints."""
+    raw, order = os.path.join(G, f"prof_layers_{tag}_raw.csv"), os.path.join(G, f"plain_layers_{tag}.log")
+    if not (os.path.exists(raw) and os.path.exists(order)):
+        return
+    labels = [l.split()[1] for l in open(order) if l.startswith("ORDER ")]
+    r = list(csv.reader(open(raw)))
+    hdr, units, rows = r[0], r[1], r[2:]
+    ix = {k: hdr.index(k) for k in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                                    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = {}
+    for i, lab in enumerate(labels):
+        if 2 * i + 1 >= len(rows):
+            break
+        row = rows[2 * i + 1]                                     # the timed launch
+        out[lab] = dict(kernel=row[ix["Kernel Name"]].split("(")[0], dur_us=float(row[ix["gpu__time_duration.sum"]]),
+                        dram_read_bytes=float(row[ix["dram__bytes_read.sum"]]) * scale[units[ix["dram__bytes_read.sum"]]],
+                        dram_write_bytes=float(row[ix["dram__bytes_write.sum"]]) * scale[units[ix["dram__bytes_write.sum"]]],
+                        tensor_pct=float(row[ix["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]]))
+    import json
+    with open(os.path.join(P, f"{tag}_ncu_by_layer.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", f"{tag}_ncu_by_layer.json", len(out), "layers")
+
+
 if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     tag = sys.argv[1]
     launches(tag)
     full(tag)
+    by_layer(tag)
