@@ -64,6 +64,10 @@ int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void
 // bn.cu
 int bn_accumulate_stats(const void* x, int x_dt, int64_t rows, int C, int groups, double* sums, cudaStream_t st);
 int tc_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStream_t);
+bool tc_upcat_ok(const gg_conv_desc*);
+size_t tc_upcat_bytes(const gg_conv_desc*);
+int tc_pack_upcat(const gg_conv_desc*, const float*, void*, cudaStream_t);
+int tc_conv_up_cat(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
 void tc_set_repeat(int);
 void tc_set_prof(void*);
 }  // namespace gg
@@ -98,6 +102,7 @@ extern "C" int gg_conv_down(const gg_conv_desc* d, const void* large, const void
 }
 extern "C" int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large, void* stream) {
   GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_up: null pointer");
+  if ((d->flags & GG_CONV_TENSOR_CORE) && (d->flags & GG_CONV_UPCAT)) return tc_conv_up_cat(d, small, w, bias, large, (cudaStream_t)stream);
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream);
   if (c3m_applicable(d)) GG_REPEAT(c3m_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream));
   if (c3_applicable(d)) GG_REPEAT(c3_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream));
@@ -129,11 +134,18 @@ extern "C" int gg_conv_up_stats(const gg_conv_desc* d, const void* small, const 
   GG_REQUIRE(d && large && w && small && stats && groups >= 1, GG_ERR_INVALID, "conv_up_stats: bad argument");
   int fused = 0;
   int rc;
-  if (d->flags & GG_CONV_TENSOR_CORE) rc = tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream, stats, groups, &fused);
+  if ((d->flags & GG_CONV_TENSOR_CORE) && (d->flags & GG_CONV_UPCAT)) rc = tc_conv_up_cat(d, small, w, bias, large, (cudaStream_t)stream, stats, groups, &fused);
+  else if (d->flags & GG_CONV_TENSOR_CORE) rc = tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream, stats, groups, &fused);
   else rc = gg_conv_up(d, small, w, bias, large, stream);
   if (rc || fused) return rc;
   const int64_t rows = (int64_t)d->N * d->D * d->H * d->W;
   return bn_accumulate_stats(large, d->large_dtype, rows, d->C, groups, stats, (cudaStream_t)stream);
+}
+
+extern "C" size_t gg_upcat_bytes(const gg_conv_desc* d) { return d ? tc_upcat_bytes(d) : 0; }
+extern "C" int gg_pack_filter_upcat(const gg_conv_desc* d, const float* w, void* wcat, void* stream) {
+  GG_REQUIRE(d && w && wcat, GG_ERR_INVALID, "pack_filter_upcat: null pointer");
+  return tc_pack_upcat(d, w, wcat, (cudaStream_t)stream);
 }
 
 static gg_conv_desc no_act(const gg_conv_desc* d) { gg_conv_desc c = *d; c.act = GG_ACT_NONE; return c; }

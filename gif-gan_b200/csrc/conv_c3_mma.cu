@@ -154,8 +154,14 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
         for (int j = 0; j < 8; ++j) { v[2 * j] = acc[j][2 * half] + bv[2 * j]; v[2 * j + 1] = acc[j][2 * half + 1] + bv[2 * j + 1]; }
         act_fwd_vec<16>(v, act, act_param);
         TSM* dst = small + (((int64_t)n * Ho + p) * Wo + q) * K + kb + t * 16;
+        if (sizeof(TSM) == 2) {                          // 16 bf16 = two 16-byte stores; the quad covers the pixel's 128-byte row
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+          d4[0] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+          d4[1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
       }
     }
   }

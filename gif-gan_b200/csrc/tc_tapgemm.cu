@@ -115,6 +115,7 @@ struct TcPixParams {
   int out_bf16;
   int stages;
   int cps;                    // 64-wide K chunks per pipeline stage (MMAs per commit = 4 * cps)
+  int cat_C;                  // > 0: the N axis is the concatenation of the output parity classes, cat_C channels each (tc_conv_up_cat)
   int splitk;                 // cluster size along K: the CTAs of a cluster share one output tile (1 = no cluster)
   unsigned long long* prof;   // optional per-CTA clock64 breakdown (tools/tc_sweep.py --prof), 8 slots per CTA
   double* stats;              // optional fused batch-norm statistics [groups][2][Nout] (fp32 output only)
@@ -377,7 +378,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       }
       if (bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
+        const float4* b4 = reinterpret_cast<const float4*>(bias + (p.cat_C ? (n0 + c0) % p.cat_C : n0 + c0));
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float4 b = __ldg(b4 + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
       }
@@ -407,8 +408,11 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     if (warp == 2 && lane == 0) {
       const int nblk = p.out_bf16 ? (p.BN >> 6) : (p.BN >> 5);
       const int cstep = p.out_bf16 ? 64 : 32;
-      for (int b = 0; b < nblk; ++b)
-        tma_store_5d(&p.omap[ci], out_base + (uint32_t)b * (TILE_M * 128u), n0 + b * cstep, mw0, mh0, md0, mn0);
+      for (int b = 0; b < nblk; ++b) {
+        const int col = n0 + b * cstep;                          // concatenated classes: column -> (class output map, channel)
+        const int oc = p.cat_C ? col / p.cat_C : ci, ch = p.cat_C ? col % p.cat_C : col;
+        tma_store_5d(&p.omap[oc], out_base + (uint32_t)b * (TILE_M * 128u), ch, mw0, mh0, md0, mn0);
+      }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (p.stats != nullptr) {
@@ -433,9 +437,10 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
             if ((mrow >> b) & 1u) { s += v; s2 = fmaf(v, v, s2); }
           }
         }
-        double* dst = p.stats + ((long long)grp * 2) * p.Nout + n0 + col;
+        const int statC = p.cat_C ? p.cat_C : p.Nout;          // every parity class of a channel feeds the same statistic
+        double* dst = p.stats + ((long long)grp * 2) * statC + (n0 + col) % statC;
         atomicAdd(dst, (double)s);
-        atomicAdd(dst + p.Nout, (double)s2);
+        atomicAdd(dst + statC, (double)s2);
       }
     }
     if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after this
@@ -888,6 +893,146 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
     if (fused) *fused = 1;
   }
   return launch_pix(p, (int)(tiles * p.ntiles_n), bias, large, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_up with the output parity classes concatenated along N  (64-channel outputs: d_h1 dgrad, g_h3 forward)
+// ------------------------------------------------------------------------------------------------
+// With N = 64 an M=128 tcgen05.mma runs at ~42 % of the tensor peak (its cost is max(~78, N/2) cycles), and the four
+// parity classes of a 5x5 stride-2 deconvolution read the SAME nine shifted input boxes (shift (dp, dq) in {-1,0,1}^2)
+// with different filter taps.  So: one tile = 128 small-grid positions x (4 classes x 64 channels) = N 256, K loop over
+// the 9 shifts; the packed filter wcat[shift][class*C + c][k] holds w[tap(class, shift)][c][k], or zero where the class
+// does not use the shift (25 of 36 (class, shift) pairs are real: 69 % useful MACs at the full N=256 rate).  A traffic
+// drops from 25 to 9 boxes per K chunk and the launch is one wave of M/128 CTAs instead of four classes of them.
+constexpr int UPCAT_MAX_SHIFTS = 27;
+struct UpcatPlan {
+  int ncls, nshift;
+  int cls_a[8][3];                       // class -> (ad, ah, aw)
+  int shift[UPCAT_MAX_SHIFTS][3];        // shift -> (od, oh, ow)
+  int tap[UPCAT_MAX_SHIFTS][8];          // (shift, class) -> filter tap index or -1
+};
+
+bool tc_upcat_ok(const gg_conv_desc* d) {
+  const int ncls = d->sd * d->sh * d->sw;
+  return (d->flags & GG_CONV_TENSOR_CORE) && ncls > 1 && ncls <= 8 && ncls * d->C == 256 && d->K % 64 == 0 && d->D % d->sd == 0 &&
+         d->H % d->sh == 0 && d->W % d->sw == 0 && d->small_dtype == GG_BF16;
+}
+
+static int upcat_plan(const gg_conv_desc* d, UpcatPlan* P) {
+  memset(P, 0, sizeof(*P));
+  for (int s = 0; s < UPCAT_MAX_SHIFTS; ++s) for (int c = 0; c < 8; ++c) P->tap[s][c] = -1;
+  int ncls = 0;
+  for (int ad = 0; ad < d->sd; ++ad)
+    for (int ah = 0; ah < d->sh; ++ah)
+      for (int aw = 0; aw < d->sw; ++aw) {
+        P->cls_a[ncls][0] = ad; P->cls_a[ncls][1] = ah; P->cls_a[ncls][2] = aw;
+        for (int a = 0; a < d->kd; ++a) {
+          if (posmod(ad + d->pd - a, d->sd) != 0) continue;
+          for (int b = 0; b < d->kh; ++b) {
+            if (posmod(ah + d->ph - b, d->sh) != 0) continue;
+            for (int e = 0; e < d->kw; ++e) {
+              if (posmod(aw + d->pw - e, d->sw) != 0) continue;
+              const int od = floordiv(ad + d->pd - a, d->sd), oh = floordiv(ah + d->ph - b, d->sh), ow = floordiv(aw + d->pw - e, d->sw);
+              int s = 0;
+              for (; s < P->nshift; ++s) if (P->shift[s][0] == od && P->shift[s][1] == oh && P->shift[s][2] == ow) break;
+              if (s == P->nshift) {
+                GG_REQUIRE(P->nshift < UPCAT_MAX_SHIFTS, GG_ERR_UNSUPPORTED, "upcat: too many shifts");
+                P->shift[s][0] = od; P->shift[s][1] = oh; P->shift[s][2] = ow; ++P->nshift;
+              }
+              P->tap[s][ncls] = (a * d->kh + b) * d->kw + e;
+            }
+          }
+        }
+        ++ncls;
+      }
+  P->ncls = ncls;
+  return GG_OK;
+}
+
+struct UpcatTable { int16_t tap[UPCAT_MAX_SHIFTS][8]; };
+
+__global__ void pack_upcat_kernel(const float* __restrict__ w, bf16* __restrict__ wcat, UpcatTable T, int ncls, int C, int K) {
+  pdl_grid_sync();
+  const int s = blockIdx.y, row = blockIdx.x;               // row = class * C + c
+  const int cls = row / C, c = row - cls * C;
+  const int tap = T.tap[s][cls];
+  bf16* dst = wcat + ((int64_t)s * ncls * C + row) * K;
+  const float* src = w + ((int64_t)(tap < 0 ? 0 : tap) * C + c) * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] = __float2bfloat16_rn(tap < 0 ? 0.f : __ldg(src + k));
+}
+
+size_t tc_upcat_bytes(const gg_conv_desc* d) {
+  UpcatPlan P;
+  if (!tc_upcat_ok(d) || upcat_plan(d, &P)) return 0;
+  return (size_t)P.nshift * P.ncls * d->C * d->K * sizeof(bf16);
+}
+
+int tc_pack_upcat(const gg_conv_desc* d, const float* w, void* wcat, cudaStream_t st) {
+  GG_REQUIRE(tc_upcat_ok(d), GG_ERR_UNSUPPORTED, "pack_filter_upcat: shape not eligible");
+  UpcatPlan P;
+  int rc = upcat_plan(d, &P);
+  if (rc) return rc;
+  UpcatTable T;
+  for (int s = 0; s < UPCAT_MAX_SHIFTS; ++s) for (int c = 0; c < 8; ++c) T.tap[s][c] = (int16_t)P.tap[s][c];
+  Launch(dim3(P.ncls * d->C, P.nshift), 128, 0, st)(pack_upcat_kernel, w, (bf16*)wcat, T, P.ncls, (int)d->C, (int)d->K);
+  return check_launch("pack_upcat");
+}
+
+int tc_conv_up_cat(const gg_conv_desc* d, const void* small, const void* wcat, const float* bias, void* large, cudaStream_t st,
+                   double* stats = nullptr, int groups = 1, int* fused = nullptr) {
+  int rc = check_tc(d, small, wcat, false, true);
+  if (rc) return rc;
+  GG_REQUIRE(tc_upcat_ok(d), GG_ERR_UNSUPPORTED, "conv_up (concatenated classes): shape not eligible");
+  UpcatPlan P;
+  rc = upcat_plan(d, &P);
+  if (rc) return rc;
+  TcPixParams p;
+  memset(&p, 0, sizeof(p));
+  const int Mw = d->W / d->sw, Mh = d->H / d->sh, Md = d->D / d->sd;      // positions = the small grid's footprint of one class
+  pick_box(Mw, Mh, Md, TILE_M, &p.bw, &p.bh, &p.bd, &p.bn);
+  const uint32_t abox[5] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+  rc = make_small_map(d, small, abox, &p.amap[0]);
+  if (rc) return rc;
+  TcClass& c = p.cls[0];
+  c.Md = Md; c.Mh = Mh; c.Mw = Mw;
+  c.tw = ceil_div(Mw, p.bw); c.th = ceil_div(Mh, p.bh); c.td = ceil_div(Md, p.bd); c.tn = ceil_div(d->N, p.bn);
+  const int64_t mtiles = (int64_t)c.tw * c.th * c.td * c.tn;
+  for (int s = 0; s < P.nshift; ++s) {
+    TcTap tp;
+    tp.view = 0; tp.od = (int8_t)P.shift[s][0]; tp.oh = (int8_t)P.shift[s][1]; tp.ow = (int8_t)P.shift[s][2];
+    tp.widx = (int16_t)s; tp.pad_ = 0;
+    p.taps[s] = tp;
+  }
+  c.tap_begin = 0; c.tap_end = P.nshift; c.tile_begin = 0;
+  const uint64_t esz = d->large_dtype == GG_BF16 ? 2 : 4;
+  for (int k = 0; k < P.ncls; ++k) {   // output map of class k: the stride-s parity view of the large tensor it writes
+    const int ad = P.cls_a[k][0], ah = P.cls_a[k][1], aw = P.cls_a[k][2];
+    const uint64_t base_elems = (((uint64_t)ad * d->H + ah) * d->W + aw) * d->C;
+    const uint64_t odims[5] = {(uint64_t)d->C, (uint64_t)Mw, (uint64_t)Mh, (uint64_t)Md, (uint64_t)d->N};
+    const uint64_t ostr[4] = {(uint64_t)d->sw * d->C * esz, (uint64_t)d->sh * d->W * d->C * esz, (uint64_t)d->sd * d->H * d->W * d->C * esz,
+                              (uint64_t)d->D * d->H * d->W * d->C * esz};
+    const uint32_t obox[5] = {(uint32_t)(128 / esz), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+    rc = encode_tmap(&p.omap[k], d->large_dtype, (const char*)large + base_elems * esz, 5, odims, ostr, obox);
+    if (rc) return rc;
+  }
+  p.BN = P.ncls * d->C;                 // 256
+  p.splitk = 1;
+  p.cat_C = d->C;
+  p.ntiles_n = 1;
+  const uint64_t bdims[3] = {(uint64_t)d->K, (uint64_t)p.BN, (uint64_t)P.nshift};
+  const uint64_t bstr[2] = {(uint64_t)d->K * 2, (uint64_t)p.BN * d->K * 2};
+  const uint32_t bbox[3] = {64, (uint32_t)p.BN, 1};
+  rc = encode_tmap_bf16(&p.bmap, wcat, 3, bdims, bstr, bbox);
+  if (rc) return rc;
+  p.nclasses = 1;
+  p.R = d->K; p.Nout = p.BN; p.Mn = d->N;
+  p.OD = d->D; p.OH = d->H; p.OW = d->W; p.osd = d->sd; p.osh = d->sh; p.osw = d->sw;
+  p.act = d->act; p.act_param = d->act_param; p.out_bf16 = (d->large_dtype == GG_BF16);
+  if (stats != nullptr && d->large_dtype == GG_F32 && groups >= 1 && d->N % groups == 0 && (d->N / groups) % p.bn == 0) {
+    p.stats = stats; p.stats_groups = groups;
+    if (fused) *fused = 1;
+  }
+  return launch_pix(p, (int)mtiles, bias, large, st);
 }
 
 int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw, cudaStream_t st) {

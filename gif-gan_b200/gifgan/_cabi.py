@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgifgan.so")
 GG_F32, GG_BF16 = 0, 1
 ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4, "tanh01": 5}
 CONV_TENSOR_CORE = 2
+CONV_UPCAT = 4
 
 
 class ConvDesc(C.Structure):
@@ -55,6 +56,8 @@ SIGNATURES = {
     "gg_conv3d_dgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),
     "gg_conv3d_wgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),
     "gg_pack_filter": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "gg_upcat_bytes": (_sz, [_dp]),
+    "gg_pack_filter_upcat": (C.c_int, [_dp, _vp, _vp, _vp]),
     "gg_linear_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "gg_linear_dgrad": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "gg_linear_wgrad": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),

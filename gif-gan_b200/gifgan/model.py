@@ -363,7 +363,7 @@ class DCGAN(object):
             self.d_optim.state.copy_(states[0]); self.g_optim.state.copy_(states[1])
             self.d_optim.t, self.g_optim.t = states[2], states[3]
             for v in self.store.vars.values():
-                v._packed_version = -1          # every replay starts with stale bf16 filter copies
+                v.invalidate_packed()          # every replay starts with stale bf16 filter copies
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -27,6 +27,7 @@ accumulation, tcgen05 tensor-core kernels where the channel counts allow.
 from __future__ import annotations
 
 import contextlib
+import os
 import ctypes
 from collections import OrderedDict
 
@@ -101,6 +102,26 @@ class Var:
                   "gg_pack_filter")
             self._packed_version = self.version
         return self._packed
+
+    def invalidate_packed(self):
+        """Force the bf16 copies to be rebuilt at their next use (CUDA-graph capture: every replay must repack)."""
+        self._packed_version = -1
+        self._upcat_version = -1
+
+    def packed_upcat(self, desc):
+        """bf16 filter with the output parity classes concatenated along N (gg_pack_filter_upcat), or None when the
+        shape is not eligible; refreshed after each update like packed()."""
+        L = cabi.lib()
+        nbytes = L.gg_upcat_bytes(ctypes.byref(desc))
+        if nbytes == 0:
+            return None
+        if getattr(self, "_upcat", None) is None or self._upcat.numel() * 2 != nbytes:
+            self._upcat = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=self.data.device)
+            self._upcat_version = -1
+        if self._upcat_version != self.version:
+            check(L.gg_pack_filter_upcat(ctypes.byref(desc), ptr(self.data), ptr(self._upcat), stream()), "gg_pack_filter_upcat")
+            self._upcat_version = self.version
+        return self._upcat
 
 
 class VariableStore:
@@ -390,7 +411,13 @@ def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, o
     large = out if out is not None else torch.empty(g.large_shape(ndim), dtype=out_dtype, device=small.device)
     tc = _tc_ok(g.C, g.K, small)
     d = g.desc(dt(large), dt(small), act, act_param, tc)
-    w = wvar.packed()[0] if tc else wvar.data
+    w = None
+    if tc and UPCAT:
+        w = wvar.packed_upcat(d)          # 64-channel outputs: parity classes concatenated along N (N = 256 MMAs)
+        if w is not None:
+            d.flags |= cabi.CONV_UPCAT
+    if w is None:
+        w = wvar.packed()[0] if tc else wvar.data
     if stats is not None:
         check(cabi.lib().gg_conv_up_stats(ctypes.byref(d), ptr(small), ptr(w), ptr(bias), ptr(large), ptr(stats), groups, stream()),
               "gg_conv_up_stats")
@@ -402,6 +429,7 @@ def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, o
 # Filter gradients are leaves of the backward pass: nothing downstream of them runs before the optimiser.  They are
 # issued on a side stream so that they overlap with the activation-gradient chain (under CUDA-graph capture the
 # fork/join becomes parallel branches of the graph).  join_side() is the join point (optimiser / all-reduce).
+UPCAT = os.environ.get("GG_UPCAT", "1") != "0"     # class-concatenated conv_up for 64-channel outputs (tc_conv_up_cat)
 OVERLAP_WGRAD = False      # enabled inside `with overlap_wgrad():` (the model's update functions)
 GRAD_READY_HOOK = None     # data parallel: called as hook(var, producer_stream) after a filter gradient was enqueued (dp.py)
 _SIDE = {}

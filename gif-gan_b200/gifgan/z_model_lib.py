@@ -307,7 +307,7 @@ class VID_DCGAN(object):
             self.d_optim.state.copy_(states[0]); self.g_optim.state.copy_(states[1])
             self.d_optim.t, self.g_optim.t = states[2], states[3]
             for v in self.store.vars.values():
-                v._packed_version = -1
+                v.invalidate_packed()
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -73,6 +73,8 @@ typedef struct gg_conv_desc {
 
 #define GG_CONV_ACCUMULATE 1 /* wgrad: dw += (default for wgrad; dw must be initialised) */
 #define GG_CONV_TENSOR_CORE 2 /* use the tcgen05 bf16 path: both dtypes BF16, packed bf16 weights */
+#define GG_CONV_UPCAT 4       /* gg_conv_up only, with GG_CONV_TENSOR_CORE: `w` is the buffer written by gg_pack_filter_upcat
+                               * (output parity classes concatenated along N; eligible when gg_upcat_bytes(desc) > 0) */
 
 int gg_version(void);
 const char* gg_last_error(void);
@@ -123,6 +125,10 @@ int gg_conv3d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float*
 /* fp32 filter [taps,C,K] -> bf16 copies for the tensor-core path:
  *   w_ck [taps,C,K] (K contiguous: B operand of conv_up) and w_kc [taps,K,C] (B operand of conv_down). */
 int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t C, int32_t K, void* stream);
+/* conv_up (deconv2d forward / conv2d dgrad, ops.py:86) whose stride classes x C == 256 (DCGAN: stride 2x2, C = 64): bytes of,
+ * and packing into, the class-concatenated bf16 filter [shifts][classes*C][K]; 0 bytes = shape not eligible. */
+size_t gg_upcat_bytes(const gg_conv_desc* d);
+int gg_pack_filter_upcat(const gg_conv_desc* d, const float* w, void* wcat, void* stream);
 
 /* ---- linear (ops.py:106-117: tf.matmul(input_, Matrix) + bias) ---------------------- */
 int gg_linear_fwd(const void* x, int32_t x_dtype, const float* matrix, const float* bias, void* y, int32_t y_dtype,
