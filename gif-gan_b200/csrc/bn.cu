@@ -20,6 +20,9 @@
 namespace gg {
 
 constexpr int BN_THREADS = 256;
+#ifndef GG_BN_UB
+#define GG_BN_UB 4          // rows per load batch in the streaming kernels (A/B switch: -DGG_BN_UB=1)
+#endif
 
 struct ColGeom {
   int tx, ty;         // block = tx * ty threads; tx over channel vectors, ty over rows
@@ -75,7 +78,7 @@ colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_
   if (active) {
     // rows in batches of 4: all loads of a batch are issued before any arithmetic (memory-level parallelism; the
     // one-row-per-trip loop was latency-bound at ~1.5 TB/s)
-    constexpr int UB = 4;
+    constexpr int UB = GG_BN_UB;
     const int64_t base = (int64_t)grp * rows_per_group;
     const int64_t rstep = (int64_t)gridDim.x * ty_dim;
     for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += UB * rstep) {
@@ -191,7 +194,7 @@ bn_train_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows
   }
   const int64_t base = (int64_t)grp * rows_per_group;
   const int64_t rstep = (int64_t)gridDim.x * ty_dim;
-  constexpr int UB = 4;
+  constexpr int UB = GG_BN_UB;
   for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += UB * rstep) {
     float o[UB][VEC];
 #pragma unroll
@@ -252,7 +255,7 @@ bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
   }
   const int64_t base = (int64_t)grp * rows_per_group;
   const int64_t rstep = (int64_t)gridDim.x * ty_dim;
-  constexpr int UB = 4;
+  constexpr int UB = GG_BN_UB;
   for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += UB * rstep) {
     float xv[UB][VEC], dv[UB][VEC];
 #pragma unroll
@@ -678,7 +681,7 @@ bias_grad_kernel(const TD* __restrict__ dy, float* __restrict__ db, int64_t rows
 #pragma unroll
   for (int v = 0; v < VEC; ++v) s[v] = 0.f;
   if (c < C) {
-    constexpr int UB = 4;                            // 4 rows per trip, loads first (see colsum_kernel)
+    constexpr int UB = GG_BN_UB;                            // 4 rows per trip, loads first (see colsum_kernel)
     const int64_t rstep = (int64_t)gridDim.x * ty_dim;
     for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows; r += UB * rstep) {
       float t[UB][VEC];

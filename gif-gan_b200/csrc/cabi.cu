@@ -48,6 +48,9 @@ int simt_linear_wgrad(const void*, int, const void*, int, float*, int, int, int,
 int skinny_linear_fwd(const void*, int, const float*, const float*, void*, int, int, int, int, int, float, cudaStream_t);
 int skinny_linear_dgrad(const void*, int, const float*, void*, int, int, int, int, cudaStream_t);
 int skinny_linear_wgrad(const void*, int, const void*, int, float*, int, int, int, cudaStream_t);
+bool thin_linear_ok(int rows, int in_dim, int out_dim);
+int thin_linear_fwd(const void*, int, const float*, const float*, void*, int, int, int, int, int, float, cudaStream_t);
+int thin_linear_wgrad(const void*, int, const void*, int, float*, float*, int, int, int, cudaStream_t);
 // conv_c3.cu
 bool c3_applicable(const gg_conv_desc*);
 int c3_conv_down(const gg_conv_desc*, const float*, const float*, const float*, void*, cudaStream_t);
@@ -164,6 +167,7 @@ extern "C" int gg_linear_fwd(const void* x, int32_t x_dt, const float* matrix, c
                              int32_t in_dim, int32_t out_dim, int32_t act, float ap, void* stream) {
   GG_REQUIRE(x && matrix && y && rows > 0 && in_dim > 0 && out_dim > 0, GG_ERR_INVALID, "linear_fwd: bad argument");
   if (out_dim <= 4) return skinny_linear_fwd(x, x_dt, matrix, bias, y, y_dt, rows, in_dim, out_dim, act, ap, (cudaStream_t)stream);
+  if (thin_linear_ok(rows, in_dim, out_dim)) return thin_linear_fwd(x, x_dt, matrix, bias, y, y_dt, rows, in_dim, out_dim, act, ap, (cudaStream_t)stream);
   return simt_linear_fwd(x, x_dt, matrix, bias, y, y_dt, rows, in_dim, out_dim, act, ap, (cudaStream_t)stream);
 }
 extern "C" int gg_linear_dgrad(const void* dy, int32_t dy_dt, const float* matrix, void* dx, int32_t dx_dt, int32_t rows, int32_t in_dim,
@@ -176,6 +180,8 @@ extern "C" int gg_linear_wgrad(const void* x, int32_t x_dt, const void* dy, int3
                                int32_t in_dim, int32_t out_dim, void* stream) {
   GG_REQUIRE(x && dy && rows > 0 && in_dim > 0 && out_dim > 0, GG_ERR_INVALID, "linear_wgrad: bad argument");
   int rc = GG_OK;
+  if (dmatrix && out_dim > 4 && thin_linear_ok(rows, in_dim, out_dim))          // one pass over dy gives dW and db
+    return thin_linear_wgrad(x, x_dt, dy, dy_dt, dmatrix, dbias, rows, in_dim, out_dim, (cudaStream_t)stream);
   if (dmatrix) {
     if (out_dim <= 4) rc = skinny_linear_wgrad(x, x_dt, dy, dy_dt, dmatrix, rows, in_dim, out_dim, (cudaStream_t)stream);
     else rc = simt_linear_wgrad(x, x_dt, dy, dy_dt, dmatrix, rows, in_dim, out_dim, (cudaStream_t)stream);

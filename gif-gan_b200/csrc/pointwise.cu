@@ -377,6 +377,23 @@ extern "C" int gg_axpby(const float* x, float a, float* y, float b, int64_t n, v
   return check_launch("axpby");
 }
 
+namespace gg {
+struct ScalarSrcs { const float* p[8]; };
+__global__ void gather_scalars_kernel(ScalarSrcs s, float* __restrict__ dst, int n) {
+  pdl_grid_sync();
+  const int i = threadIdx.x;
+  if (i < n && s.p[i] != nullptr) dst[i] = *s.p[i];
+}
+}  // namespace gg
+
+extern "C" int gg_gather_scalars(const float* const* srcs, int32_t n, float* dst, void* stream) {
+  GG_REQUIRE(srcs && dst && n > 0 && n <= 8, GG_ERR_INVALID, "gather_scalars: bad argument (1..8 device scalars)");
+  ScalarSrcs s;
+  for (int i = 0; i < 8; ++i) s.p[i] = i < n ? srcs[i] : nullptr;
+  Launch(1, 32, 0, (cudaStream_t)stream)(gather_scalars_kernel, s, dst, (int)n);
+  return check_launch("gather_scalars");
+}
+
 extern "C" int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t C, int32_t K, void* stream) {
   GG_REQUIRE(w && (w_ck || w_kc) && taps > 0 && C > 0 && K > 0, GG_ERR_INVALID, "pack_filter: bad argument");
   dim3 grid(ceil_div(K, 32), ceil_div(C, 32), taps), block(32, 8);
@@ -418,6 +435,162 @@ extern "C" int gg_adam_graph(float* p, const float* g, float* m, float* v, int64
 }
 
 namespace gg {
+// ---- thin-input linears: in_dim <= 128, wide output (g_h0_lin: z[B,100] -> [B,8192], model.py:304) -------------------
+// The generic SIMT GEMM spends 12-14 us on this 105-MFLOP problem.  Here a thread owns ONE output column: the matrix
+// row-slices it needs are coalesced across the block, the (tiny) x tile sits in shared memory transposed so that four
+// rows come back per broadcast 128-bit load, and 32 rows are accumulated in registers.
+constexpr int THIN_ROWS = 32, THIN_MAXK = 128, THIN_COLS = 64;   // block = 64 output columns x 4 reduction groups
+
+// y[r][j] = act(sum_i x[r][i] W[i][j] + b[j]): thread (c, g) accumulates i = g, g+4, ... for column c and 32 rows; the
+// four partial sums meet in shared memory.  8 matrix loads per thread are in flight before the first FMA.
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256)
+thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, TY* __restrict__ y, int rows,
+                int in_dim, int out_dim, int act, float ap) {
+  pdl_grid_sync();
+  __shared__ __align__(16) float xs[THIN_MAXK * THIN_ROWS];                 // [i][r]            16 KB
+  __shared__ __align__(16) float red[4 * THIN_ROWS * THIN_COLS];            // [g][r][c]         32 KB
+  const int r0 = blockIdx.y * THIN_ROWS;
+  for (int e = threadIdx.x; e < in_dim * THIN_ROWS; e += 256) {
+    const int r = e / in_dim, i = e - r * in_dim;               // coalesced over i
+    xs[i * THIN_ROWS + r] = (r0 + r < rows) ? ldf(x + (int64_t)(r0 + r) * in_dim + i) : 0.f;
+  }
+  __syncthreads();
+  const int c = threadIdx.x & (THIN_COLS - 1), g = threadIdx.x >> 6;
+  const int j = blockIdx.x * THIN_COLS + c;
+  const bool col_ok = j < out_dim;
+  float acc[THIN_ROWS];
+#pragma unroll
+  for (int r = 0; r < THIN_ROWS; ++r) acc[r] = 0.f;
+  for (int i0 = g; i0 < in_dim; i0 += 32) {
+    float m[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + 4 * u; m[u] = (col_ok && i < in_dim) ? __ldg(W + (int64_t)i * out_dim + j) : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + 4 * u;
+      if (i < in_dim) {
+        const float4* xr = reinterpret_cast<const float4*>(xs + i * THIN_ROWS);
+#pragma unroll
+        for (int q = 0; q < THIN_ROWS / 4; ++q) {
+          const float4 v = xr[q];
+          acc[4 * q] = fmaf(v.x, m[u], acc[4 * q]); acc[4 * q + 1] = fmaf(v.y, m[u], acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v.z, m[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v.w, m[u], acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < THIN_ROWS; ++r) red[(g * THIN_ROWS + r) * THIN_COLS + c] = acc[r];
+  __syncthreads();
+  if (!col_ok) return;
+  const float b = bias ? __ldg(bias + j) : 0.f;
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {                                  // this thread finishes rows g*8 .. g*8+7
+    const int r = g * 8 + k;
+    o[k] = b + red[(0 * THIN_ROWS + r) * THIN_COLS + c] + red[(1 * THIN_ROWS + r) * THIN_COLS + c] +
+           red[(2 * THIN_ROWS + r) * THIN_COLS + c] + red[(3 * THIN_ROWS + r) * THIN_COLS + c];
+  }
+  act_fwd_vec<8>(o, act, ap);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = r0 + g * 8 + k;
+    if (r < rows) stf(y + (int64_t)r * out_dim + j, o[k]);
+  }
+}
+
+// dW[i][j] += sum_r x[r][i] * dy[r][j]  (blockIdx.y: chunk of 32 input features);  db[j] += sum_r dy[r][j].
+// Thread (c, g) takes rows r = g, g+4, ...; partial sums meet in shared memory.
+template <typename TX, typename TD>
+__global__ void __launch_bounds__(256)
+thin_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __restrict__ dW, float* __restrict__ db, int rows, int in_dim,
+                  int out_dim) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) float thin_smem[];
+  float* red = thin_smem;                                       // [g][i][c]  32 KB
+  float* bred = red + 4 * THIN_ROWS * THIN_COLS;                // [g][c]      1 KB
+  float* xsw = bred + 4 * THIN_COLS;                            // [r][32] : this block's 32 input features of every row
+  const int i0 = blockIdx.y * THIN_ROWS;
+  for (int e = threadIdx.x; e < rows * THIN_ROWS; e += 256) {
+    const int r = e >> 5, i = e & 31;
+    xsw[e] = (i0 + i < in_dim) ? ldf(x + (int64_t)r * in_dim + i0 + i) : 0.f;
+  }
+  __syncthreads();
+  const int c = threadIdx.x & (THIN_COLS - 1), g = threadIdx.x >> 6;
+  const int j = blockIdx.x * THIN_COLS + c;
+  const bool col_ok = j < out_dim;
+  float acc[THIN_ROWS], bsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < THIN_ROWS; ++i) acc[i] = 0.f;
+  for (int rb = g; rb < rows; rb += 32) {
+    float gv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int r = rb + 4 * u; gv[u] = (col_ok && r < rows) ? ldf(dy + (int64_t)r * out_dim + j) : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = rb + 4 * u;
+      if (r < rows) {
+        bsum += gv[u];
+        const float4* xr = reinterpret_cast<const float4*>(xsw + r * THIN_ROWS);
+#pragma unroll
+        for (int q = 0; q < THIN_ROWS / 4; ++q) {
+          const float4 v = xr[q];
+          acc[4 * q] = fmaf(v.x, gv[u], acc[4 * q]); acc[4 * q + 1] = fmaf(v.y, gv[u], acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(v.z, gv[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v.w, gv[u], acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < THIN_ROWS; ++i) red[(g * THIN_ROWS + i) * THIN_COLS + c] = acc[i];
+  bred[g * THIN_COLS + c] = bsum;
+  __syncthreads();
+  if (!col_ok) return;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {                                  // this thread finishes input features g*8 .. g*8+7
+    const int i = g * 8 + k;
+    if (i0 + i < in_dim) {
+      const float sum = red[(0 * THIN_ROWS + i) * THIN_COLS + c] + red[(1 * THIN_ROWS + i) * THIN_COLS + c] +
+                        red[(2 * THIN_ROWS + i) * THIN_COLS + c] + red[(3 * THIN_ROWS + i) * THIN_COLS + c];
+      dW[(int64_t)(i0 + i) * out_dim + j] += sum;               // single writer per element
+    }
+  }
+  if (db != nullptr && blockIdx.y == 0 && g == 0) db[j] += bred[c] + bred[THIN_COLS + c] + bred[2 * THIN_COLS + c] + bred[3 * THIN_COLS + c];
+}
+
+bool thin_linear_ok(int rows, int in_dim, int out_dim) { return in_dim <= THIN_MAXK && out_dim >= 256 && rows <= 1024; }
+
+int thin_linear_fwd(const void* x, int x_dt, const float* W, const float* bias, void* y, int y_dt, int rows, int in_dim, int out_dim,
+                    int act, float ap, cudaStream_t st) {
+  const dim3 grid(ceil_div(out_dim, THIN_COLS), ceil_div(rows, THIN_ROWS));
+#define GG_TF(TX, TY) Launch(grid, 256, 0, st)(thin_fwd_kernel<TX, TY>, (const TX*)x, W, bias, (TY*)y, rows, in_dim, out_dim, act, ap)
+  if (x_dt == GG_F32 && y_dt == GG_F32) GG_TF(float, float);
+  else if (x_dt == GG_F32) GG_TF(float, bf16);
+  else if (y_dt == GG_F32) GG_TF(bf16, float);
+  else GG_TF(bf16, bf16);
+  return check_launch("thin_fwd");
+}
+
+// also accumulates the bias gradient when db != nullptr (same pass over dy)
+int thin_linear_wgrad(const void* x, int x_dt, const void* dy, int dy_dt, float* dW, float* db, int rows, int in_dim, int out_dim,
+                      cudaStream_t st) {
+  const dim3 grid(ceil_div(out_dim, THIN_COLS), ceil_div(in_dim, THIN_ROWS));
+  const size_t smem = ((size_t)rows * THIN_ROWS + 4 * THIN_ROWS * THIN_COLS + 4 * THIN_COLS) * sizeof(float);
+  GG_REQUIRE(smem <= 160 * 1024, GG_ERR_UNSUPPORTED, "thin_wgrad: too many rows");
+#define GG_TW(TX, TD)                                                                                                     \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) { cudaFuncSetAttribute(thin_wgrad_kernel<TX, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; } \
+    Launch(grid, 256, smem, st)(thin_wgrad_kernel<TX, TD>, (const TX*)x, (const TD*)dy, dW, db, rows, in_dim, out_dim);  \
+  } while (0)
+  if (x_dt == GG_F32 && dy_dt == GG_F32) GG_TW(float, float);
+  else if (x_dt == GG_F32) GG_TW(float, bf16);
+  else if (dy_dt == GG_F32) GG_TW(bf16, float);
+  else GG_TW(bf16, bf16);
+  return check_launch("thin_wgrad");
+}
+
 int skinny_linear_fwd(const void* x, int x_dt, const float* W, const float* bias, void* y, int y_dt, int rows, int in_dim, int out_dim,
                       int act, float ap, cudaStream_t st) {
 #define GG_SF(TX, TY) Launch(rows, PW_THREADS, 0, st)(skinny_fwd_kernel<TX, TY>, (const TX*)x, W, bias, (TY*)y, in_dim, out_dim, act, ap)

@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgifgan.so")
+LIB_PATH = os.environ.get("GG_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgifgan.so")   # GG_LIB: A/B builds of the same library
 
 GG_F32, GG_BF16 = 0, 1
 ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4, "tanh01": 5}
@@ -71,6 +71,7 @@ SIGNATURES = {
     "gg_bias_grad": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp]),
     "gg_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "gg_axpby": (C.c_int, [_vp, _f32, _vp, _f32, _i64, _vp]),
+    "gg_gather_scalars": (C.c_int, [C.POINTER(C.c_void_p), _i32, _vp, _vp]),
     "gg_get_std": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _sz, _vp]),
     "gg_sigmoid_ce": (C.c_int, [_vp, _i64, _f32, _f32, _vp, _i32, _vp, _vp]),
     "gg_mse": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _f32, _vp, _i32, _vp, _vp]),
@@ -130,6 +131,13 @@ def ptr(t):
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def gather_scalars(tensors, dst):
+    """dst[i] = tensors[i].reshape(-1)[0] for up to 8 device tensors (None entries are skipped): one launch."""
+    n = len(tensors)
+    arr = (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in tensors])
+    check(lib().gg_gather_scalars(arr, n, ptr(dst), stream()), "gg_gather_scalars")
 
 
 def launch_count() -> int:

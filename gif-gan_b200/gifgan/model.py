@@ -305,9 +305,7 @@ class DCGAN(object):
         outs = [d, g1, g2]
         if evals:
             outs += list(self.eval_losses(images, z, y))
-        L = ops.cabi.lib()
-        for i, o in enumerate(outs):
-            ops.check(L.gg_axpby(ops.ptr(o[0:1]), 1.0, ops.ptr(loss_vec[i:i + 1]), 0.0, 1, ops.stream()), "gg_axpby")
+        ops.cabi.gather_scalars([o.reshape(-1)[0:1] for o in outs], loss_vec)
         self.want_sigmoid = True
 
     def train_step(self, batch_images, batch_z, batch_labels=None, evals=False, use_graph=True, sync=True):

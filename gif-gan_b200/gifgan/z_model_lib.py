@@ -253,19 +253,15 @@ class VID_DCGAN(object):
     LOSS_KEYS = ("d_loss", "g_loss", "g_loss_first_frame", "images_std", "sampler_std", "real_D_std", "fake_D_std")
 
     def _step_device(self, images, z, disc_updates, gen_updates, loss_vec):
-        L = ops.cabi.lib()
-        put = lambda i, t: ops.check(L.gg_axpby(ops.ptr(t.reshape(-1)[0:1]), 1.0, ops.ptr(loss_vec[i:i + 1]), 0.0, 1, ops.stream()), "gg_axpby")
         self.img_dcgan.want_sigmoid = False
         for _ in range(disc_updates):
             d = self.d_update(images, z)
         for _ in range(gen_updates):
             g = self.g_update(z)
         self.img_dcgan.want_sigmoid = True
-        put(0, d["losses"]); put(1, g["losses"])
-        if g["first_frame"] is not None:
-            put(2, g["first_frame"])
-        for i, k in enumerate(("images_std", "sampler_std", "real_D_std", "fake_D_std")):
-            put(3 + i, d[k])
+        one = lambda t: None if t is None else t.reshape(-1)[0:1]
+        ops.cabi.gather_scalars([one(d["losses"]), one(g["losses"]), one(g["first_frame"])] +
+                                [one(d[k]) for k in ("images_std", "sampler_std", "real_D_std", "fake_D_std")], loss_vec)
 
     def train_step(self, batch_images, batch_z, disc_updates=1, gen_updates=2, use_graph=True, sync=True):
         """The loop body of z_model_lib.py:217-239 for one batch of clips ([Bv*T, s, s, c] frames, [Bv, z_in] latents;

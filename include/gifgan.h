@@ -181,6 +181,9 @@ int gg_bias_grad(const void* dy, int32_t dy_dtype, float* db, int64_t rows, int3
 int gg_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
 /* y = a*x + b*y  (fp32; gradient accumulation where a tensor feeds two consumers) */
 int gg_axpby(const float* x, float a, float* y, float b, int64_t n, void* stream);
+/* dst[i] = *srcs[i], i < n <= 8: `srcs` is a HOST array of device pointers (NULL entries are skipped) -- the scalar losses
+ * of a train step (model.py:241-243) collected with one launch for a single device->host read */
+int gg_gather_scalars(const float* const* srcs, int32_t n, float* dst, void* stream);
 /* ops.get_std (ops.py:125-128): sqrt(mean_f(var_batch(x[B,F]))) -> out[0]; ws >= 2*F*8 bytes */
 int gg_get_std(const void* x, int32_t x_dtype, int64_t B, int64_t F, float* out, void* ws, size_t ws_bytes, void* stream);
 
