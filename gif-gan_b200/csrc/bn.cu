@@ -57,7 +57,7 @@ template <typename TX, typename TD, int VEC, int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_per_group, int C,
               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-              const float* __restrict__ rstd, int act, float act_param, double* __restrict__ sums, int tx_dim) {
+              const float* __restrict__ rstd, int act, float act_param, double* __restrict__ sums, int tx_dim, int R) {
   pdl_grid_sync();
   const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
   const int grp = blockIdx.z;
@@ -129,8 +129,9 @@ colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_
     for (int v = 0; v < VEC; ++v) {
       float a = 0.f, b = 0.f;
       for (int j = 0; j < ty_dim; ++j) { a += red[0][(j * tx_dim + tx) * VEC + v]; b += red[1][(j * tx_dim + tx) * VEC + v]; }
-      atomicAdd(sums + ((int64_t)grp * 2 + 0) * C + c + v, (double)a);
-      if (MODE != 2) atomicAdd(sums + ((int64_t)grp * 2 + 1) * C + c + v, (double)b);
+      const int rep = (int)(blockIdx.x % (unsigned)R);        // replicated accumulators (common.cuh: bn_replicas)
+      atomicAdd(sums + bn_sum_index(rep, (int)gridDim.z, grp, 0, C, c + v), (double)a);
+      if (MODE != 2) atomicAdd(sums + bn_sum_index(rep, (int)gridDim.z, grp, 1, C, c + v), (double)b);
     }
   }
 }
@@ -159,13 +160,15 @@ bn_train_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows
   const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
   const int grp = blockIdx.z;
   const int c = (blockIdx.y * tx_dim + tx) * VEC;
-  if (c >= C) return;
+  const bool active = c < C;
+  const int R = bn_replicas(C, groups);
   const double inv = 1.0 / (double)rows_per_group;
+  if (!active) return;
   float mu[VEC], rs[VEC], ga[VEC], be[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    const double m = sums[((int64_t)grp * 2 + 0) * C + c + v] * inv;
-    double var = sums[((int64_t)grp * 2 + 1) * C + c + v] * inv - m * m;
+    const double m = bn_sum_read(sums, R, groups, grp, 0, C, c + v) * inv;
+    double var = bn_sum_read(sums, R, groups, grp, 1, C, c + v) * inv - m * m;
     var = var < 0.0 ? 0.0 : var;
     mu[v] = (float)m;
     rs[v] = rsqrtf((float)var + eps);
@@ -180,8 +183,8 @@ bn_train_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows
       for (int v = 0; v < VEC; ++v) {
         float mm = moving_mean ? moving_mean[c + v] : 0.f, mv = moving_var ? moving_var[c + v] : 0.f;
         for (int g = 0; g < groups; ++g) {
-          const double m = sums[((int64_t)g * 2 + 0) * C + c + v] * inv;
-          double var = sums[((int64_t)g * 2 + 1) * C + c + v] * inv - m * m;
+          const double m = bn_sum_read(sums, R, groups, g, 0, C, c + v) * inv;
+          double var = bn_sum_read(sums, R, groups, g, 1, C, c + v) * inv - m * m;
           var = var < 0.0 ? 0.0 : var;
           // assign_moving_average(moving, batch, decay) = moving - (moving - batch) * (1 - decay)
           mm -= (mm - (float)m) * (1.f - decay);
@@ -232,8 +235,10 @@ bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
   const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
   const int grp = blockIdx.z;
   const int c = (blockIdx.y * tx_dim + tx) * VEC;
-  if (c >= C) return;
+  const bool active = c < C;
+  const int R = (sums != nullptr) ? bn_replicas(C, groups) : 1;
   const float invM = 1.f / (float)rows_per_group;
+  if (!active) return;
   float mu[VEC], rs[VEC], ga[VEC], be[VEC], sg[VEC], sgx[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -241,14 +246,14 @@ bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
     be[v] = beta ? __ldg(beta + c + v) : 0.f;
     mu[v] = __ldg(mean + (int64_t)grp * C + c + v);
     rs[v] = __ldg(rstd + (int64_t)grp * C + c + v);
-    sg[v] = train ? (float)sums[((int64_t)grp * 2 + 0) * C + c + v] * invM : 0.f;
-    sgx[v] = train ? (float)sums[((int64_t)grp * 2 + 1) * C + c + v] * invM : 0.f;
+    sg[v] = train ? (float)bn_sum_read(sums, R, groups, grp, 0, C, c + v) * invM : 0.f;
+    sgx[v] = train ? (float)bn_sum_read(sums, R, groups, grp, 1, C, c + v) * invM : 0.f;
   }
   if (blockIdx.x == 0 && ty == 0 && grp == 0 && (dgamma || dbeta)) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       double a = 0.0, b = 0.0;
-      for (int g = 0; g < groups; ++g) { a += sums[((int64_t)g * 2 + 0) * C + c + v]; b += sums[((int64_t)g * 2 + 1) * C + c + v]; }
+      for (int g = 0; g < groups; ++g) { a += bn_sum_read(sums, R, groups, g, 0, C, c + v); b += bn_sum_read(sums, R, groups, g, 1, C, c + v); }
       if (dbeta) dbeta[c + v] += (float)a;
       if (dgamma) dgamma[c + v] += (float)b;
     }
@@ -306,6 +311,7 @@ bn_bwd_fused_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
   const int grp = blockIdx.z;
   const int c = (blockIdx.y * tx_dim + tx) * VEC;
   const bool active = c < C;
+  const int R = bn_replicas(C, groups);
   float mu[VEC], rs[VEC], ga[VEC], be[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -350,8 +356,9 @@ bn_bwd_fused_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
     for (int v = 0; v < VEC; ++v) {
       float a = 0.f, b = 0.f;
       for (int j = 0; j < ty_dim; ++j) { a += red[0][(j * tx_dim + tx) * VEC + v]; b += red[1][(j * tx_dim + tx) * VEC + v]; }
-      atomicAdd(sums + ((int64_t)grp * 2 + 0) * C + c + v, (double)a);
-      atomicAdd(sums + ((int64_t)grp * 2 + 1) * C + c + v, (double)b);
+      const int rep = (int)(blockIdx.x % (unsigned)R);
+      atomicAdd(sums + bn_sum_index(rep, groups, grp, 0, C, c + v), (double)a);
+      atomicAdd(sums + bn_sum_index(rep, groups, grp, 1, C, c + v), (double)b);
     }
   }
   __threadfence();
@@ -361,14 +368,14 @@ bn_bwd_fused_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
   float sg[VEC], sgx[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    sg[v] = (float)__ldcg(sums + ((int64_t)grp * 2 + 0) * C + c + v) * invM;
-    sgx[v] = (float)__ldcg(sums + ((int64_t)grp * 2 + 1) * C + c + v) * invM;
+    sg[v] = (float)bn_sum_read(sums, R, groups, grp, 0, C, c + v) * invM;
+    sgx[v] = (float)bn_sum_read(sums, R, groups, grp, 1, C, c + v) * invM;
   }
   if (blockIdx.x == 0 && ty == 0 && grp == 0 && (dgamma || dbeta)) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       double a = 0.0, b = 0.0;
-      for (int gi = 0; gi < groups; ++gi) { a += __ldcg(sums + ((int64_t)gi * 2 + 0) * C + c + v); b += __ldcg(sums + ((int64_t)gi * 2 + 1) * C + c + v); }
+      for (int gi = 0; gi < groups; ++gi) { a += bn_sum_read(sums, R, groups, gi, 0, C, c + v); b += bn_sum_read(sums, R, groups, gi, 1, C, c + v); }
       if (dbeta) dbeta[c + v] += (float)a;
       if (dgamma) dgamma[c + v] += (float)b;
     }
@@ -394,13 +401,13 @@ __global__ void add_colsum_kernel(const double* __restrict__ sums, int C, float*
 // ---- host -----------------------------------------------------------------------------
 template <typename TX, typename TD, int MODE>
 static void launch_colsum(const void* x, const void* dy, int64_t rpg, int C, int groups, const float* gamma, const float* beta,
-                          const float* mean, const float* rstd, int act, float ap, double* sums, bool vec_ok, cudaStream_t st) {
+                          const float* mean, const float* rstd, int act, float ap, double* sums, bool vec_ok, cudaStream_t st, int R) {
   ColGeom g = col_geom(rpg, C, groups, vec_ok);
   dim3 grid(g.rblocks, g.cblocks, groups);
   if (g.vec == 4)
-    Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 4, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
+    Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 4, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx, R);
   else
-    Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 1, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx);
+    Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 1, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx, R);
 }
 
 // streaming (apply) kernels: same 2-D mapping, but sized to fill the machine (no atomics at the end)
@@ -419,7 +426,7 @@ static inline int apply_blocks(int64_t total) { return (int)std::max<int64_t>(1,
 
 using namespace gg;
 
-extern "C" size_t gg_bn_workspace_bytes(int32_t C, int32_t groups) { return (size_t)2 * C * groups * sizeof(double); }
+extern "C" size_t gg_bn_workspace_bytes(int32_t C, int32_t groups) { return (size_t)bn_replicas(C, groups) * 2 * C * groups * sizeof(double); }
 
 namespace gg {
 // sums[groups][2][C] += (sum x, sum x^2) per row group -- the separate statistics pass (used when the producer
@@ -427,7 +434,7 @@ namespace gg {
 int bn_accumulate_stats(const void* x, int x_dt, int64_t rows, int C, int groups, double* sums, cudaStream_t st) {
   GG_REQUIRE(rows % groups == 0, GG_ERR_INVALID, "bn stats: rows not divisible by groups");
   const bool vec_ok = aligned16(x);
-  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, rows / groups, C, groups, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, vec_ok, st)));
+  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, rows / groups, C, groups, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, vec_ok, st, bn_replicas(C, groups))));
   return check_launch("bn_stats");
 }
 }  // namespace gg
@@ -461,7 +468,7 @@ extern "C" int gg_bn_fwd_train(const void* x, int32_t x_dt, void* y, int32_t y_d
   double* sums = (double*)ws;
   cudaMemsetAsync(sums, 0, gg_bn_workspace_bytes(C, groups), st);
   const bool vec_ok = aligned16(x) && aligned16(y);
-  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, rpg, C, groups, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, vec_ok, st)));
+  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, rpg, C, groups, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, vec_ok, st, bn_replicas(C, groups))));
   int rc = check_launch("bn_stats");
   if (rc) return rc;
   return bn_finalize_and_apply(x, x_dt, y, y_dt, rpg, C, groups, gamma, beta, moving_mean, moving_var, save_mean, save_rstd, eps, decay,
@@ -631,7 +638,7 @@ extern "C" int gg_bn_bwd(const void* x, int32_t x_dt, const void* dy, int32_t dy
       if (rc) return rc;
       if (fused) return GG_OK;
     }
-#define GG_CS(TX, TD) launch_colsum<TX, TD, 1>(x, dy, rpg, C, groups, gamma, beta, save_mean, save_rstd, act, act_param, sums, vec_ok, st)
+#define GG_CS(TX, TD) launch_colsum<TX, TD, 1>(x, dy, rpg, C, groups, gamma, beta, save_mean, save_rstd, act, act_param, sums, vec_ok, st, bn_replicas(C, groups))
     if (x_dt == GG_F32 && dy_dt == GG_F32) GG_CS(float, float);
     else if (x_dt == GG_F32) GG_CS(float, bf16);
     else if (dy_dt == GG_F32) GG_CS(bf16, float);
@@ -757,7 +764,7 @@ extern "C" int gg_get_std(const void* x, int32_t x_dt, int64_t B, int64_t F, flo
   GG_REQUIRE(ws_bytes >= (size_t)2 * F * sizeof(double), GG_ERR_WORKSPACE, "get_std: workspace too small");
   double* sums = (double*)ws;
   cudaMemsetAsync(sums, 0, (size_t)2 * F * sizeof(double), st);
-  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, B, (int)F, 1, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, aligned16(x), st)));
+  GG_DISPATCH_DTYPE(x_dt, TX, (launch_colsum<TX, TX, 0>(x, nullptr, B, (int)F, 1, nullptr, nullptr, nullptr, nullptr, 0, 0.f, sums, aligned16(x), st, 1)));
   int rc = check_launch("get_std_stats");
   if (rc) return rc;
   Launch(1, 256, 0, st)(get_std_final_kernel, sums, B, F, out);

@@ -451,9 +451,10 @@ thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const flo
   __shared__ __align__(16) float xs[THIN_MAXK * THIN_ROWS];                 // [i][r]            16 KB
   __shared__ __align__(16) float red[4 * THIN_ROWS * THIN_COLS];            // [g][r][c]         32 KB
   const int r0 = blockIdx.y * THIN_ROWS;
-  for (int e = threadIdx.x; e < in_dim * THIN_ROWS; e += 256) {
-    const int r = e / in_dim, i = e - r * in_dim;               // coalesced over i
-    xs[i * THIN_ROWS + r] = (r0 + r < rows) ? ldf(x + (int64_t)(r0 + r) * in_dim + i) : 0.f;
+  {
+    const int r = threadIdx.x >> 3, l = threadIdx.x & 7;        // 8 threads per row, 32 rows
+#pragma unroll 4
+    for (int i = l; i < in_dim; i += 8) xs[i * THIN_ROWS + r] = (r0 + r < rows) ? ldf(x + (int64_t)(r0 + r) * in_dim + i) : 0.f;
   }
   __syncthreads();
   const int c = threadIdx.x & (THIN_COLS - 1), g = threadIdx.x >> 6;
@@ -462,13 +463,14 @@ thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const flo
   float acc[THIN_ROWS];
 #pragma unroll
   for (int r = 0; r < THIN_ROWS; ++r) acc[r] = 0.f;
-  for (int i0 = g; i0 < in_dim; i0 += 32) {
-    float m[8];
+  {
+    constexpr int NB = THIN_MAXK / 4;                            // all of this thread's matrix elements in ONE load batch
+    float m[NB];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int i = i0 + 4 * u; m[u] = (col_ok && i < in_dim) ? __ldg(W + (int64_t)i * out_dim + j) : 0.f; }
+    for (int u = 0; u < NB; ++u) { const int i = g + 4 * u; m[u] = (col_ok && i < in_dim) ? __ldg(W + (int64_t)i * out_dim + j) : 0.f; }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 + 4 * u;
+    for (int u = 0; u < NB; ++u) {
+      const int i = g + 4 * u;
       if (i < in_dim) {
         const float4* xr = reinterpret_cast<const float4*>(xs + i * THIN_ROWS);
 #pragma unroll
@@ -523,12 +525,12 @@ thin_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __
   float acc[THIN_ROWS], bsum = 0.f;
 #pragma unroll
   for (int i = 0; i < THIN_ROWS; ++i) acc[i] = 0.f;
-  for (int rb = g; rb < rows; rb += 32) {
-    float gv[8];
+  for (int rb = g; rb < rows; rb += 64) {
+    float gv[16];                                                 // 16 rows per load batch (all of them at batch 64)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int r = rb + 4 * u; gv[u] = (col_ok && r < rows) ? ldf(dy + (int64_t)r * out_dim + j) : 0.f; }
+    for (int u = 0; u < 16; ++u) { const int r = rb + 4 * u; gv[u] = (col_ok && r < rows) ? ldf(dy + (int64_t)r * out_dim + j) : 0.f; }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
       const int r = rb + 4 * u;
       if (r < rows) {
         bsum += gv[u];

@@ -438,9 +438,10 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
           }
         }
         const int statC = p.cat_C ? p.cat_C : p.Nout;          // every parity class of a channel feeds the same statistic
-        double* dst = p.stats + ((long long)grp * 2) * statC + (n0 + col) % statC;
-        atomicAdd(dst, (double)s);
-        atomicAdd(dst + statC, (double)s2);
+        const int R = bn_replicas(statC, p.stats_groups);     // replicated accumulators: spread the same-address atomics
+        const int rep = tile & (R - 1), schan = (n0 + col) % statC;
+        atomicAdd(p.stats + bn_sum_index(rep, p.stats_groups, grp, 0, statC, schan), (double)s);
+        atomicAdd(p.stats + bn_sum_index(rep, p.stats_groups, grp, 1, statC, schan), (double)s2);
       }
     }
     if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after this

@@ -867,7 +867,7 @@ class _FusedBN(torch.autograd.Function):
     def forward(ctx, x, w, b, gamma, beta, prod, bn, train, act, act_param, out_dtype, groups, Cc):
         L = cabi.lib()
         fused_stats = train and prod.fuses_stats and Cc == prod.out_shape()[-1]
-        stats = _zeroed_f64(groups * 2 * Cc, x.device)[0].view(groups, 2, Cc) if fused_stats else None
+        stats = _zeroed_f64(L.gg_bn_workspace_bytes(Cc, groups) // 8, x.device)[0] if fused_stats else None   # [replicas][groups][2][C]
         pre = prod.fwd(x, b, stats=stats, groups=groups)
         rows = pre.numel() // Cc
         y = torch.empty(pre.shape, dtype=out_dtype, device=x.device)

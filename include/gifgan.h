@@ -103,7 +103,7 @@ int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, f
                   void* stream);
 
 /* conv + batch statistics of its pre-norm output in one call (what `batch_norm(conv2d(...))` needs, ops.py:10-24 after
- * ops.py:57/86): stats[groups][2][channels] (fp64, zero-initialised by the caller) += per-channel (sum, sum of squares)
+ * ops.py:57/86): stats (gg_bn_workspace_bytes(channels, groups) bytes of fp64, [replicas][groups][2][channels], zero-initialised by the caller) += per-channel (sum, sum of squares)
  * over each of `groups` equal blocks of the batch.  On the tensor-core path the sums are produced in the GEMM epilogue
  * (the tile is already in shared memory); otherwise by a coalesced pass.  Consumed by gg_bn_fwd_train_stats.            */
 int gg_conv_down_stats(const gg_conv_desc* d, const void* large, const void* w, const float* bias, void* small,
@@ -146,12 +146,15 @@ int gg_linear_wgrad(const void* x, int32_t x_dtype, const void* dy, int32_t dy_d
  * gamma/beta may be NULL (affine-free rnn_test variant); moving_* may be NULL (no EMA).
  * save_mean/save_rstd: [groups, C] fp32, consumed by gg_bn_bwd.
  * ws: >= gg_bn_workspace_bytes(C, groups) bytes, caller-owned.                          */
+/* fp64 accumulators [replicas][groups][2][C] (replicas = 1 in this build; the library may replicate them to spread per-CTA
+ * atomics, and every kernel that reads them adds the replicas).  The same size is expected for the `stats` buffer of
+ * gg_conv_down_stats / gg_conv_up_stats / gg_bn_fwd_train_stats. */
 size_t gg_bn_workspace_bytes(int32_t C, int32_t groups);
 int gg_bn_fwd_train(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t rows, int32_t C, int32_t groups,
                     const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                     float* save_mean, float* save_rstd, float eps, float decay, int32_t act, float act_param,
                     void* ws, size_t ws_bytes, void* stream);
-/* gg_bn_fwd_train without the statistics pass: `stats` = the [groups][2][C] sums written by gg_conv_*_stats */
+/* gg_bn_fwd_train without the statistics pass: `stats` = the (replicated) [groups][2][C] sums written by gg_conv_*_stats */
 int gg_bn_fwd_train_stats(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t rows, int32_t C, int32_t groups,
                           const float* gamma, const float* beta, float* moving_mean, float* moving_var,
                           float* save_mean, float* save_rstd, float eps, float decay, int32_t act, float act_param,
