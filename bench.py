@@ -88,6 +88,10 @@ def ncu_by_layer():
         return json.load(f), os.path.basename(files[-1])
 
 
+def workload_name(batch):
+    return f"DCGAN 64x64x3 per-frame GAN (BASELINE config 2: models/recurrent_z model.py), batch {batch}/GPU, 1 D + 2 G updates per step"
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -106,7 +110,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -173,7 +177,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": max(1, warmup),
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DCGAN 64x64x3 per-frame GAN (models/recurrent_z model.py), batch {args.batch}, 1 D + 2 G updates per step",
+        "config": {"workload": workload_name(args.batch), "global_batch": args.batch, "parallelism": "cpu",
                    "note": "reference TensorFlow-0.12 cannot run here; CPU restatement of the same graph (oracle/) on host cores"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -354,7 +358,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": f"DCGAN 64x64x3 per-frame GAN (BASELINE config 2), batch {B}/GPU, 1 D + 2 G updates per step",
+        "config": {"workload": workload_name(B),
                    "global_batch": frames, "parallelism": f"dp{world}", "l2": "flushed (256 MB memset) before every timed step",
                    "bn": "per-replica statistics", "graph": not args.eager, "tensor_cores": bool(ops._USE_TC)},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
