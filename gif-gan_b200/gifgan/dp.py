@@ -32,6 +32,10 @@ class DataParallel:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
+                # Measured on 8 x B200 (tools/gpu_scale_ab.sh, profiles/r01z_*): for this step's 3-20 MB gradient buckets,
+                # issued from inside a CUDA graph, in-switch reduction (NVLS) is slower than NCCL's ring/tree over
+                # NVLink (2.097 vs 2.035 ms/step), so it is off unless the user sets the variable.
+                os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
             dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world_size)
 
     # ------------------------------------------------------------------------------
@@ -54,7 +58,7 @@ class DataParallel:
     # the backward pass (the remaining dgrad / batch-norm / wgrad kernels) keeps the SMs busy.  allreduce() then only
     # has the head of the range left.  All collectives go to the one communication stream, in the same order on every
     # rank; under CUDA-graph capture the stream fork/join becomes parallel graph branches.
-    early_bytes = 2 << 20
+    early_bytes = int(float(os.environ.get("GG_DP_EARLY_MB", "2")) * (1 << 20)) or (1 << 62)   # 0 = no early buckets
 
     def _comm(self):
         if self.comm_stream is None:
