@@ -1,0 +1,125 @@
+"""CPU-side tests of the host layer that mirrors the reference's Python (no kernels run): variable names and shapes of
+the three models against the oracle's (= the reference's checkpoint keys), scope handling, optimiser
+group layout, checkpoint round trip, and the host-only queries of the C ABI."""
+import ctypes
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.fixture()
+def cpu_store():
+    from gifgan import ops
+    ops.set_precision("fp32")
+    return ops.reset_default_store(device="cpu", seed=1)
+
+
+def test_dcgan_variable_names_and_shapes_match_the_reference(cpu_store):
+    from gifgan.model import DCGAN
+    from oracle.models import DCGAN as OracleDCGAN
+    m = DCGAN(None, batch_size=4, output_size=64, c_dim=3)
+    ora = OracleDCGAN(batch_size=4, output_size=64)
+    assert set(m.store.vars) == set(ora.vars)
+    for k, v in ora.vars.items():
+        assert tuple(m.store.vars[k].shape) == tuple(v.shape), k
+    # model.py:136-139: the var_lists split on the 'd_' / 'g_' substrings; parameter counts of SURVEY 8a
+    assert sum(v.numel() for v in m.d_vars) == 4316545 and sum(v.numel() for v in m.g_vars) == 5135363
+    # optimiser groups are contiguous, 16-byte aligned ranges of one flat buffer
+    (db, de), (gb, ge) = m.store.ranges["d"], m.store.ranges["g"]
+    assert db % 4 == 0 and gb % 4 == 0 and (de <= gb or ge <= db)
+    for v in m.d_vars:
+        assert db <= v.offset < de and v.grad.data_ptr() == m.store.flat["grads"][v.offset:].data_ptr()
+
+
+def test_mnist_conditional_branch_names(cpu_store):
+    from gifgan.model import DCGAN
+    from oracle.models import DCGAN as OracleDCGAN
+    m = DCGAN(None, batch_size=4, output_size=28, y_dim=10, c_dim=1, dataset_name="mnist")
+    ora = OracleDCGAN(batch_size=4, output_size=28, y_dim=10, c_dim=1)
+    assert set(m.store.vars) == set(ora.vars)
+
+
+def test_video_models_resolve_their_scopes_from_anywhere(cpu_store):
+    """z_model.py:63 builds VID_DCGAN under tf.variable_scope('video_gan'); train/sample code then runs outside it."""
+    from gifgan import ops
+    from gifgan.z_model_lib import VID_DCGAN
+    from oracle.models import VID_DCGAN as OracleVID
+    with ops.variable_scope("video_gan"):
+        m = VID_DCGAN(None, batch_size=2, z_input_size=120, z_output_size=100, vid_length=16, input_image_size=64,
+                      output_image_size=64, c_dim=3, sample_cols=2)
+    ora = OracleVID(batch_size=2, vid_length=16, output_image_size=64)
+    assert set(m.store.vars) == set(ora.vars)
+    n_before = len(m.store.vars)
+    z = torch.empty((2, 120), device="meta")                  # trace the whole chain outside every scope
+    g, _ = m.generator(z)
+    frames = m.img_dcgan.generator(g, train=False)
+    act = m.img_dcgan.discriminator(frames, reuse=True, train=False, stop_at_h2=True)[2]
+    logits = m.discriminator(act, reuse=True)[1]
+    assert tuple(g.shape) == (32, 100) and tuple(frames.shape) == (32, 64, 64, 3)
+    assert tuple(act.shape) == (32, 8, 8, 256) and tuple(logits.shape) == (2, 1)
+    assert len(m.store.vars) == n_before                      # nothing was re-created under a wrong name
+    # z_model_lib.py:166-179: default flags train the video nets only
+    assert all("dvideo_" in v.name for v in m.d_var_list) and all("gvideo_" in v.name for v in m.g_var_list)
+    m.set_trainable(train_img_gen=True, train_img_disc=True)
+    assert any("image_gan/g_" in v.name for v in m.g_var_list) and any("image_gan/d_" in v.name for v in m.d_var_list)
+
+
+def test_recurrent_dcgan_names(cpu_store):
+    from gifgan.recurrent_dcgan import RecurrentDCGAN
+    from oracle.models import RecurrentDCGAN as OracleRec
+    m = RecurrentDCGAN(batch_size=2, video_length=3)
+    ora = OracleRec(batch_size=2, video_length=3)
+    assert set(m.store.vars) == set(ora.vars)
+    for k, v in ora.vars.items():
+        assert tuple(m.store.vars[k].shape) == tuple(v.shape), k
+
+
+def test_checkpoint_round_trip(cpu_store, tmp_path):
+    """model.py:428-452: <dir>/<dataset>_<batch>_<size>/DCGAN.model-<step> + the 'checkpoint' index file."""
+    from gifgan import ops
+    from gifgan.model import DCGAN
+    m = DCGAN(None, batch_size=4, output_size=16, gf_dim=8, df_dim=8, c_dim=3, dataset_name="faces")
+    w0 = {k: v.data.clone() for k, v in m.store.vars.items()}
+    m.store.flat["m"].uniform_(-1, 1)
+    m.d_optim.t, m.g_optim.t = 7, 14
+    path = m.save(str(tmp_path), 123)
+    assert path.endswith(os.path.join("faces_4_16", "DCGAN.model-123")) and os.path.exists(path)
+    assert open(os.path.join(os.path.dirname(path), "checkpoint")).read().startswith('model_checkpoint_path: "DCGAN.model-123"')
+    ops.reset_default_store(device="cpu", seed=99)            # different initial values
+    m2 = DCGAN(None, batch_size=4, output_size=16, gf_dim=8, df_dim=8, c_dim=3, dataset_name="faces")
+    assert not torch.equal(m2.store.vars["g_h1/w"].data, w0["g_h1/w"])
+    assert m2.load(str(tmp_path))
+    for k, v in w0.items():
+        assert torch.equal(m2.store.vars[k].data, v), k
+    assert torch.equal(m2.store.flat["m"], m.store.flat["m"]) and (m2.d_optim.t, m2.g_optim.t) == (7, 14)
+    assert not m2.load(str(tmp_path / "nothing_here"))
+
+
+def test_host_only_abi_queries():
+    """Entry points that touch no device memory can be called without a GPU."""
+    from gifgan import _cabi
+    L = _cabi.lib()
+    assert L.gg_bn_workspace_bytes(64, 2) >= 2 * 64 * 2 * 8
+    d = _cabi.ConvDesc()
+    for name, val in dict(N=64, D=1, H=32, W=32, C=64, Do=1, Ho=16, Wo=16, K=128, kd=1, kh=5, kw=5, sd=1, sh=2, sw=2, pd=0, ph=1, pw=1,
+                          large_dtype=1, small_dtype=1, act=0, flags=_cabi.CONV_TENSOR_CORE).items():
+        setattr(d, name, val)
+    # 4 parity classes x 64 channels = 256 columns, 9 shifts: the class-concatenated deconv filter
+    assert L.gg_upcat_bytes(ctypes.byref(d)) == 9 * 256 * 128 * 2
+    d.C = 128                                                  # 4 x 128 != 256: not eligible
+    assert L.gg_upcat_bytes(ctypes.byref(d)) == 0
+    assert L.gg_conv_down(ctypes.byref(d), None, None, None, None, None) != 0      # null pointers are an error, not a crash
+    assert b"null" in L.gg_last_error()
+
+
+def test_stats_arena_bump_allocation():
+    from gifgan import ops
+    a = ops._StatsArena(torch.device("cpu"), nbytes=1024)
+    x, y = a.take(3), a.take(4)
+    assert x.numel() == 3 and y.numel() == 4 and y.data_ptr() - x.data_ptr() == 4 * 8      # 16-byte granules
+    assert a.take(1000) is None                                # exhausted -> callers fall back to a fresh zero tensor
+    t, pre = ops._zeroed_f64(5, torch.device("cpu"))
+    assert not pre and float(t.abs().sum()) == 0.0
