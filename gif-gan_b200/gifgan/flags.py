@@ -1,31 +1,124 @@
-"""tf.app.flags stand-in: DEFINE_* with the reference's names/defaults -> argparse namespace (`FLAGS`)."""
+"""Command-line flags of the three entry points, as data.
+
+The reference declares its options with tf.app.flags (main.py:10-29, z_model.py:22-56, model_sampler.py:9-24).  The
+drop-in contract is the option NAMES, TYPES and DEFAULTS; here each program's options are one table
+(name, kind, default, help) turned into an argparse parser, plus the options this implementation adds
+(--precision, synthetic data).  Kinds: i = int, f = float, s = str, b = bool ("--flag", "--flag true/false").
+"""
 import argparse
+
+_TRUE = ("1", "true", "t", "yes", "y")
+
+# Options shared by every program that builds the video GAN.
+_VIDEO_SHAPE = [
+    ("vid_batch_size", "i", 64, "clips per batch"),
+    ("vid_length", "i", 16, "frames per clip"),
+    ("image_size", "i", 64, "edge of the frames fed to the image discriminator"),
+    ("output_size", "i", 64, "edge of the generated frames"),
+    ("c_dim", "i", 3, "colour channels"),
+    ("image_noise", "f", 0.0, "std of the gaussian noise added to frames before the image D"),
+    ("activation_noise", "f", 0.0, "std of the gaussian noise added to the image-D activations"),
+]
+
+_OURS = [("precision", "s", "bf16", "bf16 = tcgen05 tensor-core path, fp32 = parity mode")]
+
+TABLES = {
+    # models/recurrent_z/main.py
+    "image_gan": [
+        ("epoch", "i", 25, "passes over the dataset"),
+        ("learning_rate", "f", 0.0002, "Adam step size"),
+        ("beta1", "f", 0.5, "Adam first-moment decay"),
+        ("train_size", "i", 1 << 62, "cap on the number of training images (reference default: unbounded)"),
+        ("batch_size", "i", 64, "images per batch"),
+        ("image_size", "i", 108, "centre-crop edge applied to the input images"),
+        ("output_size", "i", 64, "edge of the generated images"),
+        ("c_dim", "i", 3, "colour channels"),
+        ("dataset", "s", "celebA", "celebA | mnist | lsun | synthetic (seeded random frames; no dataset ships here)"),
+        ("checkpoint_dir", "s", "checkpoint", "where checkpoints are written / read"),
+        ("sample_dir", "s", "samples", "where sample grids are written"),
+        ("data_dir", "s", "./data", "dataset root"),
+        ("log_dir", "s", "./logs", "log directory"),
+        ("image_glob", "s", "*.jpg", "pattern of the image files under data_dir/dataset"),
+        ("is_train", "b", False, "train (true) or just load the checkpoint (false)"),
+        ("is_crop", "b", False, "centre-crop the inputs"),
+        ("visualize", "b", False, "write visualisations after loading"),
+        ("shuffle", "b", False, "shuffle the file list every epoch"),
+    ] + _OURS,
+    # models/recurrent_z/z_model.py
+    "video_gan": [
+        ("epoch", "i", 25, "passes over the clip list"),
+        ("learning_rate", "f", 0.0002, "Adam step size"),
+        ("beta1", "f", 0.5, "Adam first-moment decay"),
+        ("image_batch_size", "i", 64, "batch of the image-GAN checkpoint being loaded"),
+    ] + _VIDEO_SHAPE[:5] + [
+        ("image_model_dir", "s", "checkpoint", "image-GAN checkpoint to start from"),
+        ("video_checkpoint_dir", "s", "checkpoint", "where video-GAN checkpoints go"),
+        ("video_sample_dir", "s", "samples", "where sample clips go"),
+        ("video_data_dir", "s", "./data", "clip dataset root"),
+        ("video_dataset", "s", "", "name of the clip dataset"),
+        ("log_dir", "s", "./logs", "log directory"),
+        ("is_train", "b", False, "run the training loop"),
+        ("video_shuffle", "b", True, "shuffle the clip list every epoch"),
+        ("train_img_gen", "b", False, "also train the image generator (default: frozen)"),
+        ("train_img_disc", "b", False, "also train the image discriminator (default: frozen)"),
+        ("disc_updates", "i", 1, "discriminator updates per batch"),
+        ("gen_updates", "i", 2, "generator updates per batch"),
+    ] + _VIDEO_SHAPE[5:] + [
+        ("first_frame_loss_scalar", "f", 0.0, "weight of the first-frame latent reconstruction loss"),
+        ("sample_frequency", "i", 10, "batches between checkpoints / samples"),
+        ("max_checkpoints_to_keep", "i", 5, "checkpoint rotation depth"),
+        ("synthetic_batches", "i", 4, "batches per epoch when training on synthetic clips"),
+    ] + _OURS,
+    # models/recurrent_z/model_sampler.py  (its two path defaults are site-specific in the reference; local ones here)
+    "sampler": _VIDEO_SHAPE + [
+        ("checkpoint_dir", "s", "checkpoint", "video-GAN checkpoint to sample from"),
+        ("num_samples", "i", 200, "GIFs to write per pass"),
+        ("output_directory", "s", "samples_nested", "where the GIFs go"),
+        ("random_seed", "i", 0, "numpy seed of the latents"),
+        ("continuous", "b", False, "keep regenerating until interrupted"),
+    ] + _OURS,
+}
+
+
+def _add(parser, name, kind, default, text):
+    if kind == "b":
+        parser.add_argument("--" + name, type=lambda v: str(v).lower() in _TRUE, nargs="?", const=True, default=default, help=text)
+    else:
+        conv = {"i": lambda s: int(float(s)), "f": float, "s": str}[kind]
+        parser.add_argument("--" + name, type=conv, default=default, help=text)
+
+
+def parser_for(program):
+    p = argparse.ArgumentParser(prog=program)
+    for spec in TABLES[program]:
+        _add(p, *spec)
+    if program == "video_gan":
+        p.add_argument("--video_list", nargs="*", default=[], help="file(s) listing the training clips; empty or 'synthetic' = seeded random clips")
+    return p
+
+
+def parse(program, argv=None):
+    """-> argparse.Namespace named like the reference's FLAGS."""
+    return parser_for(program).parse_args(argv)
 
 
 class Flags:
-    def __init__(self):
-        self._p = argparse.ArgumentParser()
-        self.FLAGS = None
+    """tf.app.flags-style incremental definition, kept for user scripts that extend a table."""
 
-    @staticmethod
-    def _bool(v):
-        return str(v).lower() in ("1", "true", "t", "yes", "y")
+    def __init__(self, program=None):
+        self._p = parser_for(program) if program else argparse.ArgumentParser()
 
     def DEFINE_integer(self, name, default, help=""):
-        self._p.add_argument("--" + name, type=lambda s: int(float(s)), default=default, help=help)
+        _add(self._p, name, "i", default, help)
 
     def DEFINE_float(self, name, default, help=""):
-        self._p.add_argument("--" + name, type=float, default=default, help=help)
+        _add(self._p, name, "f", default, help)
 
     def DEFINE_string(self, name, default, help=""):
-        self._p.add_argument("--" + name, type=str, default=default, help=help)
+        _add(self._p, name, "s", default, help)
 
     def DEFINE_boolean(self, name, default, help=""):
-        self._p.add_argument("--" + name, type=self._bool, nargs="?", const=True, default=default, help=help)
-
-    def add_argument(self, *a, **k):
-        self._p.add_argument(*a, **k)
+        _add(self._p, name, "b", default, help)
 
     def parse(self, argv=None):
-        self.FLAGS = self._p.parse_args(argv)
-        return self.FLAGS
+        return self._p.parse_args(argv)

@@ -123,3 +123,28 @@ def test_stats_arena_bump_allocation():
     assert a.take(1000) is None                                # exhausted -> callers fall back to a fresh zero tensor
     t, pre = ops._zeroed_f64(5, torch.device("cpu"))
     assert not pre and float(t.abs().sum()) == 0.0
+
+
+def test_cli_option_contract():
+    """Option names / kinds / numeric defaults the reference's programs declare (main.py:10-29, z_model.py:22-56,
+    model_sampler.py:9-24): a user's command lines keep working."""
+    from gifgan import flags
+    img = vars(flags.parse("image_gan", []))
+    for name, default in dict(epoch=25, learning_rate=0.0002, beta1=0.5, batch_size=64, image_size=108, output_size=64, c_dim=3,
+                              is_train=False, is_crop=False, visualize=False, shuffle=False, dataset="celebA", image_glob="*.jpg").items():
+        assert img[name] == default, name
+    assert img["train_size"] > 1e18                              # np.inf in the reference
+    for name in ("checkpoint_dir", "sample_dir", "data_dir", "log_dir"):
+        assert isinstance(img[name], str)
+    vid = vars(flags.parse("video_gan", []))
+    for name, default in dict(epoch=25, learning_rate=0.0002, beta1=0.5, image_batch_size=64, vid_batch_size=64, vid_length=16, image_size=64,
+                              output_size=64, c_dim=3, is_train=False, video_shuffle=True, train_img_gen=False, train_img_disc=False,
+                              disc_updates=1, gen_updates=2, image_noise=0.0, activation_noise=0.0, first_frame_loss_scalar=0.0,
+                              sample_frequency=10, max_checkpoints_to_keep=5, video_list=[]).items():
+        assert vid[name] == default, name
+    for name in ("image_model_dir", "video_checkpoint_dir", "video_sample_dir", "video_data_dir", "video_dataset", "log_dir"):
+        assert isinstance(vid[name], str)
+    smp = vars(flags.parse("sampler", ["--continuous", "--num_samples", "7"]))
+    assert smp["continuous"] is True and smp["num_samples"] == 7 and smp["vid_length"] == 16 and smp["random_seed"] == 0
+    got = flags.parse("video_gan", ["--video_list", "a.txt", "b.txt", "--train_img_gen", "true", "--gen_updates", "1"])
+    assert got.video_list == ["a.txt", "b.txt"] and got.train_img_gen is True and got.gen_updates == 1
