@@ -54,7 +54,7 @@ constexpr int DN_PROW = DN_PC * 3 + 1;          // 106 bf16 per patch row (105 +
 constexpr int DN_WROW = 88;                     // bf16 per channel row of the transposed filter (80 + 8: bank spread)
 
 template <typename TSM>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, const float* __restrict__ bias, TSM* __restrict__ small,
                 int N, int H, int W, int Ho, int Wo, int K, int kblocks, int act, float act_param) {
   pdl_grid_sync();
@@ -75,19 +75,20 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
   }
   for (int e = tid; e < DN_PR; e += 256) sp[e * DN_PROW + DN_PROW - 1] = __float2bfloat16_rn(0.f);
   __syncthreads();
-  uint32_t bw[KT5][8][2];
+  // B fragments in fragment order, swf[r][j][lane] = (b0, b1): one conflict-free 64-bit shared load per (kernel row,
+  // n-tile) in the main loop.  (Holding all 80 fragment registers per thread capped the kernel at 8 warps per SM, and
+  // ncu showed it latency-bound at 13 % warp occupancy.)
+  __shared__ __align__(16) uint2 swf[KT5 * 8 * 32];
   {
     const uint32_t* swt32 = reinterpret_cast<const uint32_t*>(swt);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = (g >> 1) * 16 + 2 * j + (g & 1);
-#pragma unroll
-      for (int r = 0; r < KT5; ++r) {
-        bw[r][j][0] = swt32[(ch * DN_WROW + r * 16 + 2 * t) >> 1];
-        bw[r][j][1] = swt32[(ch * DN_WROW + r * 16 + 2 * t + 8) >> 1];
-      }
+    for (int e = tid; e < KT5 * 8 * 32; e += 256) {
+      const int ln = e & 31, j = (e >> 5) & 7, r = e >> 8;
+      const int gg = ln >> 2, tt = ln & 3;
+      const int ch = (gg >> 1) * 16 + 2 * j + (gg & 1);
+      swf[e] = make_uint2(swt32[(ch * DN_WROW + r * 16 + 2 * tt) >> 1], swt32[(ch * DN_WROW + r * 16 + 2 * tt + 8) >> 1]);
     }
   }
+  __syncthreads();
   float bv[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) bv[i] = bias ? __ldg(bias + kb + t * 16 + i) : 0.f;
@@ -141,7 +142,10 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
       a[2] = row[3 * g + t + 4];
       a[3] = row[3 * (g + 8) + t + 4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) mma16816(acc[j], a, bw[r][j][0], bw[r][j][1]);
+      for (int j = 0; j < 8; ++j) {
+        const uint2 b = swf[(r * 8 + j) * 32 + lane];
+        mma16816(acc[j], a, b.x, b.y);
+      }
     }
     const int p = p0 + warp;
     if (p < Ho) {
@@ -185,6 +189,37 @@ c3m_up_kernel(const TSM* __restrict__ small, const float* __restrict__ w, const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int tiles_w = (Wo + UP_TW - 1) / UP_TW, tiles_h = (Ho + UP_TH - 1) / UP_TH;
   const int ntiles = N * tiles_h * tiles_w;
+  // Work items = (tile, 64-channel block); the next item's staged pixels are loaded into registers while the current
+  // item is multiplied (the kernel was latency-bound on these loads).
+  constexpr int PXC = (UP_PR * UP_PC * 8 + 255) / 256;          // 6 16-byte chunks per thread
+  int pdesc[PXC];                                               // patch row | patch col << 8 | chunk << 16, -1 = none
+#pragma unroll
+  for (int k = 0; k < PXC; ++k) {
+    const int e = tid + 256 * k, pix = e >> 3;
+    pdesc[k] = (e < UP_PR * UP_PC * 8) ? ((pix / UP_PC) | ((pix % UP_PC) << 8) | ((e & 7) << 16)) : -1;
+  }
+  uint4 xv[PXC];
+  auto prefetch = [&](int tile, int kb) {
+    const int n = tile / (tiles_h * tiles_w);
+    const int rem = tile - n * tiles_h * tiles_w;
+    const int p0 = (rem / tiles_w) * UP_TH, q0 = (rem % tiles_w) * UP_TW;
+#pragma unroll
+    for (int k = 0; k < PXC; ++k) {
+      const int p = p0 - 1 + (pdesc[k] & 0xff), q = q0 - 1 + ((pdesc[k] >> 8) & 0xff), c8 = (pdesc[k] >> 16) * 8;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (pdesc[k] >= 0 && p >= 0 && p < Ho && q >= 0 && q < Wo) {
+        const TSM* src = small + (((int64_t)n * Ho + p) * Wo + q) * K + kb + c8;
+        if (sizeof(TSM) == 2) {
+          v = __ldg(reinterpret_cast<const uint4*>(src));
+        } else {
+          const float4 f0 = ld4(reinterpret_cast<const float*>(src)), f1 = ld4(reinterpret_cast<const float*>(src) + 4);
+          v = make_uint4(pack2(f0.x, f0.y), pack2(f0.z, f0.w), pack2(f1.x, f1.y), pack2(f1.z, f1.w));
+        }
+      }
+      xv[k] = v;
+    }
+  };
+  if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n = tile / (tiles_h * tiles_w);
     const int rem = tile - n * tiles_h * tiles_w;
@@ -205,22 +240,13 @@ c3m_up_kernel(const TSM* __restrict__ small, const float* __restrict__ w, const 
           st4(swu + nn * UP_WROW + nb * 64 + k4, v);
         }
       }
-      for (int e = tid; e < UP_PR * UP_PC * 8; e += 256) {      // 8 chunks of 8 channels (16 B) per pixel
-        const int pix = e >> 3, c8 = (e & 7) * 8;
-        const int p = p0 - 1 + pix / UP_PC, q = q0 - 1 + pix % UP_PC;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (p >= 0 && p < Ho && q >= 0 && q < Wo) {
-          const TSM* src = small + (((int64_t)n * Ho + p) * Wo + q) * K + kb + c8;
-          if (sizeof(TSM) == 2) {
-            v = __ldg(reinterpret_cast<const uint4*>(src));
-          } else {
-            const float4 f0 = ld4(reinterpret_cast<const float*>(src)), f1 = ld4(reinterpret_cast<const float*>(src) + 4);
-            v = make_uint4(pack2(f0.x, f0.y), pack2(f0.z, f0.w), pack2(f1.x, f1.y), pack2(f1.z, f1.w));
-          }
-        }
-        *reinterpret_cast<uint4*>(sx + pix * UP_PIX + c8) = v;
-      }
+#pragma unroll
+      for (int k = 0; k < PXC; ++k)
+        if (pdesc[k] >= 0)
+          *reinterpret_cast<uint4*>(sx + ((pdesc[k] & 0xff) * UP_PC + ((pdesc[k] >> 8) & 0xff)) * UP_PIX + (pdesc[k] >> 16) * 8) = xv[k];
       __syncthreads();
+      if (kb + 64 < K) prefetch(tile, kb + 64);
+      else if (tile + (int)gridDim.x < ntiles) prefetch(tile + gridDim.x, 0);
       const uint32_t* swu32 = reinterpret_cast<const uint32_t*>(swu);
       // ldmatrix lane -> (matrix mi = lane / 8: rows +8 for odd mi, k +8 for mi >= 2)
       const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1), lk = 8 * (lane >> 4);
@@ -288,23 +314,33 @@ c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small,
   const int l8 = lane & 7, lm = lane >> 3;
   const int mblk = min(2 * warp + (lm & 1), 14);
   const int a_r = mblk / 3, a_s0 = 2 * (mblk % 3);
-  for (int tile = blockIdx.x / kblocks; tile < ntiles; tile += gridDim.x / kblocks) {
+  // Software pipeline: the next tile's patch pixels and small-tensor chunks are loaded into registers while the current
+  // tile is multiplied (the kernel was latency-bound on these loads: ncu long-scoreboard stalls 10.9 per issue).
+  constexpr int PPX = (WG_PR * WG_PC + 255) / 256;              // 3 patch pixels per thread
+  constexpr int PYC = WG_TH * WG_TW * 8 / 256;                  // 4 16-byte chunks of the small tile per thread
+  int pab[PPX];                                                 // a | b << 8 of this thread's patch pixels, -1 = none
+#pragma unroll
+  for (int k = 0; k < PPX; ++k) {
+    const int e = tid + 256 * k;
+    pab[k] = (e < WG_PR * WG_PC) ? ((e / WG_PC) | ((e % WG_PC) << 8)) : -1;
+  }
+  float pv[PPX][3];
+  uint4 yv[PYC];
+  auto prefetch = [&](int tile) {
     const int n = tile / (tiles_h * tiles_w);
     const int rem = tile - n * tiles_h * tiles_w;
     const int p0 = (rem / tiles_w) * WG_TH, q0 = (rem % tiles_w) * WG_TW;
     const int i0 = 2 * p0 - 1, j0 = 2 * q0 - 1;
-    __syncthreads();
-    for (int e = tid; e < WG_PR * WG_PC; e += 256) {
-      const int a = e / WG_PC, b = e - a * WG_PC;
-      const int i = i0 + a, j = j0 + b;
-      float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-      if (i >= 0 && i < H && j >= 0 && j < W) {
-        const float* src = large + (((int64_t)n * H + i) * W + j) * 3;
-        v0 = __ldg(src); v1 = __ldg(src + 1); v2 = __ldg(src + 2);
-      }
-      *reinterpret_cast<uint2*>(sp + e * 4) = make_uint2(pack2(v0, v1), pack2(v2, 0.f));
+#pragma unroll
+    for (int k = 0; k < PPX; ++k) {
+      const int i = i0 + (pab[k] & 0xff), j = j0 + (pab[k] >> 8);
+      const bool ok = pab[k] >= 0 && i >= 0 && i < H && j >= 0 && j < W;
+      const float* src = large + (((int64_t)n * H + (ok ? i : 0)) * W + (ok ? j : 0)) * 3;
+      pv[k][0] = ok ? __ldg(src) : 0.f; pv[k][1] = ok ? __ldg(src + 1) : 0.f; pv[k][2] = ok ? __ldg(src + 2) : 0.f;
     }
-    for (int e = tid; e < WG_TH * WG_TW * 8; e += 256) {
+#pragma unroll
+    for (int k = 0; k < PYC; ++k) {
+      const int e = tid + 256 * k;
       const int pix = e >> 3, c8 = (e & 7) * 8;
       const int p = p0 + pix / WG_TW, q = q0 + pix % WG_TW;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -317,8 +353,24 @@ c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small,
           v = make_uint4(pack2(f0.x, f0.y), pack2(f0.z, f0.w), pack2(f1.x, f1.y), pack2(f1.z, f1.w));
         }
       }
-      *reinterpret_cast<uint4*>(sy + pix * WG_YPIX + c8) = v;
+      yv[k] = v;
     }
+  };
+  const int tstride = gridDim.x / kblocks;
+  int tile = blockIdx.x / kblocks;
+  if (tile < ntiles) prefetch(tile);
+  for (; tile < ntiles; tile += tstride) {
+    __syncthreads();                                            // previous tile's fragments are consumed
+#pragma unroll
+    for (int k = 0; k < PPX; ++k)
+      if (pab[k] >= 0) *reinterpret_cast<uint2*>(sp + (tid + 256 * k) * 4) = make_uint2(pack2(pv[k][0], pv[k][1]), pack2(pv[k][2], 0.f));
+#pragma unroll
+    for (int k = 0; k < PYC; ++k) {
+      const int e = tid + 256 * k;
+      *reinterpret_cast<uint4*>(sy + (e >> 3) * WG_YPIX + (e & 7) * 8) = yv[k];
+    }
+    __syncthreads();
+    if (tile + tstride < ntiles) prefetch(tile + tstride);
     __syncthreads();
 #pragma unroll 2
     for (int ks = 0; ks < WG_TH * WG_TW / 16; ++ks) {          // 16 pixels per step = one tile row (WG_TW == 16)
@@ -358,7 +410,7 @@ c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small,
 int c3m_conv_down(const gg_conv_desc* d, const float* large, const float* w, const float* bias, void* small, cudaStream_t st) {
   const int kblocks = d->K / 64;
   const int ntiles = d->N * ceil_div(d->Ho, DN_TH) * ceil_div(d->Wo, DN_TW);
-  const int per_k = std::max(1, std::min(ntiles, 148 / std::min(kblocks, 148)));
+  const int per_k = std::max(1, std::min(ntiles, (148 * 2) / std::min(kblocks, 296)));     // 2 co-resident CTAs per SM
   const int grid = per_k * kblocks;
   if (d->small_dtype == GG_F32)
     Launch(grid, 256, 0, st)(c3m_down_kernel<float>, large, w, bias, (float*)small, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks, d->act, d->act_param);
