@@ -78,6 +78,29 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, bf16* __restrict
   }
 }
 
+// 64 x 64 tiles, two elements per thread: fp32 pairs in, bf16x2 out on both the straight and the transposed copy
+// (the 32 x 32 version wrote one 2-byte element per lane: 64 B per warp store)
+__global__ void __launch_bounds__(256)
+pack_filter64_kernel(const float* __restrict__ w, bf16* __restrict__ w_ck, bf16* __restrict__ w_kc, int C, int K) {
+  pdl_grid_sync();
+  __shared__ float tile[64][65];
+  const int t = blockIdx.z, c0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  const int64_t base = (int64_t)t * C * K;
+  const int x = threadIdx.x, y = threadIdx.y;                   // block (32, 8)
+#pragma unroll
+  for (int i = y; i < 64; i += 8) {
+    const float2 v = *reinterpret_cast<const float2*>(w + base + (int64_t)(c0 + i) * K + k0 + 2 * x);
+    if (w_ck) *reinterpret_cast<__nv_bfloat162*>(w_ck + base + (int64_t)(c0 + i) * K + k0 + 2 * x) = __floats2bfloat162_rn(v.x, v.y);
+    tile[i][2 * x] = v.x; tile[i][2 * x + 1] = v.y;
+  }
+  __syncthreads();
+  if (w_kc) {
+#pragma unroll
+    for (int i = y; i < 64; i += 8)                             // row i = output channel k0 + i, columns = channel pairs
+      *reinterpret_cast<__nv_bfloat162*>(w_kc + base + (int64_t)(k0 + i) * C + c0 + 2 * x) = __floats2bfloat162_rn(tile[2 * x][i], tile[2 * x + 1][i]);
+  }
+}
+
 // ---- losses --------------------------------------------------------------------------------
 __global__ void sigmoid_ce_kernel(const float* __restrict__ logits, int64_t n, float target, float weight, float* __restrict__ loss_out,
                                   int accumulate, float* __restrict__ dlogits) {
@@ -396,8 +419,13 @@ extern "C" int gg_gather_scalars(const float* const* srcs, int32_t n, float* dst
 
 extern "C" int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t C, int32_t K, void* stream) {
   GG_REQUIRE(w && (w_ck || w_kc) && taps > 0 && C > 0 && K > 0, GG_ERR_INVALID, "pack_filter: bad argument");
-  dim3 grid(ceil_div(K, 32), ceil_div(C, 32), taps), block(32, 8);
-  Launch(grid, block, 0, (cudaStream_t)stream)(pack_filter_kernel, w, (bf16*)w_ck, (bf16*)w_kc, C, K);
+  dim3 block(32, 8);
+  if (C % 64 == 0 && K % 64 == 0) {
+    Launch(dim3(K / 64, C / 64, taps), block, 0, (cudaStream_t)stream)(pack_filter64_kernel, w, (bf16*)w_ck, (bf16*)w_kc, C, K);
+  } else {
+    dim3 grid(ceil_div(K, 32), ceil_div(C, 32), taps);
+    Launch(grid, block, 0, (cudaStream_t)stream)(pack_filter_kernel, w, (bf16*)w_ck, (bf16*)w_kc, C, K);
+  }
   return check_launch("pack_filter");
 }
 
