@@ -145,6 +145,48 @@ __global__ void mse_kernel(const float* __restrict__ a, int64_t as, const float*
   if (threadIdx.x == 0) loss_out[0] = (accumulate ? loss_out[0] : 0.f) + scalar * red[0] * inv;
 }
 
+// ---- L2 + L1 distance to a constant target (latent search: z_space_finder.py:258-292) -------------------------
+// loss (+)= w2 * mean((a-t)^2) + w1 * mean|a-t|;   da = (2 w2 (a-t) + w1 sign(a-t)) / n   (tf.abs' = sign, 0 at 0).
+// Blocks write their partial sums to `partial`; the block that takes the last ticket adds them in block order, so the
+// loss does not depend on the order blocks finish in.  `ticket` must be zero on entry and is zero again on exit.
+constexpr int DIST_MAX_BLOCKS = 296;
+template <typename TA>
+__global__ void __launch_bounds__(PW_THREADS)
+distance_loss_kernel(const TA* __restrict__ a, const float* __restrict__ t, int64_t n, float w2, float w1, float* __restrict__ loss_out,
+                     int accumulate, TA* __restrict__ da, float* __restrict__ partial, unsigned* __restrict__ ticket) {
+  pdl_grid_sync();
+  __shared__ float red2[PW_THREADS / 32], red1[PW_THREADS / 32];
+  const float inv = 1.f / (float)n;
+  float s2 = 0.f, s1 = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = ldf(a + i) - __ldg(t + i);
+    s2 += d * d;
+    s1 += fabsf(d);
+    if (da) stf(da + i, (2.f * w2 * d + w1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f))) * inv);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red2[threadIdx.x >> 5] = s2; red1[threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b2 = 0.f, b1 = 0.f;
+    for (int w = 0; w < PW_THREADS / 32; ++w) { b2 += red2[w]; b1 += red1[w]; }
+    partial[2 * blockIdx.x] = b2;
+    partial[2 * blockIdx.x + 1] = b1;
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      float t2 = 0.f, t1 = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) { t2 += __ldcg(partial + 2 * b); t1 += __ldcg(partial + 2 * b + 1); }
+      loss_out[0] = (accumulate ? loss_out[0] : 0.f) + (w2 * t2 + w1 * t1) * inv;
+      *ticket = 0u;
+    }
+  }
+}
+
 // ---- TF Adam (model.py:153-156) ----------------------------------------------
 __global__ void __launch_bounds__(PW_THREADS)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr_t,
@@ -441,6 +483,25 @@ extern "C" int gg_mse(const float* a, int64_t as, const float* b, int64_t bs, in
   GG_REQUIRE(a && b && loss_out && rows > 0 && cols > 0, GG_ERR_INVALID, "mse: bad argument");
   Launch(1, PW_THREADS, 0, (cudaStream_t)stream)(mse_kernel, a, as, b, bs, rows, cols, scalar, loss_out, accumulate, da);
   return check_launch("mse");
+}
+
+extern "C" size_t gg_distance_loss_workspace_bytes(void) { return (size_t)(2 * DIST_MAX_BLOCKS) * sizeof(float) + 16; }
+
+extern "C" int gg_distance_loss(const void* a, int32_t a_dt, const float* target, int64_t n, float w_l2, float w_l1, float* loss_out,
+                                int32_t accumulate, void* da, void* ws, size_t ws_bytes, void* stream) {
+  GG_REQUIRE(a && target && loss_out && ws && n > 0, GG_ERR_INVALID, "distance_loss: bad argument");
+  GG_REQUIRE(ws_bytes >= gg_distance_loss_workspace_bytes() && al16(ws), GG_ERR_WORKSPACE, "distance_loss: workspace too small or misaligned");
+  GG_REQUIRE(a_dt == GG_F32 || a_dt == GG_BF16, GG_ERR_UNSUPPORTED, "distance_loss: dtype");
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws);                    // zeroed once by the caller; the kernel leaves it zero
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 16);
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n, PW_THREADS * 4), DIST_MAX_BLOCKS));
+  if (a_dt == GG_BF16)
+    Launch(blocks, PW_THREADS, 0, (cudaStream_t)stream)(distance_loss_kernel<bf16>, (const bf16*)a, target, n, w_l2, w_l1, loss_out,
+                                                        (int)accumulate, (bf16*)da, partial, ticket);
+  else
+    Launch(blocks, PW_THREADS, 0, (cudaStream_t)stream)(distance_loss_kernel<float>, (const float*)a, target, n, w_l2, w_l1, loss_out,
+                                                        (int)accumulate, (float*)da, partial, ticket);
+  return check_launch("distance_loss");
 }
 
 extern "C" int gg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps, float gs,

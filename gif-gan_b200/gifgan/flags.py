@@ -1,4 +1,4 @@
-"""Command-line flags of the three entry points, as data.
+"""Command-line flags of the entry points, as data.
 
 The reference declares its options with tf.app.flags (main.py:10-29, z_model.py:22-56, model_sampler.py:9-24).  The
 drop-in contract is the option NAMES, TYPES and DEFAULTS; here each program's options are one table
@@ -18,6 +18,22 @@ _VIDEO_SHAPE = [
     ("c_dim", "i", 3, "colour channels"),
     ("image_noise", "f", 0.0, "std of the gaussian noise added to frames before the image D"),
     ("activation_noise", "f", 0.0, "std of the gaussian noise added to the image-D activations"),
+]
+
+# Options shared by the latent-search programs (z_space_finder.py:31-41, discriminator_activation_optimizer.py:33-45).
+_LATENT_WEIGHTS = [
+    ("pixel_L2_weight", "f", 0.0, "weight of the L2 distance between generated and target pixels"),
+    ("pixel_L1_weight", "f", 0.0, "weight of the L1 distance between generated and target pixels"),
+    ("activations_L2_weight", "f", 1.0, "weight of the L2 distance between discriminator h2 activations"),
+    ("activations_L1_weight", "f", 0.0, "weight of the L1 distance between discriminator h2 activations"),
+    ("generator_loss_weight", "f", 0.0, "weight of the generator's adversarial loss"),
+]
+_LATENT_DCGAN = [
+    ("checkpoint_directory", "s", "", "image-GAN checkpoint to load"),
+    ("image_size", "i", 64, "edge of the target frames"),
+    ("output_size", "i", 64, "edge of the generated frames"),
+    ("c_dim", "i", 3, "colour channels"),
+    ("synthetic", "i", 0, "n > 0: search n seeded random targets instead of reading files (no dataset ships here)"),
 ]
 
 _OURS = [("precision", "s", "bf16", "bf16 = tcgen05 tensor-core path, fp32 = parity mode")]
@@ -77,6 +93,39 @@ TABLES = {
         ("random_seed", "i", 0, "numpy seed of the latents"),
         ("continuous", "b", False, "keep regenerating until interrupted"),
     ] + _OURS,
+    # models/recurrent_z/z_space_finder.py:11-41 (its required options default to "" here and are checked by the program)
+    "z_space_finder": [
+        ("video_dataset_dir", "s", "", "directory the listed clips are read from"),
+        ("output_z_folder", "s", "", "where the per-clip latents (.npy, [vid_length, 100]) are written"),
+        ("output_comparison_folder", "s", "", "optional: side-by-side target | result clips"),
+        ("output_image_folder", "s", "", "optional: one strip of the final frames per clip"),
+        ("output_frame_folder", "s", "", "optional: the final frames as single images"),
+        ("video_batch_size", "i", 8, "clips searched at once"),
+        ("stop_after", "i", 0, "debug: stop after n batches"),
+        ("random_seed", "i", 0, "seed of the initial latents"),
+        ("num_initial_steps", "i", 500, "steps spent on the first frame before tracking"),
+        ("num_steps_per_frame", "i", 100, "steps per tracked frame"),
+        ("learning_rate", "f", 0.05, "Adam step size of the search"),
+        ("lr_decay_amount", "f", 0.5, "factor applied once, after the initial steps"),
+        ("beta1", "f", 0.5, "Adam first-moment decay"),
+        ("discriminator_mode", "s", "", "train | inference: batch statistics or moving averages in the batch norms"),
+        ("vid_length", "i", 16, "frames used per clip"),
+        ("frame_skip", "i", 2, "take every n-th frame of the file"),
+    ] + _LATENT_WEIGHTS + _LATENT_DCGAN + _OURS,
+    # models/recurrent_z/discriminator_activation_optimizer.py:16-55 (GUI, progress-video and path options are not carried over)
+    "activation_optimizer": [
+        ("random_seed", "i", 0, "seed of the initial latents"),
+        ("num_rows", "i", 8, "grid rows (batch = rows x cols)"),
+        ("num_cols", "i", 8, "grid columns"),
+        ("num_steps", "i", 1000, "search steps"),
+        ("learning_rate", "f", 0.0002, "Adam step size of the search"),
+        ("beta1", "f", 0.5, "Adam first-moment decay"),
+        ("discriminator_mode", "s", "", "train | inference"),
+        ("sample_dir", "s", "", "where target.png, train_<i>.png and final.png go"),
+        ("sample_frequency", "i", 100, "steps between sample grids (0: none)"),
+        ("lr_decay_frequency", "i", 0, "steps between learning-rate decays (0: never)"),
+        ("lr_decay_amount", "f", 0.9, "decay factor"),
+    ] + _LATENT_WEIGHTS + _LATENT_DCGAN + _OURS,
 }
 
 
@@ -94,6 +143,11 @@ def parser_for(program):
         _add(p, *spec)
     if program == "video_gan":
         p.add_argument("--video_list", nargs="*", default=[], help="file(s) listing the training clips; empty or 'synthetic' = seeded random clips")
+    if program == "z_space_finder":
+        p.add_argument("--video_list", nargs="*", default=[], help="file(s) listing the clips to invert, one name per line")
+    if program == "activation_optimizer":
+        p.add_argument("--input_videos", nargs="*", default=[], help="search for the first frame of these clips")
+        p.add_argument("--input_images", nargs="*", default=[], help="search for these images")
     return p
 
 

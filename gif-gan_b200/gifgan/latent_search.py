@@ -1,0 +1,210 @@
+"""Latent search: find the z whose generated image matches a target image, in pixels and / or in the image
+discriminator's `h2` activations -- the loss graph and optimiser that /root/reference/models/recurrent_z/z_space_finder.py
+(:226-298) and discriminator_activation_optimizer*.py (:151-217) build on top of a trained DCGAN:
+
+    loss = aL2 * mean((D_h2(G(z)) - D_h2(target))^2) + aL1 * mean|...|
+         + pL2 * mean((G(z) - target)^2)             + pL1 * mean|...|
+         + gW  * mean(sigmoid_ce(D_logits(G(z)), 1))
+    optim = tf.train.AdamOptimizer(lr_tensor, beta1).minimize(loss, var_list=[z])
+
+with the five weights normalised to sum 1 and `discriminator_mode` choosing the train-mode graph (G, D_activations_,
+g_loss: batch statistics) or the inference one (sampler, D_activations_inf_, g_loss_inf: moving averages).  On the device
+one step is: generator forward, discriminator forward (to h2, or to the logits when gW > 0), the distance-loss launches
+(gg_distance_loss writes the loss and its gradient together), the input-gradient kernels back to z -- no filter
+gradients: the var_list is [z] -- and one TF-Adam launch on z.
+
+Terms whose normalised weight is zero are not evaluated (the reference still evaluates them and multiplies by 0.0; the
+only side effect of that is a d_bn3 moving-average update in train mode, which none of these tools read back).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import add_noise, distance_loss, sigmoid_cross_entropy_loss
+
+WEIGHT_NAMES = ("pixel_L2_weight", "pixel_L1_weight", "activations_L2_weight", "activations_L1_weight", "generator_loss_weight")
+
+
+def normalised_weights(opts):
+    """z_space_finder.py:229-238: divide the five loss weights by their sum."""
+    total = sum(float(getattr(opts, k)) for k in WEIGHT_NAMES)
+    if total <= 0:
+        raise ValueError("the loss weights must have a positive sum")
+    return {k: float(getattr(opts, k)) / total for k in WEIGHT_NAMES}
+
+
+class LatentSearch(object):
+    def __init__(self, dcgan, discriminator_mode="inference", pixel_L2_weight=0.0, pixel_L1_weight=0.0, activations_L2_weight=1.0,
+                 activations_L1_weight=0.0, generator_loss_weight=0.0, beta1=0.5, beta2=0.999, epsilon=1e-8, random_seed=0, z=None):
+        """`dcgan`: a gifgan.model.DCGAN (unconditional) holding the trained weights; its batch_size is the number of
+        latents searched at once.  The weights are taken as given (call normalised_weights first for CLI behaviour).
+        `z`: initial latents [batch, z_dim]; default uniform(-1, 1) (tf.random_uniform_initializer, z_space_finder.py:46)."""
+        if discriminator_mode not in ("train", "inference"):
+            raise ValueError("discriminator_mode must be 'train' or 'inference'")
+        if dcgan.y_dim:
+            raise ValueError("latent search is defined for the unconditional DCGAN only")
+        self.dcgan, self.train = dcgan, discriminator_mode == "train"
+        self.w = dict(pixel_L2_weight=float(pixel_L2_weight), pixel_L1_weight=float(pixel_L1_weight),
+                      activations_L2_weight=float(activations_L2_weight), activations_L1_weight=float(activations_L1_weight),
+                      generator_loss_weight=float(generator_loss_weight))
+        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        dev = dcgan.store.device
+        B = dcgan.batch_size
+        if z is None:
+            z = np.random.RandomState(random_seed).uniform(-1.0, 1.0, size=(B, dcgan.z_dim))
+        self.z = torch.as_tensor(np.asarray(z, dtype=np.float32)).to(dev).contiguous().requires_grad_(True)
+        if tuple(self.z.shape) != (B, dcgan.z_dim):
+            raise ValueError(f"z must have shape {(B, dcgan.z_dim)}")
+        # Adam slots of the optimiser built once for the whole run (z_space_finder.py:294-298): they, like z, carry over
+        # from one target to the next
+        self.m, self.v, self.t = torch.zeros_like(self.z), torch.zeros_like(self.z), 0
+        self._ones = torch.ones(1, dtype=torch.float32, device=dev)
+        self._loss_vec = torch.zeros(8, dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------------------------------
+    def _target(self, a):
+        return torch.as_tensor(np.asarray(a, dtype=np.float32) if not torch.is_tensor(a) else a).to(self.z.device, torch.float32).contiguous()
+
+    def target_activations(self, images):
+        """sess.run(D_activations | D_activations_inf, {images: targets}) (z_space_finder.py:127-131): float32 [B, s/8, s/8, 4*df]."""
+        with torch.no_grad():
+            h2 = self.dcgan.discriminator(add_noise(self._target(images), self.dcgan.noise_std), reuse=True, train=self.train, stop_at_h2=True)[2]
+        return h2.float().contiguous()
+
+    def images(self):
+        """sess.run(G | sampler): the images of the current latents, float32 [B, s, s, c] in (-1, 1)."""
+        with torch.no_grad():
+            return self.dcgan.generator(self.z.detach(), train=self.train)
+
+    def lr_t(self, lr):
+        return lr * float(np.sqrt(1.0 - self.beta2 ** self.t)) / (1.0 - self.beta1 ** self.t)
+
+    def loss_and_grad(self, target_images, target_activations):
+        """Loss terms (device float32 [1] each, already weighted) and d loss / d z in self.z.grad."""
+        w, d = self.w, self.dcgan
+        tgt_img = self._target(target_images) if (w["pixel_L2_weight"] or w["pixel_L1_weight"]) else None
+        need_act = bool(w["activations_L2_weight"] or w["activations_L1_weight"])
+        need_gen = bool(w["generator_loss_weight"])
+        self.z.grad = None
+        roots = []
+        with ops.trainable([]), ops.stats_arena():
+            G = d.generator(self.z, train=self.train)
+            if need_act or need_gen:
+                out = d.discriminator(add_noise(G, d.noise_std), reuse=True, train=self.train, stop_at_h2=not need_gen)
+                if need_act:
+                    roots.append(distance_loss(out[2], self._target(target_activations), w["activations_L2_weight"], w["activations_L1_weight"]))
+                if need_gen:
+                    B = out[1].shape[0]
+                    roots.append(sigmoid_cross_entropy_loss(out[1], [(0, B, 1.0, w["generator_loss_weight"])])[0:1])
+            if tgt_img is not None:
+                roots.append(distance_loss(G, tgt_img, w["pixel_L2_weight"], w["pixel_L1_weight"]))
+            torch.autograd.backward(roots, grad_tensors=[self._ones] * len(roots))
+        return roots
+
+    def step(self, target_images, target_activations, lr, fetch_loss=True):
+        """sess.run([optim, loss], {lr_tensor, activations_placeholder, target_placeholder}): one Adam step on z.
+        Returns the loss at the latents BEFORE the update (a Python float; None with fetch_loss=False)."""
+        roots = self.loss_and_grad(target_images, target_activations)
+        self.t += 1
+        z = self.z.detach()
+        ops.check(ops.cabi.lib().gg_adam(ops.ptr(z), ops.ptr(self.z.grad), ops.ptr(self.m), ops.ptr(self.v), z.numel(),
+                                         float(self.lr_t(lr)), self.beta1, self.beta2, self.epsilon, 1.0, ops.stream()), "gg_adam")
+        if not fetch_loss:
+            return None
+        ops.cabi.gather_scalars(roots, self._loss_vec)
+        return float(self._loss_vec[:len(roots)].sum().item())
+
+    # ------------------------------------------------------------------------------------------
+    def fit_video(self, targets, num_initial_steps=500, num_steps_per_frame=100, learning_rate=0.05, lr_decay_amount=0.5, log=None):
+        """z_space_finder.py:122-160 (process_batch): `targets` [B, T, s, s, c] in (-1, 1).  Searches frame 0 from the
+        current latents for num_initial_steps, multiplies the learning rate by lr_decay_amount, then tracks every frame
+        in turn (frame 0 again first) for num_steps_per_frame steps each, warm-starting from the previous frame's
+        latents.  Returns (images [B, T, s, s, c], latents [B, T, z_dim]) as float32 numpy arrays."""
+        targets = np.asarray(targets, dtype=np.float32)
+        B, T = targets.shape[:2]
+        acts = [self.target_activations(targets[:, f]) for f in range(T)]
+        imgs = [self._target(targets[:, f]) for f in range(T)]
+        results = np.zeros(targets.shape, dtype=np.float32)
+        zs = np.zeros((B, T, self.dcgan.z_dim), dtype=np.float32)
+        total = num_initial_steps + num_steps_per_frame * T
+        lr = learning_rate
+        for i in range(num_initial_steps):
+            loss = self.step(imgs[0], acts[0], lr, fetch_loss=log is not None)
+            if log is not None:
+                log("Step %d/%d: loss %f" % (i, total, loss))
+        results[:, 0], zs[:, 0] = self.images().float().cpu().numpy(), self.z.detach().cpu().numpy()
+        lr *= lr_decay_amount
+        for f in range(T):
+            for i in range(num_steps_per_frame):
+                loss = self.step(imgs[f], acts[f], lr, fetch_loss=log is not None)
+                if log is not None:
+                    log("Step %d/%d: loss %f" % (num_initial_steps + num_steps_per_frame * f + i, total, loss))
+            results[:, f], zs[:, f] = self.images().float().cpu().numpy(), self.z.detach().cpu().numpy()
+        return results, zs
+
+    def optimise(self, targets, num_steps=1000, learning_rate=0.0002, lr_decay_frequency=0, lr_decay_amount=0.9, on_step=None):
+        """discriminator_activation_optimizer.py:151-157, 231-276: match one batch of target images for num_steps steps;
+        every lr_decay_frequency steps (when > 0) the learning rate is multiplied by lr_decay_amount.  `on_step(i, loss,
+        images)` is called after each step when given (sample / progress-video writers).  Returns the final images."""
+        acts = self.target_activations(targets)
+        tgt = self._target(targets)
+        lr = learning_rate
+        for i in range(num_steps):
+            loss = self.step(tgt, acts, lr, fetch_loss=on_step is not None)
+            if on_step is not None:
+                on_step(i, loss, self)
+            if lr_decay_frequency > 0 and i % lr_decay_frequency == lr_decay_frequency - 1:
+                lr *= lr_decay_amount
+        return self.images().float().cpu().numpy()
+
+
+# ---- what the two programs share ----------------------------------------------------------------------
+def load_dcgan(opts, batch_size):
+    """load_dcgan of z_space_finder.py:43-68 / discriminator_activation_optimizer.py:57-82: an image DCGAN of
+    `batch_size` latents restored from the newest checkpoint named by <checkpoint_directory>/checkpoint."""
+    import os
+    from .model import DCGAN
+    ops.set_precision(opts.precision)
+    ops.reset_default_store()
+    dcgan = DCGAN(None, image_size=opts.image_size, batch_size=batch_size, output_size=opts.output_size, c_dim=opts.c_dim,
+                  dataset_name='', is_crop=False, checkpoint_dir='', sample_dir='', data_dir='', log_dir='', image_glob='', shuffle=False)
+    if opts.checkpoint_directory:
+        index = os.path.join(opts.checkpoint_directory, "checkpoint")
+        if not os.path.exists(index):
+            raise IOError("no checkpoint index in %s" % opts.checkpoint_directory)
+        with open(index) as f:
+            name = os.path.basename(f.readline().split('"')[1])
+        dcgan.load_payload(torch.load(os.path.join(opts.checkpoint_directory, name), map_location="cpu", weights_only=False))
+    elif not opts.synthetic:
+        raise ValueError("--checkpoint_directory is required (or --synthetic n to run on random weights and targets)")
+    return dcgan
+
+
+def search_from_options(dcgan, opts):
+    if opts.discriminator_mode not in ("train", "inference"):
+        raise ValueError("--discriminator_mode must be train or inference")
+    w = normalised_weights(opts)
+    print("Normalized loss weights:")
+    for k in WEIGHT_NAMES:
+        print(k, w[k])
+    return LatentSearch(dcgan, opts.discriminator_mode, beta1=opts.beta1, random_seed=opts.random_seed, **w)
+
+
+def read_video_frames(path, image_size, vid_length, skip):
+    """load_video of z_space_finder.py:70-88: every `skip`-th frame, resized to image_size (bilinear), RGB, x/127.5 - 1.
+    None when the file has fewer than vid_length * skip frames."""
+    import cv2
+    cap = cv2.VideoCapture(path)
+    frames = []
+    for _ in range(vid_length):
+        im = None
+        for _ in range(skip):
+            ok, im = cap.read() if cap.isOpened() else (False, None)
+            if not ok:
+                print("Video %s not long enough! Skipping!" % path)
+                return None
+        im = cv2.cvtColor(cv2.resize(im, (image_size, image_size), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2RGB)
+        frames.append(im.astype(np.float64) / 127.5 - 1.)
+    return frames

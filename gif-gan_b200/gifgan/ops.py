@@ -1052,6 +1052,43 @@ def sigmoid_cross_entropy_loss(logits, segments=None, target=None):
     return _SigmoidCESum.apply(logits, segments)
 
 
+_DIST_WS = {}
+
+
+class _DistanceLoss(torch.autograd.Function):
+    """w_l2 * mean((a - target)^2) + w_l1 * mean(|a - target|) with the gradient written by the same launch
+    (z_space_finder.py:258-292).  Like _SigmoidCESum it must be a root of backward() (upstream gradient 1)."""
+
+    @staticmethod
+    def forward(ctx, a, target, w_l2, w_l1):
+        L = cabi.lib()
+        a = a.contiguous()
+        ws = _DIST_WS.get(a.device)
+        if ws is None:          # zero-filled once; the kernel hands it back zeroed
+            ws = _DIST_WS[a.device] = torch.zeros(L.gg_distance_loss_workspace_bytes(), dtype=torch.uint8, device=a.device)
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        check(L.gg_distance_loss(ptr(a), dt(a), ptr(target), a.numel(), float(w_l2), float(w_l1), ptr(loss), 0, ptr(da), ptr(ws),
+                                 ws.numel(), stream()), "gg_distance_loss")
+        ctx.da = da
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.da, None, None, None
+
+
+def distance_loss(a, target, w_l2=1.0, w_l1=0.0):
+    """tf.reduce_mean(tf.reduce_mean(w_l2*tf.square(a - target) + w_l1*tf.abs(a - target), [1,2,3])) as a float32 [1]
+    tensor.  `target` is a constant float32 tensor of a's shape (a placeholder in the reference)."""
+    if _is_meta(a):
+        return torch.empty(1, dtype=torch.float32, device="meta")
+    _require_cuda(a, "distance_loss")
+    if target.dtype != torch.float32 or tuple(target.shape) != tuple(a.shape) or not target.is_contiguous():
+        raise ValueError("distance_loss: target must be a contiguous float32 tensor of the input's shape")
+    return _DistanceLoss.apply(a, target, w_l2, w_l1)
+
+
 def binary_cross_entropy(preds, targets, name=None):
     """ops.py:27-43 (unused by the reference's models; kept for API completeness, torch plumbing)."""
     eps = 1e-12

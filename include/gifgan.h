@@ -199,6 +199,15 @@ int gg_sigmoid_ce(const float* logits, int64_t n, float target, float weight, fl
 int gg_mse(const float* a, int64_t a_row_stride, const float* b, int64_t b_row_stride, int64_t rows, int64_t cols,
            float scalar, float* loss_out, int32_t accumulate, float* da, void* stream);
 
+/* latent search (z_space_finder.py:258-292, discriminator_activation_optimizer.py:175-204): distance of a generated
+ * tensor to a constant fp32 target,  loss_out[0] (+)= w_l2*mean((a-t)^2) + w_l1*mean|a-t|  and, when da != NULL,
+ * da = (2*w_l2*(a-t) + w_l1*sign(a-t))/n in a's dtype (the mean over [1,2,3] followed by the mean over the batch is one
+ * mean over all n elements).  ws: gg_distance_loss_workspace_bytes() bytes, 16-byte aligned, zero-filled ONCE by the
+ * caller before the first call (the kernel leaves it ready for the next); block partials are added in a fixed order. */
+size_t gg_distance_loss_workspace_bytes(void);
+int gg_distance_loss(const void* a, int32_t a_dtype, const float* target, int64_t n, float w_l2, float w_l1, float* loss_out,
+                     int32_t accumulate, void* da, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- optimiser (model.py:153-156: tf.train.AdamOptimizer(lr, beta1).minimize) -------
  * TF semantics: p -= lr_t * m / (sqrt(v) + eps) with lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
  * computed by the caller.  One launch over a flat fp32 parameter group.

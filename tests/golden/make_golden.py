@@ -14,6 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import tf_ops as T  # noqa: E402
+from oracle.latent import LatentSearch, make_trained_like  # noqa: E402
 from oracle.models import DCGAN, VID_DCGAN, RecurrentDCGAN  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -104,8 +105,34 @@ def recurrent_fixture():
     np.savez_compressed(os.path.join(OUT, "recurrent_tiny.npz"), **d)
 
 
+LATENT_WEIGHTS = dict(pixel_L2_weight=0.3, pixel_L1_weight=0.1, activations_L2_weight=0.3, activations_L1_weight=0.2,
+                      generator_loss_weight=0.1)
+
+
+def latent_fixture():
+    """Latent search on a tiny trained-like DCGAN (batch 4, 16x16, gf=df=8), all five loss terms, both modes:
+    gradient at the initial latents, 4 steps at lr 0.05 (losses, final latents and images)."""
+    tgt = np.random.RandomState(105).uniform(-1, 1, (4, 16, 16, 3))
+    d = {"targets": tgt}
+    for mode in ("train", "inference"):
+        m = make_trained_like(DCGAN(batch_size=4, output_size=16, gf_dim=8, df_dim=8, seed=7, dtype=f64))
+        s = LatentSearch(m, mode, random_seed=3, **LATENT_WEIGHTS)
+        d[f"{mode}/z0"] = s.z.numpy().copy()
+        if mode == "train":        # identical initial state in both modes (train mode never reads the moving averages)
+            for k, v in m.state_dict().items():
+                d["weights/" + k] = v.numpy()
+        acts = s.target_activations(tgt)
+        d[f"{mode}/target_activations"] = acts.numpy()
+        loss0, g0 = s.loss_and_grad(tgt, acts)
+        d[f"{mode}/loss0"], d[f"{mode}/grad0"] = np.array(loss0), g0.numpy()
+        d[f"{mode}/losses"] = np.array([s.step(tgt, acts, 0.05) for _ in range(4)])
+        d[f"{mode}/z4"], d[f"{mode}/images4"] = s.z.numpy().copy(), s.images().numpy()
+    np.savez_compressed(os.path.join(OUT, "latent_tiny.npz"), **d)
+
+
 if __name__ == "__main__":
     ops_fixture()
+    latent_fixture()
     dcgan_fixture()
     vid_fixture()
     recurrent_fixture()

@@ -148,3 +148,70 @@ def test_cli_option_contract():
     assert smp["continuous"] is True and smp["num_samples"] == 7 and smp["vid_length"] == 16 and smp["random_seed"] == 0
     got = flags.parse("video_gan", ["--video_list", "a.txt", "b.txt", "--train_img_gen", "true", "--gen_updates", "1"])
     assert got.video_list == ["a.txt", "b.txt"] and got.train_img_gen is True and got.gen_updates == 1
+
+
+def test_latent_search_host_side(cpu_store):
+    """gifgan.latent_search without a device: weight normalisation (z_space_finder.py:229-238), the uniform(-1, 1)
+    latents, argument checks -- and the loud failure of the first kernel call (no CPU fallback)."""
+    import argparse
+    from gifgan.latent_search import LatentSearch, WEIGHT_NAMES, normalised_weights
+    from gifgan.model import DCGAN
+    opts = argparse.Namespace(pixel_L2_weight=1.0, pixel_L1_weight=0.0, activations_L2_weight=2.0, activations_L1_weight=1.0,
+                              generator_loss_weight=0.0)
+    w = normalised_weights(opts)
+    assert tuple(w) == WEIGHT_NAMES and abs(sum(w.values()) - 1.0) < 1e-12 and w["activations_L2_weight"] == 0.5
+    with pytest.raises(ValueError):
+        normalised_weights(argparse.Namespace(**{k: 0.0 for k in WEIGHT_NAMES}))
+    m = DCGAN(None, batch_size=3, output_size=16, gf_dim=8, df_dim=8)
+    s = LatentSearch(m, "inference", random_seed=5, **w)
+    want = np.random.RandomState(5).uniform(-1.0, 1.0, size=(3, 100)).astype(np.float32)
+    assert np.array_equal(s.z.detach().numpy(), want) and s.z.requires_grad and s.t == 0
+    assert abs(s.lr_t.__func__(type("T", (), dict(beta1=0.5, beta2=0.999, t=1))(), 0.05) - 0.05 * np.sqrt(1 - 0.999) / 0.5) < 1e-12
+    with pytest.raises(ValueError):
+        LatentSearch(m, "sometimes")
+    with pytest.raises(ValueError):
+        LatentSearch(m, "train", z=np.zeros((2, 100)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        s.step(np.zeros((3, 16, 16, 3), np.float32), np.zeros((3, 2, 2, 32), np.float32), 0.05)
+
+
+def test_latent_cli_contract_and_clip_reader(tmp_path):
+    """Option names / defaults of z_space_finder.py:11-41 and discriminator_activation_optimizer.py:16-45; the clip
+    reader's frame skipping, resize, BGR->RGB and x/127.5-1 (z_space_finder.py:70-88); batching of synthetic clips."""
+    import cv2
+    from gifgan import flags
+    from gifgan.latent_search import read_video_frames
+    from gifgan.z_space_finder import clip_batches, out_path
+    zf = vars(flags.parse("z_space_finder", ["--discriminator_mode", "inference", "--video_list", "a.txt", "b.txt"]))
+    for name, default in dict(video_batch_size=8, stop_after=0, random_seed=0, num_initial_steps=500, num_steps_per_frame=100,
+                              learning_rate=0.05, lr_decay_amount=0.5, beta1=0.5, vid_length=16, frame_skip=2, pixel_L2_weight=0.0,
+                              pixel_L1_weight=0.0, activations_L2_weight=1.0, activations_L1_weight=0.0, generator_loss_weight=0.0,
+                              image_size=64, output_size=64, c_dim=3, output_comparison_folder="", output_image_folder="",
+                              output_frame_folder="").items():
+        assert zf[name] == default, name
+    assert zf["video_list"] == ["a.txt", "b.txt"] and zf["discriminator_mode"] == "inference"
+    ao = vars(flags.parse("activation_optimizer", ["--input_images", "x.png"]))
+    for name, default in dict(num_rows=8, num_cols=8, num_steps=1000, learning_rate=0.0002, beta1=0.5, sample_frequency=100,
+                              lr_decay_frequency=0, lr_decay_amount=0.9, activations_L2_weight=1.0, input_videos=[]).items():
+        assert ao[name] == default, name
+    assert out_path("some/dir/clip7.mp4", "/out") == "/out/clip7.npy" and out_path("clip7.mp4", "/o", ".png") == "/o/clip7.png"
+
+    path = str(tmp_path / "clip.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (48, 32))
+    if not wr.isOpened():
+        pytest.skip("no MJPG writer in this OpenCV build")
+    for i in range(9):                                           # frame i: blue channel (BGR order) = 20 * i, red = 200
+        frame = np.zeros((32, 48, 3), np.uint8)
+        frame[..., 0], frame[..., 2] = 20 * i, 200
+        wr.write(frame)
+    wr.release()
+    frames = read_video_frames(path, 16, 4, 2)                   # frames 1, 3, 5, 7 of the file
+    assert len(frames) == 4 and frames[0].shape == (16, 16, 3)
+    for k, f in enumerate(frames):
+        assert abs(f[..., 0].mean() - (200 / 127.5 - 1)) < 0.06                       # RGB: red first
+        assert abs(f[..., 2].mean() - (20 * (2 * k + 1) / 127.5 - 1)) < 0.06, k
+    assert read_video_frames(path, 16, 5, 2) is None             # 10 frames needed, 9 in the file
+
+    opts = flags.parse("z_space_finder", ["--synthetic", "5", "--video_batch_size", "2", "--vid_length", "3", "--image_size", "8"])
+    batches = list(clip_batches(opts))
+    assert [len(n) for n, _ in batches] == [2, 2, 1] and np.shape(batches[0][1]) == (2, 3, 8, 8, 3)
