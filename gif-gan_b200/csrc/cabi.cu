@@ -70,6 +70,8 @@ int tc_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStr
 bool tc_upcat_ok(const gg_conv_desc*);
 size_t tc_upcat_bytes(const gg_conv_desc*);
 int tc_pack_upcat(const gg_conv_desc*, const float*, void*, cudaStream_t);
+size_t tc_pack_plan_bytes(int);
+int tc_pack_filters(const gg_pack_job*, int, void*, size_t, int, cudaStream_t);
 int tc_conv_up_cat(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
 void tc_set_repeat(int);
 void tc_set_prof(void*);
@@ -152,6 +154,11 @@ extern "C" int gg_pack_filter_upcat(const gg_conv_desc* d, const float* w, void*
 }
 
 static gg_conv_desc no_act(const gg_conv_desc* d) { gg_conv_desc c = *d; c.act = GG_ACT_NONE; return c; }
+
+extern "C" size_t gg_pack_plan_bytes(int32_t njobs) { return njobs > 0 ? tc_pack_plan_bytes(njobs) : 0; }
+extern "C" int gg_pack_filters(const gg_pack_job* jobs, int32_t njobs, void* plan, size_t plan_bytes, int32_t upload, void* stream) {
+  return tc_pack_filters(jobs, njobs, plan, plan_bytes, upload, (cudaStream_t)stream);
+}
 
 extern "C" int gg_conv2d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* s) { return gg_conv_down(d, x, w, b, y, s); }
 extern "C" int gg_conv2d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* s) { GG_REQUIRE(d, GG_ERR_INVALID, "null desc"); gg_conv_desc c = no_act(d); return gg_conv_up(&c, dy, w, nullptr, dx, s); }

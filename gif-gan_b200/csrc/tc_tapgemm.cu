@@ -23,6 +23,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #include "tc_common.cuh"
 
@@ -977,6 +978,100 @@ int tc_pack_upcat(const gg_conv_desc* d, const float* w, void* wcat, cudaStream_
   for (int s = 0; s < UPCAT_MAX_SHIFTS; ++s) for (int c = 0; c < 8; ++c) T.tap[s][c] = (int16_t)P.tap[s][c];
   Launch(dim3(P.ncls * d->C, P.nshift), 128, 0, st)(pack_upcat_kernel, w, (bf16*)wcat, T, P.ncls, (int)d->C, (int)d->K);
   return check_launch("pack_upcat");
+}
+
+// ---- one launch re-packs every filter of an optimiser group -------------------------------------------------
+// After an Adam step all tensor-core filters of the group need fresh bf16 copies (w_ck / w_kc, and the class-concatenated
+// copy where the layer uses it).  As separate launches that is 16 small latency-bound kernels per train step; here the jobs
+// sit in a device table (uploaded once, the pointers never change) and one grid covers all of them: block -> job by the
+// ascending block_begin, then either a 64 x 64 transpose tile or one row of the class-concatenated copy.
+struct PackJobDev {
+  const float* w;
+  bf16 *ck, *kc, *cat;
+  int C, K, block_begin, tile_blocks;        // tile_blocks = taps * (C/64) * (K/64) when ck or kc is set, else 0
+  int ncls, nshift;                          // cat: nshift * ncls * C row blocks
+  int16_t tap[UPCAT_MAX_SHIFTS][8];
+};
+
+__global__ void __launch_bounds__(256) pack_batch_kernel(const PackJobDev* __restrict__ jobs, int njobs) {
+  pdl_grid_sync();
+  __shared__ float tile[64][65];
+  int b = blockIdx.x, j = 0;
+  while (j + 1 < njobs && b >= jobs[j + 1].block_begin) ++j;
+  const PackJobDev* J = jobs + j;
+  b -= J->block_begin;
+  const int C = J->C, K = J->K;
+  const float* __restrict__ w = J->w;
+  const int tid = threadIdx.x;
+  if (b < J->tile_blocks) {
+    const int kt = K / 64, ct = C / 64;
+    const int k0 = (b % kt) * 64, c0 = ((b / kt) % ct) * 64, t = b / (kt * ct);
+    const int64_t base = (int64_t)t * C * K;
+    bf16* __restrict__ w_ck = J->ck;
+    bf16* __restrict__ w_kc = J->kc;
+    const int x = tid & 31, y = tid >> 5;                       // 32 x 8, as pack_filter64_kernel
+#pragma unroll
+    for (int i = y; i < 64; i += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(w + base + (int64_t)(c0 + i) * K + k0 + 2 * x);
+      if (w_ck) *reinterpret_cast<__nv_bfloat162*>(w_ck + base + (int64_t)(c0 + i) * K + k0 + 2 * x) = __floats2bfloat162_rn(v.x, v.y);
+      tile[i][2 * x] = v.x; tile[i][2 * x + 1] = v.y;
+    }
+    __syncthreads();
+    if (w_kc) {
+#pragma unroll
+      for (int i = y; i < 64; i += 8)
+        *reinterpret_cast<__nv_bfloat162*>(w_kc + base + (int64_t)(k0 + i) * C + c0 + 2 * x) = __floats2bfloat162_rn(tile[2 * x][i], tile[2 * x + 1][i]);
+    }
+  } else {
+    b -= J->tile_blocks;
+    const int rows = J->ncls * C;
+    const int row = b % rows, sft = b / rows;
+    const int cls = row / C, c = row - cls * C;
+    const int tap = J->tap[sft][cls];
+    bf16* dst = J->cat + ((int64_t)sft * rows + row) * K;
+    const float* src = w + ((int64_t)(tap < 0 ? 0 : tap) * C + c) * K;
+    for (int k = tid; k < K; k += 256) dst[k] = __float2bfloat16_rn(tap < 0 ? 0.f : __ldg(src + k));
+  }
+}
+
+size_t tc_pack_plan_bytes(int njobs) { return (size_t)njobs * sizeof(PackJobDev); }
+
+// jobs: host array.  upload != 0: (re)build the device table in `plan` first -- a pageable-memory copy, so only outside
+// stream capture; afterwards the same jobs/plan pair is replayed with upload == 0.
+int tc_pack_filters(const gg_pack_job* jobs, int njobs, void* plan, size_t plan_bytes, int upload, cudaStream_t st) {
+  GG_REQUIRE(jobs && plan && njobs > 0 && njobs <= 64, GG_ERR_INVALID, "pack_filters: bad argument");
+  GG_REQUIRE(plan_bytes >= tc_pack_plan_bytes(njobs), GG_ERR_WORKSPACE, "pack_filters: plan buffer too small");
+  std::vector<PackJobDev> dev(njobs);
+  int blocks = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const gg_pack_job& in = jobs[j];
+    PackJobDev& o = dev[j];
+    memset(&o, 0, sizeof(o));
+    GG_REQUIRE(in.w && in.C > 0 && in.K > 0 && in.taps > 0, GG_ERR_INVALID, "pack_filters: bad job");
+    o.w = in.w; o.ck = (bf16*)in.w_ck; o.kc = (bf16*)in.w_kc; o.cat = (bf16*)in.w_cat;
+    o.C = in.C; o.K = in.K; o.block_begin = blocks;
+    if (o.ck || o.kc) {
+      GG_REQUIRE(in.C % 64 == 0 && in.K % 64 == 0, GG_ERR_UNSUPPORTED, "pack_filters: C and K must be multiples of 64");
+      o.tile_blocks = in.taps * (in.C / 64) * (in.K / 64);
+    }
+    if (o.cat) {
+      GG_REQUIRE(tc_upcat_ok(&in.cat_desc) && in.cat_desc.C == in.C && in.cat_desc.K == in.K, GG_ERR_UNSUPPORTED,
+                 "pack_filters: cat_desc not eligible for the class-concatenated layout");
+      UpcatPlan P;
+      int rc = upcat_plan(&in.cat_desc, &P);
+      if (rc) return rc;
+      o.ncls = P.ncls; o.nshift = P.nshift;
+      for (int s2 = 0; s2 < UPCAT_MAX_SHIFTS; ++s2) for (int c = 0; c < 8; ++c) o.tap[s2][c] = (int16_t)P.tap[s2][c];
+    }
+    blocks += o.tile_blocks + o.nshift * o.ncls * o.C;
+  }
+  GG_REQUIRE(blocks > 0, GG_ERR_INVALID, "pack_filters: nothing to pack");
+  if (upload) {
+    cudaError_t e = cudaMemcpyAsync(plan, dev.data(), tc_pack_plan_bytes(njobs), cudaMemcpyHostToDevice, st);
+    GG_REQUIRE(e == cudaSuccess, GG_ERR_CUDA, cudaGetErrorString(e));
+  }
+  Launch(blocks, 256, 0, st)(pack_batch_kernel, (const PackJobDev*)plan, njobs);
+  return check_launch("pack_batch");
 }
 
 int tc_conv_up_cat(const gg_conv_desc* d, const void* small, const void* wcat, const float* bias, void* large, cudaStream_t st,

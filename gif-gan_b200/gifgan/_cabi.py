@@ -27,6 +27,12 @@ class ConvDesc(C.Structure):
                  "large_dtype", "small_dtype", "act")] + [("act_param", C.c_float), ("flags", C.c_int32)]
 
 
+class PackJob(C.Structure):
+    """struct gg_pack_job (include/gifgan.h)."""
+    _fields_ = [("w", C.c_void_p), ("w_ck", C.c_void_p), ("w_kc", C.c_void_p), ("w_cat", C.c_void_p), ("taps", C.c_int32), ("C", C.c_int32),
+                ("K", C.c_int32), ("reserved", C.c_int32), ("cat_desc", ConvDesc)]
+
+
 _lib = None
 
 _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -58,6 +64,8 @@ SIGNATURES = {
     "gg_pack_filter": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "gg_upcat_bytes": (_sz, [_dp]),
     "gg_pack_filter_upcat": (C.c_int, [_dp, _vp, _vp, _vp]),
+    "gg_pack_plan_bytes": (_sz, [_i32]),
+    "gg_pack_filters": (C.c_int, [C.POINTER(PackJob), _i32, _vp, _sz, _i32, _vp]),
     "gg_linear_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "gg_linear_dgrad": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "gg_linear_wgrad": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),

@@ -34,6 +34,7 @@ _LATENT_DCGAN = [
     ("output_size", "i", 64, "edge of the generated frames"),
     ("c_dim", "i", 3, "colour channels"),
     ("synthetic", "i", 0, "n > 0: search n seeded random targets instead of reading files (no dataset ships here)"),
+    ("cuda_graph", "b", True, "replay one captured CUDA graph per search step instead of eager launches"),
 ]
 
 _OURS = [("precision", "s", "bf16", "bf16 = tcgen05 tensor-core path, fp32 = parity mode")]

@@ -37,10 +37,13 @@ def normalised_weights(opts):
 
 class LatentSearch(object):
     def __init__(self, dcgan, discriminator_mode="inference", pixel_L2_weight=0.0, pixel_L1_weight=0.0, activations_L2_weight=1.0,
-                 activations_L1_weight=0.0, generator_loss_weight=0.0, beta1=0.5, beta2=0.999, epsilon=1e-8, random_seed=0, z=None):
+                 activations_L1_weight=0.0, generator_loss_weight=0.0, beta1=0.5, beta2=0.999, epsilon=1e-8, random_seed=0, z=None,
+                 use_graph=False):
         """`dcgan`: a gifgan.model.DCGAN (unconditional) holding the trained weights; its batch_size is the number of
         latents searched at once.  The weights are taken as given (call normalised_weights first for CLI behaviour).
-        `z`: initial latents [batch, z_dim]; default uniform(-1, 1) (tf.random_uniform_initializer, z_space_finder.py:46)."""
+        `z`: initial latents [batch, z_dim]; default uniform(-1, 1) (tf.random_uniform_initializer, z_space_finder.py:46).
+        `use_graph`: replay one captured CUDA graph per step (one capture per learning-rate value) instead of ~60 eager
+        launches; the targets are then copied into fixed device buffers before each replay."""
         if discriminator_mode not in ("train", "inference"):
             raise ValueError("discriminator_mode must be 'train' or 'inference'")
         if dcgan.y_dim:
@@ -60,6 +63,8 @@ class LatentSearch(object):
         # Adam slots of the optimiser built once for the whole run (z_space_finder.py:294-298): they, like z, carry over
         # from one target to the next
         self.m, self.v, self.t = torch.zeros_like(self.z), torch.zeros_like(self.z), 0
+        self.state = torch.zeros(2, dtype=torch.int32, device=dev)      # [t, lr_t bits] on the device (gg_adam_graph)
+        self.use_graph, self._graphs, self._bufs = use_graph, {}, {}
         self._ones = torch.ones(1, dtype=torch.float32, device=dev)
         self._loss_vec = torch.zeros(8, dtype=torch.float32, device=dev)
 
@@ -103,18 +108,67 @@ class LatentSearch(object):
             torch.autograd.backward(roots, grad_tensors=[self._ones] * len(roots))
         return roots
 
-    def step(self, target_images, target_activations, lr, fetch_loss=True):
+    def _step_device(self, target_images, target_activations, lr):
+        roots = self.loss_and_grad(target_images, target_activations)
+        z = self.z.detach()
+        ops.check(ops.cabi.lib().gg_adam_graph(ops.ptr(z), ops.ptr(self.z.grad), ops.ptr(self.m), ops.ptr(self.v), z.numel(),
+                                               ops.ptr(self.state), float(lr), self.beta1, self.beta2, self.epsilon, 1.0, ops.stream()),
+                  "gg_adam_graph")
+        ops.cabi.gather_scalars(roots, self._loss_vec)
+        return len(roots)
+
+    def _static(self, name, src):
+        t = self._target(src)
+        buf = self._bufs.get(name)
+        if buf is None or buf.shape != t.shape:
+            buf = self._bufs[name] = torch.empty_like(t)
+            self._graphs.clear()
+        buf.copy_(t, non_blocking=True)
+        return buf
+
+    def _capture(self, lr):
+        """Capture one step at learning rate `lr`.  The warm-up run (allocator, lazy filter packs) and the capture must
+        not move the search: latents, Adam state and the moving averages are put back afterwards."""
+        img, act = self._bufs.get("img"), self._bufs.get("act")      # None for terms that are switched off
+        flat = self.dcgan.store.flat["params"]
+        snap = [t.clone() for t in (flat, self.z.detach(), self.m, self.v, self.state)]
+
+        def restore():
+            for dst, src in zip((flat, self.z.detach(), self.m, self.v, self.state), snap):
+                dst.copy_(src)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._step_device(img, act, lr)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        restore()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            n = self._step_device(img, act, lr)
+        restore()
+        torch.cuda.synchronize()
+        g = self._graphs[float(lr)] = dict(graph=graph, nroots=n)
+        return g
+
+    def step(self, target_images, target_activations, lr, fetch_loss=True, use_graph=None):
         """sess.run([optim, loss], {lr_tensor, activations_placeholder, target_placeholder}): one Adam step on z.
         Returns the loss at the latents BEFORE the update (a Python float; None with fetch_loss=False)."""
-        roots = self.loss_and_grad(target_images, target_activations)
+        if self.use_graph if use_graph is None else use_graph:
+            if self.w["pixel_L2_weight"] or self.w["pixel_L1_weight"]:
+                self._static("img", target_images)
+            if self.w["activations_L2_weight"] or self.w["activations_L1_weight"]:
+                self._static("act", target_activations)
+            g = self._graphs.get(float(lr)) or self._capture(lr)
+            g["graph"].replay()
+            n = g["nroots"]
+        else:
+            n = self._step_device(target_images, target_activations, lr)
         self.t += 1
-        z = self.z.detach()
-        ops.check(ops.cabi.lib().gg_adam(ops.ptr(z), ops.ptr(self.z.grad), ops.ptr(self.m), ops.ptr(self.v), z.numel(),
-                                         float(self.lr_t(lr)), self.beta1, self.beta2, self.epsilon, 1.0, ops.stream()), "gg_adam")
         if not fetch_loss:
             return None
-        ops.cabi.gather_scalars(roots, self._loss_vec)
-        return float(self._loss_vec[:len(roots)].sum().item())
+        return float(self._loss_vec[:n].sum().item())
 
     # ------------------------------------------------------------------------------------------
     def fit_video(self, targets, num_initial_steps=500, num_steps_per_frame=100, learning_rate=0.05, lr_decay_amount=0.5, log=None):
@@ -189,7 +243,7 @@ def search_from_options(dcgan, opts):
     print("Normalized loss weights:")
     for k in WEIGHT_NAMES:
         print(k, w[k])
-    return LatentSearch(dcgan, opts.discriminator_mode, beta1=opts.beta1, random_seed=opts.random_seed, **w)
+    return LatentSearch(dcgan, opts.discriminator_mode, beta1=opts.beta1, random_seed=opts.random_seed, use_graph=opts.cuda_graph, **w)
 
 
 def read_video_frames(path, image_size, vid_length, skip):

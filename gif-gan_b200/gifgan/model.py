@@ -323,6 +323,8 @@ class DCGAN(object):
         if use_graph:
             key = (B, evals, batch_labels is not None)
             g = self._graph if (self._graph is not None and self._graph["key"] == key) else self._capture(st, evals, key)
+            if ops.PACK_BATCH:
+                ops.refresh_packs(self.store)  # no-op unless weights were changed from outside (checkpoint load)
             g["graph"].replay()
             self.d_optim.t += 1
             self.g_optim.t += 2
@@ -361,7 +363,9 @@ class DCGAN(object):
             self.d_optim.state.copy_(states[0]); self.g_optim.state.copy_(states[1])
             self.d_optim.t, self.g_optim.t = states[2], states[3]
             for v in self.store.vars.values():
-                v.invalidate_packed()          # every replay starts with stale bf16 filter copies
+                v.invalidate_packed()          # every replay starts with stale bf16 filter copies ...
+            if ops.PACK_BATCH:
+                ops.refresh_packs(self.store)  # ... or with current ones when each update re-packs its group in one launch
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -103,6 +103,17 @@ class Var:
             self._packed_version = self.version
         return self._packed
 
+    def packs_stale(self):
+        return ((self._packed is not None and self._packed_version != self.version)
+                or (getattr(self, "_upcat", None) is not None and self._upcat_version != self.version))
+
+    def refresh_packs(self):
+        """Rebuild whichever bf16 copies exist and are stale (per-filter launches)."""
+        if self._packed is not None:
+            self.packed()
+        if getattr(self, "_upcat", None) is not None:
+            self.packed_upcat(self._upcat_desc)
+
     def invalidate_packed(self):
         """Force the bf16 copies to be rebuilt at their next use (CUDA-graph capture: every replay must repack)."""
         self._packed_version = -1
@@ -118,6 +129,7 @@ class Var:
         if getattr(self, "_upcat", None) is None or self._upcat.numel() * 2 != nbytes:
             self._upcat = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=self.data.device)
             self._upcat_version = -1
+            self._upcat_desc = cabi.ConvDesc.from_buffer_copy(desc)     # geometry for the batched re-pack (AdamOptimizer.repack)
         if self._upcat_version != self.version:
             check(L.gg_pack_filter_upcat(ctypes.byref(desc), ptr(self.data), ptr(self._upcat), stream()), "gg_pack_filter_upcat")
             self._upcat_version = self.version
@@ -429,6 +441,21 @@ def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, o
 # Filter gradients are leaves of the backward pass: nothing downstream of them runs before the optimiser.  They are
 # issued on a side stream so that they overlap with the activation-gradient chain (under CUDA-graph capture the
 # fork/join becomes parallel branches of the graph).  join_side() is the join point (optimiser / all-reduce).
+PACK_BATCH = os.environ.get("GG_PACK_BATCH", "0") != "0"   # one re-pack launch per optimiser update (AdamOptimizer.repack)
+
+
+def refresh_packs(store):
+    """Bring every existing bf16 filter copy up to date (eager, per filter).  With PACK_BATCH a captured train step
+    assumes current copies on entry -- it re-packs right after each update -- so this runs after anything that changes
+    weights behind the optimisers' back: the restore around graph capture, a checkpoint load."""
+    n = 0
+    for v in store.vars.values():
+        if v.packs_stale():
+            v.refresh_packs()
+            n += 1
+    return n
+
+
 UPCAT = os.environ.get("GG_UPCAT", "1") != "0"     # class-concatenated conv_up for 64-channel outputs (tc_conv_up_cat)
 OVERLAP_WGRAD = False      # enabled inside `with overlap_wgrad():` (the model's update functions)
 GRAD_READY_HOOK = None     # data parallel: called as hook(var, producer_stream) after a filter gradient was enqueued (dp.py)
@@ -1135,3 +1162,39 @@ class AdamOptimizer:
                                        ptr(self.state), self.lr, self.b1, self.b2, self.eps, grad_scale, stream()), "gg_adam_graph")
         for v in self.var_list or []:
             v.version += 1
+        if PACK_BATCH:
+            self.repack()
+
+    def repack(self):
+        """Refresh the bf16 copies of every tensor-core filter of the var_list with ONE launch (gg_pack_filters) and
+        mark them current, so that a train step carries one re-pack launch per update instead of one or two per
+        filter.  Filters join the plan once their copies exist (first use); the device job table is uploaded outside
+        stream capture only -- a capture that meets a new table falls back to the per-filter packs at first use."""
+        vs = [v for v in (self.var_list or []) if v._packed is not None or getattr(v, "_upcat", None) is not None]
+        if not vs:
+            return False
+        sig = tuple((v.data.data_ptr(), v._packed[0].data_ptr() if v._packed is not None else 0,
+                     v._upcat.data_ptr() if getattr(v, "_upcat", None) is not None else 0) for v in vs)
+        plan = getattr(self, "_pack_plan", None)
+        upload = plan is None or plan["sig"] != sig
+        L = cabi.lib()
+        if upload:
+            if torch.cuda.is_current_stream_capturing():
+                return False
+            jobs = (cabi.PackJob * len(vs))()
+            for j, v in zip(jobs, vs):
+                C_, K_ = v.data.shape[-2], v.data.shape[-1]
+                j.w, j.taps, j.C, j.K = v.data.data_ptr(), v.data.numel() // (C_ * K_), C_, K_
+                if v._packed is not None:
+                    j.w_ck, j.w_kc = v._packed[0].data_ptr(), v._packed[1].data_ptr()
+                if getattr(v, "_upcat", None) is not None:
+                    j.w_cat, j.cat_desc = v._upcat.data_ptr(), v._upcat_desc
+            dev = torch.empty(L.gg_pack_plan_bytes(len(vs)), dtype=torch.uint8, device=self.store.device)
+            plan = self._pack_plan = dict(sig=sig, jobs=jobs, dev=dev, vars=vs)
+        check(L.gg_pack_filters(plan["jobs"], len(vs), ptr(plan["dev"]), plan["dev"].numel(), 1 if upload else 0, stream()), "gg_pack_filters")
+        for v in vs:
+            if v._packed is not None:
+                v._packed_version = v.version
+            if getattr(v, "_upcat", None) is not None:
+                v._upcat_version = v.version
+        return True

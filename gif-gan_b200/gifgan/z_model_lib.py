@@ -282,6 +282,8 @@ class VID_DCGAN(object):
             g = self._graphs.get(key)
             if g is None:
                 g = self._graphs[key] = self._capture(args)
+            if ops.PACK_BATCH:
+                ops.refresh_packs(self.store)
             g["graph"].replay()
             self.d_optim.t += disc_updates
             self.g_optim.t += gen_updates
@@ -304,6 +306,8 @@ class VID_DCGAN(object):
             self.d_optim.t, self.g_optim.t = states[2], states[3]
             for v in self.store.vars.values():
                 v.invalidate_packed()
+            if ops.PACK_BATCH:
+                ops.refresh_packs(self.store)
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

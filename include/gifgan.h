@@ -130,6 +130,23 @@ int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t
 size_t gg_upcat_bytes(const gg_conv_desc* d);
 int gg_pack_filter_upcat(const gg_conv_desc* d, const float* w, void* wcat, void* stream);
 
+/* All tensor-core filters of one optimiser group re-packed by ONE launch (after the Adam step that changed them).
+ * A job names the fp32 filter [taps,C,K] and the copies to refresh: w_ck / w_kc as gg_pack_filter (C, K multiples of 64;
+ * both may be NULL) and w_cat as gg_pack_filter_upcat for the relation `cat_desc` (NULL: none).  `plan` is a device
+ * buffer of gg_pack_plan_bytes(njobs) bytes owned by the caller; upload != 0 (re)writes it from `jobs` with a host->device
+ * copy -- call that way once, outside stream capture, and whenever a pointer changes; upload == 0 only launches. */
+typedef struct gg_pack_job {
+  const float* w;
+  void* w_ck;
+  void* w_kc;
+  void* w_cat;
+  int32_t taps, C, K;
+  int32_t reserved;
+  gg_conv_desc cat_desc;
+} gg_pack_job;
+size_t gg_pack_plan_bytes(int32_t njobs);
+int gg_pack_filters(const gg_pack_job* jobs, int32_t njobs, void* plan, size_t plan_bytes, int32_t upload, void* stream);
+
 /* ---- linear (ops.py:106-117: tf.matmul(input_, Matrix) + bias) ---------------------- */
 int gg_linear_fwd(const void* x, int32_t x_dtype, const float* matrix, const float* bias, void* y, int32_t y_dtype,
                   int32_t rows, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, void* stream);

@@ -177,6 +177,36 @@ def test_fit_video_schedule_fp32():
     assert out.shape == (2, 32, 32, 3) and [i for i, _ in seen] == [0, 1, 2, 3] and s.t == 13
 
 
+@pytest.mark.parametrize("precision,mode", [("fp32", "train"), ("bf16", "inference")])
+def test_cuda_graph_steps_equal_eager_steps(precision, mode):
+    """use_graph=True replays one captured graph per learning-rate value; capturing must not move the search."""
+    width = 16 if precision == "fp32" else 64
+    size = 32 if precision == "fp32" else 64
+    B = 4 if precision == "fp32" else 8
+    tgt = np.random.RandomState(105).uniform(-1, 1, (B, size, size, 3)).astype(np.float32)
+    runs = []
+    for use_graph in (False, True):
+        s, o = make_pair(precision, B, size, width, 3.0, mode, ALL)
+        acts = s.target_activations(tgt)
+        tgt_dev = torch.tensor(tgt).cuda()
+        ema0 = s.dcgan.store.vars["g_bn1/moving_mean"].data.clone()
+        losses, lr = [], 0.05
+        for i in range(5):
+            losses.append(s.step(tgt_dev if i % 2 else tgt, acts, lr, use_graph=use_graph))
+            if i == 2:
+                lr *= 0.5
+        if use_graph:
+            assert sorted(s._graphs) == [0.025, 0.05]
+        if mode == "inference":
+            assert torch.equal(s.dcgan.store.vars["g_bn1/moving_mean"].data, ema0)
+        runs.append((losses, s.z.detach().clone(), int(s.state[0].item()), s.t))
+    (le, ze, te, he), (lg, zg, tg, hg) = runs
+    assert te == tg == 5 and he == hg == 5
+    tol = 1e-5 if precision == "fp32" else 2e-3          # bf16: batch-statistics atomics reorder -> last-bit activation flips
+    np.testing.assert_allclose(lg, le, rtol=tol)
+    assert (zg - ze).abs().max().item() < (1e-4 if precision == "fp32" else 0.11)
+
+
 # ---- bf16 tensor-core path at DCGAN-64 width ------------------------------------------------------
 @pytest.mark.parametrize("mode", ["train", "inference"])
 def test_bf16_dcgan64_against_quantised_oracle(mode):

@@ -214,3 +214,87 @@ def test_tc_cluster_split_k(splitk, monkeypatch):
         test_tc_conv2d("d_h2", 16, 16, 128, 256)
     finally:
         monkeypatch.delenv("GG_TC_SPLITK", raising=False)
+
+
+def test_batched_filter_pack_is_bit_identical():
+    """gg_pack_filters (one launch for all filters of an optimiser group) against gg_pack_filter / gg_pack_filter_upcat
+    per filter: same bits in w_ck, w_kc and the class-concatenated copy; upload=0 replays the device table."""
+    import ctypes
+    from gifgan import _cabi, ops
+    L = _cabi.lib()
+    rs = np.random.RandomState(3)
+    shapes = [(25, 128, 256), (25, 64, 128), (27, 256, 256), (25, 64, 128)]           # (taps, C, K); the last one also gets a cat copy
+    ws = [torch.tensor(rs.randn(*s).astype(np.float32)).cuda() for s in shapes]
+    d = _cabi.ConvDesc()
+    for name, val in dict(N=4, D=1, H=32, W=32, C=64, Do=1, Ho=16, Wo=16, K=128, kd=1, kh=5, kw=5, sd=1, sh=2, sw=2, pd=0, ph=1, pw=1,
+                          large_dtype=1, small_dtype=1, act=0, flags=_cabi.CONV_TENSOR_CORE).items():
+        setattr(d, name, val)
+    cat_elems = L.gg_upcat_bytes(ctypes.byref(d)) // 2
+    assert cat_elems == 9 * 256 * 128
+    want, got = [], []
+    for i, (w, s) in enumerate(zip(ws, shapes)):
+        ck, kc = torch.zeros(s, dtype=torch.bfloat16, device="cuda"), torch.zeros(s, dtype=torch.bfloat16, device="cuda")
+        ops.check(L.gg_pack_filter(ops.ptr(w), ops.ptr(ck), ops.ptr(kc), s[0], s[1], s[2], ops.stream()))
+        want.append([ck, kc])
+        got.append([torch.full(s, 7.0, dtype=torch.bfloat16, device="cuda"), torch.full(s, 7.0, dtype=torch.bfloat16, device="cuda")])
+    cat_want = torch.zeros(cat_elems, dtype=torch.bfloat16, device="cuda")
+    ops.check(L.gg_pack_filter_upcat(ctypes.byref(d), ops.ptr(ws[3]), ops.ptr(cat_want), ops.stream()))
+    cat_got = torch.full((cat_elems,), 7.0, dtype=torch.bfloat16, device="cuda")
+    jobs = (_cabi.PackJob * 4)()
+    for i, (j, w, s) in enumerate(zip(jobs, ws, shapes)):
+        j.w, j.taps, j.C, j.K = w.data_ptr(), s[0], s[1], s[2]
+        j.w_ck, j.w_kc = got[i][0].data_ptr(), got[i][1].data_ptr()
+    jobs[1].w_ck = None                                                                # only the transposed copy wanted
+    jobs[3].w_cat, jobs[3].cat_desc = cat_got.data_ptr(), d
+    plan = torch.empty(L.gg_pack_plan_bytes(4), dtype=torch.uint8, device="cuda")
+    ops.check(L.gg_pack_filters(jobs, 4, ops.ptr(plan), plan.numel(), 1, ops.stream()), "gg_pack_filters")
+
+    def compare():
+        for i in range(4):
+            if i != 1:
+                assert torch.equal(got[i][0], want[i][0]), i
+            assert torch.equal(got[i][1], want[i][1]), i
+        assert torch.equal(got[1][0], torch.full(shapes[1], 7.0, dtype=torch.bfloat16, device="cuda"))     # untouched
+        assert torch.equal(cat_got, cat_want)
+
+    compare()
+    for t in [g for pair in got for g in pair] + [cat_got]:
+        t.fill_(3.0)
+    got[1][0].fill_(7.0)
+    ops.check(L.gg_pack_filters(jobs, 4, ops.ptr(plan), plan.numel(), 0, ops.stream()), "gg_pack_filters")   # replay, no upload
+    compare()
+    assert L.gg_pack_filters(jobs, 4, ops.ptr(plan), 16, 1, ops.stream()) != 0 and b"plan buffer" in L.gg_last_error()
+
+
+def test_train_step_with_batched_repack_equals_per_filter_repack(monkeypatch):
+    """GG_PACK_BATCH: one re-pack launch per optimiser update, graph entered with current copies -- the trajectory of
+    the captured DCGAN-64 step must be the one of the per-filter packs, with fewer launches."""
+    from gifgan import ops
+    from gifgan.model import DCGAN
+    B = 8
+    img = np.random.RandomState(102).uniform(-1, 1, (B, 64, 64, 3)).astype(np.float32)
+    runs = []
+    for batch in (False, True):
+        monkeypatch.setattr(ops, "PACK_BATCH", batch)
+        ops.set_precision("bf16")
+        ops.reset_default_store(device="cuda", seed=7)
+        m = DCGAN(None, batch_size=B, output_size=64, c_dim=3)
+        losses = []
+        for step in range(3):
+            z = np.random.RandomState(1000 + step).uniform(-1, 1, (B, 100)).astype(np.float32)
+            o = m.train_step(img, z, use_graph=True)
+            losses.append([o["d_loss"], o["g_loss_first"], o["g_loss"]])
+        runs.append((np.array(losses), m.store.flat["params"].clone(), m._graph["launches"]))
+        if batch:
+            # a weight change behind the optimisers' back (checkpoint load) is picked up before the next replay
+            sd = m.store.state_dict()
+            sd["d_h1_conv/w"] = sd["d_h1_conv/w"] * 0.5
+            m.store.load_state_dict(sd)
+            assert m.store.vars["d_h1_conv/w"].packs_stale()
+            m.train_step(img, z, use_graph=True)
+            assert not m.store.vars["d_h1_conv/w"].packs_stale()
+    (l0, p0, n0), (l1, p1, n1) = runs
+    assert n1 <= n0 - 10, (n0, n1)
+    # same kernels on the same bits; only the batch-norm statistics atomics may reorder
+    np.testing.assert_allclose(l1, l0, rtol=2e-3, atol=2e-3)
+    assert ((p1 - p0).abs() > 1e-3).float().mean().item() < 0.02
