@@ -441,7 +441,7 @@ def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, o
 # Filter gradients are leaves of the backward pass: nothing downstream of them runs before the optimiser.  They are
 # issued on a side stream so that they overlap with the activation-gradient chain (under CUDA-graph capture the
 # fork/join becomes parallel branches of the graph).  join_side() is the join point (optimiser / all-reduce).
-PACK_BATCH = os.environ.get("GG_PACK_BATCH", "0") != "0"   # one re-pack launch per optimiser update (AdamOptimizer.repack)
+PACK_BATCH = os.environ.get("GG_PACK_BATCH", "1") != "0"   # one re-pack launch per optimiser update (AdamOptimizer.repack); 0: per filter, at first use
 
 
 def refresh_packs(store):

@@ -267,8 +267,9 @@ def test_batched_filter_pack_is_bit_identical():
 
 
 def test_train_step_with_batched_repack_equals_per_filter_repack(monkeypatch):
-    """GG_PACK_BATCH: one re-pack launch per optimiser update, graph entered with current copies -- the trajectory of
-    the captured DCGAN-64 step must be the one of the per-filter packs, with fewer launches."""
+    """ops.PACK_BATCH (default on; GG_PACK_BATCH=0 switches it off): one re-pack launch per optimiser update, graph
+    entered with current copies -- the trajectory of the captured DCGAN-64 step must be the one of the per-filter packs,
+    with fewer launches."""
     from gifgan import ops
     from gifgan.model import DCGAN
     B = 8
@@ -295,6 +296,12 @@ def test_train_step_with_batched_repack_equals_per_filter_repack(monkeypatch):
             assert not m.store.vars["d_h1_conv/w"].packs_stale()
     (l0, p0, n0), (l1, p1, n1) = runs
     assert n1 <= n0 - 10, (n0, n1)
-    # same kernels on the same bits; only the batch-norm statistics atomics may reorder
-    np.testing.assert_allclose(l1, l0, rtol=2e-3, atol=2e-3)
+    # Same kernels on the same bits -- except that the filter-gradient kernels add their partial sums with fp32
+    # reduce-adds in the order CTAs finish, so even two runs of ONE configuration differ in the last bits
+    # (tools/pack_ab_diag.py) and the randomly initialised GAN amplifies that from step to step.  Step 0: the D loss is
+    # computed before any update (equal), the first G loss after one Adam step of D (last-bit noise only).  A stale
+    # filter copy would show as an O(1) difference there: g_loss_first is ~13.8 with the updated D, ~1 with the old one.
+    assert abs(l1[0, 0] - l0[0, 0]) <= 1e-6 * abs(l0[0, 0]), (l0, l1)
+    assert abs(l1[0, 1] - l0[0, 1]) <= 1e-3 * abs(l0[0, 1]), (l0, l1)
+    np.testing.assert_allclose(l1, l0, rtol=0.15, atol=0.02)
     assert ((p1 - p0).abs() > 1e-3).float().mean().item() < 0.02
