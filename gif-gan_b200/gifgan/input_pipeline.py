@@ -1,0 +1,126 @@
+"""Host input pipeline.
+
+The reference decodes its batch inside the step loop, on the thread that then calls sess.run: `get_image` per file at
+models/recurrent_z/model.py:212-219, `get_videos` (OpenCV mp4 decode + resize) at z_model_lib.py:332-351 -- with a
+1.6 ms train step the decode of 64 JPEGs (or 32 x 16 video frames) is what the loop would wait for.  `Prefetcher` moves
+that work off the step's thread without changing what the loop sees:
+
+  * batches are produced IN ORDER by `load_item(item)` calls fanned out over a small thread pool (OpenCV releases the
+    GIL while it decodes and resizes), `depth` batches ahead of the consumer and never further;
+  * every batch is assembled in one of `depth + 3` reusable float32 buffers -- page-locked when a CUDA device is
+    present, so `train_step`'s `copy_(non_blocking=True)` is a true asynchronous H2D copy; a buffer is handed out again
+    only after the consumer has come back for the batch after the next one, i.e. after the step that read it has
+    synchronised;
+  * an exception in a loader surfaces in the consumer at the batch it belongs to; `close()` (or leaving the `with`
+    block, or exhausting the iterator) stops the workers.
+
+It yields `torch.Tensor` views `[len(items), *item_shape]` of those buffers.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+
+class Prefetcher(object):
+    def __init__(self, batches, load_item, item_shape, depth=2, workers=4, pin=None):
+        """`batches`: a sequence of batches, each a sequence of items (file names); `load_item(item)` -> array of
+        `item_shape` (any float / int dtype; stored as float32)."""
+        self.batches = list(batches)
+        self.load_item, self.item_shape = load_item, tuple(item_shape)
+        self.depth = max(1, int(depth))
+        rows = max((len(b) for b in self.batches), default=0)
+        pin = torch.cuda.is_available() if pin is None else pin
+        self._ring = [torch.empty((rows,) + self.item_shape, dtype=torch.float32) for _ in range(self.depth + 3)]
+        if pin:
+            self._ring = [t.pin_memory() for t in self._ring]
+        self._free = queue.Queue()
+        for i in range(len(self._ring)):
+            self._free.put(i)
+        self._ready = queue.Queue(maxsize=self.depth)
+        self._stop = threading.Event()
+        self._pool = ThreadPoolExecutor(max_workers=max(1, int(workers)), thread_name_prefix="gifgan-decode")
+        self._held = []                       # buffers the consumer may still be reading (newest last)
+        self.max_ahead = 0                    # diagnostics: how far the producer ever was ahead of the consumer
+        self._consumed = 0
+        self._producer = threading.Thread(target=self._produce, name="gifgan-prefetch", daemon=True)
+        self._producer.start()
+
+    # ---- producer thread ---------------------------------------------------------------------------
+    def _fill(self, buf, row, item):
+        buf[row].copy_(torch.from_numpy(np.ascontiguousarray(self.load_item(item), dtype=np.float32).reshape(self.item_shape)))
+
+    def _take_free(self):
+        while not self._stop.is_set():
+            try:
+                return self._free.get(timeout=0.05)
+            except queue.Empty:
+                continue
+        return None
+
+    def _produce(self):
+        for k, items in enumerate(self.batches):
+            slot = self._take_free()
+            if slot is None:
+                return
+            buf = self._ring[slot]
+            err = None
+            try:
+                futures = [self._pool.submit(self._fill, buf, r, it) for r, it in enumerate(items)]
+                for f in futures:
+                    f.result()
+            except BaseException as e:        # delivered to the consumer in batch order
+                err = e
+            self.max_ahead = max(self.max_ahead, k + 1 - self._consumed)
+            while not self._stop.is_set():
+                try:
+                    self._ready.put((slot, len(items), err), timeout=0.05)
+                    break
+                except queue.Full:
+                    continue
+            if err is not None or self._stop.is_set():
+                return
+
+    # ---- consumer ---------------------------------------------------------------------------------
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._consumed >= len(self.batches):
+            self.close()
+            raise StopIteration
+        # the batch handed out two calls ago is no longer in use: its step has synchronised before this call
+        while len(self._held) >= 2:
+            self._free.put(self._held.pop(0))
+        slot, n, err = self._ready.get()
+        self._consumed += 1
+        if err is not None:
+            self.close()
+            raise err
+        self._held.append(slot)
+        return self._ring[slot][:n]
+
+    def __len__(self):
+        return len(self.batches)
+
+    def close(self):
+        self._stop.set()
+        self._pool.shutdown(wait=False, cancel_futures=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        if self._producer.is_alive():
+            self._producer.join(timeout=2.0)
+
+
+def chunks(items, batch_size, drop_last=True):
+    """Consecutive batches of `batch_size` items (the reference's `data[idx*B:(idx+1)*B]`, model.py:212)."""
+    n = len(items) // batch_size if drop_last else -(-len(items) // batch_size)
+    return [items[i * batch_size:(i + 1) * batch_size] for i in range(n)]

@@ -415,6 +415,9 @@ class DCGAN(object):
                 batch_idxs = min(len(data_X), config.train_size) // config.batch_size
             else:
                 batch_idxs = min(len(data), config.train_size) // config.batch_size
+            loader = None
+            if config.dataset not in ('mnist', 'synthetic'):
+                loader = self.file_batches(data[:int(min(len(data), config.train_size))], config.batch_size)
             for idx in range(0, int(batch_idxs)):
                 batch_labels = None
                 if config.dataset in ('mnist', 'synthetic'):
@@ -422,12 +425,7 @@ class DCGAN(object):
                     if config.dataset == 'mnist':
                         batch_labels = data_y[idx * config.batch_size:(idx + 1) * config.batch_size]
                 else:
-                    batch_files = data[idx * config.batch_size:(idx + 1) * config.batch_size]
-                    batch = [get_image(f, self.image_size, is_crop=self.is_crop, resize_w=self.output_size,
-                                       is_grayscale=self.is_grayscale) for f in batch_files]
-                    batch_images = np.array(batch).astype(np.float32)
-                    if self.is_grayscale:
-                        batch_images = batch_images[:, :, :, None]
+                    batch_images = next(loader)      # decoded ahead of the step by input_pipeline.Prefetcher
                 batch_z = np.random.uniform(-1, 1, [config.batch_size, self.z_dim]).astype(np.float32)
 
                 last = self.train_step(batch_images, batch_z, batch_labels, evals=True)
@@ -442,6 +440,15 @@ class DCGAN(object):
                 if np.mod(counter, 500) == 2:
                     self.save(config.checkpoint_dir, counter)
         return last
+
+    def file_batches(self, files, batch_size, depth=2, workers=8):
+        """The image batches of model.py:212-219 (get_image per file, consecutive slices of the file list) as an iterator
+        that decodes `depth` batches ahead on worker threads into page-locked buffers (input_pipeline.Prefetcher)."""
+        from .input_pipeline import Prefetcher, chunks
+        s = self.output_size
+        return Prefetcher(chunks(files, batch_size),
+                          lambda f: get_image(f, self.image_size, is_crop=self.is_crop, resize_w=s, is_grayscale=self.is_grayscale),
+                          (s, s, self.c_dim), depth=depth, workers=workers)
 
     def load_mnist(self):
         """model.py:391-426."""

@@ -356,12 +356,13 @@ class VID_DCGAN(object):
         rs = np.random.RandomState(103)
         last = None
         for epoch in range(config.epoch):
+            loader = None if synthetic else self.video_batches(files, batch_size)
             for i in range(n_batches):
                 if synthetic:
                     s = self.output_image_size
                     batch_images = rs.uniform(-1, 1, (batch_size * self.vid_length, s, s, self.c_dim)).astype(np.float32)
                 else:
-                    batch_images = self.load_videos(files[i * batch_size:(i + 1) * batch_size]).astype(np.float32)
+                    batch_images = next(loader).reshape(-1, self.input_image_size, self.input_image_size, self.c_dim)
                 batch_z = np.random.uniform(-1, 1, size=(self.batch_size, self.z_input_size)).astype(np.float32)
                 last = self.train_step(batch_images, batch_z, config.disc_updates, config.gen_updates)
                 counter += 1
@@ -395,6 +396,14 @@ class VID_DCGAN(object):
             w.write(frame)
         w.release()
         return filename
+
+    def video_batches(self, files, batch_size, depth=2, workers=8):
+        """The clip batches of z_model_lib.py:226-228 (get_videos on consecutive slices of the file list), decoded
+        `depth` batches ahead on worker threads into page-locked buffers; each batch is [clips, T, s, s, c]."""
+        from .input_pipeline import Prefetcher, chunks
+        s = self.input_image_size
+        return Prefetcher(chunks(files, batch_size), lambda f: self.load_videos([f]), (self.vid_length, s, s, self.c_dim),
+                          depth=depth, workers=workers)
 
     def load_videos(self, files):
         """z_model_lib.py:332-351."""
