@@ -230,7 +230,12 @@ def load_dcgan(opts, batch_size):
             raise IOError("no checkpoint index in %s" % opts.checkpoint_directory)
         with open(index) as f:
             name = os.path.basename(f.readline().split('"')[1])
-        dcgan.load_payload(torch.load(os.path.join(opts.checkpoint_directory, name), map_location="cpu", weights_only=False))
+        path = os.path.join(opts.checkpoint_directory, name)
+        if os.path.exists(path + ".index"):                    # a TensorFlow V2 checkpoint
+            from . import checkpoint_io
+            checkpoint_io.load_tf_checkpoint(path, dcgan.store, (dcgan.d_optim, dcgan.g_optim))
+        else:
+            dcgan.load_payload(torch.load(path, map_location="cpu", weights_only=False))
     elif not opts.synthetic:
         raise ValueError("--checkpoint_directory is required (or --synthetic n to run on random weights and targets)")
     return dcgan

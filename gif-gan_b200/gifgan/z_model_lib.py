@@ -440,7 +440,7 @@ class VID_DCGAN(object):
         if not os.path.exists(index):
             return None
         with open(index) as f:
-            return os.path.join(checkpoint_dir, f.readline().split('"')[1])
+            return os.path.join(checkpoint_dir, os.path.basename(f.readline().split('"')[1]))   # z_model_lib.py:122-123
 
     def load_image_gan(self, sess, checkpoint_dir):
         """z_model_lib.py:117-134: restore the nested image GAN from a DCGAN checkpoint (prefix-stripped names)."""
@@ -448,8 +448,12 @@ class VID_DCGAN(object):
         if path is None:
             print("FAIL!")
             return False
-        payload = torch.load(path, map_location="cpu", weights_only=False)
-        self.store.load_state_dict(payload["variables"], strict=True, prefix=self.image_gan_scope_name)
+        if os.path.exists(path + ".index"):                    # a TensorFlow V2 checkpoint of the image GAN
+            from . import checkpoint_io
+            checkpoint_io.load_tf_checkpoint(path, self.store, prefix=self.image_gan_scope_name)
+        else:
+            payload = torch.load(path, map_location="cpu", weights_only=False)
+            self.store.load_state_dict(payload["variables"], strict=True, prefix=self.image_gan_scope_name)
         print("Success!")
         return True
 
@@ -459,7 +463,11 @@ class VID_DCGAN(object):
         if path is None:
             print("FAIL!")
             return False
-        payload = torch.load(path, map_location="cpu", weights_only=False)
-        self.store.load_state_dict(payload["variables"])
+        if os.path.exists(path + ".index"):
+            from . import checkpoint_io
+            checkpoint_io.load_tf_checkpoint(path, self.store)
+        else:
+            payload = torch.load(path, map_location="cpu", weights_only=False)
+            self.store.load_state_dict(payload["variables"])
         print("Success!")
         return True
