@@ -90,8 +90,17 @@ class RecurrentDCGAN(object):
     CH = [3, 64, 128, 256, 512]
 
     def __init__(self, batch_size=40, video_length=16, image_dimension=64, state_size=100, stddev=0.02,
-                 learning_rate=0.0002, beta1=0.5, store=None):
+                 learning_rate=0.0002, beta1=0.5, store=None, num_layers=1, shared_conv=False, output_keep_prob=1.0):
+        """The two variants of the reference script are options here:
+        num_layers=3: multi-layer_recurrent_DCGAN.py (:22, :206-207) -- MultiRNNCell of separately parameterised
+          BasicLSTMCells (`lstm/Cell<k>/{Matrix,Bias}`); every layer is one _LSTM over the whole sequence.
+        shared_conv=True, output_keep_prob=0.8: multi-layer_recurrent_DCGAN_with_shared_conv_and_drop_out.py -- the
+          encoder runs the DISCRIMINATOR's conv filters and d_fc (:207, :213-215; LSTM input = state_size), so the D
+          update also differentiates through the generator's encoder; the discriminator uses ReLU (:280, :300);
+          DropoutWrapper(output_keep_prob) scales every cell's OUTPUT by a {0, 1/keep} mask (:219) while the recurrent
+          state stays undropped.  `self.masks` ([layers, T, B, H]) fixes the draws (parity tests); None = draw per call."""
         self.B, self.T, self.S, self.H = batch_size, video_length, image_dimension, state_size
+        self.L, self.shared_conv, self.keep, self.masks = int(num_layers), bool(shared_conv), float(output_keep_prob), None
         self.store = st = store if store is not None else ops.default_store()
         rn = ops.random_normal_initializer(stddev)
         zeros = ops.constant_initializer(0.0)
@@ -100,11 +109,19 @@ class RecurrentDCGAN(object):
         self.fc = fc = s16 * s16 * 512
         V = {}
         with ops.variable_scope("generator"):
-            for i in range(4):
-                V[f"g_conv{i}"] = st.get_variable(f"conv_f{i + 1}", [5, 5, CH[i], CH[i + 1]], rn, filter_taps=25)
+            if not self.shared_conv:
+                for i in range(4):
+                    V[f"g_conv{i}"] = st.get_variable(f"conv_f{i + 1}", [5, 5, CH[i], CH[i + 1]], rn, filter_taps=25)
+            lstm_in = state_size if self.shared_conv else fc
             with ops.variable_scope("lstm"):
-                V["lstm_m"] = st.get_variable("Matrix", [fc + state_size, 4 * state_size], rn)
-                V["lstm_b"] = st.get_variable("Bias", [4 * state_size], zeros)
+                if self.L == 1:
+                    V["lstm_m0"] = st.get_variable("Matrix", [lstm_in + state_size, 4 * state_size], rn)
+                    V["lstm_b0"] = st.get_variable("Bias", [4 * state_size], zeros)
+                else:
+                    for k in range(self.L):
+                        with ops.variable_scope("Cell%d" % k):
+                            V[f"lstm_m{k}"] = st.get_variable("Matrix", [(lstm_in if k == 0 else state_size) + state_size, 4 * state_size], rn)
+                            V[f"lstm_b{k}"] = st.get_variable("Bias", [4 * state_size], zeros)
             V["out_w"] = st.get_variable("output_fc_w", [state_size, fc], rn)
             V["out_b"] = st.get_variable("output_fc_bias", [1, fc], zeros)
             for i in range(4):
@@ -132,10 +149,16 @@ class RecurrentDCGAN(object):
         T, B, V = self.T, self.B, self.V
         x = X
         for i in range(4):
-            x = ops.conv2d_v(x, V[f"g_conv{i}"], bn=self.bn, act="relu", groups=T)
-        enc = x.reshape(T, B, self.fc).float()
-        h = _LSTM.apply(enc, ops._wtensor(V["lstm_m"], ops._wants_grad(V["lstm_m"])),
-                        ops._wtensor(V["lstm_b"], ops._wants_grad(V["lstm_b"])), V["lstm_m"], V["lstm_b"], self.H)
+            x = ops.conv2d_v(x, V[f"d_conv{i}" if self.shared_conv else f"g_conv{i}"], bn=self.bn, act="relu", groups=T)
+        if self.shared_conv:      # the encoder's fc layer is the discriminator's (…shared_conv_and_drop_out.py:213-215)
+            enc = ops.linear_v(x.reshape(T * B, self.fc), V["d_fc_w"], V["d_fc_b"], out_dtype=torch.float32).reshape(T, B, self.H)
+        else:
+            enc = x.reshape(T, B, self.fc).float()
+        h = enc
+        for k in range(self.L):
+            h = self._lstm(h, V[f"lstm_m{k}"], V[f"lstm_b{k}"])
+            if self.keep < 1.0 and not ops._is_meta(h):
+                h = h * self._mask(k)
         s16 = self.S // 16
         d = ops.linear_v(h.reshape(T * B, self.H), V["out_w"], V["out_b"], out_dtype=torch.float32).reshape(T * B, s16, s16, 512)
         for i in range(4):
@@ -146,12 +169,24 @@ class RecurrentDCGAN(object):
                                out_dtype=torch.float32 if last else None)
         return d
 
+    def _lstm(self, x, mvar, bvar):
+        if ops._is_meta(x):
+            return torch.empty((x.shape[0], x.shape[1], self.H), dtype=torch.float32, device="meta")
+        return _LSTM.apply(x.contiguous(), ops._wtensor(mvar, ops._wants_grad(mvar)), ops._wtensor(bvar, ops._wants_grad(bvar)), mvar, bvar, self.H)
+
+    def _mask(self, k):
+        """DropoutWrapper's draw for layer k: [T, B, H] of {0, 1/keep} (tf.nn.dropout: floor(keep + uniform) / keep)."""
+        if self.masks is not None:
+            return torch.as_tensor(self.masks[k]).to(self.store.device, torch.float32)
+        u = torch.rand((self.T, self.B, self.H), device=self.store.device)
+        return torch.floor(self.keep + u) / self.keep
+
     def discriminator(self, frames):
         """frames: [T*B, S, S, 3] -> logits [B, 1]."""
         T, B, V = self.T, self.B, self.V
         x = frames
         for i in range(4):
-            x = ops.conv2d_v(x, V[f"d_conv{i}"], bn=self.bn, act="lrelu", groups=T)
+            x = ops.conv2d_v(x, V[f"d_conv{i}"], bn=self.bn, act="relu" if self.shared_conv else "lrelu", groups=T)
         per = ops.linear_v(x.reshape(T * B, self.fc), V["d_fc_w"], V["d_fc_b"], out_dtype=torch.float32)      # [T*B, 100]
         cat = per.reshape(T, B, self.H).permute(1, 0, 2).reshape(B, T * self.H)                              # tf.concat(1, series)
         return ops.linear_v(cat, V["d_final_w"], V["d_final_b"])
@@ -177,7 +212,8 @@ class RecurrentDCGAN(object):
         B = self.B
         with ops.trainable(var_list), ops.overlap_wgrad():
             if which == "d":
-                with torch.no_grad():
+                # shared encoder: d_loss reaches the discriminator's filters through the generator as well
+                with torch.enable_grad() if self.shared_conv else torch.no_grad():
                     fake = self.generator(X)
                 lf, lr = self.discriminator(fake), self.discriminator(Y)
                 loss_f = ops.sigmoid_cross_entropy_loss(lf, target=0.0)

@@ -434,18 +434,30 @@ class RecurrentDCGAN(_Graph):
     CH = [3, 64, 128, 256, 512]
 
     def __init__(self, batch_size=40, video_length=16, image_dimension=64, state_size=100,
-                 seed=7, dtype=torch.float32, lr=2e-4, beta1=0.5):
+                 seed=7, dtype=torch.float32, lr=2e-4, beta1=0.5, num_layers=1, shared_conv=False, output_keep_prob=1.0):
+        """num_layers > 1: multi-layer_recurrent_DCGAN.py:22,206-207 (MultiRNNCell of separate BasicLSTMCells).
+        shared_conv: multi-layer_recurrent_DCGAN_with_shared_conv_and_drop_out.py:169-180,207,213-215,280 -- the encoder
+        runs the DISCRIMINATOR's conv filters and its d_fc (LSTM input = state_size), the discriminator uses ReLU.
+        output_keep_prob < 1: DropoutWrapper on every cell's output (:219), masks supplied by the caller."""
         super().__init__(dtype)
         self.B, self.Tn, self.S, self.H = batch_size, video_length, image_dimension, state_size
+        self.L, self.shared_conv, self.keep = num_layers, shared_conv, output_keep_prob
         rs = np.random.RandomState(seed)
         rn = lambda shape: torch.tensor(T.random_normal(rs, shape), dtype=dtype)
         V, CH = self.vars, self.CH
         s16 = image_dimension // 16
         self.fc = fc = s16 * s16 * 512
-        for i in range(4):  # recurrent_DCGAN.py:177-180
-            V[f"generator/conv_f{i+1}"] = rn((5, 5, CH[i], CH[i + 1]))
-        V["generator/lstm/Matrix"] = rn((fc + state_size, 4 * state_size))
-        V["generator/lstm/Bias"] = torch.zeros(4 * state_size, dtype=dtype)
+        if not shared_conv:
+            for i in range(4):  # recurrent_DCGAN.py:177-180
+                V[f"generator/conv_f{i+1}"] = rn((5, 5, CH[i], CH[i + 1]))
+        lstm_in = state_size if shared_conv else fc
+        if num_layers == 1:
+            V["generator/lstm/Matrix"] = rn((lstm_in + state_size, 4 * state_size))
+            V["generator/lstm/Bias"] = torch.zeros(4 * state_size, dtype=dtype)
+        else:
+            for k in range(num_layers):
+                V[f"generator/lstm/Cell{k}/Matrix"] = rn(((lstm_in if k == 0 else state_size) + state_size, 4 * state_size))
+                V[f"generator/lstm/Cell{k}/Bias"] = torch.zeros(4 * state_size, dtype=dtype)
         V["generator/output_fc_w"] = rn((state_size, fc))
         V["generator/output_fc_bias"] = torch.zeros(1, fc, dtype=dtype)
         for i in range(4):  # recurrent_DCGAN.py:205-208: [kh,kw,Cout,Cin]
@@ -460,6 +472,13 @@ class RecurrentDCGAN(_Graph):
         self.d_vars = [k for k in V if k.startswith("discriminator")]
         self.g_optim = T.TFAdam({k: V[k] for k in self.g_vars}, lr, beta1)
         self.d_optim = T.TFAdam({k: V[k] for k in self.d_vars}, lr, beta1)
+        self.masks = None      # [L, T, B, H] of {0, 1/keep}: the DropoutWrapper draws, fixed by the caller for parity
+
+    def _cell(self, k):
+        V = self.vars
+        if self.L == 1:
+            return V["generator/lstm/Matrix"], V["generator/lstm/Bias"]
+        return V[f"generator/lstm/Cell{k}/Matrix"], V[f"generator/lstm/Cell{k}/Bias"]
 
     def generator(self, X):
         """X: list of T tensors [B,S,S,3] in [0,1).  recurrent_DCGAN.py:170-225."""
@@ -468,15 +487,23 @@ class RecurrentDCGAN(_Graph):
         enc = []
         for x in X:
             for i in range(4):
-                x = torch.relu(T.batch_norm_plain(T.conv2d(x, V[f"generator/conv_f{i+1}"])))
-            enc.append(x.reshape(B, self.fc))
-        c = torch.zeros(B, self.H, dtype=self.dtype)
-        h = torch.zeros(B, self.H, dtype=self.dtype)
+                w = V[f"discriminator/d_conv_f{i+1}"] if self.shared_conv else V[f"generator/conv_f{i+1}"]
+                x = torch.relu(T.batch_norm_plain(T.conv2d(x, w)))
+            x = x.reshape(B, self.fc)
+            if self.shared_conv:
+                x = x @ V["discriminator/d_fc_w"] + V["discriminator/d_fc_bias"]
+            enc.append(x)
+        state = [(torch.zeros(B, self.H, dtype=self.dtype), torch.zeros(B, self.H, dtype=self.dtype)) for _ in range(self.L)]
         outs = []
         for t, e in enumerate(enc):
-            c, h = T.basic_lstm_cell(e, c, h, V["generator/lstm/Matrix"], V["generator/lstm/Bias"])
-            self._rec(f"lstm_h{t}", h)
-            d = (h @ V["generator/output_fc_w"] + V["generator/output_fc_bias"]).reshape(B, s16, s16, 512)
+            inp = e
+            for k in range(self.L):      # MultiRNNCell: layer k's (dropped) output feeds layer k+1; states stay undropped
+                m, b = self._cell(k)
+                c, h = T.basic_lstm_cell(inp, state[k][0], state[k][1], m, b)
+                state[k] = (c, h)
+                inp = h if self.keep >= 1.0 else h * self.masks[k, t].to(self.dtype)
+            self._rec(f"lstm_h{t}", inp)
+            d = (inp @ V["generator/output_fc_w"] + V["generator/output_fc_bias"]).reshape(B, s16, s16, 512)
             for i in range(4):
                 d = torch.relu(T.batch_norm_plain(d))
                 sz = s16 * 2 ** (i + 1)
@@ -490,7 +517,8 @@ class RecurrentDCGAN(_Graph):
         per = []
         for x in frames:
             for i in range(4):
-                x = T.lrelu(T.batch_norm_plain(T.conv2d(x, V[f"discriminator/d_conv_f{i+1}"])))
+                x = T.batch_norm_plain(T.conv2d(x, V[f"discriminator/d_conv_f{i+1}"]))
+                x = torch.relu(x) if self.shared_conv else T.lrelu(x)
             per.append(x.reshape(B, self.fc) @ V["discriminator/d_fc_w"] + V["discriminator/d_fc_bias"])
         return torch.cat(per, 1) @ V["discriminator/d_final_fc_w"] + V["discriminator/d_final_fc_bias"]
 

@@ -130,8 +130,31 @@ def latent_fixture():
     np.savez_compressed(os.path.join(OUT, "latent_tiny.npz"), **d)
 
 
+RECURRENT_VARIANTS = {"multi": dict(num_layers=3), "shared_dropout": dict(num_layers=3, shared_conv=True, output_keep_prob=0.8)}
+
+
+def recurrent_variant_masks():
+    """The DropoutWrapper draws used by the fixture and the parity tests: [layers, T, B, H] of {0, 1/0.8}."""
+    return np.floor(0.8 + np.random.RandomState(106).uniform(size=(3, 3, 2, 100))) / 0.8
+
+
+def recurrent_variants_fixture():
+    """multi-layer_recurrent_DCGAN.py and ..._with_shared_conv_and_drop_out.py at batch 2, 3 frames: one train step."""
+    inp = np.random.RandomState(104).randint(0, 256, (2, 4, 64, 64, 3)).astype(np.int32)
+    d = {}
+    for tag, kw in RECURRENT_VARIANTS.items():
+        m = RecurrentDCGAN(batch_size=2, video_length=3, seed=7, dtype=f64, **kw)
+        m.masks = torch.tensor(recurrent_variant_masks())
+        o = m.train_step(torch.tensor(inp))
+        d[tag + "/losses"] = np.array([o["d_loss"], o["g_loss"]])
+        d[tag + "/final/generator/lstm/Cell1/Bias"] = m.vars["generator/lstm/Cell1/Bias"].numpy()
+        d[tag + "/final/discriminator/d_fc_bias"] = m.vars["discriminator/d_fc_bias"].numpy()
+    np.savez_compressed(os.path.join(OUT, "recurrent_variants.npz"), **d)
+
+
 if __name__ == "__main__":
     ops_fixture()
+    recurrent_variants_fixture()
     latent_fixture()
     dcgan_fixture()
     vid_fixture()

@@ -215,3 +215,30 @@ def test_latent_cli_contract_and_clip_reader(tmp_path):
     opts = flags.parse("z_space_finder", ["--synthetic", "5", "--video_batch_size", "2", "--vid_length", "3", "--image_size", "8"])
     batches = list(clip_batches(opts))
     assert [len(n) for n, _ in batches] == [2, 2, 1] and np.shape(batches[0][1]) == (2, 3, 8, 8, 3)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(num_layers=3), dict(num_layers=3, shared_conv=True, output_keep_prob=0.8)])
+def test_recurrent_variants_names_and_shapes(cpu_store, kw):
+    """recurrent_DCGAN.py and its two variants (multi-layer_recurrent_DCGAN.py, ..._with_shared_conv_and_drop_out.py):
+    variable inventory against the oracle's, and the graph traced on meta tensors (shapes only, no kernels)."""
+    from gifgan.recurrent_dcgan import RecurrentDCGAN
+    from oracle.models import RecurrentDCGAN as OracleRec
+    m = RecurrentDCGAN(batch_size=2, video_length=3, **kw)
+    ora = OracleRec(batch_size=2, video_length=3, **kw)
+    assert set(m.store.vars) == set(ora.vars)
+    for k, v in ora.vars.items():
+        assert tuple(m.store.vars[k].shape) == tuple(v.shape), k
+    assert [v.name for v in m.g_vars] == ora.g_vars and [v.name for v in m.d_vars] == ora.d_vars
+    if kw.get("shared_conv"):
+        assert not any("/conv_f" in v.name for v in m.g_vars)                    # the encoder's filters are the discriminator's
+        assert tuple(m.store.vars["generator/lstm/Cell0/Matrix"].shape) == (200, 400)
+    elif kw.get("num_layers"):
+        assert tuple(m.store.vars["generator/lstm/Cell0/Matrix"].shape) == (8292, 400)
+        assert tuple(m.store.vars["generator/lstm/Cell2/Matrix"].shape) == (200, 400)
+    X = torch.empty((3 * 2, 64, 64, 3), dtype=torch.float32, device="meta")
+    fake = m.generator(X)
+    assert tuple(fake.shape) == (6, 64, 64, 3) and tuple(m.discriminator(fake).shape) == (2, 1)
+    if kw.get("output_keep_prob"):
+        m.store.device = torch.device("cpu")
+        mk = m._mask(1)
+        assert tuple(mk.shape) == (3, 2, 100) and set(np.unique(mk.numpy()).round(4)) <= {0.0, 1.25}
