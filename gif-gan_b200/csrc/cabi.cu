@@ -187,7 +187,9 @@ extern "C" int gg_linear_wgrad(const void* x, int32_t x_dt, const void* dy, int3
                                int32_t in_dim, int32_t out_dim, void* stream) {
   GG_REQUIRE(x && dy && rows > 0 && in_dim > 0 && out_dim > 0, GG_ERR_INVALID, "linear_wgrad: bad argument");
   int rc = GG_OK;
-  if (dmatrix && out_dim > 4 && thin_linear_ok(rows, in_dim, out_dim))          // one pass over dy gives dW and db
+  // one pass over dy gives dW and db; the kernel stages 32 input features of EVERY row in shared memory (128 B per row on
+  // top of 33 KB), so above 960 rows (e.g. 64 clips x 16 frames through gvideo_0) the generic kernel takes over
+  if (dmatrix && out_dim > 4 && rows <= 960 && thin_linear_ok(rows, in_dim, out_dim))
     return thin_linear_wgrad(x, x_dt, dy, dy_dt, dmatrix, dbias, rows, in_dim, out_dim, (cudaStream_t)stream);
   if (dmatrix) {
     if (out_dim <= 4) rc = skinny_linear_wgrad(x, x_dt, dy, dy_dt, dmatrix, rows, in_dim, out_dim, (cudaStream_t)stream);
