@@ -1,6 +1,8 @@
 """Image inversion entry point (the role of models/recurrent_z/discriminator_activation_optimizer.py; options:
 flags.TABLES["activation_optimizer"]): search the latents of a num_rows x num_cols grid of target images (given images,
 or the first frames of given clips, repeated to fill the grid) and write target.png, train_<i>.png and final.png.
+With --vid_length N it is discriminator_activation_optimizer_video.py: all N frames of every input clip are searched at
+once (batch = clips x N, no warm start between frames; the grid has one row per clip).
 The interactive GUI, the progress video and the latent-path playback of the reference are display features outside
 the compute path and are not carried over."""
 import os
@@ -11,6 +13,21 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gifgan import flags, utils  # noqa: E402
 from gifgan.latent_search import load_dcgan, read_video_frames, search_from_options  # noqa: E402
+
+
+def load_clip_targets(opts):
+    """discriminator_activation_optimizer_video.py:64-103: [clips * vid_length, s, s, c], clip-major."""
+    if opts.synthetic:
+        return np.random.RandomState(109).uniform(-1, 1, (opts.synthetic * opts.vid_length, opts.image_size, opts.image_size, opts.c_dim)).astype(np.float32)
+    clips = []
+    for v in opts.input_videos:
+        frames = read_video_frames(v, opts.image_size, opts.vid_length, opts.frame_skip)
+        if frames is None:
+            raise SystemExit("Video %s not long enough!" % v)
+        clips.append(frames)
+    if not clips:
+        raise SystemExit("no targets: give --input_videos or --synthetic n")
+    return np.array(clips, dtype=np.float32).reshape(-1, opts.image_size, opts.image_size, opts.c_dim)
 
 
 def load_targets(opts, batch):
@@ -33,10 +50,16 @@ def main(argv=None):
     if not opts.sample_dir:
         raise SystemExit("--sample_dir is required")
     os.makedirs(opts.sample_dir, exist_ok=True)
-    batch = opts.num_rows * opts.num_cols
-    search = search_from_options(load_dcgan(opts, batch), opts)
-    targets = load_targets(opts, batch)
-    grid = [opts.num_rows, opts.num_cols]
+    if opts.vid_length > 0:
+        targets = load_clip_targets(opts)
+        batch = len(targets)
+        grid = [batch // opts.vid_length, opts.vid_length]
+        search = search_from_options(load_dcgan(opts, batch), opts)
+    else:
+        batch = opts.num_rows * opts.num_cols
+        search = search_from_options(load_dcgan(opts, batch), opts)
+        targets = load_targets(opts, batch)
+        grid = [opts.num_rows, opts.num_cols]
     utils.save_images(targets, grid, os.path.join(opts.sample_dir, "target.png"))
 
     def on_step(i, loss, srch):

@@ -126,6 +126,8 @@ TABLES = {
         ("sample_frequency", "i", 100, "steps between sample grids (0: none)"),
         ("lr_decay_frequency", "i", 0, "steps between learning-rate decays (0: never)"),
         ("lr_decay_amount", "f", 0.9, "decay factor"),
+        ("vid_length", "i", 0, "> 0: discriminator_activation_optimizer_video.py -- search every `frame_skip`-th frame of the input clips (batch = clips x vid_length, one grid row per clip)"),
+        ("frame_skip", "i", 2, "frame step when vid_length > 0"),
     ] + _LATENT_WEIGHTS + _LATENT_DCGAN + _OURS,
 }
 

@@ -83,6 +83,12 @@ class LatentSearch(object):
         with torch.no_grad():
             return self.dcgan.generator(self.z.detach(), train=self.train)
 
+    def assign(self, z):
+        """sess.run(dcgan.z.assign(z)): overwrite the latents (the Adam slots keep running, as in the reference's
+        discriminator_activation_optimizer_video.py:228-231, 243-248, which copies frame 0's latents over the later frames)."""
+        with torch.no_grad():
+            self.z.copy_(torch.as_tensor(np.asarray(z, dtype=np.float32)).reshape(self.z.shape))
+
     def lr_t(self, lr):
         return lr * float(np.sqrt(1.0 - self.beta2 ** self.t)) / (1.0 - self.beta1 ** self.t)
 

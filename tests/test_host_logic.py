@@ -242,3 +242,32 @@ def test_recurrent_variants_names_and_shapes(cpu_store, kw):
         m.store.device = torch.device("cpu")
         mk = m._mask(1)
         assert tuple(mk.shape) == (3, 2, 100) and set(np.unique(mk.numpy()).round(4)) <= {0.0, 1.25}
+
+
+def test_activation_optimizer_clip_mode_targets(tmp_path):
+    """--vid_length N (discriminator_activation_optimizer_video.py:64-103): every frame_skip-th frame of every clip,
+    clip-major, one grid row per clip."""
+    import cv2
+    from gifgan import flags
+    from gifgan.discriminator_activation_optimizer import load_clip_targets
+    paths = []
+    for c in range(2):
+        path = str(tmp_path / ("c%d.avi" % c))
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (32, 32))
+        if not wr.isOpened():
+            pytest.skip("no MJPG writer in this OpenCV build")
+        for i in range(7):
+            wr.write(np.full((32, 32, 3), 20 * i + 100 * c, np.uint8))
+        wr.release()
+        paths.append(path)
+    opts = flags.parse("activation_optimizer", ["--vid_length", "3", "--image_size", "16", "--input_videos"] + paths)
+    assert opts.frame_skip == 2
+    t = load_clip_targets(opts)
+    assert t.shape == (6, 16, 16, 3) and t.dtype == np.float32
+    want = [(20 * i + 100 * c) / 127.5 - 1 for c in range(2) for i in (1, 3, 5)]
+    assert np.allclose(t.mean(axis=(1, 2, 3)), want, atol=0.05)
+    opts = flags.parse("activation_optimizer", ["--vid_length", "4", "--image_size", "16", "--input_videos"] + paths)
+    with pytest.raises(SystemExit):
+        load_clip_targets(opts)                                   # 8 frames needed, 7 in the file
+    opts = flags.parse("activation_optimizer", ["--vid_length", "4", "--synthetic", "3", "--image_size", "8"])
+    assert load_clip_targets(opts).shape == (12, 8, 8, 3)
