@@ -1,10 +1,11 @@
 """GPU parity tests of the two recurrent_DCGAN variants (multi-layer_recurrent_DCGAN.py and
-..._with_shared_conv_and_drop_out.py) against the oracle and the committed golden trace.
+..._with_shared_conv_and_drop_out.py) against the oracle and the committed golden trace, and the 100-step loss
+comparison of the image GAN.
 
 NOT YET RUN ON HARDWARE: the variants were written after round 1's GPU budget was spent (they compose kernels that are
 covered elsewhere: the LSTM step, thin / generic linears, the conv stack, batch norm with per-frame groups).  They are
 skipped unless GG_UNVALIDATED=1 so that the default suite only holds tests that have passed on a B200; run
-    GG_UNVALIDATED=1 python -m pytest tests/test_gpu_zz_recurrent_variants.py -m gpu
+    GG_UNVALIDATED=1 python -m pytest tests/test_gpu_zz_unvalidated.py -m gpu
 first thing on the next GPU visit and drop the gate."""
 import os
 import sys
@@ -71,3 +72,28 @@ def test_shared_encoder_bf16_step_runs():
     out = m.train_step(torch.tensor(inp))
     assert np.isfinite(out["d_loss"]) and np.isfinite(out["g_loss"])
     assert not torch.equal(m.store.vars["discriminator/d_conv_f2"].data, w0)
+
+
+def test_losses_follow_the_oracle_over_100_steps_fp32():
+    """north_star: "matching loss over 100 steps".  A GAN amplifies rounding differences (tests/test_oracle_models.py::
+    test_hundred_step_divergence_floor: float32 vs float64 oracle, or a 1e-7 weight perturbation, drift apart by up to
+    0.6 % of the loss over 100 steps at this configuration), so the criterion is 3 % on every one of the 100 steps."""
+    from gifgan import ops
+    from gifgan.model import DCGAN
+    from oracle.models import DCGAN as OracleDCGAN
+    B, size, w = 8, 16, 8
+    ora = OracleDCGAN(batch_size=B, output_size=size, gf_dim=w, df_dim=w, seed=7, dtype=torch.float32)
+    ops.set_precision("fp32")
+    ops.reset_default_store(device="cuda")
+    m = DCGAN(None, batch_size=B, output_size=size, gf_dim=w, df_dim=w)
+    m.store.load_state_dict(ora.state_dict())
+    worst = 0.0
+    for s in range(100):
+        img = np.random.RandomState(102 + s).uniform(-1, 1, (B, size, size, 3)).astype(np.float32)
+        z = np.random.RandomState(1000 + s).uniform(-1, 1, (B, 100)).astype(np.float32)
+        got = m.train_step(img, z, use_graph=True)
+        want = ora.train_step(torch.tensor(img), torch.tensor(z))
+        for k in ("d_loss", "g_loss"):
+            worst = max(worst, abs(got[k] - want[k]) / max(1.0, abs(want[k])))
+            assert abs(got[k] - want[k]) < 3e-2 * max(1.0, abs(want[k])), (s, k, got[k], want[k])
+    print("worst relative loss difference over 100 steps: %.2e" % worst)
