@@ -111,6 +111,12 @@ class Prefetcher(object):
         self._stop.set()
         self._pool.shutdown(wait=False, cancel_futures=True)
 
+    def __del__(self):                       # a consumer that walks away mid-epoch must not leave the producer spinning
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def __enter__(self):
         return self
 
