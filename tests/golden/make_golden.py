@@ -152,8 +152,22 @@ def recurrent_variants_fixture():
     np.savez_compressed(os.path.join(OUT, "recurrent_variants.npz"), **d)
 
 
+def hundred_step_fixture():
+    """100-step loss trace (north_star: "matching loss over 100 steps") of the tiny DCGAN (batch 8, 16x16, gf=df=8) in
+    float64, fresh seeded images and z every step: [100, 2] = (d_loss, g_loss of the second G update)."""
+    m = DCGAN(batch_size=8, output_size=16, gf_dim=8, df_dim=8, seed=7, dtype=f64)
+    out = []
+    for s in range(100):
+        img = np.random.RandomState(102 + s).uniform(-1, 1, (8, 16, 16, 3))
+        z = np.random.RandomState(1000 + s).uniform(-1, 1, (8, 100))
+        o = m.train_step(t(img), t(z))
+        out.append([o["d_loss"], o["g_loss"]])
+    np.savez_compressed(os.path.join(OUT, "dcgan_100steps.npz"), losses=np.array(out))
+
+
 if __name__ == "__main__":
     ops_fixture()
+    hundred_step_fixture()
     recurrent_variants_fixture()
     latent_fixture()
     dcgan_fixture()

@@ -87,6 +87,7 @@ def test_losses_follow_the_oracle_over_100_steps_fp32():
     ops.reset_default_store(device="cuda")
     m = DCGAN(None, batch_size=B, output_size=size, gf_dim=w, df_dim=w)
     m.store.load_state_dict(ora.state_dict())
+    trace = np.load(os.path.join(GOLD, "dcgan_100steps.npz"))["losses"]          # float64 oracle, committed
     worst = 0.0
     for s in range(100):
         img = np.random.RandomState(102 + s).uniform(-1, 1, (B, size, size, 3)).astype(np.float32)
@@ -96,4 +97,5 @@ def test_losses_follow_the_oracle_over_100_steps_fp32():
         for k in ("d_loss", "g_loss"):
             worst = max(worst, abs(got[k] - want[k]) / max(1.0, abs(want[k])))
             assert abs(got[k] - want[k]) < 3e-2 * max(1.0, abs(want[k])), (s, k, got[k], want[k])
+        assert abs(got["d_loss"] - trace[s, 0]) < 3e-2 * max(1.0, abs(trace[s, 0])) and abs(got["g_loss"] - trace[s, 1]) < 3e-2 * max(1.0, abs(trace[s, 1])), s
     print("worst relative loss difference over 100 steps: %.2e" % worst)

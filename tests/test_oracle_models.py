@@ -110,6 +110,7 @@ def test_hundred_step_divergence_floor():
             out.append((o["d_loss"], o["g_loss"]))
         return np.array(out)
     a, b, c = run(torch.float64), run(torch.float32), run(torch.float64, 1e-7)
+    np.testing.assert_allclose(a, np.load(os.path.join(GOLD, "dcgan_100steps.npz"))["losses"], rtol=1e-6)     # committed trace
     rel_f32 = (np.abs(b - a) / np.maximum(1.0, np.abs(a))).max()
     rel_nudge = (np.abs(c - a) / np.maximum(1.0, np.abs(a))).max()
     assert np.abs(b[:3] - a[:3]).max() < 1e-5                       # identical at first ...
