@@ -14,7 +14,10 @@ import torch.nn.functional as F
 
 from oracle import tf_ops as T
 
-tf_pad = pytest.importorskip("transformers.models.mobilenet_v2.modeling_mobilenet_v2").apply_tf_padding
+
+def _tf_pad():
+    """Imported inside the test: collecting this file (e.g. for `-m gpu` runs) must not import transformers."""
+    return pytest.importorskip("transformers.models.mobilenet_v2.modeling_mobilenet_v2").apply_tf_padding
 
 
 class _Conv:                      # the attributes apply_tf_padding reads from an nn.Conv2d
@@ -25,6 +28,7 @@ class _Conv:                      # the attributes apply_tf_padding reads from a
 @pytest.mark.parametrize("k,s", [(5, 2), (3, 2), (4, 2), (3, 1), (5, 3)])
 def test_same_padding_against_the_transformers_port(k, s):
     from gifgan.ops import same_pad
+    tf_pad = _tf_pad()
     rs = np.random.RandomState(k * 10 + s)
     for n in (64, 32, 28, 16, 14, 8, 7, 5, 3, 10):
         x = torch.tensor(rs.randn(2, n, n + 1, 3))                       # NHWC, non-square
