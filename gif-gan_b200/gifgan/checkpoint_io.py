@@ -10,7 +10,7 @@ published format -- not against a file TensorFlow wrote:
 
   * `.index` is a LevelDB-format table (tensorflow/core/lib/io/table*.cc): data blocks of prefix-compressed entries
     (varint32 shared, non_shared, value_len; key suffix; value) with a restart array, each block followed by a 1-byte
-    compression tag (0 = none; the bundle writer does not compress) and a masked crc32c; a meta-index block; an index
+    compression tag (0 = none, what the bundle writer emits; 1 = snappy, decoded here too) and a masked crc32c; a meta-index block; an index
     block (separator key -> BlockHandle{offset, size} as varint64s); a 48-byte footer (two handles padded to 40 bytes +
     magic 0xdb4775248b80fb57).
   * key "" -> BundleHeaderProto{num_shards=1, endianness=2, version=3}; every other key is a variable name ->
@@ -175,18 +175,58 @@ def _parse_block(buf):
     return out
 
 
+def snappy_decompress(buf: bytes) -> bytes:
+    """Raw snappy block format (the table format's compression tag 1): varint length, then literals (tag & 3 == 0) and
+    copies with 1-, 2- or 4-byte offsets (tags 1, 2, 3).  The bundle writer does not compress; tables written with the
+    LevelDB default do."""
+    n, pos = _read_varint(buf, 0)
+    out = bytearray()
+    while pos < len(buf):
+        tag = buf[pos]
+        pos += 1
+        kind = tag & 3
+        if kind == 0:
+            ln = tag >> 2
+            if ln >= 60:
+                extra = ln - 59
+                ln = int.from_bytes(buf[pos:pos + extra], "little")
+                pos += extra
+            ln += 1
+            out += buf[pos:pos + ln]
+            pos += ln
+            continue
+        if kind == 1:
+            ln, off = ((tag >> 2) & 7) + 4, ((tag >> 5) << 8) | buf[pos]
+            pos += 1
+        elif kind == 2:
+            ln, off = (tag >> 2) + 1, int.from_bytes(buf[pos:pos + 2], "little")
+            pos += 2
+        else:
+            ln, off = (tag >> 2) + 1, int.from_bytes(buf[pos:pos + 4], "little")
+            pos += 4
+        if off == 0 or off > len(out):
+            raise ValueError("corrupt snappy block")
+        for _ in range(ln):                  # byte-wise: a copy may overlap its own output (run-length encoding)
+            out.append(out[-off])
+    if len(out) != n:
+        raise ValueError("snappy block decompressed to %d bytes, header says %d" % (len(out), n))
+    return bytes(out)
+
+
 def _handle(offset, size) -> bytes:
     return _varint(offset) + _varint(size)
 
 
 def _read_block(buf, offset, size, verify):
     body, tag = buf[offset:offset + size], buf[offset + size]
-    if tag != 0:
-        raise ValueError("compressed table block (tag %d): this reader handles the uncompressed blocks the bundle writer emits" % tag)
     if verify:
         want = struct.unpack_from("<I", buf, offset + size + 1)[0]
         if mask_crc(crc32c(bytes(buf[offset:offset + size + 1]))) != want:
             raise ValueError("table block checksum mismatch at offset %d" % offset)
+    if tag == 1:
+        body = snappy_decompress(bytes(body))
+    elif tag != 0:
+        raise ValueError("table block with unknown compression tag %d" % tag)
     return _parse_block(body)
 
 

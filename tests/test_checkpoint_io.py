@@ -142,3 +142,39 @@ def test_model_load_paths_accept_tf_checkpoints(tmp_path):
     # torch payloads still load
     a.save(str(tmp_path / "torch"), 9)
     assert b.load(str(tmp_path / "torch"))
+
+
+def test_snappy_blocks_in_a_table(tmp_path):
+    """Tables written with the LevelDB default compress their blocks (tag 1); the raw snappy format: literals, copies
+    with 1- / 2-byte offsets, overlapping copies (run-length), long literals."""
+    from gifgan import checkpoint_io as C
+    # hand-assembled streams: "abcabcabcabc" = literal "abc" + copy(offset 3, length 9, 2-byte-offset form)
+    assert C.snappy_decompress(bytes([12, (3 - 1) << 2]) + b"abc" + bytes([((9 - 1) << 2) | 2, 3, 0])) == b"abcabcabcabc"
+    # 1-byte-offset copy: length 4..11 in bits 2-4, offset high bits in 5-7:  "xyzw" + copy(offset 4, length 7)
+    assert C.snappy_decompress(bytes([11, (4 - 1) << 2]) + b"xyzw" + bytes([((7 - 4) << 2) | 1 | (0 << 5), 4])) == b"xyzwxyzwxyz"
+    # literal of 70 bytes: length-1 = 69 >= 60 -> tag 60<<2, one extra length byte
+    lit = bytes(range(70))
+    assert C.snappy_decompress(bytes([70, 60 << 2, 69]) + lit) == lit
+    with pytest.raises(ValueError):
+        C.snappy_decompress(bytes([5, (3 - 1) << 2]) + b"abc")                     # declared 5 bytes, holds 3
+
+    def literal_only(raw):              # a valid (if pointless) snappy stream: everything as literals of <= 60 bytes
+        out = bytearray(C._varint(len(raw)))
+        for i in range(0, len(raw), 60):
+            chunk = raw[i:i + 60]
+            out += bytes([(len(chunk) - 1) << 2]) + chunk
+        return bytes(out)
+
+    entries = [(b"", b"hdr")] + [(("var_%03d/w" % i).encode(), bytes([i]) * (i % 40 + 1)) for i in range(80)]
+    body = literal_only(C._block(entries))
+    index_body = C._block([(entries[-1][0], C._handle(0, len(body)))])
+    meta = C._block([])
+    out = bytearray()
+    for blk, tag in ((body, 1), (meta, 0), (index_body, 0)):
+        out += blk + bytes([tag]) + struct.pack("<I", C.mask_crc(C.crc32c(blk + bytes([tag]))))
+    moff, ioff = len(body) + 5, len(body) + 5 + len(meta) + 5
+    foot = C._handle(moff, len(meta)) + C._handle(ioff, len(index_body))
+    out += foot + b"\x00" * (40 - len(foot)) + struct.pack("<Q", C.MAGIC)
+    path = str(tmp_path / "snappy.index")
+    open(path, "wb").write(bytes(out))
+    assert C.read_table(path) == entries
