@@ -340,6 +340,102 @@ def write_tf_bundle(prefix, tensors):
     write_table(prefix + ".index", entries)
 
 
+# ---- V1 checkpoints (tf.train.Saver(write_version=1): what utils/downgrade_tf_checkpoint.py of the reference produces) ----
+# One table file (blocks usually snappy-compressed).  Key "" -> SavedTensorSlices{meta = 1: SavedTensorSliceMeta{tensor = 1:
+# SavedSliceMeta{name = 1, shape = 2, type = 3, slice = 4}}}; every other key (an order-preserving encoding of name + slice
+# that is not needed to read the file) -> SavedTensorSlices{data = 2: SavedSlice{name = 1, slice = 2, data = 3: TensorProto}}
+# with the values in the TensorProto's typed repeated field (float_val = 5, double_val = 6, int_val = 7, int64_val = 10,
+# bool_val = 11; packed) or in tensor_content = 4.
+_V1_VAL_FIELD = {1: (5, "<f4"), 2: (6, "<f8"), 3: (7, None), 9: (10, None), 10: (11, None)}
+
+
+def _tensor_proto_values(buf, dtype):
+    field, fixed = _V1_VAL_FIELD[dtype]
+    vals, content = [], None
+    for fno, wt, v in _fields(buf):
+        if fno == 4 and wt == 2:
+            content = v
+        elif fno == field:
+            if wt == 2:                                             # packed
+                if fixed:
+                    vals.append(np.frombuffer(v, dtype=fixed))
+                else:
+                    pos, out = 0, []
+                    while pos < len(v):
+                        x, pos = _read_varint(v, pos)
+                        out.append(x - (1 << 64) if x >> 63 else x)
+                    vals.append(np.array(out, dtype=np.int64))
+            elif wt == 5:
+                vals.append(np.frombuffer(struct.pack("<I", v), dtype="<f4"))
+            elif wt == 1:
+                vals.append(np.frombuffer(struct.pack("<Q", v), dtype="<f8"))
+            else:
+                vals.append(np.array([v - (1 << 64) if v >> 63 else v], dtype=np.int64))
+    if content is not None:
+        return np.frombuffer(content, dtype=np.dtype(DT[dtype]).newbyteorder("<"))
+    return np.concatenate(vals) if vals else np.zeros(0, dtype=DT[dtype])
+
+
+def read_tf_v1_checkpoint(path):
+    """A V1 checkpoint file (e.g. .../DCGAN.model-1502 itself, no .index) -> {variable name: numpy array}.
+    Variables saved as several slices (partitioned variables) are not supported."""
+    entries = read_table(path, verify=True)
+    if not entries or entries[0][0] != b"":
+        raise ValueError("%s: no SavedTensorSliceMeta entry" % path)
+    shapes = {}
+    for fno, _, v in _fields(entries[0][1]):
+        if fno != 1:
+            continue
+        for f2, _, t in _fields(v):
+            if f2 != 1:
+                continue
+            name, shape, dtype, nslices = None, (), 0, 0
+            for f3, _, x in _fields(t):
+                if f3 == 1:
+                    name = x.decode()
+                elif f3 == 2:
+                    shape = _parse_shape(x)
+                elif f3 == 3:
+                    dtype = x
+                elif f3 == 4:
+                    nslices += 1
+            if nslices > 1:
+                raise ValueError("variable %s is stored as %d slices: not supported" % (name, nslices))
+            shapes[name] = (shape, dtype)
+    out = {}
+    for key, val in entries[1:]:
+        for fno, _, v in _fields(val):
+            if fno != 2:
+                continue
+            name, data = None, b""
+            for f2, _, x in _fields(v):
+                if f2 == 1:
+                    name = x.decode()
+                elif f2 == 3:
+                    data = x
+            shape, dtype = shapes[name]
+            if dtype not in _V1_VAL_FIELD:
+                raise ValueError("variable %s: unsupported dtype enum %d" % (name, dtype))
+            vals = _tensor_proto_values(data, dtype)
+            n = int(np.prod(shape)) if shape else 1
+            if vals.size != n:
+                raise ValueError("variable %s: %d values for shape %s" % (name, vals.size, shape))
+            out[name] = vals.astype(DT[dtype]).reshape(shape)
+    return out
+
+
+def tf_format(prefix):
+    """'v2' when `<prefix>.index` exists, 'v1' when `prefix` itself is a table file, None otherwise (e.g. a torch payload)."""
+    if os.path.exists(prefix + ".index"):
+        return "v2"
+    if os.path.isfile(prefix) and os.path.getsize(prefix) >= 48:
+        with open(prefix, "rb") as f:
+            f.seek(-8, os.SEEK_END)
+            if struct.unpack("<Q", f.read(8))[0] == MAGIC:
+                return "v1"
+    return None
+
+
 def latest_checkpoint(directory):
     """tf.train.get_checkpoint_state(directory).model_checkpoint_path, re-rooted at `directory` (the stored path may be
     absolute on the machine that wrote it; z_space_finder.py:63-67 does the same)."""
@@ -427,6 +523,10 @@ def load_tf_checkpoint(directory_or_prefix, store, optimisers=(), prefix="", str
         p = latest_checkpoint(p)
         if p is None:
             raise IOError("no checkpoint state file in %s" % directory_or_prefix)
-    if not os.path.exists(p + ".index"):
-        raise IOError("%s.index not found (a V1 checkpoint is a single file: re-save it as V2 first)" % p)
-    return import_named(store, read_tf_bundle(p, verify=verify), optimisers, prefix, strict)
+    if os.path.exists(p + ".index"):
+        named = read_tf_bundle(p, verify=verify)
+    elif os.path.isfile(p):
+        named = read_tf_v1_checkpoint(p)                  # a single table file: the V1 format
+    else:
+        raise IOError("neither %s.index (V2) nor %s (V1) exists" % (p, p))
+    return import_named(store, named, optimisers, prefix, strict)

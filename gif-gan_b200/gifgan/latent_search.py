@@ -237,8 +237,8 @@ def load_dcgan(opts, batch_size):
         with open(index) as f:
             name = os.path.basename(f.readline().split('"')[1])
         path = os.path.join(opts.checkpoint_directory, name)
-        if os.path.exists(path + ".index"):                    # a TensorFlow V2 checkpoint
-            from . import checkpoint_io
+        from . import checkpoint_io
+        if checkpoint_io.tf_format(path):                      # a TensorFlow checkpoint (V2 bundle or V1 file)
             checkpoint_io.load_tf_checkpoint(path, dcgan.store, (dcgan.d_optim, dcgan.g_optim))
         else:
             dcgan.load_payload(torch.load(path, map_location="cpu", weights_only=False))

@@ -510,8 +510,8 @@ class DCGAN(object):
             return False
         with open(index) as f:
             name = os.path.basename(f.readline().split('"')[1])
-        if os.path.exists(os.path.join(checkpoint_dir, name + ".index")):      # written by TensorFlow (or checkpoint_io): V2 bundle
-            from . import checkpoint_io
+        from . import checkpoint_io
+        if checkpoint_io.tf_format(os.path.join(checkpoint_dir, name)):        # written by TensorFlow (or checkpoint_io): V2 bundle / V1 file
             checkpoint_io.load_tf_checkpoint(os.path.join(checkpoint_dir, name), self.store, (self.d_optim, self.g_optim))
             return True
         self.load_payload(torch.load(os.path.join(checkpoint_dir, name), map_location="cpu", weights_only=False))

@@ -448,8 +448,8 @@ class VID_DCGAN(object):
         if path is None:
             print("FAIL!")
             return False
-        if os.path.exists(path + ".index"):                    # a TensorFlow V2 checkpoint of the image GAN
-            from . import checkpoint_io
+        from . import checkpoint_io
+        if checkpoint_io.tf_format(path):                      # a TensorFlow checkpoint of the image GAN
             checkpoint_io.load_tf_checkpoint(path, self.store, prefix=self.image_gan_scope_name)
         else:
             payload = torch.load(path, map_location="cpu", weights_only=False)
@@ -463,8 +463,8 @@ class VID_DCGAN(object):
         if path is None:
             print("FAIL!")
             return False
-        if os.path.exists(path + ".index"):
-            from . import checkpoint_io
+        from . import checkpoint_io
+        if checkpoint_io.tf_format(path):
             checkpoint_io.load_tf_checkpoint(path, self.store)
         else:
             payload = torch.load(path, map_location="cpu", weights_only=False)

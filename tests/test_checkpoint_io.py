@@ -178,3 +178,58 @@ def test_snappy_blocks_in_a_table(tmp_path):
     path = str(tmp_path / "snappy.index")
     open(path, "wb").write(bytes(out))
     assert C.read_table(path) == entries
+
+
+def test_v1_checkpoint_reader(tmp_path):
+    """tf.train.Saver(write_version=1) files (what the reference's utils/downgrade_tf_checkpoint.py writes): one table;
+    key "" holds the SavedTensorSliceMeta (name, shape, dtype per variable), every other entry a SavedSlice whose
+    TensorProto carries the values.  The TensorProto side is built with TensorBoard's protobuf classes (independent of the
+    parser); the SavedTensorSlices wrappers are assembled by hand from the published field numbers."""
+    from gifgan import checkpoint_io as C, ops
+    from gifgan.model import DCGAN
+    from tensorboard.compat.proto import tensor_pb2, tensor_shape_pb2, types_pb2
+
+    def ld(field, payload):                                     # length-delimited field
+        return bytes([(field << 3) | 2]) + C._varint(len(payload)) + payload
+
+    rs = np.random.RandomState(4)
+    tensors = {"d_h0_conv/w": rs.randn(5, 5, 3, 8).astype(np.float32), "d_h0_conv/biases": rs.randn(8).astype(np.float32),
+               "beta1_power": np.float32(0.125), "global_step": np.int64(77), "flags": np.array([3, -4], np.int32)}
+    enum = {np.dtype(np.float32): types_pb2.DT_FLOAT, np.dtype(np.int64): types_pb2.DT_INT64, np.dtype(np.int32): types_pb2.DT_INT32}
+    metas, entries = b"", []
+    for name in sorted(tensors):
+        a = np.asarray(tensors[name])
+        shape = tensor_shape_pb2.TensorShapeProto()
+        for d in a.shape:
+            shape.dim.add().size = d
+        full_slice = b"".join(ld(1, b"") for _ in a.shape)       # TensorSliceProto: one empty Extent per dimension = everything
+        metas += ld(1, ld(1, name.encode()) + ld(2, shape.SerializeToString()) + bytes([3 << 3, enum[a.dtype]]) + ld(4, full_slice))
+        tp = tensor_pb2.TensorProto(dtype=enum[a.dtype])
+        if a.dtype == np.float32:
+            tp.float_val.extend(a.reshape(-1).tolist())
+        elif a.dtype == np.int64:
+            tp.int64_val.extend(a.reshape(-1).tolist())
+        else:
+            tp.int_val.extend(a.reshape(-1).tolist())
+        saved_slice = ld(1, name.encode()) + ld(2, full_slice) + ld(3, tp.SerializeToString())
+        entries.append((b"\x00" + name.encode(), ld(2, saved_slice)))      # (real keys are an ordered encoding of name + slice)
+    table = [(b"", ld(1, metas))] + entries
+    path = str(tmp_path / "DCGAN.model-77")
+    C.write_table(path, table, block_bytes=1024)
+    got = C.read_tf_v1_checkpoint(path)
+    assert sorted(got) == sorted(tensors)
+    for k, v in tensors.items():
+        assert got[k].dtype == np.asarray(v).dtype and got[k].shape == np.asarray(v).shape and np.array_equal(got[k], v), k
+    # load_tf_checkpoint picks the format from what is on disk
+    open(tmp_path / "checkpoint", "w").write('model_checkpoint_path: "DCGAN.model-77"\n')
+    ops.set_precision("fp32")
+    ops.reset_default_store(device="cpu", seed=2)
+    m = DCGAN(None, batch_size=2, output_size=16, gf_dim=8, df_dim=8, c_dim=3)
+    missing = C.load_tf_checkpoint(str(tmp_path), m.store, (m.d_optim, m.g_optim), strict=False)
+    assert "d_h0_conv/w" not in missing and "g_h1/w" in missing
+    assert np.array_equal(m.store.vars["d_h0_conv/w"].data.numpy(), tensors["d_h0_conv/w"]) and m.d_optim.t == 2   # 0.5^(t+1) = 0.125
+    with pytest.raises(IOError):
+        C.load_tf_checkpoint(str(tmp_path / "nothing"), m.store)
+    assert C.tf_format(path) == "v1" and C.tf_format(str(tmp_path / "nothing")) is None
+    m.save(str(tmp_path / "torch"), 5)
+    assert C.tf_format(os.path.join(str(tmp_path / "torch"), "default_2_16", "DCGAN.model-5")) is None      # a torch payload
