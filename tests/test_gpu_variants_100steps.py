@@ -1,12 +1,15 @@
 """GPU parity tests of the two recurrent_DCGAN variants (multi-layer_recurrent_DCGAN.py and
-..._with_shared_conv_and_drop_out.py) against the oracle and the committed golden trace, and the 100-step loss
-comparison of the image GAN.
+..._with_shared_conv_and_drop_out.py) against the oracle and the committed golden trace, and north_star's 100-step loss
+comparison of the image GAN.  First run on a B200 in round 2 (gpurun_out/r2b_*, tools/diag_recurrent.py).
 
-NOT YET RUN ON HARDWARE: the variants were written after round 1's GPU budget was spent (they compose kernels that are
-covered elsewhere: the LSTM step, thin / generic linears, the conv stack, batch norm with per-frame groups).  They are
-skipped unless GG_UNVALIDATED=1 so that the default suite only holds tests that have passed on a B200; run
-    GG_UNVALIDATED=1 python -m pytest tests/test_gpu_zz_unvalidated.py -m gpu
-first thing on the next GPU visit and drop the gate."""
+Tolerances.  fp32 kernels against the float64 oracle agree to ~2e-6 (max-norm, every variable) on the base model and on the
+shared-encoder variant.  On the 3-layer variant ONE LeakyReLU mask of the discriminator's first layer flips on the generated
+frames (a channel with variance 2.7e-4, i.e. |mean|/std ~ 60: an element within 4e-6 of zero after normalisation lands on
+the other side in fp32) -- tools/diag_recurrent.py recomputes that batch-norm backward in float64 from the kernel's own
+inputs and sees one O(1) element, every other layer at 1e-7 -- which moves d_conv_f1's gradient by 3.5e-3 and, through
+d(fake), every generator gradient by ~1e-3 (dense).  The oracle shows the same class of event between its own float32 and
+float64 runs on the shared-encoder variant (up to 2.3e-2 on generator/deconv_f1).  Hence: max-norm 1e-2 and L2 3e-3 on
+every variable here; the 1e-4 class is asserted where no mask flips (tests/test_gpu_video.py base model, the op tests)."""
 import os
 import sys
 
@@ -14,8 +17,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GG_UNVALIDATED", "0") == "0",
-                                                  reason="not yet validated on a B200 (set GG_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 from oracle.models import RecurrentDCGAN as OracleRec  # noqa: E402
 
@@ -39,22 +41,24 @@ def test_variant_reference_schedule_fp32_and_golden(tag):
     assert set(m.store.vars) == set(ora.vars)
     m.store.load_state_dict(ora.state_dict())
     inp = np.random.RandomState(104).randint(0, 256, (2, 4, 64, 64, 3)).astype(np.int32)
-    # gradients of the first D update and the first G update, before any Adam step
-    wd = ora.update(torch.tensor(inp), "d", apply=False)
-    gd = m.update(torch.tensor(inp), "d", apply=False)
-    assert abs(float(gd["d_loss"]) - wd["d_loss"]) < 2e-3 * max(1.0, abs(wd["d_loss"]))
-    for k in ("discriminator/d_conv_f2", "discriminator/d_fc_w", "discriminator/d_final_fc_w"):
-        got, want = m.store.vars[k].grad.cpu().double(), wd["grads"][k]
-        assert ((got - want).abs().max() / want.abs().max()).item() < 2e-3, k
-    wg = ora.update(torch.tensor(inp), "g", apply=False)
-    gg = m.update(torch.tensor(inp), "g", apply=False)
-    assert abs(float(gg["g_loss"]) - wg["g_loss"]) < 2e-3 * max(1.0, abs(wg["g_loss"]))
-    for k in ("generator/lstm/Cell0/Matrix", "generator/lstm/Cell2/Matrix", "generator/lstm/Cell1/Bias", "generator/output_fc_w", "generator/deconv_f1"):
-        got, want = m.store.vars[k].grad.cpu().double(), wg["grads"][k]
-        assert ((got - want).abs().max() / want.abs().max()).item() < 2e-3, k
-    # one full step of the schedule against the golden trace
+    # gradients of the first D update and the first G update, before any Adam step: EVERY variable of the var_list
+    for which in ("d", "g"):
+        want = ora.update(torch.tensor(inp), which, apply=False)
+        got = m.update(torch.tensor(inp), which, apply=False)
+        key = which + "_loss"
+        assert abs(float(got[key].detach()) - want[key]) < 1e-5 * max(1.0, abs(want[key])), (which, float(got[key]), want[key])
+        for k, w in want["grads"].items():
+            g_ = m.store.vars[k].grad.cpu().double()
+            assert ((g_ - w).abs().max() / w.abs().max()).item() < 1e-2, (k, "max-norm")
+            assert ((g_ - w).norm() / w.norm()).item() < 3e-3, (k, "L2")
+    # one full step of the schedule (d_optim, g_optim, g_optim): d_loss is the D update's, g_loss the last G update's;
+    # the golden trace holds the oracle's losses of the LAST update, so only its g_loss is the same quantity
     got = m.train_step(torch.tensor(inp))
-    assert abs(got["d_loss"] - g[tag + "/losses"][0]) < 2e-3 * max(1.0, abs(g[tag + "/losses"][0]))
+    wd = ora.update(torch.tensor(inp), "d")
+    ora.update(torch.tensor(inp), "g")
+    wg = ora.update(torch.tensor(inp), "g")
+    assert abs(got["d_loss"] - wd["d_loss"]) < 2e-3 * max(1.0, abs(wd["d_loss"])), (got, wd["d_loss"])
+    assert abs(got["g_loss"] - wg["g_loss"]) < 1e-2 * max(1.0, abs(wg["g_loss"])), (got, wg["g_loss"])
     assert abs(got["g_loss"] - g[tag + "/losses"][1]) < 1e-2 * max(1.0, abs(g[tag + "/losses"][1]))
     k = "generator/lstm/Cell1/Bias"
     d = (m.store.vars[k].data.cpu().double() - torch.tensor(g[tag + "/final/" + k])).abs()
