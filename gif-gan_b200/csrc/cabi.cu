@@ -68,10 +68,6 @@ int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void
 int bn_accumulate_stats(const void* x, int x_dt, int64_t rows, int C, int groups, double* sums, cudaStream_t st);
 int tc_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStream_t);
 bool tc_upcat_ok(const gg_conv_desc*);
-size_t tc_upcat_bytes(const gg_conv_desc*);
-int tc_pack_upcat(const gg_conv_desc*, const float*, void*, cudaStream_t);
-size_t tc_pack_plan_bytes(int);
-int tc_pack_filters(const gg_pack_job*, int, void*, size_t, int, cudaStream_t);
 int tc_conv_up_cat(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
 void tc_set_repeat(int);
 void tc_set_prof(void*);
@@ -107,7 +103,7 @@ extern "C" int gg_conv_down(const gg_conv_desc* d, const void* large, const void
 }
 extern "C" int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large, void* stream) {
   GG_REQUIRE(d && large && w && small, GG_ERR_INVALID, "conv_up: null pointer");
-  if ((d->flags & GG_CONV_TENSOR_CORE) && (d->flags & GG_CONV_UPCAT)) return tc_conv_up_cat(d, small, w, bias, large, (cudaStream_t)stream);
+  if ((d->flags & GG_CONV_TENSOR_CORE) && tc_upcat_ok(d)) return tc_conv_up_cat(d, small, w, bias, large, (cudaStream_t)stream);
   if (d->flags & GG_CONV_TENSOR_CORE) return tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream);
   if (c3m_applicable(d)) GG_REPEAT(c3m_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream));
   if (c3_applicable(d)) GG_REPEAT(c3_conv_up(d, small, (const float*)w, bias, (float*)large, (cudaStream_t)stream));
@@ -139,7 +135,7 @@ extern "C" int gg_conv_up_stats(const gg_conv_desc* d, const void* small, const 
   GG_REQUIRE(d && large && w && small && stats && groups >= 1, GG_ERR_INVALID, "conv_up_stats: bad argument");
   int fused = 0;
   int rc;
-  if ((d->flags & GG_CONV_TENSOR_CORE) && (d->flags & GG_CONV_UPCAT)) rc = tc_conv_up_cat(d, small, w, bias, large, (cudaStream_t)stream, stats, groups, &fused);
+  if ((d->flags & GG_CONV_TENSOR_CORE) && tc_upcat_ok(d)) rc = tc_conv_up_cat(d, small, w, bias, large, (cudaStream_t)stream, stats, groups, &fused);
   else if (d->flags & GG_CONV_TENSOR_CORE) rc = tc_conv_up(d, small, w, bias, large, (cudaStream_t)stream, stats, groups, &fused);
   else rc = gg_conv_up(d, small, w, bias, large, stream);
   if (rc || fused) return rc;
@@ -147,18 +143,7 @@ extern "C" int gg_conv_up_stats(const gg_conv_desc* d, const void* small, const 
   return bn_accumulate_stats(large, d->large_dtype, rows, d->C, groups, stats, (cudaStream_t)stream);
 }
 
-extern "C" size_t gg_upcat_bytes(const gg_conv_desc* d) { return d ? tc_upcat_bytes(d) : 0; }
-extern "C" int gg_pack_filter_upcat(const gg_conv_desc* d, const float* w, void* wcat, void* stream) {
-  GG_REQUIRE(d && w && wcat, GG_ERR_INVALID, "pack_filter_upcat: null pointer");
-  return tc_pack_upcat(d, w, wcat, (cudaStream_t)stream);
-}
-
 static gg_conv_desc no_act(const gg_conv_desc* d) { gg_conv_desc c = *d; c.act = GG_ACT_NONE; return c; }
-
-extern "C" size_t gg_pack_plan_bytes(int32_t njobs) { return njobs > 0 ? tc_pack_plan_bytes(njobs) : 0; }
-extern "C" int gg_pack_filters(const gg_pack_job* jobs, int32_t njobs, void* plan, size_t plan_bytes, int32_t upload, void* stream) {
-  return tc_pack_filters(jobs, njobs, plan, plan_bytes, upload, (cudaStream_t)stream);
-}
 
 extern "C" int gg_conv2d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* s) { return gg_conv_down(d, x, w, b, y, s); }
 extern "C" int gg_conv2d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* s) { GG_REQUIRE(d, GG_ERR_INVALID, "null desc"); gg_conv_desc c = no_act(d); return gg_conv_up(&c, dy, w, nullptr, dx, s); }

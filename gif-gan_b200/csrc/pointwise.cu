@@ -53,54 +53,6 @@ __global__ void axpby_kernel(const float* __restrict__ x, float a, float* __rest
     y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
 }
 
-// ---- filter packing for the tensor-core path ----------------------------------------------
-// w [taps][C][K] fp32 -> w_ck bf16 [taps][C][K] and w_kc bf16 [taps][K][C] (32x32 smem transpose)
-__global__ void pack_filter_kernel(const float* __restrict__ w, bf16* __restrict__ w_ck, bf16* __restrict__ w_kc, int C, int K) {
-  pdl_grid_sync();
-  __shared__ float tile[32][33];
-  const int t = blockIdx.z, c0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
-  const float* src = w + (int64_t)t * C * K;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, k = k0 + threadIdx.x;
-    float v = 0.f;
-    if (c < C && k < K) {
-      v = src[(int64_t)c * K + k];
-      if (w_ck) w_ck[(int64_t)t * C * K + (int64_t)c * K + k] = __float2bfloat16_rn(v);
-    }
-    tile[i][threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (w_kc) {
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int k = k0 + i, c = c0 + threadIdx.x;
-      if (c < C && k < K) w_kc[(int64_t)t * C * K + (int64_t)k * C + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
-    }
-  }
-}
-
-// 64 x 64 tiles, two elements per thread: fp32 pairs in, bf16x2 out on both the straight and the transposed copy
-// (the 32 x 32 version wrote one 2-byte element per lane: 64 B per warp store)
-__global__ void __launch_bounds__(256)
-pack_filter64_kernel(const float* __restrict__ w, bf16* __restrict__ w_ck, bf16* __restrict__ w_kc, int C, int K) {
-  pdl_grid_sync();
-  __shared__ float tile[64][65];
-  const int t = blockIdx.z, c0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
-  const int64_t base = (int64_t)t * C * K;
-  const int x = threadIdx.x, y = threadIdx.y;                   // block (32, 8)
-#pragma unroll
-  for (int i = y; i < 64; i += 8) {
-    const float2 v = *reinterpret_cast<const float2*>(w + base + (int64_t)(c0 + i) * K + k0 + 2 * x);
-    if (w_ck) *reinterpret_cast<__nv_bfloat162*>(w_ck + base + (int64_t)(c0 + i) * K + k0 + 2 * x) = __floats2bfloat162_rn(v.x, v.y);
-    tile[i][2 * x] = v.x; tile[i][2 * x + 1] = v.y;
-  }
-  __syncthreads();
-  if (w_kc) {
-#pragma unroll
-    for (int i = y; i < 64; i += 8)                             // row i = output channel k0 + i, columns = channel pairs
-      *reinterpret_cast<__nv_bfloat162*>(w_kc + base + (int64_t)(k0 + i) * C + c0 + 2 * x) = __floats2bfloat162_rn(tile[2 * x][i], tile[2 * x + 1][i]);
-  }
-}
-
 // ---- losses --------------------------------------------------------------------------------
 __global__ void sigmoid_ce_kernel(const float* __restrict__ logits, int64_t n, float target, float weight, float* __restrict__ loss_out,
                                   int accumulate, float* __restrict__ dlogits) {
@@ -189,8 +141,8 @@ distance_loss_kernel(const TA* __restrict__ a, const float* __restrict__ t, int6
 
 // ---- TF Adam (model.py:153-156) ----------------------------------------------
 __global__ void __launch_bounds__(PW_THREADS)
-adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n, float lr_t,
-            float b1, float b2, float eps, float gs) {
+adam_kernel(float* __restrict__ p, bf16* __restrict__ pb, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            float lr_t, float b1, float b2, float eps, float gs) {
   pdl_grid_sync();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
@@ -208,12 +160,15 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (pb != nullptr) st4(pb + 4 * i, pp);          // bf16 shadow: the tensor-core kernels' filter operand, refreshed in the same pass
   }
   for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gr = g[i] * gs;
     const float mi = b1 * m[i] + (1.f - b1) * gr, vi = b2 * v[i] + (1.f - b2) * gr * gr;
     m[i] = mi; v[i] = vi;
-    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = pi;
+    if (pb != nullptr) pb[i] = __float2bfloat16_rn(pi);
   }
 }
 
@@ -227,8 +182,8 @@ __global__ void adam_tick_kernel(int* __restrict__ state, float lr, float b1, fl
   reinterpret_cast<float*>(state)[1] = (float)lr_t;
 }
 __global__ void __launch_bounds__(PW_THREADS)
-adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-                const int* __restrict__ state, float b1, float b2, float eps, float gs) {
+adam_dev_kernel(float* __restrict__ p, bf16* __restrict__ pb, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                int64_t n, const int* __restrict__ state, float b1, float b2, float eps, float gs) {
   pdl_grid_sync();
   const float lr_t = reinterpret_cast<const float*>(state)[1];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -247,12 +202,15 @@ adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (pb != nullptr) st4(pb + 4 * i, pp);          // bf16 shadow: the tensor-core kernels' filter operand, refreshed in the same pass
   }
   for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gr = g[i] * gs;
     const float mi = b1 * m[i] + (1.f - b1) * gr, vi = b2 * v[i] + (1.f - b2) * gr * gr;
     m[i] = mi; v[i] = vi;
-    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = pi;
+    if (pb != nullptr) pb[i] = __float2bfloat16_rn(pi);
   }
 }
 
@@ -459,18 +417,6 @@ extern "C" int gg_gather_scalars(const float* const* srcs, int32_t n, float* dst
   return check_launch("gather_scalars");
 }
 
-extern "C" int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t C, int32_t K, void* stream) {
-  GG_REQUIRE(w && (w_ck || w_kc) && taps > 0 && C > 0 && K > 0, GG_ERR_INVALID, "pack_filter: bad argument");
-  dim3 block(32, 8);
-  if (C % 64 == 0 && K % 64 == 0) {
-    Launch(dim3(K / 64, C / 64, taps), block, 0, (cudaStream_t)stream)(pack_filter64_kernel, w, (bf16*)w_ck, (bf16*)w_kc, C, K);
-  } else {
-    dim3 grid(ceil_div(K, 32), ceil_div(C, 32), taps);
-    Launch(grid, block, 0, (cudaStream_t)stream)(pack_filter_kernel, w, (bf16*)w_ck, (bf16*)w_kc, C, K);
-  }
-  return check_launch("pack_filter");
-}
-
 extern "C" int gg_sigmoid_ce(const float* logits, int64_t n, float target, float weight, float* loss_out, int32_t accumulate,
                              float* dlogits, void* stream) {
   GG_REQUIRE(logits && loss_out && n > 0, GG_ERR_INVALID, "sigmoid_ce: bad argument");
@@ -504,22 +450,22 @@ extern "C" int gg_distance_loss(const void* a, int32_t a_dt, const float* target
   return check_launch("distance_loss");
 }
 
-extern "C" int gg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps, float gs,
+extern "C" int gg_adam(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps, float gs,
                        void* stream) {
   GG_REQUIRE(p && g && m && v && n > 0, GG_ERR_INVALID, "adam: bad argument");
-  GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v), GG_ERR_INVALID, "adam: buffers must be 16-byte aligned");
-  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_kernel, p, g, m, v, n, lr_t, b1, b2, eps, gs);
+  GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v) && ((uintptr_t)p_bf16 % 8) == 0, GG_ERR_INVALID, "adam: buffers must be 16-byte aligned (bf16 shadow: 8)");
+  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_kernel, p, (bf16*)p_bf16, g, m, v, n, lr_t, b1, b2, eps, gs);
   return check_launch("adam");
 }
 
-extern "C" int gg_adam_graph(float* p, const float* g, float* m, float* v, int64_t n, int32_t* state, float lr, float b1, float b2,
+extern "C" int gg_adam_graph(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, int32_t* state, float lr, float b1, float b2,
                              float eps, float gs, void* stream) {
   GG_REQUIRE(p && g && m && v && state && n > 0, GG_ERR_INVALID, "adam_graph: bad argument");
-  GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v), GG_ERR_INVALID, "adam_graph: buffers must be 16-byte aligned");
+  GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v) && ((uintptr_t)p_bf16 % 8) == 0, GG_ERR_INVALID, "adam_graph: buffers must be 16-byte aligned (bf16 shadow: 8)");
   Launch(1, 1, 0, (cudaStream_t)stream)(adam_tick_kernel, state, lr, b1, b2);
   int rc = check_launch("adam_tick");
   if (rc) return rc;
-  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel, p, g, m, v, n, state, b1, b2, eps, gs);
+  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel, p, (bf16*)p_bf16, g, m, v, n, state, b1, b2, eps, gs);
   return check_launch("adam_dev");
 }
 

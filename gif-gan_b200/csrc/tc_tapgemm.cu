@@ -92,6 +92,7 @@ struct TcTap {
   int16_t widx;             // tap index in the packed filter
   int16_t pad_;
 };
+struct TcCatOrigin { int8_t a0, b0, e0, pad_; };
 struct TcClass {
   int Md, Mh, Mw;           // M grid (per image) of this class
   int od0, oh0, ow0;        // output coordinate = m * os + o0
@@ -117,6 +118,10 @@ struct TcPixParams {
   int stages;
   int cps;                    // 64-wide K chunks per pipeline stage (MMAs per commit = 4 * cps)
   int cat_C;                  // > 0: the N axis is the concatenation of the output parity classes, cat_C channels each (tc_conv_up_cat)
+  int bmode;                  // B operand from the bf16 filter copy w[taps][C][K]: 0 = K-major rows (conv_up: N = C, reduce over K),
+                              // 1 = MN-major atoms (conv_down: N = K, reduce over C), 2 = K-major, one box per parity class (up_cat)
+  int ncat;                   // bmode 2: parity classes
+  TcCatOrigin cat_origin[TC_MAX_TAPS];            // bmode 2: shift -> first tap (kd, kh, kw) of its class box (may be < 0: TMA zero-fills)
   int splitk;                 // cluster size along K: the CTAs of a cluster share one output tile (1 = no cluster)
   unsigned long long* prof;   // optional per-CTA clock64 breakdown (tools/tc_sweep.py --prof), 8 slots per CTA
   double* stats;              // optional fused batch-norm statistics [groups][2][Nout] (fp32 output only)
@@ -240,7 +245,16 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
           const int widx = p.taps[t].widx;
           if (elect_one()) {
             mbar_expect_tx(fb, chunk_bytes);
-            tma_load_3d(dst, &p.bmap, fb, kc, n0, widx);
+            if (p.bmode == 0) {
+              tma_load_3d(dst, &p.bmap, fb, kc, n0, widx);
+            } else if (p.bmode == 1) {
+              tma_load_4d(dst, &p.bmap, fb, 0, kc, n0 >> 6, widx);           // BN/64 atoms of [64 reduction rows][64 n]
+            } else {
+              // all parity classes of the shift in ONE box: class (ad, ah, aw) uses tap (a0 + ad, b0 + ah, e0 + aw), so the
+              // classes are a (sd, sh, sw) box of the filter's tap axes; taps outside [0, k) are zero-filled by TMA
+              const TcCatOrigin o = p.cat_origin[widx];
+              tma_load_5d(dst, &p.bmap, fb, kc, 0, o.e0, o.b0, o.a0);
+            }
           }
         }
       } else if (elect_one()) {
@@ -254,9 +268,14 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     if (prof && warp == 0 && lane == 0) { prof[0] = (unsigned long long)(clock64() - t_setup); prof[1] = 0; }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 0, 0);
+    const bool b_mn = (p.bmode == 1);
+    const uint32_t idesc = make_idesc_bf16(TILE_M, p.BN, 0, b_mn ? 1 : 0);
     // descriptor = constant high word | (address >> 4): only the low word changes per stage / chunk / k-step
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024);
+    // MN-major B (conv_down reads w[tap][c][k] as it lies): 64-wide n atoms 8 KB apart (LBO), 8-row k groups 1 KB apart
+    // (SBO); one K=16 step = 16 rows = 2 KB = +128 descriptor units (as both operands of tc_wgrad_kernel)
+    const uint64_t desc_hi_b = b_mn ? make_smem_desc(0, 8192, 1024) : desc_hi;
+    const uint32_t bstep = b_mn ? 128u : 2u;
     const uint32_t b_off = (uint32_t)(cps * A_STAGE_BYTES);
     int s = 0, left = total_chunks;
     uint32_t ph = 0;
@@ -277,15 +296,15 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       left -= cps;
       if (elect_one()) {
         const uint64_t ad = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-        const uint64_t bd = desc_hi | (uint64_t)(((a_addr + b_off) & 0x3FFFFu) >> 4);
+        const uint64_t bd = desc_hi_b | (uint64_t)(((a_addr + b_off) & 0x3FFFFu) >> 4);
         umma_bf16(tmem_base, ad, bd, idesc, acc);
 #pragma unroll
-        for (int k = 1; k < KCHUNK / 16; ++k)                // +32 B per K=16 step -> +2 in 16-byte units
-          umma_bf16(tmem_base, ad + 2u * k, bd + 2u * k, idesc, 1u);
+        for (int k = 1; k < KCHUNK / 16; ++k)                // +32 B per K=16 step -> +2 in 16-byte units (K-major)
+          umma_bf16(tmem_base, ad + 2u * k, bd + bstep * k, idesc, 1u);
         if (two) {
           const uint64_t ad2 = ad + (uint64_t)(A_STAGE_BYTES >> 4), bd2 = bd + (uint64_t)(b_chunk_bytes >> 4);
 #pragma unroll
-          for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16(tmem_base, ad2 + 2u * k, bd2 + 2u * k, idesc, 1u);
+          for (int k = 0; k < KCHUNK / 16; ++k) umma_bf16(tmem_base, ad2 + 2u * k, bd2 + bstep * k, idesc, 1u);
         }
         umma_commit(eb);                                   // frees this smem stage when the MMAs retire
         if (it == iters - 1) umma_commit(tmem_full_bar);    // accumulator complete
@@ -762,9 +781,9 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
 
 // stats != nullptr: also accumulate per-channel (sum, sum of squares) of the fp32 output into stats[groups][2][channels].
 // *fused is set to 1 when the kernel did it (otherwise the caller runs a separate statistics pass).
-int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, const float* bias, void* small, cudaStream_t st,
+int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_bf, const float* bias, void* small, cudaStream_t st,
                  double* stats = nullptr, int groups = 1, int* fused = nullptr) {
-  int rc = check_tc(d, large, w_kc, true, false);
+  int rc = check_tc(d, large, w_bf, true, false);
   if (rc) return rc;
   TcPixParams p;
   memset(&p, 0, sizeof(p));
@@ -778,11 +797,15 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_kc, con
   const int64_t mtiles = (int64_t)c.tw * c.th * c.td * c.tn;
   const int taps = d->kd * d->kh * d->kw;
   pick_tile(d->K, mtiles, taps * (d->C / KCHUNK), &p.BN, &p.splitk);
-  const uint64_t bdims[3] = {(uint64_t)d->C, (uint64_t)d->K, (uint64_t)taps};
-  const uint64_t bstr[2] = {(uint64_t)d->C * 2, (uint64_t)d->C * d->K * 2};
-  const uint32_t bbox[3] = {64, (uint32_t)p.BN, 1};
-  rc = encode_tmap_bf16(&p.bmap, w_kc, 3, bdims, bstr, bbox);
-  if (rc) return rc;
+  {  // B operand straight from the bf16 filter copy w[tap][c][k] (no transposed copy): the reduction index c is the ROW
+     // axis, so the tile is MN-major -- BN/64 atoms of [64 c rows][64 k = 128 B], one 4-D box per K chunk
+    const uint64_t bdims[4] = {64, (uint64_t)d->C, (uint64_t)(d->K / 64), (uint64_t)taps};
+    const uint64_t bstr[3] = {(uint64_t)d->K * 2, 128, (uint64_t)d->C * d->K * 2};
+    const uint32_t bbox[4] = {64, 64, (uint32_t)(p.BN / 64), 1};
+    rc = encode_tmap_bf16(&p.bmap, w_bf, 4, bdims, bstr, bbox);
+    if (rc) return rc;
+    p.bmode = 1;
+  }
   {  // output map: the small tensor, dense
     const uint64_t esz = d->small_dtype == GG_BF16 ? 2 : 4;
     const uint64_t odims[5] = {(uint64_t)d->K, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->Do, (uint64_t)d->N};
@@ -906,6 +929,8 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
 // the 9 shifts; the packed filter wcat[shift][class*C + c][k] holds w[tap(class, shift)][c][k], or zero where the class
 // does not use the shift (25 of 36 (class, shift) pairs are real: 69 % useful MACs at the full N=256 rate).  A traffic
 // drops from 25 to 9 boxes per K chunk and the launch is one wave of M/128 CTAs instead of four classes of them.
+// No packed filter exists: the B tile of a shift is assembled by the TMA producer from four boxes of the plain bf16 copy
+// (TcPixParams::cat_tap), a missing (class, shift) pair being a box at an out-of-range tap index, which TMA zero-fills.
 constexpr int UPCAT_MAX_SHIFTS = 27;
 struct UpcatPlan {
   int ncls, nshift;
@@ -915,8 +940,9 @@ struct UpcatPlan {
 };
 
 bool tc_upcat_ok(const gg_conv_desc* d) {
+  static const bool enabled = [] { const char* v = getenv("GG_UPCAT"); return !(v && v[0] == '0'); }();   // A/B switch
   const int ncls = d->sd * d->sh * d->sw;
-  return (d->flags & GG_CONV_TENSOR_CORE) && ncls > 1 && ncls <= 8 && ncls * d->C == 256 && d->K % 64 == 0 && d->D % d->sd == 0 &&
+  return enabled && (d->flags & GG_CONV_TENSOR_CORE) && ncls > 1 && ncls <= 8 && ncls * d->C == 256 && d->K % 64 == 0 && d->D % d->sd == 0 &&
          d->H % d->sh == 0 && d->W % d->sw == 0 && d->small_dtype == GG_BF16;
 }
 
@@ -951,137 +977,15 @@ static int upcat_plan(const gg_conv_desc* d, UpcatPlan* P) {
   return GG_OK;
 }
 
-struct UpcatTable { int16_t tap[UPCAT_MAX_SHIFTS][8]; };
-
-__global__ void pack_upcat_kernel(const float* __restrict__ w, bf16* __restrict__ wcat, UpcatTable T, int ncls, int C, int K) {
-  pdl_grid_sync();
-  const int s = blockIdx.y, row = blockIdx.x;               // row = class * C + c
-  const int cls = row / C, c = row - cls * C;
-  const int tap = T.tap[s][cls];
-  bf16* dst = wcat + ((int64_t)s * ncls * C + row) * K;
-  const float* src = w + ((int64_t)(tap < 0 ? 0 : tap) * C + c) * K;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] = __float2bfloat16_rn(tap < 0 ? 0.f : __ldg(src + k));
-}
-
-size_t tc_upcat_bytes(const gg_conv_desc* d) {
-  UpcatPlan P;
-  if (!tc_upcat_ok(d) || upcat_plan(d, &P)) return 0;
-  return (size_t)P.nshift * P.ncls * d->C * d->K * sizeof(bf16);
-}
-
-int tc_pack_upcat(const gg_conv_desc* d, const float* w, void* wcat, cudaStream_t st) {
-  GG_REQUIRE(tc_upcat_ok(d), GG_ERR_UNSUPPORTED, "pack_filter_upcat: shape not eligible");
-  UpcatPlan P;
-  int rc = upcat_plan(d, &P);
-  if (rc) return rc;
-  UpcatTable T;
-  for (int s = 0; s < UPCAT_MAX_SHIFTS; ++s) for (int c = 0; c < 8; ++c) T.tap[s][c] = (int16_t)P.tap[s][c];
-  Launch(dim3(P.ncls * d->C, P.nshift), 128, 0, st)(pack_upcat_kernel, w, (bf16*)wcat, T, P.ncls, (int)d->C, (int)d->K);
-  return check_launch("pack_upcat");
-}
-
-// ---- one launch re-packs every filter of an optimiser group -------------------------------------------------
-// After an Adam step all tensor-core filters of the group need fresh bf16 copies (w_ck / w_kc, and the class-concatenated
-// copy where the layer uses it).  As separate launches that is 16 small latency-bound kernels per train step; here the jobs
-// sit in a device table (uploaded once, the pointers never change) and one grid covers all of them: block -> job by the
-// ascending block_begin, then either a 64 x 64 transpose tile or one row of the class-concatenated copy.
-struct PackJobDev {
-  const float* w;
-  bf16 *ck, *kc, *cat;
-  int C, K, block_begin, tile_blocks;        // tile_blocks = taps * (C/64) * (K/64) when ck or kc is set, else 0
-  int ncls, nshift;                          // cat: nshift * ncls * C row blocks
-  int16_t tap[UPCAT_MAX_SHIFTS][8];
-};
-
-__global__ void __launch_bounds__(256) pack_batch_kernel(const PackJobDev* __restrict__ jobs, int njobs) {
-  pdl_grid_sync();
-  __shared__ float tile[64][65];
-  int b = blockIdx.x, j = 0;
-  while (j + 1 < njobs && b >= jobs[j + 1].block_begin) ++j;
-  const PackJobDev* J = jobs + j;
-  b -= J->block_begin;
-  const int C = J->C, K = J->K;
-  const float* __restrict__ w = J->w;
-  const int tid = threadIdx.x;
-  if (b < J->tile_blocks) {
-    const int kt = K / 64, ct = C / 64;
-    const int k0 = (b % kt) * 64, c0 = ((b / kt) % ct) * 64, t = b / (kt * ct);
-    const int64_t base = (int64_t)t * C * K;
-    bf16* __restrict__ w_ck = J->ck;
-    bf16* __restrict__ w_kc = J->kc;
-    const int x = tid & 31, y = tid >> 5;                       // 32 x 8, as pack_filter64_kernel
-#pragma unroll
-    for (int i = y; i < 64; i += 8) {
-      const float2 v = *reinterpret_cast<const float2*>(w + base + (int64_t)(c0 + i) * K + k0 + 2 * x);
-      if (w_ck) *reinterpret_cast<__nv_bfloat162*>(w_ck + base + (int64_t)(c0 + i) * K + k0 + 2 * x) = __floats2bfloat162_rn(v.x, v.y);
-      tile[i][2 * x] = v.x; tile[i][2 * x + 1] = v.y;
-    }
-    __syncthreads();
-    if (w_kc) {
-#pragma unroll
-      for (int i = y; i < 64; i += 8)
-        *reinterpret_cast<__nv_bfloat162*>(w_kc + base + (int64_t)(k0 + i) * C + c0 + 2 * x) = __floats2bfloat162_rn(tile[2 * x][i], tile[2 * x + 1][i]);
-    }
-  } else {
-    b -= J->tile_blocks;
-    const int rows = J->ncls * C;
-    const int row = b % rows, sft = b / rows;
-    const int cls = row / C, c = row - cls * C;
-    const int tap = J->tap[sft][cls];
-    bf16* dst = J->cat + ((int64_t)sft * rows + row) * K;
-    const float* src = w + ((int64_t)(tap < 0 ? 0 : tap) * C + c) * K;
-    for (int k = tid; k < K; k += 256) dst[k] = __float2bfloat16_rn(tap < 0 ? 0.f : __ldg(src + k));
-  }
-}
-
-size_t tc_pack_plan_bytes(int njobs) { return (size_t)njobs * sizeof(PackJobDev); }
-
-// jobs: host array.  upload != 0: (re)build the device table in `plan` first -- a pageable-memory copy, so only outside
-// stream capture; afterwards the same jobs/plan pair is replayed with upload == 0.
-int tc_pack_filters(const gg_pack_job* jobs, int njobs, void* plan, size_t plan_bytes, int upload, cudaStream_t st) {
-  GG_REQUIRE(jobs && plan && njobs > 0 && njobs <= 64, GG_ERR_INVALID, "pack_filters: bad argument");
-  GG_REQUIRE(plan_bytes >= tc_pack_plan_bytes(njobs), GG_ERR_WORKSPACE, "pack_filters: plan buffer too small");
-  std::vector<PackJobDev> dev(njobs);
-  int blocks = 0;
-  for (int j = 0; j < njobs; ++j) {
-    const gg_pack_job& in = jobs[j];
-    PackJobDev& o = dev[j];
-    memset(&o, 0, sizeof(o));
-    GG_REQUIRE(in.w && in.C > 0 && in.K > 0 && in.taps > 0, GG_ERR_INVALID, "pack_filters: bad job");
-    o.w = in.w; o.ck = (bf16*)in.w_ck; o.kc = (bf16*)in.w_kc; o.cat = (bf16*)in.w_cat;
-    o.C = in.C; o.K = in.K; o.block_begin = blocks;
-    if (o.ck || o.kc) {
-      GG_REQUIRE(in.C % 64 == 0 && in.K % 64 == 0, GG_ERR_UNSUPPORTED, "pack_filters: C and K must be multiples of 64");
-      o.tile_blocks = in.taps * (in.C / 64) * (in.K / 64);
-    }
-    if (o.cat) {
-      GG_REQUIRE(tc_upcat_ok(&in.cat_desc) && in.cat_desc.C == in.C && in.cat_desc.K == in.K, GG_ERR_UNSUPPORTED,
-                 "pack_filters: cat_desc not eligible for the class-concatenated layout");
-      UpcatPlan P;
-      int rc = upcat_plan(&in.cat_desc, &P);
-      if (rc) return rc;
-      o.ncls = P.ncls; o.nshift = P.nshift;
-      for (int s2 = 0; s2 < UPCAT_MAX_SHIFTS; ++s2) for (int c = 0; c < 8; ++c) o.tap[s2][c] = (int16_t)P.tap[s2][c];
-    }
-    blocks += o.tile_blocks + o.nshift * o.ncls * o.C;
-  }
-  GG_REQUIRE(blocks > 0, GG_ERR_INVALID, "pack_filters: nothing to pack");
-  if (upload) {
-    cudaError_t e = cudaMemcpyAsync(plan, dev.data(), tc_pack_plan_bytes(njobs), cudaMemcpyHostToDevice, st);
-    GG_REQUIRE(e == cudaSuccess, GG_ERR_CUDA, cudaGetErrorString(e));
-  }
-  Launch(blocks, 256, 0, st)(pack_batch_kernel, (const PackJobDev*)plan, njobs);
-  return check_launch("pack_batch");
-}
-
-int tc_conv_up_cat(const gg_conv_desc* d, const void* small, const void* wcat, const float* bias, void* large, cudaStream_t st,
+int tc_conv_up_cat(const gg_conv_desc* d, const void* small, const void* w_bf, const float* bias, void* large, cudaStream_t st,
                    double* stats = nullptr, int groups = 1, int* fused = nullptr) {
-  int rc = check_tc(d, small, wcat, false, true);
+  int rc = check_tc(d, small, w_bf, false, true);
   if (rc) return rc;
   GG_REQUIRE(tc_upcat_ok(d), GG_ERR_UNSUPPORTED, "conv_up (concatenated classes): shape not eligible");
   UpcatPlan P;
   rc = upcat_plan(d, &P);
   if (rc) return rc;
+  GG_REQUIRE(P.nshift <= TC_MAX_TAPS && P.ncls <= TC_MAX_CLASSES, GG_ERR_UNSUPPORTED, "conv_up (concatenated classes): too many shifts");
   TcPixParams p;
   memset(&p, 0, sizeof(p));
   const int Mw = d->W / d->sw, Mh = d->H / d->sh, Md = d->D / d->sd;      // positions = the small grid's footprint of one class
@@ -1115,11 +1019,27 @@ int tc_conv_up_cat(const gg_conv_desc* d, const void* small, const void* wcat, c
   p.splitk = 1;
   p.cat_C = d->C;
   p.ntiles_n = 1;
-  const uint64_t bdims[3] = {(uint64_t)d->K, (uint64_t)p.BN, (uint64_t)P.nshift};
-  const uint64_t bstr[2] = {(uint64_t)d->K * 2, (uint64_t)p.BN * d->K * 2};
-  const uint32_t bbox[3] = {64, (uint32_t)p.BN, 1};
-  rc = encode_tmap_bf16(&p.bmap, wcat, 3, bdims, bstr, bbox);
+  // B tile of shift s: class (ad, ah, aw) reads tap (pd + ad - sd*od, ph + ah - sh*oh, pw + aw - sw*ow) -- affine in the class,
+  // so the tile is ONE 5-D box (64 k, C rows, sw, sh, sd) of the plain bf16 filter copy w[kd][kh][kw][C][K] starting at tap
+  // (pd - sd*od, ph - sh*oh, pw - sw*ow); a class that does not use the shift falls outside [0, k) and is zero-filled by TMA.
+  // Box order (aw fastest, then ah, ad) = class order of upcat_plan = row blocks of the N = ncls * C tile.
+  const uint64_t bdims[5] = {(uint64_t)d->K, (uint64_t)d->C, (uint64_t)d->kw, (uint64_t)d->kh, (uint64_t)d->kd};
+  const uint64_t bstr[4] = {(uint64_t)d->K * 2, (uint64_t)d->C * d->K * 2, (uint64_t)d->kw * d->C * d->K * 2, (uint64_t)d->kh * d->kw * d->C * d->K * 2};
+  const uint32_t bbox[5] = {64, (uint32_t)d->C, (uint32_t)d->sw, (uint32_t)d->sh, (uint32_t)d->sd};
+  rc = encode_tmap_bf16(&p.bmap, w_bf, 5, bdims, bstr, bbox);
   if (rc) return rc;
+  p.bmode = 2; p.ncat = P.ncls;
+  for (int s = 0; s < P.nshift; ++s) {
+    TcCatOrigin o;
+    o.a0 = (int8_t)(d->pd - d->sd * P.shift[s][0]); o.b0 = (int8_t)(d->ph - d->sh * P.shift[s][1]); o.e0 = (int8_t)(d->pw - d->sw * P.shift[s][2]);
+    o.pad_ = 0;
+    p.cat_origin[s] = o;
+    for (int k = 0; k < P.ncls; ++k) {      // the plan's own table must agree with the affine form
+      const int a = o.a0 + P.cls_a[k][0], b = o.b0 + P.cls_a[k][1], e = o.e0 + P.cls_a[k][2];
+      const bool in = a >= 0 && a < d->kd && b >= 0 && b < d->kh && e >= 0 && e < d->kw;
+      GG_REQUIRE((in ? (a * d->kh + b) * d->kw + e : -1) == P.tap[s][k], GG_ERR_INVALID, "conv_up (concatenated classes): tap table mismatch");
+    }
+  }
   p.nclasses = 1;
   p.R = d->K; p.Nout = p.BN; p.Mn = d->N;
   p.OD = d->D; p.OH = d->H; p.OW = d->W; p.osd = d->sd; p.osh = d->sh; p.osw = d->sw;

@@ -17,7 +17,6 @@ LIB_PATH = os.environ.get("GG_LIB") or os.path.join(os.path.dirname(_HERE), "lib
 GG_F32, GG_BF16 = 0, 1
 ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4, "tanh01": 5}
 CONV_TENSOR_CORE = 2
-CONV_UPCAT = 4
 
 
 class ConvDesc(C.Structure):
@@ -25,12 +24,6 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("N", "D", "H", "W", "C", "Do", "Ho", "Wo", "K", "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw",
                  "large_dtype", "small_dtype", "act")] + [("act_param", C.c_float), ("flags", C.c_int32)]
-
-
-class PackJob(C.Structure):
-    """struct gg_pack_job (include/gifgan.h)."""
-    _fields_ = [("w", C.c_void_p), ("w_ck", C.c_void_p), ("w_kc", C.c_void_p), ("w_cat", C.c_void_p), ("taps", C.c_int32), ("C", C.c_int32),
-                ("K", C.c_int32), ("reserved", C.c_int32), ("cat_desc", ConvDesc)]
 
 
 _lib = None
@@ -61,11 +54,6 @@ SIGNATURES = {
     "gg_conv3d_fwd": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv3d_dgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),
     "gg_conv3d_wgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),
-    "gg_pack_filter": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
-    "gg_upcat_bytes": (_sz, [_dp]),
-    "gg_pack_filter_upcat": (C.c_int, [_dp, _vp, _vp, _vp]),
-    "gg_pack_plan_bytes": (_sz, [_i32]),
-    "gg_pack_filters": (C.c_int, [C.POINTER(PackJob), _i32, _vp, _sz, _i32, _vp]),
     "gg_linear_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "gg_linear_dgrad": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "gg_linear_wgrad": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
@@ -85,8 +73,8 @@ SIGNATURES = {
     "gg_mse": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _f32, _vp, _i32, _vp, _vp]),
     "gg_distance_loss_workspace_bytes": (_sz, []),
     "gg_distance_loss": (C.c_int, [_vp, _i32, _vp, _i64, _f32, _f32, _vp, _i32, _vp, _vp, _sz, _vp]),
-    "gg_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
-    "gg_adam_graph": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "gg_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "gg_adam_graph": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
     "gg_lstm_step_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "gg_lstm_step_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
 }

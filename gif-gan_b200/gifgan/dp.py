@@ -65,13 +65,23 @@ class DataParallel:
             self.comm_stream = torch.cuda.Stream() if torch.cuda.is_available() and dist.get_backend() == "nccl" else False
         return self.comm_stream
 
+    def _segments(self, optim):
+        """The flat range of `optim` as a list of [lo, hi) segments, one per optimiser group.  Backward produces the
+        gradients of ONE group in reverse layout order, but the groups of a tuple var_list (e.g. ("dvideo", "d_img") with
+        --train_img_disc: the video discriminator's filters come first in the layout AND first in backward, the image
+        discriminator's last) are not ordered against each other -- so "everything above this offset is final" holds
+        inside a segment only, and each segment keeps its own finished tail."""
+        if isinstance(optim.group, (tuple, list)):
+            return [list(optim.store.ranges[g]) for g in optim.group]
+        return [list(optim.range())]
+
     def begin_update(self, optim):
         """Call before the backward pass of an update whose gradients `optim` owns."""
         if self.world_size <= 1:
             return
         from . import ops
-        b, e = optim.range()
-        self._cur = dict(optim=optim, lo=b, done_hi=e, issued=[])
+        # seg = [lo, done_hi]: [done_hi, hi) of the segment has been all-reduced already
+        self._cur = dict(optim=optim, segs=self._segments(optim), issued=[])
         ops.GRAD_READY_HOOK = self.grad_ready
 
     def _issue(self, lo, hi, extra_streams=()):
@@ -92,15 +102,20 @@ class DataParallel:
     def grad_ready(self, var, producer_stream=None):
         """Hook: `var`'s filter gradient has just been enqueued (on producer_stream, if not the current stream)."""
         cur = getattr(self, "_cur", None)
-        if cur is None or not (cur["lo"] <= var.offset < cur["optim"].range()[1]):
+        if cur is None:
             return
-        if var.offset >= cur["done_hi"]:
-            raise RuntimeError(f"{var.name}: a gradient was produced after its bucket had been all-reduced "
-                               "(a filter used at two call sites of one update needs early_bytes = inf)")
-        if (cur["done_hi"] - var.offset) * 4 < self.early_bytes:
+        seg = next((s for s in cur["segs"] if s[0] <= var.offset < s[1]), None)
+        if seg is None:
+            # not inside the unreduced part of any segment: either another optimiser's variable, or one whose bucket is gone
+            b, e = cur["optim"].range()
+            if b <= var.offset < e:
+                raise RuntimeError(f"{var.name}: a gradient was produced after its bucket had been all-reduced "
+                                   "(a filter used at two call sites of one update needs early_bytes = inf)")
             return
-        self._issue(var.offset, cur["done_hi"], (producer_stream,) if producer_stream is not None else ())
-        cur["done_hi"] = var.offset
+        if (seg[1] - var.offset) * 4 < self.early_bytes:
+            return
+        self._issue(var.offset, seg[1], (producer_stream,) if producer_stream is not None else ())
+        seg[1] = var.offset
 
     def allreduce(self, optim):
         """Sum-all-reduce the gradient range of `optim`'s group (what begin_update's early buckets have not covered yet)
@@ -111,10 +126,17 @@ class DataParallel:
         ops.GRAD_READY_HOOK = None
         cur = getattr(self, "_cur", None)
         if cur is None or cur["optim"] is not optim:
-            b, e = optim.range()
-            cur = self._cur = dict(optim=optim, lo=b, done_hi=e, issued=[])
-        if cur["done_hi"] > cur["lo"]:
-            self._issue(cur["lo"], cur["done_hi"])
+            cur = self._cur = dict(optim=optim, segs=self._segments(optim), issued=[])
+        # the unreduced heads; adjacent ones (a tuple group with no early bucket in between) go out as one range
+        heads = [(lo, hi) for lo, hi in cur["segs"] if hi > lo]
+        merged = []
+        for lo, hi in heads:
+            if merged and merged[-1][1] == lo:
+                merged[-1] = (merged[-1][0], hi)
+            else:
+                merged.append((lo, hi))
+        for lo, hi in merged:
+            self._issue(lo, hi)
         comm = self._comm()
         if comm is not False:
             torch.cuda.current_stream().wait_stream(comm)
@@ -126,6 +148,8 @@ class DataParallel:
         if self.world_size <= 1:
             return
         dist.broadcast(store.flat["params"], src=0)
+        for v in store.vars.values():
+            v.version += 1                          # bf16 copies of the filters are re-cast at their next use
 
     def shard(self, n_items):
         """Contiguous shard [lo, hi) of a global batch of n_items clips/frames for this rank."""

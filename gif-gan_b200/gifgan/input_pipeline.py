@@ -20,10 +20,70 @@ from __future__ import annotations
 
 import queue
 import threading
+import weakref
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
+
+
+class _Shared(object):
+    """Everything the producer thread and the decode workers touch.  They hold THIS object, never the Prefetcher, so that
+    dropping the iterator mid-epoch lets it be collected -- its finalizer then stops the threads and releases the ring."""
+
+    def __init__(self, batches, load_item, item_shape, depth, workers, pin):
+        self.batches, self.load_item, self.item_shape, self.depth = batches, load_item, item_shape, depth
+        rows = max((len(b) for b in batches), default=0)
+        self.ring = [torch.empty((rows,) + item_shape, dtype=torch.float32) for _ in range(depth + 3)]
+        if pin:
+            self.ring = [t.pin_memory() for t in self.ring]
+        self.free = queue.Queue()
+        for i in range(len(self.ring)):
+            self.free.put(i)
+        self.ready = queue.Queue(maxsize=depth)
+        self.stop = threading.Event()
+        self.pool = ThreadPoolExecutor(max_workers=max(1, int(workers)), thread_name_prefix="gifgan-decode")
+        self.max_ahead = 0                    # diagnostics: how far the producer ever was ahead of the consumer
+        self.consumed = 0
+
+    def fill(self, buf, row, item):
+        buf[row].copy_(torch.from_numpy(np.ascontiguousarray(self.load_item(item), dtype=np.float32).reshape(self.item_shape)))
+
+    def take_free(self):
+        while not self.stop.is_set():
+            try:
+                return self.free.get(timeout=0.05)
+            except queue.Empty:
+                continue
+        return None
+
+    def shutdown(self):
+        self.stop.set()
+        self.pool.shutdown(wait=False, cancel_futures=True)
+
+
+def _produce(sh: _Shared):
+    for k, items in enumerate(sh.batches):
+        slot = sh.take_free()
+        if slot is None:
+            return
+        buf = sh.ring[slot]
+        err = None
+        try:
+            futures = [sh.pool.submit(sh.fill, buf, r, it) for r, it in enumerate(items)]
+            for f in futures:
+                f.result()
+        except BaseException as e:        # delivered to the consumer in batch order
+            err = e
+        sh.max_ahead = max(sh.max_ahead, k + 1 - sh.consumed)
+        while not sh.stop.is_set():
+            try:
+                sh.ready.put((slot, len(items), err), timeout=0.05)
+                break
+            except queue.Full:
+                continue
+        if err is not None or sh.stop.is_set():
+            return
 
 
 class Prefetcher(object):
@@ -33,89 +93,43 @@ class Prefetcher(object):
         self.batches = list(batches)
         self.load_item, self.item_shape = load_item, tuple(item_shape)
         self.depth = max(1, int(depth))
-        rows = max((len(b) for b in self.batches), default=0)
         pin = torch.cuda.is_available() if pin is None else pin
-        self._ring = [torch.empty((rows,) + self.item_shape, dtype=torch.float32) for _ in range(self.depth + 3)]
-        if pin:
-            self._ring = [t.pin_memory() for t in self._ring]
-        self._free = queue.Queue()
-        for i in range(len(self._ring)):
-            self._free.put(i)
-        self._ready = queue.Queue(maxsize=self.depth)
-        self._stop = threading.Event()
-        self._pool = ThreadPoolExecutor(max_workers=max(1, int(workers)), thread_name_prefix="gifgan-decode")
+        self._sh = sh = _Shared(self.batches, load_item, self.item_shape, self.depth, workers, pin)
+        self._ring = sh.ring
         self._held = []                       # buffers the consumer may still be reading (newest last)
-        self.max_ahead = 0                    # diagnostics: how far the producer ever was ahead of the consumer
-        self._consumed = 0
-        self._producer = threading.Thread(target=self._produce, name="gifgan-prefetch", daemon=True)
+        self._producer = threading.Thread(target=_produce, args=(sh,), name="gifgan-prefetch", daemon=True)
         self._producer.start()
+        self._finalizer = weakref.finalize(self, _Shared.shutdown, sh)     # runs when the Prefetcher is collected (or at exit)
 
-    # ---- producer thread ---------------------------------------------------------------------------
-    def _fill(self, buf, row, item):
-        buf[row].copy_(torch.from_numpy(np.ascontiguousarray(self.load_item(item), dtype=np.float32).reshape(self.item_shape)))
-
-    def _take_free(self):
-        while not self._stop.is_set():
-            try:
-                return self._free.get(timeout=0.05)
-            except queue.Empty:
-                continue
-        return None
-
-    def _produce(self):
-        for k, items in enumerate(self.batches):
-            slot = self._take_free()
-            if slot is None:
-                return
-            buf = self._ring[slot]
-            err = None
-            try:
-                futures = [self._pool.submit(self._fill, buf, r, it) for r, it in enumerate(items)]
-                for f in futures:
-                    f.result()
-            except BaseException as e:        # delivered to the consumer in batch order
-                err = e
-            self.max_ahead = max(self.max_ahead, k + 1 - self._consumed)
-            while not self._stop.is_set():
-                try:
-                    self._ready.put((slot, len(items), err), timeout=0.05)
-                    break
-                except queue.Full:
-                    continue
-            if err is not None or self._stop.is_set():
-                return
+    @property
+    def max_ahead(self):
+        return self._sh.max_ahead
 
     # ---- consumer ---------------------------------------------------------------------------------
     def __iter__(self):
         return self
 
     def __next__(self):
-        if self._consumed >= len(self.batches):
+        sh = self._sh
+        if sh.consumed >= len(self.batches):
             self.close()
             raise StopIteration
         # the batch handed out two calls ago is no longer in use: its step has synchronised before this call
         while len(self._held) >= 2:
-            self._free.put(self._held.pop(0))
-        slot, n, err = self._ready.get()
-        self._consumed += 1
+            sh.free.put(self._held.pop(0))
+        slot, n, err = sh.ready.get()
+        sh.consumed += 1
         if err is not None:
             self.close()
             raise err
         self._held.append(slot)
-        return self._ring[slot][:n]
+        return sh.ring[slot][:n]
 
     def __len__(self):
         return len(self.batches)
 
     def close(self):
-        self._stop.set()
-        self._pool.shutdown(wait=False, cancel_futures=True)
-
-    def __del__(self):                       # a consumer that walks away mid-epoch must not leave the producer spinning
-        try:
-            self.close()
-        except Exception:
-            pass
+        self._finalizer()                    # idempotent: stop event + pool shutdown
 
     def __enter__(self):
         return self

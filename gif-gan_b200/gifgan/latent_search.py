@@ -117,7 +117,7 @@ class LatentSearch(object):
     def _step_device(self, target_images, target_activations, lr):
         roots = self.loss_and_grad(target_images, target_activations)
         z = self.z.detach()
-        ops.check(ops.cabi.lib().gg_adam_graph(ops.ptr(z), ops.ptr(self.z.grad), ops.ptr(self.m), ops.ptr(self.v), z.numel(),
+        ops.check(ops.cabi.lib().gg_adam_graph(ops.ptr(z), None, ops.ptr(self.z.grad), ops.ptr(self.m), ops.ptr(self.v), z.numel(),
                                                ops.ptr(self.state), float(lr), self.beta1, self.beta2, self.epsilon, 1.0, ops.stream()),
                   "gg_adam_graph")
         ops.cabi.gather_scalars(roots, self._loss_vec)
@@ -241,7 +241,7 @@ def load_dcgan(opts, batch_size):
         if checkpoint_io.tf_format(path):                      # a TensorFlow checkpoint (V2 bundle or V1 file)
             checkpoint_io.load_tf_checkpoint(path, dcgan.store, (dcgan.d_optim, dcgan.g_optim))
         else:
-            dcgan.load_payload(torch.load(path, map_location="cpu", weights_only=False))
+            dcgan.load_payload(torch.load(path, map_location="cpu", weights_only=True))
     elif not opts.synthetic:
         raise ValueError("--checkpoint_directory is required (or --synthetic n to run on random weights and targets)")
     return dcgan

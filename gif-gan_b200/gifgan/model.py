@@ -323,8 +323,7 @@ class DCGAN(object):
         if use_graph:
             key = (B, evals, batch_labels is not None)
             g = self._graph if (self._graph is not None and self._graph["key"] == key) else self._capture(st, evals, key)
-            if ops.PACK_BATCH:
-                ops.refresh_packs(self.store)  # no-op unless weights were changed from outside (checkpoint load)
+            ops.refresh_packs(self.store)      # no-op unless weights were changed from outside (checkpoint load)
             g["graph"].replay()
             self.d_optim.t += 1
             self.g_optim.t += 2
@@ -363,9 +362,8 @@ class DCGAN(object):
             self.d_optim.state.copy_(states[0]); self.g_optim.state.copy_(states[1])
             self.d_optim.t, self.g_optim.t = states[2], states[3]
             for v in self.store.vars.values():
-                v.invalidate_packed()          # every replay starts with stale bf16 filter copies ...
-            if ops.PACK_BATCH:
-                ops.refresh_packs(self.store)  # ... or with current ones when each update re-packs its group in one launch
+                v.invalidate_packed()
+            ops.refresh_packs(self.store)      # the captured step is entered with current bf16 copies (Adam keeps them current inside it)
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -514,5 +512,5 @@ class DCGAN(object):
         if checkpoint_io.tf_format(os.path.join(checkpoint_dir, name)):        # written by TensorFlow (or checkpoint_io): V2 bundle / V1 file
             checkpoint_io.load_tf_checkpoint(os.path.join(checkpoint_dir, name), self.store, (self.d_optim, self.g_optim))
             return True
-        self.load_payload(torch.load(os.path.join(checkpoint_dir, name), map_location="cpu", weights_only=False))
+        self.load_payload(torch.load(os.path.join(checkpoint_dir, name), map_location="cpu", weights_only=True))
         return True

@@ -80,8 +80,8 @@ class Var:
         self.grad = None
         self.filter_taps = filter_taps      # not None for conv/deconv/conv3d filters [taps..., C, K]
         self.version = 0
-        self._packed = None
-        self._packed_version = -1
+        self._bf16 = None          # bf16 copy (a view into the store's shadow buffer after finalize)
+        self._bf16_version = -1
 
     @property
     def shape(self):
@@ -90,50 +90,31 @@ class Var:
     def numel(self):
         return self.data.numel()
 
-    def packed(self):
-        """bf16 copies (w_ck, w_kc) for the tensor-core kernels, refreshed after each update."""
-        if self._packed is None:
-            self._packed = (torch.empty(self.data.shape, dtype=torch.bfloat16, device=self.data.device),
-                            torch.empty(self.data.shape, dtype=torch.bfloat16, device=self.data.device))
-        if self._packed_version != self.version:
-            C_, K_ = self.data.shape[-2], self.data.shape[-1]
-            taps = self.data.numel() // (C_ * K_)
-            check(cabi.lib().gg_pack_filter(ptr(self.data), ptr(self._packed[0]), ptr(self._packed[1]), taps, C_, K_, stream()),
-                  "gg_pack_filter")
-            self._packed_version = self.version
-        return self._packed
+    def bf16(self):
+        """bf16 copy of the variable, same layout -- the filter operand of the tensor-core kernels (conv_up reads it K-major,
+        conv_down MN-major, the class-concatenated conv_up one box per class: no transposed / re-packed copies exist).
+        After VariableStore.finalize it is a view into the store's bf16 shadow of the flat parameter buffer, which the
+        fused Adam launch rewrites together with the fp32 masters (AdamOptimizer.apply), so a train step carries no
+        re-pack launch; anything else that changes the variable bumps `version` and the copy is re-cast at its next use."""
+        if self._bf16 is None:
+            self._bf16 = torch.empty(self.data.shape, dtype=torch.bfloat16, device=self.data.device)
+            self._bf16_version = -1
+        if self._bf16_version != self.version:
+            check(cabi.lib().gg_cast(ptr(self.data), cabi.GG_F32, ptr(self._bf16), cabi.GG_BF16, self.data.numel(), stream()), "gg_cast")
+            self._bf16_version = self.version
+        return self._bf16
 
     def packs_stale(self):
-        return ((self._packed is not None and self._packed_version != self.version)
-                or (getattr(self, "_upcat", None) is not None and self._upcat_version != self.version))
+        return self._bf16 is not None and self._bf16_version != self.version
 
     def refresh_packs(self):
-        """Rebuild whichever bf16 copies exist and are stale (per-filter launches)."""
-        if self._packed is not None:
-            self.packed()
-        if getattr(self, "_upcat", None) is not None:
-            self.packed_upcat(self._upcat_desc)
+        """Re-cast the bf16 copy if it exists and is stale."""
+        if self._bf16 is not None:
+            self.bf16()
 
     def invalidate_packed(self):
-        """Force the bf16 copies to be rebuilt at their next use (CUDA-graph capture: every replay must repack)."""
-        self._packed_version = -1
-        self._upcat_version = -1
-
-    def packed_upcat(self, desc):
-        """bf16 filter with the output parity classes concatenated along N (gg_pack_filter_upcat), or None when the
-        shape is not eligible; refreshed after each update like packed()."""
-        L = cabi.lib()
-        nbytes = L.gg_upcat_bytes(ctypes.byref(desc))
-        if nbytes == 0:
-            return None
-        if getattr(self, "_upcat", None) is None or self._upcat.numel() * 2 != nbytes:
-            self._upcat = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=self.data.device)
-            self._upcat_version = -1
-            self._upcat_desc = cabi.ConvDesc.from_buffer_copy(desc)     # geometry for the batched re-pack (AdamOptimizer.repack)
-        if self._upcat_version != self.version:
-            check(L.gg_pack_filter_upcat(ctypes.byref(desc), ptr(self.data), ptr(self._upcat), stream()), "gg_pack_filter_upcat")
-            self._upcat_version = self.version
-        return self._upcat
+        """Force the bf16 copy to be rebuilt at its next use."""
+        self._bf16_version = -1
 
 
 class VariableStore:
@@ -157,9 +138,11 @@ class VariableStore:
         it was built under, so its methods find their variables wherever they are called from."""
         saved = self._scope
         self._scope = [p for p in prefix.split("/") if p]
+        _ACTIVE.append(self)              # variable_scope / get_variable inside resolve to THIS store
         try:
             yield self
         finally:
+            _ACTIVE.pop()
             self._scope = saved
 
     # -- creation -------------------------------------------------------------------
@@ -193,15 +176,18 @@ class VariableStore:
                     raise ValueError(f"{v.name} is in two optimiser groups")
                 seen.add(v.name)
                 ordered.append((v, off))
-                off += (v.numel() + 3) // 4 * 4
+                off += (v.numel() + 63) // 64 * 64       # 64-element granules: every variable starts on a 128-byte line in the bf16
+                                                         # shadow (TMA box rows of the filter operand = whole lines) and on 256 bytes
+                                                         # in the fp32 buffers (the filter-gradient TMA reduce-adds)
             self.ranges[gname] = (beg, off)
         for v in self.vars.values():
             if v.name not in seen:
                 ordered.append((v, off))
-                off += (v.numel() + 3) // 4 * 4
+                off += (v.numel() + 63) // 64 * 64
         total = off
         dev = self.device
         params = torch.zeros(total, dtype=torch.float32, device=dev)
+        shadow = torch.zeros(total, dtype=torch.bfloat16, device=dev)    # bf16 copy of `params`, kept current by Adam (Var.bf16)
         grads = torch.zeros(total, dtype=torch.float32, device=dev)
         trainable_end = max([e for _, e in self.ranges.values()], default=0)
         m = torch.zeros(trainable_end, dtype=torch.float32, device=dev)
@@ -214,7 +200,9 @@ class VariableStore:
             v.grad = grads[o:o + n].view(shape)
             v.offset = o
             v.version += 1
+            v._bf16, v._bf16_version = shadow[o:o + n].view(shape), -1
         self.flat = dict(params=params, grads=grads, m=m, v=v2)
+        self.shadow = shadow
 
     # -- checkpoint (keys = TF variable names) -------------------------
     def state_dict(self):
@@ -238,6 +226,7 @@ class VariableStore:
 
 _STORE = VariableStore.__new__(VariableStore)  # replaced by reset_default_store()
 _STORE_READY = False
+_ACTIVE: list = []        # stack of stores entered with use_store() / VariableStore.absolute_scope(); empty -> the default store
 
 
 def reset_default_store(device=None, seed=0) -> VariableStore:
@@ -254,11 +243,27 @@ def default_store() -> VariableStore:
     return _STORE
 
 
+def current_store() -> VariableStore:
+    """The store that variable_scope / the op constructors create variables in: the innermost use_store() /
+    absolute_scope() region, else the default store."""
+    return _ACTIVE[-1] if _ACTIVE else default_store()
+
+
+@contextlib.contextmanager
+def use_store(store: VariableStore):
+    """Make `store` the one the operator layer creates its variables in (a model built with `store=`)."""
+    _ACTIVE.append(store)
+    try:
+        yield store
+    finally:
+        _ACTIVE.pop()
+
+
 @contextlib.contextmanager
 def variable_scope(name, reuse=None):
     """tf.variable_scope(name).  Reuse is automatic: get_variable returns the existing
     variable of that name (the reference always calls reuse_variables() before a second use)."""
-    st = default_store()
+    st = current_store()
     st._scope.append(name)
     try:
         yield st
@@ -410,7 +415,7 @@ def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim,
     small = out if out is not None else torch.empty(g.small_shape(ndim), dtype=out_dtype, device=large.device)
     tc = _tc_ok(g.C, g.K, large)
     d = g.desc(dt(large), dt(small), act, act_param, tc)
-    w = wvar.packed()[1] if tc else wvar.data
+    w = wvar.bf16() if tc else wvar.data
     if stats is not None:
         check(cabi.lib().gg_conv_down_stats(ctypes.byref(d), ptr(large), ptr(w), ptr(bias), ptr(small), ptr(stats), groups, stream()),
               "gg_conv_down_stats")
@@ -423,13 +428,7 @@ def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, o
     large = out if out is not None else torch.empty(g.large_shape(ndim), dtype=out_dtype, device=small.device)
     tc = _tc_ok(g.C, g.K, small)
     d = g.desc(dt(large), dt(small), act, act_param, tc)
-    w = None
-    if tc and UPCAT:
-        w = wvar.packed_upcat(d)          # 64-channel outputs: parity classes concatenated along N (N = 256 MMAs)
-        if w is not None:
-            d.flags |= cabi.CONV_UPCAT
-    if w is None:
-        w = wvar.packed()[0] if tc else wvar.data
+    w = wvar.bf16() if tc else wvar.data
     if stats is not None:
         check(cabi.lib().gg_conv_up_stats(ctypes.byref(d), ptr(small), ptr(w), ptr(bias), ptr(large), ptr(stats), groups, stream()),
               "gg_conv_up_stats")
@@ -441,22 +440,26 @@ def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, o
 # Filter gradients are leaves of the backward pass: nothing downstream of them runs before the optimiser.  They are
 # issued on a side stream so that they overlap with the activation-gradient chain (under CUDA-graph capture the
 # fork/join becomes parallel branches of the graph).  join_side() is the join point (optimiser / all-reduce).
-PACK_BATCH = os.environ.get("GG_PACK_BATCH", "1") != "0"   # one re-pack launch per optimiser update (AdamOptimizer.repack); 0: per filter, at first use
-
-
 def refresh_packs(store):
-    """Bring every existing bf16 filter copy up to date (eager, per filter).  With PACK_BATCH a captured train step
-    assumes current copies on entry -- it re-packs right after each update -- so this runs after anything that changes
-    weights behind the optimisers' back: the restore around graph capture, a checkpoint load."""
-    n = 0
-    for v in store.vars.values():
-        if v.packs_stale():
+    """Bring the bf16 filter copies up to date.  A captured train step assumes current copies on entry -- Adam rewrites the
+    bf16 shadow of its group inside the step -- so this runs after anything that changes weights behind the optimisers'
+    back: the restore around graph capture, a checkpoint load.  With a finalized store ONE cast over the flat buffer
+    refreshes every variable; otherwise one cast per stale variable."""
+    stale = [v for v in store.vars.values() if v.packs_stale()]
+    if not stale:
+        return 0
+    sh = getattr(store, "shadow", None)
+    if sh is not None and store.flat is not None:
+        check(cabi.lib().gg_cast(ptr(store.flat["params"]), cabi.GG_F32, ptr(sh), cabi.GG_BF16, sh.numel(), stream()), "gg_cast")
+        for v in store.vars.values():
+            if v._bf16 is not None:
+                v._bf16_version = v.version
+    else:
+        for v in stale:
             v.refresh_packs()
-            n += 1
-    return n
+    return len(stale)
 
 
-UPCAT = os.environ.get("GG_UPCAT", "1") != "0"     # class-concatenated conv_up for 64-channel outputs (tc_conv_up_cat)
 OVERLAP_WGRAD = False      # enabled inside `with overlap_wgrad():` (the model's update functions)
 GRAD_READY_HOOK = None     # data parallel: called as hook(var, producer_stream) after a filter gradient was enqueued (dp.py)
 _SIDE = {}
@@ -1158,43 +1161,11 @@ class AdamOptimizer:
         self.t += 1
         b, e = self.range()
         f = self.store.flat
-        check(cabi.lib().gg_adam_graph(ptr(f["params"][b:e]), ptr(f["grads"][b:e]), ptr(f["m"][b:e]), ptr(f["v"][b:e]), e - b,
-                                       ptr(self.state), self.lr, self.b1, self.b2, self.eps, grad_scale, stream()), "gg_adam_graph")
+        sh = getattr(self.store, "shadow", None)
+        check(cabi.lib().gg_adam_graph(ptr(f["params"][b:e]), ptr(sh[b:e]) if sh is not None else None, ptr(f["grads"][b:e]), ptr(f["m"][b:e]),
+                                       ptr(f["v"][b:e]), e - b, ptr(self.state), self.lr, self.b1, self.b2, self.eps, grad_scale, stream()),
+              "gg_adam_graph")
         for v in self.var_list or []:
             v.version += 1
-        if PACK_BATCH:
-            self.repack()
-
-    def repack(self):
-        """Refresh the bf16 copies of every tensor-core filter of the var_list with ONE launch (gg_pack_filters) and
-        mark them current, so that a train step carries one re-pack launch per update instead of one or two per
-        filter.  Filters join the plan once their copies exist (first use); the device job table is uploaded outside
-        stream capture only -- a capture that meets a new table falls back to the per-filter packs at first use."""
-        vs = [v for v in (self.var_list or []) if v._packed is not None or getattr(v, "_upcat", None) is not None]
-        if not vs:
-            return False
-        sig = tuple((v.data.data_ptr(), v._packed[0].data_ptr() if v._packed is not None else 0,
-                     v._upcat.data_ptr() if getattr(v, "_upcat", None) is not None else 0) for v in vs)
-        plan = getattr(self, "_pack_plan", None)
-        upload = plan is None or plan["sig"] != sig
-        L = cabi.lib()
-        if upload:
-            if torch.cuda.is_current_stream_capturing():
-                return False
-            jobs = (cabi.PackJob * len(vs))()
-            for j, v in zip(jobs, vs):
-                C_, K_ = v.data.shape[-2], v.data.shape[-1]
-                j.w, j.taps, j.C, j.K = v.data.data_ptr(), v.data.numel() // (C_ * K_), C_, K_
-                if v._packed is not None:
-                    j.w_ck, j.w_kc = v._packed[0].data_ptr(), v._packed[1].data_ptr()
-                if getattr(v, "_upcat", None) is not None:
-                    j.w_cat, j.cat_desc = v._upcat.data_ptr(), v._upcat_desc
-            dev = torch.empty(L.gg_pack_plan_bytes(len(vs)), dtype=torch.uint8, device=self.store.device)
-            plan = self._pack_plan = dict(sig=sig, jobs=jobs, dev=dev, vars=vs)
-        check(L.gg_pack_filters(plan["jobs"], len(vs), ptr(plan["dev"]), plan["dev"].numel(), 1 if upload else 0, stream()), "gg_pack_filters")
-        for v in vs:
-            if v._packed is not None:
-                v._packed_version = v.version
-            if getattr(v, "_upcat", None) is not None:
-                v._upcat_version = v.version
-        return True
+            if sh is not None and v._bf16 is not None:
+                v._bf16_version = v.version          # the same launch rewrote the bf16 shadow of the whole range

@@ -282,8 +282,7 @@ class VID_DCGAN(object):
             g = self._graphs.get(key)
             if g is None:
                 g = self._graphs[key] = self._capture(args)
-            if ops.PACK_BATCH:
-                ops.refresh_packs(self.store)
+            ops.refresh_packs(self.store)
             g["graph"].replay()
             self.d_optim.t += disc_updates
             self.g_optim.t += gen_updates
@@ -306,8 +305,7 @@ class VID_DCGAN(object):
             self.d_optim.t, self.g_optim.t = states[2], states[3]
             for v in self.store.vars.values():
                 v.invalidate_packed()
-            if ops.PACK_BATCH:
-                ops.refresh_packs(self.store)
+            ops.refresh_packs(self.store)
 
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -452,7 +450,7 @@ class VID_DCGAN(object):
         if checkpoint_io.tf_format(path):                      # a TensorFlow checkpoint of the image GAN
             checkpoint_io.load_tf_checkpoint(path, self.store, prefix=self.image_gan_scope_name)
         else:
-            payload = torch.load(path, map_location="cpu", weights_only=False)
+            payload = torch.load(path, map_location="cpu", weights_only=True)
             self.store.load_state_dict(payload["variables"], strict=True, prefix=self.image_gan_scope_name)
         print("Success!")
         return True
@@ -467,7 +465,7 @@ class VID_DCGAN(object):
         if checkpoint_io.tf_format(path):
             checkpoint_io.load_tf_checkpoint(path, self.store)
         else:
-            payload = torch.load(path, map_location="cpu", weights_only=False)
+            payload = torch.load(path, map_location="cpu", weights_only=True)
             self.store.load_state_dict(payload["variables"])
         print("Success!")
         return True

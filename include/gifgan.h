@@ -72,9 +72,8 @@ typedef struct gg_conv_desc {
 } gg_conv_desc;
 
 #define GG_CONV_ACCUMULATE 1 /* wgrad: dw += (default for wgrad; dw must be initialised) */
-#define GG_CONV_TENSOR_CORE 2 /* use the tcgen05 bf16 path: both dtypes BF16, packed bf16 weights */
-#define GG_CONV_UPCAT 4       /* gg_conv_up only, with GG_CONV_TENSOR_CORE: `w` is the buffer written by gg_pack_filter_upcat
-                               * (output parity classes concatenated along N; eligible when gg_upcat_bytes(desc) > 0) */
+#define GG_CONV_TENSOR_CORE 2 /* use the tcgen05 path: bf16 operand activations, `w` = the bf16 copy of the filter
+                               * (same [taps,C,K] layout as the fp32 master; gg_cast or the shadow kept by gg_adam*) */
 
 int gg_version(void);
 const char* gg_last_error(void);
@@ -83,7 +82,10 @@ int gg_device_arch(void);
 
 /* ---- the three contractions of a strided-conv relation -------------------------------
  * SIMT fp32-accumulate path: w, bias, dw are fp32.  Tensor-core path
- * (GG_CONV_TENSOR_CORE): w_packed are the bf16 copies written by gg_pack_filter.        */
+ * (GG_CONV_TENSOR_CORE): w is the bf16 copy of the SAME [taps,C,K] array -- no transposed or
+ * re-packed filter exists; the kernels read it K-major (conv_up) or MN-major (conv_down)
+ * through TMA tensor maps, and conv_up with 4 stride classes x 64 channels assembles its
+ * N = 256 class-concatenated tile from four boxes of it.                                 */
 
 /* small[o,k] = act( sum_{t,c} large[s*o+t-p, c] * w[t,c,k] + bias[k] )
  * replaces tf.nn.conv2d + bias_add (ops.py:57-60), tf.nn.conv3d (ops.py:70-73), and the
@@ -121,31 +123,6 @@ int gg_deconv2d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, floa
 int gg_conv3d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* stream);     /* ops.py:70  */
 int gg_conv3d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* stream);
 int gg_conv3d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
-
-/* fp32 filter [taps,C,K] -> bf16 copies for the tensor-core path:
- *   w_ck [taps,C,K] (K contiguous: B operand of conv_up) and w_kc [taps,K,C] (B operand of conv_down). */
-int gg_pack_filter(const float* w, void* w_ck, void* w_kc, int32_t taps, int32_t C, int32_t K, void* stream);
-/* conv_up (deconv2d forward / conv2d dgrad, ops.py:86) whose stride classes x C == 256 (DCGAN: stride 2x2, C = 64): bytes of,
- * and packing into, the class-concatenated bf16 filter [shifts][classes*C][K]; 0 bytes = shape not eligible. */
-size_t gg_upcat_bytes(const gg_conv_desc* d);
-int gg_pack_filter_upcat(const gg_conv_desc* d, const float* w, void* wcat, void* stream);
-
-/* All tensor-core filters of one optimiser group re-packed by ONE launch (after the Adam step that changed them).
- * A job names the fp32 filter [taps,C,K] and the copies to refresh: w_ck / w_kc as gg_pack_filter (C, K multiples of 64;
- * both may be NULL) and w_cat as gg_pack_filter_upcat for the relation `cat_desc` (NULL: none).  `plan` is a device
- * buffer of gg_pack_plan_bytes(njobs) bytes owned by the caller; upload != 0 (re)writes it from `jobs` with a host->device
- * copy -- call that way once, outside stream capture, and whenever a pointer changes; upload == 0 only launches. */
-typedef struct gg_pack_job {
-  const float* w;
-  void* w_ck;
-  void* w_kc;
-  void* w_cat;
-  int32_t taps, C, K;
-  int32_t reserved;
-  gg_conv_desc cat_desc;
-} gg_pack_job;
-size_t gg_pack_plan_bytes(int32_t njobs);
-int gg_pack_filters(const gg_pack_job* jobs, int32_t njobs, void* plan, size_t plan_bytes, int32_t upload, void* stream);
 
 /* ---- linear (ops.py:106-117: tf.matmul(input_, Matrix) + bias) ---------------------- */
 int gg_linear_fwd(const void* x, int32_t x_dtype, const float* matrix, const float* bias, void* y, int32_t y_dtype,
@@ -228,13 +205,15 @@ int gg_distance_loss(const void* a, int32_t a_dtype, const float* target, int64_
 /* ---- optimiser (model.py:153-156: tf.train.AdamOptimizer(lr, beta1).minimize) -------
  * TF semantics: p -= lr_t * m / (sqrt(v) + eps) with lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
  * computed by the caller.  One launch over a flat fp32 parameter group.
- * grad_scale multiplies g first (1/world_size after a sum all-reduce).                  */
-int gg_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
+ * grad_scale multiplies g first (1/world_size after a sum all-reduce).
+ * p_bf16 (may be NULL): bf16 shadow of p, rewritten in the same pass -- the filter operand of
+ * the tensor-core kernels, so no separate re-pack launch follows an update.              */
+int gg_adam(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
             float grad_scale, void* stream);
 
 /* CUDA-graph-friendly variant: the step counter lives on the device.  state[0] = t (int32, advanced
  * by this call), state[1] = lr_t (float bits) = lr*sqrt(1-b2^t)/(1-b1^t) recomputed on the device.    */
-int gg_adam_graph(float* p, const float* g, float* m, float* v, int64_t n, int32_t* state, float lr, float beta1, float beta2,
+int gg_adam_graph(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, int32_t* state, float lr, float beta1, float beta2,
                   float eps, float grad_scale, void* stream);
 
 /* ---- BasicLSTMCell (recurrent_DCGAN.py:199-200) --------------------------------------

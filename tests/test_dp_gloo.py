@@ -66,6 +66,25 @@ def _worker(rank, world, port, out_dir):
     except RuntimeError:
         pass
     dp.allreduce(opt_d)
+    # a tuple var_list (VID_DCGAN with --train_img_disc: ("dvideo", "d_img")): the first group of the layout is ALSO the first
+    # one backward produces, so a finished tail is a per-group notion -- the early bucket of the first group must not
+    # take the second group's (still unwritten) gradients with it, and the later gradients must not raise
+    st2 = ops.VariableStore(device="cpu", seed=rank)
+    v1 = st2.get_variable("dvideo_a", [64], lambda r, s: np.zeros(s, dtype=np.float32))
+    v2 = st2.get_variable("dvideo_b", [64], lambda r, s: np.zeros(s, dtype=np.float32))
+    i1 = st2.get_variable("d_img_a", [64], lambda r, s: np.zeros(s, dtype=np.float32))
+    i2 = st2.get_variable("d_img_b", [64], lambda r, s: np.zeros(s, dtype=np.float32))
+    st2.finalize(OrderedDict(dvideo=[v1, v2], d_img=[i1, i2]))
+    opt = ops.AdamOptimizer(st2, ("dvideo", "d_img"))
+    dp.early_bytes = 100
+    dp.begin_update(opt)
+    for var, val in ((v2, 1.0), (v1, 2.0), (i2, 3.0), (i1, 4.0)):          # backward order: video D first, image D last
+        var.grad.fill_(val * (rank + 1))
+        dp.grad_ready(var)
+    dp.allreduce(opt)
+    for var, val in ((v2, 1.0), (v1, 2.0), (i2, 3.0), (i1, 4.0)):
+        assert torch.all(var.grad == val * 3.0), (var.name, var.grad[:3])   # each reduced exactly once: (1 + 2) * val
+    assert sorted(dp.last_buckets) == sorted([(v2.offset, v2.offset + 64), (v1.offset, v2.offset), (i2.offset, i2.offset + 64), (i1.offset, i2.offset)])
     # broadcast: every rank ends with rank 0's variables
     dp.broadcast_parameters(st)
     assert torch.all(c.data == 0.0)

@@ -229,11 +229,35 @@ def test_full_size_config2_single_step(precision):
     want = ora.d_update(torch.tensor(img).double(), torch.tensor(z).double(), apply=False)
     assert abs(losses[0].item() - want["d_loss"]) < tol_loss * max(1, abs(want["d_loss"]))
     check_grads(m, names_d, want["grads"], tol, relerr_l2)
-    gl = m.g_update(torch.tensor(z).cuda(), apply=False)
-    wg = ora.g_update(torch.tensor(z).double(), apply=False)
+    from gifgan import ops
+    ops.DEBUG_TAP, ora.trace = {}, {}
+    try:
+        gl = m.g_update(torch.tensor(z).cuda(), apply=False)
+        wg = ora.g_update(torch.tensor(z).double(), apply=False)
+        tap, trace = ops.DEBUG_TAP, ora.trace
+    finally:
+        ops.DEBUG_TAP, ora.trace = None, None
     assert abs(gl[0].item() - wg["g_loss"]) < tol_loss * max(1, abs(wg["g_loss"]))
     # generator gradients cross all eight normalised layers (D then G): twice the depth, twice the bf16 amplification
     check_grads(m, names_g, wg["grads"], tol if precision == "fp32" else 2 * tol, relerr_l2)
+    # north_star: per-layer ACTIVATIONS within 1e-4 (fp32) / 2e-2 (bf16) at full size, max-norm, every normalised layer of
+    # G and of D(G(z)): the fp32 pre-norm tensor written by the GEMM epilogue and the activation that leaves the fused
+    # node; per-layer activation GRADIENTS in the L2 metric (a mask flip is an O(1) change of single elements)
+    keys = {"g_h0_lin/Matrix": ("g_h0_lin", "g_h0"), "g_h1/w": ("g_h1_deconv", "g_h1"), "g_h2/w": ("g_h2_deconv", "g_h2"),
+            "g_h3/w": ("g_h3_deconv", "g_h3"), "d_h1_conv/w": ("d_fake_h1_conv", "d_fake_h1"),
+            "d_h2_conv/w": ("d_fake_h2_conv", "d_fake_h2"), "d_h3_conv/w": ("d_fake_h3_conv", "d_fake_h3")}
+    atol = 1e-4 if precision == "fp32" else 2e-2
+    seen = set()
+    for name, pre, y in tap["fwd"]:
+        kp, ky = keys[name]
+        assert relerr(pre.reshape(-1), trace[kp].detach().reshape(-1)) < atol, (name, "pre-norm")
+        assert relerr(y.reshape(-1), trace[ky].detach().reshape(-1)) < atol, (name, "activation")
+        seen.add(name)
+    assert seen == set(keys)
+    for name, dy, dpre in tap["bwd"]:
+        kp, ky = keys[name]
+        assert relerr_l2(dy.reshape(-1), trace[ky].grad.reshape(-1)) < (tol if precision == "fp32" else 2 * tol), (name, "d activation")
+        assert relerr_l2(dpre.reshape(-1), trace[kp].grad.reshape(-1)) < (tol if precision == "fp32" else 2 * tol), (name, "d pre-norm")
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

@@ -141,13 +141,17 @@ def test_tc_adjointness_full_batch():
     from gifgan import ops as _o
     B, H, Ci, Co = 128, 16, 128, 256
     ops, st, tv = _store(lambda t: _o.conv2d(t, Co, name="c", bias=False), (B, H, H, Ci))
-    x = torch.randn(B, H, H, Ci, device="cuda").to(torch.bfloat16).requires_grad_(True)
-    dy = torch.randn(B, H // 2, H // 2, Co, device="cuda").to(torch.bfloat16)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(B, H, H, Ci, device="cuda", generator=gen).to(torch.bfloat16).requires_grad_(True)
+    dy = torch.randn(B, H // 2, H // 2, Co, device="cuda", generator=gen).to(torch.bfloat16)
     y = ops.conv2d(x, Co, name="c", bias=False)
     y.backward(dy)
     lhs = (y.float().double() * dy.float().double()).sum().item()
     rhs = (x.detach().float().double() * x.grad.float().double()).sum().item()
-    assert abs(lhs - rhs) < 1e-2 * abs(lhs)
+    # both inner products are zero-mean random sums (|lhs| ~ ||y|| ||dy|| / sqrt(n) can come out small by chance): scale the
+    # tolerance by the Cauchy-Schwarz bound instead of |lhs|; bf16 rounding of y / dx gives ~4e-3 / sqrt(n) of it
+    scale = y.float().double().norm().item() * dy.float().double().norm().item()
+    assert abs(lhs - rhs) < 1e-4 * scale, (lhs, rhs, scale)
 
 
 # ---- image-side layers (3 channels <-> 64k channels): warp-MMA kernels of conv_c3_mma.cu in bf16 mode --------------
@@ -216,92 +220,57 @@ def test_tc_cluster_split_k(splitk, monkeypatch):
         monkeypatch.delenv("GG_TC_SPLITK", raising=False)
 
 
-def test_batched_filter_pack_is_bit_identical():
-    """gg_pack_filters (one launch for all filters of an optimiser group) against gg_pack_filter / gg_pack_filter_upcat
-    per filter: same bits in w_ck, w_kc and the class-concatenated copy; upload=0 replays the device table."""
-    import ctypes
+def test_adam_keeps_the_bf16_shadow_current():
+    """gg_adam_graph(p, p_bf16, ...): the bf16 shadow of the flat parameter buffer -- the filter operand of every tensor-core
+    kernel -- is rewritten by the Adam launch itself and equals the rounded fp32 masters bit for bit."""
     from gifgan import _cabi, ops
     L = _cabi.lib()
-    rs = np.random.RandomState(3)
-    shapes = [(25, 128, 256), (25, 64, 128), (27, 256, 256), (25, 64, 128)]           # (taps, C, K); the last one also gets a cat copy
-    ws = [torch.tensor(rs.randn(*s).astype(np.float32)).cuda() for s in shapes]
-    d = _cabi.ConvDesc()
-    for name, val in dict(N=4, D=1, H=32, W=32, C=64, Do=1, Ho=16, Wo=16, K=128, kd=1, kh=5, kw=5, sd=1, sh=2, sw=2, pd=0, ph=1, pw=1,
-                          large_dtype=1, small_dtype=1, act=0, flags=_cabi.CONV_TENSOR_CORE).items():
-        setattr(d, name, val)
-    cat_elems = L.gg_upcat_bytes(ctypes.byref(d)) // 2
-    assert cat_elems == 9 * 256 * 128
-    want, got = [], []
-    for i, (w, s) in enumerate(zip(ws, shapes)):
-        ck, kc = torch.zeros(s, dtype=torch.bfloat16, device="cuda"), torch.zeros(s, dtype=torch.bfloat16, device="cuda")
-        ops.check(L.gg_pack_filter(ops.ptr(w), ops.ptr(ck), ops.ptr(kc), s[0], s[1], s[2], ops.stream()))
-        want.append([ck, kc])
-        got.append([torch.full(s, 7.0, dtype=torch.bfloat16, device="cuda"), torch.full(s, 7.0, dtype=torch.bfloat16, device="cuda")])
-    cat_want = torch.zeros(cat_elems, dtype=torch.bfloat16, device="cuda")
-    ops.check(L.gg_pack_filter_upcat(ctypes.byref(d), ops.ptr(ws[3]), ops.ptr(cat_want), ops.stream()))
-    cat_got = torch.full((cat_elems,), 7.0, dtype=torch.bfloat16, device="cuda")
-    jobs = (_cabi.PackJob * 4)()
-    for i, (j, w, s) in enumerate(zip(jobs, ws, shapes)):
-        j.w, j.taps, j.C, j.K = w.data_ptr(), s[0], s[1], s[2]
-        j.w_ck, j.w_kc = got[i][0].data_ptr(), got[i][1].data_ptr()
-    jobs[1].w_ck = None                                                                # only the transposed copy wanted
-    jobs[3].w_cat, jobs[3].cat_desc = cat_got.data_ptr(), d
-    plan = torch.empty(L.gg_pack_plan_bytes(4), dtype=torch.uint8, device="cuda")
-    ops.check(L.gg_pack_filters(jobs, 4, ops.ptr(plan), plan.numel(), 1, ops.stream()), "gg_pack_filters")
-
-    def compare():
-        for i in range(4):
-            if i != 1:
-                assert torch.equal(got[i][0], want[i][0]), i
-            assert torch.equal(got[i][1], want[i][1]), i
-        assert torch.equal(got[1][0], torch.full(shapes[1], 7.0, dtype=torch.bfloat16, device="cuda"))     # untouched
-        assert torch.equal(cat_got, cat_want)
-
-    compare()
-    for t in [g for pair in got for g in pair] + [cat_got]:
-        t.fill_(3.0)
-    got[1][0].fill_(7.0)
-    ops.check(L.gg_pack_filters(jobs, 4, ops.ptr(plan), plan.numel(), 0, ops.stream()), "gg_pack_filters")   # replay, no upload
-    compare()
-    assert L.gg_pack_filters(jobs, 4, ops.ptr(plan), 16, 1, ops.stream()) != 0 and b"plan buffer" in L.gg_last_error()
+    n = 100003                                                      # odd tail: the scalar path writes the shadow too
+    rs = np.random.RandomState(5)
+    p = torch.tensor(rs.randn(n + 5).astype(np.float32)).cuda()[:n]
+    g = torch.tensor(rs.randn(n + 5).astype(np.float32)).cuda()[:n]
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    pb = torch.full((n,), 7.0, dtype=torch.bfloat16, device="cuda")
+    state = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        ops.check(L.gg_adam_graph(ops.ptr(p), ops.ptr(pb), ops.ptr(g), ops.ptr(m), ops.ptr(v), n, ops.ptr(state), 2e-4, 0.5, 0.999, 1e-8, 1.0,
+                                  ops.stream()), "gg_adam_graph")
+        assert torch.equal(pb, p.to(torch.bfloat16))
+    assert int(state[0]) == 3
 
 
-def test_train_step_with_batched_repack_equals_per_filter_repack(monkeypatch):
-    """ops.PACK_BATCH (default on; GG_PACK_BATCH=0 switches it off): one re-pack launch per optimiser update, graph
-    entered with current copies -- the trajectory of the captured DCGAN-64 step must be the one of the per-filter packs,
-    with fewer launches."""
+def test_train_step_enters_the_graph_with_current_filter_copies():
+    """No re-pack launches: the captured DCGAN-64 step must follow the eager step (which re-casts stale copies at first
+    use), and a weight change behind the optimisers' back (checkpoint load) must be picked up before the next replay."""
     from gifgan import ops
     from gifgan.model import DCGAN
     B = 8
     img = np.random.RandomState(102).uniform(-1, 1, (B, 64, 64, 3)).astype(np.float32)
     runs = []
-    for batch in (False, True):
-        monkeypatch.setattr(ops, "PACK_BATCH", batch)
+    for graph in (False, True):
         ops.set_precision("bf16")
         ops.reset_default_store(device="cuda", seed=7)
         m = DCGAN(None, batch_size=B, output_size=64, c_dim=3)
         losses = []
         for step in range(3):
             z = np.random.RandomState(1000 + step).uniform(-1, 1, (B, 100)).astype(np.float32)
-            o = m.train_step(img, z, use_graph=True)
+            o = m.train_step(img, z, use_graph=graph)
             losses.append([o["d_loss"], o["g_loss_first"], o["g_loss"]])
-        runs.append((np.array(losses), m.store.flat["params"].clone(), m._graph["launches"]))
-        if batch:
-            # a weight change behind the optimisers' back (checkpoint load) is picked up before the next replay
+            w = m.store.vars["d_h2_conv/w"]
+            assert not w.packs_stale() and torch.equal(w._bf16, w.data.to(torch.bfloat16))       # shadow == rounded masters
+        runs.append(np.array(losses))
+        if graph:
             sd = m.store.state_dict()
             sd["d_h1_conv/w"] = sd["d_h1_conv/w"] * 0.5
             m.store.load_state_dict(sd)
             assert m.store.vars["d_h1_conv/w"].packs_stale()
             m.train_step(img, z, use_graph=True)
-            assert not m.store.vars["d_h1_conv/w"].packs_stale()
-    (l0, p0, n0), (l1, p1, n1) = runs
-    assert n1 <= n0 - 10, (n0, n1)
-    # Same kernels on the same bits -- except that the filter-gradient kernels add their partial sums with fp32
-    # reduce-adds in the order CTAs finish, so even two runs of ONE configuration differ in the last bits
-    # (tools/pack_ab_diag.py) and the randomly initialised GAN amplifies that from step to step.  Step 0: the D loss is
-    # computed before any update (equal), the first G loss after one Adam step of D (last-bit noise only).  A stale
-    # filter copy would show as an O(1) difference there: g_loss_first is ~13.8 with the updated D, ~1 with the old one.
+            w = m.store.vars["d_h1_conv/w"]
+            assert not w.packs_stale() and torch.equal(w._bf16, w.data.to(torch.bfloat16))
+    l0, l1 = runs
+    # Same kernels on the same bits, except that the filter-gradient kernels add their partial sums with fp32 reduce-adds
+    # in CTA-finish order (last-bit differences that the GAN amplifies from step to step).  A stale filter copy would show
+    # as an O(1) difference in step 0: g_loss_first is ~13.8 with the updated D, ~1 with the old one.
     assert abs(l1[0, 0] - l0[0, 0]) <= 1e-6 * abs(l0[0, 0]), (l0, l1)
     assert abs(l1[0, 1] - l0[0, 1]) <= 1e-3 * abs(l0[0, 1]), (l0, l1)
     np.testing.assert_allclose(l1, l0, rtol=0.15, atol=0.02)
-    assert ((p1 - p0).abs() > 1e-3).float().mean().item() < 0.02

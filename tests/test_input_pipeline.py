@@ -111,3 +111,24 @@ def test_vid_dcgan_video_batches_equal_load_videos(tmp_path):
         want = m.load_videos(files[2 * k:2 * k + 2]).astype(np.float32)
         assert tuple(b.shape) == (2, 4, 64, 64, 3)
         assert np.array_equal(b.reshape(-1, 64, 64, 3).numpy(), want)
+
+
+def test_dropping_the_iterator_mid_epoch_stops_the_threads():
+    """The producer and the decode workers hold only the shared state, never the Prefetcher: `del` + gc must stop them."""
+    import gc
+    import threading
+    import time
+    from gifgan.input_pipeline import Prefetcher
+    before = {t.ident for t in threading.enumerate()}
+    pf = Prefetcher([[i] * 2 for i in range(50)], lambda i: np.full((4,), float(i), dtype=np.float32), (4,), depth=2, workers=2, pin=False)
+    assert float(next(pf)[0, 0]) == 0.0
+    prod = pf._producer
+    del pf
+    gc.collect()
+    deadline = time.time() + 5.0
+    while prod.is_alive() and time.time() < deadline:
+        time.sleep(0.05)
+    assert not prod.is_alive()
+    time.sleep(0.2)
+    leftover = [t.name for t in threading.enumerate() if t.ident not in before and t.name.startswith("gifgan-prefetch")]
+    assert not leftover, leftover

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--timeline", action="store_true", help="list every kernel of the middle replay: start, duration, stream, gap")
     a = ap.parse_args()
     from gifgan import ops
     from gifgan.model import DCGAN
@@ -50,6 +51,25 @@ def main():
     print(f"kernels {len(evs)} over {a.steps} replays; sum of kernel time {tot / a.steps:.1f} us/step; wall span {span / a.steps:.1f} us/step")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
         print(f"{k:62s} {n / a.steps:6.1f}/step {t / a.steps:9.1f} us/step {t / n:8.2f} us avg")
+    if a.timeline and evs:
+        per = len(evs) // a.steps
+        mid = evs[per * (a.steps // 2): per * (a.steps // 2 + 1)]
+        t0 = mid[0].time_range.start
+        last_end = {}
+        busy_any = 0.0
+        cur_end = t0
+        print("# timeline of one replay: start_us dur_us gap_same_stream_us stream name")
+        for e in mid:
+            st = getattr(e, "device_index", 0), getattr(e, "stream", None) if hasattr(e, "stream") else None
+            sid = getattr(e, "device_resource_id", None)
+            b, en = e.time_range.start, e.time_range.end
+            gap = b - last_end.get(sid, b)
+            last_end[sid] = en
+            if en > cur_end:
+                busy_any += en - max(b, cur_end)
+                cur_end = en
+            print(f"{b - t0:9.1f} {en - b:7.1f} {gap:7.1f} {str(sid):>4s} {e.name.split('(')[0][-70:]}")
+        print(f"# replay span {mid[-1].time_range.end - t0:.1f} us; time with >= 1 kernel running {busy_any:.1f} us")
 
 
 if __name__ == "__main__":
