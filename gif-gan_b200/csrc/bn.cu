@@ -631,7 +631,8 @@ extern "C" int gg_bn_bwd(const void* x, int32_t x_dt, const void* dy, int32_t dy
   int rc;
   if (need_sums) {
     GG_REQUIRE(ws && ws_bytes >= gg_bn_workspace_bytes(C, groups), GG_ERR_WORKSPACE, "bn_bwd: workspace too small");
-    if (train != 2) cudaMemsetAsync(sums, 0, gg_bn_workspace_bytes(C, groups), st);   // train == 2: the caller zeroed ws (one memset per update for all layers)
+    if (train != 2 && train != 3) cudaMemsetAsync(sums, 0, gg_bn_workspace_bytes(C, groups), st);   // train == 2: the caller zeroed ws (one memset per update for all layers)
+    if (train == 3) goto apply;              // ws already holds the reductions (gg_conv_dgrad_bnbwd produced them with dy)
     if (train && vec_ok && C % 4 == 0) {
       int fused = 0;
       rc = bn_bwd_fused(x, x_dt, dy, dy_dt, dx, dx_dt, rpg, C, groups, gamma, beta, save_mean, save_rstd, sums, dgamma, dbeta, act, act_param, st, &fused);
@@ -647,6 +648,7 @@ extern "C" int gg_bn_bwd(const void* x, int32_t x_dt, const void* dy, int32_t dy
     rc = check_launch("bn_bwd_reduce");
     if (rc) return rc;
   }
+apply:
   const ColGeom g = apply_geom(rpg, C, groups, vec_ok);
   dim3 grid(g.rblocks, g.cblocks, groups);
 #define GG_BA(TX, TD, TO)                                                                                                          \

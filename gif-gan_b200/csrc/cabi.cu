@@ -62,13 +62,25 @@ int c3m_conv_up(const gg_conv_desc*, const void*, const float*, const float*, fl
 int c3m_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t);
 static inline bool c3m_applicable(const gg_conv_desc* d) { return c3_applicable(d) && d->small_dtype == GG_BF16; }
 // tc_tapgemm.cu
-int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
-int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
+}  // namespace gg
+struct gg_bnbwd_args {
+  const float *pre, *mean, *rstd, *gamma, *beta;
+  double* sums;
+  int act;
+  float act_param;
+  int groups;
+};
+namespace gg {
+int tc_conv_down(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr,
+                 const gg_bnbwd_args* bnb = nullptr);
+int tc_conv_up(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr,
+               const gg_bnbwd_args* bnb = nullptr);
 // bn.cu
 int bn_accumulate_stats(const void* x, int x_dt, int64_t rows, int C, int groups, double* sums, cudaStream_t st);
 int tc_conv_wgrad(const gg_conv_desc*, const void*, const void*, float*, cudaStream_t);
 bool tc_upcat_ok(const gg_conv_desc*);
-int tc_conv_up_cat(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr);
+int tc_conv_up_cat(const gg_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t, double* stats = nullptr, int groups = 1, int* fused = nullptr,
+                   const gg_bnbwd_args* bnb = nullptr);
 void tc_set_repeat(int);
 void tc_set_prof(void*);
 }  // namespace gg
@@ -141,6 +153,28 @@ extern "C" int gg_conv_up_stats(const gg_conv_desc* d, const void* small, const 
   if (rc || fused) return rc;
   const int64_t rows = (int64_t)d->N * d->D * d->H * d->W;
   return bn_accumulate_stats(large, d->large_dtype, rows, d->C, groups, stats, (cudaStream_t)stream);
+}
+
+// Input gradient of a conv / deconv whose INPUT came out of a train-mode batch norm (+activation): the launch that produces
+// dy for that batch norm also accumulates its backward reductions (sum g, sum g*xhat per channel and row group) into `sums`
+// from the accumulator registers, so gg_bn_bwd(train = 3) can skip its reduction pass over (pre, dy).  *fused = 1 when the
+// kernel did it (tensor-core path, tiles aligned with the row groups); otherwise only the plain dgrad ran.
+extern "C" int gg_conv_dgrad_bnbwd(const gg_conv_desc* d, int32_t up, const void* dy, const void* w, void* dx, const float* pre,
+                                   const float* save_mean, const float* save_rstd, const float* gamma, const float* beta, int32_t act,
+                                   float act_param, int32_t groups, double* sums, int32_t* fused, void* stream) {
+  GG_REQUIRE(d && dy && w && dx && fused, GG_ERR_INVALID, "conv_dgrad_bnbwd: null pointer");
+  *fused = 0;
+  gg_conv_desc c = *d;
+  c.act = GG_ACT_NONE;
+  if (!(c.flags & GG_CONV_TENSOR_CORE) || !pre || !save_mean || !save_rstd || !sums)
+    return up ? gg_conv_up(&c, dy, w, nullptr, dx, stream) : gg_conv_down(&c, dy, w, nullptr, dx, stream);
+  gg_bnbwd_args b = {pre, save_mean, save_rstd, gamma, beta, sums, act, act_param, groups};
+  int f = 0, rc;
+  if (up && tc_upcat_ok(&c)) rc = tc_conv_up_cat(&c, dy, w, nullptr, dx, (cudaStream_t)stream, nullptr, 1, &f, &b);
+  else if (up) rc = tc_conv_up(&c, dy, w, nullptr, dx, (cudaStream_t)stream, nullptr, 1, &f, &b);
+  else rc = tc_conv_down(&c, dy, w, nullptr, dx, (cudaStream_t)stream, nullptr, 1, &f, &b);
+  *fused = f;
+  return rc;
 }
 
 static gg_conv_desc no_act(const gg_conv_desc* d) { gg_conv_desc c = *d; c.act = GG_ACT_NONE; return c; }

@@ -201,6 +201,24 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Column sums of a 32 x 32 tile held one ROW per lane (a[j] = element (lane, j)): returns, in lane L, the sum over the 32
+// lanes of a[L].  Butterfly transpose-reduce: each round a lane keeps the half of its values whose column bit equals its
+// own lane bit and adds the partner's copy of that half -- 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+// `a` is clobbered.
+__device__ __forceinline__ float warp_transpose_sum32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? a[i] : a[i + half];
+      const float keep = up ? a[i + half] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return a[0];
+}
+
 // ---- replicated fp64 batch-norm accumulators ---------------------------------------------------------
 // Statistics / backward reductions are accumulated with one fp64 atomic per channel per CTA (300-500 CTAs per address).
 // The accumulators can be replicated R times, sums[R][groups][2][C]: a CTA adds to replica (its index mod R), readers

@@ -126,6 +126,18 @@ struct TcPixParams {
   unsigned long long* prof;   // optional per-CTA clock64 breakdown (tools/tc_sweep.py --prof), 8 slots per CTA
   double* stats;              // optional fused batch-norm statistics [groups][2][Nout] (fp32 output only)
   int stats_groups;
+  // Optional fused batch-norm BACKWARD reductions (this launch is the dgrad that produces dy for a train-mode batch norm):
+  // per channel and row group, sum g and sum g*xhat with g = dy * act'(gamma*xhat + beta), xhat = (pre - mean) * rstd --
+  // what colsum_kernel<MODE 1> computes in a separate pass over (pre, dy).  Here dy is still in registers.
+  const float* bnb_pre;       // fp32 pre-norm tensor of the consumer batch norm, same geometry as this launch's output; nullptr = off
+  const float* bnb_mean;      // [groups][statC]
+  const float* bnb_rstd;      // [groups][statC]
+  const float* bnb_gamma;     // [statC] or nullptr
+  const float* bnb_beta;      // [statC] or nullptr
+  double* bnb_sums;           // [groups][2][statC], zeroed by the caller
+  int bnb_act;
+  float bnb_act_param;
+  int8_t cat_o[TC_MAX_CLASSES][4];   // cat: output origin (od0, oh0, ow0) of each parity class
   TcClass cls[TC_MAX_CLASSES];
   TcTap taps[TC_MAX_TAPS];
 };
@@ -323,13 +335,29 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const uint32_t row_off = (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
   const uint32_t mask_smem = bar_base + 8u * (2 * p.stages + 2);        // 4 x u32 after the barriers
+  const uint32_t bnb_consts = mask_smem + 16u;                          // float4 {rstd, -mean*rstd, gamma, beta} per column of the N tile
+  const uint32_t bnb_part = bnb_consts + 16u * (uint32_t)p.BN;          // float [4 warps][2][BN]: per-warp partial reductions
   long long t_acc = 0;
+  int r_iw = 0, r_ih = 0, r_id = 0, r_in = 0;
+  uint32_t vmask_row = 0;
   if (epi) {
     const int iw = row % p.bw, ih = (row / p.bw) % p.bh, id = (row / (p.bw * p.bh)) % p.bd, in = row / (p.bw * p.bh * p.bd);
     // rows of a partial tile that fall outside the M grid must not enter the fused batch statistics
     const bool row_valid = (mw0 + iw) < C.Mw && (mh0 + ih) < C.Mh && (md0 + id) < C.Md && (mn0 + in) < p.Mn;
+    r_iw = iw; r_ih = ih; r_id = id; r_in = in; vmask_row = row_valid ? 1u : 0u;
     const uint32_t vmask = __ballot_sync(0xffffffffu, row_valid);
     if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(mask_smem + 4u * q), "r"(vmask) : "memory");
+    if (p.bnb_pre != nullptr) {
+      const int statC = p.cat_C ? p.cat_C : p.Nout;
+      const int grp = (int)(((long long)mn0 * p.stats_groups) / p.Mn);
+      for (int col = (warp - 2) * 32 + lane; col < p.BN; col += 128) {
+        const int ch = (n0 + col) % statC;
+        const float mu = __ldg(p.bnb_mean + grp * statC + ch), rs = __ldg(p.bnb_rstd + grp * statC + ch);
+        const float ga = p.bnb_gamma ? __ldg(p.bnb_gamma + ch) : 1.f, be = p.bnb_beta ? __ldg(p.bnb_beta + ch) : 0.f;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bnb_consts + 16u * (uint32_t)col), "f"(rs), "f"(-mu * rs), "f"(ga), "f"(be) : "memory");
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");      // the four epilogue warps
+    }
     if (lane == 0) mbar_wait(tmem_full_bar, 0);   // one polling lane per warp: the spin must not steal issue slots
     __syncwarp();                                 // from the producer / MMA threads that share these schedulers
     tc_fence_after();
@@ -422,6 +450,64 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((((uint32_t)g) ^ sw) << 4)), "f"(v[g * 4]), "f"(v[g * 4 + 1]),
                        "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3]) : "memory");
       }
+      if (p.bnb_pre != nullptr) {
+        // ---- fused batch-norm backward reductions over this 32-column block (see TcPixParams::bnb_*) ----
+        const int statC = p.cat_C ? p.cat_C : p.Nout;
+        const int colg = n0 + c0;                                   // first column of the block in the N axis
+        const int oc = p.cat_C ? colg / p.cat_C : ci;               // parity class the block writes (cat: per block)
+        const int o_d = p.cat_C ? p.cat_o[oc][0] : C.od0, o_h = p.cat_C ? p.cat_o[oc][1] : C.oh0, o_w = p.cat_C ? p.cat_o[oc][2] : C.ow0;
+        const int ch0 = p.cat_C ? colg % p.cat_C : colg;
+        const bool rv = (vmask_row != 0);
+        float x[32];
+        {
+          const long long pix = ((((long long)(mn0 + r_in) * p.OD + ((md0 + r_id) * p.osd + o_d)) * p.OH + ((mh0 + r_ih) * p.osh + o_h)) * p.OW +
+                                 ((mw0 + r_iw) * p.osw + o_w));
+          const float4* xp = reinterpret_cast<const float4*>(p.bnb_pre + pix * statC + ch0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 t = rv ? __ldg(xp + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[4 * g] = t.x; x[4 * g + 1] = t.y; x[4 * g + 2] = t.z; x[4 * g + 3] = t.w;
+          }
+        }
+        // xhat and the pre-activation u in place (x <- xhat, u kept in a second array only for the slow activations)
+        if (p.bnb_act <= GG_ACT_LRELU) {
+          // none / relu / lrelu: act'(u) is 1, slope or at_zero -- branch-free selects (ONE warp-uniform branch per block: a
+          // per-element call of the general act_grad_from_pre was if-converted by ptxas into evaluating tanhf AND expf for
+          // every element: 11 k cycles per 32-column block)
+          const float slope = act_slope(p.bnb_act, p.bnb_act_param), at_zero = p.bnb_act == GG_ACT_RELU ? 0.f : 1.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float4 k;
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w) : "r"(bnb_consts + 16u * (uint32_t)(c0 + j)));
+            const float xh = fmaf(x[j], k.x, k.y);
+            const float u = fmaf(k.z, xh, k.w);
+            float gv = p.out_bf16 ? __bfloat162float(__float2bfloat16_rn(v[j])) : v[j];     // what the apply kernel will read back
+            gv *= (u > 0.f ? 1.f : (u == 0.f ? at_zero : slope));
+            gv = rv ? gv : 0.f;
+            v[j] = gv;
+            x[j] = gv * xh;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {        // fully unrolled: a partially unrolled loop indexes v / x dynamically -> local memory
+            float4 k;
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w) : "r"(bnb_consts + 16u * (uint32_t)(c0 + j)));
+            const float xh = fmaf(x[j], k.x, k.y);
+            const float u = fmaf(k.z, xh, k.w);
+            float gv = p.out_bf16 ? __bfloat162float(__float2bfloat16_rn(v[j])) : v[j];
+            gv = rv ? gv * act_grad_from_pre(u, p.bnb_act, p.bnb_act_param) : 0.f;
+            v[j] = gv;
+            x[j] = gv * xh;
+          }
+        }
+        const float s0 = warp_transpose_sum32(v, lane), s1 = warp_transpose_sum32(x, lane);   // lane = column of the block
+        // per-warp partials [warp][2][BN] in shared memory; they meet below, ONE pair of fp64 atomics per channel per CTA
+        // (atomics straight from the warps -- 8 * BN per CTA -- made the L2 atomic units the bottleneck: +24 us per launch)
+        const uint32_t pp = bnb_part + 4u * (uint32_t)((q * 2) * p.BN + c0 + lane);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp), "f"(s0) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp + 4u * (uint32_t)p.BN), "f"(s1) : "memory");
+        (void)ch0;
+      }
     }
     fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA engine
     asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
@@ -435,6 +521,26 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    if (p.bnb_pre != nullptr) {
+      // (the per-warp partials were published by the bar.sync before the TMA stores)
+      const int statC = p.cat_C ? p.cat_C : p.Nout;
+      const int uniq = p.cat_C ? p.cat_C : p.BN;                    // distinct channels among this CTA's BN columns
+      const int grp = (int)(((long long)mn0 * p.stats_groups) / p.Mn);
+      for (int u = (warp - 2) * 32 + lane; u < uniq; u += 128) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int col = u; col < p.BN; col += uniq)                  // cat: the parity classes of the channel
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            float t0, t1;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0) : "r"(bnb_part + 4u * (uint32_t)((w4 * 2) * p.BN + col)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1) : "r"(bnb_part + 4u * (uint32_t)((w4 * 2 + 1) * p.BN + col)));
+            a0 += t0; a1 += t1;
+          }
+        const int schan = (n0 + u) % statC;
+        atomicAdd(p.bnb_sums + bn_sum_index(0, p.stats_groups, grp, 0, statC, schan), (double)a0);
+        atomicAdd(p.bnb_sums + bn_sum_index(0, p.stats_groups, grp, 1, statC, schan), (double)a1);
+      }
+    }
     if (p.stats != nullptr) {
       // Fused batch-norm statistics (tf.nn.moments of the pre-norm tensor): the fp32 tile is in shared memory;
       // epilogue thread t sums column t over the tile's valid rows (a warp reads 32 consecutive floats of one
@@ -442,24 +548,27 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       uint32_t m[4];
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(mask_smem));
       const int grp = (int)(((long long)mn0 * p.stats_groups) / p.Mn);
-      for (int col = (warp - 2) * 32 + lane; col < p.BN; col += 128) {
-        const uint32_t base = smem_base + (uint32_t)(col >> 5) * (TILE_M * 128u) + (uint32_t)((col & 3) << 2);
-        const uint32_t ch = (uint32_t)((col & 31) >> 2);
+      const int statC = p.cat_C ? p.cat_C : p.Nout;          // every parity class of a channel feeds the same statistic
+      const int uniq = p.cat_C ? p.cat_C : p.BN;             // distinct channels among this CTA's BN columns
+      for (int u = (warp - 2) * 32 + lane; u < uniq; u += 128) {
         float s = 0.f, s2 = 0.f;
+        for (int col = u; col < p.BN; col += uniq) {         // cat: the classes of the channel are folded BEFORE the atomics
+          const uint32_t base = smem_base + (uint32_t)(col >> 5) * (TILE_M * 128u) + (uint32_t)((col & 3) << 2);
+          const uint32_t ch = (uint32_t)((col & 31) >> 2);
 #pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) {
-          const uint32_t mrow = m[w4];
+          for (int w4 = 0; w4 < 4; ++w4) {
+            const uint32_t mrow = m[w4];
 #pragma unroll 8
-          for (int b = 0; b < 32; ++b) {
-            const int r = w4 * 32 + b;
-            float v;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (uint32_t)r * 128u + ((ch ^ (uint32_t)(r & 7)) << 4)));
-            if ((mrow >> b) & 1u) { s += v; s2 = fmaf(v, v, s2); }
+            for (int b = 0; b < 32; ++b) {
+              const int r = w4 * 32 + b;
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + (uint32_t)r * 128u + ((ch ^ (uint32_t)(r & 7)) << 4)));
+              if ((mrow >> b) & 1u) { s += v; s2 = fmaf(v, v, s2); }
+            }
           }
         }
-        const int statC = p.cat_C ? p.cat_C : p.Nout;          // every parity class of a channel feeds the same statistic
         const int R = bn_replicas(statC, p.stats_groups);     // replicated accumulators: spread the same-address atomics
-        const int rep = tile & (R - 1), schan = (n0 + col) % statC;
+        const int rep = tile & (R - 1), schan = (n0 + u) % statC;
         atomicAdd(p.stats + bn_sum_index(rep, p.stats_groups, grp, 0, statC, schan), (double)s);
         atomicAdd(p.stats + bn_sum_index(rep, p.stats_groups, grp, 1, statC, schan), (double)s2);
       }
@@ -671,6 +780,25 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p, float* __restrict__ dw)
 // ------------------------------------------------------------------------------------------------
 // host: plans
 // ------------------------------------------------------------------------------------------------
+}  // namespace gg
+// fused batch-norm backward reductions requested by the caller of a dgrad launch (see TcPixParams::bnb_*)
+struct gg_bnbwd_args {
+  const float *pre, *mean, *rstd, *gamma, *beta;
+  double* sums;
+  int act;
+  float act_param;
+  int groups;
+};
+namespace gg {
+static void set_bnb(TcPixParams& p, const gg_bnbwd_args* b, int N, int* fused) {
+  if (b == nullptr || b->pre == nullptr || b->sums == nullptr) return;
+  if (b->groups < 1 || N % b->groups != 0 || (N / b->groups) % p.bn != 0 || ((uintptr_t)b->pre % 16) != 0) return;   // a tile must not straddle row groups
+  if (p.splitk > 1) return;
+  p.bnb_pre = b->pre; p.bnb_mean = b->mean; p.bnb_rstd = b->rstd; p.bnb_gamma = b->gamma; p.bnb_beta = b->beta;
+  p.bnb_sums = b->sums; p.bnb_act = b->act; p.bnb_act_param = b->act_param; p.stats_groups = b->groups;
+  if (fused) *fused = 1;
+}
+
 static int pow2floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 
 static void pick_box(int Mw, int Mh, int Md, int pixels, int* bw, int* bh, int* bd, int* bn) {
@@ -766,9 +894,9 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   while (p.stages * stage_bytes < out_bytes) ++p.stages;
   p.stages = std::max(1, std::min(p.stages, env_int("GG_TC_STAGES", p.stages)));
   GG_REQUIRE(p.stages * stage_bytes >= out_bytes, GG_ERR_INVALID, "tc_pixgemm: GG_TC_STAGES too small for the output tile");
-  GG_REQUIRE((size_t)p.stages * stage_bytes + 2048 <= 227 * 1024, GG_ERR_INVALID, "tc_pixgemm: pipeline does not fit in shared memory");
+  GG_REQUIRE((size_t)p.stages * stage_bytes + 2048 + 48 * 256 <= 227 * 1024, GG_ERR_INVALID, "tc_pixgemm: pipeline does not fit in shared memory");
   p.prof = g_prof;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2) + 16;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2) + 16 + (p.bnb_pre ? 48 * p.BN : 0);
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(tc_pixgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   int rc = GG_OK;
@@ -782,7 +910,7 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
 // stats != nullptr: also accumulate per-channel (sum, sum of squares) of the fp32 output into stats[groups][2][channels].
 // *fused is set to 1 when the kernel did it (otherwise the caller runs a separate statistics pass).
 int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_bf, const float* bias, void* small, cudaStream_t st,
-                 double* stats = nullptr, int groups = 1, int* fused = nullptr) {
+                 double* stats = nullptr, int groups = 1, int* fused = nullptr, const gg_bnbwd_args* bnb = nullptr) {
   int rc = check_tc(d, large, w_bf, true, false);
   if (rc) return rc;
   TcPixParams p;
@@ -835,11 +963,12 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_bf, con
     p.stats = stats; p.stats_groups = groups;
     if (fused) *fused = 1;
   }
+  set_bnb(p, bnb, d->N, fused);
   return launch_pix(p, (int)(mtiles * p.ntiles_n), bias, small, st);
 }
 
 int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const float* bias, void* large, cudaStream_t st,
-               double* stats = nullptr, int groups = 1, int* fused = nullptr) {
+               double* stats = nullptr, int groups = 1, int* fused = nullptr, const gg_bnbwd_args* bnb = nullptr) {
   int rc = check_tc(d, small, w_ck, false, true);
   if (rc) return rc;
   TcPixParams p;
@@ -917,6 +1046,7 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
     p.stats = stats; p.stats_groups = groups;
     if (fused) *fused = 1;
   }
+  set_bnb(p, bnb, d->N, fused);
   return launch_pix(p, (int)(tiles * p.ntiles_n), bias, large, st);
 }
 
@@ -978,7 +1108,7 @@ static int upcat_plan(const gg_conv_desc* d, UpcatPlan* P) {
 }
 
 int tc_conv_up_cat(const gg_conv_desc* d, const void* small, const void* w_bf, const float* bias, void* large, cudaStream_t st,
-                   double* stats = nullptr, int groups = 1, int* fused = nullptr) {
+                   double* stats = nullptr, int groups = 1, int* fused = nullptr, const gg_bnbwd_args* bnb = nullptr) {
   int rc = check_tc(d, small, w_bf, false, true);
   if (rc) return rc;
   GG_REQUIRE(tc_upcat_ok(d), GG_ERR_UNSUPPORTED, "conv_up (concatenated classes): shape not eligible");
@@ -1048,6 +1178,8 @@ int tc_conv_up_cat(const gg_conv_desc* d, const void* small, const void* w_bf, c
     p.stats = stats; p.stats_groups = groups;
     if (fused) *fused = 1;
   }
+  for (int k = 0; k < P.ncls; ++k) { p.cat_o[k][0] = (int8_t)P.cls_a[k][0]; p.cat_o[k][1] = (int8_t)P.cls_a[k][1]; p.cat_o[k][2] = (int8_t)P.cls_a[k][2]; p.cat_o[k][3] = 0; }
+  set_bnb(p, bnb, d->N, fused);
   return launch_pix(p, (int)mtiles, bias, large, st);
 }
 

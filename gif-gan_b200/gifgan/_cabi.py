@@ -44,6 +44,7 @@ SIGNATURES = {
     "gg_conv_wgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),
     "gg_conv_down_stats": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gg_conv_up_stats": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "gg_conv_dgrad_bnbwd": (C.c_int, [_dp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _vp, C.POINTER(C.c_int32), _vp]),
     "gg_bn_fwd_train_stats": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _f32, _vp, _vp]),
     "gg_conv2d_fwd": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv2d_dgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),

@@ -410,10 +410,47 @@ class _Geom:
         return (self.N, self.Ho, self.Wo, self.K) if ndim == 4 else (self.N, self.Do, self.Ho, self.Wo, self.K)
 
 
-def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None, stats=None, groups=1):
-    """stats: optional fp64 [groups, 2, K] accumulator for the batch-norm statistics of the output."""
+class _BnInfo:
+    """What a train-mode fused batch norm leaves on its output tensor (`y._gg_bn`) so that the conv that consumes y can, in
+    ITS backward pass, produce the batch norm's backward reductions together with dy (gg_conv_dgrad_bnbwd)."""
+    __slots__ = ("pre", "mean", "rstd", "gamma", "beta", "act", "act_param", "groups", "Cc", "bwd_sums", "bwd_dy", "bwd_version")
+
+    def __init__(self):
+        self.pre = self.bwd_sums = self.bwd_dy = None
+        self.bwd_version = -1
+
+
+FUSE_BN_BWD = os.environ.get("GG_FUSE_BN_BWD", "1") != "0"    # A/B switch: batch-norm backward reductions in the dgrad epilogue
+
+
+def _run_dgrad_bnbwd(g: _Geom, up, src, wvar, out, bnb: _BnInfo):
+    """dgrad launch that also accumulates the consumer batch norm's (sum g, sum g*xhat); returns True when it was fused."""
+    L = cabi.lib()
+    large, small = (out, src) if up else (src, out)
+    d = g.desc(dt(large), dt(small), None, 0.0, True)
+    sums = _zeroed_f64(L.gg_bn_workspace_bytes(bnb.Cc, bnb.groups) // 8, out.device)[0]
+    fused = ctypes.c_int32(0)
+    check(L.gg_conv_dgrad_bnbwd(ctypes.byref(d), 1 if up else 0, ptr(src), ptr(wvar.bf16()), ptr(out), ptr(bnb.pre), ptr(bnb.mean), ptr(bnb.rstd),
+                                ptr(bnb.gamma), ptr(bnb.beta), ACT[bnb.act], float(bnb.act_param), bnb.groups, ptr(sums), ctypes.byref(fused),
+                                stream()), "gg_conv_dgrad_bnbwd")
+    if fused.value:
+        bnb.bwd_sums, bnb.bwd_dy, bnb.bwd_version = sums, out, out._version
+    return bool(fused.value)
+
+
+def _bnb_usable(bnb, out_shape, out_dtype):
+    return (FUSE_BN_BWD and bnb is not None and bnb.pre is not None and tuple(bnb.pre.shape) == tuple(out_shape)
+            and bnb.pre.dtype == torch.float32 and out_shape[-1] == bnb.Cc)
+
+
+def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None, stats=None, groups=1, bnb=None):
+    """stats: optional fp64 [groups, 2, K] accumulator for the batch-norm statistics of the output.
+    bnb: the _BnInfo of the batch norm whose output gradient this launch produces (dgrad of a deconv)."""
     small = out if out is not None else torch.empty(g.small_shape(ndim), dtype=out_dtype, device=large.device)
     tc = _tc_ok(g.C, g.K, large)
+    if tc and bias is None and act is None and stats is None and _bnb_usable(bnb, small.shape, small.dtype):
+        _run_dgrad_bnbwd(g, False, large, wvar, small, bnb)
+        return small
     d = g.desc(dt(large), dt(small), act, act_param, tc)
     w = wvar.bf16() if tc else wvar.data
     if stats is not None:
@@ -424,9 +461,12 @@ def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim,
     return small
 
 
-def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None, stats=None, groups=1):
+def _run_up(g: _Geom, small, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None, stats=None, groups=1, bnb=None):
     large = out if out is not None else torch.empty(g.large_shape(ndim), dtype=out_dtype, device=small.device)
     tc = _tc_ok(g.C, g.K, small)
+    if tc and bias is None and act is None and stats is None and _bnb_usable(bnb, large.shape, large.dtype):
+        _run_dgrad_bnbwd(g, True, small, wvar, large, bnb)
+        return large
     d = g.desc(dt(large), dt(small), act, act_param, tc)
     w = wvar.bf16() if tc else wvar.data
     if stats is not None:
@@ -547,8 +587,9 @@ class _ConvRel(torch.autograd.Function):
     flat gradient buffer, input gradient through the opposite-direction kernel."""
 
     @staticmethod
-    def forward(ctx, x, w, b, wvar, bvar, geom, direction, act, act_param, out_dtype, out):
+    def forward(ctx, x, w, b, wvar, bvar, geom, direction, act, act_param, out_dtype, out, in_bn=None):
         ndim = x.dim()
+        ctx.in_bn = in_bn
         run = _run_down if direction == "down" else _run_up
         y = run(geom, x, wvar, b, out_dtype, act, act_param, ndim, out)
         if out is not None:
@@ -574,8 +615,8 @@ class _ConvRel(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             run = _run_up if ctx.direction == "down" else _run_down
-            dx = run(g, dpre, ctx.wvar, None, ctx.x_dtype, None, 0.0, ctx.ndim)
-        return dx, None, None, None, None, None, None, None, None, None, None
+            dx = run(g, dpre, ctx.wvar, None, ctx.x_dtype, None, 0.0, ctx.ndim, bnb=ctx.in_bn)
+        return dx, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _conv_common(input_, wvar, bvar, geom, direction, act, act_param, out_dtype, out=None):
@@ -590,7 +631,7 @@ def _conv_common(input_, wvar, bvar, geom, direction, act, act_param, out_dtype,
         want = geom.small_shape(x.dim()) if direction == "down" else geom.large_shape(x.dim())
         if tuple(out.shape) != tuple(want) or out.dtype != out_dtype or not out.is_contiguous():
             raise ValueError(f"out= must be a contiguous {out_dtype} tensor of shape {want}")
-    return _ConvRel.apply(x, w, b, wvar, bvar, geom, direction, act, act_param, out_dtype, out)
+    return _ConvRel.apply(x, w, b, wvar, bvar, geom, direction, act, act_param, out_dtype, out, getattr(input_, "_gg_bn", None))
 
 
 def _out_dtype(act, out_dtype):
@@ -850,9 +891,9 @@ class _ConvProducer:
         else:
             _run_wgrad(self.geom, dpre, x, self.wvar)
 
-    def dgrad(self, dpre, x_dtype):
+    def dgrad(self, dpre, x_dtype, bnb=None):
         run = _run_up if self.direction == "down" else _run_down
-        return run(self.geom, dpre, self.wvar, None, x_dtype, None, 0.0, self.ndim)
+        return run(self.geom, dpre, self.wvar, None, x_dtype, None, 0.0, self.ndim, bnb=bnb)
 
 
 class _LinearProducer:
@@ -876,7 +917,7 @@ class _LinearProducer:
         check(cabi.lib().gg_linear_wgrad(ptr(x), dt(x), ptr(dpre), dt(dpre), ptr(self.wvar.grad), None, rows, in_dim, self.out_dim,
                                          stream()), "gg_linear_wgrad")
 
-    def dgrad(self, dpre, x_dtype):
+    def dgrad(self, dpre, x_dtype, bnb=None):
         rows = dpre.shape[0]
         in_dim = self.wvar.data.shape[0]
         dx = torch.empty((rows, in_dim), dtype=x_dtype, device=dpre.device)
@@ -894,8 +935,9 @@ class _FusedBN(torch.autograd.Function):
     it is left at zero rather than filled with rounding noise."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, prod, bn, train, act, act_param, out_dtype, groups, Cc):
+    def forward(ctx, x, w, b, gamma, beta, prod, bn, train, act, act_param, out_dtype, groups, Cc, in_bn=None, info=None):
         L = cabi.lib()
+        ctx.in_bn, ctx.info = in_bn, info
         fused_stats = train and prod.fuses_stats and Cc == prod.out_shape()[-1]
         stats = _zeroed_f64(L.gg_bn_workspace_bytes(Cc, groups) // 8, x.device)[0] if fused_stats else None   # [replicas][groups][2][C]
         pre = prod.fwd(x, b, stats=stats, groups=groups)
@@ -922,6 +964,9 @@ class _FusedBN(torch.autograd.Function):
         ctx.prod, ctx.bn, ctx.train, ctx.act, ctx.act_param, ctx.groups, ctx.Cc = prod, bn, train, act, act_param, groups, Cc
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(x, pre, gamma, beta, save_mean, save_rstd)
+        if info is not None and train:
+            info.pre, info.mean, info.rstd, info.gamma, info.beta = pre, save_mean, save_rstd, gamma, beta
+            info.act, info.act_param, info.groups, info.Cc = act, act_param, groups, Cc
         if DEBUG_TAP is not None:
             DEBUG_TAP.setdefault("fwd", []).append((prod.wvar.name, pre, y))
         return y
@@ -937,18 +982,28 @@ class _FusedBN(torch.autograd.Function):
         need_g, need_be = gamma is not None and ctx.needs_input_grad[3], beta is not None and ctx.needs_input_grad[4]
         dpre = torch.empty(pre.shape, dtype=act_dtype(), device=pre.device)     # GEMM operand precision
         nbytes = L.gg_bn_workspace_bytes(Cc, ctx.groups)
-        ws, prezeroed = _zeroed_f64(nbytes // 8, pre.device) if ctx.train else (torch.empty(nbytes // 8, dtype=torch.float64, device=pre.device), False)
+        info = ctx.info
+        if (ctx.train and info is not None and info.bwd_sums is not None and dy.data_ptr() == info.bwd_dy.data_ptr()
+                and dy._version == info.bwd_version and dy.dtype == info.bwd_dy.dtype and tuple(dy.shape) == tuple(info.bwd_dy.shape)):
+            # the dgrad launch that wrote dy (the ONLY contribution to it: an accumulated gradient is another tensor or another
+            # version) already reduced (sum g, sum g*xhat) in its epilogue: apply pass only
+            ws, mode = info.bwd_sums, 3
+        else:
+            ws, prezeroed = _zeroed_f64(nbytes // 8, pre.device) if ctx.train else (torch.empty(nbytes // 8, dtype=torch.float64, device=pre.device), False)
+            mode = (2 if prezeroed else 1) if ctx.train else 0
+        if info is not None:
+            info.bwd_sums = info.bwd_dy = info.pre = None
         check(L.gg_bn_bwd(ptr(pre), dt(pre), ptr(dy), dt(dy), ptr(dpre), dt(dpre), rows, Cc, ctx.groups, ptr(gamma), ptr(beta),
                           ptr(save_mean), ptr(save_rstd), ptr(bn.gamma.grad) if need_g else None, ptr(bn.beta.grad) if need_be else None,
-                          ACT[ctx.act], float(ctx.act_param), (2 if prezeroed else 1) if ctx.train else 0, ptr(ws), nbytes, stream()), "gg_bn_bwd")
+                          ACT[ctx.act], float(ctx.act_param), mode, ptr(ws), nbytes, stream()), "gg_bn_bwd")
         if DEBUG_TAP is not None:
             DEBUG_TAP.setdefault("bwd", []).append((prod.wvar.name, dy, dpre))
         if need_b and not ctx.train:
             _bias_grad(dpre.reshape(-1, prod.bvar.data.numel()), prod.bvar)
         if need_w:
             prod.wgrad(x, dpre)
-        dx = prod.dgrad(dpre, ctx.x_dtype) if ctx.needs_input_grad[0] else None
-        return (dx,) + (None,) * 12
+        dx = prod.dgrad(dpre, ctx.x_dtype, bnb=ctx.in_bn) if ctx.needs_input_grad[0] else None
+        return (dx,) + (None,) * 14
 
 
 def _fused_bn(input_, prod, bn, train, act, act_param, out_dtype, groups, channels=None):
@@ -964,7 +1019,12 @@ def _fused_bn(input_, prod, bn, train, act, act_param, out_dtype, groups, channe
     b = _wtensor(prod.bvar, _wants_grad(prod.bvar)) if prod.bvar is not None else None
     g = _wtensor(bn.gamma, _wants_grad(bn.gamma)) if bn.affine else None
     be = _wtensor(bn.beta, _wants_grad(bn.beta)) if bn.affine else None
-    return _FusedBN.apply(input_.contiguous(), w, b, g, be, prod, bn, bool(train), act, act_param, out_dtype, groups, Cc)
+    info = _BnInfo() if (train and torch.is_grad_enabled() and FUSE_BN_BWD) else None
+    y = _FusedBN.apply(input_.contiguous(), w, b, g, be, prod, bn, bool(train), act, act_param, out_dtype, groups, Cc,
+                       getattr(input_, "_gg_bn", None), info)
+    if info is not None and y.requires_grad:
+        y._gg_bn = info          # picked up by the conv that consumes y (its dgrad produces this batch norm's backward reductions)
+    return y
 
 
 # ---- standalone activations ------------------------------------------------------------

@@ -113,6 +113,17 @@ int gg_conv_down_stats(const gg_conv_desc* d, const void* large, const void* w, 
 int gg_conv_up_stats(const gg_conv_desc* d, const void* small, const void* w, const float* bias, void* large,
                      double* stats, int32_t groups, void* stream);
 
+/* Input gradient of a conv (up != 0: gg_conv_up) or deconv (up == 0: gg_conv_down), no bias / activation, whose INPUT was the
+ * output of a train-mode batch norm + activation (`lrelu(d_bn1(conv2d(...)))` feeding the next conv2d, model.py:274-276): the
+ * launch that writes dy for that batch norm also accumulates its backward reductions -- per channel and row group, sum g and
+ * sum g*xhat with g = dy*act'(gamma*xhat+beta), xhat = (pre-mean)*rstd -- into sums ([groups][2][C] fp64, zeroed by the
+ * caller) from the accumulator registers.  pre / save_mean / save_rstd / gamma / beta are that batch norm's (gg_bn_fwd_train).
+ * *fused = 1 when the reductions were produced (tensor-core path, tiles aligned with the row groups): gg_bn_bwd(train = 3)
+ * then runs its apply pass only; *fused = 0: only the plain dgrad ran.                                                     */
+int gg_conv_dgrad_bnbwd(const gg_conv_desc* d, int32_t up, const void* dy, const void* w, void* dx, const float* pre,
+                        const float* save_mean, const float* save_rstd, const float* gamma, const float* beta, int32_t act,
+                        float act_param, int32_t groups, double* sums, int32_t* fused, void* stream);
+
 /* Reference-named aliases (same arguments, fixed direction). */
 int gg_conv2d_fwd(const gg_conv_desc* d, const void* x, const void* w, const float* b, void* y, void* stream);     /* ops.py:57  */
 int gg_conv2d_dgrad(const gg_conv_desc* d, const void* dy, const void* w, void* dx, void* stream);                   /* grad of ops.py:57 wrt input_ */
@@ -160,7 +171,8 @@ int gg_bn_fwd_infer(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, in
  * (gradient flows through mean/var); train=0: inference statistics in save_mean/save_rstd
  * as written by gg_bn_infer_stats.  dgamma/dbeta (+=, may be NULL).                      */
 /* train: 0 = inference-mode statistics (dx = gamma*rstd*g), 1 = batch statistics, 2 = batch statistics with a workspace
- * the caller has already zeroed (saves one memset per layer when a whole update shares one zeroed arena). */
+ * the caller has already zeroed (saves one memset per layer when a whole update shares one zeroed arena), 3 = batch
+ * statistics with the reductions already in ws (written by gg_conv_dgrad_bnbwd): apply pass only. */
 int gg_bn_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, void* dx, int32_t dx_dtype,
               int64_t rows, int32_t C, int32_t groups, const float* gamma, const float* beta,
               const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta,

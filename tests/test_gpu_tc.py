@@ -274,3 +274,78 @@ def test_train_step_enters_the_graph_with_current_filter_copies():
     assert abs(l1[0, 0] - l0[0, 0]) <= 1e-6 * abs(l0[0, 0]), (l0, l1)
     assert abs(l1[0, 1] - l0[0, 1]) <= 1e-3 * abs(l0[0, 1]), (l0, l1)
     np.testing.assert_allclose(l1, l0, rtol=0.15, atol=0.02)
+
+
+@pytest.mark.parametrize("kind,B,H,C0,C1,C2,groups", [
+    ("conv", 16, 32, 64, 128, 256, 2),      # d_h1 -> bn1 -> lrelu -> d_h2: the batch norm's dy comes from a conv_up launch
+    ("conv", 8, 16, 128, 64, 128, 1),       # 64-channel batch norm: its dy comes from the class-concatenated conv_up (N = 256)
+    ("conv", 6, 12, 64, 128, 64, 3),        # partial tiles (12 x 12 -> 6 x 6 -> 3 x 3), three row groups of two images
+    ("deconv", 16, 4, 512, 256, 128, 1),    # g_h1 -> bn1 -> relu -> g_h2: dy comes from a conv_down launch
+])
+def test_bn_backward_reductions_fused_into_dgrad(kind, B, H, C0, C1, C2, groups, monkeypatch):
+    """gg_conv_dgrad_bnbwd: (sum g, sum g*xhat) of a train-mode batch norm accumulated in the epilogue of the dgrad launch
+    that produces its dy (ops.FUSE_BN_BWD) must give the gradients of the two-pass path (colsum + apply) -- and both must
+    match the float64 oracle of the same two-layer stack."""
+    from gifgan import ops as _o
+    rs = np.random.RandomState(B + H + C1)
+    act = "lrelu" if kind == "conv" else "relu"
+
+    def build(t, bn):
+        if kind == "conv":
+            h = _o.conv2d(t, C1, name="a", bn=bn, act=act, groups=groups)
+            return _o.conv2d(h, C2, name="b", bias=False)
+        h = _o.deconv2d(t, [B, 2 * H, 2 * H, C1], name="a", bn=bn, act=act, groups=groups)
+        return _o.deconv2d(h, [B, 4 * H, 4 * H, C2], name="b", bias=False)
+
+    x = bf16_round(rs.randn(B, H, H, C0))
+    results = []
+    for fuse in (False, True):
+        monkeypatch.setattr(_o, "FUSE_BN_BWD", fuse)
+        bn = _o.batch_norm(name="bn")
+        ops, st, tv = _store(lambda t: build(t, bn), (B, H, H, C0))
+        if not results:
+            sd = {k: v.clone() for k, v in st.state_dict().items()}
+            sd["bn/gamma"] = torch.tensor(rs.uniform(0.5, 1.5, C1), dtype=torch.float32)
+            sd["bn/beta"] = torch.tensor(rs.uniform(-0.3, 0.3, C1), dtype=torch.float32)
+            for k in ("a/w", "b/w"):
+                sd[k] = bf16_round(sd[k] * 2.5)
+        st.load_state_dict(sd)
+        xt = x.cuda().to(torch.bfloat16).requires_grad_(True)
+        n0 = ops.cabi.launch_count()
+        with ops.trainable(tv), ops.stats_arena():
+            y = build(xt, bn)
+            if not results:
+                dy = bf16_round(rs.randn(*y.shape))
+            y.backward(dy.cuda().to(torch.bfloat16))
+        results.append(dict(dx=xt.grad.float().cpu(), launches=ops.cabi.launch_count() - n0,
+                            grads={k: st.vars[k].grad.clone().cpu() for k in ("a/w", "b/w", "bn/gamma", "bn/beta")}))
+    two, one = results
+    # the colsum launch is gone -- unless a tile would straddle two row groups (groups = 3: two images per group, four per
+    # tile), where the library must fall back to the two-pass path on its own
+    assert one["launches"] == two["launches"] - (0 if groups == 3 else 1), (one["launches"], two["launches"])
+    assert relerr(one["dx"], two["dx"]) < 5e-3
+    for k in two["grads"]:
+        assert relerr(one["grads"][k], two["grads"][k]) < 5e-3, k
+    # float64 oracle of the same stack
+    xr = x.double().requires_grad_(True)
+    wa, wb = sd["a/w"].double().requires_grad_(True), sd["b/w"].double().requires_grad_(True)
+    ga, be = sd["bn/gamma"].double().requires_grad_(True), sd["bn/beta"].double().requires_grad_(True)
+    if kind == "conv":
+        pre = T.conv2d(xr, wa, sd["a/biases"].double())
+    else:
+        pre = T.conv2d_transpose(xr, wa, [B, 2 * H, 2 * H, C1]) + sd["a/biases"].double()
+    parts = []
+    for gidx in range(groups):
+        p_ = pre[gidx * (B // groups):(gidx + 1) * (B // groups)]
+        mu, var = p_.mean((0, 1, 2)), p_.var((0, 1, 2), unbiased=False)
+        parts.append((p_ - mu) / torch.sqrt(var + 1e-5) * ga + be)
+    h = torch.cat(parts, 0)
+    h = T.lrelu(h) if act == "lrelu" else torch.relu(h)
+    h = bf16_round(h.detach()).double() + (h - h.detach())          # the activation crosses the node boundary in bf16
+    yr = T.conv2d(h, wb) if kind == "conv" else T.conv2d_transpose(h, wb, [B, 4 * H, 4 * H, C2])
+    gx, gwa, gwb, gga, gbe = torch.autograd.grad(yr, [xr, wa, wb, ga, be], dy.double())
+    # L2 metric: the activation gradient is re-rounded to bf16 between the layers (as in the model-level bf16 tests)
+    l2 = lambda a, b: float((a.double() - b).norm() / b.norm())
+    assert l2(one["dx"], gx) < 2e-2
+    for k, want in (("a/w", gwa), ("b/w", gwb), ("bn/gamma", gga), ("bn/beta", gbe)):
+        assert l2(one["grads"][k], want) < 2e-2, k

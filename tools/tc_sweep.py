@@ -31,7 +31,27 @@ def one(shape, op, reps=20):
     large = torch.randn(N, H, H, C, device="cuda").to(torch.bfloat16)
     small = torch.randn(N, H // 2, H // 2, K, device="cuda").to(torch.bfloat16)
     out_l, out_s = torch.empty_like(large), torch.empty_like(small)
-    fn = {"down": lambda: ops._run_down(g, large, wv, None, torch.bfloat16, None, 0.0, 4, out=out_s),
+    if os.environ.get("GG_SWEEP_STATS"):      # the in-step form of a layer that feeds a batch norm: fp32 pre-norm output + fused statistics
+        out_l, out_s = out_l.float(), out_s.float()
+        st_l = torch.zeros(2 * 2 * C, dtype=torch.float64, device="cuda")
+        st_s = torch.zeros(2 * 2 * K, dtype=torch.float64, device="cuda")
+        fn = {"down": lambda: ops._run_down(g, large, wv, None, torch.float32, None, 0.0, 4, out=out_s, stats=st_s, groups=2),
+              "up": lambda: ops._run_up(g, small, wv, None, torch.float32, None, 0.0, 4, out=out_l, stats=st_l, groups=2),
+              "wgrad": lambda: ops._run_wgrad(g, large, small, wv)}[op]
+    elif os.environ.get("GG_SWEEP_BNB"):      # dgrad launch with the consumer batch norm's backward reductions fused into its epilogue
+        def info(shape, Cc):
+            b = ops._BnInfo()
+            b.pre = torch.randn(shape, device="cuda")
+            b.mean, b.rstd = torch.zeros(1, Cc, device="cuda"), torch.ones(1, Cc, device="cuda")
+            b.gamma, b.beta = torch.ones(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+            b.act, b.act_param, b.groups, b.Cc = "lrelu", 0.2, 1, Cc
+            return b
+        bl, bs = info(large.shape, C), info(small.shape, K)
+        fn = {"down": lambda: ops._run_down(g, large, wv, None, torch.bfloat16, None, 0.0, 4, out=out_s, bnb=bs),
+              "up": lambda: ops._run_up(g, small, wv, None, torch.bfloat16, None, 0.0, 4, out=out_l, bnb=bl),
+              "wgrad": lambda: ops._run_wgrad(g, large, small, wv)}[op]
+    else:
+      fn = {"down": lambda: ops._run_down(g, large, wv, None, torch.bfloat16, None, 0.0, 4, out=out_s),
           "up": lambda: ops._run_up(g, small, wv, None, torch.bfloat16, None, 0.0, 4, out=out_l),
           "wgrad": lambda: ops._run_wgrad(g, large, small, wv)}[op]
     fn(); torch.cuda.synchronize()
