@@ -364,60 +364,60 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     t_acc = clock64();
   }
 
-  // ---- split-K: reduce the S partial accumulators of the cluster through distributed shared memory ----
-  // All pipeline stages are free once tmem_full fired (every MMA that read them has retired), so each CTA parks its raw
-  // fp32 partial at smem_base in the staging layout P = [BN/32 column blocks][128 rows][128 B, 16-byte chunk ^ (row & 7)].
-  // Rank r then sums rows [r*128/S, (r+1)*128/S) over all S partials (S-1 remote reads per 16-byte chunk) and writes the
-  // result into the LEADER's P (row slices are disjoint, so in place); the leader alone runs the normal epilogue from P.
+  // ---- split-K: push-style reduce-scatter of the S partial accumulators through distributed shared memory ----
+  // Rank d of the cluster FINISHES the column slice [d*ncol, (d+1)*ncol) of the tile (ncol = BN / S): every rank reads its
+  // fp32 partial from TMEM once and stores each 32-column block straight into the receive buffer of the rank that owns it
+  // (st.shared::cluster; its own slice with the same instruction), R[source][block][128 rows][128 B, 16-byte chunk ^ (row & 7)]
+  // at smem_base of the owner -- the pipeline stages, free on every rank once ALL ranks have seen their tmem_full
+  // (cluster barrier 1).  After cluster barrier 2 a rank only reads its own shared memory: it sums the S partials of its
+  // slice and runs the normal epilogue (bias, activation, statistics, TMA store) as if the tile were 128 x ncol.
+  // (The first version pulled row slices from all ranks and let the leader alone run the epilogue: ~13 k cycles at S = 8.)
+  const int ncol = p.BN / S;                       // columns this rank finishes
+  const int ncol0 = rank * ncol;                   // first of them within the N tile
   if (S > 1) {
+    if (epi) tc_fence_before();
+    cluster_sync_all();                            // 1: every rank's MMAs have retired -> all pipeline buffers are free
     if (epi) {
+      tc_fence_after();
+      const uint32_t nb = (uint32_t)(ncol >> 5);   // 32-column blocks per slice
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
-        const uint32_t blk = smem_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
+        const uint32_t d = (uint32_t)(c0 / ncol), b = (uint32_t)((c0 % ncol) >> 5);
+        const uint32_t dst = dsmem_addr(smem_base + ((uint32_t)rank * nb + b) * (TILE_M * 128u) + row_off, d);
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((((uint32_t)g) ^ sw) << 4)), "r"(r[g * 4]), "r"(r[g * 4 + 1]),
+          asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t)g) ^ sw) << 4)), "r"(r[g * 4]), "r"(r[g * 4 + 1]),
                        "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3]) : "memory");
       }
       tc_fence_before();
     }
-    cluster_sync_all();
-    if (epi) {
-      const int rows_per = TILE_M / S;
-      const int cpr_log = (p.BN == 256) ? 6 : (p.BN == 128 ? 5 : 4);          // 16-byte chunks per row = BN / 4
-      const int nchunks = rows_per << cpr_log;
-      for (int i = (warp - 2) * 32 + lane; i < nchunks; i += 128) {
-        const int rr = rank * rows_per + (i >> cpr_log);
-        const int ch = i & ((1 << cpr_log) - 1);
-        const uint32_t off = smem_base + (uint32_t)(ch >> 3) * (TILE_M * 128u) + (uint32_t)rr * 128u + ((((uint32_t)ch & 7u) ^ (uint32_t)(rr & 7)) << 4);
-        float4 part[8];
-#pragma unroll
-        for (int pr = 0; pr < 8; ++pr)
-          part[pr] = (pr < S) ? dsmem_ld4(dsmem_addr(off, (uint32_t)pr)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 acc = part[0];
-#pragma unroll
-        for (int pr = 1; pr < 8; ++pr) { acc.x += part[pr].x; acc.y += part[pr].y; acc.z += part[pr].z; acc.w += part[pr].w; }
-        dsmem_st4(dsmem_addr(off, 0u), acc);
-      }
-    }
-    cluster_sync_all();
+    cluster_sync_all();                            // 2: all partials of my slice have arrived (release / acquire)
   }
 
-  if (epi && rank == 0) {
-    // Accumulator (TMEM, or the reduced fp32 tile in P when S > 1) -> (+bias, activation) -> shared memory in the
-    // 128B-swizzled box layout -> TMA tensor store.  The TMA store clips partial tiles and, for conv_up, scatters to the
-    // stride-s output parity view.  bf16 staging of a split-K tile sits behind P (host checks the capacity).
-    const uint32_t out_base = (S > 1 && p.out_bf16) ? smem_base + (uint32_t)p.BN * 512u : smem_base;
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+  if (epi) {
+    // Accumulator (TMEM, or the S partials of this rank's column slice in R when S > 1) -> (+bias, activation) -> shared
+    // memory in the 128B-swizzled box layout -> TMA tensor store.  The TMA store clips partial tiles and, for conv_up,
+    // scatters to the stride-s output parity view.  The staging of a split-K slice sits behind R (host checks the capacity).
+    // Below, c0 counts columns of THIS RANK's slice; cg = ncol0 + c0 is the column within the N tile.
+    const uint32_t out_base = (S > 1) ? smem_base + (uint32_t)p.BN * 512u : smem_base;
+    for (int c0 = 0; c0 < ncol; c0 += 32) {
+      const int cg = ncol0 + c0;
       float v[32];
       if (S > 1) {
-        const uint32_t blk = smem_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[g * 4]), "=f"(v[g * 4 + 1]), "=f"(v[g * 4 + 2]), "=f"(v[g * 4 + 3])
-                       : "r"(blk + ((((uint32_t)g) ^ sw) << 4)) : "memory");
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int src = 0; src < S; ++src) {
+          const uint32_t blk = smem_base + ((uint32_t)src * (uint32_t)(ncol >> 5) + (uint32_t)(c0 >> 5)) * (TILE_M * 128u) + row_off;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 t;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                         : "r"(blk + ((((uint32_t)g) ^ sw) << 4)) : "memory");
+            v[g * 4] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
+          }
+        }
       } else {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -426,7 +426,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       }
       if (bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias + (p.cat_C ? (n0 + c0) % p.cat_C : n0 + c0));
+        const float4* b4 = reinterpret_cast<const float4*>(bias + (p.cat_C ? (n0 + cg) % p.cat_C : n0 + cg));
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float4 b = __ldg(b4 + j); v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w; }
       }
@@ -453,7 +453,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       if (p.bnb_pre != nullptr) {
         // ---- fused batch-norm backward reductions over this 32-column block (see TcPixParams::bnb_*) ----
         const int statC = p.cat_C ? p.cat_C : p.Nout;
-        const int colg = n0 + c0;                                   // first column of the block in the N axis
+        const int colg = n0 + cg;                                   // first column of the block in the N axis
         const int oc = p.cat_C ? colg / p.cat_C : ci;               // parity class the block writes (cat: per block)
         const int o_d = p.cat_C ? p.cat_o[oc][0] : C.od0, o_h = p.cat_C ? p.cat_o[oc][1] : C.oh0, o_w = p.cat_C ? p.cat_o[oc][2] : C.ow0;
         const int ch0 = p.cat_C ? colg % p.cat_C : colg;
@@ -478,7 +478,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float4 k;
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w) : "r"(bnb_consts + 16u * (uint32_t)(c0 + j)));
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w) : "r"(bnb_consts + 16u * (uint32_t)(cg + j)));
             const float xh = fmaf(x[j], k.x, k.y);
             const float u = fmaf(k.z, xh, k.w);
             float gv = p.out_bf16 ? __bfloat162float(__float2bfloat16_rn(v[j])) : v[j];     // what the apply kernel will read back
@@ -491,7 +491,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
 #pragma unroll
           for (int j = 0; j < 32; ++j) {        // fully unrolled: a partially unrolled loop indexes v / x dynamically -> local memory
             float4 k;
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w) : "r"(bnb_consts + 16u * (uint32_t)(c0 + j)));
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(k.x), "=f"(k.y), "=f"(k.z), "=f"(k.w) : "r"(bnb_consts + 16u * (uint32_t)(cg + j)));
             const float xh = fmaf(x[j], k.x, k.y);
             const float u = fmaf(k.z, xh, k.w);
             float gv = p.out_bf16 ? __bfloat162float(__float2bfloat16_rn(v[j])) : v[j];
@@ -503,7 +503,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
         const float s0 = warp_transpose_sum32(v, lane), s1 = warp_transpose_sum32(x, lane);   // lane = column of the block
         // per-warp partials [warp][2][BN] in shared memory; they meet below, ONE pair of fp64 atomics per channel per CTA
         // (atomics straight from the warps -- 8 * BN per CTA -- made the L2 atomic units the bottleneck: +24 us per launch)
-        const uint32_t pp = bnb_part + 4u * (uint32_t)((q * 2) * p.BN + c0 + lane);
+        const uint32_t pp = bnb_part + 4u * (uint32_t)((q * 2) * p.BN + cg + lane);
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp), "f"(s0) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp + 4u * (uint32_t)p.BN), "f"(s1) : "memory");
         (void)ch0;
@@ -512,10 +512,10 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA engine
     asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
     if (warp == 2 && lane == 0) {
-      const int nblk = p.out_bf16 ? (p.BN >> 6) : (p.BN >> 5);
+      const int nblk = p.out_bf16 ? (ncol >> 6) : (ncol >> 5);
       const int cstep = p.out_bf16 ? 64 : 32;
       for (int b = 0; b < nblk; ++b) {
-        const int col = n0 + b * cstep;                          // concatenated classes: column -> (class output map, channel)
+        const int col = n0 + ncol0 + b * cstep;                  // concatenated classes: column -> (class output map, channel)
         const int oc = p.cat_C ? col / p.cat_C : ci, ch = p.cat_C ? col % p.cat_C : col;
         tma_store_5d(&p.omap[oc], out_base + (uint32_t)b * (TILE_M * 128u), ch, mw0, mh0, md0, mn0);
       }
@@ -524,11 +524,11 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     if (p.bnb_pre != nullptr) {
       // (the per-warp partials were published by the bar.sync before the TMA stores)
       const int statC = p.cat_C ? p.cat_C : p.Nout;
-      const int uniq = p.cat_C ? p.cat_C : p.BN;                    // distinct channels among this CTA's BN columns
+      const int uniq = p.cat_C ? p.cat_C : ncol;                    // distinct channels among the columns this rank finishes
       const int grp = (int)(((long long)mn0 * p.stats_groups) / p.Mn);
       for (int u = (warp - 2) * 32 + lane; u < uniq; u += 128) {
         float a0 = 0.f, a1 = 0.f;
-        for (int col = u; col < p.BN; col += uniq)                  // cat: the parity classes of the channel
+        for (int col = ncol0 + u; col < ncol0 + ncol; col += uniq)  // cat: the parity classes of the channel
 #pragma unroll
           for (int w4 = 0; w4 < 4; ++w4) {
             float t0, t1;
@@ -536,7 +536,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1) : "r"(bnb_part + 4u * (uint32_t)((w4 * 2 + 1) * p.BN + col)));
             a0 += t0; a1 += t1;
           }
-        const int schan = (n0 + u) % statC;
+        const int schan = (n0 + ncol0 + u) % statC;
         atomicAdd(p.bnb_sums + bn_sum_index(0, p.stats_groups, grp, 0, statC, schan), (double)a0);
         atomicAdd(p.bnb_sums + bn_sum_index(0, p.stats_groups, grp, 1, statC, schan), (double)a1);
       }
@@ -549,11 +549,11 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]) : "r"(mask_smem));
       const int grp = (int)(((long long)mn0 * p.stats_groups) / p.Mn);
       const int statC = p.cat_C ? p.cat_C : p.Nout;          // every parity class of a channel feeds the same statistic
-      const int uniq = p.cat_C ? p.cat_C : p.BN;             // distinct channels among this CTA's BN columns
+      const int uniq = p.cat_C ? p.cat_C : ncol;             // distinct channels among the columns this rank finishes
       for (int u = (warp - 2) * 32 + lane; u < uniq; u += 128) {
         float s = 0.f, s2 = 0.f;
-        for (int col = u; col < p.BN; col += uniq) {         // cat: the classes of the channel are folded BEFORE the atomics
-          const uint32_t base = smem_base + (uint32_t)(col >> 5) * (TILE_M * 128u) + (uint32_t)((col & 3) << 2);
+        for (int col = u; col < ncol; col += uniq) {         // (slice-local column) cat: the classes of the channel are folded BEFORE the atomics
+          const uint32_t base = out_base + (uint32_t)(col >> 5) * (TILE_M * 128u) + (uint32_t)((col & 3) << 2);
           const uint32_t ch = (uint32_t)((col & 31) >> 2);
 #pragma unroll
           for (int w4 = 0; w4 < 4; ++w4) {
@@ -568,7 +568,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
           }
         }
         const int R = bn_replicas(statC, p.stats_groups);     // replicated accumulators: spread the same-address atomics
-        const int rep = tile & (R - 1), schan = (n0 + u) % statC;
+        const int rep = tile & (R - 1), schan = (n0 + ncol0 + u) % statC;
         atomicAdd(p.stats + bn_sum_index(rep, p.stats_groups, grp, 0, statC, schan), (double)s);
         atomicAdd(p.stats + bn_sum_index(rep, p.stats_groups, grp, 1, statC, schan), (double)s2);
       }
@@ -793,7 +793,6 @@ namespace gg {
 static void set_bnb(TcPixParams& p, const gg_bnbwd_args* b, int N, int* fused) {
   if (b == nullptr || b->pre == nullptr || b->sums == nullptr) return;
   if (b->groups < 1 || N % b->groups != 0 || (N / b->groups) % p.bn != 0 || ((uintptr_t)b->pre % 16) != 0) return;   // a tile must not straddle row groups
-  if (p.splitk > 1) return;
   p.bnb_pre = b->pre; p.bnb_mean = b->mean; p.bnb_rstd = b->rstd; p.bnb_gamma = b->gamma; p.bnb_beta = b->beta;
   p.bnb_sums = b->sums; p.bnb_act = b->act; p.bnb_act_param = b->act_param; p.stats_groups = b->groups;
   if (fused) *fused = 1;
@@ -858,22 +857,48 @@ static int env_int(const char* name, int dflt) {
 }
 void tc_set_repeat(int n) { g_repeat = n < 1 ? 1 : n; }
 
-// Output-channel tile and split-K factor.  An M=128 tcgen05.mma from shared memory costs max(~78, N/2) cycles, so a
-// wider N is cheaper per FLOP -- but at batch 64 the wide tiles leave most SMs idle.  Default: the widest tile that
-// still yields ~1 wave of CTAs, no split.  GG_TC_SPLITK=S (2/4/8) instead takes the widest N that divides Nout and
-// splits K over a cluster of S CTAs reduced through distributed shared memory (implemented and parity-tested; with
-// the current pull-style reduction the 13 k-cycle DSMEM phase eats the main-loop gain at these sizes: 22 -> 31 us for
-// g_h1.down, profiles/r01k_tc_clock64.log -- a push-style reduce-scatter is the next step).
-static void pick_tile(int Nout, int64_t mtiles, int min_chunks, int* bn_out, int* split_out) {
-  int S = std::max(1, std::min(8, env_int("GG_TC_SPLITK", 1)));
+// Output-channel tile and split-K factor.  An M=128 tcgen05.mma from shared memory costs max(~76, N/2) cycles, so a
+// wider N is cheaper per FLOP -- but at batch 64 the wide tiles leave most SMs idle.  Without split: the widest tile that
+// still yields ~1 wave of CTAs.  The 4x4 / 8x8 layers (g_h1, d_h3: 8-32 M tiles, 100-200 K chunks per tile) then end up
+// with N = 64 tiles at 42 % of the MMA rate; for them the K loop of a WIDE tile is split over a thread-block cluster of S
+// CTAs instead, reduced by a push-style reduce-scatter through distributed shared memory (tc_pixgemm_kernel).
+// MEASURED (round 2, profiles/r2p_*): the main loop halves as modelled (d_h3.down 34.3 k -> 18.2 k cycles to accumulator-
+// ready) but the reduce-scatter costs ~20 k cycles per CTA -- distributed shared memory moves ~17-21 B/clk per SM, and a
+// 128 x 256 fp32 partial is 128 KB (96 KB out + 96 KB in at S = 4) -- so the kernels get SLOWER (g_h1.up 17.5 -> 23.3 us,
+// step 1.488 -> 1.549 ms).  Split-K is therefore opt-in: GG_TC_SPLITK=2 / 4 forces S (parity-tested), GG_TC_SPLITK=auto
+// lets the cycle model below choose; default off.  GG_TC_BN forces the tile.
+static void pick_tile(int Nout, int64_t mtiles, int min_chunks, int max_chunks, bool out_bf16, bool allow_split, int* bn_out, int* split_out) {
   int bn = Nout % 256 == 0 ? 256 : (Nout % 128 == 0 ? 128 : 64);
-  if (S == 1) while (bn > 64 && mtiles * (Nout / bn) < 120) bn /= 2;
-  const int forced = env_int("GG_TC_BN", 0);
-  if (forced > 0 && Nout % forced == 0) bn = forced;
-  if (S > 1) {
-    const int64_t tiles = mtiles * (Nout / bn);
-    while (S > 1 && (tiles * S > 148 || min_chunks / S < 4)) S /= 2;
-    while (S > 1 && (int64_t)(S - 1) * ((min_chunks + S - 1) / S) >= min_chunks) S /= 2;   // every rank needs >= 1 chunk
+  while (bn > 64 && mtiles * (Nout / bn) < 120) bn /= 2;
+  const int forced_bn = env_int("GG_TC_BN", 0);
+  if (forced_bn > 0 && Nout % forced_bn == 0) bn = forced_bn;
+  int S = 1;
+  const char* sk = getenv("GG_TC_SPLITK");
+  const bool auto_split = sk && sk[0] == 'a';
+  const int forced_s = auto_split ? 0 : env_int("GG_TC_SPLITK", 1);
+  auto cycles = [&](int b, int s) {        // one CTA: main loop of the heaviest class + fixed cost + the reduce-scatter
+    const int mma = std::max(76, b / 2);
+    return (int64_t)ceil_div(max_chunks, s) * 4 * mma + 6000 + (s > 1 ? 1500 + 6 * b : 0);
+  };
+  auto split_ok = [&](int b, int s) {
+    if (Nout % b != 0 || b % (32 * s) != 0 || b / s < (out_bf16 ? 64 : 32)) return false;
+    if (mtiles * (Nout / b) * s > 148) return false;                                   // clusters: one wave
+    return (int64_t)(s - 1) * ceil_div(min_chunks, s) < min_chunks && min_chunks / s >= 2;   // every rank has work
+  };
+  if (allow_split && forced_s != 1) {
+    const int64_t tiles0 = mtiles * (Nout / bn);
+    int64_t best = cycles(bn, 1) * ceil_div64(tiles0, 148);
+    if (forced_s > 1) best = INT64_MAX;
+    const int bn0 = bn;
+    for (int b : {256, 128})
+      for (int s2 : {2, 4}) {
+        if (forced_s > 1 && s2 != forced_s) continue;
+        if (forced_bn > 0 && b != forced_bn) continue;
+        if (!split_ok(b, s2)) continue;
+        const int64_t c = cycles(b, s2);
+        if (forced_s > 1 ? c < best : c * 100 < best * 85) { best = (forced_s > 1) ? c : c * 100 / 85; bn = b; S = s2; }
+      }
+    (void)bn0;
   }
   *bn_out = bn; *split_out = S;
 }
@@ -890,7 +915,8 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   const int stage_bytes = p.cps * chunk_bytes;
   p.stages = std::max(2, std::min(8, budget / stage_bytes));
   // the epilogue stages the tile in the pipeline buffers; a split-K tile parks its fp32 partial there first (+ bf16 staging behind it)
-  const int out_bytes = p.splitk > 1 ? TILE_M * p.BN * (p.out_bf16 ? 6 : 4) : TILE_M * p.BN * (p.out_bf16 ? 2 : 4);
+  // split-K: S x (BN / S) columns of fp32 partials (= BN * 512 bytes) + the staging of this rank's slice behind them
+  const int out_bytes = p.splitk > 1 ? p.BN * 512 + TILE_M * (p.BN / p.splitk) * (p.out_bf16 ? 2 : 4) : TILE_M * p.BN * (p.out_bf16 ? 2 : 4);
   while (p.stages * stage_bytes < out_bytes) ++p.stages;
   p.stages = std::max(1, std::min(p.stages, env_int("GG_TC_STAGES", p.stages)));
   GG_REQUIRE(p.stages * stage_bytes >= out_bytes, GG_ERR_INVALID, "tc_pixgemm: GG_TC_STAGES too small for the output tile");
@@ -924,7 +950,7 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_bf, con
   c.tw = ceil_div(d->Wo, p.bw); c.th = ceil_div(d->Ho, p.bh); c.td = ceil_div(d->Do, p.bd); c.tn = ceil_div(d->N, p.bn);
   const int64_t mtiles = (int64_t)c.tw * c.th * c.td * c.tn;
   const int taps = d->kd * d->kh * d->kw;
-  pick_tile(d->K, mtiles, taps * (d->C / KCHUNK), &p.BN, &p.splitk);
+  pick_tile(d->K, mtiles, taps * (d->C / KCHUNK), taps * (d->C / KCHUNK), d->small_dtype == GG_BF16, true, &p.BN, &p.splitk);
   {  // B operand straight from the bf16 filter copy w[tap][c][k] (no transposed copy): the reduction index c is the ROW
      // axis, so the tile is MN-major -- BN/64 atoms of [64 c rows][64 k = 128 B], one 4-D box per K chunk
     const uint64_t bdims[4] = {64, (uint64_t)d->C, (uint64_t)(d->K / 64), (uint64_t)taps};
@@ -1023,9 +1049,12 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
         p.cls[ncls++] = c;
       }
   {
-    int min_taps = TC_MAX_TAPS;
-    for (int i = 0; i < ncls; ++i) min_taps = std::min(min_taps, p.cls[i].tap_end - p.cls[i].tap_begin);
-    pick_tile(d->C, tiles, min_taps * (d->K / KCHUNK), &p.BN, &p.splitk);
+    int min_taps = TC_MAX_TAPS, max_taps = 0;
+    for (int i = 0; i < ncls; ++i) {
+      min_taps = std::min(min_taps, p.cls[i].tap_end - p.cls[i].tap_begin);
+      max_taps = std::max(max_taps, p.cls[i].tap_end - p.cls[i].tap_begin);
+    }
+    pick_tile(d->C, tiles, min_taps * (d->K / KCHUNK), max_taps * (d->K / KCHUNK), d->large_dtype == GG_BF16, true, &p.BN, &p.splitk);
   }
   p.ntiles_n = d->C / p.BN;
   for (int i = 0; i < ncls; ++i) p.cls[i].tile_begin *= p.ntiles_n;

@@ -207,15 +207,18 @@ def test_c3_deconv2d_image_side(B, h, w_, Ci):
     assert relerr(st.vars["g/biases"].grad, gb) < TOL
 
 
-@pytest.mark.parametrize("splitk", [2, 4, 8])
+@pytest.mark.parametrize("splitk", ["auto", 2, 4])
 def test_tc_cluster_split_k(splitk, monkeypatch):
-    """GG_TC_SPLITK: the K loop of a tile split over a thread-block cluster and reduced through distributed shared
-    memory must give the same conv / deconv results (fp32-accumulated partials, one final rounding)."""
+    """Cluster split-K (opt-in, GG_TC_SPLITK: auto = the library's cycle model, 2 / 4 forced): the K loop of a wide tile split over a
+    thread-block cluster and combined by the push-style reduce-scatter through distributed shared memory must give the same
+    conv / deconv results (fp32-accumulated partials, one final rounding) -- forward, input gradient, fused statistics."""
     monkeypatch.setenv("GG_TC_SPLITK", str(splitk))
     try:
         test_tc_conv2d("d_h3", 16, 8, 256, 512)
         test_tc_deconv2d("g_h1", 16, 4, 512, 256)
         test_tc_conv2d("d_h2", 16, 16, 128, 256)
+        test_bn_backward_reductions_fused_into_dgrad("conv", 16, 16, 128, 256, 512, 2, monkeypatch)      # d_h2 -> bn2 -> d_h3: split dgrad + fused reductions
+        test_bn_backward_reductions_fused_into_dgrad("deconv", 16, 4, 512, 256, 128, 1, monkeypatch)
     finally:
         monkeypatch.delenv("GG_TC_SPLITK", raising=False)
 
