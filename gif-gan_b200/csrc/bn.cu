@@ -80,13 +80,17 @@ colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_
     // one-row-per-trip loop was latency-bound at ~1.5 TB/s)
     constexpr int UB = GG_BN_UB;
     const int64_t base = (int64_t)grp * rows_per_group;
-    const int64_t rstep = (int64_t)gridDim.x * ty_dim;
-    for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += UB * rstep) {
+    // a CTA owns a CONTIGUOUS chunk of rows (its warps stream consecutive 128-512 byte rows: whole DRAM pages), not every
+    // gridDim.x-th row block (that layout touched a different page with every load: ~1.7 TB/s from HBM)
+    const int64_t rows_per_cta = (rows_per_group + gridDim.x - 1) / gridDim.x;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(rows_per_group, r_begin + rows_per_cta);
+    const int64_t rstep = ty_dim;
+    for (int64_t r = r_begin + ty; r < r_end; r += UB * rstep) {
       float xv[UB][VEC], dv[UB][VEC];
 #pragma unroll
       for (int ub = 0; ub < UB; ++ub) {
         const int64_t rr = r + ub * rstep;
-        if (rr < rows_per_group) {
+        if (rr < r_end) {
           const int64_t off = (base + rr) * C + c;
           if (VEC == 4) {
             float4 t = ld4(x + off); xv[ub][0] = t.x; xv[ub][1] = t.y; xv[ub][2] = t.z; xv[ub][3] = t.w;
@@ -150,7 +154,7 @@ __global__ void bn_infer_stats_kernel(const float* __restrict__ mm, const float*
 // per-channel constants live in registers and the row loop has no divisions.  Every thread derives mean / rstd of
 // its channels from the fp64 sums (cheap, redundant); the first row-block also stores them for the backward pass and
 // applies the EMA updates, sequentially over the row groups (ops.py:18-24: real batch first, then fake).
-template <typename TX, typename TY, int VEC>
+template <typename TX, typename TY, int VEC, int UB>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_train_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows_per_group, int C, int groups,
                       const float* __restrict__ gamma, const float* __restrict__ beta, const double* __restrict__ sums, float eps,
@@ -164,6 +168,23 @@ bn_train_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows
   const int R = bn_replicas(C, groups);
   const double inv = 1.0 / (double)rows_per_group;
   if (!active) return;
+  const int64_t base = (int64_t)grp * rows_per_group;
+  const int64_t rows_per_cta = (rows_per_group + gridDim.x - 1) / gridDim.x;      // contiguous row chunk per CTA (see colsum_kernel)
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(rows_per_group, r_begin + rows_per_cta);
+  const int64_t rstep = ty_dim;
+  // The kernel is a chain of memory round trips (statistics, then one per load batch; ncu: SMs active 60 % of the launch,
+  // DRAM at 20 %): the first batch of x is requested BEFORE the statistics are read, so that the two latencies overlap.
+  float o[UB][VEC];
+  int64_t r = r_begin + ty;
+#pragma unroll
+  for (int ub = 0; ub < UB; ++ub) {
+    const int64_t rr = r + ub * rstep;
+    if (rr < r_end) {
+      const int64_t off = (base + rr) * C + c;
+      if (VEC == 4) { float4 t = ld4(x + off); o[ub][0] = t.x; o[ub][1] = t.y; o[ub][2] = t.z; o[ub][3] = t.w; }
+      else o[ub][0] = ldf(x + off);
+    }
+  }
   float mu[VEC], rs[VEC], ga[VEC], be[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -195,24 +216,11 @@ bn_train_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows
       }
     }
   }
-  const int64_t base = (int64_t)grp * rows_per_group;
-  const int64_t rstep = (int64_t)gridDim.x * ty_dim;
-  constexpr int UB = GG_BN_UB;
-  for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += UB * rstep) {
-    float o[UB][VEC];
+  while (r < r_end) {
 #pragma unroll
     for (int ub = 0; ub < UB; ++ub) {
       const int64_t rr = r + ub * rstep;
-      if (rr < rows_per_group) {
-        const int64_t off = (base + rr) * C + c;
-        if (VEC == 4) { float4 t = ld4(x + off); o[ub][0] = t.x; o[ub][1] = t.y; o[ub][2] = t.z; o[ub][3] = t.w; }
-        else o[ub][0] = ldf(x + off);
-      }
-    }
-#pragma unroll
-    for (int ub = 0; ub < UB; ++ub) {
-      const int64_t rr = r + ub * rstep;
-      if (rr < rows_per_group) {
+      if (rr < r_end) {
         const int64_t off = (base + rr) * C + c;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) o[ub][v] = fmaf((o[ub][v] - mu[v]) * rs[v], ga[v], be[v]);
@@ -221,12 +229,22 @@ bn_train_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, int64_t rows
         else stf(y + off, o[ub][0]);
       }
     }
+    r += UB * rstep;
+#pragma unroll
+    for (int ub = 0; ub < UB; ++ub) {
+      const int64_t rr = r + ub * rstep;
+      if (rr < r_end) {
+        const int64_t off = (base + rr) * C + c;
+        if (VEC == 4) { float4 t = ld4(x + off); o[ub][0] = t.x; o[ub][1] = t.y; o[ub][2] = t.z; o[ub][3] = t.w; }
+        else o[ub][0] = ldf(x + off);
+      }
+    }
   }
 }
 
 // ---- backward apply (+ gamma / beta gradients from the same reductions) ----------------------------------------------
-template <typename TX, typename TD, typename TO, int VEC>
-__global__ void __launch_bounds__(BN_THREADS)
+template <typename TX, typename TD, typename TO, int VEC, int UB>
+__global__ void __launch_bounds__(BN_THREADS, 3)
 bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __restrict__ dx, int64_t rows_per_group, int C,
                     int groups, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const double* __restrict__ sums, float* __restrict__ dgamma,
@@ -239,6 +257,24 @@ bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
   const int R = (sums != nullptr) ? bn_replicas(C, groups) : 1;
   const float invM = 1.f / (float)rows_per_group;
   if (!active) return;
+  const int64_t base = (int64_t)grp * rows_per_group;
+  const int64_t rows_per_cta = (rows_per_group + gridDim.x - 1) / gridDim.x;      // contiguous row chunk per CTA (see colsum_kernel)
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(rows_per_group, r_begin + rows_per_cta);
+  const int64_t rstep = ty_dim;
+  // first batch of (x, dy) requested before the per-channel constants and reductions are read (see bn_train_apply_kernel)
+  float xv[UB][VEC], dv[UB][VEC];
+  int64_t r = r_begin + ty;
+#pragma unroll
+  for (int ub = 0; ub < UB; ++ub) {
+    const int64_t rr = r + ub * rstep;
+    if (rr < r_end) {
+      const int64_t off = (base + rr) * C + c;
+      if (VEC == 4) {
+        float4 t = ld4(x + off); xv[ub][0] = t.x; xv[ub][1] = t.y; xv[ub][2] = t.z; xv[ub][3] = t.w;
+        float4 u = ld4(dy + off); dv[ub][0] = u.x; dv[ub][1] = u.y; dv[ub][2] = u.z; dv[ub][3] = u.w;
+      } else { xv[ub][0] = ldf(x + off); dv[ub][0] = ldf(dy + off); }
+    }
+  }
   float mu[VEC], rs[VEC], ga[VEC], be[VEC], sg[VEC], sgx[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -258,26 +294,11 @@ bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
       if (dgamma) dgamma[c + v] += (float)b;
     }
   }
-  const int64_t base = (int64_t)grp * rows_per_group;
-  const int64_t rstep = (int64_t)gridDim.x * ty_dim;
-  constexpr int UB = GG_BN_UB;
-  for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows_per_group; r += UB * rstep) {
-    float xv[UB][VEC], dv[UB][VEC];
+  while (r < r_end) {
 #pragma unroll
     for (int ub = 0; ub < UB; ++ub) {
       const int64_t rr = r + ub * rstep;
-      if (rr < rows_per_group) {
-        const int64_t off = (base + rr) * C + c;
-        if (VEC == 4) {
-          float4 t = ld4(x + off); xv[ub][0] = t.x; xv[ub][1] = t.y; xv[ub][2] = t.z; xv[ub][3] = t.w;
-          float4 u = ld4(dy + off); dv[ub][0] = u.x; dv[ub][1] = u.y; dv[ub][2] = u.z; dv[ub][3] = u.w;
-        } else { xv[ub][0] = ldf(x + off); dv[ub][0] = ldf(dy + off); }
-      }
-    }
-#pragma unroll
-    for (int ub = 0; ub < UB; ++ub) {
-      const int64_t rr = r + ub * rstep;
-      if (rr < rows_per_group) {
+      if (rr < r_end) {
         const int64_t off = (base + rr) * C + c;
         float xh[VEC], u[VEC], o[VEC];
 #pragma unroll
@@ -287,6 +308,18 @@ bn_bwd_apply_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, TO* __r
         for (int v = 0; v < VEC; ++v) o[v] = train ? ga[v] * rs[v] * (dv[ub][v] - sg[v] - xh[v] * sgx[v]) : ga[v] * rs[v] * dv[ub][v];
         if (VEC == 4) st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
         else stf(dx + off, o[0]);
+      }
+    }
+    r += UB * rstep;
+#pragma unroll
+    for (int ub = 0; ub < UB; ++ub) {
+      const int64_t rr = r + ub * rstep;
+      if (rr < r_end) {
+        const int64_t off = (base + rr) * C + c;
+        if (VEC == 4) {
+          float4 t = ld4(x + off); xv[ub][0] = t.x; xv[ub][1] = t.y; xv[ub][2] = t.z; xv[ub][3] = t.w;
+          float4 u = ld4(dy + off); dv[ub][0] = u.x; dv[ub][1] = u.y; dv[ub][2] = u.z; dv[ub][3] = u.w;
+        } else { xv[ub][0] = ldf(x + off); dv[ub][0] = ldf(dy + off); }
       }
     }
   }
@@ -411,9 +444,13 @@ static void launch_colsum(const void* x, const void* dy, int64_t rpg, int C, int
 }
 
 // streaming (apply) kernels: same 2-D mapping, but sized to fill the machine (no atomics at the end)
-static ColGeom apply_geom(int64_t rows_per_group, int C, int groups, bool vec_ok) {
+static ColGeom apply_geom(int64_t rows_per_group, int C, int groups, bool vec_ok, int per_sm_dflt = 4) {
   ColGeom g = col_geom(rows_per_group, C, groups, vec_ok);
-  int64_t want = std::max<int64_t>(1, (148 * 6) / ((int64_t)g.cblocks * groups));
+  // CTAs per SM of the streaming kernels: 256 threads x <= 64 registers -> 4 resident CTAs per SM; a grid of exactly one
+  // resident wave (148 x 4) avoids the half-empty second wave the earlier 148 x 6 produced (GG_APPLY_PER_SM: A/B knob)
+  static const int per_sm_env = [] { const char* v = getenv("GG_APPLY_PER_SM"); return (v && *v) ? atoi(v) : 0; }();
+  const int per_sm = per_sm_env > 0 ? per_sm_env : per_sm_dflt;
+  int64_t want = std::max<int64_t>(1, (148 * per_sm) / ((int64_t)g.cblocks * groups));
   int64_t maxr = ceil_div64(rows_per_group, (int64_t)g.ty * 2);  // >= 2 rows per thread
   g.rblocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, maxr));
   return g;
@@ -481,10 +518,14 @@ static int bn_finalize_and_apply(const void* x, int32_t x_dt, void* y, int32_t y
                                  cudaStream_t st) {
   const ColGeom g = apply_geom(rpg, C, groups, aligned16(x) && aligned16(y));
   dim3 grid(g.rblocks, g.cblocks, groups);
+  // GG_APPLY_UB=8: 8 loads in flight per thread (97 registers -> 2 resident CTAs per SM: pair it with GG_APPLY_PER_SM=2); default 4
+  static const int ub_env = [] { const char* v = getenv("GG_APPLY_UB"); return (v && *v) ? atoi(v) : 4; }();
+  const bool ub8 = ub_env >= 8 && ceil_div64(rpg, (int64_t)g.rblocks * g.ty) > 4;
 #define GG_APPLY(TX, TY)                                                                                              \
   do {                                                                                                                \
-    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_train_apply_kernel<TX, TY, 4>, (const TX*)x, (TY*)y, rpg, C, groups, gamma, beta, sums, eps, decay, moving_mean, moving_var, save_mean, save_rstd, act, act_param, g.tx); \
-    else Launch(grid, BN_THREADS, 0, st)(bn_train_apply_kernel<TX, TY, 1>, (const TX*)x, (TY*)y, rpg, C, groups, gamma, beta, sums, eps, decay, moving_mean, moving_var, save_mean, save_rstd, act, act_param, g.tx);          \
+    if (g.vec == 4 && ub8) Launch(grid, BN_THREADS, 0, st)(bn_train_apply_kernel<TX, TY, 4, 8>, (const TX*)x, (TY*)y, rpg, C, groups, gamma, beta, sums, eps, decay, moving_mean, moving_var, save_mean, save_rstd, act, act_param, g.tx); \
+    else if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_train_apply_kernel<TX, TY, 4, 4>, (const TX*)x, (TY*)y, rpg, C, groups, gamma, beta, sums, eps, decay, moving_mean, moving_var, save_mean, save_rstd, act, act_param, g.tx); \
+    else Launch(grid, BN_THREADS, 0, st)(bn_train_apply_kernel<TX, TY, 1, 4>, (const TX*)x, (TY*)y, rpg, C, groups, gamma, beta, sums, eps, decay, moving_mean, moving_var, save_mean, save_rstd, act, act_param, g.tx);          \
   } while (0)
   if (x_dt == GG_F32 && y_dt == GG_F32) GG_APPLY(float, float);
   else if (x_dt == GG_F32) GG_APPLY(float, bf16);
@@ -649,12 +690,12 @@ extern "C" int gg_bn_bwd(const void* x, int32_t x_dt, const void* dy, int32_t dy
     if (rc) return rc;
   }
 apply:
-  const ColGeom g = apply_geom(rpg, C, groups, vec_ok);
+  const ColGeom g = apply_geom(rpg, C, groups, vec_ok, 3);      // bn_bwd_apply: 80 registers -> 3 resident CTAs per SM
   dim3 grid(g.rblocks, g.cblocks, groups);
 #define GG_BA(TX, TD, TO)                                                                                                          \
   do {                                                                                                                             \
-    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 4>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, groups, gamma, beta, save_mean, save_rstd, sums, dgamma, dbeta, act, act_param, train, g.tx); \
-    else Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 1>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, groups, gamma, beta, save_mean, save_rstd, sums, dgamma, dbeta, act, act_param, train, g.tx);          \
+    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 4, 4>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, groups, gamma, beta, save_mean, save_rstd, sums, dgamma, dbeta, act, act_param, train, g.tx); \
+    else Launch(grid, BN_THREADS, 0, st)(bn_bwd_apply_kernel<TX, TD, TO, 1, 4>, (const TX*)x, (const TD*)dy, (TO*)dx, rpg, C, groups, gamma, beta, save_mean, save_rstd, sums, dgamma, dbeta, act, act_param, train, g.tx);          \
   } while (0)
   const int key = (x_dt == GG_BF16 ? 4 : 0) | (dy_dt == GG_BF16 ? 2 : 0) | (dx_dt == GG_BF16 ? 1 : 0);
   switch (key) {
@@ -691,13 +732,15 @@ bias_grad_kernel(const TD* __restrict__ dy, float* __restrict__ db, int64_t rows
   for (int v = 0; v < VEC; ++v) s[v] = 0.f;
   if (c < C) {
     constexpr int UB = GG_BN_UB;                            // 4 rows per trip, loads first (see colsum_kernel)
-    const int64_t rstep = (int64_t)gridDim.x * ty_dim;
-    for (int64_t r = (int64_t)blockIdx.x * ty_dim + ty; r < rows; r += UB * rstep) {
+    const int64_t rows_per_cta = (rows + gridDim.x - 1) / gridDim.x;              // contiguous row chunk per CTA (see colsum_kernel)
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = min(rows, r_begin + rows_per_cta);
+    const int64_t rstep = ty_dim;
+    for (int64_t r = r_begin + ty; r < r_end; r += UB * rstep) {
       float t[UB][VEC];
 #pragma unroll
       for (int ub = 0; ub < UB; ++ub) {
         const int64_t rr = r + ub * rstep;
-        if (rr < rows) {
+        if (rr < r_end) {
           if (VEC == 4) { float4 q = ld4(dy + rr * C + c); t[ub][0] = q.x; t[ub][1] = q.y; t[ub][2] = q.z; t[ub][3] = q.w; }
           else t[ub][0] = ldf(dy + rr * C + c);
         } else {

@@ -58,6 +58,9 @@ SIGNATURES = {
     "gg_linear_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "gg_linear_dgrad": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "gg_linear_wgrad": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "gg_linear_bn_ok": (C.c_int, [_i32, _i32, _i32, _i32, _i32]),
+    "gg_linear_bn_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _f32, _vp]),
+    "gg_linear_bn_bwd": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "gg_bn_workspace_bytes": (_sz, [_i32, _i32]),
     "gg_bn_fwd_train": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _f32, _vp, _sz, _vp]),
     "gg_bn_fwd_infer": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _f32, _vp]),

@@ -303,11 +303,15 @@ def _require_cuda(t, what):
 
 
 def _wtensor(var: Var, requires_grad: bool):
-    """The autograd handle of a variable: its data tensor with requires_grad set by the
-    current var_list (see `trainable`)."""
-    t = var.data
-    if t.requires_grad != requires_grad:
-        t.requires_grad_(requires_grad)
+    """The autograd handle of a variable for ONE op call: a fresh detached alias of its data with requires_grad set by the
+    current var_list (see `trainable`).  A fresh leaf per call, not the stored tensor itself: a leaf's AccumulateGrad node is
+    cached on the tensor together with the stream it was created on, and it stays alive as long as ANY graph that used the
+    tensor does -- e.g. the loss tensor of an earlier eager update that the caller still holds.  Re-using such a leaf while a
+    CUDA graph is being captured made the autograd engine synchronise the capture stream with that (uncaptured) stream:
+    cudaErrorStreamCaptureIsolation.  The ops write filter gradients themselves (Var.grad) and return None to autograd."""
+    t = var.data.detach()
+    if requires_grad:
+        t.requires_grad_(True)
     return t
 
 
@@ -420,6 +424,7 @@ class _BnInfo:
         self.bwd_version = -1
 
 
+FUSE_LINEAR_BN = os.environ.get("GG_FUSE_LINEAR_BN", "0") == "1"    # opt-in: thin linear + batch norm + activation as one kernel per direction (csrc/linbn.cu: measured break-even)
 FUSE_BN_BWD = os.environ.get("GG_FUSE_BN_BWD", "1") != "0"    # A/B switch: batch-norm backward reductions in the dgrad epilogue
 
 
@@ -938,6 +943,26 @@ class _FusedBN(torch.autograd.Function):
     def forward(ctx, x, w, b, gamma, beta, prod, bn, train, act, act_param, out_dtype, groups, Cc, in_bn=None, info=None):
         L = cabi.lib()
         ctx.in_bn, ctx.info = in_bn, info
+        ctx.linbn = False
+        if (FUSE_LINEAR_BN and train and isinstance(prod, _LinearProducer) and x.dim() == 2
+                and L.gg_linear_bn_ok(x.shape[0], x.shape[1], prod.out_dim, Cc, groups)):
+            # thin linear + batch statistics + normalise + activation in ONE launch (a CTA owns whole channels)
+            rows, in_dim = x.shape
+            pre = torch.empty((rows, prod.out_dim), dtype=torch.float32, device=x.device)
+            y = torch.empty((rows, prod.out_dim), dtype=out_dtype, device=x.device)
+            save_mean = torch.empty((1, Cc), dtype=torch.float32, device=x.device)
+            save_rstd = torch.empty((1, Cc), dtype=torch.float32, device=x.device)
+            mm = bn.moving_mean.data if bn.moving_mean is not None else None
+            mv = bn.moving_variance.data if bn.moving_variance is not None else None
+            check(L.gg_linear_bn_fwd(ptr(x), dt(x), ptr(prod.wvar.data), ptr(b), ptr(gamma), ptr(beta), ptr(mm), ptr(mv), ptr(pre), ptr(y), dt(y),
+                                     ptr(save_mean), ptr(save_rstd), rows, in_dim, prod.out_dim, Cc, bn.epsilon, bn.momentum, ACT[act],
+                                     float(act_param), stream()), "gg_linear_bn_fwd")
+            ctx.prod, ctx.bn, ctx.train, ctx.act, ctx.act_param, ctx.groups, ctx.Cc = prod, bn, train, act, act_param, groups, Cc
+            ctx.x_dtype, ctx.linbn = x.dtype, True
+            ctx.save_for_backward(x, pre, gamma, beta, save_mean, save_rstd)
+            if DEBUG_TAP is not None:
+                DEBUG_TAP.setdefault("fwd", []).append((prod.wvar.name, pre, y))
+            return y
         fused_stats = train and prod.fuses_stats and Cc == prod.out_shape()[-1]
         stats = _zeroed_f64(L.gg_bn_workspace_bytes(Cc, groups) // 8, x.device)[0] if fused_stats else None   # [replicas][groups][2][C]
         pre = prod.fwd(x, b, stats=stats, groups=groups)
@@ -980,6 +1005,14 @@ class _FusedBN(torch.autograd.Function):
         rows = pre.numel() // Cc
         need_w, need_b = ctx.needs_input_grad[1], prod.bvar is not None and ctx.needs_input_grad[2]
         need_g, need_be = gamma is not None and ctx.needs_input_grad[3], beta is not None and ctx.needs_input_grad[4]
+        if ctx.linbn and need_w and not ctx.needs_input_grad[0] and DEBUG_TAP is None:
+            # batch-norm backward + filter gradient of the thin linear in ONE launch (dpre never leaves the CTA)
+            r_, in_dim = x.shape
+            check(L.gg_linear_bn_bwd(ptr(x), dt(x), ptr(pre), ptr(dy), dt(dy), ptr(gamma), ptr(beta), ptr(save_mean), ptr(save_rstd),
+                                     ptr(prod.wvar.grad), ptr(bn.gamma.grad) if need_g else None, ptr(bn.beta.grad) if need_be else None,
+                                     r_, in_dim, prod.out_dim, Cc, ACT[ctx.act], float(ctx.act_param), 1 if act_dtype() == torch.bfloat16 else 0,
+                                     stream()), "gg_linear_bn_bwd")
+            return (None,) * 15
         dpre = torch.empty(pre.shape, dtype=act_dtype(), device=pre.device)     # GEMM operand precision
         nbytes = L.gg_bn_workspace_bytes(Cc, ctx.groups)
         info = ctx.info

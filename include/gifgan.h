@@ -144,6 +144,24 @@ int gg_linear_dgrad(const void* dy, int32_t dy_dtype, const float* matrix, void*
 int gg_linear_wgrad(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, float* dmatrix, float* dbias,
                     int32_t rows, int32_t in_dim, int32_t out_dim, void* stream);
 
+/* ---- thin linear + train-mode batch norm + activation in one launch per direction --------------------------------------
+ * The generator's input projection relu(g_bn0(reshape(linear(z, 8192), [-1,4,4,512]))) (model.py:304-307): x [rows, in_dim]
+ * with in_dim <= 128 and rows <= 128, Matrix [in_dim, out_dim]; the batch norm normalises channel c = column % C over
+ * rows * (out_dim / C) values.  A CTA owns whole channels (all their columns, all rows), so statistics and backward
+ * reductions stay inside it.  gg_linear_bn_ok() != 0 says the shape is eligible (otherwise the calls return
+ * GG_ERR_UNSUPPORTED and the caller composes gg_linear_* with gg_bn_*).
+ * fwd: pre [rows, out_dim] fp32 (kept for backward), y = act(bn(pre)) in y_dtype, save_mean / save_rstd [C], EMAs updated.
+ * bwd: dmatrix += x^T dpre, dgamma +=, dbeta += (NULL: skipped); dpre is rounded to bf16 first when round_bf16 != 0 (what
+ *      the two-kernel path does when activations are bf16).  The producer's bias gradient is exactly zero in train mode. */
+int gg_linear_bn_ok(int32_t rows, int32_t in_dim, int32_t out_dim, int32_t C, int32_t groups);
+int gg_linear_bn_fwd(const void* x, int32_t x_dtype, const float* matrix, const float* bias, const float* gamma, const float* beta,
+                     float* moving_mean, float* moving_var, float* pre, void* y, int32_t y_dtype, float* save_mean, float* save_rstd,
+                     int32_t rows, int32_t in_dim, int32_t out_dim, int32_t C, float eps, float decay, int32_t act, float act_param,
+                     void* stream);
+int gg_linear_bn_bwd(const void* x, int32_t x_dtype, const float* pre, const void* dy, int32_t dy_dtype, const float* gamma, const float* beta,
+                     const float* save_mean, const float* save_rstd, float* dmatrix, float* dgamma, float* dbeta, int32_t rows,
+                     int32_t in_dim, int32_t out_dim, int32_t C, int32_t act, float act_param, int32_t round_bf16, void* stream);
+
 /* ---- batch norm (ops.py:10-24: tf.contrib.layers.batch_norm; recurrent_DCGAN.py:190-191) ----
  * x is [rows, C] (all leading axes flattened).  groups>1 normalises `groups` equal row
  * blocks independently (the reference's separate D(real)/D(fake) calls batched into one

@@ -329,3 +329,50 @@ def test_get_std_and_errors():
         ops.lrelu(torch.zeros(4))
     with pytest.raises(TypeError):
         ops.lrelu(torch.zeros(4, device="cuda", dtype=torch.float16))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,i,o,C", [(64, 100, 8192, 512), (128, 100, 2048, 128), (37, 110, 1024, 1024), (8, 100, 512, 128)])
+def test_linear_bn_act_one_kernel_per_direction(precision, rows, i, o, C, monkeypatch):
+    """gg_linear_bn_fwd / gg_linear_bn_bwd (the generator's input projection: thin linear + train-mode batch norm + ReLU,
+    model.py:304-307) against the composed path (gg_linear_fwd + statistics + apply; colsum + bn_bwd_apply + thin_wgrad) and
+    the float64 oracle: output, EMAs, and the gradients of Matrix, gamma, beta."""
+    from gifgan import ops as _o
+    rs = np.random.RandomState(rows + o)
+    x, M, b = rs.uniform(-1, 1, (rows, i)), rs.randn(i, o) * 0.05, rs.randn(o) * 0.1
+    gam, bet = rs.rand(C) + 0.5, rs.randn(C) * 0.2
+    dy = rs.randn(rows, o)
+    res = []
+    for fuse in (False, True):
+        monkeypatch.setattr(_o, "FUSE_LINEAR_BN", fuse)
+        bn = _o.batch_norm(name="bn")
+        ops, st, tv = _setup(precision, lambda t: _o.linear(t, o, "l", bn=bn, bn_channels=C, act="relu"), [(rows, i)])
+        st.load_state_dict({"l/Matrix": M, "l/bias": b, "bn/gamma": gam, "bn/beta": bet, "bn/moving_mean": np.zeros(C), "bn/moving_variance": np.ones(C)})
+        assert bool(ops.cabi.lib().gg_linear_bn_ok(rows, i, o, C, 1))
+        xt = torch.tensor(x, dtype=torch.float32, device="cuda")                      # z stays fp32 (model.py feeds it as such)
+        n0 = ops.cabi.launch_count()
+        with ops.trainable(tv):
+            y = ops.linear(xt, o, "l", bn=bn, bn_channels=C, act="relu")
+            y.backward(_cuda(dy, precision, grad=False))
+        res.append(dict(y=y.detach().float().cpu(), n=ops.cabi.launch_count() - n0, mm=st.vars["bn/moving_mean"].data.cpu().clone(),
+                        mv=st.vars["bn/moving_variance"].data.cpu().clone(),
+                        g={k: st.vars[k].grad.cpu().clone() for k in ("l/Matrix", "bn/gamma", "bn/beta", "l/bias")}))
+    two, one = res
+    assert one["n"] == 2 and two["n"] >= 5, (one["n"], two["n"])
+    tol = TOL[precision]
+    # float64 oracle
+    xr = torch.tensor(x, dtype=torch.float64)
+    Mr, br = torch.tensor(M, dtype=torch.float64, requires_grad=True), torch.tensor(b, dtype=torch.float64, requires_grad=True)
+    gr, ber = torch.tensor(gam, dtype=torch.float64, requires_grad=True), torch.tensor(bet, dtype=torch.float64, requires_grad=True)
+    pre = (xr @ Mr + br).reshape(-1, C)
+    mu, var = pre.mean(0), pre.var(0, unbiased=False)
+    yr = torch.relu((pre - mu) / torch.sqrt(var + 1e-5) * gr + ber).reshape(rows, o)
+    dyr = torch.tensor(dy, dtype=y.dtype).double()
+    gM, gg, gb = torch.autograd.grad(yr, [Mr, gr, ber], dyr)
+    for r_ in (one, two):
+        assert relerr(r_["y"], yr) < tol
+        assert relerr(r_["mm"], 0.1 * mu.detach()) < max(tol, 1e-4) and relerr(r_["mv"], 0.9 + 0.1 * var.detach()) < max(tol, 1e-4)
+        l2 = lambda a, w: float((a.double() - w).norm() / w.norm())
+        assert (relerr(r_["g"]["l/Matrix"], gM) < tol) if precision == "fp32" else (l2(r_["g"]["l/Matrix"], gM) < tol)
+        assert relerr(r_["g"]["bn/gamma"], gg) < tol and relerr(r_["g"]["bn/beta"], gb) < tol
+        assert float(r_["g"]["l/bias"].abs().max()) == 0.0          # exactly zero through a train-mode batch norm: left untouched

@@ -103,6 +103,9 @@ def by_layer(tag):
                         dram_write_bytes=float(row[ix["dram__bytes_write.sum"]]) * scale[units[ix["dram__bytes_write.sum"]]],
                         tensor_pct=float(row[ix["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]]))
     import json
+    sys.path.insert(0, ROOT)
+    import bench
+    out["_kernel_source_sha"] = bench.kernel_source_sha()        # bench.py quotes `traffic` only from a capture of the CURRENT kernel sources
     with open(os.path.join(P, f"{tag}_ncu_by_layer.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", f"{tag}_ncu_by_layer.json", len(out), "layers")
