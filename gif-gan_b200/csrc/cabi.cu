@@ -83,6 +83,8 @@ int tc_conv_up_cat(const gg_conv_desc*, const void*, const void*, const float*, 
                    const gg_bnbwd_args* bnb = nullptr);
 void tc_set_repeat(int);
 void tc_set_prof(void*);
+int tc_set_workspace(void*, size_t);
+size_t tc_workspace_bytes();
 }  // namespace gg
 
 using namespace gg;
@@ -97,6 +99,9 @@ extern "C" void gg_debug_set_repeat(int n) { g_cabi_repeat = n < 1 ? 1 : n; tc_s
 #define GG_REPEAT(call) do { int rc_ = GG_OK; for (int r_ = 0; r_ < g_cabi_repeat && rc_ == GG_OK; ++r_) rc_ = (call); return rc_; } while (0)
 // measurement hook: device buffer of 512 x 8 uint64 receiving a per-CTA clock64 breakdown of tc_pixgemm (NULL = off)
 extern "C" void gg_debug_set_prof(void* buf) { tc_set_prof(buf); }
+// workspace of the split-K tensor-core launches (see include/gifgan.h)
+extern "C" size_t gg_workspace_bytes(void) { return tc_workspace_bytes(); }
+extern "C" int gg_set_workspace(void* device_buf, size_t bytes) { return tc_set_workspace(device_buf, bytes); }
 
 extern "C" int gg_device_arch(void) {
   int dev = 0, major = 0, minor = 0;

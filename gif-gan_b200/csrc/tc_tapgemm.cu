@@ -122,7 +122,10 @@ struct TcPixParams {
                               // 1 = MN-major atoms (conv_down: N = K, reduce over C), 2 = K-major, one box per parity class (up_cat)
   int ncat;                   // bmode 2: parity classes
   TcCatOrigin cat_origin[TC_MAX_TAPS];            // bmode 2: shift -> first tap (kd, kh, kw) of its class box (may be < 0: TMA zero-fills)
-  int splitk;                 // cluster size along K: the CTAs of a cluster share one output tile (1 = no cluster)
+  int splitk;                 // S: the K loop of an output tile is split over S CTAs (blockIdx.x % S = rank); 1 = no split
+  int sk_mode;                // how the S fp32 partials meet: 0 = thread-block cluster + distributed shared memory, 1 = through L2 (sk_*)
+  CUtensorMap skmap;          // sk_mode 1: this launch's scratch as a 2-D fp32 tensor [tiles * S * BN/32 * 128 rows][32], box = (32, 128)
+  unsigned int* sk_cnt;       // sk_mode 1: [tiles][2] arrive / depart counters, zero at rest
   unsigned long long* prof;   // optional per-CTA clock64 breakdown (tools/tc_sweep.py --prof), 8 slots per CTA
   double* stats;              // optional fused batch-norm statistics [groups][2][Nout] (fp32 output only)
   int stats_groups;
@@ -175,6 +178,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 1);
+  const uint32_t sk_bar = bar_base + 8u * (2 * p.stages + 2);          // split-K through L2: the partials of my slice have landed
 
   // ---- which tile ------------------------------------------------------------------------
   const int S = p.splitk;                      // cluster (S, 1, 1): rank in cluster == blockIdx.x % S
@@ -205,6 +209,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     // full: one arrival per producer warp that touches the stage (2 operands x cps chunk slots)
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2 * p.cps); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(sk_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.bmap);
   }
@@ -277,7 +282,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       s += sstep;
       if (s >= nst) { s -= nst; ph ^= 1u; }
     }
-    if (prof && warp == 0 && lane == 0) { prof[0] = (unsigned long long)(clock64() - t_setup); prof[1] = 0; }
+    if (prof && warp == 0 && lane == 0) prof[0] = (unsigned long long)(clock64() - t_setup);
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool b_mn = (p.bmode == 1);
@@ -334,7 +339,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const int row = q * 32 + lane;                 // accumulator row = pixel within the tile
   const uint32_t row_off = (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
-  const uint32_t mask_smem = bar_base + 8u * (2 * p.stages + 2);        // 4 x u32 after the barriers
+  const uint32_t mask_smem = bar_base + 8u * (2 * p.stages + 4);        // 4 x u32 after the barriers (16-byte aligned)
   const uint32_t bnb_consts = mask_smem + 16u;                          // float4 {rstd, -mean*rstd, gamma, beta} per column of the N tile
   const uint32_t bnb_part = bnb_consts + 16u * (uint32_t)p.BN;          // float [4 warps][2][BN]: per-warp partial reductions
   long long t_acc = 0;
@@ -374,7 +379,65 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   // (The first version pulled row slices from all ranks and let the leader alone run the epilogue: ~13 k cycles at S = 8.)
   const int ncol = p.BN / S;                       // columns this rank finishes
   const int ncol0 = rank * ncol;                   // first of them within the N tile
-  if (S > 1) {
+  if (S > 1 && p.sk_mode == 1) {
+    // ---- the same reduce-scatter THROUGH L2 (no cluster): deterministic, and ~6 k cycles where the DSMEM exchange took ~20 k ----
+    // Every rank parks its fp32 partial in global scratch with TMA stores (BN/32 boxes of [128 rows][32 columns], written from
+    // the 128B-swizzled staging this kernel's fp32 epilogue uses anyway), counts itself in, waits until all S ranks of the tile
+    // have done so (the launch is ONE wave with one CTA per SM, so they are co-resident; the spin is bounded) and TMA-loads the
+    // boxes of ITS column slice from all S partials into R[source][block] -- exactly where the DSMEM variant receives them.
+    // The last rank to leave re-arms the counters (they are zero whenever no launch is using them).
+    if (epi) {
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const uint32_t blk = smem_base + (uint32_t)(c0 >> 5) * (TILE_M * 128u) + row_off;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((((uint32_t)g) ^ sw) << 4)), "r"(r[g * 4]), "r"(r[g * 4 + 1]),
+                       "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3]) : "memory");
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        const long long k0 = clock64();
+        long long k1, k2, k3;
+        const int nbk = p.BN >> 5, nb = ncol >> 5;     // 32-column boxes of the tile / of a slice
+        for (int b = 0; b < nbk; ++b)
+          tma_store_2d(&p.skmap, smem_base + (uint32_t)b * (TILE_M * 128u), 0, ((tile * S + rank) * nbk + b) * TILE_M);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // written (not only read): the staging is free again, too
+        k1 = clock64();
+        fence_proxy_async_all();
+        __threadfence();
+        unsigned int* cnt = p.sk_cnt + 2 * tile;
+        atomicAdd(cnt, 1u);
+        if (ld_acquire_gpu(cnt) < (uint32_t)S) {
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(cnt) < (uint32_t)S) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000ll) __trap();
+          }
+        }
+        k2 = clock64();
+        __threadfence();
+        fence_proxy_async_all();
+        mbar_expect_tx(sk_bar, (uint32_t)(S * nb) * (TILE_M * 128u));
+        for (int src = 0; src < S; ++src)
+          for (int b = 0; b < nb; ++b)
+            tma_load_2d(smem_base + (uint32_t)(src * nb + b) * (TILE_M * 128u), &p.skmap, sk_bar, 0, ((tile * S + src) * nbk + rank * nb + b) * TILE_M);
+        if (atomicAdd(cnt + 1, 1u) == (unsigned int)(S - 1)) { cnt[0] = 0u; cnt[1] = 0u; __threadfence(); }
+        if (prof) {   // exchange breakdown, 16 cycles per unit: [staged since accumulator-ready | stores complete | all ranks in | loads landed]
+          mbar_wait(sk_bar, 0);
+          k3 = clock64();
+          auto u16 = [](long long c) { return (unsigned long long)min(65535ll, c >> 4); };
+          prof[1] = u16(k0 - t_acc) | (u16(k1 - k0) << 16) | (u16(k2 - k1) << 32) | (u16(k3 - k2) << 48);
+        }
+      }
+      if (lane == 0) mbar_wait(sk_bar, 0);
+      __syncwarp();
+    }
+  } else if (S > 1) {
     if (epi) tc_fence_before();
     cluster_sync_all();                            // 1: every rank's MMAs have retired -> all pipeline buffers are free
     if (epi) {
@@ -857,50 +920,82 @@ static int env_int(const char* name, int dflt) {
 }
 void tc_set_repeat(int n) { g_repeat = n < 1 ? 1 : n; }
 
+// ---- split-K workspace (gg_set_workspace): [64 KB of arrive / depart counters, zero at rest | scratch ring for the fp32 partials] ----
+struct TcWorkspace {
+  char* base = nullptr;           // scratch ring
+  size_t bytes = 0, head = 0;
+  unsigned int* cnt = nullptr;    // counter ring
+  size_t cnt_n = 0, cnt_head = 0;
+};
+static TcWorkspace g_ws;
+static std::mutex g_ws_mu;
+constexpr size_t WS_COUNTER_BYTES = 64 * 1024;
+size_t tc_workspace_bytes() { return WS_COUNTER_BYTES + (size_t)96 * 1024 * 1024; }
+int tc_set_workspace(void* ptr, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  if (ptr == nullptr || bytes <= WS_COUNTER_BYTES + (1 << 20)) { g_ws = TcWorkspace(); return GG_OK; }
+  GG_REQUIRE(((uintptr_t)ptr % 1024) == 0, GG_ERR_INVALID, "gg_set_workspace: the buffer must be 1024-byte aligned");
+  g_ws.cnt = (unsigned int*)ptr; g_ws.cnt_n = WS_COUNTER_BYTES / 4; g_ws.cnt_head = 0;
+  g_ws.base = (char*)ptr + WS_COUNTER_BYTES; g_ws.bytes = bytes - WS_COUNTER_BYTES; g_ws.head = 0;
+  return GG_OK;
+}
+
 // Output-channel tile and split-K factor.  An M=128 tcgen05.mma from shared memory costs max(~76, N/2) cycles, so a
 // wider N is cheaper per FLOP -- but at batch 64 the wide tiles leave most SMs idle.  Without split: the widest tile that
 // still yields ~1 wave of CTAs.  The 4x4 / 8x8 layers (g_h1, d_h3: 8-32 M tiles, 100-200 K chunks per tile) then end up
-// with N = 64 tiles at 42 % of the MMA rate; for them the K loop of a WIDE tile is split over a thread-block cluster of S
-// CTAs instead, reduced by a push-style reduce-scatter through distributed shared memory (tc_pixgemm_kernel).
-// MEASURED (round 2, profiles/r2p_*): the main loop halves as modelled (d_h3.down 34.3 k -> 18.2 k cycles to accumulator-
-// ready) but the reduce-scatter costs ~20 k cycles per CTA -- distributed shared memory moves ~17-21 B/clk per SM, and a
-// 128 x 256 fp32 partial is 128 KB (96 KB out + 96 KB in at S = 4) -- so the kernels get SLOWER (g_h1.up 17.5 -> 23.3 us,
-// step 1.488 -> 1.549 ms).  Split-K is therefore opt-in: GG_TC_SPLITK=2 / 4 forces S (parity-tested), GG_TC_SPLITK=auto
-// lets the cycle model below choose; default off.  GG_TC_BN forces the tile.
-static void pick_tile(int Nout, int64_t mtiles, int min_chunks, int max_chunks, bool out_bf16, bool allow_split, int* bn_out, int* split_out) {
+// with N = 64 tiles at 42 % of the MMA rate; for them the K loop of a WIDE tile is split over S CTAs instead and the S
+// fp32 partials are combined by a reduce-scatter: every rank finishes (bias, activation, statistics, store) BN / S columns.
+// Two transports (tc_pixgemm_kernel), both parity-tested (tests/test_gpu_tc.py::test_tc_split_k), both OPT-IN:
+//   * GG_TC_SPLITK_MODE=cluster: thread-block cluster + distributed shared memory, S in {2, 4}.  MEASURED (profiles/r2p_*):
+//     the main loop halves as modelled (d_h3.down 34.3 k -> 18.2 k cycles to accumulator-ready) but the exchange costs
+//     ~20 k cycles per CTA -- DSMEM moves ~17-21 B/clk per SM, a 128 x 256 fp32 partial is 128 KB (g_h1.up 17.5 -> 23.3 us).
+//   * default mode (needs gg_set_workspace): through L2 with TMA stores / loads of 16 KB boxes and a per-tile arrive counter;
+//     S in {2, 4, 8}; deterministic (fixed summation order), no cluster scheduling constraints.  MEASURED (profiles/
+//     r4c_splitk_l2_sweep.md, per-CTA clock64): a 128 KB partial costs staging 2.1 k + TMA store 4.3 k (~30 B/clk per SM into
+//     L2) + counter / skew 2.3 k + TMA load 3.2 k + 2 k of extra epilogue = ~14 k cycles on top of the normal epilogue, a 64 KB
+//     partial ~9 k.  Alone, the split launches are 0-25 % faster (g_h1.down with statistics 23.7 -> 17.6 us at N = 128, S = 4;
+//     g_h1.up / d_h3 within +-3 %); INSIDE the train step they lose (1.525 -> 1.569 ms): a one-wave launch that spins on its
+//     tile mates shares the SMs with the filter-gradient stream, and each launch streams 8-16 MB of scratch through L2.
+// GG_TC_SPLITK=auto lets the cycle model below choose, =2 / 4 / 8 forces S; unset = no split.  GG_TC_BN forces the tile.
+static void pick_tile(int Nout, int64_t mtiles, int min_chunks, int max_chunks, bool out_bf16, bool allow_split, int* bn_out, int* split_out, int* mode_out) {
   int bn = Nout % 256 == 0 ? 256 : (Nout % 128 == 0 ? 128 : 64);
   while (bn > 64 && mtiles * (Nout / bn) < 120) bn /= 2;
   const int forced_bn = env_int("GG_TC_BN", 0);
   if (forced_bn > 0 && Nout % forced_bn == 0) bn = forced_bn;
   int S = 1;
   const char* sk = getenv("GG_TC_SPLITK");
+  const char* skm = getenv("GG_TC_SPLITK_MODE");
+  const bool cluster = skm && skm[0] == 'c';
   const bool auto_split = sk && sk[0] == 'a';
-  const int forced_s = auto_split ? 0 : env_int("GG_TC_SPLITK", 1);
+  const int forced_s = auto_split ? 0 : ((sk && *sk) ? std::max(1, atoi(sk)) : 1);
+  const bool have_ws = g_ws.base != nullptr;
+  if (!cluster && !have_ws) allow_split = false;
   auto cycles = [&](int b, int s) {        // one CTA: main loop of the heaviest class + fixed cost + the reduce-scatter
     const int mma = std::max(76, b / 2);
-    return (int64_t)ceil_div(max_chunks, s) * 4 * mma + 6000 + (s > 1 ? 1500 + 6 * b : 0);
+    const int xchg = cluster ? 1500 + 75 * b : 3000 + 14 * b;             // cluster: ~20 k cycles at b = 256; L2: store + counter + load of b * 512 bytes
+    return (int64_t)ceil_div(max_chunks, s) * 4 * mma + 6000 + (s > 1 ? xchg : 0);
   };
   auto split_ok = [&](int b, int s) {
     if (Nout % b != 0 || b % (32 * s) != 0 || b / s < (out_bf16 ? 64 : 32)) return false;
-    if (mtiles * (Nout / b) * s > 148) return false;                                   // clusters: one wave
+    if (mtiles * (Nout / b) * s > 148) return false;                                   // one wave, one CTA per SM: the ranks of a tile are co-resident
+    if (!cluster && (size_t)mtiles * (Nout / b) * s * b * 512 > g_ws.bytes) return false;
+    if (cluster && s > 4) return false;
     return (int64_t)(s - 1) * ceil_div(min_chunks, s) < min_chunks && min_chunks / s >= 2;   // every rank has work
   };
   if (allow_split && forced_s != 1) {
     const int64_t tiles0 = mtiles * (Nout / bn);
     int64_t best = cycles(bn, 1) * ceil_div64(tiles0, 148);
     if (forced_s > 1) best = INT64_MAX;
-    const int bn0 = bn;
     for (int b : {256, 128})
-      for (int s2 : {2, 4}) {
+      for (int s2 : {2, 4, 8}) {
         if (forced_s > 1 && s2 != forced_s) continue;
         if (forced_bn > 0 && b != forced_bn) continue;
         if (!split_ok(b, s2)) continue;
         const int64_t c = cycles(b, s2);
         if (forced_s > 1 ? c < best : c * 100 < best * 85) { best = (forced_s > 1) ? c : c * 100 / 85; bn = b; S = s2; }
       }
-    (void)bn0;
   }
-  *bn_out = bn; *split_out = S;
+  *bn_out = bn; *split_out = S; *mode_out = (S > 1 && !cluster) ? 1 : 0;
 }
 
 static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* out, cudaStream_t st) {
@@ -922,12 +1017,29 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   GG_REQUIRE(p.stages * stage_bytes >= out_bytes, GG_ERR_INVALID, "tc_pixgemm: GG_TC_STAGES too small for the output tile");
   GG_REQUIRE((size_t)p.stages * stage_bytes + 2048 + 48 * 256 <= 227 * 1024, GG_ERR_INVALID, "tc_pixgemm: pipeline does not fit in shared memory");
   p.prof = g_prof;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 2) + 16 + (p.bnb_pre ? 48 * p.BN : 0);
+  if (p.splitk > 1 && p.sk_mode == 1) {
+    // scratch of this launch: the next chunk of the ring (launches that may run concurrently -- other streams, parallel
+    // branches of a captured graph -- must not share one; stream order protects a chunk that comes round again)
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    const size_t need = (size_t)total_tiles * p.splitk * p.BN * 512;
+    GG_REQUIRE(g_ws.base != nullptr && need <= g_ws.bytes && (size_t)2 * total_tiles <= g_ws.cnt_n, GG_ERR_INVALID, "tc_pixgemm: split-K workspace missing or too small");
+    if (g_ws.head + need > g_ws.bytes) g_ws.head = 0;
+    if (g_ws.cnt_head + 2 * (size_t)total_tiles > g_ws.cnt_n) g_ws.cnt_head = 0;
+    const uint64_t kdims[2] = {32, (uint64_t)total_tiles * p.splitk * (p.BN / 32) * TILE_M};
+    const uint64_t kstr[1] = {128};
+    const uint32_t kbox[2] = {32, TILE_M};
+    int rc = encode_tmap(&p.skmap, GG_F32, g_ws.base + g_ws.head, 2, kdims, kstr, kbox);
+    if (rc) return rc;
+    p.sk_cnt = g_ws.cnt + g_ws.cnt_head;
+    g_ws.head += need;
+    g_ws.cnt_head += 2 * (size_t)total_tiles;
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 4) + 16 + (p.bnb_pre ? 48 * p.BN : 0);
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(tc_pixgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   int rc = GG_OK;
   for (int r = 0; r < g_repeat && rc == GG_OK; ++r) {
-    Launch(total_tiles * p.splitk, TC_THREADS, smem, st, p.splitk)(tc_pixgemm_kernel, p, bias, out);
+    Launch(total_tiles * p.splitk, TC_THREADS, smem, st, p.sk_mode == 1 ? 1 : p.splitk)(tc_pixgemm_kernel, p, bias, out);
     rc = check_launch("tc_pixgemm");
   }
   return rc;
@@ -950,7 +1062,7 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_bf, con
   c.tw = ceil_div(d->Wo, p.bw); c.th = ceil_div(d->Ho, p.bh); c.td = ceil_div(d->Do, p.bd); c.tn = ceil_div(d->N, p.bn);
   const int64_t mtiles = (int64_t)c.tw * c.th * c.td * c.tn;
   const int taps = d->kd * d->kh * d->kw;
-  pick_tile(d->K, mtiles, taps * (d->C / KCHUNK), taps * (d->C / KCHUNK), d->small_dtype == GG_BF16, true, &p.BN, &p.splitk);
+  pick_tile(d->K, mtiles, taps * (d->C / KCHUNK), taps * (d->C / KCHUNK), d->small_dtype == GG_BF16, true, &p.BN, &p.splitk, &p.sk_mode);
   {  // B operand straight from the bf16 filter copy w[tap][c][k] (no transposed copy): the reduction index c is the ROW
      // axis, so the tile is MN-major -- BN/64 atoms of [64 c rows][64 k = 128 B], one 4-D box per K chunk
     const uint64_t bdims[4] = {64, (uint64_t)d->C, (uint64_t)(d->K / 64), (uint64_t)taps};
@@ -1054,7 +1166,7 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
       min_taps = std::min(min_taps, p.cls[i].tap_end - p.cls[i].tap_begin);
       max_taps = std::max(max_taps, p.cls[i].tap_end - p.cls[i].tap_begin);
     }
-    pick_tile(d->C, tiles, min_taps * (d->K / KCHUNK), max_taps * (d->K / KCHUNK), d->large_dtype == GG_BF16, true, &p.BN, &p.splitk);
+    pick_tile(d->C, tiles, min_taps * (d->K / KCHUNK), max_taps * (d->K / KCHUNK), d->large_dtype == GG_BF16, true, &p.BN, &p.splitk, &p.sk_mode);
   }
   p.ntiles_n = d->C / p.BN;
   for (int i = 0; i < ncls; ++i) p.cls[i].tile_begin *= p.ntiles_n;

@@ -39,6 +39,8 @@ SIGNATURES = {
     "gg_launch_count": (C.c_uint64, []),
     "gg_debug_set_repeat": (None, [C.c_int]),
     "gg_debug_set_prof": (None, [C.c_void_p]),
+    "gg_workspace_bytes": (C.c_size_t, []),
+    "gg_set_workspace": (C.c_int, [C.c_void_p, C.c_size_t]),
     "gg_conv_down": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv_up": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv_wgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),

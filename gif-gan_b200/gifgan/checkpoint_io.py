@@ -17,8 +17,11 @@ published format -- not against a file TensorFlow wrote:
     BundleEntryProto{dtype=1, shape=2 (TensorShapeProto), shard_id=3, offset=4, size=5, crc32c=6 (fixed32, masked)}.
   * `.data-SSSSS-of-NNNNN`: the tensors' little-endian row-major bytes at [offset, offset + size).
 
-Adam state of the reference's full `Saver()`: slots `<var>/Adam` (m), `<var>/Adam_1` (v) and the scalars `beta1_power`,
-`beta2_power` (= beta^(t+1) after t updates), `<scope>/beta1_power` for the second optimiser.
+Adam state, WHEN a checkpoint holds it: slots `<var>/Adam` (m), `<var>/Adam_1` (v) and the scalars `beta1_power`,
+`beta2_power` (= beta^(t+1) after t updates), `<scope>/beta1_power` for the second optimiser.  The reference's image DCGAN
+builds its `tf.train.Saver()` BEFORE the optimisers exist (model.py:141 vs :146-149), so its checkpoints hold the model
+variables only; the video GAN's Saver (z_model_lib.py:204) is built after them and holds the slots.  Both load here: slots
+are taken when both of a variable's are present and left at zero otherwise.
 """
 from __future__ import annotations
 
@@ -483,7 +486,7 @@ def import_named(store, named, optimisers=(), prefix="", strict=True):
                 v.data.copy_(torch.as_tensor(a.astype(np.float32)))
                 v.version += 1
                 n = v.numel()
-                if store.flat is not None and key + "/Adam" in named and v.offset + n <= store.flat["m"].numel():
+                if store.flat is not None and key + "/Adam" in named and key + "/Adam_1" in named and v.offset + n <= store.flat["m"].numel():
                     store.flat["m"][v.offset:v.offset + n].copy_(torch.as_tensor(np.asarray(named[key + "/Adam"], dtype=np.float32)).reshape(-1))
                     store.flat["v"][v.offset:v.offset + n].copy_(torch.as_tensor(np.asarray(named[key + "/Adam_1"], dtype=np.float32)).reshape(-1))
             else:

@@ -21,12 +21,23 @@ import torch.distributed as dist
 
 
 class DataParallel:
-    def __init__(self, world_size=None, rank=None, backend=None, bucket_bytes=32 << 20, init=True):
+    def __init__(self, world_size=None, rank=None, backend=None, bucket_bytes=32 << 20, init=True, grad_dtype=None, nvls=None, overlap_update=None):
+        """grad_dtype: 'fp32' | 'bf16' | None -- dtype the gradient buckets cross NVLink in.  None = GG_DP_GRAD_DTYPE, else 'bf16'
+        when the operator layer computes in bf16 (activation gradients are bf16 already; the buckets are cast on the
+        communication stream, summed by NCCL in bf16 and cast back: half the bytes) and 'fp32' in the fp32 parity mode.
+        nvls: use NCCL's in-switch reduction (NVLS); None = GG_DP_NVLS, else off (measured slower for these 3-20 MB buckets
+        launched from a graph: profiles/r01z_*).  Only takes effect if the process group is created here.
+        overlap_update: run an update's last bucket AND its Adam launch on the communication stream, so that the next update's
+        generator forward (which does not read the discriminator's weights) overlaps them (GG_DP_OVERLAP_UPDATE, default on)."""
         self.world_size = int(os.environ.get("WORLD_SIZE", "1")) if world_size is None else world_size
         self.rank = int(os.environ.get("RANK", "0")) if rank is None else rank
         self.local_rank = int(os.environ.get("LOCAL_RANK", str(self.rank)))
         self.bucket_bytes = bucket_bytes
         self.comm_stream = None
+        self.grad_dtype = grad_dtype or os.environ.get("GG_DP_GRAD_DTYPE") or None      # resolved at first use (needs ops' precision)
+        self.overlap_update = (os.environ.get("GG_DP_OVERLAP_UPDATE", "1") != "0") if overlap_update is None else bool(overlap_update)
+        self._pending = False
+        self._bf16 = None
         if init and self.world_size > 1 and not dist.is_initialized():
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
@@ -34,8 +45,10 @@ class DataParallel:
                 torch.cuda.set_device(self.local_rank)
                 # Measured on 8 x B200 (tools/gpu_scale_ab.sh, profiles/r01z_*): for this step's 3-20 MB gradient buckets,
                 # issued from inside a CUDA graph, in-switch reduction (NVLS) is slower than NCCL's ring/tree over
-                # NVLink (2.097 vs 2.035 ms/step), so it is off unless the user sets the variable.
-                os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+                # NVLink (2.097 vs 2.035 ms/step).  The choice is the constructor's `nvls` argument / GG_DP_NVLS (default
+                # off); a NCCL_NVLS_ENABLE already set by the user wins.
+                want_nvls = (os.environ.get("GG_DP_NVLS", "0") == "1") if nvls is None else bool(nvls)
+                os.environ.setdefault("NCCL_NVLS_ENABLE", "1" if want_nvls else "0")
             dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world_size)
 
     # ------------------------------------------------------------------------------
@@ -84,19 +97,39 @@ class DataParallel:
         self._cur = dict(optim=optim, segs=self._segments(optim), issued=[])
         ops.GRAD_READY_HOOK = self.grad_ready
 
+    def _use_bf16(self):
+        if self.grad_dtype is None:
+            from . import ops
+            self.grad_dtype = "bf16" if ops.get_precision() == "bf16" else "fp32"
+        return self.grad_dtype == "bf16"
+
+    def _reduce(self, grads, x, y):
+        """Sum-all-reduce grads[x:y] in place (on the current stream)."""
+        if self._use_bf16() and grads.is_cuda:
+            from . import ops
+            if self._bf16 is None or self._bf16.numel() != grads.numel():
+                self._bf16 = torch.empty(grads.numel(), dtype=torch.bfloat16, device=grads.device)
+            c, L = ops.cabi, ops.cabi.lib()
+            half = self._bf16[x:y]
+            ops.check(L.gg_cast(c.ptr(grads[x:y]), c.GG_F32, c.ptr(half), c.GG_BF16, y - x, c.stream()), "gg_cast")
+            dist.all_reduce(half, op=dist.ReduceOp.SUM)
+            ops.check(L.gg_cast(c.ptr(half), c.GG_BF16, c.ptr(grads[x:y]), c.GG_F32, y - x, c.stream()), "gg_cast")
+        else:
+            dist.all_reduce(grads[x:y], op=dist.ReduceOp.SUM)
+
     def _issue(self, lo, hi, extra_streams=()):
         grads = self._cur["optim"].store.flat["grads"]
         comm = self._comm()
         if comm is False:                          # gloo / CPU: no streams, reduce in place
             for (x, y) in self.buckets(lo, hi):
-                dist.all_reduce(grads[x:y], op=dist.ReduceOp.SUM)
+                self._reduce(grads, x, y)
         else:
             comm.wait_stream(torch.cuda.current_stream())
             for s in extra_streams:
                 comm.wait_stream(s)
             with torch.cuda.stream(comm):
                 for (x, y) in self.buckets(lo, hi):
-                    dist.all_reduce(grads[x:y], op=dist.ReduceOp.SUM)
+                    self._reduce(grads, x, y)
         self._cur["issued"].append((lo, hi))
 
     def grad_ready(self, var, producer_stream=None):
@@ -117,31 +150,59 @@ class DataParallel:
         self._issue(var.offset, seg[1], (producer_stream,) if producer_stream is not None else ())
         seg[1] = var.offset
 
-    def allreduce(self, optim):
-        """Sum-all-reduce the gradient range of `optim`'s group (what begin_update's early buckets have not covered yet)
-        and make the current stream wait for the exchange.  Adam divides by world_size."""
-        if self.world_size <= 1:
-            return
+    def _finish_buckets(self, optim):
+        """Issue what begin_update's early buckets have not covered yet (no wait)."""
         from . import ops
         ops.GRAD_READY_HOOK = None
         cur = getattr(self, "_cur", None)
         if cur is None or cur["optim"] is not optim:
             cur = self._cur = dict(optim=optim, segs=self._segments(optim), issued=[])
         # the unreduced heads; adjacent ones (a tuple group with no early bucket in between) go out as one range
-        heads = [(lo, hi) for lo, hi in cur["segs"] if hi > lo]
         merged = []
-        for lo, hi in heads:
+        for lo, hi in [(lo, hi) for lo, hi in cur["segs"] if hi > lo]:
             if merged and merged[-1][1] == lo:
                 merged[-1] = (merged[-1][0], hi)
             else:
                 merged.append((lo, hi))
         for lo, hi in merged:
             self._issue(lo, hi)
+        self.last_buckets = cur["issued"]
+        self._cur = None
+
+    def allreduce(self, optim):
+        """Sum-all-reduce the gradient range of `optim`'s group (what begin_update's early buckets have not covered yet)
+        and make the current stream wait for the exchange.  Adam divides by world_size."""
+        if self.world_size <= 1:
+            return
+        self._finish_buckets(optim)
         comm = self._comm()
         if comm is not False:
             torch.cuda.current_stream().wait_stream(comm)
-        self.last_buckets = cur["issued"]
-        self._cur = None
+
+    def finish_update(self, optim, apply_fn):
+        """The tail of an update: remaining buckets, then `apply_fn()` (the optimiser's fused Adam launch).  With
+        overlap_update both go to the communication stream and the current stream does NOT wait: what follows on it -- the next
+        update's generator forward, which reads none of these weights -- overlaps the exchange and the Adam pass; the caller
+        must call wait_pending() before the first kernel that reads the updated variables (or their gradients' buffer)."""
+        if self.world_size <= 1:
+            apply_fn()
+            return
+        comm = self._comm()
+        if not self.overlap_update or comm is False:
+            self.allreduce(optim)
+            apply_fn()
+            return
+        self._finish_buckets(optim)
+        comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(comm):
+            apply_fn()
+        self._pending = True
+
+    def wait_pending(self):
+        """Make the current stream wait for a finish_update() still in flight on the communication stream."""
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self._comm())
+            self._pending = False
 
     def broadcast_parameters(self, store):
         """Make every rank start from rank 0's variables (weights and EMAs)."""

@@ -236,6 +236,8 @@ class DCGAN(object):
         both = self._both_buffer(B)
         if images.data_ptr() != both.data_ptr():
             both[:B].copy_(images)
+        if self.dp is not None:
+            self.dp.wait_pending()
         self.d_optim.zero_grad()
         if self.dp is not None:
             self.dp.begin_update(self.d_optim)
@@ -248,10 +250,14 @@ class DCGAN(object):
             logits = self.discriminator(both, yy, reuse=True, groups=2)[1]
             losses = sigmoid_cross_entropy_loss(logits, [(0, B, 1.0, 1.0), (B, 2 * B, 0.0, 1.0)])
             torch.autograd.backward(losses, grad_tensors=self._ones(losses))
-        if self.dp is not None:
-            self.dp.allreduce(self.d_optim)
-        if apply:
-            self.d_optim.apply(grad_scale=self._grad_scale())
+        if self.dp is not None and apply:
+            # remaining bucket + Adam on the communication stream: the next update's generator forward overlaps them
+            self.dp.finish_update(self.d_optim, lambda: self.d_optim.apply(grad_scale=self._grad_scale()))
+        else:
+            if self.dp is not None:
+                self.dp.allreduce(self.d_optim)
+            if apply:
+                self.d_optim.apply(grad_scale=self._grad_scale())
         return losses          # [d_loss, d_loss_real, d_loss_fake]
 
     def g_update(self, z, y=None, apply=True):
@@ -261,6 +267,8 @@ class DCGAN(object):
             self.dp.begin_update(self.g_optim)
         with ops.trainable(self.g_vars), ops.overlap_wgrad(), ops.stats_arena():
             G = self.generator(z, y)
+            if self.dp is not None:
+                self.dp.wait_pending()      # the discriminator's update (exchange + Adam) may still be in flight
             logits = self.discriminator(add_noise(G, self.noise_std), y, reuse=True)[1]
             losses = sigmoid_cross_entropy_loss(logits, target=1.0)
             torch.autograd.backward(losses, grad_tensors=self._ones(losses))
@@ -287,10 +295,11 @@ class DCGAN(object):
         train-mode BN (each advances the EMAs, App. A.4)."""
         with torch.no_grad():
             G = self.generator(z, y)
-            errD_fake = sigmoid_cross_entropy_loss(self.discriminator(G, y, reuse=True)[1], target=0.0)
-            errD_real = sigmoid_cross_entropy_loss(self.discriminator(images, y, reuse=True)[1], target=1.0)
+            # the losses are the training graph's tensors: D sees its inputs through add_noise (model.py:105-107)
+            errD_fake = sigmoid_cross_entropy_loss(self.discriminator(add_noise(G, self.noise_std), y, reuse=True)[1], target=0.0)
+            errD_real = sigmoid_cross_entropy_loss(self.discriminator(add_noise(images, self.noise_std), y, reuse=True)[1], target=1.0)
             G = self.generator(z, y)
-            errG = sigmoid_cross_entropy_loss(self.discriminator(G, y, reuse=True)[1], target=1.0)
+            errG = sigmoid_cross_entropy_loss(self.discriminator(add_noise(G, self.noise_std), y, reuse=True)[1], target=1.0)
         return errD_fake, errD_real, errG
 
     LOSS_KEYS = ("d_loss", "g_loss_first", "g_loss", "errD_fake", "errD_real", "errG")
@@ -388,10 +397,12 @@ class DCGAN(object):
         if config.dataset == 'mnist':
             data_X, data_y = self.load_mnist()
         elif config.dataset == 'synthetic':
-            n = int(min(getattr(config, "train_size", 1024), 1 << 16))
-            rs = np.random.RandomState(102)
+            # the flag's default train_size is "everything" (1 << 62): a synthetic epoch is 4096 samples unless a smaller size is asked
+            # for, drawn in float32 (a float64 draw of 65536 x 64 x 64 x 3 would take 6.4 GB of host memory)
+            n = int(min(getattr(config, "train_size", 4096), 4096))
+            gen = np.random.Generator(np.random.PCG64(102))
             data = None
-            data_X = rs.uniform(-1, 1, (n, self.output_size, self.output_size, self.c_dim)).astype(np.float32)
+            data_X = gen.random((n, self.output_size, self.output_size, self.c_dim), dtype=np.float32) * 2.0 - 1.0
         else:
             data = glob(os.path.join(self.data_dir, config.dataset, self.image_glob))
             if self.shuffle:

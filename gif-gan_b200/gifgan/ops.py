@@ -51,6 +51,29 @@ def set_precision(p: str, tensor_cores=None):
     if p not in ("fp32", "bf16"):
         raise ValueError("precision must be 'fp32' or 'bf16'")
     _PRECISION, _USE_TC = p, (TC_DEFAULT if tensor_cores is None else bool(tensor_cores))
+    if _PRECISION == "bf16" and _USE_TC:
+        ensure_workspace()
+
+
+_WORKSPACE = None
+
+
+def ensure_workspace():
+    """Hand the library its split-K workspace (include/gifgan.h: gg_set_workspace) once per process: a zero-filled device buffer
+    that lives as long as the process, allocated here -- outside any CUDA-graph capture -- because the library never allocates
+    device memory.  GG_TC_WORKSPACE_MB overrides the size (0 = none: the small-M layers then run unsplit)."""
+    global _WORKSPACE
+    if _WORKSPACE is not None or not torch.cuda.is_available():
+        return
+    L = cabi.lib()
+    mb = os.environ.get("GG_TC_WORKSPACE_MB")
+    nbytes = int(L.gg_workspace_bytes()) if mb is None else int(float(mb) * (1 << 20))
+    if nbytes <= 0:
+        _WORKSPACE = False
+        return
+    _WORKSPACE = torch.zeros(nbytes + 1024, dtype=torch.uint8, device="cuda")
+    base = (_WORKSPACE.data_ptr() + 1023) // 1024 * 1024
+    check(L.gg_set_workspace(base, nbytes), "gg_set_workspace")
 
 
 def get_precision() -> str:

@@ -204,6 +204,8 @@ class VID_DCGAN(object):
         both = self._both()
         if images.data_ptr() != both.data_ptr():
             both[:n].copy_(images)
+        if self.dp is not None:
+            self.dp.wait_pending()
         self.d_optim.zero_grad()
         if self.dp is not None:
             self.dp.begin_update(self.d_optim)
@@ -216,10 +218,14 @@ class VID_DCGAN(object):
             logits = self.discriminator(act, reuse=True, groups=2)[1]
             losses = sigmoid_cross_entropy_loss(logits, [(0, Bv, 1.0, 1.0), (Bv, 2 * Bv, 0.0, 1.0)])
             torch.autograd.backward(losses, grad_tensors=self._ones(losses))
-        if self.dp is not None:
-            self.dp.allreduce(self.d_optim)
-        if apply:
-            self.d_optim.apply(grad_scale=1.0 if self.dp is None else 1.0 / self.dp.world_size)
+        if self.dp is not None and apply:
+            # remaining bucket + Adam on the communication stream: the next update's generator / image-GAN forward overlaps them
+            self.dp.finish_update(self.d_optim, lambda: self.d_optim.apply(grad_scale=1.0 / self.dp.world_size))
+        else:
+            if self.dp is not None:
+                self.dp.allreduce(self.d_optim)
+            if apply:
+                self.d_optim.apply(grad_scale=1.0 if self.dp is None else 1.0 / self.dp.world_size)
         out = dict(losses=losses)
         if diagnostics:   # the std fetches of z_model_lib.py:220-222
             out.update(images_std=get_std(both[:n]), sampler_std=get_std(both[n:]),
@@ -235,7 +241,11 @@ class VID_DCGAN(object):
         with ops.trainable(self.g_var_list), ops.overlap_wgrad(), ops.stats_arena():
             G_out, _ = self.generator(z, train=True)
             frames = img.generator(G_out, train=False)
+            if self.dp is not None and self.train_img_disc:
+                self.dp.wait_pending()      # --train_img_disc: the pending D update also rewrites the image discriminator
             act = img.discriminator(add_noise(frames, self.image_noise_std), reuse=True, train=False, stop_at_h2=True)[2]
+            if self.dp is not None:
+                self.dp.wait_pending()      # the video discriminator's update (exchange + Adam) may still be in flight
             logits = self.discriminator(add_noise(act, self.activation_noise_std), reuse=True)[1]
             losses = sigmoid_cross_entropy_loss(logits, target=1.0)
             roots, grads = [losses], [self._ones(losses)]

@@ -258,6 +258,17 @@ int gg_lstm_step_bwd(const float* gates, const float* c_prev, const float* c_out
                      const float* Wh, float* dgates, float* dc_prev, float* dh_prev,
                      int32_t B, int32_t H, float forget_bias, void* stream);
 
+/* ---- workspace ------------------------------------------------------------------------
+ * The tensor-core conv launches that split their K loop over several CTAs (the 4x4 / 8x8 layers at batch 64: few
+ * output tiles, 100-200 K chunks each) exchange fp32 partial tiles through a caller-owned DEVICE buffer: 64 KB of
+ * counters followed by a scratch ring.  The buffer must be 1024-byte aligned, ZERO-FILLED when handed over, live until
+ * replaced (NULL / 0 = none) and at least gg_workspace_bytes() long for every eligible layer to split; without a
+ * workspace those launches run unsplit.  One workspace per process (= per device).  The library never allocates
+ * device memory itself, so a captured CUDA graph stays valid as long as the buffer does.
+ * (SURVEY.md 8b proposed gg_workspace_bytes; there is no reference counterpart -- TensorFlow's allocator did this.)   */
+size_t gg_workspace_bytes(void);
+int gg_set_workspace(void* device_buf, size_t bytes);
+
 /* ---- introspection for tests/bench -------------------------------------------------- */
 /* measurement hook (tools/, bench.py): tensor-core conv calls launch their kernel n times back to back */
 void gg_debug_set_repeat(int n);

@@ -207,12 +207,15 @@ def test_c3_deconv2d_image_side(B, h, w_, Ci):
     assert relerr(st.vars["g/biases"].grad, gb) < TOL
 
 
-@pytest.mark.parametrize("splitk", ["auto", 2, 4])
-def test_tc_cluster_split_k(splitk, monkeypatch):
-    """Cluster split-K (opt-in, GG_TC_SPLITK: auto = the library's cycle model, 2 / 4 forced): the K loop of a wide tile split over a
-    thread-block cluster and combined by the push-style reduce-scatter through distributed shared memory must give the same
-    conv / deconv results (fp32-accumulated partials, one final rounding) -- forward, input gradient, fused statistics."""
+@pytest.mark.parametrize("mode,splitk", [("l2", "auto"), ("l2", 2), ("l2", 4), ("l2", 8), ("l2", 1), ("cluster", "auto"), ("cluster", 2), ("cluster", 4)])
+def test_tc_split_k(mode, splitk, monkeypatch):
+    """Split-K of the tcgen05 pixel GEMM (GG_TC_SPLITK: auto = the library's cycle model, 2 / 4 / 8 forced, 1 = off): the K loop of
+    a wide tile split over S CTAs whose fp32 partials meet in a reduce-scatter -- through L2 (default: TMA stores / loads of
+    16 KB boxes in the workspace + a per-tile counter; deterministic) or, opt-in, through a thread-block cluster's distributed
+    shared memory -- must give the same conv / deconv results (fp32-accumulated partials, one final rounding): forward, input
+    gradient, fused statistics, fused batch-norm backward reductions.  The L2 variant is also run twice for bit equality."""
     monkeypatch.setenv("GG_TC_SPLITK", str(splitk))
+    monkeypatch.setenv("GG_TC_SPLITK_MODE", mode)
     try:
         test_tc_conv2d("d_h3", 16, 8, 256, 512)
         test_tc_deconv2d("g_h1", 16, 4, 512, 256)
@@ -221,6 +224,33 @@ def test_tc_cluster_split_k(splitk, monkeypatch):
         test_bn_backward_reductions_fused_into_dgrad("deconv", 16, 4, 512, 256, 128, 1, monkeypatch)
     finally:
         monkeypatch.delenv("GG_TC_SPLITK", raising=False)
+        monkeypatch.delenv("GG_TC_SPLITK_MODE", raising=False)
+
+
+def test_tc_split_k_full_batch_deterministic_and_equal_to_unsplit(monkeypatch):
+    """At the bench shapes (batch 64: g_h1 / d_h3, where the split is chosen by default) the split launch must (a) reproduce
+    itself bit for bit -- the partials are summed in rank order -- and (b) agree with the unsplit launch to fp32 summation-order
+    noise on the fp32 pre-norm output and its fused statistics."""
+    from gifgan import ops as _o
+    B, H, Ci, Co = 64, 8, 256, 512
+    outs = {}
+    for sk in ("1", "auto", "auto", "8"):
+        monkeypatch.setenv("GG_TC_SPLITK", sk)
+        ops, st, tv = _store(lambda t: _o.conv2d(t, Co, name="c"), (B, H, H, Ci))
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.randn(B, H, H, Ci, device="cuda", generator=gen).to(torch.bfloat16).requires_grad_(True)
+        dy = torch.randn(B, H // 2, H // 2, Co, device="cuda", generator=gen).to(torch.bfloat16)
+        y = ops.conv2d(x, Co, name="c")
+        y.backward(dy)
+        torch.cuda.synchronize()
+        outs.setdefault(sk, []).append((y.float().clone(), x.grad.float().clone()))
+    monkeypatch.delenv("GG_TC_SPLITK", raising=False)
+    a, b = outs["auto"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for k in ("auto", "8"):
+        for i in range(2):
+            ref, got = outs["1"][0][i], outs[k][0][i]
+            assert ((got - ref).abs().max() / ref.abs().max()).item() < 1e-2, (k, i)      # one bf16 ulp of the largest element at most
 
 
 def test_adam_keeps_the_bf16_shadow_current():

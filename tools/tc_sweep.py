@@ -70,9 +70,13 @@ def one(shape, op, reps=20):
         _cabi.lib().gg_debug_set_prof(None)
         b = buf.cpu().reshape(512, 8).double()
         b = b[b[:, 6] > 0]
-        names = ["prodA_loop", "prodA_wait_empty", "mma_loop", "mma_wait_full", "acc_ready", "epi_done", "cta_total", "setup"]
-        print("PROF ctas=%d " % len(b) + " ".join("%s=%.0f" % (n, b[:, i].mean().item()) for i, n in enumerate(names)) +
-              " cta_total_max=%.0f acc_ready_max=%.0f" % (b[:, 6].max().item(), b[:, 4].max().item()), flush=True)
+        names = ["prodA_loop", "xchg", "mma_loop", "mma_wait_full", "acc_ready", "epi_done", "cta_total", "setup"]
+        raw = buf.cpu().reshape(512, 8)
+        raw = raw[raw[:, 6] > 0][:, 1]
+        xc = [(((raw >> (16 * k)) & 0xFFFF).double().mean().item() * 16) for k in range(4)]      # split-K through L2: exchange phases
+        print("PROF ctas=%d " % len(b) + " ".join("%s=%.0f" % (n, b[:, i].mean().item()) for i, n in enumerate(names) if n != "xchg") +
+              " cta_total_max=%.0f acc_ready_max=%.0f" % (b[:, 6].max().item(), b[:, 4].max().item()) +
+              " xchg_stage=%.0f xchg_store=%.0f xchg_wait=%.0f xchg_load=%.0f" % tuple(xc), flush=True)
     import bench
     fl = bench.conv_flops_per_image(H, C, K) * N
     print("RESULT " + json.dumps(dict(shape=shape, op=op, us=round(best * 1e3, 2), tflops=round(fl / best / 1e9, 1),
