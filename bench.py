@@ -539,6 +539,18 @@ def hbm_kernel_table(model, batch, flush, peaks, conv_rows):
     ms = once(lambda: check(L.gg_bn_bwd(ptr(pre), 0, ptr(dy), 1, ptr(dx), 1, rows_n, C, 2, ptr(gamma), ptr(beta), ptr(sm), ptr(sr), None, None, 2, 0.2, 1,
                                         ptr(ws), nb, stream()), "bn_bwd"))
     add(f"bn_bwd two-pass: memset + colsum + bn_bwd_apply [{B2} x 16 x 16 x 128]", rows_n * C * (2 * (4 + 2) + 2), ms, 7)
+    # the generator's input projection (model.py:304: z[B,100] -> [B,8192], batch norm over 512 channels): streams its matrix
+    zin, od, Cc = 100, 8192, 512
+    zx = torch.randn(batch, zin, device="cuda")
+    Wm, bm = torch.randn(zin, od, device="cuda") * 0.02, torch.zeros(od, device="cuda")
+    yl = torch.empty(batch, od, device="cuda")
+    st8 = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+    ms = once(lambda: check(L.gg_linear_fwd_stats(ptr(zx), 0, ptr(Wm), ptr(bm), ptr(yl), batch, zin, od, Cc, 1, ptr(st8), stream()), "linear_fwd_stats"))
+    add(f"g_h0_lin fwd + batch statistics [{batch} x 100 -> 8192] (thin_fwd)", zin * od * 4 + batch * od * 4, ms, 3)
+    dyl = torch.randn(batch, od, device="cuda").to(torch.bfloat16)
+    dWm = torch.zeros_like(Wm)
+    ms = once(lambda: check(L.gg_linear_wgrad(ptr(zx), 0, ptr(dyl), 1, ptr(dWm), None, batch, zin, od, stream()), "linear_wgrad"))
+    add(f"g_h0_lin wgrad [{batch} x 100 -> 8192] (thin_wgrad: dW += x^T dy)", batch * od * 2 + 2 * zin * od * 4, ms, 2)
     # image-side conv layers (3 channels <-> 64): HBM-bound by design (31-63 flop/B)
     for r in conv_rows:
         if r.get("bytes"):

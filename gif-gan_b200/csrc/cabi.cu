@@ -49,7 +49,8 @@ int skinny_linear_fwd(const void*, int, const float*, const float*, void*, int, 
 int skinny_linear_dgrad(const void*, int, const float*, void*, int, int, int, int, cudaStream_t);
 int skinny_linear_wgrad(const void*, int, const void*, int, float*, int, int, int, cudaStream_t);
 bool thin_linear_ok(int rows, int in_dim, int out_dim);
-int thin_linear_fwd(const void*, int, const float*, const float*, void*, int, int, int, int, int, float, cudaStream_t);
+int thin_linear_fwd(const void*, int, const float*, const float*, void*, int, int, int, int, int, float, cudaStream_t, double* stats = nullptr, int Cc = 0, int groups = 1);
+bool thin_linear_stats_ok(int rows, int in_dim, int out_dim, int Cc, int groups);
 int thin_linear_wgrad(const void*, int, const void*, int, float*, float*, int, int, int, cudaStream_t);
 // conv_c3.cu
 bool c3_applicable(const gg_conv_desc*);
@@ -84,6 +85,11 @@ int tc_conv_up_cat(const gg_conv_desc*, const void*, const void*, const float*, 
 void tc_set_repeat(int);
 void tc_set_prof(void*);
 int tc_set_workspace(void*, size_t);
+// dp_allreduce.cu
+int dp_ipc_export(const void*, void*, uint64_t*);
+int dp_ipc_import(const void*, uint64_t, void**);
+size_t dp_signal_bytes();
+int dp_allreduce(void* const*, void* const*, void* const*, int, int, int64_t, int64_t, int, cudaStream_t);
 size_t tc_workspace_bytes();
 }  // namespace gg
 
@@ -99,6 +105,21 @@ extern "C" void gg_debug_set_repeat(int n) { g_cabi_repeat = n < 1 ? 1 : n; tc_s
 #define GG_REPEAT(call) do { int rc_ = GG_OK; for (int r_ = 0; r_ < g_cabi_repeat && rc_ == GG_OK; ++r_) rc_ = (call); return rc_; } while (0)
 // measurement hook: device buffer of 512 x 8 uint64 receiving a per-CTA clock64 breakdown of tc_pixgemm (NULL = off)
 extern "C" void gg_debug_set_prof(void* buf) { tc_set_prof(buf); }
+// data-parallel gradient exchange over peer memory (see include/gifgan.h)
+extern "C" int gg_ipc_export(const void* device_ptr, void* handle64, uint64_t* offset) {
+  GG_REQUIRE(device_ptr && handle64 && offset, GG_ERR_INVALID, "gg_ipc_export: bad argument");
+  return dp_ipc_export(device_ptr, handle64, offset);
+}
+extern "C" int gg_ipc_import(const void* handle64, uint64_t offset, void** device_ptr) {
+  GG_REQUIRE(handle64 && device_ptr, GG_ERR_INVALID, "gg_ipc_import: bad argument");
+  return dp_ipc_import(handle64, offset, device_ptr);
+}
+extern "C" size_t gg_dp_signal_bytes(void) { return dp_signal_bytes(); }
+extern "C" int gg_dp_allreduce(void* const* grads, void* const* stage, void* const* signals, int32_t rank, int32_t world, int64_t lo, int64_t n,
+                               int32_t wire_bf16, void* stream) {
+  GG_REQUIRE(grads && stage && signals, GG_ERR_INVALID, "gg_dp_allreduce: bad argument");
+  return dp_allreduce(grads, stage, signals, rank, world, lo, n, wire_bf16, (cudaStream_t)stream);
+}
 // workspace of the split-K tensor-core launches (see include/gifgan.h)
 extern "C" size_t gg_workspace_bytes(void) { return tc_workspace_bytes(); }
 extern "C" int gg_set_workspace(void* device_buf, size_t bytes) { return tc_set_workspace(device_buf, bytes); }
@@ -200,6 +221,18 @@ extern "C" int gg_linear_fwd(const void* x, int32_t x_dt, const float* matrix, c
   if (out_dim <= 4) return skinny_linear_fwd(x, x_dt, matrix, bias, y, y_dt, rows, in_dim, out_dim, act, ap, (cudaStream_t)stream);
   if (thin_linear_ok(rows, in_dim, out_dim)) return thin_linear_fwd(x, x_dt, matrix, bias, y, y_dt, rows, in_dim, out_dim, act, ap, (cudaStream_t)stream);
   return simt_linear_fwd(x, x_dt, matrix, bias, y, y_dt, rows, in_dim, out_dim, act, ap, (cudaStream_t)stream);
+}
+// linear feeding a train-mode batch norm over channel = column % Cc: y is the fp32 pre-norm tensor; stats[groups][2][Cc] (zeroed by
+// the caller) receives (sum, sum of squares) per row group -- from the same launch on the thin path, else from a statistics pass
+extern "C" int gg_linear_fwd_stats(const void* x, int32_t x_dt, const float* matrix, const float* bias, float* y, int32_t rows, int32_t in_dim,
+                                   int32_t out_dim, int32_t Cc, int32_t groups, double* stats, void* stream) {
+  GG_REQUIRE(x && matrix && y && stats && rows > 0 && in_dim > 0 && out_dim > 0 && Cc > 0 && out_dim % Cc == 0 && groups >= 1, GG_ERR_INVALID,
+             "linear_fwd_stats: bad argument");
+  if (thin_linear_stats_ok(rows, in_dim, out_dim, Cc, groups))
+    return thin_linear_fwd(x, x_dt, matrix, bias, y, GG_F32, rows, in_dim, out_dim, GG_ACT_NONE, 0.f, (cudaStream_t)stream, stats, Cc, groups);
+  int rc = gg_linear_fwd(x, x_dt, matrix, bias, y, GG_F32, rows, in_dim, out_dim, GG_ACT_NONE, 0.f, stream);
+  if (rc) return rc;
+  return bn_accumulate_stats(y, GG_F32, (int64_t)rows * (out_dim / Cc), Cc, groups, stats, (cudaStream_t)stream);
 }
 extern "C" int gg_linear_dgrad(const void* dy, int32_t dy_dt, const float* matrix, void* dx, int32_t dx_dt, int32_t rows, int32_t in_dim,
                                int32_t out_dim, void* stream) {

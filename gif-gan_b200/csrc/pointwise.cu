@@ -478,10 +478,13 @@ constexpr int THIN_ROWS = 32, THIN_MAXK = 128, THIN_COLS = 64;   // block = 64 o
 
 // y[r][j] = act(sum_i x[r][i] W[i][j] + b[j]): thread (c, g) accumulates i = g, g+4, ... for column c and 32 rows; the
 // four partial sums meet in shared memory.  8 matrix loads per thread are in flight before the first FMA.
+// stats != nullptr (fp32 pre-norm output feeding a train-mode batch norm over channel = column % Cc): the block also adds
+// (sum, sum of squares) of its 32 rows x 64 columns to the fp64 accumulators [groups][2][Cc] -- the statistics pass
+// (memset + colsum, 8-13 us for g_h0_lin's [64, 8192]) disappears; rows of one block lie in one row group (host checks).
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(256)
 thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, TY* __restrict__ y, int rows,
-                int in_dim, int out_dim, int act, float ap) {
+                int in_dim, int out_dim, int act, float ap, double* __restrict__ stats, int Cc, int groups) {
   pdl_grid_sync();
   __shared__ __align__(16) float xs[THIN_MAXK * THIN_ROWS];                 // [i][r]            16 KB
   __shared__ __align__(16) float red[4 * THIN_ROWS * THIN_COLS];            // [g][r][c]         32 KB
@@ -520,8 +523,7 @@ thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const flo
 #pragma unroll
   for (int r = 0; r < THIN_ROWS; ++r) red[(g * THIN_ROWS + r) * THIN_COLS + c] = acc[r];
   __syncthreads();
-  if (!col_ok) return;
-  const float b = bias ? __ldg(bias + j) : 0.f;
+  const float b = (bias && col_ok) ? __ldg(bias + j) : 0.f;
   float o[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {                                  // this thread finishes rows g*8 .. g*8+7
@@ -530,10 +532,26 @@ thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const flo
            red[(2 * THIN_ROWS + r) * THIN_COLS + c] + red[(3 * THIN_ROWS + r) * THIN_COLS + c];
   }
   act_fwd_vec<8>(o, act, ap);
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int r = r0 + g * 8 + k;
-    if (r < rows) stf(y + (int64_t)r * out_dim + j, o[k]);
+    if (r < rows && col_ok) { stf(y + (int64_t)r * out_dim + j, o[k]); s1 += o[k]; s2 = fmaf(o[k], o[k], s2); }
+  }
+  if (stats != nullptr) {                                        // uniform over the block
+    float* sred = xs;                                            // the x tile is dead: [2][4][64]
+    sred[g * THIN_COLS + c] = s1;
+    sred[(4 + g) * THIN_COLS + c] = s2;
+    __syncthreads();
+    if (threadIdx.x < 2 * THIN_COLS) {
+      const int which = threadIdx.x >> 6, cc = threadIdx.x & (THIN_COLS - 1), jj = blockIdx.x * THIN_COLS + cc;
+      if (jj < out_dim) {
+        const float* q = sred + which * 4 * THIN_COLS + cc;
+        const float t = (q[0] + q[THIN_COLS]) + (q[2 * THIN_COLS] + q[3 * THIN_COLS]);
+        const int grp = (int)(((int64_t)r0 * groups) / rows);
+        atomicAdd(stats + bn_sum_index(0, groups, grp, which, Cc, jj % Cc), (double)t);
+      }
+    }
   }
 }
 
@@ -598,10 +616,16 @@ thin_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __
 
 bool thin_linear_ok(int rows, int in_dim, int out_dim) { return in_dim <= THIN_MAXK && out_dim >= 256 && rows <= 1024; }
 
+// a block's 32 rows must lie in one row group for the fused statistics
+bool thin_linear_stats_ok(int rows, int in_dim, int out_dim, int Cc, int groups) {
+  return thin_linear_ok(rows, in_dim, out_dim) && Cc > 0 && out_dim % Cc == 0 && groups >= 1 && rows % groups == 0 &&
+         (groups == 1 || (rows / groups) % THIN_ROWS == 0);
+}
+
 int thin_linear_fwd(const void* x, int x_dt, const float* W, const float* bias, void* y, int y_dt, int rows, int in_dim, int out_dim,
-                    int act, float ap, cudaStream_t st) {
+                    int act, float ap, cudaStream_t st, double* stats = nullptr, int Cc = 0, int groups = 1) {
   const dim3 grid(ceil_div(out_dim, THIN_COLS), ceil_div(rows, THIN_ROWS));
-#define GG_TF(TX, TY) Launch(grid, 256, 0, st)(thin_fwd_kernel<TX, TY>, (const TX*)x, W, bias, (TY*)y, rows, in_dim, out_dim, act, ap)
+#define GG_TF(TX, TY) Launch(grid, 256, 0, st)(thin_fwd_kernel<TX, TY>, (const TX*)x, W, bias, (TY*)y, rows, in_dim, out_dim, act, ap, stats, Cc, groups)
   if (x_dt == GG_F32 && y_dt == GG_F32) GG_TF(float, float);
   else if (x_dt == GG_F32) GG_TF(float, bf16);
   else if (y_dt == GG_F32) GG_TF(bf16, float);

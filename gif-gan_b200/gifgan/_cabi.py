@@ -39,6 +39,10 @@ SIGNATURES = {
     "gg_launch_count": (C.c_uint64, []),
     "gg_debug_set_repeat": (None, [C.c_int]),
     "gg_debug_set_prof": (None, [C.c_void_p]),
+    "gg_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "gg_ipc_import": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "gg_dp_signal_bytes": (C.c_size_t, []),
+    "gg_dp_allreduce": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32, _i32, _i64, _i64, _i32, _vp]),
     "gg_workspace_bytes": (C.c_size_t, []),
     "gg_set_workspace": (C.c_int, [C.c_void_p, C.c_size_t]),
     "gg_conv_down": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
@@ -58,6 +62,7 @@ SIGNATURES = {
     "gg_conv3d_dgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),
     "gg_conv3d_wgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),
     "gg_linear_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "gg_linear_fwd_stats": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "gg_linear_dgrad": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "gg_linear_wgrad": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "gg_linear_bn_ok": (C.c_int, [_i32, _i32, _i32, _i32, _i32]),

@@ -2,12 +2,16 @@
 
 One process per GPU (torchrun); clips/frames are sharded over ranks with no data-path
 collective; the only exchange is one sum all-reduce of each optimiser group's flat fp32
-gradient range per update (NCCL over NVLink 5 / NVSwitch), after which the fused Adam
-kernel applies grad_scale = 1/world_size.  Because a group's gradients are one
-contiguous range of the VariableStore's flat buffer, the all-reduce is issued in a few
-large buckets (launch-latency-bound at these sizes: D 17.3 MB, G 20.5 MB) -- bucket
-boundaries follow the reverse layer order so a bucket can start as soon as the backward
-pass has produced it (see DataParallel.allreduce_ready).
+gradient range per update, after which the fused Adam kernel applies grad_scale =
+1/world_size.  Two transports:
+
+* peer memory (default on one NVLink / NVSwitch box, 2..8 ranks): every rank's flat gradient
+  buffer is mapped into every process (CUDA IPC) and ONE kernel of the library per update
+  (gg_dp_allreduce: two-shot reduce-scatter + all-gather by peer loads, summed in rank order)
+  reduces the group's range in place -- csrc/dp_allreduce.cu has the measurements behind it;
+* NCCL (torch.distributed.all_reduce; GG_DP_P2P=0, gloo on CPU, or when the buffers cannot be
+  exported): a few large buckets whose boundaries follow the reverse layer order, so that a
+  bucket can start as soon as the backward pass has produced it (grad_ready).
 
 Batch-norm statistics stay per replica (the usual DDP semantics; SURVEY.md section 7,
 hard part 9): an N-GPU run equals N replicas of the per-GPU batch with averaged gradients.
@@ -38,6 +42,8 @@ class DataParallel:
         self.overlap_update = (os.environ.get("GG_DP_OVERLAP_UPDATE", "1") != "0") if overlap_update is None else bool(overlap_update)
         self._pending = False
         self._bf16 = None
+        self._p2p = {}          # id(grads storage) -> peer tables, or False when the exchange cannot use peer memory
+        self.p2p = os.environ.get("GG_DP_P2P", "1") != "0"
         if init and self.world_size > 1 and not dist.is_initialized():
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
@@ -55,6 +61,8 @@ class DataParallel:
     def buckets(self, begin, end):
         """Split the flat element range [begin, end) into buckets of <= bucket_bytes (fp32)."""
         per = max(1, self.bucket_bytes // 4)
+        if any(self._p2p.values()):
+            per = 1 << 62          # the peer exchange takes a range whole
         out = []
         b = begin
         while b < end:
@@ -95,7 +103,71 @@ class DataParallel:
         from . import ops
         # seg = [lo, done_hi]: [done_hi, hi) of the segment has been all-reduced already
         self._cur = dict(optim=optim, segs=self._segments(optim), issued=[])
+        if self._peer_tables(optim.store.flat["grads"]):
+            return            # peer-memory exchange: one launch over the whole range once backward is done (no early buckets)
         ops.GRAD_READY_HOOK = self.grad_ready
+
+    # -- peer-memory exchange ------------------------------------------------------------
+    def _peer_tables(self, grads):
+        """Map the flat gradient buffer (and a signal buffer) of every rank into this process; returns the ctypes pointer tables
+        of gg_dp_allreduce, or False when this run cannot use them (every rank takes the same branch).  Collective: the first
+        call for a given buffer must happen on all ranks, outside CUDA-graph capture (prepare())."""
+        key = grads.data_ptr()
+        if key in self._p2p:
+            return self._p2p[key]
+        eligible = (self.p2p and grads.is_cuda and dist.is_initialized() and dist.get_backend() == "nccl"
+                    and 2 <= self.world_size <= 8 and self.world_size <= torch.cuda.device_count())      # the same on every rank
+        if not eligible:
+            self._p2p[key] = False
+            return False
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("DataParallel: call prepare(store) (or broadcast_parameters) before capturing a step: the peer-memory "
+                               "exchange is set up by a collective handshake")
+        import ctypes
+        from . import _cabi as c
+        L = c.lib()
+        mine = sig = stage = None
+        try:
+            sig = torch.zeros(int(L.gg_dp_signal_bytes()), dtype=torch.uint8, device=grads.device)
+            stage = torch.empty(-(-grads.numel() // self.world_size) + 8, dtype=torch.float32, device=grads.device)
+            mine = []
+            for t in (grads, stage, sig):
+                h = ctypes.create_string_buffer(64)
+                off = ctypes.c_uint64(0)
+                c.check(L.gg_ipc_export(c.ptr(t), h, ctypes.byref(off)), "gg_ipc_export")
+                mine.append((h.raw, int(off.value)))
+            torch.cuda.synchronize()              # the zero fill of the signals has landed before a peer can write a flag
+        except RuntimeError:
+            mine = None                           # e.g. an expandable-segments pool: cannot be exported
+        everyone = [None] * self.world_size
+        dist.all_gather_object(everyone, mine)
+        tabs = False
+        if all(e is not None for e in everyone):
+            try:
+                gp, tp, sp = (ctypes.c_void_p * 8)(), (ctypes.c_void_p * 8)(), (ctypes.c_void_p * 8)()
+                for r, rec in enumerate(everyone):
+                    if r == self.rank:
+                        gp[r], tp[r], sp[r] = grads.data_ptr(), stage.data_ptr(), sig.data_ptr()
+                        continue
+                    for arr, (h, off) in zip((gp, tp, sp), rec):
+                        out = ctypes.c_void_p()
+                        c.check(L.gg_ipc_import(h, off, ctypes.byref(out)), "gg_ipc_import")
+                        arr[r] = out.value
+                tabs = dict(grads=gp, stage=tp, sig=sp, keep=(sig, stage))
+            except RuntimeError:
+                tabs = False
+        flag = torch.tensor([1 if tabs else 0], device=grads.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # everyone, or no one
+        if int(flag.item()) == 0:
+            tabs = False
+        self._p2p[key] = tabs
+        return tabs
+
+    def prepare(self, store):
+        """Set up the peer-memory exchange for `store`'s gradient buffer (collective; call once after finalize(), before the
+        first captured step).  Without it the first update does it lazily -- which must not happen inside a graph capture."""
+        if self.world_size > 1 and store.flat is not None:
+            self._peer_tables(store.flat["grads"])
 
     def _use_bf16(self):
         if self.grad_dtype is None:
@@ -105,6 +177,11 @@ class DataParallel:
 
     def _reduce(self, grads, x, y):
         """Sum-all-reduce grads[x:y] in place (on the current stream)."""
+        tabs = self._peer_tables(grads)
+        if tabs:
+            from . import _cabi as c
+            c.check(c.lib().gg_dp_allreduce(tabs["grads"], tabs["stage"], tabs["sig"], self.rank, self.world_size, x, y - x, 1 if self._use_bf16() else 0, c.stream()), "gg_dp_allreduce")
+            return
         if self._use_bf16() and grads.is_cuda:
             from . import ops
             if self._bf16 is None or self._bf16.numel() != grads.numel():
@@ -205,7 +282,8 @@ class DataParallel:
             self._pending = False
 
     def broadcast_parameters(self, store):
-        """Make every rank start from rank 0's variables (weights and EMAs)."""
+        """Make every rank start from rank 0's variables (weights and EMAs); also sets up the peer-memory exchange."""
+        self.prepare(store)
         if self.world_size <= 1:
             return
         dist.broadcast(store.flat["params"], src=0)

@@ -324,6 +324,8 @@ class DCGAN(object):
         includes the device->host read of the losses) or the device loss vector (sync=False)."""
         st = self._static_buffers(np.shape(batch_images)[0], batch_labels is not None)
         B = st["B"]
+        if self.dp is not None:
+            self.dp.prepare(self.store)        # peer-memory exchange: collective handshake, first call only (never inside a capture)
         st["both"][:B].copy_(torch.as_tensor(batch_images), non_blocking=True)
         st["z"].copy_(torch.as_tensor(batch_z), non_blocking=True)
         if batch_labels is not None:

@@ -928,14 +928,18 @@ class _LinearProducer:
     def __init__(self, mvar, bvar, rows, out_dim):
         self.wvar, self.bvar, self.rows, self.out_dim = mvar, bvar, rows, out_dim
 
-    fuses_stats = False
+    fuses_stats = True      # gg_linear_fwd_stats: batch statistics from the same launch (thin path) or a pass inside the call
 
     def out_shape(self):
         return (self.rows, self.out_dim)
 
-    def fwd(self, x, b, stats=None, groups=1):
+    def fwd(self, x, b, stats=None, groups=1, Cc=None):
         rows, in_dim = x.shape
         y = torch.empty((rows, self.out_dim), dtype=torch.float32, device=x.device)
+        if stats is not None:
+            check(cabi.lib().gg_linear_fwd_stats(ptr(x), dt(x), ptr(self.wvar.data), ptr(b), ptr(y), rows, in_dim, self.out_dim,
+                                                 Cc or self.out_dim, groups, ptr(stats), stream()), "gg_linear_fwd_stats")
+            return y
         check(cabi.lib().gg_linear_fwd(ptr(x), dt(x), ptr(self.wvar.data), ptr(b), ptr(y), dt(y), rows, in_dim, self.out_dim, 0, 0.0,
                                        stream()), "gg_linear_fwd")
         return y
@@ -986,9 +990,10 @@ class _FusedBN(torch.autograd.Function):
             if DEBUG_TAP is not None:
                 DEBUG_TAP.setdefault("fwd", []).append((prod.wvar.name, pre, y))
             return y
-        fused_stats = train and prod.fuses_stats and Cc == prod.out_shape()[-1]
+        is_lin = isinstance(prod, _LinearProducer)
+        fused_stats = train and prod.fuses_stats and (Cc == prod.out_shape()[-1] or (is_lin and x.dim() == 2 and x.shape[0] % groups == 0))
         stats = _zeroed_f64(L.gg_bn_workspace_bytes(Cc, groups) // 8, x.device)[0] if fused_stats else None   # [replicas][groups][2][C]
-        pre = prod.fwd(x, b, stats=stats, groups=groups)
+        pre = prod.fwd(x, b, stats=stats, groups=groups, Cc=Cc) if is_lin else prod.fwd(x, b, stats=stats, groups=groups)
         rows = pre.numel() // Cc
         y = torch.empty(pre.shape, dtype=out_dtype, device=x.device)
         save_mean = torch.empty((groups, Cc), dtype=torch.float32, device=x.device)

@@ -284,6 +284,8 @@ class VID_DCGAN(object):
                                      loss_dev=torch.zeros(7, dtype=torch.float32, device=dev),
                                      loss_host=torch.zeros(7, dtype=torch.float32).pin_memory())
         both = self._both()
+        if self.dp is not None:
+            self.dp.prepare(self.store)        # peer-memory exchange: collective handshake, first call only (never inside a capture)
         both[:n].copy_(torch.as_tensor(batch_images), non_blocking=True)
         st["z"].copy_(torch.as_tensor(batch_z), non_blocking=True)
         args = (both[:n], st["z"], disc_updates, gen_updates, st["loss_dev"])

@@ -138,6 +138,11 @@ int gg_conv3d_wgrad(const gg_conv_desc* d, const void* x, const void* dy, float*
 /* ---- linear (ops.py:106-117: tf.matmul(input_, Matrix) + bias) ---------------------- */
 int gg_linear_fwd(const void* x, int32_t x_dtype, const float* matrix, const float* bias, void* y, int32_t y_dtype,
                   int32_t rows, int32_t in_dim, int32_t out_dim, int32_t act, float act_param, void* stream);
+/* the same feeding a train-mode batch norm over channel = column % Cc (model.py:304-307: g_h0_lin -> reshape -> g_bn0):
+ * y is the fp32 pre-norm tensor and stats[groups][2][Cc] (fp64, zeroed by the caller) receives (sum, sum of squares) per
+ * row group -- for gg_bn_fwd_train_stats -- from the same launch where the thin kernel applies, else from a statistics pass */
+int gg_linear_fwd_stats(const void* x, int32_t x_dtype, const float* matrix, const float* bias, float* y, int32_t rows, int32_t in_dim,
+                        int32_t out_dim, int32_t Cc, int32_t groups, double* stats, void* stream);
 int gg_linear_dgrad(const void* dy, int32_t dy_dtype, const float* matrix, void* dx, int32_t dx_dtype,
                     int32_t rows, int32_t in_dim, int32_t out_dim, void* stream);
 /* dmatrix += x^T dy ; dbias += colsum(dy) (either may be NULL) */
@@ -268,6 +273,26 @@ int gg_lstm_step_bwd(const float* gates, const float* c_prev, const float* c_out
  * (SURVEY.md 8b proposed gg_workspace_bytes; there is no reference counterpart -- TensorFlow's allocator did this.)   */
 size_t gg_workspace_bytes(void);
 int gg_set_workspace(void* device_buf, size_t bytes);
+
+/* ---- data-parallel gradient exchange (one box, 2..8 GPUs, one process per GPU) ----------
+ * Replaces the reference's single-process training loop's implicit "one device" with the exchange north_star asks for
+ * ("gg_allreduce_bucket"): the flat fp32 gradient buffer of every rank is mapped into every process with CUDA
+ * IPC and ONE kernel per optimiser update sum-all-reduces a range of it in place over NVLink peer loads (two-shot:
+ * reduce-scatter in rank order, then all-gather; deterministic, bit-identical on every rank).  Host protocol:
+ *   1. every rank: gg_ipc_export() of three device buffers -- grads (the flat gradient buffer), stage (at least
+ *      ceil(largest range / world) + 4 floats, 16-byte aligned) and signals (gg_dp_signal_bytes() of ZEROED memory) -- and
+ *      sends the (handle, offset) pairs to its peers by any host channel (torch.distributed object all-gather);
+ *   2. every rank: gg_ipc_import() of each peer's three buffers (its own stay plain pointers);
+ *   3. per update: gg_dp_allreduce(grads[world], stage[world], signals[world], rank, world, lo, n, wire_bf16, stream) on every
+ *      rank, same arguments, same order of calls; lo (elements) 16-byte aligned.  Capturable into a CUDA graph (no host state).
+ *      wire_bf16 = 1: the reduced sums (fp32 over the ranks' fp32 gradients) are rounded to bf16 before they are distributed --
+ *      half the all-gather bytes; every rank, the reducing one included, ends up with the same rounded values.
+ * Buffers from a VMM / expandable-segments pool cannot be exported (status GG_ERR_CUDA; callers fall back to NCCL).      */
+int gg_ipc_export(const void* device_ptr, void* handle64, uint64_t* offset);
+int gg_ipc_import(const void* handle64, uint64_t offset, void** device_ptr);
+size_t gg_dp_signal_bytes(void);
+int gg_dp_allreduce(void* const* grads, void* const* stage, void* const* signals, int32_t rank, int32_t world, int64_t lo, int64_t n,
+                    int32_t wire_bf16, void* stream);
 
 /* ---- introspection for tests/bench -------------------------------------------------- */
 /* measurement hook (tools/, bench.py): tensor-core conv calls launch their kernel n times back to back */

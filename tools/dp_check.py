@@ -64,14 +64,21 @@ def main():
     r = run(dp)
     if dp.rank == 0:
         ref = json.load(open(path))
-        worst = 0.0
+        worst = first = 0.0
         for k in ref:
             a, b = np.array(ref[k]), np.array(r[k])
-            worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(a)))))
-        print("dp world", dp.world_size, "grad dtype", dp.grad_dtype, "overlap", dp.overlap_update, "worst rel loss difference vs single GPU: %.3e" % worst)
+            rel = np.abs(a - b) / np.maximum(1.0, np.abs(a))
+            worst = max(worst, float(rel.max()))
+            first = max(first, float(rel[0].max()))
+        print("dp world", dp.world_size, "grad dtype", dp.grad_dtype, "overlap", dp.overlap_update, "p2p", bool(any(dp._p2p.values())),
+              "worst rel loss difference vs single GPU: %.3e (first step %.3e)" % (worst, first))
         print("  dcgan", r["dcgan"][-1], "ref", ref["dcgan"][-1], "| vid", r["vid"][-1], "ref", ref["vid"][-1])
-        # bf16 buckets: 0.4 % rounding of the exchanged gradients, amplified over a few GAN steps; fp32 buckets: reduction order only
-        assert worst < (5e-2 if dp.grad_dtype == "bf16" else 2e-2), worst
+        # N ranks fed the same batch average N identical gradients: the FIRST step (one D update and two G updates from identical
+        # weights) must agree closely -- fp32 exchange: summation order only; bf16 buckets: 0.4 % rounding of the exchanged
+        # gradients.  Later steps only loosely: two single-GPU runs already drift apart by a few % within 3-4 steps (the
+        # filter-gradient kernels add their pixel splits in arrival order; profiles/r03b_pack_ab_run_to_run.log).
+        assert first < (2e-2 if dp.grad_dtype == "bf16" else 5e-3), first
+        assert worst < 0.15, worst
     torch.distributed.destroy_process_group()
 
 
