@@ -22,6 +22,7 @@
 // A flag is the launch sequence number (monotonic, kept in the signal buffer): replays of a captured CUDA graph need no
 // host-side state.  Spins are bounded: a protocol bug or a missing peer traps (launch error) instead of hanging the box.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -33,7 +34,7 @@
 namespace gg {
 
 constexpr int DP_MAX_RANKS = 8;
-constexpr int DP_BLOCKS = 64;
+constexpr int DP_BLOCKS = 128;          // capacity of the signal buffer; the launch uses GG_DP_BLOCKS (default 64) of them
 constexpr int DP_THREADS = 512;
 
 // signal buffer of one rank (zero-filled by the caller): counter[b] = launches block b has completed;
@@ -189,14 +190,47 @@ dp_allreduce_kernel(const __grid_constant__ DpPeers P, int rank, long long lo, l
   dp_barrier(P, 1, rank, WORLD, seq, true);
   const long long t_b1 = clock64();
   if (has_tail) P.grads[rank][lo + (nv << 2) + threadIdx.x] = tail;      // peers have read the raw value (barrier 1)
-#pragma unroll 1
-  for (int q = 1; q < WORLD; ++q) {
-    const int p = (rank + q) % WORLD;                  // every rank starts with a different peer
-    const long long c0 = min(nv, (long long)p * per), c1 = min(nv, c0 + per);
-    float4* dst = reinterpret_cast<float4*>(P.grads[rank] + lo) + c0;
-    const long long len = c1 - c0;
+  if (!WIRE16) {
+    // every trip reads element i of ALL the other ranks' chunks (WORLD - 1 independent loads to WORLD - 1 different GPUs), two
+    // elements per trip: a rank that walked its peers one after the other got 430 GB/s at N = 8 (profiles/r4h_*)
+    const float4* src[WORLD];
+    float4* dst[WORLD];
+    long long len[WORLD];
+#pragma unroll
+    for (int q = 1; q < WORLD; ++q) {
+      const int p = (rank + q) % WORLD;
+      const long long c0 = min(nv, (long long)p * per), c1 = min(nv, c0 + per);
+      src[q] = reinterpret_cast<const float4*>(P.stage[p]);
+      dst[q] = reinterpret_cast<float4*>(P.grads[rank] + lo) + c0;
+      len[q] = c1 - c0;
+    }
+    long long common = len[1];
+#pragma unroll
+    for (int q = 2; q < WORLD; ++q) common = min(common, len[q]);
     long long i = first;
-    if (WIRE16) {
+    constexpr int U2 = WORLD <= 2 ? 4 : (WORLD <= 4 ? 2 : 1);       // elements per trip: 4-7 independent peer loads in flight per thread
+    for (; i + (U2 - 1) * stride < common; i += U2 * stride) {
+      float4 a[U2][WORLD];
+#pragma unroll
+      for (int u = 0; u < U2; ++u)
+#pragma unroll
+        for (int q = 1; q < WORLD; ++q) a[u][q] = ld_peer4(src[q] + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < U2; ++u)
+#pragma unroll
+        for (int q = 1; q < WORLD; ++q) dst[q][i + u * stride] = a[u][q];
+    }
+#pragma unroll
+    for (int q = 1; q < WORLD; ++q)
+      for (long long k = i; k < len[q]; k += stride) dst[q][k] = ld_peer4(src[q] + k);
+  } else {
+#pragma unroll 1
+    for (int q = 1; q < WORLD; ++q) {
+      const int p = (rank + q) % WORLD;                  // every rank starts with a different peer
+      const long long c0 = min(nv, (long long)p * per), c1 = min(nv, c0 + per);
+      float4* dst = reinterpret_cast<float4*>(P.grads[rank] + lo) + c0;
+      const long long len = c1 - c0;
+      long long i = first;
       const uint2* src16 = reinterpret_cast<const uint2*>(P.stage[p]);
       for (; i + 7 * stride < len; i += 8 * stride) {
         uint2 h[8];
@@ -206,14 +240,7 @@ dp_allreduce_kernel(const __grid_constant__ DpPeers P, int rank, long long lo, l
         for (int u = 0; u < 8; ++u) dst[i + u * stride] = unpack_bf16x4(h[u]);
       }
       for (; i < len; i += stride) dst[i] = unpack_bf16x4(ld_peer2(src16 + i));
-      continue;
     }
-    const float4* src = reinterpret_cast<const float4*>(P.stage[p]);
-    for (; i + 3 * stride < len; i += 4 * stride) {
-      const float4 a = ld_peer4(src + i), b = ld_peer4(src + i + stride), c = ld_peer4(src + i + 2 * stride), d = ld_peer4(src + i + 3 * stride);
-      dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
-    }
-    for (; i < len; i += stride) dst[i] = ld_peer4(src + i);
   }
   if (threadIdx.x == 0) {
     P.sig[rank]->counter[blockIdx.x] = seq;
@@ -292,10 +319,15 @@ int dp_allreduce(void* const* grads, void* const* stage, void* const* signals, i
   }
   GG_REQUIRE(((uintptr_t)(P.grads[rank] + lo) % 16) == 0 && ((uintptr_t)P.stage[rank] % 16) == 0, GG_ERR_INVALID,
              "gg_dp_allreduce: the range and the staging buffer must start 16-byte aligned");
+  static const int nblocks = [] {
+    const char* v = getenv("GG_DP_BLOCKS");
+    const int b = (v && *v) ? atoi(v) : 64;
+    return b < 1 ? 1 : (b > DP_BLOCKS ? DP_BLOCKS : b);
+  }();
 #define GG_DP(W)                                                                                                          \
   case W:                                                                                                                 \
-    if (wire_bf16) Launch(DP_BLOCKS, DP_THREADS, 0, st)(dp_allreduce_kernel<W, true>, P, rank, (long long)lo, (long long)n);   \
-    else Launch(DP_BLOCKS, DP_THREADS, 0, st)(dp_allreduce_kernel<W, false>, P, rank, (long long)lo, (long long)n);            \
+    if (wire_bf16) Launch(nblocks, DP_THREADS, 0, st)(dp_allreduce_kernel<W, true>, P, rank, (long long)lo, (long long)n);     \
+    else Launch(nblocks, DP_THREADS, 0, st)(dp_allreduce_kernel<W, false>, P, rank, (long long)lo, (long long)n);              \
     break
   switch (world) {
     GG_DP(2); GG_DP(3); GG_DP(4); GG_DP(5); GG_DP(6); GG_DP(7); GG_DP(8);

@@ -1363,7 +1363,11 @@ int tc_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, f
   const int64_t tiles = (int64_t)p.mtiles * p.ntiles_n;
   // One CTA per SM (the pipeline takes ~190 KB of shared memory): size the pixel split for ONE full wave.  (The
   // earlier target of 2 x 148 CTAs ran as 2-3 waves, the last one nearly empty: d_h3 100 tiles x 3 = 300 CTAs.)
-  const int64_t cta_target = env_int("GG_WG_CTAS", 148);
+  // GG_DETERMINISTIC=1: no pixel split -- every dw element then receives exactly ONE reduce-add (onto the zero-filled or
+  // previously accumulated gradient), so the filter gradients are bit-reproducible run to run; with splits the partial sums of
+  // a tile land in L2 in CTA-finish order (last-bit differences that a GAN amplifies to a few % within 3-4 steps).
+  const bool deterministic = env_int("GG_DETERMINISTIC", 0) != 0;
+  const int64_t cta_target = deterministic ? 1 : env_int("GG_WG_CTAS", 148);
   int splits = (int)std::max<int64_t>(1, cta_target / tiles);
   splits = std::min(splits, std::max(1, p.ptiles / 4));
   p.ptiles_per_split = ceil_div(p.ptiles, splits);

@@ -44,6 +44,9 @@ class DataParallel:
         self._bf16 = None
         self._p2p = {}          # id(grads storage) -> peer tables, or False when the exchange cannot use peer memory
         self.p2p = os.environ.get("GG_DP_P2P", "1") != "0"
+        # the peer exchange moves fp32 by default: measured at 8 GPUs (profiles/r4h_scale8_p2p.log) its bf16 all-gather phase is
+        # request-rate bound on 8-byte peer loads and SLOWER (109 vs 80 us for 17.3 MB); GG_DP_P2P_WIRE=bf16 selects it anyway
+        self._wire16 = 1 if os.environ.get("GG_DP_P2P_WIRE", "fp32") == "bf16" else 0
         if init and self.world_size > 1 and not dist.is_initialized():
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
@@ -180,7 +183,7 @@ class DataParallel:
         tabs = self._peer_tables(grads)
         if tabs:
             from . import _cabi as c
-            c.check(c.lib().gg_dp_allreduce(tabs["grads"], tabs["stage"], tabs["sig"], self.rank, self.world_size, x, y - x, 1 if self._use_bf16() else 0, c.stream()), "gg_dp_allreduce")
+            c.check(c.lib().gg_dp_allreduce(tabs["grads"], tabs["stage"], tabs["sig"], self.rank, self.world_size, x, y - x, self._wire16, c.stream()), "gg_dp_allreduce")
             return
         if self._use_bf16() and grads.is_cuda:
             from . import ops

@@ -253,6 +253,30 @@ def test_tc_split_k_full_batch_deterministic_and_equal_to_unsplit(monkeypatch):
             assert ((got - ref).abs().max() / ref.abs().max()).item() < 1e-2, (k, i)      # one bf16 ulp of the largest element at most
 
 
+def test_tc_wgrad_deterministic_mode(monkeypatch):
+    """GG_DETERMINISTIC=1: the tensor-core filter-gradient kernel runs without its pixel split (one reduce-add per element), so two
+    runs give bit-identical gradients -- and they agree with the split (default) launch to fp32 summation-order noise."""
+    from gifgan import ops as _o
+    B, H, Ci, Co = 64, 16, 128, 256
+    ops, st, tv = _store(lambda t: _o.conv2d(t, Co, name="c", bias=False), (B, H, H, Ci))
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(B, H, H, Ci, device="cuda", generator=gen).to(torch.bfloat16)
+    dy = torch.randn(B, H // 2, H // 2, Co, device="cuda", generator=gen).to(torch.bfloat16)
+    g = ops._Geom(B, (1, H, H), Ci, (1, H // 2, H // 2), Co, (1, 5, 5), (1, 2, 2), (0, 1, 1))
+    wv = st.vars["c/w"]
+    outs = []
+    for mode in ("1", "1", "0"):
+        monkeypatch.setenv("GG_DETERMINISTIC", mode)
+        wv.grad.zero_()
+        ops._run_wgrad(g, x, dy, wv)
+        ops.join_side()
+        torch.cuda.synchronize()
+        outs.append(wv.grad.clone())
+    monkeypatch.delenv("GG_DETERMINISTIC", raising=False)
+    assert torch.equal(outs[0], outs[1])
+    assert ((outs[2] - outs[0]).abs().max() / outs[0].abs().max()).item() < 1e-5
+
+
 def test_adam_keeps_the_bf16_shadow_current():
     """gg_adam_graph(p, p_bf16, ...): the bf16 shadow of the flat parameter buffer -- the filter operand of every tensor-core
     kernel -- is rewritten by the Adam launch itself and equals the rounded fp32 masters bit for bit."""

@@ -6,6 +6,11 @@ O=gpurun_out; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 LOG=$O/${TAG}_summary.log; : > $LOG
 for what in $WHAT; do case $what in
+p2p)   # the exchange kernel alone: correctness + time per all-reduce, at two grid sizes
+  for nb in 64 128; do
+    GG_DP_BLOCKS=$nb timeout 300 $TR --master-port 2952$((nb/64)) tools/dp_p2p_check.py --time > $O/${TAG}_p2p_$nb.log 2>&1
+    echo "== GG_DP_BLOCKS=$nb" | tee -a $LOG; grep -E "dp_p2p_check|TIMING|Error|error|assert" $O/${TAG}_p2p_$nb.log | cut -c1-1500 | head -8 | tee -a $LOG
+  done;;
 check)
   timeout 300 $TR --master-port 29529 tools/dp_p2p_check.py --time > $O/${TAG}_p2p.log 2>&1; grep -E "dp_p2p_check|TIMING|Error|error|assert" $O/${TAG}_p2p.log | cut -c1-600 | head -8 | tee -a $LOG
   timeout 200 python tools/dp_check.py single > $O/${TAG}_single.log 2>&1; tail -1 $O/${TAG}_single.log | cut -c1-200 | tee -a $LOG
