@@ -532,24 +532,24 @@ thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const flo
            red[(2 * THIN_ROWS + r) * THIN_COLS + c] + red[(3 * THIN_ROWS + r) * THIN_COLS + c];
   }
   act_fwd_vec<8>(o, act, ap);
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
+  double s1 = 0.0, s2 = 0.0;                                     // fp64 from the first add on: 16 DFMAs per thread, and the
+#pragma unroll                                                   // statistics do not depend on how rows are split over threads
   for (int k = 0; k < 8; ++k) {
     const int r = r0 + g * 8 + k;
-    if (r < rows && col_ok) { stf(y + (int64_t)r * out_dim + j, o[k]); s1 += o[k]; s2 = fmaf(o[k], o[k], s2); }
+    if (r < rows && col_ok) { stf(y + (int64_t)r * out_dim + j, o[k]); s1 += (double)o[k]; s2 += (double)o[k] * (double)o[k]; }
   }
   if (stats != nullptr) {                                        // uniform over the block
-    float* sred = xs;                                            // the x tile is dead: [2][4][64]
+    double* sred = reinterpret_cast<double*>(xs);                // the x tile is dead: [2][4][64] doubles = 4 KB
     sred[g * THIN_COLS + c] = s1;
     sred[(4 + g) * THIN_COLS + c] = s2;
     __syncthreads();
     if (threadIdx.x < 2 * THIN_COLS) {
       const int which = threadIdx.x >> 6, cc = threadIdx.x & (THIN_COLS - 1), jj = blockIdx.x * THIN_COLS + cc;
       if (jj < out_dim) {
-        const float* q = sred + which * 4 * THIN_COLS + cc;
-        const float t = (q[0] + q[THIN_COLS]) + (q[2 * THIN_COLS] + q[3 * THIN_COLS]);
+        const double* q = sred + which * 4 * THIN_COLS + cc;
+        const double t = (q[0] + q[THIN_COLS]) + (q[2 * THIN_COLS] + q[3 * THIN_COLS]);
         const int grp = (int)(((int64_t)r0 * groups) / rows);
-        atomicAdd(stats + bn_sum_index(0, groups, grp, which, Cc, jj % Cc), (double)t);
+        atomicAdd(stats + bn_sum_index(0, groups, grp, which, Cc, jj % Cc), t);
       }
     }
   }
@@ -558,7 +558,7 @@ thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const flo
 // dW[i][j] += sum_r x[r][i] * dy[r][j]  (blockIdx.y: chunk of 32 input features);  db[j] += sum_r dy[r][j].
 // Thread (c, g) takes rows r = g, g+4, ...; partial sums meet in shared memory.
 template <typename TX, typename TD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)        // <= 64 registers: the 512 CTAs of g_h0_lin (128 column blocks x 4 feature chunks) run as ONE wave
 thin_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __restrict__ dW, float* __restrict__ db, int rows, int in_dim,
                   int out_dim) {
   pdl_grid_sync();

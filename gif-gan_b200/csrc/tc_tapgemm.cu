@@ -133,6 +133,11 @@ struct TcPixParams {
   // per channel and row group, sum g and sum g*xhat with g = dy * act'(gamma*xhat + beta), xhat = (pre - mean) * rstd --
   // what colsum_kernel<MODE 1> computes in a separate pass over (pre, dy).  Here dy is still in registers.
   const float* bnb_pre;       // fp32 pre-norm tensor of the consumer batch norm, same geometry as this launch's output; nullptr = off
+  int epi2;                   // 1: a second set of four warps (the idle producers 0 / 6 / 7 and the MMA warp 1: TMEM lane quarters 0, 2, 3, 1)
+                              //    takes every other 32-column block of the epilogue (not with split-K)
+  int pre_tma;                // 1: the pre-norm tile is staged by TMA through pmap (box = 32 fp32 columns x the tile's 128 pixels)
+  uint32_t pre_off;           // pre_tma: byte offset (from the 1 KB-aligned smem base) of the two 16 KB staging buffers
+  CUtensorMap pmap[TC_MAX_CLASSES];   // pre_tma: the pre-norm tensor seen like omap[] (per output-parity class)
   const float* bnb_mean;      // [groups][statC]
   const float* bnb_rstd;      // [groups][statC]
   const float* bnb_gamma;     // [statC] or nullptr
@@ -179,6 +184,8 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 1);
   const uint32_t sk_bar = bar_base + 8u * (2 * p.stages + 2);          // split-K through L2: the partials of my slice have landed
+  const uint32_t pre_bar0 = bar_base + 8u * (2 * p.stages + 3);        // fused batch-norm backward: pre-norm block landed (buffer 0)
+  const uint32_t pre_bar1 = bar_base + 8u * (2 * p.stages + 4) + 16u;  // (buffer 1; sits behind the row mask)
 
   // ---- which tile ------------------------------------------------------------------------
   const int S = p.splitk;                      // cluster (S, 1, 1): rank in cluster == blockIdx.x % S
@@ -210,6 +217,8 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2 * p.cps); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     mbar_init(sk_bar, 1);
+    mbar_init(pre_bar0, 1);
+    mbar_init(pre_bar1, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.bmap);
   }
@@ -334,13 +343,22 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
   }
 
   // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
-  const bool epi = (warp >= 2 && warp <= 5);
+  // With epi2 the producer warps 0 / 6 / 7 and the MMA warp 1 -- idle once their loops are done, and between them they own all
+  // four TMEM lane quarters as well -- form a second set that takes the odd 32-column blocks: the epilogue is a per-warp
+  // dependent chain (one warp per scheduler, ~900 instructions per block with the fused batch-norm backward at IPC ~0.3), so
+  // a second warp on each scheduler nearly halves it.
+  const bool use_b = (S == 1) && p.epi2 != 0;
+  const bool epiA = (warp >= 2 && warp <= 5);
+  const bool epiB = use_b && (warp == 0 || warp == 1 || warp == 6 || warp == 7);
+  const bool epi = epiA || epiB;
+  const int eset = epiB ? 1 : 0;
+  const uint32_t n_epi = use_b ? 256u : 128u;
   const int q = warp & 3;
   const int row = q * 32 + lane;                 // accumulator row = pixel within the tile
   const uint32_t row_off = (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
   const uint32_t mask_smem = bar_base + 8u * (2 * p.stages + 4);        // 4 x u32 after the barriers (16-byte aligned)
-  const uint32_t bnb_consts = mask_smem + 16u;                          // float4 {rstd, -mean*rstd, gamma, beta} per column of the N tile
+  const uint32_t bnb_consts = mask_smem + 32u;                          // float4 {rstd, -mean*rstd, gamma, beta} per column of the N tile
   const uint32_t bnb_part = bnb_consts + 16u * (uint32_t)p.BN;          // float [4 warps][2][BN]: per-warp partial reductions
   long long t_acc = 0;
   int r_iw = 0, r_ih = 0, r_id = 0, r_in = 0;
@@ -355,13 +373,13 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     if (p.bnb_pre != nullptr) {
       const int statC = p.cat_C ? p.cat_C : p.Nout;
       const int grp = (int)(((long long)mn0 * p.stats_groups) / p.Mn);
-      for (int col = (warp - 2) * 32 + lane; col < p.BN; col += 128) {
+      for (int col = epiA ? (warp - 2) * 32 + lane : p.BN; col < p.BN; col += 128) {
         const int ch = (n0 + col) % statC;
         const float mu = __ldg(p.bnb_mean + grp * statC + ch), rs = __ldg(p.bnb_rstd + grp * statC + ch);
         const float ga = p.bnb_gamma ? __ldg(p.bnb_gamma + ch) : 1.f, be = p.bnb_beta ? __ldg(p.bnb_beta + ch) : 0.f;
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bnb_consts + 16u * (uint32_t)col), "f"(rs), "f"(-mu * rs), "f"(ga), "f"(be) : "memory");
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");      // the four epilogue warps
+      asm volatile("bar.sync 2, %0;" ::"r"(n_epi) : "memory");      // the epilogue warps (both sets)
     }
     if (lane == 0) mbar_wait(tmem_full_bar, 0);   // one polling lane per warp: the spin must not steal issue slots
     __syncwarp();                                 // from the producer / MMA threads that share these schedulers
@@ -465,7 +483,33 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
     // scatters to the stride-s output parity view.  The staging of a split-K slice sits behind R (host checks the capacity).
     // Below, c0 counts columns of THIS RANK's slice; cg = ncol0 + c0 is the column within the N tile.
     const uint32_t out_base = (S > 1) ? smem_base + (uint32_t)p.BN * 512u : smem_base;
-    for (int c0 = 0; c0 < ncol; c0 += 32) {
+    // Fused batch-norm backward with pre_tma: the fp32 pre-norm tile of each 32-column block arrives by TMA (the box of the
+    // output store, fp32 elements) in one of two 16 KB buffers, two blocks ahead of its use, and a thread reads ITS row with
+    // eight conflict-free 16-byte shared loads.  (Reading the row straight from global memory made every LDG.128 touch 32
+    // different lines: the epilogue was bound by L1 request throughput, ~2 k cycles per block -- profiles/r4n_*.)
+    const bool pre_tma = p.bnb_pre != nullptr && p.pre_tma != 0;
+    const uint32_t pre_buf = smem_base + p.pre_off;
+    // one set: blocks alternate between the two buffers (two blocks ahead); two sets: each set owns one buffer and refills it
+    // as soon as its four warps have read their rows (the block's arithmetic hides the load)
+    auto issue_pre = [&](int blk, int buf) {           // one thread of the set
+      const int colg = n0 + ncol0 + blk * 32;
+      const int oc = p.cat_C ? colg / p.cat_C : ci, ch = p.cat_C ? colg % p.cat_C : colg;
+      const uint32_t bar = buf ? pre_bar1 : pre_bar0;
+      mbar_expect_tx(bar, TILE_M * 128u);
+      tma_load_5d(pre_buf + (uint32_t)buf * (TILE_M * 128u), &p.pmap[oc], bar, ch, mw0, mh0, md0, mn0);
+    };
+    const bool pre_issuer = lane == 0 && (eset ? warp == 0 : warp == 2);
+    const int c_first = use_b ? eset * 32 : 0, c_step = use_b ? 64 : 32;
+    if (pre_tma && pre_issuer) {
+      if (use_b) {
+        if (c_first < ncol) issue_pre(c_first >> 5, eset);
+      } else {
+        issue_pre(0, 0);
+        if (ncol > 32) issue_pre(1, 1);
+      }
+    }
+    int kseq = 0;                                      // how many blocks this set has taken
+    for (int c0 = c_first; c0 < ncol; c0 += c_step, ++kseq) {
       const int cg = ncol0 + c0;
       float v[32];
       if (S > 1) {
@@ -522,7 +566,23 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
         const int ch0 = p.cat_C ? colg % p.cat_C : colg;
         const bool rv = (vmask_row != 0);
         float x[32];
-        {
+        if (pre_tma) {
+          const int buf = use_b ? eset : (kseq & 1);
+          const uint32_t par = (uint32_t)(use_b ? (kseq & 1) : ((kseq >> 1) & 1));
+          if (lane == 0) mbar_wait(buf ? pre_bar1 : pre_bar0, par);
+          __syncwarp();
+          const uint32_t rowp = pre_buf + (uint32_t)buf * (TILE_M * 128u) + row_off;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 t;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(rowp + ((((uint32_t)g) ^ sw) << 4)) : "memory");
+            x[4 * g] = t.x; x[4 * g + 1] = t.y; x[4 * g + 2] = t.z; x[4 * g + 3] = t.w;
+          }
+          if (use_b && c0 + 64 < ncol) {            // two sets: refill this set's buffer now
+            if (eset) asm volatile("bar.sync 4, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
+            if (pre_issuer) issue_pre((c0 >> 5) + 2, eset);
+          }
+        } else {
           const long long pix = ((((long long)(mn0 + r_in) * p.OD + ((md0 + r_id) * p.osd + o_d)) * p.OH + ((mh0 + r_ih) * p.osh + o_h)) * p.OW +
                                  ((mw0 + r_iw) * p.osw + o_w));
           const float4* xp = reinterpret_cast<const float4*>(p.bnb_pre + pix * statC + ch0);
@@ -570,10 +630,14 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp), "f"(s0) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp + 4u * (uint32_t)p.BN), "f"(s1) : "memory");
         (void)ch0;
+        if (pre_tma && !use_b && c0 + 64 < ncol) {      // one set: refill this block's buffer with block + 2 (all four warps are done with it)
+          asm volatile("bar.sync 3, 128;" ::: "memory");
+          if (pre_issuer) issue_pre((c0 >> 5) + 2, kseq & 1);
+        }
       }
     }
     fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA engine
-    asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps
+    asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory");  // the epilogue warps (both sets)
     if (warp == 2 && lane == 0) {
       const int nblk = p.out_bf16 ? (ncol >> 6) : (ncol >> 5);
       const int cstep = p.out_bf16 ? 64 : 32;
@@ -584,7 +648,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (p.bnb_pre != nullptr) {
+    if (p.bnb_pre != nullptr && epiA) {
       // (the per-warp partials were published by the bar.sync before the TMA stores)
       const int statC = p.cat_C ? p.cat_C : p.Nout;
       const int uniq = p.cat_C ? p.cat_C : ncol;                    // distinct channels among the columns this rank finishes
@@ -604,7 +668,7 @@ tc_pixgemm_kernel(const __grid_constant__ TcPixParams p, const float* __restrict
         atomicAdd(p.bnb_sums + bn_sum_index(0, p.stats_groups, grp, 1, statC, schan), (double)a1);
       }
     }
-    if (p.stats != nullptr) {
+    if (p.stats != nullptr && epiA) {
       // Fused batch-norm statistics (tf.nn.moments of the pre-norm tensor): the fp32 tile is in shared memory;
       // epilogue thread t sums column t over the tile's valid rows (a warp reads 32 consecutive floats of one
       // swizzled row per step: conflict-free) and adds (sum, sum of squares) to the fp64 accumulators of its group.
@@ -861,6 +925,20 @@ static void set_bnb(TcPixParams& p, const gg_bnbwd_args* b, int N, int* fused) {
   if (fused) *fused = 1;
 }
 
+// The pre-norm tensor of a fused batch-norm backward, seen through the geometry of output map k (same dims, same element
+// strides, fp32): pmap[k].  `estr` are the ELEMENT strides of dims 1..4, `base_elems` the element offset of the class view.
+static int encode_pre_like(TcPixParams& p, const gg_bnbwd_args* b, int k, const uint64_t* odims, const uint64_t* estr, uint64_t base_elems) {
+  if (b == nullptr || b->pre == nullptr || b->sums == nullptr) return GG_OK;
+  static const bool enabled = [] { const char* v = getenv("GG_BNB_TMA"); return !(v && v[0] == '0'); }();   // A/B switch
+  if (!enabled) return GG_OK;
+  const uint64_t pstr[4] = {estr[0] * 4, estr[1] * 4, estr[2] * 4, estr[3] * 4};
+  const uint32_t pbox[5] = {32, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+  int rc = encode_tmap(&p.pmap[k], GG_F32, (const char*)b->pre + base_elems * 4, 5, odims, pstr, pbox);
+  if (rc) return rc;
+  p.pre_tma = 1;
+  return GG_OK;
+}
+
 static int pow2floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 
 static void pick_box(int Mw, int Mh, int Md, int pixels, int* bw, int* bh, int* bd, int* bn) {
@@ -1011,7 +1089,13 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
   p.stages = std::max(2, std::min(8, budget / stage_bytes));
   // the epilogue stages the tile in the pipeline buffers; a split-K tile parks its fp32 partial there first (+ bf16 staging behind it)
   // split-K: S x (BN / S) columns of fp32 partials (= BN * 512 bytes) + the staging of this rank's slice behind them
-  const int out_bytes = p.splitk > 1 ? p.BN * 512 + TILE_M * (p.BN / p.splitk) * (p.out_bf16 ? 2 : 4) : TILE_M * p.BN * (p.out_bf16 ? 2 : 4);
+  int out_bytes = p.splitk > 1 ? p.BN * 512 + TILE_M * (p.BN / p.splitk) * (p.out_bf16 ? 2 : 4) : TILE_M * p.BN * (p.out_bf16 ? 2 : 4);
+  if (p.bnb_pre == nullptr || p.splitk > 1) p.pre_tma = 0;       // (split-K slices keep the direct loads)
+  p.epi2 = (p.splitk == 1 && env_int("GG_TC_EPI2", 1) != 0) ? 1 : 0;
+  if (p.pre_tma) {                                               // two 16 KB buffers for the pre-norm blocks, behind the output staging
+    p.pre_off = (uint32_t)((out_bytes + 1023) & ~1023);
+    out_bytes = (int)p.pre_off + 2 * TILE_M * 128;
+  }
   while (p.stages * stage_bytes < out_bytes) ++p.stages;
   p.stages = std::max(1, std::min(p.stages, env_int("GG_TC_STAGES", p.stages)));
   GG_REQUIRE(p.stages * stage_bytes >= out_bytes, GG_ERR_INVALID, "tc_pixgemm: GG_TC_STAGES too small for the output tile");
@@ -1034,7 +1118,7 @@ static int launch_pix(TcPixParams& p, int total_tiles, const float* bias, void* 
     g_ws.head += need;
     g_ws.cnt_head += 2 * (size_t)total_tiles;
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 4) + 16 + (p.bnb_pre ? 48 * p.BN : 0);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * (2 * p.stages + 4) + 32 + (p.bnb_pre ? 48 * p.BN : 0);
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(tc_pixgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   int rc = GG_OK;
@@ -1079,6 +1163,9 @@ int tc_conv_down(const gg_conv_desc* d, const void* large, const void* w_bf, con
                               (uint64_t)d->Do * d->Ho * d->Wo * d->K * esz};
     const uint32_t obox[5] = {(uint32_t)(128 / esz), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
     rc = encode_tmap(&p.omap[0], d->small_dtype, small, 5, odims, ostr, obox);
+    if (rc) return rc;
+    const uint64_t estr[4] = {(uint64_t)d->K, (uint64_t)d->Wo * d->K, (uint64_t)d->Ho * d->Wo * d->K, (uint64_t)d->Do * d->Ho * d->Wo * d->K};
+    rc = encode_pre_like(p, bnb, 0, odims, estr, 0);
     if (rc) return rc;
   }
   int t = 0;
@@ -1156,6 +1243,9 @@ int tc_conv_up(const gg_conv_desc* d, const void* small, const void* w_ck, const
                                     (uint64_t)d->sd * d->H * d->W * d->C * esz, (uint64_t)d->D * d->H * d->W * d->C * esz};
           const uint32_t obox[5] = {(uint32_t)(128 / esz), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
           rc = encode_tmap(&p.omap[ncls], d->large_dtype, (const char*)large + base_elems * esz, 5, odims, ostr, obox);
+          if (rc) return rc;
+          const uint64_t estr[4] = {(uint64_t)d->sw * d->C, (uint64_t)d->sh * d->W * d->C, (uint64_t)d->sd * d->H * d->W * d->C, (uint64_t)d->D * d->H * d->W * d->C};
+          rc = encode_pre_like(p, bnb, ncls, odims, estr, base_elems);
           if (rc) return rc;
         }
         p.cls[ncls++] = c;
@@ -1284,6 +1374,9 @@ int tc_conv_up_cat(const gg_conv_desc* d, const void* small, const void* w_bf, c
                               (uint64_t)d->D * d->H * d->W * d->C * esz};
     const uint32_t obox[5] = {(uint32_t)(128 / esz), (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
     rc = encode_tmap(&p.omap[k], d->large_dtype, (const char*)large + base_elems * esz, 5, odims, ostr, obox);
+    if (rc) return rc;
+    const uint64_t estr[4] = {(uint64_t)d->sw * d->C, (uint64_t)d->sh * d->W * d->C, (uint64_t)d->sd * d->H * d->W * d->C, (uint64_t)d->D * d->H * d->W * d->C};
+    rc = encode_pre_like(p, bnb, k, odims, estr, base_elems);
     if (rc) return rc;
   }
   p.BN = P.ncls * d->C;                 // 256
