@@ -58,7 +58,9 @@ int c3_conv_down(const gg_conv_desc*, const float*, const float*, const float*, 
 int c3_conv_up(const gg_conv_desc*, const void*, const float*, const float*, float*, cudaStream_t);
 int c3_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t);
 // conv_c3_mma.cu (bf16 mode: warp-level tensor-core MMAs; the fp32 parity mode keeps the SIMT kernels)
-int c3m_conv_down(const gg_conv_desc*, const float*, const float*, const float*, void*, cudaStream_t);
+int c3m_conv_down(const gg_conv_desc*, const float*, const float*, const float*, void*, cudaStream_t, const float* pre = nullptr,
+                  const float* mean = nullptr, const float* rstd = nullptr, const float* gamma = nullptr, const float* beta = nullptr,
+                  double* sums = nullptr, int bact = 0, float bact_param = 0.f, int* fused = nullptr);
 int c3m_conv_up(const gg_conv_desc*, const void*, const float*, const float*, float*, cudaStream_t);
 int c3m_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t);
 static inline bool c3m_applicable(const gg_conv_desc* d) { return c3_applicable(d) && d->small_dtype == GG_BF16; }
@@ -192,6 +194,15 @@ extern "C" int gg_conv_dgrad_bnbwd(const gg_conv_desc* d, int32_t up, const void
   *fused = 0;
   gg_conv_desc c = *d;
   c.act = GG_ACT_NONE;
+  if (!(c.flags & GG_CONV_TENSOR_CORE) && !up && pre && save_mean && save_rstd && sums && groups == 1 && c3m_applicable(&c)) {
+    // image-side layer (g_h4's dgrad produces dy of g_bn3): warp-MMA kernel with the reductions in its epilogue
+    int f = 0, rc = GG_OK;
+    for (int r = 0; r < g_cabi_repeat && rc == GG_OK; ++r)          // (measurement hook: gg_debug_set_repeat)
+      rc = c3m_conv_down(&c, (const float*)dy, (const float*)w, nullptr, dx, (cudaStream_t)stream, pre, save_mean, save_rstd, gamma, beta, sums,
+                         act, act_param, &f);
+    *fused = f;
+    return rc;
+  }
   if (!(c.flags & GG_CONV_TENSOR_CORE) || !pre || !save_mean || !save_rstd || !sums)
     return up ? gg_conv_up(&c, dy, w, nullptr, dx, stream) : gg_conv_down(&c, dy, w, nullptr, dx, stream);
   gg_bnbwd_args b = {pre, save_mean, save_rstd, gamma, beta, sums, act, act_param, groups};

@@ -53,11 +53,25 @@ constexpr int DN_PC = 2 * DN_TW + 3;            // 35 patch columns
 constexpr int DN_PROW = DN_PC * 3 + 1;          // 106 bf16 per patch row (105 + the column read by the zero weight)
 constexpr int DN_WROW = 88;                     // bf16 per channel row of the transposed filter (80 + 8: bank spread)
 
-template <typename TSM>
+// Fused batch-norm BACKWARD reductions (BNB): when this launch is the dgrad of g_h4 (model.py:321), its output IS dy of g_bn3
+// (train mode, ReLU): per channel sum g and sum g*xhat with g = bf16(dy) * act'(gamma*xhat + beta), xhat = (pre - mean) * rstd --
+// what a separate colsum pass over (pre fp32, dy bf16) = 25 MB computed in ~20 us.  Here the thread that holds 16 channels
+// of a pixel loads the matching 64 bytes of `pre` (a quad reads the pixel's whole 256-byte row), per-tile partials are
+// reduced over the 8 pixel lanes by shuffles and meet in shared memory; ONE pair of fp64 atomics per channel per CTA.
+struct C3Bnb {
+  const float *pre, *mean, *rstd, *gamma, *beta;
+  double* sums;               // [2][K], zeroed by the caller
+  int act;
+  float act_param;
+};
+
+template <typename TSM, bool BNB>
 __global__ void __launch_bounds__(256, 2)
 c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, const float* __restrict__ bias, TSM* __restrict__ small,
-                int N, int H, int W, int Ho, int Wo, int K, int kblocks, int act, float act_param) {
+                int N, int H, int W, int Ho, int Wo, int K, int kblocks, int act, float act_param, const C3Bnb bnb) {
   pdl_grid_sync();
+  __shared__ float4 bconst[BNB ? 64 : 1];                   // {rstd, -mean*rstd, gamma, beta} of this CTA's 64 channels
+  __shared__ float bsum[2][BNB ? 64 : 1];
   __shared__ __align__(16) bf16 swt[64 * DN_WROW];          // [channel][kk]
   __shared__ __align__(16) bf16 sp[DN_PR * DN_PROW];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -88,10 +102,16 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
       swf[e] = make_uint2(swt32[(ch * DN_WROW + r * 16 + 2 * tt) >> 1], swt32[(ch * DN_WROW + r * 16 + 2 * tt + 8) >> 1]);
     }
   }
+  if (BNB && tid < 64) {
+    const float mu = __ldg(bnb.mean + kb + tid), rs = __ldg(bnb.rstd + kb + tid);
+    bconst[tid] = make_float4(rs, -mu * rs, bnb.gamma ? __ldg(bnb.gamma + kb + tid) : 1.f, bnb.beta ? __ldg(bnb.beta + kb + tid) : 0.f);
+    bsum[0][tid] = 0.f;
+    bsum[1][tid] = 0.f;
+  }
   __syncthreads();
   float bv[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) bv[i] = bias ? __ldg(bias + kb + t * 16 + i) : 0.f;
+  for (int i = 0; i < 16; ++i) bv[i] = (!BNB && bias) ? __ldg(bias + kb + t * 16 + i) : 0.f;     // (a dgrad launch has no bias: frees 16 registers for BNB)
 
   // Patch elements of this thread: e = tid + 256 k -> (row a, element x in the row, column x / 3), fixed for all tiles.
   constexpr int PK = (DN_PR * DN_PC * 3 + 255) / 256;           // 8 elements per thread
@@ -129,6 +149,23 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
       if (pdesc[k] >= 0) sp[(pdesc[k] & 0xff) * DN_PROW + ((pdesc[k] >> 8) & 0xff)] = __float2bfloat16_rn(pv[k]);
     __syncthreads();
     if (tile + tstride < ntiles) prefetch(tile + tstride);      // next patch streams in while this one is multiplied
+    // BNB: this thread's 16 channels of the pre-norm tensor at its two pixels, requested BEFORE the MMAs (the epilogue would
+    // otherwise expose one more memory round trip per tile: +18 us per launch measured)
+    float xpre[BNB ? 2 : 1][BNB ? 16 : 1];
+    if (BNB) {
+      const int pp = p0 + warp;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int qq = q0 + g + 8 * half;
+        const bool ok = pp < Ho && qq < Wo;
+        const float4* xp = reinterpret_cast<const float4*>(bnb.pre + (((int64_t)n * Ho + (ok ? pp : 0)) * Wo + (ok ? qq : 0)) * K + kb + t * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 u = ok ? __ldg(xp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xpre[half][4 * i] = u.x; xpre[half][4 * i + 1] = u.y; xpre[half][4 * i + 2] = u.z; xpre[half][4 * i + 3] = u.w;
+        }
+      }
+    }
     float acc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
@@ -148,6 +185,11 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
       }
     }
     const int p = p0 + warp;
+    float tg[BNB ? 16 : 1], tgx[BNB ? 16 : 1];                  // this tile's partial reductions of the thread's 16 channels
+    if (BNB) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { tg[i] = 0.f; tgx[i] = 0.f; }
+    }
     if (p < Ho) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -157,6 +199,21 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
 #pragma unroll
         for (int j = 0; j < 8; ++j) { v[2 * j] = acc[j][2 * half] + bv[2 * j]; v[2 * j + 1] = acc[j][2 * half + 1] + bv[2 * j + 1]; }
         act_fwd_vec<16>(v, act, act_param);
+        if (BNB) {
+          const float* x = xpre[BNB ? half : 0];                // (register array: every index below is a compile-time constant)
+          const float slope = act_slope(bnb.act, bnb.act_param), at_zero = bnb.act == GG_ACT_RELU ? 0.f : 1.f;
+          const bool simple = bnb.act <= GG_ACT_LRELU;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 k = bconst[t * 16 + i];
+            const float xh = fmaf(x[i], k.x, k.y);
+            const float u = fmaf(k.z, xh, k.w);
+            float gv = sizeof(TSM) == 2 ? __bfloat162float(__float2bfloat16_rn(v[i])) : v[i];      // what the apply kernel reads back
+            gv *= simple ? (u > 0.f ? 1.f : (u == 0.f ? at_zero : slope)) : act_grad_from_pre(u, bnb.act, bnb.act_param);
+            tg[i] += gv;
+            tgx[i] = fmaf(gv, xh, tgx[i]);
+          }
+        }
         TSM* dst = small + (((int64_t)n * Ho + p) * Wo + q) * K + kb + t * 16;
         if (sizeof(TSM) == 2) {                          // 16 bf16 = two 16-byte stores; the quad covers the pixel's 128-byte row
           uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -167,6 +224,27 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
           for (int i = 0; i < 16; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         }
       }
+    }
+    if (BNB) {       // (all 32 lanes: rows beyond Ho contribute zeros) reduce over the 8 pixel lanes g (lane bits 2..4), then shared atomics
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int m = 4; m <= 16; m <<= 1) {
+          tg[i] += __shfl_xor_sync(0xffffffffu, tg[i], m);
+          tgx[i] += __shfl_xor_sync(0xffffffffu, tgx[i], m);
+        }
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { atomicAdd(&bsum[0][t * 16 + i], tg[i]); atomicAdd(&bsum[1][t * 16 + i], tgx[i]); }
+      }
+    }
+  }
+  if (BNB) {
+    __syncthreads();
+    if (tid < 128) {
+      const int which = tid >> 6, ch = tid & 63;
+      atomicAdd(bnb.sums + bn_sum_index(0, 1, 0, which, K, kb + ch), (double)bsum[which][ch]);
     }
   }
 }
@@ -407,15 +485,23 @@ c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small,
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-int c3m_conv_down(const gg_conv_desc* d, const float* large, const float* w, const float* bias, void* small, cudaStream_t st) {
+// bnb (optional, bf16 output, one row group): also accumulate the consumer batch norm's backward reductions; *fused = 1 when done
+int c3m_conv_down(const gg_conv_desc* d, const float* large, const float* w, const float* bias, void* small, cudaStream_t st,
+                  const float* pre = nullptr, const float* mean = nullptr, const float* rstd = nullptr, const float* gamma = nullptr,
+                  const float* beta = nullptr, double* sums = nullptr, int bact = 0, float bact_param = 0.f, int* fused = nullptr) {
   const int kblocks = d->K / 64;
   const int ntiles = d->N * ceil_div(d->Ho, DN_TH) * ceil_div(d->Wo, DN_TW);
   const int per_k = std::max(1, std::min(ntiles, (148 * 2) / std::min(kblocks, 296)));     // 2 co-resident CTAs per SM
   const int grid = per_k * kblocks;
-  if (d->small_dtype == GG_F32)
-    Launch(grid, 256, 0, st)(c3m_down_kernel<float>, large, w, bias, (float*)small, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks, d->act, d->act_param);
-  else
-    Launch(grid, 256, 0, st)(c3m_down_kernel<bf16>, large, w, bias, (bf16*)small, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks, d->act, d->act_param);
+  C3Bnb b = {pre, mean, rstd, gamma, beta, sums, bact, bact_param};
+  if (pre != nullptr && sums != nullptr && d->small_dtype == GG_BF16 && ((uintptr_t)pre % 16) == 0) {
+    Launch(grid, 256, 0, st)(c3m_down_kernel<bf16, true>, large, w, bias, (bf16*)small, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks, d->act, d->act_param, b);
+    if (fused) *fused = 1;
+  } else if (d->small_dtype == GG_F32) {
+    Launch(grid, 256, 0, st)(c3m_down_kernel<float, false>, large, w, bias, (float*)small, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks, d->act, d->act_param, b);
+  } else {
+    Launch(grid, 256, 0, st)(c3m_down_kernel<bf16, false>, large, w, bias, (bf16*)small, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks, d->act, d->act_param, b);
+  }
   return check_launch("c3m_down");
 }
 

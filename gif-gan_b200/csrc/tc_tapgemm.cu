@@ -59,6 +59,11 @@ int encode_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const u
                 const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
   GG_REQUIRE(enc != nullptr, GG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.  A thread that has only had its
+  // device selected (an autograd worker before its first runtime call) has none yet -> CUDA_ERROR_INVALID_CONTEXT (201);
+  // one runtime call binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { (void)cudaFree(nullptr); ctx_bound = true; }
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }

@@ -184,7 +184,7 @@ class DCGAN(object):
             # relu(g_bnN(...)): linear/deconv + batch norm + ReLU as one fused node each (model.py:304-319)
             h0, self.h0_w, self.h0_b = linear(z, self.gf_dim * 8 * s16 * s16, 'g_h0_lin', with_w=True, bn=self.g_bn0,
                                               bn_channels=self.gf_dim * 8, train=train, act='relu')
-            h0 = h0.reshape(-1, s16, s16, self.gf_dim * 8)
+            h0 = ops.reshape(h0, (-1, s16, s16, self.gf_dim * 8))
             h1, self.h1_w, self.h1_b = deconv2d(h0, [B, s8, s8, self.gf_dim * 4], name='g_h1', with_w=True, bn=self.g_bn1,
                                                 train=train, act='relu')
             h2, self.h2_w, self.h2_b = deconv2d(h1, [B, s4, s4, self.gf_dim * 2], name='g_h2', with_w=True, bn=self.g_bn2,

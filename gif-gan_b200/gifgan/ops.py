@@ -451,14 +451,14 @@ FUSE_LINEAR_BN = os.environ.get("GG_FUSE_LINEAR_BN", "0") == "1"    # opt-in: th
 FUSE_BN_BWD = os.environ.get("GG_FUSE_BN_BWD", "1") != "0"    # A/B switch: batch-norm backward reductions in the dgrad epilogue
 
 
-def _run_dgrad_bnbwd(g: _Geom, up, src, wvar, out, bnb: _BnInfo):
+def _run_dgrad_bnbwd(g: _Geom, up, src, wvar, out, bnb: _BnInfo, tc=True):
     """dgrad launch that also accumulates the consumer batch norm's (sum g, sum g*xhat); returns True when it was fused."""
     L = cabi.lib()
     large, small = (out, src) if up else (src, out)
-    d = g.desc(dt(large), dt(small), None, 0.0, True)
+    d = g.desc(dt(large), dt(small), None, 0.0, tc)
     sums = _zeroed_f64(L.gg_bn_workspace_bytes(bnb.Cc, bnb.groups) // 8, out.device)[0]
     fused = ctypes.c_int32(0)
-    check(L.gg_conv_dgrad_bnbwd(ctypes.byref(d), 1 if up else 0, ptr(src), ptr(wvar.bf16()), ptr(out), ptr(bnb.pre), ptr(bnb.mean), ptr(bnb.rstd),
+    check(L.gg_conv_dgrad_bnbwd(ctypes.byref(d), 1 if up else 0, ptr(src), ptr(wvar.bf16() if tc else wvar.data), ptr(out), ptr(bnb.pre), ptr(bnb.mean), ptr(bnb.rstd),
                                 ptr(bnb.gamma), ptr(bnb.beta), ACT[bnb.act], float(bnb.act_param), bnb.groups, ptr(sums), ctypes.byref(fused),
                                 stream()), "gg_conv_dgrad_bnbwd")
     if fused.value:
@@ -467,8 +467,23 @@ def _run_dgrad_bnbwd(g: _Geom, up, src, wvar, out, bnb: _BnInfo):
 
 
 def _bnb_usable(bnb, out_shape, out_dtype):
-    return (FUSE_BN_BWD and bnb is not None and bnb.pre is not None and tuple(bnb.pre.shape) == tuple(out_shape)
+    # same memory layout is what matters: [B, s*s*C] of a linear feeding a batch norm over C channels IS [B, s, s, C]
+    n = 1
+    for e in out_shape:
+        n *= int(e)
+    return (FUSE_BN_BWD and bnb is not None and bnb.pre is not None and bnb.pre.numel() == n
             and bnb.pre.dtype == torch.float32 and out_shape[-1] == bnb.Cc)
+
+
+def reshape(x, shape):
+    """x.reshape(shape) that keeps the batch-norm hand-over of a fused node's output (`_gg_bn`), so that the conv consuming the
+    reshaped tensor still produces that batch norm's backward reductions in its dgrad launch (model.py:305: the generator's
+    [B, 8192] projection viewed as [B, 4, 4, 512])."""
+    y = x.reshape(shape)
+    info = getattr(x, "_gg_bn", None)
+    if info is not None and y.shape[-1] == info.Cc:
+        y._gg_bn = info
+    return y
 
 
 def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim, out=None, stats=None, groups=1, bnb=None):
@@ -476,8 +491,10 @@ def _run_down(g: _Geom, large, wvar: Var, bias, out_dtype, act, act_param, ndim,
     bnb: the _BnInfo of the batch norm whose output gradient this launch produces (dgrad of a deconv)."""
     small = out if out is not None else torch.empty(g.small_shape(ndim), dtype=out_dtype, device=large.device)
     tc = _tc_ok(g.C, g.K, large)
-    if tc and bias is None and act is None and stats is None and _bnb_usable(bnb, small.shape, small.dtype):
-        _run_dgrad_bnbwd(g, False, large, wvar, small, bnb)
+    # image-side layer in bf16 mode (g_h4's dgrad: fp32 image gradient in, bf16 dy of g_bn3 out): the warp-MMA kernel fuses too
+    c3 = (not tc) and g.C == 3 and _PRECISION == "bf16" and small.dtype == torch.bfloat16 and large.dtype == torch.float32 and bnb is not None and bnb.groups == 1
+    if (tc or c3) and bias is None and act is None and stats is None and _bnb_usable(bnb, small.shape, small.dtype):
+        _run_dgrad_bnbwd(g, False, large, wvar, small, bnb, tc=tc)
         return small
     d = g.desc(dt(large), dt(small), act, act_param, tc)
     w = wvar.bf16() if tc else wvar.data
@@ -1045,7 +1062,7 @@ class _FusedBN(torch.autograd.Function):
         nbytes = L.gg_bn_workspace_bytes(Cc, ctx.groups)
         info = ctx.info
         if (ctx.train and info is not None and info.bwd_sums is not None and dy.data_ptr() == info.bwd_dy.data_ptr()
-                and dy._version == info.bwd_version and dy.dtype == info.bwd_dy.dtype and tuple(dy.shape) == tuple(info.bwd_dy.shape)):
+                and dy._version == info.bwd_version and dy.dtype == info.bwd_dy.dtype and dy.numel() == info.bwd_dy.numel()):
             # the dgrad launch that wrote dy (the ONLY contribution to it: an accumulated gradient is another tensor or another
             # version) already reduced (sum g, sum g*xhat) in its epilogue: apply pass only
             ws, mode = info.bwd_sums, 3

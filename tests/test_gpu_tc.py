@@ -338,6 +338,8 @@ def test_train_step_enters_the_graph_with_current_filter_copies():
     ("conv", 8, 16, 128, 64, 128, 1),       # 64-channel batch norm: its dy comes from the class-concatenated conv_up (N = 256)
     ("conv", 6, 12, 64, 128, 64, 3),        # partial tiles (12 x 12 -> 6 x 6 -> 3 x 3), three row groups of two images
     ("deconv", 16, 4, 512, 256, 128, 1),    # g_h1 -> bn1 -> relu -> g_h2: dy comes from a conv_down launch
+    ("deconv", 8, 16, 128, 64, 3, 1),       # g_h3 -> bn3 -> relu -> g_h4 (image side): dy comes from the warp-MMA c3m_down launch
+    ("deconv", 3, 10, 64, 64, 3, 1),        # the same with partial 8 x 16 tiles (20 x 20 small grid)
 ])
 def test_bn_backward_reductions_fused_into_dgrad(kind, B, H, C0, C1, C2, groups, monkeypatch):
     """gg_conv_dgrad_bnbwd: (sum g, sum g*xhat) of a train-mode batch norm accumulated in the epilogue of the dgrad launch
@@ -352,7 +354,8 @@ def test_bn_backward_reductions_fused_into_dgrad(kind, B, H, C0, C1, C2, groups,
             h = _o.conv2d(t, C1, name="a", bn=bn, act=act, groups=groups)
             return _o.conv2d(h, C2, name="b", bias=False)
         h = _o.deconv2d(t, [B, 2 * H, 2 * H, C1], name="a", bn=bn, act=act, groups=groups)
-        return _o.deconv2d(h, [B, 4 * H, 4 * H, C2], name="b", bias=False)
+        # (3 output channels: the image side -- fp32 image out, as g_h4 in the model)
+        return _o.deconv2d(h, [B, 4 * H, 4 * H, C2], name="b", bias=False, out_dtype=torch.float32 if C2 == 3 else None)
 
     x = bf16_round(rs.randn(B, H, H, C0))
     results = []
@@ -373,7 +376,7 @@ def test_bn_backward_reductions_fused_into_dgrad(kind, B, H, C0, C1, C2, groups,
             y = build(xt, bn)
             if not results:
                 dy = bf16_round(rs.randn(*y.shape))
-            y.backward(dy.cuda().to(torch.bfloat16))
+            y.backward(dy.cuda().to(y.dtype))
         results.append(dict(dx=xt.grad.float().cpu(), launches=ops.cabi.launch_count() - n0,
                             grads={k: st.vars[k].grad.clone().cpu() for k in ("a/w", "b/w", "bn/gamma", "bn/beta")}))
     two, one = results
