@@ -80,12 +80,25 @@ c3m_down_kernel(const float* __restrict__ large, const float* __restrict__ w, co
   const int ntiles = N * tiles_h * tiles_w;
 
   // ---- filter block -> shared (transposed, bf16, zero pad columns) -> B fragments in registers
+  // (all 19 filter loads of a thread are issued before anything waits on one: as a load -> convert -> store loop the staging
+  //  was a chain of 19 L2 round trips, ~half of the launch at batch 64)
+  constexpr int NWL = (75 * 64 + 255) / 256;
+  float wl[NWL];
+#pragma unroll
+  for (int k = 0; k < NWL; ++k) {
+    const int e = tid + 256 * k;
+    wl[k] = (e < 75 * 64) ? __ldg(w + (int64_t)(e >> 6) * K + kb + (e & 63)) : 0.f;
+  }
   for (int e = tid; e < 64 * DN_WROW; e += 256) swt[e] = __float2bfloat16_rn(0.f);
   __syncthreads();
-  for (int e = tid; e < 75 * 64; e += 256) {
-    const int tc = e >> 6, ch = e & 63;
-    const int kk = (tc / 15) * 16 + (tc % 15);
-    swt[ch * DN_WROW + kk] = __float2bfloat16_rn(__ldg(w + (int64_t)tc * K + kb + ch));
+#pragma unroll
+  for (int k = 0; k < NWL; ++k) {
+    const int e = tid + 256 * k;
+    if (e < 75 * 64) {
+      const int tc = e >> 6, ch = e & 63;
+      const int kk = (tc / 15) * 16 + (tc % 15);
+      swt[ch * DN_WROW + kk] = __float2bfloat16_rn(wl[k]);
+    }
   }
   for (int e = tid; e < DN_PR; e += 256) sp[e * DN_PROW + DN_PROW - 1] = __float2bfloat16_rn(0.f);
   __syncthreads();
@@ -309,13 +322,26 @@ c3m_up_kernel(const TSM* __restrict__ small, const float* __restrict__ w, const 
       __syncthreads();
       // expanded filter of this channel block: swu[n][(dp+1)*3 + (dq+1)][k] = w[a+1-2dp][b+1-2dq][c][kb+k] (0 if outside 5x5)
       if (kb > 0 || tile == (int)blockIdx.x || K > 64) {
-        for (int e = tid; e < 16 * 9 * 16; e += 256) {          // 4 channels per item
-          const int k4 = (e & 15) * 4, nb = (e >> 4) % 9, nn = e / (16 * 9);
-          const int cls = nn / 3, c = nn - cls * 3, a = cls >> 1, b = cls & 1;
-          const int r = a + 1 - 2 * (nb / 3 - 1), s = b + 1 - 2 * (nb % 3 - 1);
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (nn < 12 && r >= 0 && r < KT5 && s >= 0 && s < KT5) v = ld4(w + ((int64_t)((r * KT5 + s) * 3 + c)) * K + kb + k4);
-          st4(swu + nn * UP_WROW + nb * 64 + k4, v);
+        // 9 items of 4 channels per thread, loads batched 3 at a time (three L2 round trips instead of nine; the whole batch of
+        // nine does not fit the 80-register budget of three co-resident CTAs without spilling)
+#pragma unroll 1
+        for (int k0 = 0; k0 < 9; k0 += 3) {
+          float4 wu[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int e = tid + 256 * (k0 + k);
+            const int k4 = (e & 15) * 4, nb = (e >> 4) % 9, nn = e / (16 * 9);
+            const int cls = nn / 3, c = nn - cls * 3, a = cls >> 1, b = cls & 1;
+            const int r = a + 1 - 2 * (nb / 3 - 1), s = b + 1 - 2 * (nb % 3 - 1);
+            wu[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (nn < 12 && r >= 0 && r < KT5 && s >= 0 && s < KT5) wu[k] = ld4(w + ((int64_t)((r * KT5 + s) * 3 + c)) * K + kb + k4);
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int e = tid + 256 * (k0 + k);
+            const int k4 = (e & 15) * 4, nb = (e >> 4) % 9, nn = e / (16 * 9);
+            st4(swu + nn * UP_WROW + nb * 64 + k4, wu[k]);
+          }
         }
       }
 #pragma unroll

@@ -226,6 +226,7 @@ skinny_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const f
   if (out_dim == 1 && (in_dim & 3) == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)W % 16 == 0)) {
     // the GEMV of d_h3_lin / dvideo_h4: 4 elements per thread per trip, all loads independent
     const TX* xr = x + (int64_t)r * in_dim;
+#pragma unroll 8                                                // (8 trips for d_h3_lin's 8192 inputs: their 16 loads go out together)
     for (int k = threadIdx.x * 4; k < in_dim; k += blockDim.x * 4) {
       const float4 xv = ld4(xr + k), wv = ld4(W + k);
       acc[0] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[0]))));
@@ -491,8 +492,17 @@ thin_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ W, const flo
   const int r0 = blockIdx.y * THIN_ROWS;
   {
     const int r = threadIdx.x >> 3, l = threadIdx.x & 7;        // 8 threads per row, 32 rows
-#pragma unroll 4
-    for (int i = l; i < in_dim; i += 8) xs[i * THIN_ROWS + r] = (r0 + r < rows) ? ldf(x + (int64_t)(r0 + r) * in_dim + i) : 0.f;
+    float xv[THIN_MAXK / 8];                                    // all of the thread's loads first (<= 16), then the transposed stores
+#pragma unroll
+    for (int u = 0; u < THIN_MAXK / 8; ++u) {
+      const int i = l + 8 * u;
+      xv[u] = (i < in_dim && r0 + r < rows) ? ldf(x + (int64_t)(r0 + r) * in_dim + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < THIN_MAXK / 8; ++u) {
+      const int i = l + 8 * u;
+      if (i < in_dim) xs[i * THIN_ROWS + r] = xv[u];
+    }
   }
   __syncthreads();
   const int c = threadIdx.x & (THIN_COLS - 1), g = threadIdx.x >> 6;
@@ -567,9 +577,18 @@ thin_wgrad_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, float* __
   float* bred = red + 4 * THIN_ROWS * THIN_COLS;                // [g][c]      1 KB
   float* xsw = bred + 4 * THIN_COLS;                            // [r][32] : this block's 32 input features of every row
   const int i0 = blockIdx.y * THIN_ROWS;
-  for (int e = threadIdx.x; e < rows * THIN_ROWS; e += 256) {
-    const int r = e >> 5, i = e & 31;
-    xsw[e] = (i0 + i < in_dim) ? ldf(x + (int64_t)r * in_dim + i0 + i) : 0.f;
+  for (int e0 = threadIdx.x; e0 < rows * THIN_ROWS; e0 += 8 * 256) {      // eight loads in flight per thread (a load -> store loop is a
+    float xv[8];                                                          // chain of L2 round trips: 8 of them at batch 64)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + 256 * u, r = e >> 5, i = e & 31;
+      xv[u] = (e < rows * THIN_ROWS && i0 + i < in_dim) ? ldf(x + (int64_t)r * in_dim + i0 + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + 256 * u;
+      if (e < rows * THIN_ROWS) xsw[e] = xv[u];
+    }
   }
   __syncthreads();
   const int c = threadIdx.x & (THIN_COLS - 1), g = threadIdx.x >> 6;
