@@ -31,14 +31,28 @@ struct ColGeom {
   int vec;
 };
 
-static ColGeom col_geom(int64_t rows_per_group, int C, int groups, bool vec_ok) {
+// Threads per CTA of the column REDUCTIONS (colsum, bias_grad).  Their grid is kept at ~2 CTAs per SM (every CTA ends with
+// 2 C fp64 atomics on the same addresses), so with 256 threads an SM held 16 warps and a thread walked its rows in ~7
+// dependent load batches: latency-bound at ~1.3 TB/s.  More threads per CTA = the same grid, more warps, fewer batches.
+// Measured inside the step (same box, GG_COLSUM_THREADS): 256 -> 1.4192, 512 -> 1.4125, 1024 -> 1.4153 ms: 512.
+constexpr int CS_MAX_THREADS = 1024;
+static int colsum_threads() {
+  static const int t = [] {
+    const char* v = getenv("GG_COLSUM_THREADS");
+    const int n = (v && *v) ? atoi(v) : 512;
+    return (n == 256 || n == 512 || n == 1024) ? n : 512;
+  }();
+  return t;
+}
+
+static ColGeom col_geom(int64_t rows_per_group, int C, int groups, bool vec_ok, int threads = BN_THREADS) {
   ColGeom g;
   g.vec = (vec_ok && C % 4 == 0) ? 4 : 1;
   const int lanes = C / g.vec;
   int tx = 1;
   while (tx < lanes && tx < BN_THREADS) tx <<= 1;
   g.tx = tx;
-  g.ty = BN_THREADS / tx;
+  g.ty = threads / tx;
   g.cblocks = ceil_div(lanes, tx);
   // ~2 CTAs per SM in total: every CTA ends with 2*C fp64 atomics on the same C addresses, so the tail cost grows
   // with the CTA count while the streaming part is bandwidth-trivial at these sizes
@@ -54,12 +68,12 @@ static ColGeom col_geom(int64_t rows_per_group, int C, int groups, bool vec_ok) 
 // MODE 1: (g, g*xhat), g = dy*act'(gamma*xhat+beta)  -> BN backward reductions
 // MODE 2: (x, 0) column sum                          -> bias gradient
 template <typename TX, typename TD, int VEC, int MODE>
-__global__ void __launch_bounds__(BN_THREADS)
+__global__ void __launch_bounds__(MODE == 1 ? 512 : CS_MAX_THREADS)      // (the backward reductions need > 64 registers: 512 threads)
 colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_per_group, int C,
               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
               const float* __restrict__ rstd, int act, float act_param, double* __restrict__ sums, int tx_dim, int R) {
   pdl_grid_sync();
-  const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
+  const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = (int)blockDim.x / tx_dim;
   const int grp = blockIdx.z;
   const int c = (blockIdx.y * tx_dim + tx) * VEC;
   const bool active = c < C;
@@ -124,7 +138,7 @@ colsum_kernel(const TX* __restrict__ x, const TD* __restrict__ dy, int64_t rows_
     }
   }
   // block reduction over ty
-  __shared__ float red[2][BN_THREADS * 4];
+  __shared__ float red[2][CS_MAX_THREADS * VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { red[0][threadIdx.x * VEC + v] = s0[v]; red[1][threadIdx.x * VEC + v] = s1[v]; }
   __syncthreads();
@@ -435,12 +449,13 @@ __global__ void add_colsum_kernel(const double* __restrict__ sums, int C, float*
 template <typename TX, typename TD, int MODE>
 static void launch_colsum(const void* x, const void* dy, int64_t rpg, int C, int groups, const float* gamma, const float* beta,
                           const float* mean, const float* rstd, int act, float ap, double* sums, bool vec_ok, cudaStream_t st, int R) {
-  ColGeom g = col_geom(rpg, C, groups, vec_ok);
+  const int threads = MODE == 1 ? std::min(512, colsum_threads()) : colsum_threads();
+  ColGeom g = col_geom(rpg, C, groups, vec_ok, threads);
   dim3 grid(g.rblocks, g.cblocks, groups);
   if (g.vec == 4)
-    Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 4, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx, R);
+    Launch(grid, threads, 0, st)(colsum_kernel<TX, TD, 4, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx, R);
   else
-    Launch(grid, BN_THREADS, 0, st)(colsum_kernel<TX, TD, 1, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx, R);
+    Launch(grid, threads, 0, st)(colsum_kernel<TX, TD, 1, MODE>, (const TX*)x, (const TD*)dy, rpg, C, gamma, beta, mean, rstd, act, ap, sums, g.tx, R);
 }
 
 // streaming (apply) kernels: same 2-D mapping, but sized to fill the machine (no atomics at the end)
@@ -722,10 +737,10 @@ extern "C" int gg_bias_grad(const void* dy, int32_t dy_dt, float* db, int64_t ro
 
 namespace gg {
 template <typename TD, int VEC>
-__global__ void __launch_bounds__(BN_THREADS)
+__global__ void __launch_bounds__(CS_MAX_THREADS)
 bias_grad_kernel(const TD* __restrict__ dy, float* __restrict__ db, int64_t rows, int C, int tx_dim) {
   pdl_grid_sync();
-  const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = BN_THREADS / tx_dim;
+  const int tx = threadIdx.x % tx_dim, ty = threadIdx.x / tx_dim, ty_dim = (int)blockDim.x / tx_dim;
   const int c = (blockIdx.y * tx_dim + tx) * VEC;
   float s[VEC];
 #pragma unroll
@@ -754,7 +769,7 @@ bias_grad_kernel(const TD* __restrict__ dy, float* __restrict__ db, int64_t rows
         for (int v = 0; v < VEC; ++v) s[v] += t[ub][v];
     }
   }
-  __shared__ float red[BN_THREADS * 4];
+  __shared__ float red[CS_MAX_THREADS * VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) red[threadIdx.x * VEC + v] = s[v];
   __syncthreads();
@@ -770,14 +785,15 @@ bias_grad_kernel(const TD* __restrict__ dy, float* __restrict__ db, int64_t rows
 }  // namespace gg
 
 int bias_grad_impl(const void* dy, int dy_dt, float* db, int64_t rows, int C, cudaStream_t st) {
-  ColGeom g = col_geom(rows, C, 1, aligned16(dy));
+  const int threads = colsum_threads();
+  ColGeom g = col_geom(rows, C, 1, aligned16(dy), threads);
   dim3 grid(g.rblocks, g.cblocks, 1);
   if (dy_dt == GG_F32) {
-    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bias_grad_kernel<float, 4>, (const float*)dy, db, rows, C, g.tx);
-    else Launch(grid, BN_THREADS, 0, st)(bias_grad_kernel<float, 1>, (const float*)dy, db, rows, C, g.tx);
+    if (g.vec == 4) Launch(grid, threads, 0, st)(bias_grad_kernel<float, 4>, (const float*)dy, db, rows, C, g.tx);
+    else Launch(grid, threads, 0, st)(bias_grad_kernel<float, 1>, (const float*)dy, db, rows, C, g.tx);
   } else {
-    if (g.vec == 4) Launch(grid, BN_THREADS, 0, st)(bias_grad_kernel<bf16, 4>, (const bf16*)dy, db, rows, C, g.tx);
-    else Launch(grid, BN_THREADS, 0, st)(bias_grad_kernel<bf16, 1>, (const bf16*)dy, db, rows, C, g.tx);
+    if (g.vec == 4) Launch(grid, threads, 0, st)(bias_grad_kernel<bf16, 4>, (const bf16*)dy, db, rows, C, g.tx);
+    else Launch(grid, threads, 0, st)(bias_grad_kernel<bf16, 1>, (const bf16*)dy, db, rows, C, g.tx);
   }
   return check_launch("bias_grad");
 }
