@@ -401,7 +401,7 @@ constexpr int WG_YPIX = 72;                     // bf16 per staged small pixel
 
 template <typename TSM>
 __global__ void __launch_bounds__(256, 2)
-c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small, float* __restrict__ dw,
+c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small, float* __restrict__ dw, float* __restrict__ dbias,
                  int N, int H, int W, int Ho, int Wo, int K, int kblocks) {
   pdl_grid_sync();
   __shared__ __align__(16) bf16 sp[WG_PR * WG_PC * 4];          // [row][col][4]   5,472 B
@@ -465,9 +465,21 @@ c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small,
   if (tile < ntiles) prefetch(tile);
   for (; tile < ntiles; tile += tstride) {
     __syncthreads();                                            // previous tile's fragments are consumed
+    // The staged pixels have a fourth, unused channel slot (its filter-gradient rows are discarded).  With dbias it holds 1 for
+    // in-image pixels: the row of tap (1, 1) -- input pixel (2p, 2q), inside the image for every small pixel -- then accumulates
+    // sum_pixels 1 * small[pixel, k] = the bias gradient of the conv, at no extra MMA.
+    int ti0 = 0, tj0 = 0;
+    if (dbias) {
+      const int rem = tile % (tiles_h * tiles_w);
+      ti0 = 2 * ((rem / tiles_w) * WG_TH) - 1; tj0 = 2 * ((rem % tiles_w) * WG_TW) - 1;
+    }
 #pragma unroll
     for (int k = 0; k < PPX; ++k)
-      if (pab[k] >= 0) *reinterpret_cast<uint2*>(sp + (tid + 256 * k) * 4) = make_uint2(pack2(pv[k][0], pv[k][1]), pack2(pv[k][2], 0.f));
+      if (pab[k] >= 0) {
+        const int i = ti0 + (pab[k] & 0xff), j = tj0 + (pab[k] >> 8);
+        const float one = (dbias && i >= 0 && i < H && j >= 0 && j < W) ? 1.f : 0.f;
+        *reinterpret_cast<uint2*>(sp + (tid + 256 * k) * 4) = make_uint2(pack2(pv[k][0], pv[k][1]), pack2(pv[k][2], one));
+      }
 #pragma unroll
     for (int k = 0; k < PYC; ++k) {
       const int e = tid + 256 * k;
@@ -499,6 +511,11 @@ c3m_wgrad_kernel(const float* __restrict__ large, const TSM* __restrict__ small,
   for (int half = 0; half < 2; ++half) {
     const int mb = 2 * warp + half;                             // m = 8*half + g  ->  m block, entry g
     const int r = mb / 3, s = 2 * (mb % 3) + (g >> 2), c = g & 3;
+    if (dbias && r == 1 && s == 1 && c == 3) {                  // the ones-channel row of tap (1, 1): bias gradient
+#pragma unroll
+      for (int jn = 0; jn < 8; ++jn)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dbias + kb + 2 * t + jn * 8), "f"(acc[jn][2 * half]), "f"(acc[jn][2 * half + 1]) : "memory");
+    }
     if (mb >= 15 || s >= KT5 || c >= 3) continue;
     float* dst = dw + ((int64_t)((r * KT5 + s) * 3 + c)) * K + kb + 2 * t;
 #pragma unroll
@@ -541,15 +558,16 @@ int c3m_conv_up(const gg_conv_desc* d, const void* small, const float* w, const 
   return check_launch("c3m_up");
 }
 
-int c3m_conv_wgrad(const gg_conv_desc* d, const float* large, const void* small, float* dw, cudaStream_t st) {
+// dbias (optional): the conv's bias gradient sum_pixels small[pixel, k] is accumulated (+=) by the same launch
+int c3m_conv_wgrad(const gg_conv_desc* d, const float* large, const void* small, float* dw, cudaStream_t st, float* dbias) {
   const int kblocks = d->K / 64;
   const int ntiles = d->N * ceil_div(d->Ho, WG_TH) * ceil_div(d->Wo, WG_TW);
   const int per_k = std::max(1, std::min(ntiles, (148 * 2) / std::min(kblocks, 296)));
   const int grid = per_k * kblocks;
   if (d->small_dtype == GG_F32)
-    Launch(grid, 256, 0, st)(c3m_wgrad_kernel<float>, large, (const float*)small, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
+    Launch(grid, 256, 0, st)(c3m_wgrad_kernel<float>, large, (const float*)small, dw, dbias, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
   else
-    Launch(grid, 256, 0, st)(c3m_wgrad_kernel<bf16>, large, (const bf16*)small, dw, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
+    Launch(grid, 256, 0, st)(c3m_wgrad_kernel<bf16>, large, (const bf16*)small, dw, dbias, d->N, d->H, d->W, d->Ho, d->Wo, d->K, kblocks);
   return check_launch("c3m_wgrad");
 }
 

@@ -134,11 +134,11 @@ class DCGAN(object):
         self.all_vars = mine
 
     # ------------------------------------------------------------------------------
-    def discriminator(self, image, y=None, reuse=False, train=True, groups=1, stop_at_h2=False):
+    def discriminator(self, image, y=None, reuse=False, train=True, groups=1, stop_at_h2=False, ce_segments=None):
         with self.store.absolute_scope(self.scope_prefix):
-            return self._discriminator(image, y, reuse, train, groups, stop_at_h2)
+            return self._discriminator(image, y, reuse, train, groups, stop_at_h2, ce_segments)
 
-    def _discriminator(self, image, y=None, reuse=False, train=True, groups=1, stop_at_h2=False):
+    def _discriminator(self, image, y=None, reuse=False, train=True, groups=1, stop_at_h2=False, ce_segments=None):
         """model.py:268-296.  `groups=2` runs D(real) and D(fake) as one batch whose halves are
         batch-normalised separately (identical numbers to two calls, half the launches).  `stop_at_h2`
         evaluates only what D_activations needs (what TF's pruning does for VID_DCGAN's fetches)."""
@@ -153,7 +153,9 @@ class DCGAN(object):
             h1 = conv2d(h0, self.df_dim * 2, name='d_h1_conv', bn=self.d_bn1, train=train, act='lrelu', groups=groups)
             h2 = conv2d(h1, self.df_dim * 4, name='d_h2_conv', bn=self.d_bn2, train=train, act='lrelu', groups=groups)
             h3 = conv2d(h2, self.df_dim * 8, name='d_h3_conv', bn=self.d_bn3, train=train, act='lrelu', groups=groups)
-            h4 = linear(h3.reshape(B, -1), 1, 'd_h3_lin')
+            # `ce_segments`: the train step's cross-entropy means (model.py:121-131) ride in the same launch as the logits, and
+            # the launch that back-propagates them carries d_bn3's backward reductions (ops.reshape keeps the hand-over)
+            h4 = linear(ops.reshape(h3, (B, -1)), 1, 'd_h3_lin', ce_segments=ce_segments)
             return (ops.sigmoid(h4) if self.want_sigmoid else None), h4, h2
         else:
             B = image.shape[0]
@@ -238,7 +240,7 @@ class DCGAN(object):
             both[:B].copy_(images)
         if self.dp is not None:
             self.dp.wait_pending()
-        self.d_optim.zero_grad()
+        self.d_optim.zero_grad(overlap=self.dp is None)
         if self.dp is not None:
             self.dp.begin_update(self.d_optim)
         with ops.trainable(self.d_vars), ops.overlap_wgrad(), ops.stats_arena():
@@ -247,8 +249,10 @@ class DCGAN(object):
             if self.noise_std:
                 both = add_noise(both, self.noise_std)
             yy = torch.cat([y, y], 0) if y is not None else None
-            logits = self.discriminator(both, yy, reuse=True, groups=2)[1]
-            losses = sigmoid_cross_entropy_loss(logits, [(0, B, 1.0, 1.0), (B, 2 * B, 0.0, 1.0)])
+            segs = [(0, B, 1.0, 1.0), (B, 2 * B, 0.0, 1.0)]
+            logits = self.discriminator(both, yy, reuse=True, groups=2, ce_segments=segs)[1]
+            losses = sigmoid_cross_entropy_loss(logits, segs)
+            ops.join_side()         # the gradient zero-fill (side stream) precedes every gradient kernel
             torch.autograd.backward(losses, grad_tensors=self._ones(losses))
         if self.dp is not None and apply:
             # remaining bucket + Adam on the communication stream: the next update's generator forward overlaps them
@@ -262,15 +266,17 @@ class DCGAN(object):
 
     def g_update(self, z, y=None, apply=True):
         """sess.run([g_optim, g_sum]) (model.py:232-234): G fwd, D(fake), backward through D into g_vars, Adam."""
-        self.g_optim.zero_grad()
+        self.g_optim.zero_grad(overlap=self.dp is None)
         if self.dp is not None:
             self.dp.begin_update(self.g_optim)
         with ops.trainable(self.g_vars), ops.overlap_wgrad(), ops.stats_arena():
             G = self.generator(z, y)
             if self.dp is not None:
                 self.dp.wait_pending()      # the discriminator's update (exchange + Adam) may still be in flight
-            logits = self.discriminator(add_noise(G, self.noise_std), y, reuse=True)[1]
-            losses = sigmoid_cross_entropy_loss(logits, target=1.0)
+            segs = [(0, z.shape[0], 1.0, 1.0)]
+            logits = self.discriminator(add_noise(G, self.noise_std), y, reuse=True, ce_segments=segs)[1]
+            losses = sigmoid_cross_entropy_loss(logits, segs)
+            ops.join_side()
             torch.autograd.backward(losses, grad_tensors=self._ones(losses))
         if self.dp is not None:
             self.dp.allreduce(self.g_optim)

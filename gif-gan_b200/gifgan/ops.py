@@ -481,7 +481,7 @@ def reshape(x, shape):
     [B, 8192] projection viewed as [B, 4, 4, 512])."""
     y = x.reshape(shape)
     info = getattr(x, "_gg_bn", None)
-    if info is not None and y.shape[-1] == info.Cc:
+    if info is not None and y.shape[-1] % info.Cc == 0:      # channel = last index % Cc in both views (same memory)
         y._gg_bn = info
     return y
 
@@ -783,14 +783,33 @@ def bn_act(x, bn, *, act=None, act_param=0.2, out_dtype=None, train=True, groups
     return bn(x, train=train, act=act, act_param=act_param, out_dtype=out_dtype, groups=groups)
 
 
+TC_LINEAR = os.environ.get("GG_TC_LINEAR", "1") != "0"    # A/B switch: wide linears on the tcgen05 kernels (a linear is a one-tap conv)
+TC_LINEAR_MIN_ROWS = 64
+
+
+def _lin_geom(rows, in_dim, out_dim) -> _Geom:
+    """tf.matmul(x[rows, in], Matrix[in, out]) as the strided-conv relation with ONE tap on a 1x1x1 grid per row: the Matrix IS
+    the filter w[tap = 0][C = in][K = out], forward = `down`, input gradient = `up`, Matrix gradient = `wgrad`."""
+    return _Geom(rows, (1, 1, 1), in_dim, (1, 1, 1), out_dim, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+
+
+def _lin_tc(rows, in_dim, out_dim, *tensors) -> bool:
+    """Wide linears (recurrent_z's gvideo_1/2: 512 x 512 at clips x frames rows, z_model_lib.py:160-161) go to the tcgen05 pixel GEMM;
+    thin ones (in_dim 100/101, out_dim 1 / 100 / 400) have no 64-channel rows for a TMA box and stay on the SIMT kernels."""
+    return TC_LINEAR and rows >= TC_LINEAR_MIN_ROWS and _tc_ok(in_dim, out_dim, *tensors)
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, wvar, bvar, act, act_param, out_dtype):
         rows, in_dim = x.shape
         out_dim = w.shape[1]
-        y = torch.empty((rows, out_dim), dtype=out_dtype, device=x.device)
-        check(cabi.lib().gg_linear_fwd(ptr(x), dt(x), ptr(w), ptr(b), ptr(y), dt(y), rows, in_dim, out_dim, ACT[act], float(act_param),
-                                       stream()), "gg_linear_fwd")
+        if _lin_tc(rows, in_dim, out_dim, x):
+            y = _run_down(_lin_geom(rows, in_dim, out_dim), x.view(rows, 1, 1, in_dim), wvar, b, out_dtype, act, act_param, 4).view(rows, out_dim)
+        else:
+            y = torch.empty((rows, out_dim), dtype=out_dtype, device=x.device)
+            check(cabi.lib().gg_linear_fwd(ptr(x), dt(x), ptr(w), ptr(b), ptr(y), dt(y), rows, in_dim, out_dim, ACT[act], float(act_param),
+                                           stream()), "gg_linear_fwd")
         ctx.wvar, ctx.bvar, ctx.act, ctx.act_param = wvar, bvar, act, act_param
         ctx.save_for_backward(x, y if act else None)
         return y
@@ -804,27 +823,102 @@ class _Linear(torch.autograd.Function):
         out_dim = dpre.shape[1]
         L = cabi.lib()
         wg, bg = ctx.needs_input_grad[1], ctx.bvar is not None and ctx.needs_input_grad[2]
+        g = _lin_geom(rows, in_dim, out_dim)
+        if wg and _lin_tc(rows, in_dim, out_dim, x, dpre):
+            _run_wgrad(g, x.view(rows, 1, 1, in_dim), dpre.view(rows, 1, 1, out_dim), ctx.wvar)
+            wg = False
+            if bg:
+                _bias_grad(dpre, ctx.bvar)
+                bg = False
         if wg or bg:
             check(L.gg_linear_wgrad(ptr(x), dt(x), ptr(dpre), dt(dpre), ptr(ctx.wvar.grad) if wg else None,
                                     ptr(ctx.bvar.grad) if bg else None, rows, in_dim, out_dim, stream()), "gg_linear_wgrad")
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            check(L.gg_linear_dgrad(ptr(dpre), dt(dpre), ptr(ctx.wvar.data), ptr(dx), dt(dx), rows, in_dim, out_dim, stream()),
-                  "gg_linear_dgrad")
+            if x.dtype == torch.bfloat16 and _lin_tc(rows, in_dim, out_dim, dpre):
+                dx = _run_up(g, dpre.view(rows, 1, 1, out_dim), ctx.wvar, None, x.dtype, None, 0.0, 4).view(rows, in_dim)
+            else:
+                dx = torch.empty_like(x)
+                check(L.gg_linear_dgrad(ptr(dpre), dt(dpre), ptr(ctx.wvar.data), ptr(dx), dt(dx), rows, in_dim, out_dim, stream()),
+                      "gg_linear_dgrad")
         return dx, None, None, None, None, None, None, None
 
 
+ZERO_ON_SIDE = os.environ.get("GG_ZERO_ON_SIDE", "1") != "0"        # A/B switch: gradient zero-fill under the forward pass
+FUSE_LOSS_HEAD = os.environ.get("GG_FUSE_LOSS_HEAD", "1") != "0"    # A/B switch: d_h3_lin + cross-entropy means as two launches
+_LH_TICKET = {}
+
+
+class _LossHead(torch.autograd.Function):
+    """linear(h, 1) + sum_i weight_i * reduce_mean(sigmoid_cross_entropy_with_logits(logits[a_i:b_i], target_i)) as ONE node:
+    one forward launch (gg_loss_head_fwd: logits, loss parts, d loss / d logits) and one backward launch (gg_loss_head_bwd:
+    Matrix and bias gradients, dh, and the backward reductions of the batch norm that produced h).  Returns (parts, logits);
+    like _SigmoidCESum, `parts` must be the root of backward() (upstream gradient taken to be 1); logits carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, h, w, b, mvar, bvar, segs, in_bn):
+        L = cabi.lib()
+        rows, in_dim = h.shape
+        logits = torch.empty((rows, 1), dtype=torch.float32, device=h.device)
+        parts = torch.empty(len(segs) + 1, dtype=torch.float32, device=h.device)
+        need = any(ctx.needs_input_grad[:3])
+        dl = torch.empty(rows, dtype=torch.float32, device=h.device) if need else None
+        tk = _LH_TICKET.get(h.device)
+        if tk is None:          # zero-filled once; the kernel hands it back zeroed
+            tk = _LH_TICKET[h.device] = torch.zeros(4, dtype=torch.int32, device=h.device)
+        I, F = ctypes.c_int32 * len(segs), ctypes.c_float * len(segs)
+        check(L.gg_loss_head_fwd(ptr(h), dt(h), ptr(w), ptr(b), rows, in_dim, I(*[s[0] for s in segs]), I(*[s[1] for s in segs]),
+                                 F(*[s[2] for s in segs]), F(*[s[3] for s in segs]), len(segs), ptr(logits), ptr(parts), ptr(dl), ptr(tk),
+                                 stream()), "gg_loss_head_fwd")
+        ctx.mvar, ctx.bvar, ctx.in_bn, ctx.dl = mvar, bvar, in_bn, dl
+        ctx.save_for_backward(h)
+        ctx.mark_non_differentiable(logits)
+        return parts, logits
+
+    @staticmethod
+    def backward(ctx, g_parts, g_logits):
+        (h,) = ctx.saved_tensors
+        L = cabi.lib()
+        rows, in_dim = h.shape
+        wg, bg, xg = ctx.needs_input_grad[1], ctx.bvar is not None and ctx.needs_input_grad[2], ctx.needs_input_grad[0]
+        dh = torch.empty_like(h) if xg else None
+        bnb = ctx.in_bn
+        use_bn = (xg and FUSE_BN_BWD and bnb is not None and bnb.pre is not None and bnb.pre.numel() == h.numel()
+                  and bnb.pre.dtype == torch.float32 and in_dim % bnb.Cc == 0)
+        sums = _zeroed_f64(L.gg_bn_workspace_bytes(bnb.Cc, bnb.groups) // 8, h.device)[0] if use_bn else None
+        fused = ctypes.c_int32(0)
+        check(L.gg_loss_head_bwd(ptr(h), dt(h), ptr(ctx.dl), ptr(ctx.mvar.data), rows, in_dim, ptr(ctx.mvar.grad) if wg else None,
+                                 ptr(ctx.bvar.grad) if bg else None, ptr(dh), ptr(bnb.pre) if use_bn else None,
+                                 ptr(bnb.mean) if use_bn else None, ptr(bnb.rstd) if use_bn else None, ptr(bnb.gamma) if use_bn else None,
+                                 ptr(bnb.beta) if use_bn else None, ACT[bnb.act] if use_bn else 0, float(bnb.act_param) if use_bn else 0.0,
+                                 bnb.groups if use_bn else 1, bnb.Cc if use_bn else 0, ptr(sums), ctypes.byref(fused), stream()),
+              "gg_loss_head_bwd")
+        if use_bn and fused.value:
+            bnb.bwd_sums, bnb.bwd_dy, bnb.bwd_version = sums, dh, dh._version
+        return dh, None, None, None, None, None, None
+
+
 def linear(input_, output_size, scope=None, stddev=0.02, bias_start=0.0, with_w=False, *, act=None, act_param=0.2, out_dtype=None,
-           bn=None, bn_channels=None, train=True, groups=1):
+           bn=None, bn_channels=None, train=True, groups=1, ce_segments=None):
     """ops.py:106-117 -- tf.matmul(input_, Matrix) + bias; variables `scope/Matrix`, `scope/bias`.
     `bn=` fuses the batch norm (+activation) that follows; `bn_channels` is the channel count it normalises
-    when the reference reshapes the output to [-1, h, w, bn_channels] first (model.py:306-307)."""
+    when the reference reshapes the output to [-1, h, w, bn_channels] first (model.py:306-307).
+    `ce_segments=[(begin, end, target, weight), ...]` (output_size 1: the discriminator's last layer, model.py:277) also
+    evaluates the sigmoid cross-entropy means of model.py:121-131 over those row ranges in the same launch; the logits are
+    returned as usual and `sigmoid_cross_entropy_loss(logits, ce_segments)` hands the fused result over."""
     rows, in_dim = input_.shape
     with variable_scope(scope or "Linear") as st:
         mvar = st.get_variable("Matrix", [in_dim, output_size], random_normal_initializer(stddev))
         bvar = st.get_variable("bias", [output_size], constant_initializer(bias_start))
     od = out_dtype if out_dtype is not None else (torch.float32 if output_size <= 4 else act_dtype())
+    if (ce_segments is not None and FUSE_LOSS_HEAD and output_size == 1 and bn is None and act is None and od == torch.float32
+            and not _is_meta(input_) and cabi.lib().gg_loss_head_ok(rows, in_dim, len(ce_segments))):
+        _require_cuda(input_, "linear")
+        segs = tuple((int(a), int(b), float(t), float(w)) for a, b, t, w in ce_segments)
+        parts, y = _LossHead.apply(input_.contiguous(), _wtensor(mvar, _wants_grad(mvar)), _wtensor(bvar, _wants_grad(bvar)), mvar, bvar,
+                                   segs, getattr(input_, "_gg_bn", None))
+        y._gg_ce = (segs, parts)
+        return (y, mvar, bvar) if with_w else y
     if bn is not None:
         y = _fused_bn(input_, _LinearProducer(mvar, bvar, rows, output_size), bn, train, act, act_param, od, groups, bn_channels or output_size)
         return (y, mvar, bvar) if with_w else y
@@ -952,6 +1046,10 @@ class _LinearProducer:
 
     def fwd(self, x, b, stats=None, groups=1, Cc=None):
         rows, in_dim = x.shape
+        if _lin_tc(rows, in_dim, self.out_dim, x) and (stats is None or (Cc or self.out_dim) == self.out_dim):
+            # one-tap tcgen05 GEMM; the batch statistics (channel = column) come out of its epilogue like a conv's
+            return _run_down(_lin_geom(rows, in_dim, self.out_dim), x.view(rows, 1, 1, in_dim), self.wvar, b, torch.float32, None, 0.0, 4,
+                             stats=stats, groups=groups).view(rows, self.out_dim)
         y = torch.empty((rows, self.out_dim), dtype=torch.float32, device=x.device)
         if stats is not None:
             check(cabi.lib().gg_linear_fwd_stats(ptr(x), dt(x), ptr(self.wvar.data), ptr(b), ptr(y), rows, in_dim, self.out_dim,
@@ -963,12 +1061,19 @@ class _LinearProducer:
 
     def wgrad(self, x, dpre):
         rows, in_dim = x.shape
+        if _lin_tc(rows, in_dim, self.out_dim, x, dpre):
+            _run_wgrad(_lin_geom(rows, in_dim, self.out_dim), x.view(rows, 1, 1, in_dim), dpre.view(rows, 1, 1, self.out_dim), self.wvar)
+            return
         check(cabi.lib().gg_linear_wgrad(ptr(x), dt(x), ptr(dpre), dt(dpre), ptr(self.wvar.grad), None, rows, in_dim, self.out_dim,
                                          stream()), "gg_linear_wgrad")
 
     def dgrad(self, dpre, x_dtype, bnb=None):
         rows = dpre.shape[0]
         in_dim = self.wvar.data.shape[0]
+        if x_dtype == torch.bfloat16 and _lin_tc(rows, in_dim, self.out_dim, dpre):
+            # the launch also carries the backward reductions of the batch norm that produced x (bnb), like a conv's dgrad
+            return _run_up(_lin_geom(rows, in_dim, self.out_dim), dpre.view(rows, 1, 1, self.out_dim), self.wvar, None, x_dtype, None, 0.0, 4,
+                           bnb=bnb).view(rows, in_dim)
         dx = torch.empty((rows, in_dim), dtype=x_dtype, device=dpre.device)
         check(cabi.lib().gg_linear_dgrad(ptr(dpre), dt(dpre), ptr(self.wvar.data), ptr(dx), dt(dx), rows, in_dim, self.out_dim, stream()),
               "gg_linear_dgrad")
@@ -1217,6 +1322,9 @@ def sigmoid_cross_entropy_loss(logits, segments=None, target=None):
         return torch.empty(len(segments) + 1, dtype=torch.float32, device="meta")
     if logits.dtype != torch.float32:
         raise TypeError("logits must be float32")
+    ce = getattr(logits, "_gg_ce", None)
+    if ce is not None and ce[0] == tuple((int(a), int(b), float(t), float(w)) for a, b, t, w in segments):
+        return ce[1]            # linear(..., ce_segments=...) already evaluated exactly these means (gg_loss_head_fwd)
     return _SigmoidCESum.apply(logits, segments)
 
 
@@ -1286,8 +1394,19 @@ class AdamOptimizer:
             return rs[0][0], rs[-1][1]
         return self.store.ranges[self.group]
 
-    def zero_grad(self):
+    def zero_grad(self, overlap=False):
+        """Zero the group's gradient range.  overlap=True issues the fill on the side stream (GG_ZERO_ON_SIDE=0 disables), so
+        it runs under the update's forward pass -- one-wave launches that leave SMs and all of HBM idle -- instead of in front
+        of it; the caller must `join_side()` before the first gradient kernel (the filter gradients queue up behind the fill
+        on the side stream by themselves)."""
         b, e = self.range()
+        if overlap and ZERO_ON_SIDE and torch.cuda.is_available():
+            s = _side_stream()
+            s["stream"].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s["stream"]):
+                self.store.flat["grads"][b:e].zero_()
+            s["dirty"] = True
+            return
         self.store.flat["grads"][b:e].zero_()
 
     def lr_t(self, t):

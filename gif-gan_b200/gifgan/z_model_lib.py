@@ -162,11 +162,11 @@ class VID_DCGAN(object):
         layers.gr3 = linear(layers.gr2, self.z_output_size, 'gvideo_3', act='tanh', out_dtype=torch.float32)
         return layers.gr3, layers
 
-    def discriminator(self, vid, reuse=False, groups=1):
+    def discriminator(self, vid, reuse=False, groups=1, ce_segments=None):
         with self.store.absolute_scope(self.scope_prefix + 'video_discriminator/'):
-            return self._discriminator(vid, reuse, groups)
+            return self._discriminator(vid, reuse, groups, ce_segments)
 
-    def _discriminator(self, vid, reuse=False, groups=1):
+    def _discriminator(self, vid, reuse=False, groups=1, ce_segments=None):
         """z_model_lib.py:384-418 (batch norm always in train mode).  `groups=2`: real and fake clips as one batch."""
         layers = Layers()
         nclips = vid.shape[0] // self.vid_length
@@ -175,7 +175,7 @@ class VID_DCGAN(object):
         layers.dr1 = conv3d(layers.dr0, 256, name='dvideo_h1', act='lrelu')
         layers.dr2 = conv3d(layers.dr1, 256, name='dvideo_h2', bn=self.d_bn2, act='lrelu', groups=groups)
         layers.dr3 = conv3d(layers.dr2, 256, name='dvideo_h3', bn=self.d_bn3, act='lrelu', groups=groups)
-        layers.d4 = linear(layers.dr3.reshape(nclips, -1), 1, 'dvideo_h4')
+        layers.d4 = linear(ops.reshape(layers.dr3, (nclips, -1)), 1, 'dvideo_h4', ce_segments=ce_segments)   # (see DCGAN._discriminator)
         return None, layers.d4, layers
 
     # ------------------------------------------------------------------------------
@@ -215,8 +215,9 @@ class VID_DCGAN(object):
                 img.generator(G_out, train=False, out=both[n:])                  # img_dcgan.sampler(G_out)
             act = img.discriminator(add_noise(both, self.image_noise_std), reuse=True, train=False, stop_at_h2=True)[2]   # D_activations_inf(_)
             act = add_noise(act, self.activation_noise_std)
-            logits = self.discriminator(act, reuse=True, groups=2)[1]
-            losses = sigmoid_cross_entropy_loss(logits, [(0, Bv, 1.0, 1.0), (Bv, 2 * Bv, 0.0, 1.0)])
+            segs = [(0, Bv, 1.0, 1.0), (Bv, 2 * Bv, 0.0, 1.0)]
+            logits = self.discriminator(act, reuse=True, groups=2, ce_segments=segs)[1]
+            losses = sigmoid_cross_entropy_loss(logits, segs)
             torch.autograd.backward(losses, grad_tensors=self._ones(losses))
         if self.dp is not None and apply:
             # remaining bucket + Adam on the communication stream: the next update's generator / image-GAN forward overlaps them
@@ -246,8 +247,9 @@ class VID_DCGAN(object):
             act = img.discriminator(add_noise(frames, self.image_noise_std), reuse=True, train=False, stop_at_h2=True)[2]
             if self.dp is not None:
                 self.dp.wait_pending()      # the video discriminator's update (exchange + Adam) may still be in flight
-            logits = self.discriminator(add_noise(act, self.activation_noise_std), reuse=True)[1]
-            losses = sigmoid_cross_entropy_loss(logits, target=1.0)
+            segs = [(0, act.shape[0] // self.vid_length, 1.0, 1.0)]
+            logits = self.discriminator(add_noise(act, self.activation_noise_std), reuse=True, ce_segments=segs)[1]
+            losses = sigmoid_cross_entropy_loss(logits, segs)
             roots, grads = [losses], [self._ones(losses)]
             first = None
             if self.first_frame_loss_scalar:

@@ -224,6 +224,26 @@ int gg_get_std(const void* x, int32_t x_dtype, int64_t B, int64_t F, float* out,
  * (dlogits may be NULL for forward-only).  accumulate!=0 adds into loss_out.             */
 int gg_sigmoid_ce(const float* logits, int64_t n, float target, float weight, float* loss_out, int32_t accumulate,
                   float* dlogits, void* stream);
+/* Discriminator loss head as two launches (model.py:277 `linear(reshape(h3,[B,-1]), 1, 'd_h3_lin')` + model.py:121-131 the
+ * cross-entropy means; z_model_lib.py:416 dvideo_h4 likewise).
+ * fwd: logits[r] = h[r,:].w + bias[0];  parts[1+i] = weight_i * mean_{seg_begin_i <= r < seg_end_i} CE(logits[r], target_i),
+ *      parts[0] = sum_i parts[1+i];  dlogits[r] = weight_i (sigmoid(logits[r]) - target_i) / n_i   (dlogits may be NULL).
+ *      The segment arrays are HOST arrays (read at call time), 1..4 segments.  ticket: 4 bytes of device memory zero-filled
+ *      ONCE by the caller (the kernel hands it back zeroed).  Same numbers as gg_linear_fwd + gg_sigmoid_ce.
+ * bwd: dW[k] += sum_r dlogits[r] h[r,k];  dbias[0] += sum_r dlogits[r];  dh[r,k] = dlogits[r] w[k]  (dh in h's dtype; dW /
+ *      dbias / dh may be NULL).  When h is the output of a train-mode batch norm over channel = column % C (pre, save_mean,
+ *      save_rstd, sums non-NULL; in_dim % C == 0, rows % groups == 0) the launch also accumulates that batch norm's backward
+ *      reductions (sum g, sum g*xhat; g = dh * act'(gamma*xhat + beta)) into sums[groups][2][C] (zeroed by the caller) and sets
+ *      *fused = 1, so gg_bn_bwd(train = 3) can skip its reduction pass -- as gg_conv_dgrad_bnbwd does for conv layers.
+ * Needs in_dim % 64 == 0 (gg_loss_head_ok); otherwise GG_ERR_UNSUPPORTED and the caller composes the separate calls. */
+int gg_loss_head_ok(int32_t rows, int32_t in_dim, int32_t nsegs);
+int gg_loss_head_fwd(const void* h, int32_t h_dtype, const float* w, const float* bias, int32_t rows, int32_t in_dim,
+                     const int32_t* seg_begin, const int32_t* seg_end, const float* seg_target, const float* seg_weight, int32_t nsegs,
+                     float* logits, float* parts, float* dlogits, void* ticket, void* stream);
+int gg_loss_head_bwd(const void* h, int32_t h_dtype, const float* dlogits, const float* w, int32_t rows, int32_t in_dim, float* dW,
+                     float* dbias, void* dh, const float* pre, const float* save_mean, const float* save_rstd, const float* gamma,
+                     const float* beta, int32_t act, float act_param, int32_t groups, int32_t C, double* sums, int32_t* fused,
+                     void* stream);
 /* z_model_lib.py:109-111: loss (+)= scalar*mean((a-b)^2); da = scalar*2(a-b)/n  (a strided rows) */
 int gg_mse(const float* a, int64_t a_row_stride, const float* b, int64_t b_row_stride, int64_t rows, int64_t cols,
            float scalar, float* loss_out, int32_t accumulate, float* da, void* stream);

@@ -376,3 +376,73 @@ def test_linear_bn_act_one_kernel_per_direction(precision, rows, i, o, C, monkey
         assert (relerr(r_["g"]["l/Matrix"], gM) < tol) if precision == "fp32" else (l2(r_["g"]["l/Matrix"], gM) < tol)
         assert relerr(r_["g"]["bn/gamma"], gg) < tol and relerr(r_["g"]["bn/beta"], gb) < tol
         assert float(r_["g"]["l/bias"].abs().max()) == 0.0          # exactly zero through a train-mode batch norm: left untouched
+
+
+# discriminator loss head (model.py:277 d_h3_lin + model.py:121-131 the cross-entropy means) as two launches, with the backward
+# reductions of the batch norm that feeds it (d_bn3: channel = column % 512, one set per real / fake half)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,hw,C,groups", [(64, 4, 512, 2), (64, 4, 512, 1), (6, 2, 64, 2), (5, 1, 64, 1)])
+def test_loss_head_fused(precision, B, hw, C, groups):
+    from gifgan import ops as _o
+    rows = B * groups
+    rs = np.random.RandomState(B + C)
+    xin = rs.randn(rows, hw, hw, 64).astype(np.float32)
+    wc, wl = (rs.randn(1, 1, 64, C) * 0.1).astype(np.float32), (rs.randn(hw * hw * C, 1) * 0.05).astype(np.float32)
+    ga, be = rs.uniform(0.5, 1.5, C).astype(np.float32), (rs.randn(C) * 0.1).astype(np.float32)
+    segs = [(0, B, 1.0, 1.0), (B, 2 * B, 0.0, 1.0)] if groups == 2 else [(0, rows, 1.0, 0.7)]
+
+    def run(fused):
+        _o.FUSE_LOSS_HEAD = fused
+        try:
+            bnv = _o.batch_norm(name="d_bn3")
+
+            def build(t):
+                h = _o.conv2d(t, C, 1, 1, 1, 1, name="c", bn=bnv, act="lrelu", groups=groups)
+                return _o.linear(_o.reshape(h, (rows, -1)), 1, "d_h3_lin")
+            ops, st, tv = _setup(precision, build, [(rows, hw, hw, 64)])
+            st.load_state_dict({"c/w": wc, "d_h3_lin/Matrix": wl, "d_h3_lin/bias": np.array([0.3], np.float32), "d_bn3/gamma": ga,
+                                "d_bn3/beta": be}, strict=False)
+            x = _cuda(xin, precision)
+            L = ops.cabi.lib()
+            with ops.trainable(tv), ops.stats_arena():
+                h = _o.conv2d(x, C, 1, 1, 1, 1, name="c", bn=bnv, act="lrelu", groups=groups)
+                n0 = L.gg_launch_count()
+                logits = _o.linear(_o.reshape(h, (rows, -1)), 1, "d_h3_lin", ce_segments=segs)
+                losses = _o.sigmoid_cross_entropy_loss(logits, segs)
+                n_fwd = L.gg_launch_count() - n0
+                torch.autograd.backward(losses, grad_tensors=torch.ones_like(losses))
+            ops.join_side()
+            torch.cuda.synchronize()
+            n_bwd = L.gg_launch_count() - n0 - n_fwd
+            g = {k: st.vars[k].grad.clone().cpu() for k in ("c/w", "d_h3_lin/Matrix", "d_h3_lin/bias", "d_bn3/gamma", "d_bn3/beta")}
+            return logits.detach().cpu(), losses.detach().cpu(), x.grad.float().cpu(), g, (n_fwd, n_bwd)
+        finally:
+            _o.FUSE_LOSS_HEAD = True
+
+    lf, pf, gxf, gf, nf = run(True)
+    lc, pc, gxc, gc, nc = run(False)
+    assert nf[0] == 1 and nc[0] == 1 + 2 * len(segs)    # one launch instead of linear + (cross-entropy, sum) per segment
+    assert nf[1] == nc[1] - 3                           # Matrix gradient + bias gradient + dh + d_bn3's reduction pass -> one launch
+    assert torch.equal(lf, lc) and torch.equal(pf, pc)  # same formula, same summation order: bit-identical logits and losses
+    tol = TOL[precision]
+    for k in gf:
+        assert relerr(gf[k], gc[k]) < tol, k
+    assert relerr(gxf, gxc) < tol
+    # and against the float64 oracle (fp32 mode: no quantisation points to mirror)
+    if precision == "fp32":
+        xr = torch.tensor(xin).double().requires_grad_(True)
+        wr, lr_ = torch.tensor(wc).double().requires_grad_(True), torch.tensor(wl).double().requires_grad_(True)
+        gr, br = torch.tensor(ga).double().requires_grad_(True), torch.tensor(be).double().requires_grad_(True)
+        pre = T.conv2d(xr, wr, None, 1, 1)
+        rpg = rows // groups
+        hs = []
+        for g_ in range(groups):
+            p_ = pre[g_ * rpg:(g_ + 1) * rpg]
+            m_, v_ = p_.mean((0, 1, 2)), p_.var((0, 1, 2), unbiased=False)
+            hs.append(T.lrelu((p_ - m_) / torch.sqrt(v_ + 1e-5) * gr + br))
+        lg = T.linear(torch.cat(hs, 0).reshape(rows, -1), lr_, torch.tensor([0.3]).double())
+        tot = sum(w_ * T.sigmoid_cross_entropy_with_logits(lg[a:b], torch.full_like(lg[a:b], t_)).mean() for a, b, t_, w_ in segs)
+        gx, gw, gl, gg_, gb_ = torch.autograd.grad(tot, [xr, wr, lr_, gr, br])
+        assert abs(pf[0].item() - tot.item()) < 1e-5 * max(1.0, abs(tot.item()))
+        assert relerr(gxf, gx) < 1e-4 and relerr(gf["c/w"], gw) < 1e-4 and relerr(gf["d_h3_lin/Matrix"], gl) < 1e-4
+        assert relerr(gf["d_bn3/gamma"], gg_) < 1e-4 and relerr(gf["d_bn3/beta"], gb_) < 1e-4

@@ -409,3 +409,74 @@ def test_bn_backward_reductions_fused_into_dgrad(kind, B, H, C0, C1, C2, groups,
     assert l2(one["dx"], gx) < 2e-2
     for k, want in (("a/w", gwa), ("b/w", gwb), ("bn/gamma", gga), ("bn/beta", gbe)):
         assert l2(one["grads"][k], want) < 2e-2, k
+
+
+# wide linears (z_model_lib.py:160-161 gvideo_1 / gvideo_2: [clips*frames, 512] x [512, 512]) run as ONE-TAP tcgen05 GEMMs
+@pytest.mark.parametrize("rows,ind,outd,act", [(512, 512, 512, "relu"), (200, 128, 192, None), (64, 64, 64, "lrelu")])
+def test_tc_linear(rows, ind, outd, act):
+    rs = np.random.RandomState(rows + ind)
+    x, w, b = bf16_round(rs.randn(rows, ind)), bf16_round(rs.randn(ind, outd) * 0.05), torch.tensor(rs.randn(outd) * 0.1, dtype=torch.float32)
+    from gifgan import ops as _o
+    ops, st, tv = _store(lambda t: _o.linear(t, outd, "l", act=act), (rows, ind))
+    st.load_state_dict({"l/Matrix": w.numpy(), "l/bias": b.numpy()})
+    xt = x.cuda().to(torch.bfloat16).requires_grad_(True)
+    assert ops._lin_tc(rows, ind, outd, xt)
+    dy = bf16_round(rs.randn(rows, outd))
+    L = __import__("gifgan._cabi", fromlist=["lib"]).lib()
+    n0 = L.gg_launch_count()
+    with ops.trainable(tv):
+        y = ops.linear(xt, outd, "l", act=act)
+        y.backward(dy.cuda().to(torch.bfloat16))
+    ops.join_side()
+    torch.cuda.synchronize()
+    assert L.gg_launch_count() - n0 <= 6        # (bf16 cast of the Matrix,) fwd, (act'), bias grad, wgrad, dgrad: one tcgen05 launch each
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = T.linear(xr, wr, br)
+    if act == "relu":
+        yr = torch.relu(yr)
+    elif act == "lrelu":
+        yr = T.lrelu(yr)
+    gx, gw, gb = torch.autograd.grad(yr, [xr, wr, br], dy.double())
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (rows, outd)
+    assert relerr(y, yr) < TOL
+    assert relerr(xt.grad, gx) < TOL
+    assert relerr(st.vars["l/Matrix"].grad, gw) < TOL
+    assert relerr(st.vars["l/bias"].grad, gb) < TOL
+
+
+def test_tc_linear_bn_chain_matches_simt_route():
+    """Two 512-wide linear + batch norm + ReLU layers (gvideo_1 -> gvideo_2): the tcgen05 route -- statistics from the GEMM epilogue,
+    g_bn1's backward reductions from gvideo_2's input-gradient launch -- against the SIMT route on the same bf16 inputs."""
+    import gifgan.ops as _o
+    rs = np.random.RandomState(11)
+    rows = 512
+    x = bf16_round(rs.randn(rows, 512))
+    dy = bf16_round(rs.randn(rows, 512))
+    res = {}
+    for tc in (True, False):
+        _o.TC_LINEAR = tc
+        try:
+            def build(t):
+                h = _o.linear(t, 512, "gvideo_1", bn=_o.batch_norm(name="g_bn1"), act="relu")
+                return _o.linear(h, 512, "gvideo_2", bn=_o.batch_norm(name="g_bn2"), act="relu")
+            ops, st, tv = _store(build, (rows, 512))
+            st.load_state_dict({"gvideo_1/Matrix": bf16_round(np.random.RandomState(1).randn(512, 512) * 0.05).numpy(),
+                                "gvideo_2/Matrix": bf16_round(np.random.RandomState(2).randn(512, 512) * 0.05).numpy()}, strict=False)
+            xt = x.cuda().to(torch.bfloat16).requires_grad_(True)
+            bn1, bn2 = _o.batch_norm(name="g_bn1"), _o.batch_norm(name="g_bn2")
+            with ops.trainable(tv):
+                h = _o.linear(xt, 512, "gvideo_1", bn=bn1, act="relu")
+                y = _o.linear(h, 512, "gvideo_2", bn=bn2, act="relu")
+                y.backward(dy.cuda().to(torch.bfloat16))
+            ops.join_side()
+            torch.cuda.synchronize()
+            res[tc] = dict(y=y.float().cpu(), gx=xt.grad.float().cpu(), g1=st.vars["gvideo_1/Matrix"].grad.clone().cpu(),
+                           g2=st.vars["gvideo_2/Matrix"].grad.clone().cpu(), gg=st.vars["g_bn1/gamma"].grad.clone().cpu(),
+                           gb=st.vars["g_bn1/beta"].grad.clone().cpu())
+        finally:
+            _o.TC_LINEAR = True
+    for k in res[True]:
+        a, b = res[True][k].double(), res[False][k].double()
+        err = ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+        assert err < TOL, (k, err)
