@@ -62,7 +62,7 @@ int c3m_conv_down(const gg_conv_desc*, const float*, const float*, const float*,
                   const float* mean = nullptr, const float* rstd = nullptr, const float* gamma = nullptr, const float* beta = nullptr,
                   double* sums = nullptr, int bact = 0, float bact_param = 0.f, int* fused = nullptr);
 int c3m_conv_up(const gg_conv_desc*, const void*, const float*, const float*, float*, cudaStream_t);
-int c3m_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t);
+int c3m_conv_wgrad(const gg_conv_desc*, const float*, const void*, float*, cudaStream_t, float* dbias = nullptr);
 static inline bool c3m_applicable(const gg_conv_desc* d) { return c3_applicable(d) && d->small_dtype == GG_BF16; }
 // tc_tapgemm.cu
 }  // namespace gg
@@ -155,6 +155,17 @@ extern "C" int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const voi
   if (c3m_applicable(d)) GG_REPEAT(c3m_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream));
   if (c3_applicable(d)) GG_REPEAT(c3_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream));
   GG_REPEAT(simt_conv_wgrad(d, large, small, dw, (cudaStream_t)stream));
+}
+
+// filter gradient + bias gradient (dbias[k] += sum over the small grid of small[., k]) of a `down` conv.  The image-side warp-MMA
+// kernel produces both in one launch (the bias gradient rides in an unused row of its GEMM); otherwise two launches.
+extern "C" int gg_conv_wgrad_bias(const gg_conv_desc* d, const void* large, const void* small, float* dw, float* dbias, void* stream) {
+  GG_REQUIRE(d && large && dw && small && dbias, GG_ERR_INVALID, "conv_wgrad_bias: null pointer");
+  if (!(d->flags & GG_CONV_TENSOR_CORE) && c3m_applicable(d) && g_cabi_repeat == 1)
+    return c3m_conv_wgrad(d, (const float*)large, small, dw, (cudaStream_t)stream, dbias);
+  int rc = gg_conv_wgrad(d, large, small, dw, stream);
+  if (rc) return rc;
+  return gg_bias_grad(small, d->small_dtype, dbias, (int64_t)d->N * d->Do * d->Ho * d->Wo, d->K, stream);
 }
 
 // conv + batch statistics of its (pre-norm) output: stats[groups][2][channels] += (sum, sum of squares) per row group.

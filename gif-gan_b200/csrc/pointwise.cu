@@ -181,11 +181,25 @@ __global__ void adam_tick_kernel(int* __restrict__ state, float lr, float b1, fl
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
   reinterpret_cast<float*>(state)[1] = (float)lr_t;
 }
+// TICK: the launch advances the step counter itself (no adam_tick launch in front of it): lane 0 of every warp evaluates lr_t
+// for step t = state[0] + 1 -- after the warp's first loads are in flight -- and the block that takes the last ticket
+// (state[2]) publishes t and lr_t; nobody reads state[0] after that point (every block read it before taking its ticket).
+template <bool TICK>
 __global__ void __launch_bounds__(PW_THREADS)
 adam_dev_kernel(float* __restrict__ p, bf16* __restrict__ pb, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                int64_t n, const int* __restrict__ state, float b1, float b2, float eps, float gs) {
+                int64_t n, int* state, float lr, float b1, float b2, float eps, float gs) {
   pdl_grid_sync();
-  const float lr_t = reinterpret_cast<const float*>(state)[1];
+  float lr_t;
+  int t_new = 0;
+  if (TICK) {
+    if ((threadIdx.x & 31) == 0) {
+      t_new = *reinterpret_cast<volatile int*>(state) + 1;
+      lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t_new)) / (1.0 - pow((double)b1, (double)t_new)));
+    }
+    lr_t = __shfl_sync(0xffffffffu, lr_t, 0);
+  } else {
+    lr_t = reinterpret_cast<const float*>(state)[1];
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -211,6 +225,17 @@ adam_dev_kernel(float* __restrict__ p, bf16* __restrict__ pb, const float* __res
     const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
     p[i] = pi;
     if (pb != nullptr) pb[i] = __float2bfloat16_rn(pi);
+  }
+  if (TICK) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(reinterpret_cast<unsigned int*>(state) + 2, 1u) == gridDim.x - 1) {
+        state[0] = t_new;
+        reinterpret_cast<float*>(state)[1] = lr_t;
+        state[2] = 0;
+      }
+    }
   }
 }
 
@@ -345,6 +370,59 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __
 
 using namespace gg;
 
+namespace gg {
+// dx = dy * act'(y) and, from the same pass, the bias gradient of the layer that produced y: dbias[c] += sum_rows dx[row, c] for a
+// channel-last fp32 tensor with C <= 4 channels (g_h4: tanh' of the generated image + the 3-channel bias gradient, model.py:321-324).
+// A thread owns 4 consecutive elements per trip (channel of element e = e % C); block partials -> one atomic per channel per block.
+__global__ void __launch_bounds__(PW_THREADS)
+act_bwd_bias_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, int64_t n, int C, int act, float ap,
+                    float* __restrict__ dbias) {
+  pdl_grid_sync();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
+    const float4 a = ld4(y + i * 4), g = ld4(dy + i * 4);
+    float gv[4] = {g.x, g.y, g.z, g.w};
+    const float yv[4] = {a.x, a.y, a.z, a.w};
+    act_bwd_out_vec<4>(gv, yv, act, ap);
+    st4(dx + i * 4, make_float4(gv[0], gv[1], gv[2], gv[3]));
+    int c = (int)((i * 4) % C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += (q == c) ? gv[k] : 0.f;
+      c = (c + 1 == C) ? 0 : c + 1;
+    }
+  }
+  __shared__ float red[4][PW_THREADS / 32];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float v = warp_sum(acc[q]);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < C) {
+    float v = 0.f;
+    for (int w = 0; w < PW_THREADS / 32; ++w) v += red[threadIdx.x][w];
+    atomicAdd(dbias + threadIdx.x, v);
+  }
+}
+}  // namespace gg
+
+extern "C" int gg_act_bwd_bias(const void* y, int32_t y_dt, const void* dy, int32_t dy_dt, void* dx, int32_t dx_dt, int64_t rows, int32_t C,
+                               int32_t act, float ap, float* dbias, void* stream) {
+  GG_REQUIRE(y && dy && dx && dbias && rows > 0 && C > 0, GG_ERR_INVALID, "act_bwd_bias: bad argument");
+  const int64_t n = rows * C;
+  if (y_dt == GG_F32 && dy_dt == GG_F32 && dx_dt == GG_F32 && C <= 4 && n % 4 == 0 && al16(y) && al16(dy) && al16(dx)) {
+    Launch(pw_blocks(n / 4), PW_THREADS, 0, (cudaStream_t)stream)(act_bwd_bias_kernel, (const float*)y, (const float*)dy, (float*)dx, n, (int)C,
+                                                                  (int)act, ap, dbias);
+    return check_launch("act_bwd_bias");
+  }
+  int rc = gg_act_bwd(y, y_dt, dy, dy_dt, dx, dx_dt, n, act, ap, stream);       // any other case: the two separate launches
+  if (rc) return rc;
+  return gg_bias_grad(dx, dx_dt, dbias, rows, C, stream);
+}
+
 extern "C" int gg_act_bwd(const void* y, int32_t y_dt, const void* dy, int32_t dy_dt, void* dx, int32_t dx_dt, int64_t n, int32_t act,
                           float ap, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -463,10 +541,15 @@ extern "C" int gg_adam_graph(float* p, void* p_bf16, const float* g, float* m, f
                              float eps, float gs, void* stream) {
   GG_REQUIRE(p && g && m && v && state && n > 0, GG_ERR_INVALID, "adam_graph: bad argument");
   GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v) && ((uintptr_t)p_bf16 % 8) == 0, GG_ERR_INVALID, "adam_graph: buffers must be 16-byte aligned (bf16 shadow: 8)");
-  Launch(1, 1, 0, (cudaStream_t)stream)(adam_tick_kernel, state, lr, b1, b2);
-  int rc = check_launch("adam_tick");
-  if (rc) return rc;
-  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel, p, (bf16*)p_bf16, g, m, v, n, state, b1, b2, eps, gs);
+  static const bool separate_tick = getenv("GG_ADAM_TICK") && getenv("GG_ADAM_TICK")[0] == '1';     // A/B: the two-launch form
+  if (separate_tick) {
+    Launch(1, 1, 0, (cudaStream_t)stream)(adam_tick_kernel, state, lr, b1, b2);
+    int rc = check_launch("adam_tick");
+    if (rc) return rc;
+    Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel<false>, p, (bf16*)p_bf16, g, m, v, n, (int*)state, lr, b1, b2, eps, gs);
+  } else {
+    Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel<true>, p, (bf16*)p_bf16, g, m, v, n, (int*)state, lr, b1, b2, eps, gs);
+  }
   return check_launch("adam_dev");
 }
 

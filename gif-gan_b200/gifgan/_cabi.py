@@ -48,6 +48,7 @@ SIGNATURES = {
     "gg_conv_down": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv_up": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv_wgrad": (C.c_int, [_dp, _vp, _vp, _vp, _vp]),
+    "gg_conv_wgrad_bias": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp]),
     "gg_conv_down_stats": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gg_conv_up_stats": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gg_conv_dgrad_bnbwd": (C.c_int, [_dp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _vp, C.POINTER(C.c_int32), _vp]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "gg_bn_infer_stats": (C.c_int, [_vp, _vp, _f32, _i32, _vp, _vp, _vp]),
     "gg_act_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i64, _i32, _f32, _vp]),
     "gg_act_fwd": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _f32, _vp]),
+    "gg_act_bwd_bias": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _i64, _i32, _i32, _f32, _vp, _vp]),
     "gg_bias_grad": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp]),
     "gg_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "gg_axpby": (C.c_int, [_vp, _f32, _vp, _f32, _i64, _vp]),

@@ -63,7 +63,7 @@ class LatentSearch(object):
         # Adam slots of the optimiser built once for the whole run (z_space_finder.py:294-298): they, like z, carry over
         # from one target to the next
         self.m, self.v, self.t = torch.zeros_like(self.z), torch.zeros_like(self.z), 0
-        self.state = torch.zeros(2, dtype=torch.int32, device=dev)      # [t, lr_t bits] on the device (gg_adam_graph)
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)      # [t, lr_t bits, ticket, -] on the device (gg_adam_graph)
         self.use_graph, self._graphs, self._bufs = use_graph, {}, {}
         self._ones = torch.ones(1, dtype=torch.float32, device=dev)
         self._loss_vec = torch.zeros(8, dtype=torch.float32, device=dev)

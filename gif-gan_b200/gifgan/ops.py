@@ -605,11 +605,16 @@ def join_side():
         s["dirty"] = False
 
 
-def _run_wgrad(g: _Geom, large, small, wvar: Var):
+def _run_wgrad(g: _Geom, large, small, wvar: Var, bvar: Var = None):
+    """bvar: also produce the bias gradient of a `down` conv (sum of `small` over its grid) -- one launch on the image-side layer."""
     tc = _tc_ok(g.C, g.K, large, small)
     d = g.desc(dt(large), dt(small), None, 0.0, tc)
     with _on_side(large, small):
-        check(cabi.lib().gg_conv_wgrad(ctypes.byref(d), ptr(large), ptr(small), ptr(wvar.grad), stream()), "gg_conv_wgrad")
+        if bvar is not None:
+            check(cabi.lib().gg_conv_wgrad_bias(ctypes.byref(d), ptr(large), ptr(small), ptr(wvar.grad), ptr(bvar.grad), stream()),
+                  "gg_conv_wgrad_bias")
+        else:
+            check(cabi.lib().gg_conv_wgrad(ctypes.byref(d), ptr(large), ptr(small), ptr(wvar.grad), stream()), "gg_conv_wgrad")
     if GRAD_READY_HOOK is not None:
         GRAD_READY_HOOK(wvar, _side_stream()["stream"] if OVERLAP_WGRAD else None)
 
@@ -648,13 +653,25 @@ class _ConvRel(torch.autograd.Function):
     def backward(ctx, dy):
         x, y = ctx.saved_tensors
         dy = dy.contiguous()
-        dpre = _act_bwd(y, dy, ctx.act, ctx.act_param) if ctx.act else dy
         g = ctx.geom
-        if ctx.bvar is not None and ctx.needs_input_grad[2]:
+        need_b = ctx.bvar is not None and ctx.needs_input_grad[2]
+        if (FUSE_ACT_BIAS and ctx.act and need_b and y.shape[-1] <= 4 and y.dtype == torch.float32 and dy.dtype == torch.float32):
+            # image-side deconv (g_h4 + tanh): activation' and the 3-channel bias gradient in one pass over the image gradient
+            dpre = torch.empty_like(y)
+            Cc = y.shape[-1]
+            check(cabi.lib().gg_act_bwd_bias(ptr(y), dt(y), ptr(dy), dt(dy), ptr(dpre), dt(dpre), y.numel() // Cc, Cc, ACT[ctx.act],
+                                             float(ctx.act_param), ptr(ctx.bvar.grad), stream()), "gg_act_bwd_bias")
+            need_b = False
+        else:
+            dpre = _act_bwd(y, dy, ctx.act, ctx.act_param) if ctx.act else dy
+        # image-side conv (d_h0_conv) in bf16 mode: the filter-gradient launch carries the bias gradient
+        wb = (FUSE_WGRAD_BIAS and need_b and ctx.needs_input_grad[1] and ctx.direction == "down" and g.C == 3 and _PRECISION == "bf16"
+              and dpre.dtype == torch.bfloat16 and x.dtype == torch.float32)
+        if need_b and not wb:
             _bias_grad(dpre, ctx.bvar)
         if ctx.needs_input_grad[1]:
             if ctx.direction == "down":
-                _run_wgrad(g, x, dpre, ctx.wvar)
+                _run_wgrad(g, x, dpre, ctx.wvar, ctx.bvar if wb else None)
             else:
                 _run_wgrad(g, dpre, x, ctx.wvar)
         dx = None
@@ -844,6 +861,8 @@ class _Linear(torch.autograd.Function):
         return dx, None, None, None, None, None, None, None
 
 
+FUSE_ACT_BIAS = os.environ.get("GG_FUSE_ACT_BIAS", "1") != "0"      # A/B switch: g_h4's tanh' + bias gradient as one launch
+FUSE_WGRAD_BIAS = os.environ.get("GG_FUSE_WGRAD_BIAS", "1") != "0"  # A/B switch: d_h0_conv's bias gradient inside its filter-gradient launch
 ZERO_ON_SIDE = os.environ.get("GG_ZERO_ON_SIDE", "1") != "0"        # A/B switch: gradient zero-fill under the forward pass
 FUSE_LOSS_HEAD = os.environ.get("GG_FUSE_LOSS_HEAD", "1") != "0"    # A/B switch: d_h3_lin + cross-entropy means as two launches
 _LH_TICKET = {}
@@ -1381,7 +1400,7 @@ class AdamOptimizer:
         self.lr, self.b1, self.b2, self.eps = learning_rate, beta1, beta2, epsilon
         self.t = 0
         self.var_list = None
-        self.state = torch.zeros(2, dtype=torch.int32, device=store.device)   # [t, lr_t bits] (device-side, graph-safe)
+        self.state = torch.zeros(4, dtype=torch.int32, device=store.device)   # [t, lr_t bits, ticket, -] (device-side, graph-safe)
 
     def range(self):
         """Element range of this optimiser's var_list in the flat buffers.  `group` may be a tuple of

@@ -103,6 +103,10 @@ int gg_conv_up(const gg_conv_desc* d, const void* small, const void* w, const fl
  * replaces the filter-gradient of tf.nn.conv2d / conv3d / conv2d_transpose.             */
 int gg_conv_wgrad(const gg_conv_desc* d, const void* large, const void* small, float* dw,
                   void* stream);
+/* the same plus the bias gradient of a `down` conv (ops.py:59 bias_add), dbias[k] += sum_o small[o,k]: one launch on the
+ * image-side layer (d_h0_conv, model.py:273), where it rides in an unused row of the filter-gradient GEMM.              */
+int gg_conv_wgrad_bias(const gg_conv_desc* d, const void* large, const void* small, float* dw, float* dbias,
+                       void* stream);
 
 /* conv + batch statistics of its pre-norm output in one call (what `batch_norm(conv2d(...))` needs, ops.py:10-24 after
  * ops.py:57/86): stats (gg_bn_workspace_bytes(channels, groups) bytes of fp64, [replicas][groups][2][channels], zero-initialised by the caller) += per-channel (sum, sum of squares)
@@ -208,6 +212,10 @@ int gg_bn_infer_stats(const float* moving_mean, const float* moving_var, float e
 int gg_act_bwd(const void* y, int32_t y_dtype, const void* dy, int32_t dy_dtype, void* dx, int32_t dx_dtype,
                int64_t n, int32_t act, float act_param, void* stream);
 int gg_act_fwd(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, int32_t act, float act_param, void* stream);
+/* gg_act_bwd over a channel-last [rows, C] tensor + gg_bias_grad of the result (db[c] += sum_rows dx[r,c]) -- one launch for fp32
+ * tensors with C <= 4 (g_h4: tanh' of the generated image and the 3-channel bias gradient, model.py:321-324), else the two calls */
+int gg_act_bwd_bias(const void* y, int32_t y_dtype, const void* dy, int32_t dy_dtype, void* dx, int32_t dx_dtype, int64_t rows,
+                    int32_t C, int32_t act, float act_param, float* db, void* stream);
 /* db[c] += sum_rows dy[r,c]   (gradient of tf.nn.bias_add, ops.py:60,95) */
 int gg_bias_grad(const void* dy, int32_t dy_dtype, float* db, int64_t rows, int32_t C, void* stream);
 int gg_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
@@ -266,8 +274,9 @@ int gg_distance_loss(const void* a, int32_t a_dtype, const float* target, int64_
 int gg_adam(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
             float grad_scale, void* stream);
 
-/* CUDA-graph-friendly variant: the step counter lives on the device.  state[0] = t (int32, advanced
- * by this call), state[1] = lr_t (float bits) = lr*sqrt(1-b2^t)/(1-b1^t) recomputed on the device.    */
+/* CUDA-graph-friendly variant: the step counter lives on the device.  state = FOUR int32 (16 bytes), zero-filled by the
+ * caller before the first step: state[0] = t (advanced by this call), state[1] = lr_t (float bits) =
+ * lr*sqrt(1-b2^t)/(1-b1^t) recomputed on the device, state[2] = block ticket of the launch (zero between calls).   */
 int gg_adam_graph(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, int32_t* state, float lr, float beta1, float beta2,
                   float eps, float grad_scale, void* stream);
 

@@ -183,22 +183,26 @@ def test_c3_conv2d_image_side(B, H, W, Co):
 
 
 # g_h4 (model.py:321): bf16 activation in, fp32 image out (tanh applied by the caller in the model; here plain).
+# act = "tanh" is the model's form (model.py:324): its backward runs tanh' and the 3-channel bias gradient as one launch (gg_act_bwd_bias)
+@pytest.mark.parametrize("act", [None, "tanh"])
 @pytest.mark.parametrize("B,h,w_,Ci", [(2, 8, 8, 64), (3, 10, 6, 64), (2, 32, 32, 64), (4, 16, 16, 128), (40, 32, 32, 64)])
-def test_c3_deconv2d_image_side(B, h, w_, Ci):
+def test_c3_deconv2d_image_side(B, h, w_, Ci, act):
     rs = np.random.RandomState(h + Ci + B)
     x, w, b = bf16_round(rs.randn(B, h, w_, Ci)), bf16_round(rs.randn(5, 5, 3, Ci) * 0.05), torch.tensor(rs.randn(3) * 0.1, dtype=torch.float32)
     out_shape = [B, 2 * h, 2 * w_, 3]
     from gifgan import ops as _o
-    ops, st, tv = _store(lambda t: _o.deconv2d(t, out_shape, name="g"), (B, h, w_, Ci))
+    ops, st, tv = _store(lambda t: _o.deconv2d(t, out_shape, name="g", act=act, out_dtype=torch.float32), (B, h, w_, Ci))
     st.load_state_dict({"g/w": w.numpy(), "g/biases": b.numpy()})
     xt = x.cuda().to(torch.bfloat16).requires_grad_(True)
     dy = torch.tensor(rs.randn(*out_shape), dtype=torch.float32)
     with ops.trainable(tv):
-        y = ops.deconv2d(xt, out_shape, name="g")
+        y = ops.deconv2d(xt, out_shape, name="g", act=act, out_dtype=torch.float32)
         y.backward(dy.cuda().to(y.dtype))
     xr = x.double().requires_grad_(True)
     wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
     yr = T.conv2d_transpose(xr, wr, out_shape, br)
+    if act == "tanh":
+        yr = torch.tanh(yr)
     gx, gw, gb = torch.autograd.grad(yr, [xr, wr, br], dy.double())
     assert tuple(y.shape) == tuple(out_shape)
     assert relerr(y, yr) < TOL
@@ -288,7 +292,7 @@ def test_adam_keeps_the_bf16_shadow_current():
     g = torch.tensor(rs.randn(n + 5).astype(np.float32)).cuda()[:n]
     m, v = torch.zeros_like(p), torch.zeros_like(p)
     pb = torch.full((n,), 7.0, dtype=torch.bfloat16, device="cuda")
-    state = torch.zeros(2, dtype=torch.int32, device="cuda")
+    state = torch.zeros(4, dtype=torch.int32, device="cuda")
     for _ in range(3):
         ops.check(L.gg_adam_graph(ops.ptr(p), ops.ptr(pb), ops.ptr(g), ops.ptr(m), ops.ptr(v), n, ops.ptr(state), 2e-4, 0.5, 0.999, 1e-8, 1.0,
                                   ops.stream()), "gg_adam_graph")
