@@ -511,7 +511,7 @@ def hbm_kernel_table(model, batch, flush, peaks, conv_rows):
     for opt, uses, nm in ((model.d_optim, 1, "adam[D group]"), (model.g_optim, 2, "adam[G group]")):
         b, e = opt.range()
         ms = once(lambda: opt.apply())
-        add(nm + " (adam_tick + adam_dev)", (e - b) * 30, ms, uses)
+        add(nm + " (adam_tick + adam_dev; in the step the tick runs early on the side stream)", (e - b) * 30, ms, uses)
     # batch norm at the largest layer of the step: d_h1 on the 2B batch [2B,16,16,128]: fp32 pre-norm in, bf16 out
     B2, H, C = 2 * batch, 16, 128
     rows_n = B2 * H * H
@@ -538,7 +538,8 @@ def hbm_kernel_table(model, batch, flush, peaks, conv_rows):
     add(f"bn_bwd_apply [{B2} x 16 x 16 x 128] (reductions from the dgrad epilogue)", rows_n * C * (4 + 2 + 2), ms, 17)
     ms = once(lambda: check(L.gg_bn_bwd(ptr(pre), 0, ptr(dy), 1, ptr(dx), 1, rows_n, C, 2, ptr(gamma), ptr(beta), ptr(sm), ptr(sr), None, None, 2, 0.2, 1,
                                         ptr(ws), nb, stream()), "bn_bwd"))
-    add(f"bn_bwd two-pass: memset + colsum + bn_bwd_apply [{B2} x 16 x 16 x 128]", rows_n * C * (2 * (4 + 2) + 2), ms, 7)
+    add(f"bn_bwd two-pass: memset + colsum + bn_bwd_apply [{B2} x 16 x 16 x 128] (not in the step any more: every reduction rides in a "
+        "dgrad or loss-head launch)", rows_n * C * (2 * (4 + 2) + 2), ms, 0)
     # the generator's input projection (model.py:304: z[B,100] -> [B,8192], batch norm over 512 channels): streams its matrix
     zin, od, Cc = 100, 8192, 512
     zx = torch.randn(batch, zin, device="cuda")
@@ -555,12 +556,26 @@ def hbm_kernel_table(model, batch, flush, peaks, conv_rows):
     for r in conv_rows:
         if r.get("bytes"):
             add(r["kernel"] + f" ({r['path']}, 10 back-to-back launches after one flush)", r["bytes"], r["ms"], r["uses"])
-    # loss
-    lg = torch.randn(2 * batch, 1, device="cuda")
-    out = torch.empty(1, device="cuda")
-    dl = torch.empty_like(lg)
-    ms = once(lambda: check(L.gg_sigmoid_ce(ptr(lg), 2 * batch, 1.0, 1.0, ptr(out), 0, ptr(dl), stream()), "ce"))
-    add(f"sigmoid_ce fwd+bwd [{2 * batch} logits] (latency-bound)", 2 * batch * 8, ms, 4)
+    # loss head of the D update (model.py:277 + 121-131): d_h3_lin over [2B, 8192] + both cross-entropy means in one launch; its
+    # backward (Matrix / bias gradients, dh, d_bn3's backward reductions) in another.  Latency-bound: 2-8 MB per launch.
+    R, F_, Cb = 2 * batch, 8192, 512
+    h = torch.randn(R, F_, device="cuda").to(torch.bfloat16)
+    w1, b1 = torch.randn(F_, device="cuda") * 0.02, torch.zeros(1, device="cuda")
+    lg, parts, dl = torch.empty(R, device="cuda"), torch.empty(3, device="cuda"), torch.empty(R, device="cuda")
+    tk = torch.zeros(4, dtype=torch.int32, device="cuda")
+    I2, F2 = ctypes.c_int32 * 2, ctypes.c_float * 2
+    ms = once(lambda: check(L.gg_loss_head_fwd(ptr(h), 1, ptr(w1), ptr(b1), R, F_, I2(0, batch), I2(batch, R), F2(1.0, 0.0), F2(1.0, 1.0), 2,
+                                               ptr(lg), ptr(parts), ptr(dl), ptr(tk), stream()), "loss_head_fwd"))
+    add(f"loss_head_fwd [{R} x {F_} -> logits, 2 cross-entropy means, dlogits] (latency-bound)", R * F_ * 2 + F_ * 4, ms, 3)
+    pre = torch.randn(R, F_, device="cuda")
+    dh, dW, db = torch.empty_like(h), torch.zeros(F_, device="cuda"), torch.zeros(1, device="cuda")
+    smn, srs = torch.zeros(2, Cb, device="cuda"), torch.ones(2, Cb, device="cuda")
+    gam, bet = torch.ones(Cb, device="cuda"), torch.zeros(Cb, device="cuda")
+    sums = torch.zeros(2 * 2 * Cb, dtype=torch.float64, device="cuda")
+    fz = ctypes.c_int32(0)
+    ms = once(lambda: check(L.gg_loss_head_bwd(ptr(h), 1, ptr(dl), ptr(w1), R, F_, ptr(dW), ptr(db), ptr(dh), ptr(pre), ptr(smn), ptr(srs), ptr(gam),
+                                               ptr(bet), 2, 0.2, 2, Cb, ptr(sums), ctypes.byref(fz), stream()), "loss_head_bwd"))
+    add(f"loss_head_bwd [{R} x {F_}: dW, db, dh + d_bn3 backward reductions] (latency-bound)", R * F_ * (2 + 4 + 2) + 2 * F_ * 4, ms, 3)
     return rows
 
 

@@ -181,25 +181,11 @@ __global__ void adam_tick_kernel(int* __restrict__ state, float lr, float b1, fl
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
   reinterpret_cast<float*>(state)[1] = (float)lr_t;
 }
-// TICK: the launch advances the step counter itself (no adam_tick launch in front of it): lane 0 of every warp evaluates lr_t
-// for step t = state[0] + 1 -- after the warp's first loads are in flight -- and the block that takes the last ticket
-// (state[2]) publishes t and lr_t; nobody reads state[0] after that point (every block read it before taking its ticket).
-template <bool TICK>
 __global__ void __launch_bounds__(PW_THREADS)
 adam_dev_kernel(float* __restrict__ p, bf16* __restrict__ pb, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                int64_t n, int* state, float lr, float b1, float b2, float eps, float gs) {
+                int64_t n, const int* __restrict__ state, float b1, float b2, float eps, float gs) {
   pdl_grid_sync();
-  float lr_t;
-  int t_new = 0;
-  if (TICK) {
-    if ((threadIdx.x & 31) == 0) {
-      t_new = *reinterpret_cast<volatile int*>(state) + 1;
-      lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t_new)) / (1.0 - pow((double)b1, (double)t_new)));
-    }
-    lr_t = __shfl_sync(0xffffffffu, lr_t, 0);
-  } else {
-    lr_t = reinterpret_cast<const float*>(state)[1];
-  }
+  const float lr_t = reinterpret_cast<const float*>(state)[1];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -225,17 +211,6 @@ adam_dev_kernel(float* __restrict__ p, bf16* __restrict__ pb, const float* __res
     const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
     p[i] = pi;
     if (pb != nullptr) pb[i] = __float2bfloat16_rn(pi);
-  }
-  if (TICK) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(reinterpret_cast<unsigned int*>(state) + 2, 1u) == gridDim.x - 1) {
-        state[0] = t_new;
-        reinterpret_cast<float*>(state)[1] = lr_t;
-        state[2] = 0;
-      }
-    }
   }
 }
 
@@ -541,15 +516,26 @@ extern "C" int gg_adam_graph(float* p, void* p_bf16, const float* g, float* m, f
                              float eps, float gs, void* stream) {
   GG_REQUIRE(p && g && m && v && state && n > 0, GG_ERR_INVALID, "adam_graph: bad argument");
   GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v) && ((uintptr_t)p_bf16 % 8) == 0, GG_ERR_INVALID, "adam_graph: buffers must be 16-byte aligned (bf16 shadow: 8)");
-  static const bool separate_tick = getenv("GG_ADAM_TICK") && getenv("GG_ADAM_TICK")[0] == '1';     // A/B: the two-launch form
-  if (separate_tick) {
-    Launch(1, 1, 0, (cudaStream_t)stream)(adam_tick_kernel, state, lr, b1, b2);
-    int rc = check_launch("adam_tick");
-    if (rc) return rc;
-    Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel<false>, p, (bf16*)p_bf16, g, m, v, n, (int*)state, lr, b1, b2, eps, gs);
-  } else {
-    Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel<true>, p, (bf16*)p_bf16, g, m, v, n, (int*)state, lr, b1, b2, eps, gs);
-  }
+  Launch(1, 1, 0, (cudaStream_t)stream)(adam_tick_kernel, state, lr, b1, b2);
+  int rc = check_launch("adam_tick");
+  if (rc) return rc;
+  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel, p, (bf16*)p_bf16, g, m, v, n, state, b1, b2, eps, gs);
+  return check_launch("adam_dev");
+}
+
+// The two halves of gg_adam_graph as separate calls: the tick (one thread: t += 1, lr_t in double precision) depends only on the
+// previous step of the same group, so a caller can issue it EARLY on another stream -- under the update's forward pass -- and
+// keep the 2.5 us launch (+ gap) off the critical path in front of the Adam launch.
+extern "C" int gg_adam_tick(int32_t* state, float lr, float b1, float b2, void* stream) {
+  GG_REQUIRE(state, GG_ERR_INVALID, "adam_tick: bad argument");
+  Launch(1, 1, 0, (cudaStream_t)stream)(adam_tick_kernel, state, lr, b1, b2);
+  return check_launch("adam_tick");
+}
+extern "C" int gg_adam_apply(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, const int32_t* state, float b1, float b2,
+                             float eps, float gs, void* stream) {
+  GG_REQUIRE(p && g && m && v && state && n > 0, GG_ERR_INVALID, "adam_apply: bad argument");
+  GG_REQUIRE(al16(p) && al16(g) && al16(m) && al16(v) && ((uintptr_t)p_bf16 % 8) == 0, GG_ERR_INVALID, "adam_apply: buffers must be 16-byte aligned (bf16 shadow: 8)");
+  Launch(pw_blocks(n / 4 + 1), PW_THREADS, 0, (cudaStream_t)stream)(adam_dev_kernel, p, (bf16*)p_bf16, g, m, v, n, state, b1, b2, eps, gs);
   return check_launch("adam_dev");
 }
 

@@ -91,6 +91,8 @@ SIGNATURES = {
     "gg_distance_loss": (C.c_int, [_vp, _i32, _vp, _i64, _f32, _f32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "gg_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
     "gg_adam_graph": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "gg_adam_tick": (C.c_int, [_vp, _f32, _f32, _f32, _vp]),
+    "gg_adam_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _vp]),
     "gg_lstm_step_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "gg_lstm_step_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp]),
 }

@@ -240,7 +240,7 @@ class DCGAN(object):
             both[:B].copy_(images)
         if self.dp is not None:
             self.dp.wait_pending()
-        self.d_optim.zero_grad(overlap=self.dp is None)
+        self.d_optim.zero_grad(overlap=self.dp is None, tick=apply)
         if self.dp is not None:
             self.dp.begin_update(self.d_optim)
         with ops.trainable(self.d_vars), ops.overlap_wgrad(), ops.stats_arena():
@@ -266,7 +266,7 @@ class DCGAN(object):
 
     def g_update(self, z, y=None, apply=True):
         """sess.run([g_optim, g_sum]) (model.py:232-234): G fwd, D(fake), backward through D into g_vars, Adam."""
-        self.g_optim.zero_grad(overlap=self.dp is None)
+        self.g_optim.zero_grad(overlap=self.dp is None, tick=apply)
         if self.dp is not None:
             self.dp.begin_update(self.g_optim)
         with ops.trainable(self.g_vars), ops.overlap_wgrad(), ops.stats_arena():

@@ -861,6 +861,7 @@ class _Linear(torch.autograd.Function):
         return dx, None, None, None, None, None, None, None
 
 
+EARLY_ADAM_TICK = os.environ.get("GG_EARLY_ADAM_TICK", "1") != "0"  # A/B switch: Adam's step-counter tick on the side stream, under the forward pass
 FUSE_ACT_BIAS = os.environ.get("GG_FUSE_ACT_BIAS", "1") != "0"      # A/B switch: g_h4's tanh' + bias gradient as one launch
 FUSE_WGRAD_BIAS = os.environ.get("GG_FUSE_WGRAD_BIAS", "1") != "0"  # A/B switch: d_h0_conv's bias gradient inside its filter-gradient launch
 ZERO_ON_SIDE = os.environ.get("GG_ZERO_ON_SIDE", "1") != "0"        # A/B switch: gradient zero-fill under the forward pass
@@ -1413,17 +1414,21 @@ class AdamOptimizer:
             return rs[0][0], rs[-1][1]
         return self.store.ranges[self.group]
 
-    def zero_grad(self, overlap=False):
+    def zero_grad(self, overlap=False, tick=False):
         """Zero the group's gradient range.  overlap=True issues the fill on the side stream (GG_ZERO_ON_SIDE=0 disables), so
         it runs under the update's forward pass -- one-wave launches that leave SMs and all of HBM idle -- instead of in front
         of it; the caller must `join_side()` before the first gradient kernel (the filter gradients queue up behind the fill
-        on the side stream by themselves)."""
+        on the side stream by themselves).  tick=True (the caller WILL call apply() for this update) also advances Adam's
+        device-side step counter there (gg_adam_tick), so apply() is the Adam launch alone."""
         b, e = self.range()
         if overlap and ZERO_ON_SIDE and torch.cuda.is_available():
             s = _side_stream()
             s["stream"].wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s["stream"]):
                 self.store.flat["grads"][b:e].zero_()
+                if tick and EARLY_ADAM_TICK:
+                    check(cabi.lib().gg_adam_tick(ptr(self.state), self.lr, self.b1, self.b2, stream()), "gg_adam_tick")
+                    self._ticked = True
             s["dirty"] = True
             return
         self.store.flat["grads"][b:e].zero_()
@@ -1438,9 +1443,15 @@ class AdamOptimizer:
         b, e = self.range()
         f = self.store.flat
         sh = getattr(self.store, "shadow", None)
-        check(cabi.lib().gg_adam_graph(ptr(f["params"][b:e]), ptr(sh[b:e]) if sh is not None else None, ptr(f["grads"][b:e]), ptr(f["m"][b:e]),
-                                       ptr(f["v"][b:e]), e - b, ptr(self.state), self.lr, self.b1, self.b2, self.eps, grad_scale, stream()),
-              "gg_adam_graph")
+        if getattr(self, "_ticked", False):       # zero_grad(tick=True) advanced the step counter under the forward pass
+            self._ticked = False
+            check(cabi.lib().gg_adam_apply(ptr(f["params"][b:e]), ptr(sh[b:e]) if sh is not None else None, ptr(f["grads"][b:e]), ptr(f["m"][b:e]),
+                                           ptr(f["v"][b:e]), e - b, ptr(self.state), self.b1, self.b2, self.eps, grad_scale, stream()),
+                  "gg_adam_apply")
+        else:
+            check(cabi.lib().gg_adam_graph(ptr(f["params"][b:e]), ptr(sh[b:e]) if sh is not None else None, ptr(f["grads"][b:e]), ptr(f["m"][b:e]),
+                                           ptr(f["v"][b:e]), e - b, ptr(self.state), self.lr, self.b1, self.b2, self.eps, grad_scale, stream()),
+                  "gg_adam_graph")
         for v in self.var_list or []:
             v.version += 1
             if sh is not None and v._bf16 is not None:

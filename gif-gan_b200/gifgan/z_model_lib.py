@@ -206,7 +206,7 @@ class VID_DCGAN(object):
             both[:n].copy_(images)
         if self.dp is not None:
             self.dp.wait_pending()
-        self.d_optim.zero_grad()
+        self.d_optim.zero_grad(overlap=self.dp is None, tick=apply)
         if self.dp is not None:
             self.dp.begin_update(self.d_optim)
         with ops.trainable(self.d_var_list), ops.overlap_wgrad(), ops.stats_arena():
@@ -218,6 +218,7 @@ class VID_DCGAN(object):
             segs = [(0, Bv, 1.0, 1.0), (Bv, 2 * Bv, 0.0, 1.0)]
             logits = self.discriminator(act, reuse=True, groups=2, ce_segments=segs)[1]
             losses = sigmoid_cross_entropy_loss(logits, segs)
+            ops.join_side()         # the gradient zero-fill / Adam tick (side stream) precede every gradient kernel
             torch.autograd.backward(losses, grad_tensors=self._ones(losses))
         if self.dp is not None and apply:
             # remaining bucket + Adam on the communication stream: the next update's generator / image-GAN forward overlaps them
@@ -236,7 +237,7 @@ class VID_DCGAN(object):
     def g_update(self, z, apply=True):
         """One generator update (z_model_lib.py:233-239)."""
         img = self.img_dcgan
-        self.g_optim.zero_grad()
+        self.g_optim.zero_grad(overlap=self.dp is None, tick=apply)
         if self.dp is not None:
             self.dp.begin_update(self.g_optim)
         with ops.trainable(self.g_var_list), ops.overlap_wgrad(), ops.stats_arena():
@@ -255,6 +256,7 @@ class VID_DCGAN(object):
             if self.first_frame_loss_scalar:
                 first = _FirstFrameMSE.apply(G_out, z, self.vid_length, self.z_output_size, self.first_frame_loss_scalar)
                 roots.append(first); grads.append(self._ones(first))
+            ops.join_side()
             torch.autograd.backward(roots, grad_tensors=grads)
         if self.dp is not None:
             self.dp.allreduce(self.g_optim)

@@ -274,10 +274,15 @@ int gg_distance_loss(const void* a, int32_t a_dtype, const float* target, int64_
 int gg_adam(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2, float eps,
             float grad_scale, void* stream);
 
-/* CUDA-graph-friendly variant: the step counter lives on the device.  state = FOUR int32 (16 bytes), zero-filled by the
- * caller before the first step: state[0] = t (advanced by this call), state[1] = lr_t (float bits) =
- * lr*sqrt(1-b2^t)/(1-b1^t) recomputed on the device, state[2] = block ticket of the launch (zero between calls).   */
+/* CUDA-graph-friendly variant: the step counter lives on the device.  state = FOUR int32 (16 bytes; two are used), zero-filled
+ * by the caller before the first step: state[0] = t (advanced by this call), state[1] = lr_t (float bits) =
+ * lr*sqrt(1-b2^t)/(1-b1^t) recomputed on the device in double precision.                                           */
 int gg_adam_graph(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, int32_t* state, float lr, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream);
+/* the two halves of gg_adam_graph as separate calls: gg_adam_tick (t += 1, lr_t) depends only on the group's previous step, so
+ * it can be issued early on another stream; gg_adam_apply is the Adam launch alone, reading lr_t from state[1].            */
+int gg_adam_tick(int32_t* state, float lr, float beta1, float beta2, void* stream);
+int gg_adam_apply(float* p, void* p_bf16, const float* g, float* m, float* v, int64_t n, const int32_t* state, float beta1, float beta2,
                   float eps, float grad_scale, void* stream);
 
 /* ---- BasicLSTMCell (recurrent_DCGAN.py:199-200) --------------------------------------
