@@ -91,27 +91,33 @@ REC_FLOPS_PER_CLIP = 105.1e9          # recurrent_image recurrent_DCGAN.py, 16 f
 MNIST_FLOPS_PER_IMAGE = 0.04e12 / 64  # config 1, ~0.04 TFLOP per step of 64
 
 
-def kernel_source_sha():
-    """Identity of the kernel sources: a committed ncu capture is only quoted when it was taken from THESE sources."""
+# the files that DEFINE each kernel family (kernel + every header it includes): a capture stays valid while they are unchanged
+KERNEL_FAMILY_SOURCES = {"tcgen05": ("tc_tapgemm.cu", "tc_common.cuh", "common.cuh"), "mma.sync": ("conv_c3_mma.cu", "common.cuh")}
+
+
+def kernel_source_sha(path=None, csrc=None):
+    """Identity of the kernel sources: a committed ncu capture is only quoted when it was taken from THESE sources.
+    path = "tcgen05" | "mma.sync": the files that define that kernel family; None: every .cu / .cuh of the library."""
     h = hashlib.sha256()
-    d = os.path.join(ROOT, "gif-gan_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            with open(os.path.join(d, f), "rb") as fh:
-                h.update(f.encode() + b"\0" + fh.read())
+    d = csrc or os.path.join(ROOT, "gif-gan_b200", "csrc")
+    files = KERNEL_FAMILY_SOURCES[path] if path else [f for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh"))]
+    for f in sorted(files):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
     return h.hexdigest()[:16]
 
 
-def ncu_by_layer():
+def ncu_by_layer(family="tcgen05"):
     """profiles/*_ncu_by_layer.json (tools/summarize_profiles.py): per-launch DRAM traffic and tensor-pipe activity of each layer
-    kernel from a committed `ncu --set full` capture of tools/layer_kernels.py.  Only a capture whose recorded
-    `_kernel_source_sha` equals the current sources' is used -- otherwise `traffic` is null (never a stale number)."""
+    kernel from a committed `ncu --set full` capture of tools/layer_kernels.py.  Only a capture whose recorded source identity
+    of the kernel's family (`_kernel_source_sha_by_family`: the files that define the kernel, hashed from the commit the capture
+    ran on) equals the current sources' is used -- otherwise `traffic` is null (never a stale number)."""
     import glob
-    sha = kernel_source_sha()
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_by_layer.json")), key=os.path.getmtime, reverse=True):
+    sha = kernel_source_sha(family)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_by_layer.json")), reverse=True):
         with open(path) as f:
             d = json.load(f)
-        if d.get("_kernel_source_sha") == sha:
+        if d.get("_kernel_source_sha_by_family", {}).get(family) == sha or d.get("_kernel_source_sha") == kernel_source_sha():
             return d, os.path.basename(path)
     return {}, None
 
@@ -620,13 +626,13 @@ def run_ours(args):
         rows = layer_rooflines(wl.model, wl.B, args.precision, flush)
         tc_rows = [r for r in rows if r["path"] == "tcgen05"] or rows
         top = tc_rows[0]
-        ncu, ncu_file = ncu_by_layer()
+        ncu, ncu_file = ncu_by_layer(top["path"] if top["path"] in KERNEL_FAMILY_SOURCES else "tcgen05")
         prof = ncu.get(top["kernel"], {})
         traffic = (prof["dram_read_bytes"] + prof["dram_write_bytes"]) if prof else None
         roofline = {"bound": "tensor", "kernel": top["kernel"], "path": top["path"], "achieved": top["tflops"], "peak": peaks["tf_burst"],
                     "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tf_burst"], "traffic": traffic, "peak_source": peaks["source"],
                     "traffic_note": (f"ncu --set full capture {ncu_file} of these kernel sources" if prof else
-                                     "null: no committed ncu capture matches the current kernel sources (sha %s)" % kernel_source_sha()),
+                                     "null: no committed ncu capture matches the current sources of this kernel family (sha %s)" % kernel_source_sha(top["path"] if top["path"] in KERNEL_FAMILY_SOURCES else "tcgen05")),
                     "ncu": {"file": ncu_file, "tensor_pipe_active_pct": prof.get("tensor_pct"), "duration_us": prof.get("dur_us")} if prof else None,
                     "flops_per_launch": top["flops"], "launch_ms": top["ms"],
                     "timing": "CUDA events, 10 back-to-back launches after one L2 flush (operands L2-warm for 9 of 10, as in the step where the producer kernel has just written them), 5 repetitions",

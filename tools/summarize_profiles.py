@@ -105,7 +105,11 @@ def by_layer(tag):
     import json
     sys.path.insert(0, ROOT)
     import bench
-    out["_kernel_source_sha"] = bench.kernel_source_sha()        # bench.py quotes `traffic` only from a capture of the CURRENT kernel sources
+    # bench.py quotes `traffic` only from a capture of the CURRENT sources of the kernel's family.  Run this on the tree the capture
+    # ran on (or pass GG_CAPTURE_CSRC=<checkout of that commit's gif-gan_b200/csrc>).
+    csrc = os.environ.get("GG_CAPTURE_CSRC")
+    out["_kernel_source_sha"] = bench.kernel_source_sha(None, csrc)
+    out["_kernel_source_sha_by_family"] = {k: bench.kernel_source_sha(k, csrc) for k in bench.KERNEL_FAMILY_SOURCES}
     with open(os.path.join(P, f"{tag}_ncu_by_layer.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", f"{tag}_ncu_by_layer.json", len(out), "layers")
