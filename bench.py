@@ -582,6 +582,14 @@ def hbm_kernel_table(model, batch, flush, peaks, conv_rows):
     ms = once(lambda: check(L.gg_loss_head_bwd(ptr(h), 1, ptr(dl), ptr(w1), R, F_, ptr(dW), ptr(db), ptr(dh), ptr(pre), ptr(smn), ptr(srs), ptr(gam),
                                                ptr(bet), 2, 0.2, 2, Cb, ptr(sums), ctypes.byref(fz), stream()), "loss_head_bwd"))
     add(f"loss_head_bwd [{R} x {F_}: dW, db, dh + d_bn3 backward reductions] (latency-bound)", R * F_ * (2 + 4 + 2) + 2 * F_ * 4, ms, 3)
+    # decode tail of the input frames (z_model_lib.py:339-346: cv2.resize INTER_LINEAR + BGR->RGB + /127.5-1), config 3's batch of
+    # 32 clips x 16 frames, uint8 128 x 128 -> fp32 64 x 64 (OpenCV's 2x shortcut: every source byte is read): byte work, HBM-bound
+    nf, Hs, Sd = 32 * 16, 128, 64
+    fr = torch.randint(0, 256, (nf, Hs, Hs, 3), dtype=torch.uint8, device="cuda")
+    fo = torch.empty(nf, Sd, Sd, 3, device="cuda")
+    ms = once(lambda: check(L.gg_frames_to_input(ptr(fr), nf, Hs, Hs, Hs * Hs * 3, Hs * 3, ptr(fo), Sd, Sd, 1, stream()), "frames_to_input"))
+    add(f"frames_to_input [{nf} frames u8 {Hs}x{Hs}x3 -> fp32 {Sd}x{Sd}x3] (input side of the e2e path, not in the device-timed step)",
+        nf * Hs * Hs * 3 + nf * Sd * Sd * 12, ms, 0)
     return rows
 
 

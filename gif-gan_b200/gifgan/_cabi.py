@@ -84,6 +84,7 @@ SIGNATURES = {
     "gg_get_std": (C.c_int, [_vp, _i32, _i64, _i64, _vp, _vp, _sz, _vp]),
     "gg_sigmoid_ce": (C.c_int, [_vp, _i64, _f32, _f32, _vp, _i32, _vp, _vp]),
     "gg_mse": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _f32, _vp, _i32, _vp, _vp]),
+    "gg_frames_to_input": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _vp, _i32, _i32, _i32, _vp]),
     "gg_loss_head_ok": (C.c_int, [_i32, _i32, _i32]),
     "gg_loss_head_fwd": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "gg_loss_head_bwd": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp]),

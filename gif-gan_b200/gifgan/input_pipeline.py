@@ -31,10 +31,12 @@ class _Shared(object):
     """Everything the producer thread and the decode workers touch.  They hold THIS object, never the Prefetcher, so that
     dropping the iterator mid-epoch lets it be collected -- its finalizer then stops the threads and releases the ring."""
 
-    def __init__(self, batches, load_item, item_shape, depth, workers, pin):
+    def __init__(self, batches, load_item, item_shape, depth, workers, pin, dtype=torch.float32):
         self.batches, self.load_item, self.item_shape, self.depth = batches, load_item, item_shape, depth
+        self.dtype = dtype
+        self.np_dtype = np.uint8 if dtype == torch.uint8 else np.float32
         rows = max((len(b) for b in batches), default=0)
-        self.ring = [torch.empty((rows,) + item_shape, dtype=torch.float32) for _ in range(depth + 3)]
+        self.ring = [torch.empty((rows,) + item_shape, dtype=dtype) for _ in range(depth + 3)]
         if pin:
             self.ring = [t.pin_memory() for t in self.ring]
         self.free = queue.Queue()
@@ -47,7 +49,10 @@ class _Shared(object):
         self.consumed = 0
 
     def fill(self, buf, row, item):
-        buf[row].copy_(torch.from_numpy(np.ascontiguousarray(self.load_item(item), dtype=np.float32).reshape(self.item_shape)))
+        a = self.load_item(item)
+        if self.np_dtype == np.uint8 and np.asarray(a).dtype != np.uint8:
+            raise TypeError("a uint8 Prefetcher needs uint8 items (raw decoded bytes)")
+        buf[row].copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=self.np_dtype).reshape(self.item_shape)))
 
     def take_free(self):
         while not self.stop.is_set():
@@ -87,14 +92,15 @@ def _produce(sh: _Shared):
 
 
 class Prefetcher(object):
-    def __init__(self, batches, load_item, item_shape, depth=2, workers=4, pin=None):
+    def __init__(self, batches, load_item, item_shape, depth=2, workers=4, pin=None, dtype=torch.float32):
         """`batches`: a sequence of batches, each a sequence of items (file names); `load_item(item)` -> array of
-        `item_shape` (any float / int dtype; stored as float32)."""
+        `item_shape` (any float / int dtype; stored as float32).  dtype=torch.uint8: the buffers hold raw decoded bytes
+        (items must be uint8) for a GPU-side decode tail (ops.frames_to_input): a quarter of the host-to-device bytes."""
         self.batches = list(batches)
         self.load_item, self.item_shape = load_item, tuple(item_shape)
         self.depth = max(1, int(depth))
         pin = torch.cuda.is_available() if pin is None else pin
-        self._sh = sh = _Shared(self.batches, load_item, self.item_shape, self.depth, workers, pin)
+        self._sh = sh = _Shared(self.batches, load_item, self.item_shape, self.depth, workers, pin, dtype)
         self._ring = sh.ring
         self._held = []                       # buffers the consumer may still be reading (newest last)
         self._producer = threading.Thread(target=_produce, args=(sh,), name="gifgan-prefetch", daemon=True)

@@ -1300,6 +1300,27 @@ def get_std(inpt):
     return out[0]
 
 
+def frames_to_input(frames_u8, size, swap_rb=True, out=None):
+    """The tail of the reference's frame decode on the GPU (z_model_lib.py:339-346, utils.py:57-63):
+    `transform(cv2.cvtColor(cv2.resize(im, (size, size), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2RGB), is_crop=False)` for a
+    whole batch of decoded uint8 frames [n, H0, W0, 3] already in device memory -> float32 [n, size, size, 3] in [-1, 1], bit for
+    bit what the host code produces (gg_frames_to_input).  `out=` writes into a caller buffer (a slice of the step's static input)."""
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
+        raise ValueError("frames_to_input: expects uint8 frames [n, H, W, 3]")
+    n, H0, W0, _ = frames_u8.shape
+    if _is_meta(frames_u8):
+        return torch.empty((n, size, size, 3), dtype=torch.float32, device="meta")
+    _require_cuda(frames_u8, "frames_to_input")
+    fr = frames_u8.contiguous()
+    if out is None:
+        out = torch.empty((n, size, size, 3), dtype=torch.float32, device=fr.device)
+    elif tuple(out.shape) != (n, size, size, 3) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f"out= must be a contiguous float32 tensor of shape {(n, size, size, 3)}")
+    check(cabi.lib().gg_frames_to_input(ptr(fr), n, H0, W0, H0 * W0 * 3, W0 * 3, ptr(out), size, size, 1 if swap_rb else 0, stream()),
+          "gg_frames_to_input")
+    return out
+
+
 def conv_cond_concat(x, y):
     """ops.py:45-49 -- concat y broadcast over H, W on the channel axis (MNIST branch; tensor plumbing)."""
     B, H, W, _ = x.shape

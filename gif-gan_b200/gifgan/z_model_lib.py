@@ -419,6 +419,43 @@ class VID_DCGAN(object):
         return Prefetcher(chunks(files, batch_size), lambda f: self.load_videos([f]), (self.vid_length, s, s, self.c_dim),
                           depth=depth, workers=workers)
 
+    def raw_video_batches(self, files, batch_size, frame_hw, depth=2, workers=8):
+        """video_batches with the decode TAIL left to the GPU: the workers only decode (cv2.VideoCapture.read) and the batches are
+        the raw uint8 BGR frames [clips, T, H0, W0, 3] at the files' own resolution `frame_hw` (one resolution per data set);
+        `frames_from_raw` turns a batch into what `load_videos` returns -- resize, BGR -> RGB, / 127.5 - 1 -- in one launch."""
+        from .input_pipeline import Prefetcher, chunks
+        H0, W0 = frame_hw
+        return Prefetcher(chunks(files, batch_size), lambda f: self.load_videos_raw([f], frame_hw)[0], (self.vid_length, H0, W0, self.c_dim),
+                          depth=depth, workers=workers, dtype=torch.uint8)
+
+    def load_videos_raw(self, files, frame_hw):
+        """The decode half of z_model_lib.py:332-351: uint8 BGR frames [n, T, H0, W0, 3] exactly as cap.read() returns them."""
+        import cv2
+        H0, W0 = frame_hw
+        videos = np.zeros((len(files), self.vid_length, H0, W0, self.c_dim), dtype=np.uint8)
+        for (i, f) in enumerate(files):
+            cap = cv2.VideoCapture(f)
+            frame = 0
+            while cap.isOpened() and frame < self.vid_length:
+                ret, im = cap.read()
+                if not ret:
+                    break
+                if im.shape != (H0, W0, self.c_dim):
+                    raise ValueError(f"{f}: frame shape {im.shape}, expected {(H0, W0, self.c_dim)}")
+                videos[i, frame] = im
+                frame += 1
+            assert frame == self.vid_length
+        return videos
+
+    def frames_from_raw(self, raw_u8, out=None):
+        """raw uint8 BGR frames [clips, T, H0, W0, 3] (host, page-locked, or device) -> the float32 batch
+        [clips * T, s, s, 3] of load_videos, bit for bit (ops.frames_to_input: the H2D copy moves bytes, the rest is one launch)."""
+        t = raw_u8 if isinstance(raw_u8, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(raw_u8))
+        t = t.reshape(-1, t.shape[-3], t.shape[-2], t.shape[-1])
+        if not t.is_cuda:
+            t = t.to(self.store.device, non_blocking=True)
+        return ops.frames_to_input(t, self.input_image_size, swap_rb=True, out=out)
+
     def load_videos(self, files):
         """z_model_lib.py:332-351."""
         import cv2

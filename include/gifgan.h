@@ -265,6 +265,16 @@ size_t gg_distance_loss_workspace_bytes(void);
 int gg_distance_loss(const void* a, int32_t a_dtype, const float* target, int64_t n, float w_l2, float w_l1, float* loss_out,
                      int32_t accumulate, void* da, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- input frames (z_model_lib.py:339-346 + utils.py:57-63: the tail of the reference's per-frame decode) --------
+ * frames: n decoded uint8 3-channel frames [src_h, src_w, 3] in device memory (frame f at frames + f*frame_stride_bytes, rows
+ * row_stride_bytes apart; OpenCV's VideoCapture order is BGR).  out[n, dst_h, dst_w, 3] fp32 =
+ *   cv2.resize(frame, (dst_w, dst_h), INTER_LINEAR)  ->  (swap_rb: BGR -> RGB)  ->  x / 127.5 - 1
+ * bit for bit: OpenCV's 8-bit fixed-point bilinear incl. its 2x INTER_AREA shortcut (restated in oracle/image_ops.py and pinned
+ * against cv2.resize), the normalisation evaluated in float64 and rounded once like numpy's.  One launch per batch; the host
+ * ships 1 byte per sample instead of 4.                                                                              */
+int gg_frames_to_input(const uint8_t* frames, int32_t n, int32_t src_h, int32_t src_w, int64_t frame_stride_bytes,
+                       int64_t row_stride_bytes, float* out, int32_t dst_h, int32_t dst_w, int32_t swap_rb, void* stream);
+
 /* ---- optimiser (model.py:153-156: tf.train.AdamOptimizer(lr, beta1).minimize) -------
  * TF semantics: p -= lr_t * m / (sqrt(v) + eps) with lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
  * computed by the caller.  One launch over a flat fp32 parameter group.

@@ -113,6 +113,41 @@ def test_vid_dcgan_video_batches_equal_load_videos(tmp_path):
         assert np.array_equal(b.reshape(-1, 64, 64, 3).numpy(), want)
 
 
+def test_vid_dcgan_raw_batches_plus_decode_tail_equal_load_videos(tmp_path):
+    """The split loader -- raw uint8 BGR frames from the workers (raw_video_batches), resize + BGR->RGB + /127.5-1 afterwards --
+    gives exactly load_videos' batch (z_model_lib.py:332-351).  The tail is evaluated here with the oracle restatement (CPU);
+    tests/test_gpu_frames.py checks the CUDA kernel against the same oracle bit for bit."""
+    import cv2
+    from gifgan import ops
+    from gifgan.z_model_lib import VID_DCGAN
+    from oracle import image_ops as I
+    rs = np.random.RandomState(4)
+    files = []
+    for i in range(4):
+        f = str(tmp_path / ("clip%d.avi" % i))
+        wr = cv2.VideoWriter(f, cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (40, 24))       # (width, height): non-square, enlarged AND reduced
+        if not wr.isOpened():
+            pytest.skip("no MJPG writer in this OpenCV build")
+        for t in range(4):
+            wr.write(cv2.resize(rs.randint(0, 256, (6, 10, 3)).astype(np.uint8), (40, 24), interpolation=cv2.INTER_CUBIC))
+        wr.release()
+        files.append(f)
+    ops.set_precision("fp32")
+    ops.reset_default_store(device="cpu", seed=1)
+    with ops.variable_scope("video_gan"):
+        m = VID_DCGAN(None, batch_size=2, z_input_size=120, z_output_size=100, vid_length=4, input_image_size=32,
+                      output_image_size=32, c_dim=3, sample_cols=2)
+    got = list(m.raw_video_batches(files, 2, (24, 40), workers=2))
+    assert len(got) == 2
+    for k, b in enumerate(got):
+        assert b.dtype == torch.uint8 and tuple(b.shape) == (2, 4, 24, 40, 3)
+        want = m.load_videos(files[2 * k:2 * k + 2]).astype(np.float32)
+        tail = I.frames_to_input(b.reshape(-1, 24, 40, 3).numpy(), 32)
+        assert np.array_equal(tail, want)
+    with pytest.raises(ValueError):
+        m.load_videos_raw(files[:1], (24, 24))                                           # wrong declared resolution
+
+
 def test_dropping_the_iterator_mid_epoch_stops_the_threads():
     """The producer and the decode workers hold only the shared state, never the Prefetcher: `del` + gc must stop them."""
     import gc
