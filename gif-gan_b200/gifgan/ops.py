@@ -893,6 +893,7 @@ class _LossHead(torch.autograd.Function):
         ctx.mvar, ctx.bvar, ctx.in_bn, ctx.dl = mvar, bvar, in_bn, dl
         ctx.save_for_backward(h)
         ctx.mark_non_differentiable(logits)
+        ctx.set_materialize_grads(False)      # no zero-filled gradient tensor for the logits output (a fill launch per backward)
         return parts, logits
 
     @staticmethod

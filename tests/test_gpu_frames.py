@@ -30,7 +30,7 @@ def test_frames_match_the_cv2_fixture_bit_for_bit():
 
 
 @pytest.mark.parametrize("H,W,S", [(96, 128, 64), (128, 128, 64), (64, 64, 64), (48, 40, 64), (75, 131, 64), (240, 320, 64), (360, 480, 128),
-                                   (1, 1, 4), (2, 3, 1), (63, 200, 64), (17, 500, 32)])
+                                   (1, 1, 4), (2, 3, 1), (63, 200, 64), (17, 500, 32), (12, 12, 6), (8, 8, 4)])
 def test_frames_match_the_oracle(H, W, S):
     rs = np.random.RandomState(H * 7 + W)
     fr = rs.randint(0, 256, (5, H, W, 3)).astype(np.uint8)
