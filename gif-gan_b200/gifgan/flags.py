@@ -128,6 +128,13 @@ TABLES = {
         ("lr_decay_amount", "f", 0.9, "decay factor"),
         ("vid_length", "i", 0, "> 0: discriminator_activation_optimizer_video.py -- search every `frame_skip`-th frame of the input clips (batch = clips x vid_length, one grid row per clip)"),
         ("frame_skip", "i", 2, "frame step when vid_length > 0"),
+        ("nested", "b", False, "discriminator_activation_optimizer_nested.py: search the VIDEO latent [batch, 120] of a VID_DCGAN checkpoint so "
+                               "that the first frame of every generated clip matches its target; writes the clips (vid_length default 16)"),
+        ("iterative", "b", False, "with vid_length > 0: discriminator_activation_optimizer_video_iterative.py -- batch = clips; frame 0 for "
+                                  "num_initial_steps, then every frame in turn for num_steps_per_frame steps, warm-started from the previous frame"),
+        ("num_initial_steps", "i", 500, "iterative: steps on frame 0 before tracking"),
+        ("num_steps_per_frame", "i", 100, "iterative: steps per tracked frame"),
+        ("tween_frames", "i", 2, "iterative: frames interpolated in latent space between consecutive tracked frames (tween_frames/ output)"),
     ] + _LATENT_WEIGHTS + _LATENT_DCGAN + _OURS,
 }
 

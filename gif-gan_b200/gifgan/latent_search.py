@@ -54,12 +54,12 @@ class LatentSearch(object):
                       generator_loss_weight=float(generator_loss_weight))
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
         dev = dcgan.store.device
-        B = dcgan.batch_size
+        zshape = self._z_shape()
         if z is None:
-            z = np.random.RandomState(random_seed).uniform(-1.0, 1.0, size=(B, dcgan.z_dim))
+            z = np.random.RandomState(random_seed).uniform(-1.0, 1.0, size=zshape)
         self.z = torch.as_tensor(np.asarray(z, dtype=np.float32)).to(dev).contiguous().requires_grad_(True)
-        if tuple(self.z.shape) != (B, dcgan.z_dim):
-            raise ValueError(f"z must have shape {(B, dcgan.z_dim)}")
+        if tuple(self.z.shape) != tuple(zshape):
+            raise ValueError(f"z must have shape {tuple(zshape)}")
         # Adam slots of the optimiser built once for the whole run (z_space_finder.py:294-298): they, like z, carry over
         # from one target to the next
         self.m, self.v, self.t = torch.zeros_like(self.z), torch.zeros_like(self.z), 0
@@ -67,6 +67,9 @@ class LatentSearch(object):
         self.use_graph, self._graphs, self._bufs = use_graph, {}, {}
         self._ones = torch.ones(1, dtype=torch.float32, device=dev)
         self._loss_vec = torch.zeros(8, dtype=torch.float32, device=dev)
+
+    def _z_shape(self):
+        return (self.dcgan.batch_size, self.dcgan.z_dim)
 
     # ------------------------------------------------------------------------------------------
     def _target(self, a):
@@ -218,6 +221,62 @@ class LatentSearch(object):
             if lr_decay_frequency > 0 and i % lr_decay_frequency == lr_decay_frequency - 1:
                 lr *= lr_decay_amount
         return self.images().float().cpu().numpy()
+
+
+class NestedLatentSearch(LatentSearch):
+    """discriminator_activation_optimizer_nested.py: the search runs THROUGH the video generator.  The variable is the video
+    latent z [clips, z_input_size] (120); the clip is vid.generator(z) -> [clips * T, 100] image latents -> the image GAN's
+    generator -> [clips * T, s, s, c] frames -> the image discriminator; the activation and pixel terms compare only the FIRST
+    frame of every clip with the target (`[::vid_length]`, reference lines 180-198), the generator term is the image GAN's g_loss
+    over all frames (line 192).  `discriminator_mode` also sets the video generator's batch-norm mode (`is_training`, line 242).
+    Batch-norm statistics in train mode run over all clips * T frames, so the target activations are taken, as in the reference
+    (lines 148-157), from a batch that holds the targets in the frame-0 slots and zeros elsewhere."""
+
+    def __init__(self, vid, **kw):
+        self.vid, self.T = vid, vid.vid_length
+        super().__init__(vid.img_dcgan, **kw)
+
+    def _z_shape(self):
+        return (self.vid.batch_size, self.vid.z_input_size)
+
+    def _frames(self, z):
+        G_out, _ = self.vid.generator(z, train=self.train)
+        return self.vid.img_dcgan.generator(G_out, train=self.train)
+
+    def target_activations(self, images):
+        t = self._target(images)
+        full = torch.zeros((t.shape[0] * self.T,) + tuple(t.shape[1:]), dtype=torch.float32, device=t.device)
+        full[::self.T] = t
+        with torch.no_grad():
+            h2 = self.dcgan.discriminator(add_noise(full, self.dcgan.noise_std), reuse=True, train=self.train, stop_at_h2=True)[2]
+        return h2[::self.T].float().contiguous()
+
+    def images(self):
+        """All frames of the current clips, float32 [clips * T, s, s, c]; `[::T]` are the searched first frames."""
+        with torch.no_grad():
+            return self._frames(self.z.detach())
+
+    def loss_and_grad(self, target_images, target_activations):
+        w, d, T_ = self.w, self.dcgan, self.T
+        tgt_img = self._target(target_images) if (w["pixel_L2_weight"] or w["pixel_L1_weight"]) else None
+        need_act = bool(w["activations_L2_weight"] or w["activations_L1_weight"])
+        need_gen = bool(w["generator_loss_weight"])
+        self.z.grad = None
+        roots = []
+        with ops.trainable([]), ops.stats_arena():
+            G = self._frames(self.z)
+            if need_act or need_gen:
+                out = d.discriminator(add_noise(G, d.noise_std), reuse=True, train=self.train, stop_at_h2=not need_gen)
+                if need_act:
+                    roots.append(distance_loss(out[2][::T_].contiguous(), self._target(target_activations), w["activations_L2_weight"],
+                                               w["activations_L1_weight"]))
+                if need_gen:
+                    n = out[1].shape[0]
+                    roots.append(sigmoid_cross_entropy_loss(out[1], [(0, n, 1.0, w["generator_loss_weight"])])[0:1])
+            if tgt_img is not None:
+                roots.append(distance_loss(G[::T_].contiguous(), tgt_img, w["pixel_L2_weight"], w["pixel_L1_weight"]))
+            torch.autograd.backward(roots, grad_tensors=[self._ones] * len(roots))
+        return roots
 
 
 # ---- what the two programs share ----------------------------------------------------------------------

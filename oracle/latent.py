@@ -116,3 +116,58 @@ class LatentSearch:
                 losses.append(self.step(targets[:, f], acts[f], lr))
             results[:, f], zs[:, f] = self.images().numpy(), self.z.numpy()
         return results, zs, losses
+
+
+class NestedLatentSearch(LatentSearch):
+    """/root/reference/models/recurrent_z/discriminator_activation_optimizer_nested.py:146-217: the variable is the VIDEO latent
+    z [clips, 120]; frames = image_gan.generator(video_generator(z)); activation and pixel terms on the first frame of every clip
+    (`[::vid_length]`), generator term = the image GAN's g_loss over all frames; target activations from a batch holding the targets
+    in the frame-0 slots and zeros elsewhere (lines 148-157); `train` also switches the video generator's batch norm (line 242)."""
+
+    def __init__(self, vid, discriminator_mode="inference", z=None, random_seed=0, **kw):
+        self.vid, self.Tn = vid, vid.vid_length
+        if z is None:
+            z = np.random.RandomState(random_seed).uniform(-1.0, 1.0, size=(vid.batch_size, vid.z_input_size))
+        super().__init__(vid.img_dcgan, discriminator_mode=discriminator_mode, z=z, **kw)
+
+    def _frames(self, z):
+        return self.vid.img_dcgan.generator(self.vid.generator(z, train=self.train), train=self.train, tag="s")
+
+    def target_activations(self, images):
+        t = self._t(images)
+        full = torch.zeros((t.shape[0] * self.Tn,) + tuple(t.shape[1:]), dtype=t.dtype)
+        full[::self.Tn] = t
+        with torch.no_grad():
+            return self.dcgan.discriminator(full, train=self.train, tag="d_target")[2][::self.Tn].clone()
+
+    def images(self):
+        with torch.no_grad():
+            return self._frames(self.z)
+
+    def loss_terms(self, z, target_images, target_activations):
+        w, d, Tn = self.w, self.dcgan, self.Tn
+        G = self._frames(z)
+        terms = {}
+        if w["activations_L2_weight"] or w["activations_L1_weight"] or w["generator_loss_weight"]:
+            _, logits, h2 = d.discriminator(G, train=self.train, tag="d_fake")
+            diff = h2[::Tn] - self._t(target_activations)
+            if w["activations_L2_weight"]:
+                terms["activations_L2"] = w["activations_L2_weight"] * diff.square().mean(dim=(1, 2, 3)).mean()
+            if w["activations_L1_weight"]:
+                terms["activations_L1"] = w["activations_L1_weight"] * diff.abs().mean(dim=(1, 2, 3)).mean()
+            if w["generator_loss_weight"]:
+                terms["generator"] = w["generator_loss_weight"] * d._ce(logits, 1.0)
+        if w["pixel_L2_weight"] or w["pixel_L1_weight"]:
+            pd = G[::Tn] - self._t(target_images)
+            if w["pixel_L2_weight"]:
+                terms["pixel_L2"] = w["pixel_L2_weight"] * pd.square().mean(dim=(1, 2, 3)).mean()
+            if w["pixel_L1_weight"]:
+                terms["pixel_L1"] = w["pixel_L1_weight"] * pd.abs().mean(dim=(1, 2, 3)).mean()
+        return terms
+
+    def loss_and_grad(self, target_images, target_activations):
+        self.vid.set_requires_grad(set())
+        z = self.z.detach().clone().requires_grad_(True)
+        loss = sum(self.loss_terms(z, target_images, target_activations).values())
+        loss.backward()
+        return float(loss.item()), z.grad.detach().clone()

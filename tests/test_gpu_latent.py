@@ -230,3 +230,78 @@ def test_bf16_dcgan64_against_quantised_oracle(mode):
         first = got if first is None else first
         assert abs(got - want) < 3e-2 * abs(want), (i, got, want)
     assert got < first
+
+
+def test_activation_optimizer_iterative_cli(tmp_path):
+    """discriminator_activation_optimizer.py --vid_length N --iterative (the reference's _video_iterative.py) end to end on
+    synthetic targets: the fit_video schedule (checked against the oracle in test_fit_video_schedule_fp32) + the output files."""
+    import os
+    from gifgan import discriminator_activation_optimizer as dao
+    d = str(tmp_path / "out")
+    os.makedirs(d)
+    opts = dao.flags.parse("activation_optimizer", ["--vid_length", "3", "--iterative", "--synthetic", "2", "--image_size", "32", "--output_size", "32",
+                                                     "--num_initial_steps", "3", "--num_steps_per_frame", "2", "--learning_rate", "0.05",
+                                                     "--lr_decay_amount", "0.5", "--discriminator_mode", "inference", "--sample_dir", d,
+                                                     "--precision", "fp32", "--cuda_graph", "false"])
+    search, results, zs = dao.run_iterative(opts)
+    assert results.shape == (2, 3, 32, 32, 3) and zs.shape == (2, 3, 100) and search.t == 9
+    assert np.isfinite(results).all() and np.abs(results).max() <= 1.0
+    assert not np.array_equal(zs[:, 0], zs[:, 1])                      # every frame moved on from the previous one's latents
+    for f in ["target.png", "final.png", "final_z.npy", "final_frames/final_frame_002.png", "tween_frames/tween_frame_006.png",
+              "tween_frames/tween_frame_004.png"]:
+        assert os.path.exists(os.path.join(d, f)), f
+    assert np.array_equal(np.load(os.path.join(d, "final_z.npy")), zs)
+
+
+# ---- nested search: the video latent through the video generator (discriminator_activation_optimizer_nested.py) ---------------
+@pytest.mark.parametrize("mode", ["train", "inference"])
+def test_nested_search_matches_oracle_fp32(mode):
+    """z [clips, 120] -> video generator -> image generator -> image discriminator; activation / pixel terms on the first frame of
+    every clip, generator term over all frames: loss, d loss / d z and a 4-step Adam trajectory against oracle/latent.py."""
+    from gifgan import ops
+    from gifgan.latent_search import NestedLatentSearch
+    from gifgan.z_model_lib import VID_DCGAN
+    from oracle.latent import NestedLatentSearch as OracleNested
+    from oracle.models import VID_DCGAN as OracleVID
+    Bv, T = 2, 4
+    ora = make_trained_like(OracleVID(batch_size=Bv, vid_length=T, output_image_size=32, seed=7, dtype=torch.float32), gain=4.0)
+    ops.set_precision("fp32")
+    ops.reset_default_store(device="cuda")
+    with ops.variable_scope('video_gan'):
+        m = VID_DCGAN(None, batch_size=Bv, z_input_size=120, z_output_size=100, vid_length=T, input_image_size=32, output_image_size=32,
+                      c_dim=3, sample_cols=Bv)
+    assert set(m.store.vars) == set(ora.vars)
+    m.store.load_state_dict(ora.state_dict())
+    s, o = NestedLatentSearch(m, discriminator_mode=mode, random_seed=3, **ALL), OracleNested(ora, mode, random_seed=3, **ALL)
+    assert tuple(s.z.shape) == (Bv, 120)
+    tgt = np.random.RandomState(107).uniform(-1, 1, (Bv, 32, 32, 3)).astype(np.float32)
+    acts, want_acts = s.target_activations(tgt), o.target_activations(tgt)
+    assert tuple(acts.shape) == (Bv, 4, 4, 256) and relmax(acts, want_acts) < 1e-4
+    roots = s.loss_and_grad(tgt, want_acts.numpy())
+    want_loss, want_grad = o.loss_and_grad(tgt, want_acts)
+    got_loss = sum(r.item() for r in roots)
+    assert len(roots) == 3 and abs(got_loss - want_loss) < 1e-4 * max(1.0, abs(want_loss)), (got_loss, want_loss)
+    assert relmax(s.z.grad, want_grad) < 2e-4
+    assert float(m.store.flat["grads"].abs().max()) == 0.0                      # the var_list is [z]
+    assert tuple(s.images().shape) == (Bv * T, 32, 32, 3) and relmax(s.images(), o.images()) < 1e-4
+    for _ in range(4):
+        gl, wl = s.step(tgt, want_acts.numpy(), 0.01), o.step(tgt, want_acts, 0.01)
+        assert abs(gl - wl) < 5e-4 * max(1.0, abs(wl))
+    assert relmax(s.z, o.z) < 1e-3
+
+
+def test_activation_optimizer_nested_cli(tmp_path):
+    """discriminator_activation_optimizer.py --nested end to end on random weights / synthetic targets: file outputs and shapes."""
+    import os
+    from gifgan import discriminator_activation_optimizer as dao
+    d = str(tmp_path / "nested")
+    os.makedirs(d)
+    opts = dao.flags.parse("activation_optimizer", ["--nested", "--synthetic", "1", "--num_rows", "1", "--num_cols", "2", "--vid_length", "4",
+                                                     "--image_size", "32", "--output_size", "32", "--num_steps", "3", "--learning_rate", "0.01",
+                                                     "--discriminator_mode", "inference", "--sample_dir", d, "--precision", "fp32",
+                                                     "--sample_frequency", "2", "--cuda_graph", "false"])
+    search, frames = dao.run_nested(opts)
+    assert frames.shape == (8, 32, 32, 3) and tuple(search.z.shape) == (2, 120) and search.t == 3
+    for f in ["target.png", "train_0.png", "train_2.png", "final.png", "final_z.npy", "final.mp4"]:
+        assert os.path.exists(os.path.join(d, f)), f
+    assert np.load(os.path.join(d, "final_z.npy")).shape == (2, 120)

@@ -267,3 +267,20 @@ def test_activation_optimizer_clip_mode_targets(tmp_path):
         load_clip_targets(opts)                                   # 8 frames needed, 7 in the file
     opts = flags.parse("activation_optimizer", ["--vid_length", "4", "--synthetic", "3", "--image_size", "8"])
     assert load_clip_targets(opts).shape == (12, 8, 8, 3)
+
+
+def test_activation_optimizer_iterative_contract_and_tweening():
+    """discriminator_activation_optimizer_video_iterative.py: option names / defaults (lines 15-23) and the latent tweening of
+    lines 243-262 (tween_frames latents between consecutive tracked frames: end * delta + start * (1 - delta), delta = j / (n + 1))."""
+    from gifgan import flags
+    from gifgan.discriminator_activation_optimizer import tween_latents
+    o = flags.parse("activation_optimizer", ["--vid_length", "4", "--iterative", "--synthetic", "2"])
+    assert o.iterative and (o.num_initial_steps, o.num_steps_per_frame, o.frame_skip, o.tween_frames) == (500, 100, 2, 2)
+    assert not flags.parse("activation_optimizer", ["--vid_length", "4"]).iterative
+    zs = np.arange(2 * 3 * 5, dtype=np.float32).reshape(2, 3, 5)
+    seq = tween_latents(zs, 2)
+    assert [i for i, _, _ in seq] == list(range(7)) and [t for _, _, t in seq] == [True, False, False, True, False, False, True]
+    assert np.array_equal(seq[0][1], zs[:, 0]) and np.array_equal(seq[3][1], zs[:, 1]) and np.array_equal(seq[6][1], zs[:, 2])
+    np.testing.assert_allclose(seq[1][1], zs[:, 1] * (1 / 3.0) + zs[:, 0] * (2 / 3.0), rtol=1e-6)
+    np.testing.assert_allclose(seq[5][1], zs[:, 2] * (2 / 3.0) + zs[:, 1] * (1 / 3.0), rtol=1e-6)
+    assert [i for i, _, _ in tween_latents(zs, 0)] == [0, 1, 2]

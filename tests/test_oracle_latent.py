@@ -117,3 +117,64 @@ def test_latent_tiny_matches_golden(mode):
     np.testing.assert_allclose(losses, g[f"{mode}/losses"], rtol=1e-9)
     np.testing.assert_allclose(s.z.numpy(), g[f"{mode}/z4"], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(s.images().numpy(), g[f"{mode}/images4"], rtol=1e-6, atol=1e-9)
+
+
+# ---- nested search: through the video generator (discriminator_activation_optimizer_nested.py) --------------------------------
+def tiny_nested(dtype=torch.float64, Bv=2, Tn=3):
+    from oracle.models import VID_DCGAN
+    v = VID_DCGAN(batch_size=Bv, z_input_size=12, z_output_size=10, vid_length=Tn, output_image_size=16, seed=9, dtype=dtype)
+    make_trained_like(v)
+    tgt = np.random.RandomState(13).uniform(-1, 1, (Bv, 16, 16, 3))
+    return v, tgt
+
+
+@pytest.mark.parametrize("mode", ["train", "inference"])
+def test_nested_terms_use_first_frames_only(mode):
+    from oracle.latent import NestedLatentSearch
+    v, tgt = tiny_nested()
+    s = NestedLatentSearch(v, mode, **ALL)
+    assert tuple(s.z.shape) == (2, 12)
+    acts = s.target_activations(tgt)
+    train = mode == "train"
+    with torch.no_grad():
+        full = torch.zeros(6, 16, 16, 3, dtype=torch.float64)
+        full[::3] = torch.tensor(tgt)
+        want_acts = v.img_dcgan.discriminator(full, train=train)[2][::3]
+        frames = v.img_dcgan.generator(v.generator(s.z, train=train), train=train)
+        _, logits, h2 = v.img_dcgan.discriminator(frames, train=train)
+    assert torch.equal(acts, want_acts) and tuple(frames.shape) == (6, 16, 16, 3)
+    terms = s.loss_terms(s.z, tgt, acts)
+    t = torch.tensor(tgt)
+    want = dict(
+        pixel_L2=0.3 * np.mean([((frames[3 * b] - t[b]) ** 2).mean().item() for b in range(2)]),
+        pixel_L1=0.1 * np.mean([(frames[3 * b] - t[b]).abs().mean().item() for b in range(2)]),
+        activations_L2=0.3 * np.mean([((h2[3 * b] - acts[b]) ** 2).mean().item() for b in range(2)]),
+        activations_L1=0.2 * np.mean([(h2[3 * b] - acts[b]).abs().mean().item() for b in range(2)]),
+        generator=0.1 * np.mean([max(x, 0) - x + np.log1p(np.exp(-abs(x))) for x in logits.reshape(-1).tolist()]))     # ALL frames
+    for k, val in want.items():
+        assert abs(terms[k].item() - val) < 1e-12 * max(1.0, abs(val)), k
+
+
+@pytest.mark.parametrize("mode", ["train", "inference"])
+def test_nested_gradient_against_central_differences(mode):
+    from oracle.latent import NestedLatentSearch
+    v, tgt = tiny_nested()
+    s = NestedLatentSearch(v, mode, **ALL)
+    acts = s.target_activations(tgt)
+    _, g = s.loss_and_grad(tgt, acts)
+    assert tuple(g.shape) == (2, 12) and g.abs().max() > 0
+    rs = np.random.RandomState(4)
+    for _ in range(6):
+        b, i = rs.randint(2), rs.randint(12)
+        e = torch.zeros_like(s.z)
+        e[b, i] = 1e-7       # 6 rows through three ReLU layers and two L1 terms: kinks within 1e-5 of z; the slope is exact at 1e-7
+        with torch.no_grad():
+            lp = sum(s.loss_terms(s.z + e, tgt, acts).values()).item()
+            lm = sum(s.loss_terms(s.z - e, tgt, acts).values()).item()
+        fd = (lp - lm) / 2e-7
+        assert abs(fd - g[b, i].item()) < 1e-5 * max(1.0, abs(fd)) + 1e-8, (b, i, fd, g[b, i].item())
+    # one optimiser step moves z; the loss goes down over a few steps at a small step size
+    l0 = s.step(tgt, acts, 0.01)
+    for _ in range(5):
+        l1 = s.step(tgt, acts, 0.01)
+    assert l1 < l0
