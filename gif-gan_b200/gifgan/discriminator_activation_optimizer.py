@@ -149,7 +149,7 @@ def write_clip_grid(videos, filename, fps=25.0):
     import cv2
     rows, cols, T, sz, _, c = videos.shape
     print("Writing samples to", filename)
-    wr = cv2.VideoWriter(filename, 0x20, fps, (cols * sz, rows * sz))
+    wr = utils.open_video_writer(filename, fps, (cols * sz, rows * sz))
     for t in range(T):
         frame = np.zeros((rows * sz, cols * sz, c), dtype=np.uint8)
         for r in range(rows):

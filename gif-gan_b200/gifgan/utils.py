@@ -63,3 +63,16 @@ def save_images(images, size, image_path):
     img = merge(inverse_transform(images), size)
     img = np.clip(np.around(img * 255), 0, 255).astype(np.uint8)
     return cv2.imwrite(image_path, cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+
+
+def open_video_writer(filename, fps, frame_size):
+    """cv2.VideoWriter(filename, 0x20, fps, frame_size) as the reference opens it (z_model_lib.py:303, 0x20 = MPEG-4 in the
+    OpenCV 2/3 builds it ran on); OpenCV 4 builds reject that tag for .mp4 ("tag 0x00000020 is not found") and would silently
+    write nothing, so fall back to the container's own MPEG-4 tag 'mp4v'."""
+    import cv2
+    w = cv2.VideoWriter(filename, 0x20, fps, frame_size)
+    if not w.isOpened():
+        w = cv2.VideoWriter(filename, cv2.VideoWriter_fourcc(*"mp4v"), fps, frame_size)
+    if not w.isOpened():
+        raise IOError("cannot open a video writer for %s" % filename)
+    return w

@@ -21,7 +21,7 @@ import torch
 from . import ops
 from .model import DCGAN
 from .ops import batch_norm, conv3d, linear, add_noise, get_std, sigmoid_cross_entropy_loss, variable_scope
-from .utils import inverse_transform, transform
+from .utils import inverse_transform, open_video_writer, transform
 
 
 class Layers(object):
@@ -400,7 +400,7 @@ class VID_DCGAN(object):
         folder = os.path.join(config.video_sample_dir, "train" if is_training else "inference")
         os.makedirs(folder, exist_ok=True)
         filename = '{}/{}train_{:02d}_{:04d}.mp4'.format(folder, prefix, epoch, idx)
-        w = cv2.VideoWriter(filename, 0x20, 25.0, (self.sample_cols * sz, self.sample_rows * sz))
+        w = open_video_writer(filename, 25.0, (self.sample_cols * sz, self.sample_rows * sz))
         for t in range(self.vid_length):
             frame = np.zeros(shape=[self.sample_rows * sz, self.sample_cols * sz, self.c_dim], dtype=np.uint8)
             for r in range(self.sample_rows):

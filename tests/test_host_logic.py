@@ -284,3 +284,21 @@ def test_activation_optimizer_iterative_contract_and_tweening():
     np.testing.assert_allclose(seq[1][1], zs[:, 1] * (1 / 3.0) + zs[:, 0] * (2 / 3.0), rtol=1e-6)
     np.testing.assert_allclose(seq[5][1], zs[:, 2] * (2 / 3.0) + zs[:, 1] * (1 / 3.0), rtol=1e-6)
     assert [i for i, _, _ in tween_latents(zs, 0)] == [0, 1, 2]
+
+
+def test_clip_grid_writer_produces_a_readable_mp4(tmp_path):
+    """write_clip_grid (discriminator_activation_optimizer_nested.py:305-324) / utils.open_video_writer: the reference's fourcc 0x20 is
+    rejected by OpenCV 4 for .mp4 (nothing would be written); the fallback tag must give T frames of the rows x cols grid."""
+    cv2 = pytest.importorskip("cv2")
+    from gifgan.discriminator_activation_optimizer import write_clip_grid
+    v = np.random.RandomState(0).uniform(-1, 1, (2, 3, 5, 16, 16, 3)).astype(np.float32)
+    path = str(tmp_path / "grid.mp4")
+    write_clip_grid(v, path)
+    cap = cv2.VideoCapture(path)
+    n, shape = 0, None
+    while True:
+        ok, im = cap.read()
+        if not ok:
+            break
+        n, shape = n + 1, im.shape
+    assert n == 5 and shape == (32, 48, 3)
