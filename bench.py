@@ -590,7 +590,29 @@ def hbm_kernel_table(model, batch, flush, peaks, conv_rows):
     ms = once(lambda: check(L.gg_frames_to_input(ptr(fr), nf, Hs, Hs, Hs * Hs * 3, Hs * 3, ptr(fo), Sd, Sd, 1, stream()), "frames_to_input"))
     add(f"frames_to_input [{nf} frames u8 {Hs}x{Hs}x3 -> fp32 {Sd}x{Sd}x3] (input side of the e2e path, not in the device-timed step)",
         nf * Hs * Hs * 3 + nf * Sd * Sd * 12, ms, 0)
+    rows[-1]["cpu_reference"] = frames_cpu_reference(nf, Hs, Sd)      # the reference's own host code for the same frames, timed beside it
     return rows
+
+
+def frames_cpu_reference(nf, Hs, Sd):
+    """The reference's per-frame host code (z_model_lib.py:339-346: cv2.resize INTER_LINEAR, cv2.cvtColor BGR2RGB, utils.transform) on
+    the same number of frames, one host thread as in the reference's loop.  None when OpenCV is missing; never raises."""
+    try:
+        import cv2
+        frames = np.random.RandomState(0).randint(0, 256, (nf, Hs, Hs, 3)).astype(np.uint8)
+        out = np.zeros((nf, Sd, Sd, 3))
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            for i in range(nf):
+                im = cv2.cvtColor(cv2.resize(frames[i], (Sd, Sd), interpolation=cv2.INTER_LINEAR), cv2.COLOR_BGR2RGB)
+                out[i] = np.array(im) / 127.5 - 1.
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return {"ms": round(best * 1e3, 3), "frames_per_s": round(nf / best, 1), "threads": 1,
+                "what": "cv2.resize + cv2.cvtColor + x / 127.5 - 1 per frame on one host thread (the reference's loop), best of 3"}
+    except Exception as e:      # noqa: BLE001 -- a missing / different OpenCV must not cost the bench line
+        return {"unavailable": str(e)[:120]}
 
 
 def run_ours(args):
