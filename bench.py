@@ -478,12 +478,16 @@ def layer_rooflines(model, batch, precision, flush, reps=5, launches=10):
                 if is_d and kind == "up" and C == 3 and B_ == 2 * batch:
                     continue   # d_h0 dgrad is not needed in the D update
                 ms = time_kernel(fns[kind], flush, reps, launches)
+                try:        # the same launch COLD: one launch per L2 flush (operands from HBM), the pessimistic reading beside `ms`
+                    ms_cold = time_kernel(fns[kind], flush, 3, 1)
+                except Exception:       # noqa: BLE001
+                    ms_cold = None
                 tc = ops._tc_ok(C, K, large, small)
                 path = "tcgen05" if tc else ("mma.sync" if (C == 3 and K % 64 == 0 and precision == "bf16") else "simt")
                 # algorithmic bytes of the image-side (HBM-bound) layers: the fp32 image + the bf16 activation, each touched once
                 nbytes = (B_ * hw * hw * C * 4 + B_ * (hw // 2) ** 2 * K * 2) if C == 3 else None
                 rows.append(dict(kernel=f"{name}.{kind}[B={B_}]", ms=ms, flops=fl, tflops=fl / ms / 1e9, uses=n_use,
-                                 path=path, share_ms=ms * n_use, order=len(rows), bytes=nbytes))
+                                 path=path, share_ms=ms * n_use, order=len(rows), bytes=nbytes, ms_cold=ms_cold))
     rows.sort(key=lambda r: -r["share_ms"])
     return rows
 
@@ -517,7 +521,7 @@ def hbm_kernel_table(model, batch, flush, peaks, conv_rows):
     for opt, uses, nm in ((model.d_optim, 1, "adam[D group]"), (model.g_optim, 2, "adam[G group]")):
         b, e = opt.range()
         ms = once(lambda: opt.apply())
-        add(nm + " (adam_tick + adam_dev; in the step the tick runs early on the side stream)", (e - b) * 30, ms, uses)
+        add(nm + " (adam_tick + adam_dev)", (e - b) * 30, ms, uses)
     # batch norm at the largest layer of the step: d_h1 on the 2B batch [2B,16,16,128]: fp32 pre-norm in, bf16 out
     B2, H, C = 2 * batch, 16, 128
     rows_n = B2 * H * H
@@ -665,6 +669,9 @@ def run_ours(args):
                                      "null: no committed ncu capture matches the current sources of this kernel family (sha %s)" % kernel_source_sha(top["path"] if top["path"] in KERNEL_FAMILY_SOURCES else "tcgen05")),
                     "ncu": {"file": ncu_file, "tensor_pipe_active_pct": prof.get("tensor_pct"), "duration_us": prof.get("dur_us")} if prof else None,
                     "flops_per_launch": top["flops"], "launch_ms": top["ms"],
+                    "launch_ms_cold": top.get("ms_cold"),
+                    "frac_cold": (top["flops"] / top["ms_cold"] / 1e9 / peaks["tf_burst"]) if top.get("ms_cold") else None,
+                    "timing_cold": "one launch per L2 flush (operands from HBM), 3 repetitions -- the pessimistic reading; `frac` is the in-step-like one",
                     "timing": "CUDA events, 10 back-to-back launches after one L2 flush (operands L2-warm for 9 of 10, as in the step where the producer kernel has just written them), 5 repetitions",
                     "step": {"gemm_tflop_per_step": main["gemm_tflop_per_step"], "achieved_tflops": main["achieved_tflops_per_gpu"],
                              "frac_of_sustained": main["frac_of_sustained_bf16_peak"]},
