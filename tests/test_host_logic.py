@@ -302,3 +302,23 @@ def test_clip_grid_writer_produces_a_readable_mp4(tmp_path):
             break
         n, shape = n + 1, im.shape
     assert n == 5 and shape == (32, 48, 3)
+
+
+def test_new_entry_points_have_no_cpu_fallback_and_trace_on_meta(cpu_store):
+    """frames_to_input / the fused loss head: shape inference on meta tensors (what the model constructors trace), a loud error on
+    host tensors (the product never computes on the CPU), argument validation before any launch."""
+    from gifgan import ops
+    fr = torch.zeros(3, 12, 16, 3, dtype=torch.uint8)
+    assert tuple(ops.frames_to_input(fr.to("meta"), 8).shape) == (3, 8, 8, 3)
+    with pytest.raises(RuntimeError):
+        ops.frames_to_input(fr, 8)
+    with pytest.raises(ValueError):
+        ops.frames_to_input(fr.float(), 8)
+    with pytest.raises(ValueError):
+        ops.frames_to_input(torch.zeros(3, 12, 16, 4, dtype=torch.uint8), 8)
+    # linear(..., ce_segments=...) on meta tensors creates the variables and returns logits of the right shape without a launch
+    h = torch.empty(6, 128, device="meta")
+    y = ops.linear(h, 1, "d_h3_lin", ce_segments=[(0, 3, 1.0, 1.0), (3, 6, 0.0, 1.0)])
+    assert tuple(y.shape) == (6, 1) and "d_h3_lin/Matrix" in cpu_store.vars
+    L = ops.cabi.lib()
+    assert L.gg_loss_head_ok(128, 8192, 2) == 1 and L.gg_loss_head_ok(128, 100, 2) == 0 and L.gg_loss_head_ok(128, 8192, 5) == 0
