@@ -322,3 +322,23 @@ def test_new_entry_points_have_no_cpu_fallback_and_trace_on_meta(cpu_store):
     assert tuple(y.shape) == (6, 1) and "d_h3_lin/Matrix" in cpu_store.vars
     L = ops.cabi.lib()
     assert L.gg_loss_head_ok(128, 8192, 2) == 1 and L.gg_loss_head_ok(128, 100, 2) == 0 and L.gg_loss_head_ok(128, 8192, 5) == 0
+
+
+def test_image_side_index_maps_emulated_on_the_cpu():
+    """tools/emulate_c3_mma.py mirrors the thread / fragment index maps of csrc/conv_c3_mma.cu (mma.sync m16n8k16, ldmatrix) line by
+    line, including the bias rider of the filter-gradient kernel (ones channel in the staged patch -> the discarded row (1, 1, c = 3)
+    sums dy over the pixels) on partial tiles: the emulated kernels must reproduce the direct sums."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "emulate_c3_mma.py")
+    spec = importlib.util.spec_from_file_location("emulate_c3_mma", path)
+    E = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(E)
+    rs = np.random.RandomState(0)
+    x, w = rs.randn(1, 20, 36, 3), rs.randn(5, 5, 3, 64)
+    assert np.abs(E.emu_down(x, w) - E.ref_down(x, w)).max() < 1e-9
+    xs = rs.randn(1, 10, 18, 64)
+    assert np.abs(E.emu_up(xs, w) - E.ref_up(xs, w)).max() < 1e-9
+    ys = rs.randn(1, 10, 18, 64)
+    dw, db = E.emu_wgrad(x, ys, with_bias=True)
+    assert np.abs(dw - E.ref_wgrad(x, ys)).max() < 1e-9 and np.abs(db - ys.sum((0, 1, 2))).max() < 1e-9

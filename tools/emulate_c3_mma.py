@@ -176,10 +176,13 @@ def ref_wgrad(x, ys):
     return dw
 
 
-def emu_wgrad(x, ys):
+def emu_wgrad(x, ys, with_bias=False):
+    """with_bias: the bias rider of c3m_wgrad_kernel -- the unused fourth channel slot of every staged IN-IMAGE pixel holds 1, and the
+    discarded row (r = 1, s = 1, c = 3) of the GEMM then accumulates sum_pixels ys[pixel, k]; returns (dw, dbias)."""
     N, H, W, _ = x.shape; K = ys.shape[-1]; Ho, Wo = H // 2, W // 2
     TH, TW, PR, PC, YPIX = 8, 16, 19, 36, 72
     dw = np.zeros((75, K))
+    dbias = np.zeros(K)
     for kb in range(0, K, 64):
         acc = np.zeros((8, 8, 32, 4))      # warp, jn, lane, 4
         for n in range(N):
@@ -192,6 +195,8 @@ def emu_wgrad(x, ys):
                         i, j = i0 + a, j0 + b
                         if 0 <= i < H and 0 <= j < W:
                             sp[e * 4:e * 4 + 3] = x[n, i, j]
+                            if with_bias:
+                                sp[e * 4 + 3] = 1.0
                     sy = np.zeros(TH * TW * YPIX)
                     for pix in range(TH * TW):
                         p, q = p0 + pix // TW, q0 + pix % TW
@@ -222,13 +227,17 @@ def emu_wgrad(x, ys):
                 for half in range(2):
                     mb = 2 * warp + half
                     r, s, c = mb // 3, 2 * (mb % 3) + (g >> 2), g & 3
+                    if with_bias and r == 1 and s == 1 and c == 3:
+                        for jn in range(8):
+                            dbias[kb + jn * 8 + 2 * t] += acc[warp, jn][l][2 * half]
+                            dbias[kb + jn * 8 + 2 * t + 1] += acc[warp, jn][l][2 * half + 1]
                     if mb >= 15 or s >= 5 or c >= 3:
                         continue
                     row = (r * 5 + s) * 3 + c
                     for jn in range(8):
                         dw[row, kb + jn * 8 + 2 * t] += acc[warp, jn][l][2 * half]
                         dw[row, kb + jn * 8 + 2 * t + 1] += acc[warp, jn][l][2 * half + 1]
-    return dw.reshape(5, 5, 3, K)
+    return (dw.reshape(5, 5, 3, K), dbias) if with_bias else dw.reshape(5, 5, 3, K)
 
 
 if __name__ == "__main__":
@@ -242,4 +251,7 @@ if __name__ == "__main__":
     ys = rs.randn(1, 10, 18, 64)
     d = np.abs(emu_wgrad(x, ys) - ref_wgrad(x, ys)).max()
     print("wgrad max err", d); assert d < 1e-9
+    dw, db = emu_wgrad(x, ys, with_bias=True)                  # the bias rider leaves dw untouched and yields sum_pixels ys
+    d = max(np.abs(dw - ref_wgrad(x, ys)).max(), np.abs(db - ys.sum((0, 1, 2))).max())
+    print("wgrad + bias rider max err", d); assert d < 1e-9
     print("ok")
